@@ -1,0 +1,247 @@
+"""TEST INFRASTRUCTURE — CPU restatement (NumPy) of the reference's triangulation hot path.
+
+This module is the *checker*: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import it.  The product (`pose2sim_b200/`) never does; it fails loudly
+when the CUDA library is missing.
+
+Parity pinning: the reference's own tests hold no numeric vectors for this path, so
+this restatement is pinned against outputs of the UNMODIFIED reference run in the build container
+(`oracle/make_golden.py` -> `tests/golden/*.npz`, checked by `tests/test_oracle_golden.py`).
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+It is written per unit / per candidate on purpose: that is the reference's cost structure
+(a Python call per (frame, person, keypoint), a NumPy SVD per candidate camera subset), which makes it
+the stand-in for "the reference's CPU path" when bench.py times a CPU baseline on a box where the
+reference itself is absent.
+"""
+import itertools
+import math
+
+import numpy as np
+
+__all__ = [
+    "weighted_dlt", "reproject", "pixel_distance", "solve_subset",
+    "triangulate_unit", "triangulate_units", "person_id_rows", "associate_frame",
+]
+
+
+# ---------------------------------------------------------------------------------------------
+# leaf math
+# ---------------------------------------------------------------------------------------------
+def weighted_dlt(P_sub, x, y, w):
+    """Likelihood-weighted DLT.  Pose2Sim/common.py:327-354 (`weighted_triangulation`).
+
+    Two rows per camera, `(P[0]-x*P[2])*w` and `(P[1]-y*P[2])*w` (:344-345); with >= 4 rows the
+    solution is the right singular vector of the smallest singular value, de-homogenised
+    (:347-350); otherwise NaN (:351-352).  The reference calls `cv2.SVDecomp`; any SVD gives the same
+    vector up to sign/rounding because the result is `V[:3,3]/V[3,3]`.
+    """
+    m = len(x)
+    if 2 * m < 4:
+        return np.array([np.nan, np.nan, np.nan, 1.0])
+    A = np.empty((2 * m, 4))
+    for c in range(m):
+        Pc = P_sub[c]
+        A[2 * c] = (Pc[0] - x[c] * Pc[2]) * w[c]
+        A[2 * c + 1] = (Pc[1] - y[c] * Pc[2]) * w[c]
+    v = np.linalg.svd(A)[2][3]
+    with np.errstate(all="ignore"):
+        return np.array([v[0] / v[3], v[1] / v[3], v[2] / v[3], 1.0])
+
+
+def reproject(P_sub, Q):
+    """Pose2Sim/common.py:357-375 (`reprojection`): x = P[0].Q / P[2].Q, y = P[1].Q / P[2].Q."""
+    xs, ys = [], []
+    with np.errstate(all="ignore"):
+        for Pc in P_sub:
+            den = Pc[2] @ Q
+            xs.append(Pc[0] @ Q / den)
+            ys.append(Pc[1] @ Q / den)
+    return xs, ys
+
+
+def pixel_distance(q1, q2):
+    """Pose2Sim/common.py:378-403 (`euclidean_distance`): sqrt(nansum(d^2)); if every component of
+    the difference is NaN the distance is +inf (:394-396)."""
+    d = np.asarray(q2, float) - np.asarray(q1, float)
+    if np.isnan(d).all():
+        return np.inf
+    return float(np.sqrt(np.nansum(d * d)))
+
+
+def solve_subset(P, x, y, w, cams):
+    """DLT + reprojection + mean pixel error over the cameras `cams` (ascending indices).
+
+    Pose2Sim/triangulation.py:469 (DLT), :478 (reprojection), :485-489 (mean distance).
+    Zero cameras -> mean of an empty list = NaN; one camera -> NaN point -> distance inf.
+    """
+    P_sub = [P[c] for c in cams]
+    xs = [x[c] for c in cams]
+    ys = [y[c] for c in cams]
+    ws = [w[c] for c in cams]
+    Q = weighted_dlt(P_sub, xs, ys, ws)
+    xc, yc = reproject(P_sub, Q)
+    d = [pixel_distance((xs[i], ys[i]), (xc[i], yc[i])) for i in range(len(cams))]
+    err = float(np.mean(d)) if len(d) else float("nan")
+    return Q, err
+
+
+# ---------------------------------------------------------------------------------------------
+# triangulation exclusion search  (Pose2Sim/triangulation.py:363-604, handle_LR_swap and
+# undistort_points off, as in every shipped config: SURVEY.md §5)
+# ---------------------------------------------------------------------------------------------
+def triangulate_unit(x, y, w, P, thr, min_cams):
+    """One (frame, person, keypoint) unit.  Returns (Q[3], err, nb_cams_excluded, id_excluded_cams).
+
+    Follows `triangulation_from_best_cameras`:
+      * level loop condition `error_min > thr and n_cams - k >= min_cams`            (:408)
+      * candidates = lexicographic k-subsets of ALL camera indices                   (:411)
+      * excluded cameras become NaN                                                   (:426-432)
+      * per candidate: list of NaN cameras (:435), count of NaN-or-zero cameras       (:436)
+      * the level is abandoned, results untouched, when the WORST candidate excludes
+        more than n_cams - min_cams cameras                                           (:437-441)
+      * valid cameras = likelihood neither NaN nor 0                                  (:450-465)
+      * error_min = nanmin, best = nanargmin (first index on ties)                    (:500-505)
+      * after the loop: ids of the last evaluated level's best candidate, or all
+        cameras when no level was evaluated                                           (:588-596)
+      * failure -> error NaN, Q NaN                                                   (:600-602)
+    """
+    x = np.asarray(x, float)
+    y = np.asarray(y, float)
+    w = np.asarray(w, float)
+    C = len(w)
+    err_min = math.inf
+    Q = np.array([np.nan, np.nan, np.nan])
+    nexcl, ids = None, None
+    k = 0
+    while err_min > thr and C - k >= min_cams:
+        cands = list(itertools.combinations(range(C), k))
+        nan_sets, counts = [], []
+        for cand in cands:
+            wl = w.copy()
+            wl[list(cand)] = np.nan
+            nan_sets.append(np.flatnonzero(np.isnan(wl)))
+            counts.append(int(np.count_nonzero(np.nan_to_num(wl) == 0)))
+        if max(counts) > C - min_cams:
+            break
+        errs, Qs = [], []
+        for cand in cands:
+            wl = w.copy()
+            wl[list(cand)] = np.nan
+            cams = [c for c in range(C) if not np.isnan(wl[c]) and wl[c] != 0.0]
+            Qc, ec = solve_subset(P, x, y, w, cams)
+            Qs.append(Qc)
+            errs.append(ec)
+        errs = np.array(errs)
+        if np.all(np.isnan(errs)):
+            # the reference would raise in np.nanargmin here (unreachable for sane inputs);
+            # defined behaviour for the restatement: keep the first candidate, NaN error.
+            best = 0
+            err_min = float("nan")
+        else:
+            best = int(np.nanargmin(errs))
+            err_min = float(errs[best])
+        nexcl = counts[best]
+        ids = [int(i) for i in nan_sets[best]]
+        Q = Qs[best][:3].copy()
+        k += 1
+    if ids is None:
+        ids = list(range(C))
+        nexcl = C
+    err = err_min
+    if err_min > thr:
+        err = float("nan")
+        Q = np.array([np.nan, np.nan, np.nan])
+    return Q, err, nexcl, ids
+
+
+def triangulate_units(x, y, w, P, thr, min_cams):
+    """Batched convenience wrapper: x, y, w are [U, C]; returns (Q[U,3], err[U], nexcl[U], mask[U])
+    with mask bit c set iff camera c is in `id_excluded_cams`."""
+    U = x.shape[0]
+    Q = np.empty((U, 3))
+    err = np.empty(U)
+    nexcl = np.empty(U, np.int32)
+    mask = np.zeros(U, np.uint32)
+    for u in range(U):
+        q, e, n, ids = triangulate_unit(x[u], y[u], w[u], P, thr, min_cams)
+        Q[u], err[u], nexcl[u] = q, e, n
+        m = 0
+        for c in ids:
+            m |= 1 << c
+        mask[u] = m
+    return Q, err, nexcl, mask
+
+
+# ---------------------------------------------------------------------------------------------
+# single-person association search  (Pose2Sim/personAssociation.py:67-257)
+# ---------------------------------------------------------------------------------------------
+def person_id_rows(n_per_cam):
+    """Pose2Sim/personAssociation.py:67-99 (`persons_combinations`): cartesian product of the
+    per-camera person ranges in camera order; cameras without a detection get NaN."""
+    ranges = [range(n if n != 0 else 1) for n in n_per_cam]
+    rows = np.array(list(itertools.product(*ranges)), float)
+    rows[:, [c for c, n in enumerate(n_per_cam) if n == 0]] = np.nan
+    return rows
+
+
+def associate_frame(obs, n_per_cam, P, thr, lik_thr, min_cams):
+    """One frame of `best_persons_and_cameras_combination` (personAssociation.py:154-257).
+
+    obs[c][p] = (x, y, likelihood) of the tracked keypoint of person p in camera c.
+    Returns (best_error, comb[C] (person index or NaN per camera), Q[3]).
+
+      * cameras NaN in every row are "missing"                                       (:187-188)
+      * level loop `error_min > thr and C - (missing + k) >= min_cams`               (:194)
+      * rows visited in product order; a camera whose likelihood is below lik_thr
+        becomes 0 and the row entry is set to NaN IN PLACE (persists)                (:215-216)
+      * row skipped when fewer than min_cams cameras stay active                     (:219-221)
+      * candidates = k-subsets of the ACTIVE cameras                                 (:222-225)
+      * row skipped when every candidate error is NaN                                (:235-236)
+      * error_min = nanmin, chosen candidate = np.argmin (first NaN wins if any)     (:238-240)
+      * global best updated on strict '<'                                            (:242-245)
+      * first row whose error_min < thr ends the level's row loop                    (:247-248)
+      * nothing evaluable -> (inf, NaN.., NaN)                                       (:252-253)
+    """
+    C = len(n_per_cam)
+    rows = person_id_rows(n_per_cam)
+    n_missing = int(np.all(np.isnan(rows), axis=0).sum())
+    err_min = math.inf
+    best_err, best_comb, best_Q = math.inf, None, None
+    k = 0
+    while err_min > thr and C - (n_missing + k) >= min_cams:
+        for row in rows:
+            coords = np.full((C, 3), np.nan)
+            for c in range(C):
+                if not np.isnan(row[c]):
+                    p = int(row[c])
+                    if p < len(obs[c]):
+                        coords[c] = obs[c][p]
+            with np.errstate(invalid="ignore"):
+                coords[coords[:, 2] < lik_thr, 2] = 0.0
+            row[coords[:, 2] == 0.0] = np.nan
+            active = np.flatnonzero(~np.isnan(row))
+            if len(active) < min_cams:
+                continue
+            cands = list(itertools.combinations(active, k))
+            errs, combs, Qs = [], [], []
+            for cand in cands:
+                comb = row.copy()
+                comb[list(cand)] = np.nan
+                cams = [c for c in range(C) if not np.isnan(comb[c])]
+                Qc, ec = solve_subset(P, coords[:, 0], coords[:, 1], coords[:, 2], cams)
+                errs.append(ec)
+                combs.append(comb)
+                Qs.append(Qc)
+            if len(errs) == 0 or np.all(np.isnan(errs)):
+                continue
+            err_min = float(np.nanmin(errs))
+            b = int(np.argmin(errs))
+            if err_min < best_err:
+                best_err, best_comb, best_Q = err_min, combs[b], Qs[b][:3].copy()
+            if err_min < thr:
+                break
+        k += 1
+    if best_comb is None:
+        return math.inf, np.full(C, np.nan), np.full(3, np.nan)
+    return best_err, best_comb, best_Q
