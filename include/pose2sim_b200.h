@@ -1,0 +1,147 @@
+/*
+ * pose2sim_b200 — C ABI of the B200 (sm_100a) triangulation / person-association hot path.
+ *
+ * The reference (sakagawa-star/pose2sim) is pure Python and has no FFI; the seam this library
+ * replaces is the per-unit Python function boundary, batched:
+ *
+ *   p2s_triangulate_*   replaces  Pose2Sim/triangulation.py:363  triangulation_from_best_cameras
+ *                       (called once per frame x person x keypoint at triangulation.py:840), with the
+ *                       leaf math of Pose2Sim/common.py:327 weighted_triangulation, :357 reprojection,
+ *                       :378 euclidean_distance;
+ *   p2s_stage_*         replaces  the likelihood gate at triangulation.py:817-821 plus the
+ *                       (3, n_cams) slicing at triangulation.py:837-838;
+ *   p2s_associate_*     replaces  Pose2Sim/personAssociation.py:154  best_persons_and_cameras_combination
+ *                       (+ :67 persons_combinations, :102 triangulate_comb), called per frame at :774.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all sizes are explicit;
+ *   - `*_device` entry points take DEVICE pointers, enqueue work on `stream` (a cudaStream_t passed
+ *     as void*, NULL = default stream) and return immediately;
+ *   - `*_host` entry points take HOST pointers, do host<->device copies on internal streams and
+ *     return when the results are in the caller's buffers;
+ *   - return value: 0 = ok, otherwise a P2S_E* code (p2s_status_string gives text).  Argument errors
+ *     are reported that way; numerical failure of a unit is NaN in its outputs, as in the reference
+ *     (triangulation.py:600-602);
+ *   - no global state: everything lives in the p2s_handle (one per GPU per host thread).
+ *   - There is NO CPU fallback: without a CUDA device p2s_create fails with P2S_ENODEVICE.
+ */
+#ifndef POSE2SIM_B200_H
+#define POSE2SIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2S_MAX_CAMS 32          /* one uint32 exclusion mask per unit */
+#define P2S_MAX_PERSONS 16       /* persons per camera in the association search */
+
+enum {
+    P2S_OK = 0,
+    P2S_EINVAL = 1,              /* bad argument (n_cams outside 2..32, min_cams < 1, null pointer ...) */
+    P2S_ENODEVICE = 2,           /* no usable CUDA device / wrong architecture (needs sm_100) */
+    P2S_ECUDA = 3,               /* a CUDA call failed; p2s_last_cuda_error() has the text */
+    P2S_ENOMEM = 4,
+    P2S_ETOODEEP = 5             /* search level needs more candidates than the engine enumerates */
+};
+
+typedef struct p2s_handle p2s_handle;
+
+/* Layout of the statistics block written by the triangulation kernels (uint64 each).           */
+enum {
+    P2S_STAT_LEVEL0 = 0,         /* [0..32]  units whose LAST EVALUATED exclusion level was k     */
+    P2S_STAT_NOT_EVALUATED = 33, /* units for which no level could be evaluated (nexcl = n_cams)  */
+    P2S_STAT_FAILED = 34,        /* units returned as NaN (error above threshold at the end)      */
+    P2S_STAT_CANDIDATES = 35,    /* candidate camera subsets solved (DLT + reprojection)          */
+    P2S_STAT_CAM_SOLVES = 36,    /* sum over solved candidates of their number of valid cameras   */
+    P2S_STAT_BAND_THRESHOLD = 37,/* units with |error_min - threshold| < eps at an evaluated level */
+    P2S_STAT_BAND_ARGMIN = 38,   /* units whose best and second-best DISTINCT candidate errors at
+                                    an evaluated level differ by < eps                            */
+    P2S_STAT_NEWTON_STEPS = 39,  /* eigen-solver iterations summed over candidates                */
+    P2S_STAT_COUNT = 48
+};
+
+typedef struct p2s_device_info {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    int clock_khz;               /* SM clock reported by the runtime */
+    size_t total_mem;
+    char name[128];
+} p2s_device_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int p2s_create(int device, p2s_handle **out);
+int p2s_destroy(p2s_handle *h);
+const char *p2s_status_string(int status);
+const char *p2s_last_cuda_error(const p2s_handle *h);
+int p2s_get_device_info(const p2s_handle *h, p2s_device_info *info);
+/* eps of the two decision bands counted in the statistics block (default 1e-6 px). */
+int p2s_set_band_eps(p2s_handle *h, double eps_px);
+/* eigen-solver selection: 0 = safeguarded secular Newton (default), 1 = cyclic Jacobi sweeps
+ * (the north-star's nominal solver; kept for A/B evidence). */
+int p2s_set_solver(p2s_handle *h, int solver);
+
+/* ---- staging (triangulation.py:817-821 + layout) -------------------------------------------- *
+ * x, y, lik: [n_units][n_cams] float32, row-major (unit = frame x person x keypoint).
+ * obs_out  : float4 [n_cams][n_units] = {x, y, likelihood, 0}; likelihood < lik_thr (and not NaN)
+ *            turns the whole triple into NaN, exactly like the reference's gate.
+ *            Pass lik_thr = -INFINITY (or NaN) to stage without gating.                          */
+size_t p2s_obs_bytes(long long n_units, int n_cams);
+int p2s_stage_observations_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                  long long n_units, int n_cams, double lik_thr,
+                                  void *obs_out, void *stream);
+
+/* ---- triangulation with camera-exclusion search --------------------------------------------- *
+ * obs        : staged float4 [n_cams][n_units] (device)
+ * P          : HOST pointer, n_cams x 12 float64 (row-major 3x4 per camera, common.py:291 computeP)
+ * out_Q      : [n_units][3] float64, NaN when the unit failed
+ * out_err    : [n_units]    float64 reprojection error (px), NaN when failed
+ * out_nexcl  : [n_units]    uint8   nb_cams_excluded (NaN-or-zero likelihood count of the chosen subset)
+ * out_mask   : [n_units]    uint32  bit c set <=> camera c in id_excluded_cams
+ * stats      : device pointer to P2S_STAT_COUNT uint64 (accumulated, caller zeroes) or NULL      */
+int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P,
+                           long long n_units, int n_cams, double reproj_thr, int min_cams,
+                           double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                           unsigned long long *stats, void *stream);
+
+/* Whole job from host buffers: chunked H2D -> stage -> search -> D2H, overlapped on internal
+ * streams.  x/y/lik as for p2s_stage_observations_device but HOST pointers (pinned = faster);
+ * outputs HOST pointers; stats: HOST pointer to P2S_STAT_COUNT uint64 (overwritten) or NULL.     */
+int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik,
+                         const double *P, long long n_units, int n_cams,
+                         double lik_thr, double reproj_thr, int min_cams,
+                         double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                         unsigned long long *stats);
+
+/* ---- single-person association search (personAssociation.py:154) ---------------------------- *
+ * obs        : float4 [n_frames][n_cams][max_persons] = {x, y, likelihood, 0} of the tracked keypoint
+ *              (device for *_device, host for *_host); entries >= count are ignored
+ * count      : int32 [n_frames][n_cams] persons detected per camera (0 = none)
+ * out_err    : [n_frames] float64 best error (+inf when nothing was evaluable)
+ * out_comb   : [n_frames][n_cams] int8 chosen person index per camera, -1 = camera off (NaN)
+ * out_Q      : [n_frames][3] float64
+ * out_stats  : [n_frames][2] uint32 {combination rows visited, candidates solved} or NULL        */
+int p2s_associate_device(p2s_handle *h, const void *obs, const int32_t *count, const double *P,
+                         long long n_frames, int n_cams, int max_persons,
+                         double reproj_thr, double lik_thr, int min_cams,
+                         double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats,
+                         void *stream);
+int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, const double *P,
+                       long long n_frames, int n_cams, int max_persons,
+                       double reproj_thr, double lik_thr, int min_cams,
+                       double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+/* Dependent-chain FP64 FMA microbenchmark on the handle's device: achieved DFMA TFLOP/s
+ * (2 flops per FMA) — the FP64 roofline denominator MEASURED_PEAKS.json does not carry.         */
+int p2s_measure_fp64_peak(p2s_handle *h, double *tflops, double *ms);
+/* Number of kernels this library launched through the handle since creation.                    */
+long long p2s_launch_count(const p2s_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSE2SIM_B200_H */

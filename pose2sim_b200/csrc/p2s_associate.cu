@@ -1,0 +1,247 @@
+// Single-person association search: which detected person of each camera (and which cameras)
+// triangulate the tracked keypoint best.
+//
+// Replaces, per frame, `persons_combinations` + `best_persons_and_cameras_combination` +
+// `triangulate_comb` (Pose2Sim/personAssociation.py:67-99, :154-257, :102-151), restated in
+// SURVEY.md §8(a) `associate_frame`:
+//
+//   rows = itertools.product(range(max(n_c, 1)) for c)       last camera fastest            (:95-97)
+//   k = 0; err_last = inf; best = inf
+//   while err_last > thr and C - (n_missing + k) >= min_cams:                                (:194)
+//       for row in rows (product order):                                                     (:196)
+//           camera off when n_c == 0, likelihood < lik_thr, or likelihood == 0               (:215-216)
+//           skip if fewer than min_cams active                                               (:219-221)
+//           candidates = lexicographic k-subsets of the ACTIVE cameras                       (:222-225)
+//           solve each; skip row if all NaN; err_last = nanmin                               (:229-238)
+//           best updated on strict '<'; first row with err_last < thr ends the row loop      (:242-248)
+//       k += 1
+//
+// Mapping: one warp per frame (frames are plentiful, rows per frame usually few), one LANE PER ROW
+// in ordered chunks of 32 rows.  Each lane walks its row's candidate subsets serially (the
+// lexicographic k-subsets of the active cameras are the subsequence of the all-camera table whose
+// members are subsets of `active`, so the triangulation kernel's mask table is reused).  The ordered
+// early exit is a ballot: the first lane whose row is under the threshold wins and later lanes of
+// the chunk are discarded; the running best is a shuffle arg-min over (error, row).
+#include "p2s_math.cuh"
+#include "p2s_internal.h"
+
+namespace p2s {
+
+struct AssocArgs {
+    const float4 *obs;            // [n_frames][n_cams][max_persons]
+    const int32_t *count;         // [n_frames][n_cams]
+    long long n_frames;
+    int n_cams, max_persons, min_cams;
+    double thr, lik_thr;
+    const uint32_t *cand_masks;
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    double *out_err;
+    int8_t *out_comb;
+    double *out_Q;
+    uint32_t *out_stats;
+    unsigned int *tile_counter;
+};
+
+template <int CMAX>
+__global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int C = a.n_cams, NP = a.max_persons;
+    // per-warp slab: obs float4 [C][NP], then n_c' (uint32 [CMAX]), ok masks (uint32 [CMAX])
+    const size_t slab = (size_t)CMAX * NP * sizeof(float4) + 2 * CMAX * sizeof(uint32_t);
+    unsigned char *base = smem_raw + slab * warp;
+    float4 *sobs = reinterpret_cast<float4 *>(base);
+    uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * sizeof(float4));
+    uint32_t *s_ok = s_n + CMAX;
+    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+
+    for (;;) {
+        unsigned int f = 0;
+        if (lane == 0) f = atomicAdd(a.tile_counter, 1u);
+        f = __shfl_sync(P2S_FULL, f, 0);
+        if ((long long)f >= a.n_frames) break;
+
+        // ---- stage the frame ------------------------------------------------------------------------
+        const float4 *fobs = a.obs + (long long)f * C * NP;
+        for (int i = lane; i < C * NP; i += 32) sobs[i] = __ldg(fobs + i);
+        __syncwarp();
+        if (lane < C) {
+            int n = a.count[(long long)f * C + lane];
+            n = max(0, min(n, NP));
+            uint32_t ok = 0;
+            for (int p = 0; p < n; ++p) {
+                const double l = (double)sobs[lane * NP + p].z;
+                // gate (:215-216): likelihood < thr -> 0 -> off; likelihood == 0 -> off; NaN stays on
+                if (!(l < a.lik_thr) && !(l == 0.0)) ok |= 1u << p;
+            }
+            s_n[lane] = (uint32_t)n;
+            s_ok[lane] = ok;
+        }
+        __syncwarp();
+        uint32_t present = 0;
+        unsigned long long total_rows = 1;
+        bool overflow = false;
+        for (int c = 0; c < C; ++c) {
+            const uint32_t n = s_n[c];
+            if (n) present |= 1u << c;
+            const unsigned long long nn = n ? n : 1u;
+            if (total_rows > (0x7fffffffffffffffULL / nn)) overflow = true; else total_rows *= nn;
+        }
+        const int n_missing = C - __popc(present);
+
+        double err_last = inf64();
+        unsigned long long best_key = P2S_KEY_EMPTY;          // key of the global best (strict '<' updates)
+        double bqx = nan64(), bqy = bqx, bqz = bqx;
+        uint32_t b_valid = 0;                                 // cameras used by the best candidate
+        unsigned long long b_row = 0;
+        unsigned int st_rows = 0, st_cands = 0;
+
+        for (int k = 0; !overflow && err_last > a.thr && C - (n_missing + k) >= a.min_cams; ++k) {
+            const bool tabled = k <= a.max_table_level;
+            const uint32_t ncand_all = tabled ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
+            const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
+            bool hit = false;
+            for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += 32) {
+                const unsigned long long r = rbase + lane;
+                const bool row_ok = r < total_rows;
+                // decode the row: last camera fastest (itertools.product)
+                uint32_t dig[4] = {0, 0, 0, 0};               // 4 bits per camera
+                uint32_t active = 0;
+                {
+                    unsigned long long q = r;
+#pragma unroll
+                    for (int c = CMAX - 1; c >= 0; --c) {
+                        if (c < C) {
+                            const uint32_t n = s_n[c];
+                            uint32_t p = 0;
+                            if (n > 1) { p = (uint32_t)(q % n); q /= n; }
+                            dig[c >> 3] |= p << ((c & 7) * 4);
+                            if (n && ((s_ok[c] >> p) & 1u)) active |= 1u << c;
+                        }
+                    }
+                }
+                const int na = __popc(active);
+                unsigned long long rkey = P2S_KEY_EMPTY;
+                double rqx = nan64(), rqy = rqx, rqz = rqx;
+                uint32_t rvalid = 0;
+                if (row_ok && na >= a.min_cams && k <= na) {
+                    auto fetch = [&](int c) -> float4 { return sobs[c * NP + ((dig[c >> 3] >> ((c & 7) * 4)) & 15u)]; };
+                    for (uint32_t ci = 0; ci < ncand_all; ++ci) {
+                        const uint32_t cm = tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
+                        if (cm & ~active) continue;           // not a subset of the active cameras
+                        double cqx, cqy, cqz, e;
+                        solve_subset<CMAX, 0>(cams, fetch, C, active & ~cm, cqx, cqy, cqz, e);
+                        ++st_cands;
+                        const unsigned long long key = err_key(e);
+                        if (key < rkey) { rkey = key; rqx = cqx; rqy = cqy; rqz = cqz; rvalid = active & ~cm; }
+                    }
+                }
+                // all-NaN rows are skipped (:235-236); rows without candidates too
+                const bool evaluated = rkey < P2S_KEY_NAN;
+                const double rerr = key_err(rkey);
+                const uint32_t evalmask = __ballot_sync(P2S_FULL, evaluated);
+                const uint32_t hitmask = __ballot_sync(P2S_FULL, evaluated && rerr < a.thr);
+                uint32_t upto = 0xffffffffu;                  // lanes at or before the first hit
+                if (hitmask) { const int fh = __ffs(hitmask) - 1; upto = (fh == 31) ? 0xffffffffu : ((2u << fh) - 1u); hit = true; }
+                const uint32_t considered = evalmask & upto;
+                st_rows += (unsigned)__popc(__ballot_sync(P2S_FULL, row_ok) & upto);
+                if (considered) {
+                    // err_last = error of the last evaluated row in visiting order
+                    const int last = 31 - __clz(considered);
+                    err_last = __shfl_sync(P2S_FULL, rerr, last);
+                    // chunk arg-min over (key, lane) among considered lanes
+                    unsigned long long ck = ((considered >> lane) & 1u) ? rkey : P2S_KEY_EMPTY;
+                    int cl = lane;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const unsigned long long ok2 = __shfl_xor_sync(P2S_FULL, ck, off);
+                        const int ol = __shfl_xor_sync(P2S_FULL, cl, off);
+                        if (ok2 < ck || (ok2 == ck && ol < cl)) { ck = ok2; cl = ol; }
+                    }
+                    if (ck < best_key) {                      // strict '<' (:242)
+                        best_key = ck;
+                        bqx = __shfl_sync(P2S_FULL, rqx, cl);
+                        bqy = __shfl_sync(P2S_FULL, rqy, cl);
+                        bqz = __shfl_sync(P2S_FULL, rqz, cl);
+                        b_valid = __shfl_sync(P2S_FULL, rvalid, cl);
+                        b_row = rbase + (unsigned long long)cl;
+                    }
+                }
+            }
+        }
+
+        // ---- write the frame's result -----------------------------------------------------------------
+        if (lane == 0) {
+            const bool any = best_key != P2S_KEY_EMPTY;
+            a.out_err[f] = any ? key_err(best_key) : inf64();
+            double *q = a.out_Q + (long long)f * 3;
+            q[0] = any ? bqx : nan64(); q[1] = any ? bqy : nan64(); q[2] = any ? bqz : nan64();
+            if (a.out_stats) { a.out_stats[(long long)f * 2] = st_rows; a.out_stats[(long long)f * 2 + 1] = 0; }
+        }
+        if (a.out_stats) {
+            unsigned int sc = st_cands;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(P2S_FULL, sc, off);
+            if (lane == 0) a.out_stats[(long long)f * 2 + 1] = sc;
+        }
+        if (lane < C) {
+            int8_t v = -1;
+            if (best_key != P2S_KEY_EMPTY && ((b_valid >> lane) & 1u)) {
+                // digit of camera `lane` in row b_row
+                unsigned long long q = b_row;
+                uint32_t p = 0;
+                for (int c = C - 1; c >= lane; --c) {
+                    const uint32_t n = s_n[c];
+                    p = 0;
+                    if (n > 1) { p = (uint32_t)(q % n); q /= n; }
+                }
+                v = (int8_t)p;
+            }
+            a.out_comb[(long long)f * C + lane] = v;
+        }
+        __syncwarp();
+    }
+    (void)cmask;
+}
+
+template <int CMAX>
+static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0) {
+    CamParams<CMAX> cams;
+    for (int c = 0; c < CMAX; ++c)
+        for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
+    AssocArgs a = a0;
+    const size_t slab = (size_t)CMAX * L.max_persons * sizeof(float4) + 2 * CMAX * sizeof(uint32_t);
+    const size_t smem = slab * 4;
+    auto kern = associate_kernel<CMAX>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (L.n_frames + 3) / 4;
+    long long grid = (long long)L.sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_associate(const AssocLaunch &L) {
+    AssocArgs a;
+    a.obs = (const float4 *)L.obs; a.count = L.count; a.n_frames = L.n_frames;
+    a.n_cams = L.n_cams; a.max_persons = L.max_persons; a.min_cams = L.min_cams;
+    a.thr = L.thr; a.lik_thr = L.lik_thr; a.cand_masks = L.cand_masks;
+    for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
+    a.max_table_level = L.max_table_level;
+    a.out_err = L.out_err; a.out_comb = L.out_comb; a.out_Q = L.out_Q; a.out_stats = L.out_stats;
+    a.tile_counter = L.tile_counter;
+    if (L.n_cams <= 4) return launch_assoc<4>(L, a);
+    if (L.n_cams <= 8) return launch_assoc<8>(L, a);
+    if (L.n_cams <= 16) return launch_assoc<16>(L, a);
+    return launch_assoc<32>(L, a);
+}
+
+}  // namespace p2s

@@ -1,0 +1,404 @@
+// C-ABI layer (include/pose2sim_b200.h): handle, subset tables, stream pipeline for host buffers.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "p2s_internal.h"
+
+namespace {
+
+constexpr int kSlots = 3;                         // H2D / compute / D2H overlap
+constexpr long long kChunkUnits = 1 << 18;        // units per pipeline chunk
+constexpr long long kChunkFrames = 1 << 14;       // association frames per chunk
+constexpr unsigned long long kMaxTableEntries = 1ULL << 22;
+
+struct SubsetTable {
+    uint32_t *d_masks = nullptr;
+    uint32_t level_off[P2S_MAX_CAMS + 2] = {0};
+    int max_level = -1;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf x, y, lik, obs, Q, err, nexcl, mask, count, comb, astats;
+};
+
+}  // namespace
+
+struct p2s_handle {
+    int device = 0;
+    cudaDeviceProp prop;
+    double band_eps = 1e-6;
+    int solver = 0;
+    long long launches = 0;
+    std::string last_error;
+    SubsetTable tables[P2S_MAX_CAMS + 1];
+    Slot slots[kSlots];
+    unsigned int *d_counters = nullptr;           // ring of tile counters
+    int counter_next = 0;
+    unsigned long long *d_stats = nullptr;
+    double *d_peak = nullptr;
+};
+
+namespace {
+
+constexpr int kCounterRing = 256;
+
+int cuda_fail(p2s_handle *h, cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    if (h) h->last_error = buf;
+    return P2S_ECUDA;
+}
+
+#define P2S_CUDA(h, call)                                          \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail((h), e__, #call); \
+    } while (0)
+
+int ensure(p2s_handle *h, DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes) return P2S_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cuda_fail(h, e, "cudaMalloc"); return P2S_ENOMEM; }
+    b.cap = want;
+    return P2S_OK;
+}
+
+// Lexicographic k-subsets of {0..n-1} as bit masks, levels 0..max_level concatenated
+// (itertools.combinations order, triangulation.py:411).
+int build_table(p2s_handle *h, int n) {
+    SubsetTable &t = h->tables[n];
+    if (t.d_masks) return P2S_OK;
+    std::vector<uint32_t> masks;
+    unsigned long long total = 0;
+    int level = 0;
+    t.level_off[0] = 0;
+    for (; level <= n; ++level) {
+        // C(n, level)
+        unsigned long long cnt = 1;
+        for (int i = 1; i <= level; ++i) cnt = cnt * (unsigned)(n - level + i) / (unsigned)i;
+        if (total + cnt > kMaxTableEntries) break;
+        std::vector<int> idx(level);
+        for (int i = 0; i < level; ++i) idx[i] = i;
+        for (;;) {
+            uint32_t m = 0;
+            for (int i = 0; i < level; ++i) m |= 1u << idx[i];
+            masks.push_back(m);
+            int i = level - 1;
+            while (i >= 0 && idx[i] == n - level + i) --i;
+            if (i < 0) break;
+            ++idx[i];
+            for (int j = i + 1; j < level; ++j) idx[j] = idx[j - 1] + 1;
+        }
+        total += cnt;
+        t.level_off[level + 1] = (uint32_t)total;
+    }
+    t.max_level = level - 1;
+    for (int l = level + 1; l < P2S_MAX_CAMS + 2; ++l) t.level_off[l] = (uint32_t)total;
+    P2S_CUDA(h, cudaMalloc((void **)&t.d_masks, masks.size() * sizeof(uint32_t)));
+    P2S_CUDA(h, cudaMemcpy(t.d_masks, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return P2S_OK;
+}
+
+unsigned int *next_counter(p2s_handle *h) {
+    unsigned int *c = h->d_counters + h->counter_next;
+    h->counter_next = (h->counter_next + 1) % kCounterRing;
+    return c;
+}
+
+int check_tri_args(int n_cams, int min_cams, long long n_units) {
+    if (n_cams < 2 || n_cams > P2S_MAX_CAMS) return P2S_EINVAL;
+    if (min_cams < 1) return P2S_EINVAL;
+    if (n_units < 0 || n_units > 0x7fffffffLL * 32) return P2S_EINVAL;
+    return P2S_OK;
+}
+
+int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, long long n_units, int n_cams,
+                        double thr, int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask,
+                        unsigned long long *stats, cudaStream_t stream) {
+    int rc = build_table(h, n_cams);
+    if (rc) return rc;
+    if (n_units == 0) return P2S_OK;
+    p2s::TriLaunch L;
+    L.obs = obs; L.P = P; L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams;
+    L.solver = h->solver; L.sm_count = h->prop.multiProcessorCount;
+    L.thr = thr; L.band_eps = h->band_eps;
+    const SubsetTable &t = h->tables[n_cams];
+    L.cand_masks = t.d_masks;
+    std::memcpy(L.level_off, t.level_off, sizeof L.level_off);
+    L.max_table_level = t.max_level;
+    L.out_Q = Q; L.out_err = err; L.out_nexcl = nexcl; L.out_mask = mask; L.stats = stats;
+    L.tile_counter = next_counter(h);
+    L.stream = stream;
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
+    P2S_CUDA(h, p2s::launch_triangulate(L));
+    h->launches += 1;
+    return P2S_OK;
+}
+
+int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, const double *P, long long n_frames,
+                      int n_cams, int max_persons, double thr, double lik_thr, int min_cams,
+                      double *err, int8_t *comb, double *Q, uint32_t *stats, cudaStream_t stream) {
+    int rc = build_table(h, n_cams);
+    if (rc) return rc;
+    if (n_frames == 0) return P2S_OK;
+    p2s::AssocLaunch L;
+    L.obs = obs; L.count = count; L.P = P; L.n_frames = n_frames; L.n_cams = n_cams;
+    L.max_persons = max_persons; L.min_cams = min_cams; L.sm_count = h->prop.multiProcessorCount;
+    L.thr = thr; L.lik_thr = lik_thr;
+    const SubsetTable &t = h->tables[n_cams];
+    L.cand_masks = t.d_masks;
+    std::memcpy(L.level_off, t.level_off, sizeof L.level_off);
+    L.max_table_level = t.max_level;
+    L.out_err = err; L.out_comb = comb; L.out_Q = Q; L.out_stats = stats;
+    L.tile_counter = next_counter(h);
+    L.stream = stream;
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
+    P2S_CUDA(h, p2s::launch_associate(L));
+    h->launches += 1;
+    return P2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *p2s_status_string(int s) {
+    switch (s) {
+        case P2S_OK: return "ok";
+        case P2S_EINVAL: return "invalid argument";
+        case P2S_ENODEVICE: return "no usable CUDA device (sm_100 required); there is no CPU fallback";
+        case P2S_ECUDA: return "CUDA error";
+        case P2S_ENOMEM: return "out of device memory";
+        case P2S_ETOODEEP: return "search too deep to enumerate";
+        default: return "unknown status";
+    }
+}
+
+int p2s_create(int device, p2s_handle **out) {
+    if (!out) return P2S_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return P2S_ENODEVICE;
+    p2s_handle *h = new (std::nothrow) p2s_handle();
+    if (!h) return P2S_ENOMEM;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
+        delete h;
+        return P2S_ENODEVICE;
+    }
+    if (h->prop.major != 10) {                     // the fatbin holds sm_100a code only
+        delete h;
+        return P2S_ENODEVICE;
+    }
+    for (int i = 0; i < kSlots; ++i)
+        if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return P2S_ECUDA; }
+    if (cudaMalloc((void **)&h->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long)) != cudaSuccess) {
+        delete h;
+        return P2S_ENOMEM;
+    }
+    *out = h;
+    return P2S_OK;
+}
+
+int p2s_destroy(p2s_handle *h) {
+    if (!h) return P2S_EINVAL;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &t : h->tables) if (t.d_masks) cudaFree(t.d_masks);
+    for (auto &s : h->slots) {
+        for (DevBuf *b : {&s.x, &s.y, &s.lik, &s.obs, &s.Q, &s.err, &s.nexcl, &s.mask, &s.count, &s.comb, &s.astats})
+            if (b->p) cudaFree(b->p);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (h->d_counters) cudaFree(h->d_counters);
+    if (h->d_stats) cudaFree(h->d_stats);
+    if (h->d_peak) cudaFree(h->d_peak);
+    delete h;
+    return P2S_OK;
+}
+
+const char *p2s_last_cuda_error(const p2s_handle *h) { return h ? h->last_error.c_str() : ""; }
+
+int p2s_get_device_info(const p2s_handle *h, p2s_device_info *info) {
+    if (!h || !info) return P2S_EINVAL;
+    std::memset(info, 0, sizeof *info);
+    info->device = h->device;
+    info->sm_count = h->prop.multiProcessorCount;
+    info->cc_major = h->prop.major;
+    info->cc_minor = h->prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    info->clock_khz = khz;
+    info->total_mem = h->prop.totalGlobalMem;
+    std::strncpy(info->name, h->prop.name, sizeof info->name - 1);
+    return P2S_OK;
+}
+
+int p2s_set_band_eps(p2s_handle *h, double eps) {
+    if (!h || !(eps >= 0.0)) return P2S_EINVAL;
+    h->band_eps = eps;
+    return P2S_OK;
+}
+
+int p2s_set_solver(p2s_handle *h, int solver) {
+    if (!h || (solver != 0 && solver != 1)) return P2S_EINVAL;
+    h->solver = solver;
+    return P2S_OK;
+}
+
+size_t p2s_obs_bytes(long long n_units, int n_cams) {
+    if (n_units < 0 || n_cams < 0) return 0;
+    return (size_t)n_units * (size_t)n_cams * 16u;
+}
+
+int p2s_stage_observations_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                  long long n_units, int n_cams, double lik_thr, void *obs_out, void *stream) {
+    if (!h || !x || !y || !lik || !obs_out) return P2S_EINVAL;
+    if (n_cams < 1 || n_cams > P2S_MAX_CAMS || n_units < 0) return P2S_EINVAL;
+    if (n_units == 0) return P2S_OK;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, p2s::launch_stage(x, y, lik, n_units, n_cams, lik_thr, obs_out, h->prop.multiProcessorCount, (cudaStream_t)stream));
+    h->launches += 1;
+    return P2S_OK;
+}
+
+int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P, long long n_units, int n_cams,
+                           double reproj_thr, int min_cams, double *out_Q, double *out_err, uint8_t *out_nexcl,
+                           uint32_t *out_mask, unsigned long long *stats, void *stream) {
+    if (!h || !P || (n_units > 0 && (!obs || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    return enqueue_triangulate(h, obs, P, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl, out_mask,
+                               stats, (cudaStream_t)stream);
+}
+
+int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik, const double *P,
+                         long long n_units, int n_cams, double lik_thr, double reproj_thr, int min_cams,
+                         double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                         unsigned long long *stats) {
+    if (!h || !P || (n_units > 0 && (!x || !y || !lik || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    if (stats) P2S_CUDA(h, cudaMemsetAsync(h->d_stats, 0, P2S_STAT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
+    if (stats) P2S_CUDA(h, cudaStreamSynchronize(h->slots[0].stream));
+    const size_t C = (size_t)n_cams;
+    long long chunk = std::min<long long>(kChunkUnits, std::max<long long>(n_units, 1));
+    int i = 0;
+    for (long long u0 = 0; u0 < n_units; u0 += chunk, ++i) {
+        const long long nu = std::min(chunk, n_units - u0);
+        Slot &s = h->slots[i % kSlots];
+        if ((rc = ensure(h, s.x, nu * C * 4)) || (rc = ensure(h, s.y, nu * C * 4)) || (rc = ensure(h, s.lik, nu * C * 4)) ||
+            (rc = ensure(h, s.obs, nu * C * 16)) || (rc = ensure(h, s.Q, nu * 24)) || (rc = ensure(h, s.err, nu * 8)) ||
+            (rc = ensure(h, s.nexcl, nu)) || (rc = ensure(h, s.mask, nu * 4)))
+            return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(s.x.p, x + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(s.y.p, y + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(s.lik.p, lik + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, p2s::launch_stage((const float *)s.x.p, (const float *)s.y.p, (const float *)s.lik.p, nu, n_cams,
+                                     lik_thr, s.obs.p, h->prop.multiProcessorCount, s.stream));
+        h->launches += 1;
+        rc = enqueue_triangulate(h, s.obs.p, P, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
+                                 (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream);
+        if (rc) return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(out_Q + u0 * 3, s.Q.p, nu * 24, cudaMemcpyDeviceToHost, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(out_err + u0, s.err.p, nu * 8, cudaMemcpyDeviceToHost, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(out_nexcl + u0, s.nexcl.p, nu, cudaMemcpyDeviceToHost, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(out_mask + u0, s.mask.p, nu * 4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
+    if (stats) P2S_CUDA(h, cudaMemcpy(stats, h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return P2S_OK;
+}
+
+int p2s_associate_device(p2s_handle *h, const void *obs, const int32_t *count, const double *P, long long n_frames,
+                         int n_cams, int max_persons, double reproj_thr, double lik_thr, int min_cams,
+                         double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats, void *stream) {
+    if (!h || !P || (n_frames > 0 && (!obs || !count || !out_err || !out_comb || !out_Q))) return P2S_EINVAL;
+    if (n_cams < 2 || n_cams > P2S_MAX_CAMS || min_cams < 1 || n_frames < 0 || n_frames > 0xfffffff0LL) return P2S_EINVAL;
+    if (max_persons < 1 || max_persons > P2S_MAX_PERSONS) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    return enqueue_associate(h, obs, count, P, n_frames, n_cams, max_persons, reproj_thr, lik_thr, min_cams, out_err,
+                             out_comb, out_Q, out_stats, (cudaStream_t)stream);
+}
+
+int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, const double *P, long long n_frames,
+                       int n_cams, int max_persons, double reproj_thr, double lik_thr, int min_cams,
+                       double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats) {
+    if (!h || !P || (n_frames > 0 && (!obs || !count || !out_err || !out_comb || !out_Q))) return P2S_EINVAL;
+    if (n_cams < 2 || n_cams > P2S_MAX_CAMS || min_cams < 1 || n_frames < 0 || n_frames > 0xfffffff0LL) return P2S_EINVAL;
+    if (max_persons < 1 || max_persons > P2S_MAX_PERSONS) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    const size_t C = (size_t)n_cams, NP = (size_t)max_persons;
+    int rc, i = 0;
+    const long long chunk = kChunkFrames;
+    for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
+        const long long nf = std::min(chunk, n_frames - f0);
+        Slot &s = h->slots[i % kSlots];
+        if ((rc = ensure(h, s.obs, nf * C * NP * 16)) || (rc = ensure(h, s.count, nf * C * 4)) || (rc = ensure(h, s.err, nf * 8)) ||
+            (rc = ensure(h, s.comb, nf * C)) || (rc = ensure(h, s.Q, nf * 24)) || (rc = ensure(h, s.astats, nf * 8)))
+            return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(s.obs.p, obs + f0 * C * NP * 4, nf * C * NP * 16, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(s.count.p, count + f0 * C, nf * C * 4, cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue_associate(h, s.obs.p, (const int32_t *)s.count.p, P, nf, n_cams, max_persons, reproj_thr, lik_thr,
+                               min_cams, (double *)s.err.p, (int8_t *)s.comb.p, (double *)s.Q.p,
+                               out_stats ? (uint32_t *)s.astats.p : nullptr, s.stream);
+        if (rc) return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(out_err + f0, s.err.p, nf * 8, cudaMemcpyDeviceToHost, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(out_comb + f0 * C, s.comb.p, nf * C, cudaMemcpyDeviceToHost, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(out_Q + f0 * 3, s.Q.p, nf * 24, cudaMemcpyDeviceToHost, s.stream));
+        if (out_stats) P2S_CUDA(h, cudaMemcpyAsync(out_stats + f0 * 2, s.astats.p, nf * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
+    return P2S_OK;
+}
+
+int p2s_measure_fp64_peak(p2s_handle *h, double *tflops, double *ms_out) {
+    if (!h || !tflops) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    const int blocks = h->prop.multiProcessorCount * 8, iters = 4096;
+    if (!h->d_peak) P2S_CUDA(h, cudaMalloc((void **)&h->d_peak, (size_t)blocks * 256 * sizeof(double)));
+    cudaStream_t st = h->slots[0].stream;
+    cudaEvent_t e0, e1;
+    P2S_CUDA(h, cudaEventCreate(&e0));
+    P2S_CUDA(h, cudaEventCreate(&e1));
+    double best = 0.0, best_ms = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        P2S_CUDA(h, cudaEventRecord(e0, st));
+        P2S_CUDA(h, p2s::launch_fp64_peak(h->d_peak, blocks, iters, st));
+        P2S_CUDA(h, cudaEventRecord(e1, st));
+        P2S_CUDA(h, cudaEventSynchronize(e1));
+        h->launches += 1;
+        float ms = 0.f;
+        P2S_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * 256.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) { best = tf; best_ms = ms; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    if (ms_out) *ms_out = best_ms;
+    return P2S_OK;
+}
+
+long long p2s_launch_count(const p2s_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

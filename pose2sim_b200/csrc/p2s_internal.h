@@ -1,0 +1,50 @@
+// Internal launch descriptors shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/pose2sim_b200.h"
+
+namespace p2s {
+
+struct TriLaunch {
+    const void *obs;              // float4 [n_cams][n_units], device
+    const double *P;              // host, n_cams x 12
+    long long n_units;
+    int n_cams, min_cams, solver, sm_count;
+    double thr, band_eps;
+    const uint32_t *cand_masks;   // device
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    double *out_Q, *out_err;
+    uint8_t *out_nexcl;
+    uint32_t *out_mask;
+    unsigned long long *stats;    // device or null
+    unsigned int *tile_counter;   // device, zeroed on the same stream before the launch
+    cudaStream_t stream;
+};
+
+struct AssocLaunch {
+    const void *obs;              // float4 [n_frames][n_cams][max_persons], device
+    const int32_t *count;         // [n_frames][n_cams], device
+    const double *P;              // host
+    long long n_frames;
+    int n_cams, max_persons, min_cams, sm_count;
+    double thr, lik_thr;
+    const uint32_t *cand_masks;   // same lexicographic all-camera table as the triangulation kernel
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    double *out_err;
+    int8_t *out_comb;
+    double *out_Q;
+    uint32_t *out_stats;
+    unsigned int *tile_counter;
+    cudaStream_t stream;
+};
+
+cudaError_t launch_triangulate(const TriLaunch &L);
+cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
+                         double lik_thr, void *out, int sm_count, cudaStream_t stream);
+cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
+cudaError_t launch_associate(const AssocLaunch &L);
+
+}  // namespace p2s

@@ -1,0 +1,265 @@
+// Device-side leaf math of the triangulation hot path (sm_100a, FP64 CUDA-core pipe).
+//
+// What is computed (reference: Pose2Sim/common.py:327-403, restated in SURVEY.md §8(a) `solve`):
+//   M   = sum over valid cameras c, ascending, of r1 r1^T + r2 r2^T,
+//         r1 = (P_c[0] - x_c P_c[2]) w_c,  r2 = (P_c[1] - y_c P_c[2]) w_c          (common.py:344-345)
+//   Q   = v[0:3]/v[3], v = eigenvector of M for its smallest eigenvalue
+//         (= right singular vector of A for the smallest singular value, common.py:348-350)
+//   err = mean over valid cameras of hypot(x_c - P_c[0].Q~/P_c[2].Q~, y_c - P_c[1].Q~/P_c[2].Q~)
+//                                                    (common.py:357-375, triangulation.py:485-489)
+//
+// How the eigenvector is obtained.  With M = [[A, b], [b^T, c]] (A 3x3) and v = (q, 1), the smallest
+// eigenpair satisfies (A - lam I) q = -b and the secular equation
+//        f(lam) = c - lam + b.q(lam) = 0,   f'(lam) = -(1 + |q|^2),
+// whose smallest root lies left of A's smallest eigenvalue.  f is concave and decreasing there, so
+// Newton from lam = 0 overshoots once and then converges monotonically and quadratically from the
+// right; a pivot check on the 3x3 LDL^T (positive definite <=> lam left of the pole) with bisection
+// back towards the last lam known to be left of the root makes it unconditional.  It needs 3-6
+// factorisations of a 3x3 (about 45 FP64 instructions each) instead of the ~2000 flops + 100
+// divisions/square roots of six cyclic Jacobi sweeps, returns q already de-homogenised, and agrees
+// with cv2.SVDecomp to ~3e-14 m (measured).  The Jacobi variant is kept below for A/B.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define P2S_FULL 0xffffffffu
+
+namespace p2s {
+
+template <int CMAX>
+struct CamParams {           // passed BY VALUE as a kernel parameter => lives in the constant bank,
+    double P[CMAX][12];      // read as immediate-offset constant operands inside the unrolled loops
+};
+
+__device__ __forceinline__ double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double inf64() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// 1/d to ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + one cubic correction (3 DFMA).
+__device__ __forceinline__ double rcp_fast(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// sqrt(a) for a >= 0 to ~1 ulp: MUFU.RSQ64H seed + Halley step + one residual correction.
+__device__ __forceinline__ double sqrt_fast(double a) {
+    double s = fmax(a, 1e-300);                     // a == 0 -> result 0 without a 0*inf NaN
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    double t = s * r;
+    double e = fma(-t, r, 1.0);                     // 1 - s r^2
+    double p = fma(0.375, e, 0.5);
+    r = fma(r * e, p, r);                           // r (1 + e/2 + 3 e^2/8)
+    double q = a * r;
+    double res = fma(-q, q, a);
+    return fma(res * 0.5, r, q);
+}
+
+struct Sym4 {                                       // upper triangle of the symmetric 4x4 normal matrix
+    double m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
+};
+
+__device__ __forceinline__ void sym4_zero(Sym4 &M) {
+    M.m00 = M.m01 = M.m02 = M.m03 = M.m11 = M.m12 = M.m13 = M.m22 = M.m23 = M.m33 = 0.0;
+}
+
+// M += r r^T
+__device__ __forceinline__ void sym4_rank1(Sym4 &M, double r0, double r1, double r2, double r3) {
+    M.m00 = fma(r0, r0, M.m00); M.m01 = fma(r0, r1, M.m01); M.m02 = fma(r0, r2, M.m02); M.m03 = fma(r0, r3, M.m03);
+    M.m11 = fma(r1, r1, M.m11); M.m12 = fma(r1, r2, M.m12); M.m13 = fma(r1, r3, M.m13);
+    M.m22 = fma(r2, r2, M.m22); M.m23 = fma(r2, r3, M.m23);
+    M.m33 = fma(r3, r3, M.m33);
+}
+
+// Adds camera c's two weighted DLT rows to M (common.py:344-345).
+__device__ __forceinline__ void accumulate_camera(Sym4 &M, const double *Pc, double x, double y, double w) {
+    double a0 = fma(-x, Pc[8], Pc[0]) * w, a1 = fma(-x, Pc[9], Pc[1]) * w;
+    double a2 = fma(-x, Pc[10], Pc[2]) * w, a3 = fma(-x, Pc[11], Pc[3]) * w;
+    sym4_rank1(M, a0, a1, a2, a3);
+    double b0 = fma(-y, Pc[8], Pc[4]) * w, b1 = fma(-y, Pc[9], Pc[5]) * w;
+    double b2 = fma(-y, Pc[10], Pc[6]) * w, b3 = fma(-y, Pc[11], Pc[7]) * w;
+    sym4_rank1(M, b0, b1, b2, b3);
+}
+
+// Smallest eigenvector of M, de-homogenised: safeguarded Newton on the secular equation.
+// Returns the number of factorisations used.
+__device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
+    double lam = 0.0, lo = 0.0, prev = inf64();
+    double x0 = nan64(), x1 = x0, x2 = x0;
+    int it = 0;
+#pragma unroll 1
+    for (; it < 24; ++it) {
+        double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
+        double r0 = rcp_fast(a00);
+        double l10 = M.m01 * r0, l20 = M.m02 * r0;
+        double d1 = fma(-l10, M.m01, a11), t21 = fma(-l20, M.m01, M.m12);
+        double r1 = rcp_fast(d1);
+        double l21 = t21 * r1;
+        double d2 = fma(-l21, t21, fma(-l20, M.m02, a22));
+        if (!(a00 > 0.0 && d1 > 0.0 && d2 > 0.0)) {          // right of the pole (or NaN input)
+            if (!(lam > lo)) break;                          // not even positive definite at lo: give up (NaN)
+            lam = 0.5 * (lam + lo);
+            prev = inf64();
+            continue;
+        }
+        double r2 = rcp_fast(d2);
+        double z0 = -M.m03;
+        double z1 = fma(-l10, z0, -M.m13);
+        double z2 = fma(-l21, z1, fma(-l20, z0, -M.m23));
+        z0 *= r0; z1 *= r1; z2 *= r2;
+        x2 = z2;
+        x1 = fma(-l21, x2, z1);
+        x0 = fma(-l20, x2, fma(-l10, x1, z0));
+        double f = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - lam)));
+        double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
+        double dl = f * rcp_fast(g);
+        if (f > 0.0) lo = lam;
+        double adl = fabs(dl);
+        double dmin = fmin(a00, fmin(d1, d2));
+        // converged: the step no longer moves q (|dq|/|q| ~ |dl|/dmin), or it has reached the
+        // rounding floor of f (stops shrinking while already tiny)
+        if (adl <= 1e-16 * dmin || (adl >= prev && adl <= 1e-9 * dmin)) { ++it; break; }
+        prev = adl;
+        lam += dl;
+    }
+    qx = x0; qy = x1; qz = x2;
+    return it;
+}
+
+// Cyclic Jacobi on the 4x4 (north-star's nominal solver), eigenvectors accumulated; A/B only.
+static __device__ __noinline__ int smallest_eigvec_jacobi(const Sym4 &M, double &qx, double &qy, double &qz) {
+    double a[4][4] = {{M.m00, M.m01, M.m02, M.m03}, {M.m01, M.m11, M.m12, M.m13},
+                      {M.m02, M.m12, M.m22, M.m23}, {M.m03, M.m13, M.m23, M.m33}};
+    double v[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    int sweeps = 0;
+#pragma unroll 1
+    for (; sweeps < 12; ++sweeps) {
+        double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[0][3]) + fabs(a[1][2]) + fabs(a[1][3]) + fabs(a[2][3]);
+        double dia = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]) + fabs(a[3][3]);
+        if (!(off > 1e-22 * dia)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                double apq = a[p][q];
+                if (apq != 0.0) {
+                    double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                    double t = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    t = theta < 0.0 ? -t : t;
+                    double c = 1.0 / sqrt(fma(t, t, 1.0)), s = t * c;
+                    a[p][p] = fma(-t, apq, a[p][p]);
+                    a[q][q] = fma(t, apq, a[q][q]);
+                    a[p][q] = a[q][p] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r != p && r != q) {
+                            double arp = a[r][p], arq = a[r][q];
+                            a[r][p] = a[p][r] = fma(c, arp, -s * arq);
+                            a[r][q] = a[q][r] = fma(s, arp, c * arq);
+                        }
+                        double vrp = v[r][p], vrq = v[r][q];
+                        v[r][p] = fma(c, vrp, -s * vrq);
+                        v[r][q] = fma(s, vrp, c * vrq);
+                    }
+                }
+            }
+        }
+    }
+    int k = 0;
+    double dmin = a[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (a[i][i] < dmin) { dmin = a[i][i]; k = i; }
+    double w = 1.0 / (k == 0 ? v[3][0] : k == 1 ? v[3][1] : k == 2 ? v[3][2] : v[3][3]);
+    qx = (k == 0 ? v[0][0] : k == 1 ? v[0][1] : k == 2 ? v[0][2] : v[0][3]) * w;
+    qy = (k == 0 ? v[1][0] : k == 1 ? v[1][1] : k == 2 ? v[1][2] : v[1][3]) * w;
+    qz = (k == 0 ? v[2][0] : k == 1 ? v[2][1] : k == 2 ? v[2][2] : v[2][3]) * w;
+    return sweeps;
+}
+
+// Pixel distance between the observation (x, y) and the reprojection of Q~ = (qx, qy, qz, 1).
+__device__ __forceinline__ double reproj_distance(const double *Pc, double qx, double qy, double qz, double x, double y) {
+    double u = fma(Pc[0], qx, fma(Pc[1], qy, fma(Pc[2], qz, Pc[3])));
+    double v = fma(Pc[4], qx, fma(Pc[5], qy, fma(Pc[6], qz, Pc[7])));
+    double d = fma(Pc[8], qx, fma(Pc[9], qy, fma(Pc[10], qz, Pc[11])));
+    double rd = rcp_fast(d);
+    double dx = fma(-u, rd, x), dy = fma(-v, rd, y);
+    return sqrt_fast(fma(dx, dx, dy * dy));
+}
+
+// One candidate camera subset `valid` (bit c = camera c used).  `fetch(c)` returns the unit's
+// observation {x, y, likelihood, -} for camera c (from the warp's shared-memory slab).
+// Follows SURVEY.md §8(a) `solve`:
+//   no camera -> (NaN, NaN)   [mean of an empty list];  one camera -> (NaN, +inf)  [common.py:351, :394-396]
+template <int CMAX, int SOLVER, class Fetch>
+__device__ __forceinline__ int solve_subset(const CamParams<CMAX> &cams, Fetch fetch, int n_cams, uint32_t valid,
+                                            double &qx, double &qy, double &qz, double &err) {
+    const int m = __popc(valid);
+    if (m < 2) {
+        qx = qy = qz = nan64();
+        err = (m == 0) ? nan64() : inf64();
+        return 0;
+    }
+    Sym4 M;
+    sym4_zero(M);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < n_cams && ((valid >> c) & 1u)) {
+            const float4 o = fetch(c);
+            accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)o.z);
+        }
+    }
+    int iters;
+    if (SOLVER == 0) iters = smallest_eigvec_secular(M, qx, qy, qz);
+    else iters = smallest_eigvec_jacobi(M, qx, qy, qz);
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < n_cams && ((valid >> c) & 1u)) {
+            const float4 o = fetch(c);
+            sum += reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
+        }
+    }
+    err = sum / (double)m;
+    return iters;
+}
+
+// Order-preserving key for the arg-min over candidate errors (errors are >= 0): finite values by
+// value, +inf after them, NaN after that (np.nanargmin skips NaN; when EVERY candidate is NaN the
+// reference would raise — here the first candidate wins with a NaN error), "no candidate" last.
+#define P2S_KEY_NAN 0xfffffffffffffffeULL
+#define P2S_KEY_EMPTY 0xffffffffffffffffULL
+__device__ __forceinline__ unsigned long long err_key(double e) {
+    return (e != e) ? P2S_KEY_NAN : (unsigned long long)__double_as_longlong(e);
+}
+__device__ __forceinline__ double key_err(unsigned long long k) {
+    return (k >= P2S_KEY_NAN) ? nan64() : __longlong_as_double((long long)k);
+}
+
+// ---- subset enumeration beyond the tabulated levels ------------------------------------------------
+__device__ __forceinline__ uint32_t binom_u32(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    if (k > n - k) k = n - k;
+    unsigned long long r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (unsigned)(n - k + i) / (unsigned)i;
+    return r > 0xffffffffULL ? 0xffffffffu : (uint32_t)r;
+}
+
+// rank -> mask of the rank-th k-subset of {0..n-1} in lexicographic order (itertools.combinations).
+static __device__ __noinline__ uint32_t unrank_subset(int n, int k, uint32_t rank) {
+    uint32_t mask = 0;
+    int x = 0;
+    for (int i = 0; i < k; ++i) {
+        for (;; ++x) {
+            uint32_t cnt = binom_u32(n - 1 - x, k - 1 - i);
+            if (rank < cnt) break;
+            rank -= cnt;
+        }
+        mask |= 1u << x;
+        ++x;
+    }
+    return mask;
+}
+
+}  // namespace p2s

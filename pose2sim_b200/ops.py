@@ -1,0 +1,186 @@
+"""Batched device operators behind the reference's per-unit function seam.
+
+`Engine.triangulate*`  <->  Pose2Sim/triangulation.py:363 `triangulation_from_best_cameras`
+`Engine.associate*`    <->  Pose2Sim/personAssociation.py:154 `best_persons_and_cameras_combination`
+
+PyTorch is used for device memory and streams only; all arithmetic runs in the hand-written sm_100a
+kernels of `libp2s_b200.so`, reached through its C ABI with ctypes.  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_ENGINES = {}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def get_engine(device=0):
+    """One Engine (C-ABI handle) per GPU per process."""
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def _as_P(P, n_cams):
+    P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(n_cams, 12))
+    return P
+
+
+def _ptr(a):
+    """Raw pointer of a numpy array or torch tensor (None -> NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def stats_dict(stats):
+    s = [int(v) for v in stats]
+    levels = s[_lib.STAT_LEVEL0:_lib.STAT_LEVEL0 + 33]
+    while len(levels) > 1 and levels[-1] == 0:
+        levels.pop()
+    return {"level_hist": levels, "not_evaluated": s[_lib.STAT_NOT_EVALUATED], "failed": s[_lib.STAT_FAILED],
+            "candidates": s[_lib.STAT_CANDIDATES], "cam_solves": s[_lib.STAT_CAM_SOLVES],
+            "band_threshold": s[_lib.STAT_BAND_THRESHOLD], "band_argmin": s[_lib.STAT_BAND_ARGMIN],
+            "solver_steps": s[_lib.STAT_NEWTON_STEPS]}
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(None, self.lib.p2s_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        info = _lib.DeviceInfo()
+        _lib.check(self.h, self.lib.p2s_get_device_info(self.h, C.byref(info)))
+        self.info = {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
+                     "clock_khz": info.clock_khz, "total_mem": info.total_mem}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.p2s_destroy(self.h)
+            self.h = None
+
+    # ---- knobs ---------------------------------------------------------------------------------
+    def set_band_eps(self, eps_px):
+        _lib.check(self.h, self.lib.p2s_set_band_eps(self.h, float(eps_px)))
+
+    def set_solver(self, solver):
+        _lib.check(self.h, self.lib.p2s_set_solver(self.h, {"secular": 0, "jacobi": 1}.get(solver, solver)))
+
+    def launch_count(self):
+        return int(self.lib.p2s_launch_count(self.h))
+
+    def fp64_peak(self):
+        tf, ms = C.c_double(), C.c_double()
+        _lib.check(self.h, self.lib.p2s_measure_fp64_peak(self.h, C.byref(tf), C.byref(ms)))
+        return tf.value
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    # ---- device-resident path ------------------------------------------------------------------------
+    def stage_observations(self, x, y, lik, lik_thr=None, out=None):
+        """x, y, lik: CUDA float32 tensors [U, C] -> staged float4 tensor [C, U, 4] with the
+        likelihood gate of triangulation.py:817-821 (lik_thr=None: no gate)."""
+        torch = _torch()
+        U, Cn = x.shape
+        for t in (x, y, lik):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (U, Cn)
+        if out is None:
+            out = torch.empty((Cn, U, 4), dtype=torch.float32, device=x.device)
+        thr = float("-inf") if lik_thr is None else float(lik_thr)
+        _lib.check(self.h, self.lib.p2s_stage_observations_device(self.h, _ptr(x), _ptr(y), _ptr(lik), U, Cn, thr,
+                                                                  _ptr(out), self._stream()))
+        return out
+
+    def triangulate(self, obs, P, reproj_thr, min_cams, out=None, stats=None):
+        """obs: staged CUDA tensor [C, U, 4]; returns dict of CUDA tensors Q[U,3] f64, err[U] f64,
+        nexcl[U] u8, mask[U] i32 (bit pattern of the uint32 mask).  Asynchronous on the current stream."""
+        torch = _torch()
+        Cn, U, four = obs.shape
+        assert four == 4 and obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()
+        dev = obs.device
+        if out is None:
+            out = {"Q": torch.empty((U, 3), dtype=torch.float64, device=dev),
+                   "err": torch.empty((U,), dtype=torch.float64, device=dev),
+                   "nexcl": torch.empty((U,), dtype=torch.uint8, device=dev),
+                   "mask": torch.empty((U,), dtype=torch.int32, device=dev)}
+        Pm = _as_P(P, Cn)
+        _lib.check(self.h, self.lib.p2s_triangulate_device(
+            self.h, _ptr(obs), Pm.ctypes.data, U, Cn, float(reproj_thr), int(min_cams),
+            _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
+        return out
+
+    def new_stats(self):
+        torch = _torch()
+        return torch.zeros(_lib.P2S_STAT_COUNT, dtype=torch.int64, device=f"cuda:{self.device}")
+
+    # ---- host-buffer path (what triangulate_all calls) ---------------------------------------------
+    def triangulate_host(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, want_stats=True):
+        """x, y, lik: host float32 arrays [U, C] (numpy, or pinned torch CPU tensors).  Returns dict of
+        numpy arrays Q[U,3], err[U], nexcl[U] (uint8), mask[U] (uint32) and `stats`."""
+        U, Cn = x.shape
+        for t in (x, y, lik):
+            assert tuple(t.shape) == (U, Cn)
+        xs, ys, ls = (np.ascontiguousarray(t, dtype=np.float32) if isinstance(t, np.ndarray) else t for t in (x, y, lik))
+        if out is None:
+            out = {"Q": np.empty((U, 3), np.float64), "err": np.empty(U, np.float64),
+                   "nexcl": np.empty(U, np.uint8), "mask": np.empty(U, np.uint32)}
+        stats = np.zeros(_lib.P2S_STAT_COUNT, np.uint64) if want_stats else None
+        Pm = _as_P(P, Cn)
+        thr = float("-inf") if lik_thr is None else float(lik_thr)
+        _lib.check(self.h, self.lib.p2s_triangulate_host(
+            self.h, _ptr(xs), _ptr(ys), _ptr(ls), Pm.ctypes.data, U, Cn, thr, float(reproj_thr), int(min_cams),
+            _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats)))
+        if want_stats:
+            out["stats"] = stats_dict(stats)
+        return out
+
+    # ---- association ----------------------------------------------------------------------------------
+    def associate(self, obs, count, P, reproj_thr, lik_thr, min_cams, want_stats=False):
+        """obs: CUDA float32 [F, C, NP, 4]; count: CUDA int32 [F, C].  Returns dict of CUDA tensors."""
+        torch = _torch()
+        F, Cn, NP, four = obs.shape
+        assert four == 4 and obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()
+        assert count.is_cuda and count.dtype == torch.int32 and tuple(count.shape) == (F, Cn) and count.is_contiguous()
+        dev = obs.device
+        out = {"err": torch.empty((F,), dtype=torch.float64, device=dev),
+               "comb": torch.empty((F, Cn), dtype=torch.int8, device=dev),
+               "Q": torch.empty((F, 3), dtype=torch.float64, device=dev)}
+        st = torch.zeros((F, 2), dtype=torch.int32, device=dev) if want_stats else None
+        Pm = _as_P(P, Cn)
+        _lib.check(self.h, self.lib.p2s_associate_device(
+            self.h, _ptr(obs), _ptr(count), Pm.ctypes.data, F, Cn, NP, float(reproj_thr), float(lik_thr), int(min_cams),
+            _ptr(out["err"]), _ptr(out["comb"]), _ptr(out["Q"]), _ptr(st), self._stream()))
+        if want_stats:
+            out["stats"] = st
+        return out
+
+    def associate_host(self, obs, count, P, reproj_thr, lik_thr, min_cams, want_stats=False):
+        """obs: host float32 [F, C, NP, 3 or 4] (x, y, likelihood[, pad]); count: int32 [F, C]."""
+        obs = np.asarray(obs, dtype=np.float32)
+        F, Cn, NP = obs.shape[:3]
+        if obs.shape[3] == 3:
+            o4 = np.zeros((F, Cn, NP, 4), np.float32)
+            o4[..., :3] = obs
+            obs = o4
+        obs = np.ascontiguousarray(obs)
+        count = np.ascontiguousarray(count, dtype=np.int32)
+        out = {"err": np.empty(F, np.float64), "comb": np.empty((F, Cn), np.int8), "Q": np.empty((F, 3), np.float64)}
+        st = np.zeros((F, 2), np.uint32) if want_stats else None
+        Pm = _as_P(P, Cn)
+        _lib.check(self.h, self.lib.p2s_associate_host(
+            self.h, obs.ctypes.data, count.ctypes.data, Pm.ctypes.data, F, Cn, NP, float(reproj_thr), float(lik_thr),
+            int(min_cams), _ptr(out["err"]), _ptr(out["comb"]), _ptr(out["Q"]), _ptr(st)))
+        if want_stats:
+            out["stats"] = st
+        return out

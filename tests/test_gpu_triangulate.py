@@ -1,0 +1,169 @@
+"""CUDA triangulation path (through the C ABI) against (a) the reference's own outputs stored as
+golden vectors and (b) the NumPy oracle on seeded synthetic streams.
+
+Tolerances (BASELINE.json north_star): |dQ| <= 1e-6 m; exclusion counts / masks bit-exact except
+units whose error lies within eps = 1e-6 px of the threshold or of an arg-min tie (counted)."""
+import warnings
+
+import numpy as np
+import pytest
+
+import p2s_oracle as orc
+from conftest import tri_cases
+from pose2sim_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+Q_TOL = 1e-6     # metres (north_star)
+E_TOL = 1e-6     # pixels
+EPS_BAND = 1e-6  # pixels
+
+
+def run_gpu(engine, P, x, y, w, thr, mc):
+    out = engine.triangulate_host(np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32),
+                                  np.ascontiguousarray(w, np.float32), P, None, thr, mc)
+    return out
+
+
+def compare(out, Q, err, nexcl, mask, thr, allow_band=True):
+    """Returns the number of units that differ in a decision but sit inside the eps band."""
+    dn = out["nexcl"].astype(np.int64) != np.asarray(nexcl, np.int64)
+    dm = out["mask"].astype(np.uint32) != np.asarray(mask, np.uint32)
+    dnan = np.isnan(out["err"]) != np.isnan(err)
+    bad = dn | dm | dnan
+    n_band = 0
+    if bad.any():
+        assert allow_band, f"{bad.sum()} decision mismatches"
+        # a decision may only differ when the oracle's error is within eps of the threshold
+        near = np.abs(np.nan_to_num(err, nan=thr) - thr) < EPS_BAND
+        assert not (bad & ~near).any(), f"{(bad & ~near).sum()} decision mismatches outside the eps band"
+        n_band = int(bad.sum())
+    ok = ~bad
+    assert np.allclose(out["Q"][ok], Q[ok], atol=Q_TOL, rtol=0, equal_nan=True)
+    assert np.allclose(out["err"][ok], err[ok], atol=E_TOL, rtol=0, equal_nan=True)
+    return n_band
+
+
+def test_edge_case_table(engine, golden):
+    g = golden("tri_edge_cases.npz")
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "e{}_", len(g["names"])):
+        out = run_gpu(engine, P, x, y, w, thr, mc)
+        assert compare(out, Q, err, nexcl, mask, thr, allow_band=False) == 0, name
+
+
+def test_reference_random_units(engine, golden):
+    g = golden("tri_random_units.npz")
+    worst = 0.0
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        out = run_gpu(engine, P, x, y, w, thr, mc)
+        assert compare(out, Q, err, nexcl, mask, thr, allow_band=False) == 0, name
+        worst = max(worst, float(np.nanmax(np.abs(out["Q"] - Q), initial=0.0)))
+    assert worst < 1e-9          # in practice ~1e-13 m: far inside the 1e-6 m bar
+
+
+def test_reference_cfg1_demo_cameras(engine, golden):
+    g = golden("tri_cfg1_demo.npz")
+    thr, mc = g["params"]
+    out = run_gpu(engine, g["P"], g["x"], g["y"], g["w"], float(thr), int(mc))
+    assert compare(out, g["Q"], g["err"], g["nexcl"], g["mask"], float(thr), allow_band=False) == 0
+    st = out["stats"]
+    assert sum(st["level_hist"]) + st["not_evaluated"] == 2600
+
+
+@pytest.mark.parametrize("C,mc,thr,seed", [(8, 2, 15.0, 202), (16, 3, 15.0, 303), (4, 2, 15.0, 101),
+                                          (5, 3, 10.0, 7), (12, 8, 15.0, 11), (32, 28, 15.0, 532)])
+def test_oracle_synthetic(engine, C, mc, thr, seed):
+    F = 12 if C <= 8 else (6 if C <= 16 else 3)
+    wl = synth.make_triangulation_workload(C, F, 1, 26, seed=seed)
+    out = run_gpu(engine, wl["P"], wl["x"], wl["y"], wl["lik"], thr, mc)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(wl["x"].astype(float), wl["y"].astype(float),
+                                                    wl["lik"].astype(float), wl["P"], thr, mc)
+    compare(out, Q, err, nexcl, mask, thr)
+
+
+def test_likelihood_gate_matches_reference_rule(engine):
+    """triangulation.py:817-821: lik < thr -> NaN triple (compared in float64 like the reference)."""
+    import torch
+    lik = np.array([[0.3, 0.29999998, 0.30000001, np.nan, 0.0, 1.0, 0.1, 0.5]], np.float32)
+    x = np.arange(8, dtype=np.float32)[None] + 1
+    y = x + 100
+    xs, ys, ls = (torch.from_numpy(a).cuda() for a in (x, y, lik))
+    obs = engine.stage_observations(xs, ys, ls, 0.3).cpu().numpy()      # [C, U, 4]
+    exp_nan = (lik.astype(np.float64) < 0.3)[0] | np.isnan(lik[0])
+    assert np.array_equal(np.isnan(obs[:, 0, 2]), exp_nan)
+    assert np.array_equal(np.isnan(obs[:, 0, 0]), (lik.astype(np.float64) < 0.3)[0])
+    keep = ~np.isnan(obs[:, 0, 0])
+    assert np.array_equal(obs[keep, 0, 0], x[0][keep]) and np.array_equal(obs[keep, 0, 1], y[0][keep])
+
+
+def test_ragged_and_empty(engine):
+    P = synth.ring_cameras(8)[0]
+    out = run_gpu(engine, P, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), 15.0, 2)
+    assert out["Q"].shape == (0, 3)
+    for U in (1, 31, 33, 257):                       # tiles that do not fill a warp
+        wl = synth.make_triangulation_workload(8, 10, 1, 26, seed=U)
+        x, y, w = wl["x"][:U], wl["y"][:U], wl["lik"][:U]
+        out = run_gpu(engine, P, x, y, w, 15.0, 2)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, err, nexcl, mask = orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), P, 15.0, 2)
+        compare(out, Q, err, nexcl, mask, 15.0)
+
+
+def test_argument_errors(engine):
+    from pose2sim_b200 import _lib
+    P = synth.ring_cameras(8)[0]
+    z = np.zeros((4, 8), np.float32)
+    with pytest.raises(_lib.P2SError):
+        engine.triangulate_host(z, z, z, P, None, 15.0, 0)            # min_cams < 1
+    z1 = np.zeros((4, 1), np.float32)
+    with pytest.raises(_lib.P2SError):
+        engine.triangulate_host(z1, z1, z1, P[:1], None, 15.0, 1)     # n_cams < 2
+
+
+def test_full_size_properties_cfg2(engine):
+    """BASELINE config 2 at full size (8 cams x 26 kpts x 100k frames): size-independent properties.
+    - determinism (two runs bit-identical), - invariance to a permutation of the units,
+    - every finite unit has err <= thr and a finite Q; failed units are NaN in both,
+    - histogram of levels sums to U,  - triangulated points lie near the generating truth."""
+    C, F, thr, mc = 8, 100_000, 15.0, 2
+    wl = synth.make_triangulation_workload(C, F, 1, 26, seed=202)
+    out = run_gpu(engine, wl["P"], wl["x"], wl["y"], wl["lik"], thr, mc)
+    U = F * 26
+    st = out["stats"]
+    assert sum(st["level_hist"]) + st["not_evaluated"] == U
+    ok = np.isfinite(out["err"])
+    assert ok.mean() > 0.99
+    assert (out["err"][ok] <= thr).all() and np.isfinite(out["Q"][ok]).all()
+    assert np.isnan(out["Q"][~ok]).all()
+    assert np.median(np.linalg.norm(out["Q"][ok] - wl["truth"][ok], axis=1)) < 0.02
+    out2 = run_gpu(engine, wl["P"], wl["x"], wl["y"], wl["lik"], thr, mc)
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert np.array_equal(out[k], out2[k], equal_nan=True)
+    perm = np.random.default_rng(0).permutation(U)
+    outp = run_gpu(engine, wl["P"], wl["x"][perm], wl["y"][perm], wl["lik"][perm], thr, mc)
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert np.array_equal(out[k][perm], outp[k], equal_nan=True)
+    # oracle on a deterministic subsample of the full-size run
+    sub = np.arange(0, U, U // 1500)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(wl["x"][sub].astype(float), wl["y"][sub].astype(float),
+                                                    wl["lik"][sub].astype(float), wl["P"], thr, mc)
+    compare({k: out[k][sub] for k in ("Q", "err", "nexcl", "mask")}, Q, err, nexcl, mask, thr)
+
+
+def test_jacobi_solver_agrees(engine):
+    """A/B: the north-star's nominal Jacobi eigen-solver gives the same decisions and Q."""
+    wl = synth.make_triangulation_workload(8, 40, 1, 26, seed=9)
+    a = run_gpu(engine, wl["P"], wl["x"], wl["y"], wl["lik"], 15.0, 2)
+    engine.set_solver("jacobi")
+    try:
+        b = run_gpu(engine, wl["P"], wl["x"], wl["y"], wl["lik"], 15.0, 2)
+    finally:
+        engine.set_solver("secular")
+    assert np.array_equal(a["nexcl"], b["nexcl"]) and np.array_equal(a["mask"], b["mask"])
+    assert np.allclose(a["Q"], b["Q"], atol=1e-9, rtol=0, equal_nan=True)
+    assert np.allclose(a["err"], b["err"], atol=1e-8, rtol=0, equal_nan=True)

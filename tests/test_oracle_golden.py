@@ -1,0 +1,93 @@
+"""The NumPy oracle restatement (oracle/p2s_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, made by oracle/make_golden.py in the build container).  CPU only."""
+import warnings
+
+import numpy as np
+import pytest
+
+import p2s_oracle as orc
+from conftest import tri_cases
+
+Q_TOL = 1e-9      # metres; SVD backends differ by ~1e-14
+E_TOL = 1e-8      # pixels
+
+
+def _check_units(P, x, y, w, thr, mc, Q, err, nexcl, mask):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q, e, n, m = orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), P, thr, mc)
+    assert np.array_equal(n, nexcl)
+    assert np.array_equal(m, mask)
+    assert np.array_equal(np.isnan(e), np.isnan(err))
+    assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+    assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+
+
+def test_edge_case_table(golden):
+    g = golden("tri_edge_cases.npz")
+    n = len(g["names"])
+    assert n >= 16
+    for case in tri_cases(g, "e{}_", n):
+        _check_units(*case[1:])
+
+
+def test_edge_case_known_answers(golden):
+    """nb_cams_excluded / id_excluded_cams pinned by name."""
+    g = golden("tri_edge_cases.npz")
+    names = list(g["names"])
+    expect = {"clean": (0, 0b0), "cam3_nan": (1, 0b1000), "cam3_nan_cam0_outlier": (2, 0b1001),
+              "two_valid": (2, 0b1100), "two_valid_outlier": (2, 0b1100), "one_valid": (4, 0b1111),
+              "all_nan": (4, 0b1111), "cam1_zero": (1, 0b0), "cam1_zero_cam0_outlier": (2, 0b1),
+              "two_outliers": (2, 0b11), "min3_one_outlier": (1, 0b100), "min4_one_outlier": (0, 0),
+              "min1_three_nan": (3, 0b1110), "c8_two_nan_one_outlier": (3, 0b11000100)}
+    for name, (nx, mk) in expect.items():
+        i = names.index(name)
+        assert int(g[f"e{i}_nexcl"][0]) == nx, name
+        assert int(g[f"e{i}_mask"][0]) == mk, name
+    for name in ("two_valid_outlier", "one_valid", "all_nan", "three_outliers_same_dir", "min3_two_outliers",
+                 "min4_one_outlier", "min1_three_nan"):
+        i = names.index(name)
+        assert np.isnan(g[f"e{i}_err"][0]) and np.isnan(g[f"e{i}_Q"]).all(), name
+
+
+def test_random_units(golden):
+    g = golden("tri_random_units.npz")
+    for case in tri_cases(g, "r{}_", int(g["n"])):
+        _check_units(*case[1:])
+
+
+def test_cfg1_demo_cameras(golden):
+    g = golden("tri_cfg1_demo.npz")
+    thr, mc = g["params"]
+    sel = slice(0, 2600, 4)          # a quarter of the 2600 units keeps the CPU suite short
+    _check_units(g["P"], g["x"][sel], g["y"][sel], g["w"][sel], float(thr), int(mc),
+                 g["Q"][sel], g["err"][sel], g["nexcl"][sel], g["mask"][sel])
+
+
+def test_association_frames(golden):
+    g = golden("assoc_random_frames.npz")
+    for i in range(int(g["assoc_n"])):
+        p = f"assoc{i}_"
+        thr, lt, mc = g[p + "params"]
+        obs = g[p + "obs"].astype(float)
+        cnt = g[p + "count"]
+        for f in range(0, obs.shape[0], 2):
+            ob = [[obs[f, c, pp] for pp in range(cnt[f, c])] for c in range(obs.shape[1])]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                e, comb, Q = orc.associate_frame(ob, list(cnt[f]), g[p + "P"], float(thr), float(lt), int(mc))
+            assert np.array_equal(np.nan_to_num(comb, nan=-1), np.nan_to_num(g[p + "comb"][f], nan=-1)), (i, f)
+            assert np.isclose(e, g[p + "err"][f], atol=E_TOL, rtol=0, equal_nan=True) or (np.isinf(e) and np.isinf(g[p + "err"][f]))
+            assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
+
+
+def test_subset_order_is_itertools():
+    """The kernel's candidate tables must follow itertools.combinations order (triangulation.py:411)."""
+    import itertools
+    from pose2sim_b200 import combos
+    for n in (2, 3, 4, 5, 8, 11):
+        for k in range(0, n + 1):
+            ref = [sum(1 << c for c in cc) for cc in itertools.combinations(range(n), k)]
+            assert combos.subset_masks(n, k).tolist() == ref
+            for r in (0, len(ref) // 2, len(ref) - 1):
+                assert combos.unrank_subset(n, k, r) == ref[r]
