@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the triangulation hot path (BASELINE.json metric) — one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input resident in HBM:
+stage (likelihood gate + float4 SoA) -> triangulate with camera-exclusion search; at N > 1 every rank
+owns its own frame block (weak scaling, no data-path collective) and the packed per-unit outputs are
+gathered to rank 0 over NCCL inside the timed region (north_star's "final gather").
+
+Keys beyond the base contract: `roofline` (FP64 CUDA-core bound, plus the HBM view), `cpu_baseline`
+(the oracle port on this box's host cores), `e2e` (host buffers through the C ABI, copies timed).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "keypoint triangulations/sec w/ exclusion search"
+UNIT = "triangulations/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(C=8, F=100_000, N=1, K=26, seed=202, thr=15.0, min_cams=2, lik_thr=0.3,
+                 name="cfg2: synthetic 8 cams x HALPE_26 x 100k frames, likelihood-weighted DLT + reproj exclusion"),
+    # BASELINE.json configs[2] at 1/8 of its frames per GPU (1M frames over 8 GPUs)
+    "cfg3": dict(C=16, F=125_000, N=1, K=26, seed=303, thr=15.0, min_cams=3, lik_thr=0.3,
+                 name="cfg3 shard: synthetic 16 cams x Body_with_feet x 125k frames (1M/8), min_cameras=3"),
+}
+
+# FP64 operations the kernels execute per unit of work (DESIGN.md "Algorithmic work"); FMA = 2 flops.
+FLOPS_PER_CAM = 64 + 47          # normal-matrix rows + rank-1 updates, reprojection distance
+FLOPS_PER_SOLVER_STEP = 68       # one secular-Newton factorisation/solve
+FLOPS_PER_CANDIDATE = 1          # the mean
+
+
+def algorithmic_flops(st):
+    return FLOPS_PER_CAM * st["cam_solves"] + FLOPS_PER_SOLVER_STEP * st["solver_steps"] + FLOPS_PER_CANDIDATE * st["candidates"]
+
+
+def algorithmic_bytes(U, C):
+    return (16 * C + 37) * U     # float4 obs in, Q + err + mask + count out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while `active` (the timed region)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.active, self.stop_flag = index, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                         nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                         nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonGpuIdle", 0x1): "gpu_idle",
+                 getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                 getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSyncBoost", 0x10): "sync_boost",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown"}
+        bits = 0
+        for _, r, _ in self.samples:
+            bits |= r
+        reasons = sorted(n for b, n in names.items() if bits & b and n != "gpu_idle")
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(s[2] for s in self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------
+def _port_worker(args):
+    import warnings
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import p2s_oracle as orc
+    x, y, w, P, thr, mc = args
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), P, thr, mc)
+    return len(x)
+
+
+class PythonPort:
+    """The NumPy restatement of the reference's per-unit path on all host cores (multiprocessing)."""
+
+    def __init__(self, wl, cfg):
+        import multiprocessing as mp
+        self.cores = len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.wl, self.cfg = wl, cfg
+
+    def run(self, n_units):
+        """Time the first n_units units of the workload; returns seconds."""
+        wl, cfg = self.wl, self.cfg
+        n_units = min(n_units, wl["x"].shape[0])
+        per = max(1, -(-n_units // (self.cores * 4)))
+        jobs = [(wl["x"][i:min(i + per, n_units)], wl["y"][i:min(i + per, n_units)], wl["lik"][i:min(i + per, n_units)],
+                 wl["P"], cfg["thr"], cfg["min_cams"]) for i in range(0, n_units, per)]
+        t0 = time.perf_counter()
+        done = sum(self.pool.map(_port_worker, jobs, chunksize=1))
+        dt = time.perf_counter() - t0
+        assert done == n_units
+        return dt, n_units
+
+    def close(self):
+        self.pool.terminate()
+
+
+def c_port_rate(wl, cfg, n_units):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+    n_units = min(n_units, wl["x"].shape[0])
+    co.triangulate_units(wl["x"][:2000], wl["y"][:2000], wl["lik"][:2000], wl["P"], cfg["thr"], cfg["min_cams"])
+    t0 = time.perf_counter()
+    co.triangulate_units(wl["x"][:n_units], wl["y"][:n_units], wl["lik"][:n_units], wl["P"], cfg["thr"], cfg["min_cams"])
+    dt = time.perf_counter() - t0
+    return n_units / dt, co.max_threads(), n_units
+
+
+def run_reference_arm(args, cfg, rank, world):
+    """`--impl reference`: the reference is pure Python and cannot travel to the GPU box, so this arm
+    times the oracle port (oracle/p2s_oracle.py: same per-unit / per-candidate NumPy structure as the
+    reference) on all host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from pose2sim_b200 import synth
+    sample_frames = 4000
+    wl = synth.make_triangulation_workload(cfg["C"], sample_frames, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=cfg["lik_thr"])
+    port = PythonPort(wl, cfg)
+    dt, n = port.run(port.cores * 64)                          # calibration (also warms the pool)
+    rate = n / dt
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    per_step = int(max(port.cores * 16, min(wl["x"].shape[0], rate * budget)))
+    for _ in range(args.warmup):
+        port.run(per_step)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, n = port.run(per_step)
+        t += dt
+    port.close()
+    value = per_step * args.steps / t
+    c_rate, c_threads, c_n = c_port_rate(wl, cfg, 100_000)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "n_cams": cfg["C"], "keypoints": cfg["K"],
+                       "reproj_error_threshold_triangulation": cfg["thr"], "min_cameras_for_triangulation": cfg["min_cams"],
+                       "likelihood_threshold_triangulation": cfg["lik_thr"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.cores, "kind": "port",
+                             "sample": f"first {per_step} units of the workload per step, NumPy per-unit port of "
+                                       f"triangulation_from_best_cameras, multiprocessing over all host cores",
+                             "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
+                                        "what": "plain-C restatement (one-sided Jacobi SVD), OpenMP"}},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pose2sim_b200 import ops, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = ops.get_engine(local)
+
+    # ---- workload: every rank owns its own block of frames (weak scaling) ---------------------------
+    C, F, thr, mc = cfg["C"], cfg["F"], cfg["thr"], cfg["min_cams"]
+    # raw likelihoods: the gate (triangulation.py:817-821) is applied on the device by the stage kernel
+    wl = synth.make_triangulation_workload(C, F, cfg["N"], cfg["K"], seed=cfg["seed"] + 1000 * rank,
+                                           lik_thr=None, frame0=rank * F)
+    U = wl["x"].shape[0]
+    hx, hy, hl = (torch.from_numpy(wl[k]).pin_memory() for k in ("x", "y", "lik"))
+    x, y, lik = (t.to(dev, non_blocking=True) for t in (hx, hy, hl))
+    obs = torch.empty((C, U, 4), dtype=torch.float32, device=dev)
+    # per-unit outputs packed contiguously (Q | err | mask | nexcl = 37 B/unit) so that the final
+    # gather is ONE NCCL call; two buffers alternate so the gather of step i overlaps step i+1
+    packs = [torch.empty(37 * U, dtype=torch.uint8, device=dev) for _ in range(2)]
+    outs = [{"Q": p[:24 * U].view(torch.float64).view(U, 3), "err": p[24 * U:32 * U].view(torch.float64),
+             "mask": p[32 * U:36 * U].view(torch.int32), "nexcl": p[36 * U:]} for p in packs]
+    out = outs[0]
+    gather_lists = [[torch.empty_like(packs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    stats = eng.new_stats()
+    pending = [None, None]
+    step_no = [0]
+
+    def step(record=None):
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()              # stream-side wait: the buffer's previous gather must be done
+        eng.stage_observations(x, y, lik, cfg["lik_thr"], out=obs)
+        if record is not None:
+            record[0].record()
+        eng.triangulate(obs, wl["P"], thr, mc, out=outs[b])
+        if record is not None:
+            record[1].record()
+        if world > 1:
+            pending[b] = dist.gather(packs[b], gather_lists[b], dst=0, async_op=True)
+        return pending[b]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one counted pass for the level histogram / algorithmic work of this workload
+    eng.stage_observations(x, y, lik, cfg["lik_thr"], out=obs)
+    eng.triangulate(obs, wl["P"], thr, mc, out=out, stats=stats)
+    torch.cuda.synchronize()
+    st = ops.stats_dict(stats.cpu().numpy())
+    fp64_peak = eng.fp64_peak()
+
+    for _ in range(args.warmup):
+        w = step()
+        if w is not None:
+            w.wait()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count()
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    e_begin.record()
+    works = []
+    for i in range(args.steps):
+        works.append(step(evs[i]))
+    for w in works:
+        if w is not None:
+            w.wait()
+    e_end.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.active = False
+    launches = eng.launch_count() - launches0
+    dev_ms = e_begin.elapsed_time(e_end)
+    tri_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- e2e: host buffers through the C ABI (H2D + stage + search + D2H inside the timed region) -----
+    ho = {"Q": torch.empty((U, 3), dtype=torch.float64).pin_memory().numpy(),
+          "err": torch.empty(U, dtype=torch.float64).pin_memory().numpy(),
+          "nexcl": torch.empty(U, dtype=torch.uint8).pin_memory().numpy(),
+          "mask": torch.empty(U, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        eng.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], cfg["lik_thr"], thr, mc, out=ho, want_stats=False)
+    barrier()
+    sampler.active = True
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], cfg["lik_thr"], thr, mc, out=ho, want_stats=False)
+    barrier()
+    e2e_s = (time.perf_counter() - t1) / e2e_steps
+    sampler.active = False
+    sampler.stop_flag = True
+
+    # ---- max over ranks --------------------------------------------------------------------------------
+    tm = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, tri_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_ms, tri_ms_max = (float(v) for v in tm.cpu())
+    step_ms = max(dev_ms, 0.0) / args.steps
+    total_units = U * world
+    value = total_units / (step_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        flops = algorithmic_flops(st)
+        tf = flops / (tri_ms * 1e-3) / 1e12
+        gbs = algorithmic_bytes(U, C) / (tri_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "n_cams": C, "keypoints": cfg["K"], "frames_per_gpu": F,
+                       "units_per_gpu": U, "reproj_error_threshold_triangulation": thr,
+                       "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
+                       "seed": cfg["seed"], "l2": f"inputs {((12 + 16) * C * U) >> 20} MiB per step > 126 MB L2, no flush",
+                       "step": "stage kernel + triangulation kernel" + (" + NCCL gather to rank 0" if world > 1 else ""),
+                       "level_hist": st["level_hist"], "candidates_per_unit": st["candidates"] / U,
+                       "failed_units": st["failed"], "eps_band_px": 1e-6,
+                       "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
+            "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                         "traffic": None, "kernel": "triangulate_kernel<8,secular>" if C <= 8 else "triangulate_kernel",
+                         "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
+                         "peak_source": "dependent-chain DFMA microbenchmark in this run (p2s_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": algorithmic_bytes(U, C)}},
+            "e2e": {"value": total_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * C * U,
+                    "d2h_bytes_per_step": 37 * U, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "p2s_triangulate_host (pinned host buffers, chunked H2D/compute/D2H on 3 streams)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "wall_ms_per_step": wall_ms / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # bounded CPU sample: the oracle port on this box's host cores
+            sample_frames = 2000
+            cwl = synth.make_triangulation_workload(C, sample_frames, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=cfg["lik_thr"])
+            port = PythonPort(cwl, cfg)
+            port.run(port.cores * 32)                                  # warms the pool
+            cdt, cn = port.run(port.cores * 64)                        # calibrates the rate
+            n_units = int(min(cwl["x"].shape[0], max(port.cores * 64, 12.0 * cn / cdt)))    # ~12 s of CPU work
+            dt, n = port.run(n_units)
+            port.close()
+            c_rate, c_threads, c_n = c_port_rate(cwl, cfg, 52_000)
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
+                                    "sample": f"first {n} units (of {U}) of the same workload, NumPy per-unit port of "
+                                              f"triangulation_from_best_cameras (oracle/p2s_oracle.py), one process per core",
+                                    "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
+                                               "what": "plain-C restatement (oracle/p2s_oracle.c), OpenMP"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

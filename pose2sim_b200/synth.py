@@ -90,7 +90,7 @@ def observe(Q, P, seed, sigma=2.0, p_out=0.05, p_low=0.05):
 def gate_likelihood(x, y, lik, lik_thr):
     """Pose2Sim/triangulation.py:817-821: likelihood below threshold => x, y, likelihood = NaN."""
     with np.errstate(invalid="ignore"):
-        low = lik < np.float32(lik_thr) if lik.dtype == np.float32 else lik < lik_thr
+        low = lik.astype(np.float64) < float(lik_thr)          # the reference compares in float64
     x = np.where(low, np.nan, x).astype(x.dtype)
     y = np.where(low, np.nan, y).astype(y.dtype)
     lik = np.where(low, np.nan, lik).astype(lik.dtype)
@@ -100,12 +100,14 @@ def gate_likelihood(x, y, lik, lik_thr):
 def make_triangulation_workload(C, F, N=1, K=HALPE_26_COUNT, seed=202, lik_thr=0.3, frame0=0, P=None,
                                 sigma=2.0, p_out=0.05, p_low=0.05):
     """Units in (frame, person, keypoint) order: returns dict with P[C,3,4] and x,y,lik [U, C] float32,
-    likelihood gate (lik < lik_thr -> NaN) already applied like triangulate_all does before the search."""
+    likelihood gate (lik < lik_thr -> NaN) already applied like triangulate_all does before the search
+    (lik_thr=None: raw likelihoods, gate left to the device)."""
     if P is None:
         P = ring_cameras(C)[0]
     Q = truth_points(F, N, K, seed, frame0)
     x, y, lik = observe(Q, P, seed, sigma, p_out, p_low)
-    x, y, lik = gate_likelihood(x, y, lik, lik_thr)
+    if lik_thr is not None:                                   # None: leave the gate to the device stage kernel
+        x, y, lik = gate_likelihood(x, y, lik, lik_thr)
     U = F * N * K
     return {"P": P, "x": x.reshape(U, C), "y": y.reshape(U, C), "lik": lik.reshape(U, C),
             "truth": Q.reshape(U, 3), "F": F, "N": N, "K": K, "C": C}

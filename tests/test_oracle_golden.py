@@ -91,3 +91,49 @@ def test_subset_order_is_itertools():
             assert combos.subset_masks(n, k).tolist() == ref
             for r in (0, len(ref) // 2, len(ref) - 1):
                 assert combos.unrank_subset(n, k, r) == ref[r]
+
+
+# ---- the plain-C oracle (oracle/p2s_oracle.c) against the same reference outputs -------------------
+def test_c_oracle_triangulation(golden):
+    import c_oracle as co
+    for fn, fmt in (("tri_edge_cases.npz", "e{}_"), ("tri_random_units.npz", "r{}_")):
+        g = golden(fn)
+        n = len(g["names"]) if "names" in g else int(g["n"])
+        for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, fmt, n):
+            q, e, nx, m, lv, nc = co.triangulate_units(x, y, w, P, thr, mc)
+            assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask), name
+            assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+            assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+    g = golden("tri_cfg1_demo.npz")
+    q, e, nx, m, lv, nc = co.triangulate_units(g["x"], g["y"], g["w"], g["P"], 15.0, 2)
+    assert np.array_equal(nx, g["nexcl"].astype(np.uint8)) and np.array_equal(m, g["mask"])
+    assert np.allclose(q, g["Q"], atol=Q_TOL, rtol=0, equal_nan=True)
+    assert np.allclose(e, g["err"], atol=E_TOL, rtol=0, equal_nan=True)
+
+
+def test_c_oracle_association(golden):
+    import c_oracle as co
+    g = golden("assoc_random_frames.npz")
+    for i in range(int(g["assoc_n"])):
+        p = f"assoc{i}_"
+        thr, lt, mc = g[p + "params"]
+        e, comb, Q = co.associate_frames(g[p + "obs"], g[p + "count"], g[p + "P"], float(thr), float(lt), int(mc))
+        assert np.array_equal(comb.astype(int), np.nan_to_num(g[p + "comb"], nan=-1).astype(int))
+        fin = np.isfinite(g[p + "err"])
+        assert np.array_equal(np.isinf(e), ~fin)
+        assert np.allclose(e[fin], g[p + "err"][fin], atol=E_TOL, rtol=0)
+        assert np.allclose(Q, g[p + "Q"], atol=Q_TOL, rtol=0, equal_nan=True)
+
+
+def test_c_and_numpy_oracles_agree_on_synthetic():
+    import c_oracle as co
+    from pose2sim_b200 import synth
+    for C, mc in ((8, 2), (16, 12)):
+        wl = synth.make_triangulation_workload(C, 6, 1, 26, seed=300 + C)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, err, nexcl, mask = orc.triangulate_units(wl["x"].astype(float), wl["y"].astype(float),
+                                                        wl["lik"].astype(float), wl["P"], 15.0, mc)
+        q, e, nx, m, lv, nc = co.triangulate_units(wl["x"], wl["y"], wl["lik"], wl["P"], 15.0, mc)
+        assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask)
+        assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
