@@ -1,0 +1,181 @@
+"""TEST INFRASTRUCTURE — end-to-end golden fixtures made by running the UNMODIFIED reference's stage
+entry points on synthetic trials (build container only; needs /root/reference):
+
+    python oracle/make_golden_e2e.py
+
+  * Pose2Sim/triangulation.py:656      triangulate_all(config)   single person, shipped demo cameras (cfg1)
+  * Pose2Sim/triangulation.py:656      triangulate_all(config)   multi person (re-ID across frames)
+  * Pose2Sim/personAssociation.py:642  associate_all(config)     single-person mode
+
+For each trial the INPUT keypoint arrays (float32, enough to rebuild the JSON directories with
+pose2sim_b200.synth_project) and the reference's OUTPUT (TRC text / chosen people) are stored in
+tests/golden/e2e_*.npz.  tests/test_dropin_*.py rebuild the trial in a temp dir, run the drop-in and
+compare.
+"""
+import contextlib
+import glob
+import io
+import json
+import logging
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shim  # noqa: E402
+from pose2sim_b200 import skeletons, synth, synth_project  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+J = 26                                                  # HALPE_26 keypoints per person in the JSON
+
+
+@contextlib.contextmanager
+def in_dir(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)
+
+
+def run_reference(fn, cfg, project_dir):
+    """cwd = the trial directory (single-trial layout, triangulation.py:680-682)."""
+    buf = io.StringIO()
+    handler = logging.StreamHandler(buf)
+    logging.getLogger().addHandler(handler)
+    logging.getLogger().setLevel(logging.INFO)
+    try:
+        with in_dir(project_dir), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            fn(cfg)
+    finally:
+        logging.getLogger().removeHandler(handler)
+    return buf.getvalue()
+
+
+def single_person_trial():
+    """cfg1-shaped: the 4 shipped Qualisys cameras, 100 frames, HALPE_26; the person is absent in the
+    first frames (trimmed), some keypoints vanish for short (interpolated) and long (filled) spans."""
+    ids, names = skeletons.keypoints("HALPE_26")
+    calib_text = open(os.path.join(GOLDEN, "Calib_demo.toml")).read()
+    g = np.load(os.path.join(GOLDEN, "tri_cfg1_demo.npz"))
+    P = g["P"]
+    F, C, K = 100, 4, 26
+    wl = synth.make_triangulation_workload(C, F, 1, K, seed=111, P=P, lik_thr=None, p_out=0.08, p_low=0.10)
+    x, y, lik = (wl[k].reshape(F, 1, K, C).transpose(0, 3, 1, 2).copy() for k in ("x", "y", "lik"))   # [F, C, 1, K]
+    lik[:4] = 0.05                                       # nobody visible in frames 0..3
+    lik[30:36, :, :, 5] = 0.1                            # short gap on one keypoint  -> interpolated
+    lik[50:80, :, :, 9] = 0.1                            # long gap on another        -> not interpolated
+    lik[60:63] = 0.0                                     # whole person lost for 3 frames
+    kp = synth_project.pack_openpose(x, y, lik, ids, J)  # [F, C, 1, 78]
+    return calib_text, [f"cam{c + 1:02d}" for c in range(C)], kp, None
+
+
+def multi_person_trial():
+    """3 persons, 4 ring cameras, 70 frames; the people list is permuted identically in all cameras
+    from some frames on (what `pose-associated` looks like), one person leaves for a while."""
+    ids, names = skeletons.keypoints("HALPE_26")
+    C, F, Np, K = 4, 70, 3, 26
+    calib_text, cams, P = synth_project.ring_calibration_toml(C)
+    Q = synth.truth_points(F, Np, K, 222)
+    x, y, lik = synth.observe(Q, P, 222, sigma=1.5, p_out=0.04, p_low=0.05)      # [F, Np, K, C]
+    x, y, lik = (a.transpose(0, 3, 1, 2).copy() for a in (x, y, lik))            # [F, C, Np, K]
+    order = np.tile(np.arange(Np), (F, 1))
+    order[20:45] = [1, 2, 0]
+    order[45:] = [2, 0, 1]
+    fidx = np.arange(F)[:, None]
+    x, y, lik = (a[fidx, :, order].transpose(0, 2, 1, 3) for a in (x, y, lik))   # people permuted per frame
+    present = np.ones((F, C, Np), bool)
+    lik[30:41, :, 2] = 0.01                               # the person at slot 2 is not seen for 11 frames
+    kp = synth_project.pack_openpose(x, y, lik, ids, J)
+    return calib_text, cams, kp, present
+
+
+def association_trial():
+    """Single-person association: 4 ring cameras, 2-3 detections per camera in random order,
+    outliers, low likelihoods, missing detections."""
+    ids, names = skeletons.keypoints("HALPE_26")
+    C, F, Np, K = 4, 60, 3, 26
+    calib_text, cams, P = synth_project.ring_calibration_toml(C)
+    Q = synth.truth_points(F, Np, K, 333)
+    x, y, lik = synth.observe(Q, P, 333, sigma=1.5, p_out=0.10, p_low=0.10)
+    x, y, lik = (a.transpose(0, 3, 1, 2).copy() for a in (x, y, lik))            # [F, C, Np, K]
+    g = np.random.default_rng(333)
+    perm = np.stack([np.stack([g.permutation(Np) for _ in range(C)]) for _ in range(F)])   # [F, C, Np]
+    fidx, cidx = np.arange(F)[:, None, None], np.arange(C)[None, :, None]
+    x, y, lik = (a[fidx, cidx, perm] for a in (x, y, lik))
+    present = np.ones((F, C, Np), bool)
+    present[:, :, 2] = g.random((F, C)) < 0.7             # the third detection is often missing
+    present[g.random((F, C)) < 0.08] = False              # sometimes a camera sees nobody
+    kp = synth_project.pack_openpose(x, y, lik, ids, J)
+    return calib_text, cams, kp, present
+
+
+def read_people_arrays(root, cams, frames, n_slots):
+    """[F, C, n_slots, 3J] keypoints of the files under root (NaN where a slot is `{}` or missing) and
+    exists[F, C]."""
+    F, C = len(frames), len(cams)
+    out = np.full((F, C, n_slots, 3 * J), np.nan)
+    exists = np.zeros((F, C), bool)
+    for c, cam in enumerate(cams):
+        for fi, f in enumerate(frames):
+            path = os.path.join(root, f"{cam}_json", f"{cam}_{f:06d}.json")
+            if not os.path.exists(path):
+                continue
+            exists[fi, c] = True
+            people = json.load(open(path))["people"]
+            assert len(people) <= n_slots
+            for p, person in enumerate(people):
+                if person:
+                    out[fi, c, p] = person["pose_keypoints_2d"]
+    return out, exists
+
+
+def main():
+    ref = ref_shim.load_reference()
+    os.makedirs(GOLDEN, exist_ok=True)
+
+    # 1. single person --------------------------------------------------------------------------------
+    for tag, trial, multi, extra in (("e2e_tri_single", single_person_trial, False, {}),
+                                     ("e2e_tri_multi", multi_person_trial, True, {"interpolation": "cubic", "fill_large_gaps_with": "nan"})):
+        calib_text, cams, kp, present = trial()
+        with tempfile.TemporaryDirectory() as td:
+            proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+            cfg = synth_project.base_config(proj, multi_person=multi, **extra)
+            log = run_reference(ref.triangulation.triangulate_all, cfg, proj)
+            trcs = sorted(glob.glob(os.path.join(proj, "pose-3d", "*.trc")))
+            assert trcs, "reference wrote no TRC"
+            out = {"calib": np.array(calib_text), "cams": np.array(cams), "kp": kp.astype(np.float32),
+                   "present": np.ones(kp.shape[:3], bool) if present is None else present,
+                   "multi_person": np.array(multi), "extra": np.array(json.dumps(extra)),
+                   "trc_names": np.array([os.path.basename(t) for t in trcs]), "log": np.array(log)}
+            for i, t in enumerate(trcs):
+                out[f"trc{i}"] = np.array(open(t).read())
+            np.savez_compressed(os.path.join(GOLDEN, tag + ".npz"), **out)
+            print(tag, [os.path.basename(t) for t in trcs])
+            print("   " + "\n   ".join(l for l in log.splitlines() if l.startswith("-->") or "Camera" in l)[:600])
+
+    # 2. association -----------------------------------------------------------------------------------
+    calib_text, cams, kp, present = association_trial()
+    with tempfile.TemporaryDirectory() as td:
+        proj = synth_project.write_project(os.path.join(td, "trial_assoc"), calib_text, cams, kp, present=present)
+        cfg = synth_project.base_config(proj)
+        log = run_reference(ref.personAssociation.associate_all, cfg, proj)
+        chosen, exists = read_people_arrays(os.path.join(proj, "pose-associated"), cams, range(kp.shape[0]), 1)
+        np.savez_compressed(os.path.join(GOLDEN, "e2e_assoc_single.npz"), calib=np.array(calib_text), cams=np.array(cams),
+                            kp=kp.astype(np.float32), present=present, chosen=chosen[:, :, 0].astype(np.float32),
+                            exists=exists, log=np.array(log))
+        print("e2e_assoc_single", "cameras off per frame:", np.isnan(chosen[:, :, 0, 0]).sum(1).mean())
+        print("   " + "\n   ".join(l for l in log.splitlines() if l.startswith("-->")))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+"""Drop-in `associate_all(config_dict)` — same entry point, inputs and `pose-associated/` output as
+Pose2Sim/personAssociation.py:642-809 (single-person mode), with the per-frame search
+(`persons_combinations` :67, `best_persons_and_cameras_combination` :154, `triangulate_comb` :102)
+replaced by ONE batched call into the sm_100a library (`p2s_associate_host`).
+
+    stage_project()    host    :663-772   config, calibration, tracked keypoint, JSON -> obs[F,C,P,4], count[F,C]
+    solve_frames()     DEVICE  :771-774   ordered person-combination x camera-subset search, all frames
+    write_outputs()    host    :776-808   rewrite JSON with the chosen person per camera, recap
+
+Multi-person mode (Plücker-ray affinity + SVT matching, :277-549) is a SURVEY §8(f) "next" row and is
+refused loudly; there is no CPU search in this package.
+"""
+import json
+import logging
+import os
+
+import numpy as np
+
+from . import _lib
+from . import calib as _calib
+from . import skeletons as _skel
+from . import staging as _stg
+
+
+def read_settings(config_dict):
+    """personAssociation.py:663-675, :177-180."""
+    prj, pa, tri = config_dict.get("project"), config_dict.get("personAssociation"), config_dict.get("triangulation")
+    sp = pa.get("single_person")
+    mp = pa.get("multi_person") or {}
+    return {
+        "project_dir": prj.get("project_dir"),
+        "multi_person": prj.get("multi_person"),
+        "frame_range": prj.get("frame_range"),
+        "pose_model": config_dict.get("pose").get("pose_model"),
+        "tracked_keypoint": sp.get("tracked_keypoint"),
+        "reproj_thr": sp.get("reproj_error_threshold_association"),
+        "lik_thr": pa.get("likelihood_threshold_association"),            # sic: read from the parent table (:180)
+        "lik_thr_recap": sp.get("likelihood_threshold_association", 0.3),  # the recap reads the other one (:609)
+        "min_cams": tri.get("min_cameras_for_triangulation"),
+        "undistort_points": tri.get("undistort_points"),
+        "reconstruction_error_threshold": mp.get("reconstruction_error_threshold"),
+        "min_affinity": mp.get("min_affinity"),
+    }
+
+
+class StagedAssociation:
+    __slots__ = ("settings", "calib_file", "P", "cam_dirs", "dirs", "table", "f_range", "n_cams",
+                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact")
+
+
+def stage_project(config_dict):
+    s = read_settings(config_dict)
+    if s["undistort_points"]:
+        raise NotImplementedError("[triangulation] undistort_points = true is not available in the B200 path")
+    session_dir = _calib.session_dir_of(s["project_dir"])
+    calib_file = _calib.find_calibration_file(session_dir)
+    P = _calib.compute_P(calib_file, undistort=False)
+    _skel.model_nodes(s["pose_model"], config_dict)          # NameError when the model is unknown (:689-707)
+
+    dirs = _stg.PoseDirs(s["project_dir"])
+    cam_dirs = dirs.camera_dirs()
+    _, files = dirs.files_for_association(cam_dirs)
+    if not os.path.exists(dirs.tracked_dir):
+        os.mkdir(dirs.tracked_dir)
+    for d in cam_dirs:
+        try:
+            os.mkdir(os.path.join(dirs.tracked_dir, d))
+        except OSError:
+            break                                             # the reference stops at the first failure (:735-736)
+    fr = s["frame_range"]
+    f_range = [0, max(len(j) for j in files)] if fr in ("all", "auto", []) else fr
+    n_cams = len(cam_dirs)
+    if n_cams != len(P):
+        raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
+                        f"file, and {n_cams} cameras based on the number of pose folders.")
+    if s["multi_person"]:
+        logging.info("\nMulti-person analysis selected.")
+        raise NotImplementedError("multi_person association (affinity + SVT, personAssociation.py:277-549) is not "
+                                  "available in the B200 path yet")
+    logging.info("\nSingle-person analysis selected.")
+    kid, fallback = _skel.tracked_keypoint_id(s["pose_model"], s["tracked_keypoint"], config_dict)
+    if fallback is not None:
+        logging.warning(f"{s['tracked_keypoint']} not found in {s['pose_model']}, consider editing tracked_keypoint "
+                        f"in Config.toml. Tracking {fallback} instead.")
+
+    st = StagedAssociation()
+    st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
+    st.cam_dirs, st.dirs, st.f_range, st.n_cams, st.tracked_keypoint_id = cam_dirs, dirs, list(f_range), n_cams, kid
+    st.table = _stg.frame_file_table(files, f_range)
+    # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
+    obs, st.count, st.parsed = _stg.stage_association(dirs.pose_dir, cam_dirs, st.table, kid, _lib.P2S_MAX_PERSONS)
+    st.inexact = _stg.float32_inexact(obs[..., :3])
+    if st.inexact:
+        logging.warning(f"{st.inexact} 2D values are not exactly representable in float32 and were rounded for the "
+                        f"device staging layout.")
+    st.obs = obs.astype(np.float32)
+    return st
+
+
+def solve_frames(st, engine=None):
+    """ONE device call for all frames.  Returns err[F], comb[F, C] (float, NaN = camera off), Q[F, 3]."""
+    from . import ops
+    eng = engine if engine is not None else ops.get_engine(0)
+    s = st.settings
+    n_p = max(1, int(st.count.max(initial=0)))
+    obs = np.ascontiguousarray(st.obs[:, :, :n_p, :])
+    out = eng.associate_host(obs, st.count, st.P, s["reproj_thr"], s["lik_thr"], s["min_cams"])
+    comb = out["comb"].astype(np.float64)
+    comb[out["comb"] < 0] = np.nan
+    return {"err": out["err"], "comb": comb, "Q": out["Q"]}
+
+
+def rewrite_frame(tracked_paths, source_js, proposals):
+    """personAssociation.py:552-580: per camera write the source JSON with `people` replaced by the chosen
+    person of every proposal ({} when the camera is off); a camera without a readable source gets no file.
+    N.B. like the reference the RAW `people` list is indexed here."""
+    for cam, path in enumerate(tracked_paths):
+        try:
+            with open(path, "w") as out:
+                js = source_js[cam]
+                if js is None:
+                    raise FileNotFoundError
+                new = dict(js)
+                new["people"] = []
+                for comb in proposals:
+                    new["people"] += [js["people"][int(comb[cam])]] if not np.isnan(comb[cam]) else [{}]
+                out.write(json.dumps(new))
+        except Exception:
+            os.remove(path)
+
+
+def write_outputs(st, res):
+    """personAssociation.py:776-808."""
+    errors, cams_off = [], []
+    for fi, names in enumerate(st.table):
+        e, comb = res["err"][fi], res["comb"][fi]
+        if not np.isinf(e):
+            errors.append(float(e))
+        cams_off.append(int(np.count_nonzero(np.isnan(comb))))
+        tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
+        rewrite_frame(tracked, st.parsed[fi], [comb])
+    log_recap(st, errors, cams_off)
+    return {"error": errors, "cameras_off": cams_off}
+
+
+def log_recap(st, errors, cams_off):
+    """personAssociation.py:583-639 `recap_tracking`, single-person branch."""
+    s = st.settings
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        e_px = np.around(np.nanmean(errors) if len(errors) else np.nan, decimals=1)
+    fm, Dm = _calib.first_camera_scale(st.calib_file)
+    e_mm = np.around(e_px * Dm / fm * 1000, decimals=1)
+    off = np.around(np.mean(cams_off), decimals=2)
+    logging.info(f"\n--> Mean reprojection error for {s['tracked_keypoint']} point on all frames is {e_px} px, which "
+                 f"roughly corresponds to {e_mm} mm. ")
+    logging.info(f"--> In average, {off} cameras had to be excluded to reach the demanded {s['reproj_thr']} px error "
+                 f"threshold after excluding points with likelihood below {s['lik_thr_recap']}.")
+    logging.info(f"\nTracked json files are stored in {os.path.realpath(st.dirs.tracked_dir)}.")
+
+
+def associate_all(config_dict):
+    """Same contract as Pose2Sim/personAssociation.py:642: reads calibration + per-camera JSON, writes
+    `pose-associated/<cam>_json/*.json` with one person of interest, logs the recap.  Returns None."""
+    st = stage_project(config_dict)
+    res = solve_frames(st)
+    write_outputs(st, res)

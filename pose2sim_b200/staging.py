@@ -1,0 +1,244 @@
+"""Host staging: OpenPose-format JSON directories -> packed float32 arrays for ONE batched device call.
+
+The reference re-opens every camera's JSON once per person and rescans the whole file list per frame
+(Pose2Sim/triangulation.py:796-803, :607-653; Pose2Sim/personAssociation.py:758-774, :67-99, :260-274).
+Here every file is parsed once, but the VALUES and their ORDER follow the reference exactly:
+
+  * camera directories: sub-directories of `pose/` whose name contains 'json', ordered by the last
+    number in the name (common.py:568-583, triangulation.py:752-758);
+  * the input directory is pose-associated -> pose-sync -> pose for triangulation (:759-771) and
+    pose-sync -> pose for association (personAssociation.py:724-731);
+  * the file of frame f in camera c is the one whose LAST number equals f (:799), 'none' if absent;
+  * keypoint k of person n in camera c is `people[n].pose_keypoints_2d[3*id_k : 3*id_k+3]`, any
+    failure (missing file, person, short list) is a NaN triple (:626-644).
+
+Observations are stored as float32 (north_star: float4 SoA staging).  Pose2Sim's own pose stage writes
+float32 values (`kp[0].item()`, poseEstimation.py:260), so nothing is lost for its files; when a JSON
+holds values that float32 cannot represent, `float32_inexact` counts them and the callers log it.
+"""
+import fnmatch
+import json
+import os
+import re
+
+import numpy as np
+
+_LAST_NUMBER = re.compile(r"\d+")
+
+
+def sort_by_last_number(names):
+    """common.py:568-583: strings with a number first, by their last number; the rest alphabetically."""
+    def key(s):
+        nums = _LAST_NUMBER.findall(s)
+        return (False, int(nums[-1])) if nums else (True, s)
+    return sorted(names, key=key)
+
+
+def frame_number(name):
+    """triangulation.py:799 `int(re.split(r'(\\d+)', j)[-2])`: the last run of digits in the name.
+    Raises IndexError for a name without digits, like the reference."""
+    return int(re.split(r"(\d+)", name)[-2])
+
+
+class PoseDirs:
+    """Directory discovery shared by the two stages."""
+
+    def __init__(self, project_dir):
+        self.project_dir = project_dir
+        self.pose_dir = os.path.join(project_dir, "pose")
+        self.sync_dir = os.path.join(project_dir, "pose-sync")
+        self.tracked_dir = os.path.join(project_dir, "pose-associated")
+
+    def camera_dirs(self):
+        """triangulation.py:752-758 / personAssociation.py:713-720."""
+        try:
+            names = next(os.walk(self.pose_dir))[1]
+            os.listdir(os.path.join(self.pose_dir, names[0]))[0]
+        except Exception:
+            raise ValueError(f"No json files found in {self.pose_dir} subdirectories. "
+                             f"Make sure you run Pose2Sim.poseEstimation() first.")
+        names = sort_by_last_number(names)
+        return [k for k in names if "json" in k]
+
+    @staticmethod
+    def _list(base, cam_dirs):
+        return [fnmatch.filter(os.listdir(os.path.join(base, d)), "*.json") for d in cam_dirs]
+
+    def files_for_triangulation(self, cam_dirs):
+        """Returns (input_dir, per-camera sorted file names): pose-associated, else pose-sync, else pose."""
+        for base in (self.tracked_dir, self.sync_dir, self.pose_dir):
+            try:
+                names = self._list(base, cam_dirs)
+                return base, [sort_by_last_number(n) for n in names]
+            except Exception:
+                continue
+        raise Exception(f"No json files found in {self.pose_dir}, {self.sync_dir}, nor {self.tracked_dir} "
+                        f"subdirectories. Make sure you run Pose2Sim.poseEstimation() first.")
+
+    def files_for_association(self, cam_dirs):
+        """pose-sync, else pose (personAssociation.py:724-731).  N.B. the reference LISTS pose-sync but
+        then READS from pose/ because of an `os.path.exist` typo (:762-766); both are kept."""
+        for base in (self.sync_dir, self.pose_dir):
+            try:
+                names = self._list(base, cam_dirs)
+                return base, [sort_by_last_number(n) for n in names]
+            except Exception:
+                continue
+        raise ValueError(f"No json files found in {self.pose_dir} nor {self.sync_dir} subdirectories. "
+                         f"Make sure you run Pose2Sim.poseEstimation() first.")
+
+
+def frame_file_table(json_files_names, f_range):
+    """File name per (frame, camera) with the reference's selection rule (:799-800) in O(F):
+    every camera contributes ALL its files whose last number is f, or 'none'; the lists are then
+    flattened and the first n_cams entries are used (so a camera with two files for one frame shifts
+    the later cameras, exactly as in the reference)."""
+    n_cams = len(json_files_names)
+    per_cam = []
+    for names in json_files_names:
+        d = {}
+        for j in names:
+            d.setdefault(frame_number(j), []).append(j)
+        per_cam.append(d)
+    table = []
+    for f in range(*f_range):
+        flat = []
+        for c in range(n_cams):
+            flat.extend(per_cam[c].get(f) or ["none"])
+        table.append(flat[:n_cams])
+    return table
+
+
+def load_json(path):
+    """Parsed file or None when it cannot be opened / parsed (the reference's bare `except:`)."""
+    try:
+        with open(path, "r") as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def _person_keypoints(js, n):
+    """`js['people'][n]['pose_keypoints_2d']` as a float64 vector, or None on any failure."""
+    try:
+        kp = js["people"][n]["pose_keypoints_2d"]
+        return np.asarray(kp, dtype=np.float64).reshape(-1)
+    except Exception:
+        return None
+
+
+def gather_keypoints(kp, ids3):
+    """x, y, likelihood of the keypoints at flat offsets ids3 (= 3 * id); NaN where out of range."""
+    K = len(ids3)
+    out = np.full((3, K), np.nan)
+    if kp is None:
+        return out
+    ok = ids3 + 2 < kp.shape[0]
+    if ok.all():
+        out[0], out[1], out[2] = kp[ids3], kp[ids3 + 1], kp[ids3 + 2]
+    else:
+        i = ids3[ok]
+        out[0, ok], out[1, ok], out[2, ok] = kp[i], kp[i + 1], kp[i + 2]
+    return out
+
+
+def float32_inexact(*arrays):
+    """Number of finite values that change when rounded to float32."""
+    n = 0
+    for a in arrays:
+        with np.errstate(invalid="ignore", over="ignore"):
+            n += int(np.count_nonzero(np.isfinite(a) & (a.astype(np.float32).astype(np.float64) != a)))
+    return n
+
+
+def stage_triangulation(input_dir, cam_dirs, json_files_names, f_range, keypoints_ids, nb_persons):
+    """All frames of `extract_files_frame_f` (triangulation.py:607-653) at once.
+
+    Returns x, y, lik as float64 arrays [F, N, K, C] (unit-major, camera fastest: the layout
+    `p2s_triangulate_host` takes once cast to float32 and viewed as [F*N*K, C])."""
+    table = frame_file_table(json_files_names, f_range)
+    F, C, K, N = len(table), len(cam_dirs), len(keypoints_ids), nb_persons
+    ids3 = 3 * np.asarray(keypoints_ids, dtype=np.int64)
+    x = np.full((F, N, K, C), np.nan)
+    y = np.full((F, N, K, C), np.nan)
+    lik = np.full((F, N, K, C), np.nan)
+    for fi, names in enumerate(table):
+        for c in range(C):
+            js = load_json(os.path.join(input_dir, cam_dirs[c], names[c]))
+            if js is None:
+                continue
+            for n in range(N):
+                v = gather_keypoints(_person_keypoints(js, n), ids3)
+                x[fi, n, :, c], y[fi, n, :, c], lik[fi, n, :, c] = v[0], v[1], v[2]
+    return x, y, lik
+
+
+def count_persons(input_dir, cam_dirs, json_files_names):
+    """triangulation.py:784 + :77-90: the largest `len(people)` over EVERY listed json of every camera.
+    A file that cannot be parsed raises, as in the reference."""
+    best = 0
+    for c, names in enumerate(json_files_names):
+        for name in names:
+            with open(os.path.join(input_dir, cam_dirs[c], name), "r") as f:
+                best = max(best, len(json.load(f).get("people", [])))
+    return best
+
+
+# ---- association --------------------------------------------------------------------------------------
+def persons_per_camera(js):
+    """personAssociation.py:81-89: people whose x values are not all NaN; any failure -> 0."""
+    try:
+        people = js["people"]
+        return len([p for p in people if not all(np.isnan(p["pose_keypoints_2d"][::3]))])
+    except Exception:
+        return 0
+
+
+def read_people(js):
+    """personAssociation.py:260-274 `read_json`: keypoint lists with at least 3 values; any failure -> []."""
+    try:
+        out = []
+        for p in js["people"]:
+            if len(p["pose_keypoints_2d"]) < 3:
+                continue
+            out.append(p["pose_keypoints_2d"])
+        return out
+    except Exception:
+        return []
+
+
+def stage_association(read_dir, cam_dirs, table, tracked_keypoint_id, max_persons):
+    """Tracked-keypoint observations of every detected person: obs [F, C, max_persons, 4] float32
+    {x, y, likelihood, 0} and count [F, C] int32.
+
+    Two index spaces of the reference are kept apart: `count` comes from `persons_combinations`
+    (people with a non-NaN x), while the observation of person index p is taken from `read_json`'s
+    list (people with >= 3 values); an index beyond that list is a NaN triple (the `except` at
+    personAssociation.py:203-205).  Raises ValueError when a camera shows more than `max_persons`."""
+    F, C = len(table), len(cam_dirs)
+    obs = np.full((F, C, max_persons, 4), np.nan, np.float64)
+    obs[..., 3] = 0.0
+    count = np.zeros((F, C), np.int32)
+    parsed = []
+    t3 = 3 * int(tracked_keypoint_id)
+    for fi, names in enumerate(table):
+        row = []
+        for c in range(C):
+            js = load_json(os.path.join(read_dir, cam_dirs[c], names[c]))
+            row.append(js)
+            if js is None:
+                continue
+            n = persons_per_camera(js)
+            if n > max_persons:
+                raise ValueError(f"{n} persons in {names[c]}: the device search handles at most {max_persons} per camera")
+            count[fi, c] = n
+            people = read_people(js)
+            for p in range(min(n, len(people))):
+                try:
+                    v = [float(t) for t in people[p][t3:t3 + 3]]
+                except Exception:
+                    continue
+                if len(v) == 3:
+                    obs[fi, c, p, :3] = v
+        parsed.append(row)
+    return obs, count, parsed

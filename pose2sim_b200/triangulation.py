@@ -1,0 +1,463 @@
+"""Drop-in `triangulate_all(config_dict)` — same entry point, inputs and TRC output as
+Pose2Sim/triangulation.py:656-959, with the per-(frame, person, keypoint) Python loop (:831-845,
+`triangulation_from_best_cameras` :363-604) replaced by ONE batched call into the sm_100a library
+(`p2s_triangulate_host`, include/pose2sim_b200.h).
+
+    stage_project()     host   :678-821   config, calibration TOML, skeleton order, JSON -> [F, N, K, C] arrays
+    solve_units()       DEVICE :831-845   likelihood gate + weighted DLT + camera-exclusion search, all units
+    reidentify()        host   :847-865   multi-person re-ID, sequential over frames (common.py:1037-1136)
+    write_outputs()     host   :877-959   interpolation, trimming, fill, TRC (+C3D), exclusion recap
+
+There is no CPU implementation of the search in this package: `solve_units` needs the built CUDA
+library and a B200 and raises otherwise.  `handle_LR_swap` / `undistort_points` under
+`[triangulation]` (off in every shipped config) are refused loudly.
+"""
+import glob
+import logging
+import os
+
+import numpy as np
+
+from . import calib as _calib
+from . import skeletons as _skel
+from . import staging as _stg
+
+
+# ---------------------------------------------------------------------------------------------------
+# settings
+# ---------------------------------------------------------------------------------------------------
+def read_settings(config_dict):
+    """The config keys the stage reads (triangulation.py:678-696, :389-393)."""
+    prj, tri = config_dict.get("project"), config_dict.get("triangulation")
+    s = {
+        "project_dir": prj.get("project_dir"),
+        "multi_person": prj.get("multi_person"),
+        "frame_range": prj.get("frame_range"),
+        "frame_rate": prj.get("frame_rate"),
+        "pose_model": config_dict.get("pose").get("pose_model"),
+        "vid_img_extension": config_dict.get("pose").get("vid_img_extension"),
+        "reproj_thr": tri.get("reproj_error_threshold_triangulation"),
+        "lik_thr": tri.get("likelihood_threshold_triangulation"),
+        "min_cams": tri.get("min_cameras_for_triangulation"),
+        "interpolation": tri.get("interpolation"),
+        "interp_gap": tri.get("interp_if_gap_smaller_than"),
+        "max_distance_m": tri.get("max_distance_m", None),
+        "remove_incomplete_frames": tri.get("remove_incomplete_frames", False),
+        "sections_to_keep": tri.get("sections_to_keep"),
+        "min_chunk_size": tri.get("min_chunk_size", 10),
+        "fill_large_gaps_with": tri.get("fill_large_gaps_with"),
+        "show_interp_indices": tri.get("show_interp_indices"),
+        "undistort_points": tri.get("undistort_points"),
+        "handle_LR_swap": tri.get("handle_LR_swap"),
+        "make_c3d": tri.get("make_c3d"),
+    }
+    if s["min_chunk_size"] is None:
+        s["min_chunk_size"] = 10
+    return s
+
+
+def refuse_unsupported(s):
+    """not built yet -> refuse, never fall back to a CPU path."""
+    if s["undistort_points"]:
+        raise NotImplementedError("[triangulation] undistort_points = true is not available in the B200 path")
+    if s["handle_LR_swap"]:
+        raise NotImplementedError("[triangulation] handle_LR_swap = true is not available in the B200 path")
+
+
+# ---------------------------------------------------------------------------------------------------
+# staging
+# ---------------------------------------------------------------------------------------------------
+class StagedProject:
+    """Everything `solve_units` / `write_outputs` need; arrays are unit-major, camera fastest."""
+    __slots__ = ("settings", "calib_file", "P", "keypoints_ids", "keypoints_names", "cam_dirs", "input_dir",
+                 "f_range", "n_cams", "n_persons", "x", "y", "lik", "inexact")
+
+
+def stage_project(config_dict):
+    s = read_settings(config_dict)
+    refuse_unsupported(s)
+    session_dir = _calib.session_dir_of(s["project_dir"])
+    calib_file = _calib.find_calibration_file(session_dir)
+    P = _calib.compute_P(calib_file, undistort=False)
+    ids, names = _skel.keypoints(s["pose_model"], config_dict)
+
+    dirs = _stg.PoseDirs(s["project_dir"])
+    cam_dirs = dirs.camera_dirs()
+    input_dir, files = dirs.files_for_triangulation(cam_dirs)
+    n_cams = len(cam_dirs)
+    fr = s["frame_range"]
+    f_range = [0, min(len(j) for j in files)] if fr in ("all", "auto", []) else fr
+    if n_cams != len(P):
+        raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
+                        f"file, and {n_cams} cameras based on the number of pose folders.")
+    n_persons = _stg.count_persons(input_dir, cam_dirs, files) if s["multi_person"] else 1
+
+    x, y, lik = _stg.stage_triangulation(input_dir, cam_dirs, files, f_range, ids, n_persons)
+    st = StagedProject()
+    st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
+    st.keypoints_ids, st.keypoints_names = ids, names
+    st.cam_dirs, st.input_dir, st.f_range, st.n_cams, st.n_persons = cam_dirs, input_dir, list(f_range), n_cams, n_persons
+    st.inexact = _stg.float32_inexact(x, y, lik)
+    st.x, st.y, st.lik = (a.astype(np.float32) for a in (x, y, lik))
+    if st.inexact:
+        logging.warning(f"{st.inexact} 2D values are not exactly representable in float32 and were rounded for the "
+                        f"device staging layout (Pose2Sim's own pose stage writes float32 values).")
+    return st
+
+
+# ---------------------------------------------------------------------------------------------------
+# device
+# ---------------------------------------------------------------------------------------------------
+def solve_units(st, engine=None):
+    """ONE device call for all F*N*K units: likelihood gate (:817-821) + exclusion search (:363-604).
+    Returns Q[F,N,K,3], err[F,N,K], nexcl[F,N,K] (int), mask[F,N,K] (uint32 id_excluded_cams bit sets)."""
+    from . import ops
+    eng = engine if engine is not None else ops.get_engine(0)
+    F, N, K, C = st.x.shape
+    U = F * N * K
+    s = st.settings
+    out = eng.triangulate_host(st.x.reshape(U, C), st.y.reshape(U, C), st.lik.reshape(U, C), st.P,
+                               s["lik_thr"], s["reproj_thr"], s["min_cams"])
+    return {"Q": out["Q"].reshape(F, N, K, 3), "err": out["err"].reshape(F, N, K),
+            "nexcl": out["nexcl"].reshape(F, N, K).astype(np.int64), "mask": out["mask"].reshape(F, N, K),
+            "stats": out.get("stats")}
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-person re-identification across frames (host, sequential)
+# ---------------------------------------------------------------------------------------------------
+def match_to_previous(prev, cur, max_dist=None):
+    """common.py:1037-1136 `sort_people_sports2d` without scores: Hungarian assignment on the mean
+    per-keypoint distance, `max_dist` gate, unmatched detections appended as new persons.
+    Returns (carried_prev, sorted_cur, ids) with ids[i] = index into `cur` or -1."""
+    from scipy.optimize import linear_sum_assignment
+    n_prev, n_cur = len(prev), len(cur)
+    with np.errstate(invalid="ignore"):
+        d = np.sqrt(np.nansum((cur[None, :, :, :] - prev[:, None, :, :]) ** 2, axis=3))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            D = np.nanmean(d, axis=2)
+    D = np.nan_to_num(D, nan=1e10, posinf=1e10)
+    rows, cols = linear_sum_assignment(D)
+    pairs = [(r, c) for r, c in zip(rows, cols) if max_dist is None or D[r, c] <= max_dist]
+    taken = {c for _, c in pairs}
+    fresh = [i for i in range(n_cur) if i not in taken]
+    n_total = n_prev + len(fresh)
+    sorted_cur = np.full((n_total,) + cur.shape[1:], np.nan)
+    ids = np.full(n_total, -1)
+    for r, c in pairs:
+        sorted_cur[r], ids[r] = cur[c], c
+    for j, c in enumerate(fresh):
+        sorted_cur[n_prev + j], ids[n_prev + j] = cur[c], c
+    padded = prev if n_prev >= n_total else np.concatenate([prev, np.full((n_total - n_prev,) + prev.shape[1:], np.nan)])
+    carried = np.where(np.isnan(sorted_cur) & ~np.isnan(padded), padded, sorted_cur)
+    return carried, sorted_cur, ids
+
+
+def reidentify(res, f_range, n_cams, max_distance_m):
+    """triangulation.py:822-865 for all frames: reorder persons frame by frame.  Only the first
+    N rows survive each frame (:868), persons not seen get NaN / n_cams / all-camera ids (:860-863)."""
+    Q, err, nexcl, mask = res["Q"], res["err"], res["nexcl"], res["mask"]
+    F, N, K, _ = Q.shape
+    all_cams = np.uint32((1 << n_cams) - 1) if n_cams < 32 else np.uint32(0xFFFFFFFF)
+    oQ, oe, on, om = np.empty_like(Q), np.empty_like(err), np.empty_like(nexcl), np.empty_like(mask)
+    last = np.full((N, K, 3), np.nan)          # the previous frame's (sorted) persons
+    memory = np.full((N, K, 3), np.nan)        # last known position of every tracked person
+    for fi, f in enumerate(range(*f_range)):
+        memory = np.where(np.isnan(last), memory, last)
+        cur = Q[fi]
+        if f != 0:
+            memory, cur_sorted, ids = match_to_previous(memory, cur, max_distance_m)
+            for n in range(N):
+                j = ids[n]
+                if j >= 0:
+                    oe[fi, n], on[fi, n], om[fi, n] = err[fi, j], nexcl[fi, j], mask[fi, j]
+                else:
+                    oe[fi, n], on[fi, n], om[fi, n] = np.nan, n_cams, all_cams
+            cur = cur_sorted
+        else:
+            oe[fi], on[fi], om[fi] = err[fi], nexcl[fi], mask[fi]
+        oQ[fi] = cur[:N]
+        last = cur
+    return {"Q": oQ, "err": oe, "nexcl": on, "mask": om}
+
+
+# ---------------------------------------------------------------------------------------------------
+# post-processing
+# ---------------------------------------------------------------------------------------------------
+def fill_small_gaps(col, index, max_gap, kind):
+    """common.py:669-712 `interpolate_zeros_nans` on one coordinate column (values at labels `index`)."""
+    from scipy import interpolate
+    good = ~(np.isnan(col) | (col == 0))
+    if np.count_nonzero(good) <= 4:
+        return col
+    f = interpolate.interp1d(index[good], col[good], kind=kind, fill_value="extrapolate", bounds_error=False)
+    out = np.where(good, col, f(index))
+    bad = np.flatnonzero(~good)
+    if bad.size:
+        for seq in np.split(bad, np.flatnonzero(np.diff(index[bad]) > 1) + 1):
+            if len(seq) > max_gap:
+                out[seq] = np.nan
+    return out
+
+
+def valid_chunk(series, min_chunk_size=10, method="largest"):
+    """triangulation.py:93-148: (start, end) positions of the runs of >= min_chunk_size non-NaN values
+    selected by `method` ('largest' | 'all' | 'first' | 'last'); (0, 0) when there is none."""
+    ok = ~np.isnan(np.asarray(series, dtype=np.float64))
+    edges = np.flatnonzero(np.diff(np.concatenate([[0], ok.astype(np.int8), [0]])))
+    runs = [(int(a), int(b)) for a, b in zip(edges[::2], edges[1::2]) if b - a >= min_chunk_size]
+    if not runs:
+        return 0, 0
+    if method not in ("largest", "all", "first", "last"):
+        method = "all"
+    if method == "largest":
+        return max(runs, key=lambda r: r[1] - r[0])       # first of the longest, like a stable sort
+    if method == "all":
+        return runs[0][0], runs[-1][1]
+    return runs[0] if method == "first" else runs[-1]
+
+
+def _ffill_bfill(a):
+    """DataFrame.ffill().bfill() down the rows (NaN only)."""
+    def ffill(v):
+        idx = np.where(~np.isnan(v), np.arange(v.shape[0])[:, None], 0)
+        np.maximum.accumulate(idx, axis=0, out=idx)
+        return np.take_along_axis(v, idx, axis=0)
+    a = ffill(a)
+    return ffill(a[::-1])[::-1]
+
+
+def frame_rate_of(s):
+    """triangulation.py:171-185."""
+    rate = s["frame_rate"]
+    if rate == "auto":
+        try:
+            import cv2
+            vids = glob.glob(os.path.join(s["project_dir"], "videos", "*" + s["vid_img_extension"]))
+            cap = cv2.VideoCapture(vids[0])
+            cap.read()
+            if cap.read()[0] is False:
+                raise RuntimeError
+            rate = round(cap.get(cv2.CAP_PROP_FPS))
+        except Exception:
+            logging.warning("Cannot read video. Frame rate will be set to 60 fps.")
+            rate = 30                                      # sic: the reference logs 60 and uses 30
+    return rate
+
+
+def write_trc(s, Q, frames, keypoints_names, id_person=-1):
+    """triangulation.py:151-215 `make_trc`: Q [n, 3K] Z-up, `frames` their labels.  Returns the path."""
+    import pandas as pd
+    project_dir = s["project_dir"]
+    base = os.path.basename(os.path.realpath(project_dir))
+    seq = f"{base}_P{id_person}" if s["multi_person"] else base
+    out_dir = os.path.join(project_dir, "pose-3d")
+    rate = frame_rate_of(s)
+    name = f"{seq}_{frames[0]}-{frames[-1]}.trc"
+    K = len(keypoints_names)
+    header = ["PathFileType\t4\t(X/Y/Z)\t" + name,
+              "DataRate\tCameraRate\tNumFrames\tNumMarkers\tUnits\tOrigDataRate\tOrigDataStartFrame\tOrigNumFrames",
+              "\t".join(map(str, [rate, rate, len(Q), K, "m", rate, frames[0], len(Q)])),
+              "Frame#\tTime\t" + "\t\t\t".join(keypoints_names) + "\t\t\t",
+              "\t\t" + "\t".join(f"X{i + 1}\tY{i + 1}\tZ{i + 1}" for i in range(K)) + "\t"]
+    yup = Q.reshape(len(Q), K, 3)[:, :, [1, 2, 0]].reshape(len(Q), 3 * K)      # common.py:596-612: X,Y,Z <- Y,Z,X
+    df = pd.DataFrame(yup, index=pd.Index(frames))
+    df.insert(0, "t", df.index / rate)
+    if not os.path.exists(out_dir):
+        os.mkdir(out_dir)
+    path = os.path.realpath(os.path.join(out_dir, name))
+    with open(path, "w") as f:
+        f.write("\n".join(header) + "\n")
+        df.to_csv(f, sep="\t", index=True, header=None, lineterminator="\n")
+    return path
+
+
+def write_c3d(trc_path):
+    """common.py:615-665 `convert_to_c3d`, when the optional `c3d` package is importable."""
+    import c3d
+    with open(trc_path) as f:
+        names = f.readlines()[3].strip().split("\t")[2::3]
+    data = np.genfromtxt(trc_path, skip_header=5, delimiter="\t")[:, 1:]
+    t = data[:, 0]
+    rate = round((len(t) - 1) / (t[-1] - t[0]))
+    w = c3d.Writer(point_rate=rate, analog_rate=0, point_scale=1.0, point_units="mm", gen_scale=-1.0)
+    w.set_point_labels(names)
+    w.set_screen_axis(X="+Z", Y="+Y")
+    for row in data:
+        pts = np.hstack([row[1:].reshape(-1, 3) * 1000, np.zeros((len(names), 2))])
+        w.add_frames([(pts, np.array([]))])
+    w.set_start_frame(0)
+    w._set_last_frame(len(data) - 1)
+    path = trc_path.replace(".trc", ".c3d")
+    with open(path, "wb") as h:
+        w.write(h)
+    return path
+
+
+def _gap_strings(positions, max_gap):
+    seqs = np.split(positions, np.flatnonzero(np.diff(positions) > 1) + 1)
+    short = [f"{q[0]}:{q[-1]}" for q in seqs if 0 < len(q) <= max_gap]
+    long_ = [f"{q[0]}:{q[-1]}" for q in seqs if len(q) > max_gap]
+    return short, long_
+
+
+def write_outputs(st, res):
+    """triangulation.py:877-959.  `res`: Q[F,N,K,3], err[F,N,K], nexcl[F,N,K], mask[F,N,K].
+    Returns a dict with the TRC paths and the recap statistics (also logged)."""
+    s = st.settings
+    F, N, K, _ = res["Q"].shape
+    frames = np.arange(*st.f_range)
+    n_cams = st.n_cams
+    min_chunk = s["min_chunk_size"]
+    trimmed, trc_paths, cam_excluded, interp_frames, non_interp_frames = [], [], [], [], []
+    err_kept, nexcl_kept = [], []
+    for n in range(N):
+        Qn = res["Q"][:, n].reshape(F, 3 * K).astype(np.float64).copy()
+        en = res["err"][:, n].astype(np.float64)
+        xn = res["nexcl"][:, n].astype(np.float64)
+        mn = res["mask"][:, n]
+        if s["interpolation"] != "none":
+            try:
+                cols = [fill_small_gaps(Qn[:, j], frames, s["interp_gap"], s["interpolation"]) for j in range(3 * K)]
+                Qn = np.stack(cols, axis=1) if cols else Qn
+            except Exception:
+                logging.warning(f"Interpolation was not possible for person {n}. This means that not enough points "
+                                f"are available, which is often due to a bad calibration.")
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            e_mean = en.mean(axis=1) if s["remove_incomplete_frames"] else np.nanmean(en, axis=1)
+        x_mean = xn.mean(axis=1)
+        a, b = valid_chunk(e_mean, min_chunk, s["sections_to_keep"])
+        trimmed.append([a, b])
+        if b - a <= min_chunk:
+            cam_excluded.append({})
+            interp_frames.append([])
+            non_interp_frames.append([])
+            trc_paths.append("")
+            err_kept.append(None)
+            nexcl_kept.append(None)
+            logging.info(f"\nPerson {n}: Less than {min_chunk} valid frames in a row. Deleting person.")
+            continue
+        Qn, en, xn, mn, fr = Qn[a:b], en[a:b], xn[a:b], mn[a:b], frames[a:b]
+        err_kept.append(np.concatenate([en, e_mean[a:b, None]], axis=1))
+        nexcl_kept.append(np.concatenate([xn, x_mean[a:b, None]], axis=1))
+        xs = Qn[:, ::3].T
+        kpt_i, pos = np.where((xs == 0) | ~np.isfinite(xs))
+        bad_per_kpt = [pos[kpt_i == k] for k in range(K)]
+        bad_per_kpt = [z[(a < z) & (b > z)] for z in bad_per_kpt]            # sic (:906): positions vs. bounds
+
+        if s["fill_large_gaps_with"] == "last_value":
+            Qn = _ffill_bfill(Qn)
+            Qn[np.isnan(Qn) | (Qn == np.inf)] = 0
+        elif s["fill_large_gaps_with"] == "zeros":
+            Qn[np.isnan(Qn) | (Qn == np.inf)] = 0
+
+        trc_paths.append(write_trc(s, Qn, fr, st.keypoints_names, id_person=n))
+        if s["make_c3d"]:
+            try:
+                write_c3d(trc_paths[-1])
+            except ImportError:
+                logging.warning("make_c3d = true but the optional `c3d` package is not installed: no .c3d written.")
+
+        opportunities = len(Qn) * K
+        counts = {c: int(np.count_nonzero((mn >> np.uint32(c)) & np.uint32(1))) for c in range(n_cams)}
+        cam_excluded.append({c: v / opportunities for c, v in counts.items()})
+        if s["show_interp_indices"]:
+            pairs = [_gap_strings(bad_per_kpt[k], s["interp_gap"]) for k in range(K)]
+            interp_frames.append([p[0] for p in pairs])
+            non_interp_frames.append([p[1] for p in pairs])
+        else:
+            interp_frames.append(None)
+            non_interp_frames.append([])
+
+    if np.all(np.diff(np.array(trimmed)) == 0):
+        raise Exception("No persons have been triangulated. Please check your calibration and your synchronization, "
+                        "or the triangulation parameters in Config.toml.")
+    recap = {"trc_paths": trc_paths, "f_range_trimmed": trimmed, "cam_excluded_count": cam_excluded,
+             "error": err_kept, "nb_cams_excluded": nexcl_kept, "interp_frames": interp_frames,
+             "non_interp_frames": non_interp_frames}
+    log_recap(st, recap)
+    return recap
+
+
+def log_recap(st, r):
+    """triangulation.py:255-360 `recap_triangulate` (log lines only)."""
+    s = st.settings
+    names = np.array(_calib.camera_names(st.calib_file))
+    names = names[list(r["cam_excluded_count"][0].keys())]
+    fm, Dm = _calib.first_camera_scale(st.calib_file)
+    kind, gap = s["interpolation"], s["interp_gap"]
+    logging.info("")
+    N = len(r["error"])
+    import warnings
+    for n in range(N):
+        a, b = r["f_range_trimmed"][n]
+        if b - a <= s["min_chunk_size"]:
+            continue
+        if N > 1:
+            logging.info(f"\n\nPARTICIPANT {n}\n")
+        err, nex = r["error"][n], r["nb_cams_excluded"][n]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            for k, name in enumerate(st.keypoints_names):
+                e_px = np.around(np.nanmean(err[:, k]), decimals=1)
+                e_m = np.around(e_px * Dm / fm, decimals=3)
+                excl = np.around(np.nanmean(nex[:, k]), decimals=2)
+                logging.info(f"Mean reprojection error for {name} is {e_px} px (~ {e_m} m), reached with {excl} excluded cameras. ")
+                if s["show_interp_indices"]:
+                    if kind != "none":
+                        done, skipped = r["interp_frames"][n][k], r["non_interp_frames"][n][k]
+                        if not done and not skipped:
+                            logging.info("  No frames needed to be interpolated.")
+                        if done:
+                            logging.info("  Frames " + ", ".join(d.replace(":", " to ") for d in done) + " were interpolated.")
+                        if skipped:
+                            logging.info("  Frames " + ", ".join(d.replace(":", " to ") for d in skipped) + " were not interpolated.")
+                    else:
+                        logging.info("  No frames were interpolated because 'interpolation_kind' was set to none. ")
+            e_px = np.around(np.nanmean(err[:, -1]), decimals=1)
+            e_mm = np.around(e_px * Dm / fm * 1000, decimals=1)
+            excl = np.around(np.nanmean(nex[:, -1]), decimals=2)
+        logging.info(f"\n--> Mean reprojection error for all points on frames {a} to {b} is {e_px} px, which roughly corresponds to {e_mm} mm. ")
+        logging.info(f"Cameras were excluded if likelihood was below {s['lik_thr']} and if the reprojection error was above {s['reproj_thr']} px.")
+        if kind != "none":
+            fill = {"last_value": "the last valid value", "zeros": "zeros"}.get(s["fill_large_gaps_with"], "NaNs")
+            logging.info(f"Gaps were interpolated with {kind} method if smaller than {gap} frames. Larger gaps were filled with {fill}.")
+        logging.info(f"In average, {excl} cameras had to be excluded to reach these thresholds.")
+        if len(range(a, b)) < len(range(*st.f_range)):
+            logging.warning(f"\nSome frames could not be correctly triangulated: trial trimmed between frames {[a, b]}.\n"
+                            "You might need to tweak the triangulation parameters in Config.toml (for example, try "
+                            'increasing "reproj_error_threshold_triangulation").')
+        named = dict(zip(names, r["cam_excluded_count"][n].values()))
+        named = dict(sorted(named.items(), key=lambda kv: kv[1])[::-1])
+        r["cam_excluded_count"][n] = named
+        parts = []
+        for i, (cam, v) in enumerate(named.items()):
+            pct = int(np.round(v * 100))
+            if i == 0:
+                parts.append(f"Camera {cam} was excluded {pct}% of the time, ")
+            elif i == len(named) - 1:
+                parts.append(f"and Camera {cam}: {pct}%.")
+            else:
+                parts.append(f"Camera {cam}: {pct}%, ")
+        logging.info("".join(parts))
+        logging.info(f"3D coordinates are stored at {r['trc_paths'][n]}.")
+    logging.info("\n\n")
+    if s["make_c3d"]:
+        logging.info("All trc files have been converted to c3d.")
+    logging.info(f"Limb swapping was {'handled' if s['handle_LR_swap'] else 'not handled'}.")
+    logging.info(f"Lens distortions were {'taken into account' if s['undistort_points'] else 'not taken into account'}.")
+
+
+# ---------------------------------------------------------------------------------------------------
+def triangulate_all(config_dict):
+    """Same contract as Pose2Sim/triangulation.py:656: reads the calibration TOML and the per-camera
+    OpenPose JSON of the trial, writes `pose-3d/*.trc`, logs the recap.  Returns None."""
+    st = stage_project(config_dict)
+    res = solve_units(st)
+    if st.settings["multi_person"]:
+        res = reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
+    write_outputs(st, res)

@@ -1,0 +1,122 @@
+"""Host logic of the drop-in stages on a CPU box: staging (JSON -> arrays), multi-person re-ID,
+interpolation / trimming / fill, TRC writer, association JSON rewrite — checked against what the
+UNMODIFIED reference wrote for the same trials (tests/golden/e2e_*.npz).
+
+The device call in the middle is replaced HERE (test code only) by the NumPy oracle; the product
+functions `triangulate_all` / `associate_all` have no such seam and need the CUDA library."""
+import logging
+import warnings
+
+import numpy as np
+import pytest
+
+import p2s_oracle as orc
+from dropin_util import (assert_trc_equal, associated_people, golden_trcs, in_dir, rebuild_trial, written_trcs)
+from pose2sim_b200 import personAssociation as pa
+from pose2sim_b200 import staging, triangulation as tri
+
+
+def oracle_units(st):
+    F, N, K, C = st.x.shape
+    U = F * N * K
+    s = st.settings
+    x, y, w = (a.reshape(U, C).astype(np.float64) for a in (st.x, st.y, st.lik))
+    with np.errstate(invalid="ignore"):
+        low = w < s["lik_thr"]                              # triangulation.py:817-821
+    x[low] = np.nan; y[low] = np.nan; w[low] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"])
+    return {"Q": Q.reshape(F, N, K, 3), "err": err.reshape(F, N, K), "nexcl": nexcl.reshape(F, N, K).astype(np.int64),
+            "mask": mask.reshape(F, N, K)}
+
+
+@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi"])
+def test_triangulation_host_pipeline_matches_reference_trc(golden, tmp_path, tag, caplog):
+    g = golden(tag + ".npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    with in_dir(proj), caplog.at_level(logging.INFO):
+        st = tri.stage_project(cfg)
+        assert st.inexact == 0
+        res = oracle_units(st)
+        if st.settings["multi_person"]:
+            res = tri.reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
+        tri.write_outputs(st, res)
+    got, ref = written_trcs(proj), golden_trcs(g)
+    assert sorted(got) == sorted(ref)
+    for name in ref:
+        assert_trc_equal(got[name], ref[name], tol=1e-6)
+    # the recap lines the reference logged appear in ours too (same numbers)
+    ref_lines = [l.strip() for l in str(g["log"]).splitlines()
+                 if l.startswith("--> Mean reprojection error") or l.startswith("Camera ") or l.startswith("In average")]
+    ours = caplog.text
+    assert ref_lines
+    for line in ref_lines:
+        assert line in ours, line
+
+
+def test_staging_matches_reference_order(golden, tmp_path):
+    """Keypoints come out in skeleton pre-order and units are (frame, person, keypoint)-major."""
+    g = golden("e2e_tri_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    with in_dir(proj):
+        st = tri.stage_project(cfg)
+    assert st.keypoints_ids == [19, 12, 14, 16, 21, 23, 25, 11, 13, 15, 20, 22, 24, 18, 17, 0, 1, 2, 3, 4, 6, 8, 10, 5, 7, 9]
+    kp = g["kp"]                                            # [F, C, 1, 78]
+    ids = np.asarray(st.keypoints_ids)
+    assert st.x.shape == (100, 1, 26, 4)
+    assert np.array_equal(st.x[:, 0], kp[:, :, 0, :][:, :, 3 * ids].transpose(0, 2, 1))
+    assert np.array_equal(st.lik[:, 0], kp[:, :, 0, :][:, :, 3 * ids + 2].transpose(0, 2, 1))
+
+
+def test_file_selection_rules():
+    assert staging.sort_by_last_number(["json1", "zero", "js4on2.b", "aaaa", "eypoints_0000003.json", "ajson0", "json10"]) == \
+        ["ajson0", "json1", "js4on2.b", "eypoints_0000003.json", "json10", "aaaa", "zero"]
+    assert staging.frame_number("cam01_000012.json") == 12
+    table = staging.frame_file_table([["a_0.json", "a_2.json"], ["b_0.json", "b_1.json", "b_2.json"]], [0, 3])
+    assert table == [["a_0.json", "b_0.json"], ["none", "b_1.json"], ["a_2.json", "b_2.json"]]
+
+
+def test_valid_chunk_and_gap_filling():
+    s = np.array([np.nan, 1, 1, 1, np.nan, 1, 1, 1, 1, np.nan, 1])
+    assert tri.valid_chunk(s, 3, "all") == (1, 9)
+    assert tri.valid_chunk(s, 3, "largest") == (5, 9)
+    assert tri.valid_chunk(s, 3, "first") == (1, 4)
+    assert tri.valid_chunk(s, 3, "last") == (5, 9)
+    assert tri.valid_chunk(s, 5, "all") == (0, 0)
+    col = np.array([1.0, 2.0, np.nan, 4.0, 5.0, 0.0, 0.0, 0.0, 9.0, 10.0])
+    out = tri.fill_small_gaps(col, np.arange(10), 2, "linear")
+    assert out[2] == 3.0 and np.isnan(out[5:8]).all() and out[8] == 9.0
+
+
+def test_refuses_unbuilt_modes(golden, tmp_path):
+    g = golden("e2e_tri_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    cfg["triangulation"]["undistort_points"] = True
+    with in_dir(proj), pytest.raises(NotImplementedError):
+        tri.stage_project(cfg)
+    cfg["triangulation"]["undistort_points"] = False
+    cfg["triangulation"]["handle_LR_swap"] = True
+    with in_dir(proj), pytest.raises(NotImplementedError):
+        tri.stage_project(cfg)
+
+
+def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
+    g = golden("e2e_assoc_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_assoc")
+    with in_dir(proj):
+        st = pa.stage_project(cfg)
+        assert st.tracked_keypoint_id == 18                  # 'Neck' in HALPE_26
+        F, C = st.count.shape
+        err, comb, Q = np.empty(F), np.empty((F, C)), np.empty((F, 3))
+        s = st.settings
+        for f in range(F):
+            ob = [[st.obs[f, c, p, :3].astype(float) for p in range(st.count[f, c])] for c in range(C)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                err[f], comb[f], Q[f] = orc.associate_frame(ob, list(st.count[f]), st.P, s["reproj_thr"], s["lik_thr"], s["min_cams"])
+        pa.write_outputs(st, {"err": err, "comb": comb, "Q": Q})
+    chosen, exists = associated_people(proj, [str(c) for c in g["cams"]], F, g["chosen"].shape[2])
+    assert np.array_equal(exists, g["exists"])
+    assert np.array_equal(np.isnan(chosen), np.isnan(g["chosen"]))
+    assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
