@@ -84,44 +84,51 @@ __device__ __forceinline__ void accumulate_camera(Sym4 &M, const double *Pc, dou
 }
 
 // Smallest eigenvector of M, de-homogenised: safeguarded Newton on the secular equation.
-// Returns the number of factorisations used.
+// (Newton on f is Rayleigh-quotient iteration for v = (q, 1): lam + f/g is the Rayleigh quotient of
+// the current v, so convergence is cubic.)  When the step dl is already tiny against the smallest
+// pivot, q(lam + dl) is obtained from the factorisation at hand by the first-order update
+// q += dl (A - lam I)^-1 q   [d q/d lam = (A - lam I)^-1 q],  error O((dl/dmin)^2) <= 1e-16 |q|,
+// instead of paying one more factorisation just to confirm.  Returns the factorisations used.
 __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
-    double lam = 0.0, lo = 0.0, prev = inf64();
+    double lam = 0.0, lo = 0.0;
     double x0 = nan64(), x1 = x0, x2 = x0;
     int it = 0;
 #pragma unroll 1
     for (; it < 24; ++it) {
-        double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
-        double r0 = rcp_fast(a00);
-        double l10 = M.m01 * r0, l20 = M.m02 * r0;
-        double d1 = fma(-l10, M.m01, a11), t21 = fma(-l20, M.m01, M.m12);
-        double r1 = rcp_fast(d1);
-        double l21 = t21 * r1;
-        double d2 = fma(-l21, t21, fma(-l20, M.m02, a22));
+        const double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
+        const double r0 = rcp_fast(a00);
+        const double l10 = M.m01 * r0, l20 = M.m02 * r0;
+        const double d1 = fma(-l10, M.m01, a11), t21 = fma(-l20, M.m01, M.m12);
+        const double r1 = rcp_fast(d1);
+        const double l21 = t21 * r1;
+        const double d2 = fma(-l21, t21, fma(-l20, M.m02, a22));
         if (!(a00 > 0.0 && d1 > 0.0 && d2 > 0.0)) {          // right of the pole (or NaN input)
             if (!(lam > lo)) break;                          // not even positive definite at lo: give up (NaN)
             lam = 0.5 * (lam + lo);
-            prev = inf64();
             continue;
         }
-        double r2 = rcp_fast(d2);
+        const double r2 = rcp_fast(d2);
         double z0 = -M.m03;
         double z1 = fma(-l10, z0, -M.m13);
         double z2 = fma(-l21, z1, fma(-l20, z0, -M.m23));
-        z0 *= r0; z1 *= r1; z2 *= r2;
-        x2 = z2;
-        x1 = fma(-l21, x2, z1);
-        x0 = fma(-l20, x2, fma(-l10, x1, z0));
-        double f = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - lam)));
-        double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
-        double dl = f * rcp_fast(g);
+        x2 = z2 * r2;
+        x1 = fma(-l21, x2, z1 * r1);
+        x0 = fma(-l20, x2, fma(-l10, x1, z0 * r0));
+        const double f = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - lam)));
+        const double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
+        const double dl = f * rcp_fast(g);
         if (f > 0.0) lo = lam;
-        double adl = fabs(dl);
-        double dmin = fmin(a00, fmin(d1, d2));
-        // converged: the step no longer moves q (|dq|/|q| ~ |dl|/dmin), or it has reached the
-        // rounding floor of f (stops shrinking while already tiny)
-        if (adl <= 1e-16 * dmin || (adl >= prev && adl <= 1e-9 * dmin)) { ++it; break; }
-        prev = adl;
+        const double dmin = fmin(a00, fmin(d1, d2));
+        if (fabs(dl) <= 1e-8 * dmin) {                       // converged: first-order update, no refactorisation
+            const double y1 = fma(-l10, x0, x1);
+            const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
+            const double w2 = y2 * r2;
+            const double w1 = fma(-l21, w2, y1 * r1);
+            const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
+            x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);
+            ++it;
+            break;
+        }
         lam += dl;
     }
     qx = x0; qy = x1; qz = x2;
@@ -178,14 +185,46 @@ static __device__ __noinline__ int smallest_eigvec_jacobi(const Sym4 &M, double 
     return sweeps;
 }
 
-// Pixel distance between the observation (x, y) and the reprojection of Q~ = (qx, qy, qz, 1).
+// Pixel distance between the observation (x, y) and the reprojection of Q~ = (qx, qy, qz, 1):
+//   hypot(x - u/d, y - v/d) = sqrt(N) / |d| = N * rsqrt(N d^2),   N = (u - x d)^2 + (v - y d)^2,
+// i.e. ONE reciprocal square root (MUFU.RSQ64H seed + a cubic correction, ~1.5 ulp) instead of a
+// reciprocal plus a square root.  The 1e-300 keeps N = 0 at distance 0 (0 * rsqrt(tiny)).
 __device__ __forceinline__ double reproj_distance(const double *Pc, double qx, double qy, double qz, double x, double y) {
-    double u = fma(Pc[0], qx, fma(Pc[1], qy, fma(Pc[2], qz, Pc[3])));
-    double v = fma(Pc[4], qx, fma(Pc[5], qy, fma(Pc[6], qz, Pc[7])));
-    double d = fma(Pc[8], qx, fma(Pc[9], qy, fma(Pc[10], qz, Pc[11])));
-    double rd = rcp_fast(d);
-    double dx = fma(-u, rd, x), dy = fma(-v, rd, y);
-    return sqrt_fast(fma(dx, dx, dy * dy));
+    const double u = fma(Pc[0], qx, fma(Pc[1], qy, fma(Pc[2], qz, Pc[3])));
+    const double v = fma(Pc[4], qx, fma(Pc[5], qy, fma(Pc[6], qz, Pc[7])));
+    const double d = fma(Pc[8], qx, fma(Pc[9], qy, fma(Pc[10], qz, Pc[11])));
+    const double dx = fma(-x, d, u), dy = fma(-y, d, v);
+    const double N = fma(dx, dx, dy * dy);
+    const double S = fma(N, d * d, 1e-300);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(S));
+    const double t = S * r;
+    const double e = fma(-t, r, 1.0);                // 1 - S r^2
+    const double p = fma(0.375, e, 0.5);
+    r = fma(r * e, p, r);                            // r (1 + e/2 + 3 e^2/8)
+    return N * r;
+}
+
+// sum / m for a small positive integer m without the IEEE division slow path: reciprocal + one
+// residual correction (correctly rounded except in rare half-way cases).
+__device__ __forceinline__ double div_small(double sum, double m) {
+    const double r = rcp_fast(m);
+    const double e = sum * r;
+    return fma(fma(-m, e, sum), r, e);
+}
+
+// Camera c's contribution to the normal matrix as a block: B = a a^T + b b^T with the two weighted
+// DLT rows a = (P[0] - x P[2]) w, b = (P[1] - y P[2]) w (common.py:344-345).  Pc may point to shared
+// memory (dynamic camera index).  blk = {m00, m01, m02, m03, m11, m12, m13, m22, m23, m33}.
+__device__ __forceinline__ void camera_block(const double *Pc, double x, double y, double w, double *blk) {
+    const double a0 = fma(-x, Pc[8], Pc[0]) * w, a1 = fma(-x, Pc[9], Pc[1]) * w;
+    const double a2 = fma(-x, Pc[10], Pc[2]) * w, a3 = fma(-x, Pc[11], Pc[3]) * w;
+    const double b0 = fma(-y, Pc[8], Pc[4]) * w, b1 = fma(-y, Pc[9], Pc[5]) * w;
+    const double b2 = fma(-y, Pc[10], Pc[6]) * w, b3 = fma(-y, Pc[11], Pc[7]) * w;
+    blk[0] = fma(b0, b0, a0 * a0); blk[1] = fma(b0, b1, a0 * a1); blk[2] = fma(b0, b2, a0 * a2); blk[3] = fma(b0, b3, a0 * a3);
+    blk[4] = fma(b1, b1, a1 * a1); blk[5] = fma(b1, b2, a1 * a2); blk[6] = fma(b1, b3, a1 * a3);
+    blk[7] = fma(b2, b2, a2 * a2); blk[8] = fma(b2, b3, a2 * a3);
+    blk[9] = fma(b3, b3, a3 * a3);
 }
 
 // One candidate camera subset `valid` (bit c = camera c used).  `fetch(c)` returns the unit's
@@ -221,7 +260,7 @@ __device__ __forceinline__ int solve_subset(const CamParams<CMAX> &cams, Fetch f
             sum += reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
         }
     }
-    err = sum / (double)m;
+    err = div_small(sum, (double)m);
     return iters;
 }
 

@@ -51,29 +51,67 @@ struct TriArgs {
 template <int CMAX>
 struct WarpSlab {                 // per-warp shared memory
     float4 obs[CMAX][32];         // staged observations of the tile
+    double blk[32][10];           // camera blocks of the current group pass, slot = group * C + camera
+    double mall[16][10];          // per group: sum of the unit's valid camera blocks
     double r_err[32];             // level results published by the winning lane of each unit
     double r_qx[32], r_qy[32], r_qz[32];
+    unsigned long long st64[4];   // per-warp statistics: candidates, camera-solves, solver steps
+    uint32_t st32[12];            // level histogram [0..7], failed, not evaluated, threshold band, arg-min band
     uint32_t r_nan[32];           // NaN-camera set of the winner (id_excluded_cams)
     uint32_t r_flags[32];         // bit0..7: excl count, bit 8: argmin band hit
     uint32_t nan0[32];            // cameras whose likelihood is NaN
     uint32_t inv0[32];            // NaN or zero likelihood
+    uint32_t plist[32];           // owner lanes of the units pending at the current level, compacted
 };
+
+// Weighted-DLT normal matrix of ONE unit accumulated straight from the observations (level 0:
+// thread per unit).  Invalid cameras enter with x = y = w = 0, i.e. exact zeros are added — no
+// branch per camera, so the unrolled cameras interleave in the FP64 pipe.
+template <int CMAX>
+__device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX> &cams, const float4 (*obs)[32],
+                                                  int ul, uint32_t valid) {
+    sym4_zero(M);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        float4 o = obs[c][ul];
+        const bool v = (valid >> c) & 1u;
+        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; o.z = v ? o.z : 0.f;
+        accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)o.z);
+    }
+}
+
+// Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded
+// ones are dropped by a select: no branch, full instruction-level parallelism across cameras).
+template <int CMAX>
+__device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const float4 (*obs)[32], int ul,
+                                                    uint32_t valid, int m, double qx, double qy, double qz) {
+    double sum = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const float4 o = obs[c][ul];
+        const double dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
+        sum += ((valid >> c) & 1u) ? dist : 0.0;
+    }
+    return div_small(sum, (double)m);
+}
 
 template <int CMAX, int SOLVER>
 __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMAX> cams, const TriArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw)[warp];
+    double *sP = reinterpret_cast<double *>(smem_raw);                 // projection matrices for dynamic camera index
+    WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
 
     const int C = a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const long long n_tiles = (a.n_units + 31) >> 5;
 
-    // per-warp statistics, flushed once at the end
-    unsigned long long st_cands = 0, st_camsolves = 0, st_iters = 0;
-    unsigned int st_failed = 0, st_noeval = 0, st_band_thr = 0, st_band_arg = 0;
-    unsigned int st_level[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // levels >= 7 go straight to global
+    for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
+    if (lane < 4) S.st64[lane] = 0ULL;
+    if (lane < 12) S.st32[lane] = 0u;
+    __syncthreads();
 
     for (;;) {
         unsigned int tile = 0;
@@ -88,18 +126,16 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
         uint32_t nan0 = 0, inv0 = 0;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            if (c < C) {
-                float4 o = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f);
-                if (active) o = __ldg(a.obs + (long long)c * a.n_units + u);
-                S.obs[c][lane] = o;
-                const bool isn = o.z != o.z;
-                nan0 |= (uint32_t)isn << c;
-                inv0 |= (uint32_t)(isn || o.z == 0.f) << c;
-            }
+            float4 o = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f);
+            if (c < C && active) o = __ldg(a.obs + (long long)c * a.n_units + u);
+            S.obs[c][lane] = o;
+            const bool isn = o.z != o.z;
+            nan0 |= (uint32_t)isn << c;
+            inv0 |= (uint32_t)(isn || o.z == 0.f) << c;
         }
+        nan0 &= cmask; inv0 &= cmask;
         S.nan0[lane] = nan0;
         S.inv0[lane] = inv0;
-        __syncwarp();
 
         // ---- per-unit state (owner lane) -----------------------------------------------------
         double err_min = inf64();
@@ -108,25 +144,12 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
         int last_level = -1;
         bool band_thr = false, band_arg = false;
         const int ninv0 = __popc(inv0);
+        uint32_t t_cands = 0, t_cams = 0, t_iters = 0;      // per-tile work counters of this lane
 
-        // ---- level 0: thread per unit -----------------------------------------------------------
-        {
-            const bool go = active && (C >= a.min_cams) && !(ninv0 > C - a.min_cams);
-            if (go) {
-                double e;
-                auto fetch = [&](int c) -> float4 { return S.obs[c][lane]; };
-                int it = solve_subset<CMAX, SOLVER>(cams, fetch, C, cmask & ~inv0, qx, qy, qz, e);
-                err_min = e;
-                ids = nan0;
-                nexcl = (uint32_t)ninv0;
-                last_level = 0;
-                st_cands += 1; st_camsolves += (unsigned)(C - ninv0); st_iters += (unsigned)it;
-                band_thr |= fabs(e - a.thr) < a.band_eps;
-            }
-        }
-
-        // ---- levels k >= 1: lanes enumerate subsets ---------------------------------------------
-        for (int k = 1; k <= C; ++k) {
+        // ---- exclusion levels ------------------------------------------------------------------
+        // k = 0 has one candidate per unit: W = 1, thread per unit.  k >= 1: lanes enumerate subsets,
+        // W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units at a time.
+        for (int k = 0; k < C || k == 0; ++k) {
             // reference loop condition (:408) and break rule (:437-441) in closed form:
             // max_i |inv0 U cand_i| = min(C, |inv0| + k)
             const bool pend = active && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
@@ -134,31 +157,99 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
             const uint32_t pmask = __ballot_sync(P2S_FULL, pend);
             if (pmask == 0) break;
             const int npend = __popc(pmask);
-            const uint32_t ncand = (k <= a.max_table_level) ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
+            if (pend) S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
+            const uint32_t ncand = (k == 0) ? 1u : (k <= a.max_table_level) ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
             int W = 32;
             if (ncand <= 16) { W = 1; while ((uint32_t)W < ncand) W <<= 1; }
             const int G = 32 / W;
             const int grp = lane / W, sub = lane - grp * W;
             const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
+            const bool blocks = k > 0;                       // then W >= C: one lane per camera for the block pass
+            const bool subtract = 2 * k <= C;                // M = M_all - excluded blocks, else sum of the kept blocks
+            __syncwarp();
 
             for (int base = 0; base < npend; base += G) {
                 const int idx = base + grp;
                 const bool on = idx < npend;
-                const int ul = on ? (int)__fns(pmask, 0, idx + 1) : 0;     // owner lane of my unit
+                const int ul = on ? (int)S.plist[idx] : 0;                 // owner lane of my unit
                 const uint32_t u_nan0 = S.nan0[ul], u_inv0 = S.inv0[ul];
+
+                if (blocks) {
+                    // camera-parallel: lane `sub` builds the block of camera `sub` of its group's unit,
+                    // then the group's M_all (fixed ascending camera order => identical for every candidate)
+                    __syncwarp();
+                    if (on && sub < C) {
+                        float4 o = S.obs[sub][ul];
+                        const bool v = !((u_inv0 >> sub) & 1u);
+                        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; o.z = v ? o.z : 0.f;
+                        double b[10];
+                        camera_block(sP + sub * 12, (double)o.x, (double)o.y, (double)o.z, b);
+                        double2 *dst = reinterpret_cast<double2 *>(S.blk[grp * C + sub]);
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
+                    }
+                    __syncwarp();
+                    if (on) {
+                        for (int e = sub; e < 10; e += W) {
+                            double s = 0.0;
+                            for (int c = 0; c < C; ++c) s += S.blk[grp * C + c][e];
+                            S.mall[grp][e] = s;
+                        }
+                    }
+                    __syncwarp();
+                }
 
                 unsigned long long bkey = P2S_KEY_EMPTY, skey = P2S_KEY_EMPTY;
                 uint32_t bcand = 0xffffffffu, bnan = 0, bexcl = 0;
                 double bqx = nan64(), bqy = bqx, bqz = bqx;
                 if (on) {
                     for (uint32_t cand = (uint32_t)sub; cand < ncand; cand += (uint32_t)W) {
-                        const uint32_t cm = (k <= a.max_table_level) ? __ldg(table + cand) : unrank_subset(C, k, cand);
+                        const uint32_t cm = !blocks ? 0u : (k <= a.max_table_level) ? __ldg(table + cand) : unrank_subset(C, k, cand);
                         const uint32_t nanset = u_nan0 | cm;
                         const uint32_t invset = u_inv0 | cm;
+                        const uint32_t valid = cmask & ~invset;
+                        const int m = __popc(valid);
                         double cqx, cqy, cqz, e;
-                        auto fetch = [&](int c) -> float4 { return S.obs[c][ul]; };
-                        int it = solve_subset<CMAX, SOLVER>(cams, fetch, C, cmask & ~invset, cqx, cqy, cqz, e);
-                        st_cands += 1; st_camsolves += (unsigned)(C - __popc(invset)); st_iters += (unsigned)it;
+                        if (m < 2) {                          // common.py:351, :394-396 / mean of an empty list
+                            cqx = cqy = cqz = nan64();
+                            e = (m == 0) ? nan64() : inf64();
+                        } else {
+                            Sym4 M;
+                            if (!blocks) {
+                                accumulate_direct<CMAX>(M, cams, S.obs, ul, valid);
+                            } else {
+                                uint32_t bits;
+                                double sgn;
+                                if (subtract) {
+                                    const double2 *src = reinterpret_cast<const double2 *>(S.mall[grp]);
+                                    const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                    M.m00 = v0.x; M.m01 = v0.y; M.m02 = v1.x; M.m03 = v1.y; M.m11 = v2.x;
+                                    M.m12 = v2.y; M.m13 = v3.x; M.m22 = v3.y; M.m23 = v4.x; M.m33 = v4.y;
+                                    bits = cm & ~u_inv0 & cmask;
+                                    sgn = -1.0;
+                                } else {
+                                    sym4_zero(M);
+                                    bits = valid;
+                                    sgn = 1.0;
+                                }
+                                while (bits) {                // ascending camera order
+                                    const int c = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    const double2 *src = reinterpret_cast<const double2 *>(S.blk[grp * C + c]);
+                                    const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                    M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
+                                    M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
+                                    M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
+                                    M.m33 = fma(sgn, v4.y, M.m33);
+                                }
+                            }
+                            int it;
+                            if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
+                            else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
+                            e = mean_reproj_error<CMAX>(cams, S.obs, ul, valid, m, cqx, cqy, cqz);
+                            t_iters += (uint32_t)it;
+                        }
+                        t_cands += 1; t_cams += (uint32_t)m;
                         const unsigned long long key = err_key(e);
                         if (key < bkey) {                       // ascending cand per lane: strict < keeps the first
                             skey = bkey;
@@ -193,9 +284,8 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                     S.r_err[ul] = e;
                     S.r_qx[ul] = bqx; S.r_qy[ul] = bqy; S.r_qz[ul] = bqz;
                     S.r_nan[ul] = bnan;
-                    bool barg = false;
                     // runner-up among DISTINCT errors (duplicates of the winner are bitwise equal)
-                    barg = (key_err(skey) - e) < a.band_eps;              // NaN / inf compare false
+                    const bool barg = (key_err(skey) - e) < a.band_eps;   // NaN / inf compare false
                     S.r_flags[ul] = bexcl | (barg ? 0x100u : 0u);
                 }
             }
@@ -214,56 +304,53 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
         }
 
         // ---- finalise (:588-602) and write -------------------------------------------------------
+        const bool failed = active && (err_min > a.thr);
         if (active) {
             double e_out = err_min;
-            const bool failed = err_min > a.thr;
             if (failed) { e_out = nan64(); qx = qy = qz = nan64(); }
             double *q = a.out_Q + u * 3;
             q[0] = qx; q[1] = qy; q[2] = qz;
             a.out_err[u] = e_out;
             a.out_nexcl[u] = (uint8_t)nexcl;
             a.out_mask[u] = ids;
-            st_failed += failed ? 1u : 0u;
-            st_noeval += last_level < 0 ? 1u : 0u;
-            st_band_thr += band_thr ? 1u : 0u;
-            st_band_arg += band_arg ? 1u : 0u;
-            if (last_level >= 0) {
-                if (last_level < 7) {
+        }
+        // ---- per-tile statistics: warp-wide counts, lane 0 keeps the warp's totals in shared ----------
+        if (a.stats) {
+            const uint32_t s_c = __reduce_add_sync(P2S_FULL, t_cands);
+            const uint32_t s_m = __reduce_add_sync(P2S_FULL, t_cams);
+            const uint32_t s_i = __reduce_add_sync(P2S_FULL, t_iters);
+            const uint32_t n_fail = __popc(__ballot_sync(P2S_FULL, failed));
+            const uint32_t n_noev = __popc(__ballot_sync(P2S_FULL, active && last_level < 0));
+            const uint32_t n_bthr = __popc(__ballot_sync(P2S_FULL, active && band_thr));
+            const uint32_t n_barg = __popc(__ballot_sync(P2S_FULL, active && band_arg));
+            uint32_t hist = 0;
 #pragma unroll
-                    for (int l = 0; l < 7; ++l) st_level[l] += (last_level == l) ? 1u : 0u;
-                } else if (a.stats) {
-                    atomicAdd(a.stats + P2S_STAT_LEVEL0 + last_level, 1ULL);
-                }
+            for (int l = 0; l < 8; ++l) {
+                const uint32_t n = __popc(__ballot_sync(P2S_FULL, active && last_level == l));
+                if (lane == l) hist = n;
             }
+            if (lane < 8) S.st32[lane] += hist;
+            if (lane == 0) {
+                S.st64[0] += s_c; S.st64[1] += s_m; S.st64[2] += s_i;
+                S.st32[8] += n_fail; S.st32[9] += n_noev; S.st32[10] += n_bthr; S.st32[11] += n_barg;
+            }
+            if (active && last_level >= 8) atomicAdd(a.stats + P2S_STAT_LEVEL0 + last_level, 1ULL);
         }
         __syncwarp();
     }
 
-    // ---- flush statistics: warp-reduce, one atomic per counter per warp ---------------------------
+    // ---- flush statistics: one atomic per counter per warp ---------------------------------------------
     if (a.stats) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            st_cands += __shfl_xor_sync(P2S_FULL, st_cands, off);
-            st_camsolves += __shfl_xor_sync(P2S_FULL, st_camsolves, off);
-            st_iters += __shfl_xor_sync(P2S_FULL, st_iters, off);
-            st_failed += __shfl_xor_sync(P2S_FULL, st_failed, off);
-            st_noeval += __shfl_xor_sync(P2S_FULL, st_noeval, off);
-            st_band_thr += __shfl_xor_sync(P2S_FULL, st_band_thr, off);
-            st_band_arg += __shfl_xor_sync(P2S_FULL, st_band_arg, off);
-#pragma unroll
-            for (int l = 0; l < 7; ++l) st_level[l] += __shfl_xor_sync(P2S_FULL, st_level[l], off);
-        }
-        if (lane == 0) {
-            if (st_cands) atomicAdd(a.stats + P2S_STAT_CANDIDATES, st_cands);
-            if (st_camsolves) atomicAdd(a.stats + P2S_STAT_CAM_SOLVES, st_camsolves);
-            if (st_iters) atomicAdd(a.stats + P2S_STAT_NEWTON_STEPS, st_iters);
-            if (st_failed) atomicAdd(a.stats + P2S_STAT_FAILED, (unsigned long long)st_failed);
-            if (st_noeval) atomicAdd(a.stats + P2S_STAT_NOT_EVALUATED, (unsigned long long)st_noeval);
-            if (st_band_thr) atomicAdd(a.stats + P2S_STAT_BAND_THRESHOLD, (unsigned long long)st_band_thr);
-            if (st_band_arg) atomicAdd(a.stats + P2S_STAT_BAND_ARGMIN, (unsigned long long)st_band_arg);
-#pragma unroll
-            for (int l = 0; l < 7; ++l)
-                if (st_level[l]) atomicAdd(a.stats + P2S_STAT_LEVEL0 + l, (unsigned long long)st_level[l]);
+        __syncwarp();
+        if (lane < 8 && S.st32[lane]) atomicAdd(a.stats + P2S_STAT_LEVEL0 + lane, (unsigned long long)S.st32[lane]);
+        if (lane == 8) {
+            if (S.st64[0]) atomicAdd(a.stats + P2S_STAT_CANDIDATES, S.st64[0]);
+            if (S.st64[1]) atomicAdd(a.stats + P2S_STAT_CAM_SOLVES, S.st64[1]);
+            if (S.st64[2]) atomicAdd(a.stats + P2S_STAT_NEWTON_STEPS, S.st64[2]);
+            if (S.st32[8]) atomicAdd(a.stats + P2S_STAT_FAILED, (unsigned long long)S.st32[8]);
+            if (S.st32[9]) atomicAdd(a.stats + P2S_STAT_NOT_EVALUATED, (unsigned long long)S.st32[9]);
+            if (S.st32[10]) atomicAdd(a.stats + P2S_STAT_BAND_THRESHOLD, (unsigned long long)S.st32[10]);
+            if (S.st32[11]) atomicAdd(a.stats + P2S_STAT_BAND_ARGMIN, (unsigned long long)S.st32[11]);
         }
     }
 }
@@ -326,7 +413,7 @@ static cudaError_t launch_tri(const TriLaunch &L) {
     a.max_table_level = L.max_table_level;
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
-    const size_t smem = sizeof(WarpSlab<CMAX>) * 4;
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;
     cudaError_t e;
     if (L.solver == 0) {
         auto kern = triangulate_kernel<CMAX, 0>;
