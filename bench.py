@@ -36,14 +36,27 @@ WORKLOADS = {
                  name="cfg3 shard: synthetic 16 cams x Body_with_feet x 125k frames (1M/8), min_cameras=3"),
 }
 
-# FP64 operations the kernels execute per unit of work (DESIGN.md "Algorithmic work"); FMA = 2 flops.
-FLOPS_PER_CAM = 64 + 47          # normal-matrix rows + rank-1 updates, reprojection distance
-FLOPS_PER_SOLVER_STEP = 68       # one secular-Newton factorisation/solve
-FLOPS_PER_CANDIDATE = 1          # the mean
+# FP64 operations per unit of ALGORITHMIC work of the triangulation kernel (FMA = 2 flops,
+# MUFU seeds not counted).  The work items are counted by the kernel itself (statistics block), so the
+# figure follows the measured exclusion-level histogram instead of an assumed one.
+FLOPS = {
+    "direct_cams": 64,    # level 0: two weighted DLT rows (24) + two rank-1 updates of the 4x4 (40) per valid camera
+    "blocks": 54,         # levels >= 1: rows (24) + 10-entry block a a^T + b b^T (30) per valid camera, unit and level
+    "entry_adds": 1,      # levels >= 1: M_all and M_all -/+ excluded/kept blocks
+    "solver_steps": 70,   # one secular-Newton step: 3x3 LDL^T, two triangular solves, f, g, step
+    "solved": 21 + 11,    # first-order final update of q + the mean (reciprocal of m with one correction)
+    "cam_solves": 44,     # reprojection distance per valid camera: 3 dot-4, N, one refined rsqrt
+}
 
 
 def algorithmic_flops(st):
-    return FLOPS_PER_CAM * st["cam_solves"] + FLOPS_PER_SOLVER_STEP * st["solver_steps"] + FLOPS_PER_CANDIDATE * st["candidates"]
+    return sum(w * st[k] for k, w in FLOPS.items())
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` capture of this same command (profiles/): 332.9 MB read + 77.9 MB written on cfg2.
+NCU_TRAFFIC = {("cfg2", 1): 410.8e6}
+NCU_TRAFFIC_SOURCE = "profiles/r1c_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
@@ -215,7 +228,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pose2sim_b200 import ops, synth
+    from pose2sim_b200 import ops, sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU fallback (use --impl reference for the CPU arm)")
@@ -236,9 +249,8 @@ def main():
     obs = torch.empty((C, U, 4), dtype=torch.float32, device=dev)
     # per-unit outputs packed contiguously (Q | err | mask | nexcl = 37 B/unit) so that the final
     # gather is ONE NCCL call; two buffers alternate so the gather of step i overlaps step i+1
-    packs = [torch.empty(37 * U, dtype=torch.uint8, device=dev) for _ in range(2)]
-    outs = [{"Q": p[:24 * U].view(torch.float64).view(U, 3), "err": p[24 * U:32 * U].view(torch.float64),
-             "mask": p[32 * U:36 * U].view(torch.int32), "nexcl": p[36 * U:]} for p in packs]
+    packs = [torch.empty(sharding.PACK_BYTES * U, dtype=torch.uint8, device=dev) for _ in range(2)]
+    outs = [sharding.packed_views(p, U) for p in packs]
     out = outs[0]
     gather_lists = [[torch.empty_like(packs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     stats = eng.new_stats()
@@ -349,7 +361,9 @@ def main():
                        "failed_units": st["failed"], "eps_band_px": 1e-6,
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
             "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                         "traffic": None, "kernel": "triangulate_kernel<8,secular>" if C <= 8 else "triangulate_kernel",
+                         "traffic": NCU_TRAFFIC.get((args.workload, world)), "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "kernel": f"triangulate_kernel<{4 if C <= 4 else 8 if C <= 8 else 16 if C <= 16 else 32},secular>",
+                         "grid_ctas": eng.last_grid(),
                          "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "dependent-chain DFMA microbenchmark in this run (p2s_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",

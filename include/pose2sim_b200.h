@@ -60,6 +60,10 @@ enum {
     P2S_STAT_BAND_ARGMIN = 38,   /* units whose best and second-best DISTINCT candidate errors at
                                     an evaluated level differ by < eps                            */
     P2S_STAT_NEWTON_STEPS = 39,  /* eigen-solver iterations summed over candidates                */
+    P2S_STAT_SOLVED = 40,        /* candidates with >= 2 valid cameras (eigen-solve + reprojection)  */
+    P2S_STAT_DIRECT_CAMS = 41,   /* level 0: valid cameras accumulated straight into the normal matrix */
+    P2S_STAT_BLOCKS = 42,        /* levels >= 1: per-camera 4x4 blocks built (valid cameras x unit x level) */
+    P2S_STAT_ENTRY_ADDS = 43,    /* levels >= 1: FP64 additions forming M_all and M_all -/+ blocks     */
     P2S_STAT_COUNT = 48
 };
 
@@ -140,6 +144,9 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
 int p2s_measure_fp64_peak(p2s_handle *h, double *tflops, double *ms);
 /* Number of kernels this library launched through the handle since creation.                    */
 long long p2s_launch_count(const p2s_handle *h);
+/* Grid size (CTAs) of the last triangulation / association kernel launched through the handle:
+ * SM count x resident CTAs per SM for a persistent launch (occupancy evidence for the profiles). */
+int p2s_last_grid(const p2s_handle *h);
 
 #ifdef __cplusplus
 }

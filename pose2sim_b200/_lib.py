@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2s_b200.so")
+# P2S_LIB: another build of the same library (kernel A/B experiments, tools/kernel_ab.py)
+LIB_PATH = os.environ.get("P2S_LIB") or os.path.join(_HERE, "libp2s_b200.so")
 
 P2S_MAX_CAMS = 32
 P2S_MAX_PERSONS = 16
@@ -21,6 +22,10 @@ STAT_CAM_SOLVES = 36
 STAT_BAND_THRESHOLD = 37
 STAT_BAND_ARGMIN = 38
 STAT_NEWTON_STEPS = 39
+STAT_SOLVED = 40
+STAT_DIRECT_CAMS = 41
+STAT_BLOCKS = 42
+STAT_ENTRY_ADDS = 43
 
 STATUS = {0: "P2S_OK", 1: "P2S_EINVAL", 2: "P2S_ENODEVICE", 3: "P2S_ECUDA", 4: "P2S_ENOMEM", 5: "P2S_ETOODEEP"}
 
@@ -55,6 +60,7 @@ SIGNATURES = {
     "p2s_associate_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "p2s_measure_fp64_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "p2s_launch_count": (_ll, [_vp]),
+    "p2s_last_grid": (_i, [_vp]),
 }
 
 _lib = None

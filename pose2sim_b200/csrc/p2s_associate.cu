@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
 }
 
 template <int CMAX>
-static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0) {
+static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0, int *grid_out) {
     CamParams<CMAX> cams;
     for (int c = 0; c < CMAX; ++c)
         for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
@@ -225,11 +225,12 @@ static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0) {
     long long grid = (long long)L.sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
     kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_associate(const AssocLaunch &L) {
+cudaError_t launch_associate(const AssocLaunch &L, int *grid_out) {
     AssocArgs a;
     a.obs = (const float4 *)L.obs; a.count = L.count; a.n_frames = L.n_frames;
     a.n_cams = L.n_cams; a.max_persons = L.max_persons; a.min_cams = L.min_cams;
@@ -238,10 +239,10 @@ cudaError_t launch_associate(const AssocLaunch &L) {
     a.max_table_level = L.max_table_level;
     a.out_err = L.out_err; a.out_comb = L.out_comb; a.out_Q = L.out_Q; a.out_stats = L.out_stats;
     a.tile_counter = L.tile_counter;
-    if (L.n_cams <= 4) return launch_assoc<4>(L, a);
-    if (L.n_cams <= 8) return launch_assoc<8>(L, a);
-    if (L.n_cams <= 16) return launch_assoc<16>(L, a);
-    return launch_assoc<32>(L, a);
+    if (L.n_cams <= 4) return launch_assoc<4>(L, a, grid_out);
+    if (L.n_cams <= 8) return launch_assoc<8>(L, a, grid_out);
+    if (L.n_cams <= 16) return launch_assoc<16>(L, a, grid_out);
+    return launch_assoc<32>(L, a, grid_out);
 }
 
 }  // namespace p2s

@@ -40,6 +40,7 @@ struct p2s_handle {
     double band_eps = 1e-6;
     int solver = 0;
     long long launches = 0;
+    int last_grid = 0;
     std::string last_error;
     SubsetTable tables[P2S_MAX_CAMS + 1];
     Slot slots[kSlots];
@@ -145,7 +146,7 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, long lo
     L.tile_counter = next_counter(h);
     L.stream = stream;
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
-    P2S_CUDA(h, p2s::launch_triangulate(L));
+    P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
     h->launches += 1;
     return P2S_OK;
 }
@@ -168,7 +169,7 @@ int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, cons
     L.tile_counter = next_counter(h);
     L.stream = stream;
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
-    P2S_CUDA(h, p2s::launch_associate(L));
+    P2S_CUDA(h, p2s::launch_associate(L, &h->last_grid));
     h->launches += 1;
     return P2S_OK;
 }
@@ -400,5 +401,7 @@ int p2s_measure_fp64_peak(p2s_handle *h, double *tflops, double *ms_out) {
 }
 
 long long p2s_launch_count(const p2s_handle *h) { return h ? h->launches : 0; }
+
+int p2s_last_grid(const p2s_handle *h) { return h ? h->last_grid : 0; }
 
 }  // extern "C"

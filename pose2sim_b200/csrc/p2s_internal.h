@@ -41,10 +41,10 @@ struct AssocLaunch {
     cudaStream_t stream;
 };
 
-cudaError_t launch_triangulate(const TriLaunch &L);
+cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out);
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
                          double lik_thr, void *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
-cudaError_t launch_associate(const AssocLaunch &L);
+cudaError_t launch_associate(const AssocLaunch &L, int *grid_out);
 
 }  // namespace p2s

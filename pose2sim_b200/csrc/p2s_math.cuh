@@ -118,8 +118,8 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
         const double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
         const double dl = f * rcp_fast(g);
         if (f > 0.0) lo = lam;
-        const double dmin = fmin(a00, fmin(d1, d2));
-        if (fabs(dl) <= 1e-8 * dmin) {                       // converged: first-order update, no refactorisation
+        // converged when |dl| ||(A - lam I)^-1|| is tiny; r0 + r1 + r2 bounds the largest reciprocal pivot
+        if (fabs(dl) * (r0 + r1 + r2) <= 1e-8) {             // -> first-order update, no refactorisation
             const double y1 = fma(-l10, x0, x1);
             const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
             const double w2 = y2 * r2;

@@ -48,14 +48,20 @@ struct TriArgs {
     unsigned int *tile_counter;
 };
 
+#ifndef P2S_TRI_MIN_BLOCKS
+#define P2S_TRI_MIN_BLOCKS 4        /* 4 vs 5 resident CTAs per SM measured equal (tools/kernel_ab.py); 4 has no spills */
+#endif
+
 template <int CMAX>
 struct WarpSlab {                 // per-warp shared memory
     float4 obs[CMAX][32];         // staged observations of the tile
-    double blk[32][10];           // camera blocks of the current group pass, slot = group * C + camera
+    double blk[32 * 10 + 32];     // camera blocks of the current group pass: block (group, camera) at
+                                  // group * (10 C + 2) + 10 camera (the +2 staggers the groups over the banks)
     double mall[16][10];          // per group: sum of the unit's valid camera blocks
     double r_err[32];             // level results published by the winning lane of each unit
     double r_qx[32], r_qy[32], r_qz[32];
-    unsigned long long st64[4];   // per-warp statistics: candidates, camera-solves, solver steps
+    unsigned long long st64[8];   // per-warp statistics: candidates, camera-solves, solver steps, solved,
+                                  // direct cameras, blocks, entry additions
     uint32_t st32[12];            // level histogram [0..7], failed, not evaluated, threshold band, arg-min band
     uint32_t r_nan[32];           // NaN-camera set of the winner (id_excluded_cams)
     uint32_t r_flags[32];         // bit0..7: excl count, bit 8: argmin band hit
@@ -96,7 +102,7 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 }
 
 template <int CMAX, int SOLVER>
-__global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMAX> cams, const TriArgs a) {
+__global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams, const TriArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
     const long long n_tiles = (a.n_units + 31) >> 5;
 
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
-    if (lane < 4) S.st64[lane] = 0ULL;
+    if (lane < 8) S.st64[lane] = 0ULL;
     if (lane < 12) S.st32[lane] = 0u;
     __syncthreads();
 
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
         bool band_thr = false, band_arg = false;
         const int ninv0 = __popc(inv0);
         uint32_t t_cands = 0, t_cams = 0, t_iters = 0;      // per-tile work counters of this lane
+        uint32_t t_solved = 0, t_direct = 0, t_blocks = 0, t_adds = 0;
 
         // ---- exclusion levels ------------------------------------------------------------------
         // k = 0 has one candidate per unit: W = 1, thread per unit.  k >= 1: lanes enumerate subsets,
@@ -163,8 +170,10 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
             if (ncand <= 16) { W = 1; while ((uint32_t)W < ncand) W <<= 1; }
             const int G = 32 / W;
             const int grp = lane / W, sub = lane - grp * W;
+            const uint32_t gmask = (W == 32) ? P2S_FULL : (((1u << W) - 1u) << (grp * W));
             const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
             const bool blocks = k > 0;                       // then W >= C: one lane per camera for the block pass
+            double *gblk = S.blk + grp * (C * 10 + 2);
             const bool subtract = 2 * k <= C;                // M = M_all - excluded blocks, else sum of the kept blocks
             __syncwarp();
 
@@ -184,7 +193,8 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                         o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; o.z = v ? o.z : 0.f;
                         double b[10];
                         camera_block(sP + sub * 12, (double)o.x, (double)o.y, (double)o.z, b);
-                        double2 *dst = reinterpret_cast<double2 *>(S.blk[grp * C + sub]);
+                        t_blocks += v ? 1u : 0u;
+                        double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
 #pragma unroll
                         for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
                     }
@@ -192,8 +202,9 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                     if (on) {
                         for (int e = sub; e < 10; e += W) {
                             double s = 0.0;
-                            for (int c = 0; c < C; ++c) s += S.blk[grp * C + c][e];
+                            for (int c = 0; c < C; ++c) s += gblk[c * 10 + e];
                             S.mall[grp][e] = s;
+                            t_adds += (uint32_t)C;
                         }
                     }
                     __syncwarp();
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                             Sym4 M;
                             if (!blocks) {
                                 accumulate_direct<CMAX>(M, cams, S.obs, ul, valid);
+                                t_direct += (uint32_t)m;
                             } else {
                                 uint32_t bits;
                                 double sgn;
@@ -232,10 +244,11 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                                     bits = valid;
                                     sgn = 1.0;
                                 }
+                                t_adds += 10u * (uint32_t)__popc(bits);
                                 while (bits) {                // ascending camera order
                                     const int c = __ffs(bits) - 1;
                                     bits &= bits - 1;
-                                    const double2 *src = reinterpret_cast<const double2 *>(S.blk[grp * C + c]);
+                                    const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
                                     const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
                                     M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
                                     M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
@@ -248,6 +261,7 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
                             e = mean_reproj_error<CMAX>(cams, S.obs, ul, valid, m, cqx, cqy, cqz);
                             t_iters += (uint32_t)it;
+                            t_solved += 1u;
                         }
                         t_cands += 1; t_cams += (uint32_t)m;
                         const unsigned long long key = err_key(e);
@@ -260,25 +274,26 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
                         }
                     }
                 }
-                // ---- (error, index) arg-min + runner-up across the W lanes of the group -------------
-                for (int off = W >> 1; off > 0; off >>= 1) {
-                    const unsigned long long okey = __shfl_xor_sync(P2S_FULL, bkey, off);
-                    const unsigned long long oskey = __shfl_xor_sync(P2S_FULL, skey, off);
-                    const uint32_t ocand = __shfl_xor_sync(P2S_FULL, bcand, off);
-                    const bool take = (okey < bkey) || (okey == bkey && ocand < bcand);
-                    // runner-up: smallest key strictly above the new best
-                    const unsigned long long nb = take ? okey : bkey;
-                    unsigned long long ns = P2S_KEY_EMPTY;
-                    if (bkey > nb && bkey < ns) ns = bkey;
-                    if (okey > nb && okey < ns) ns = okey;
-                    if (skey > nb && skey < ns) ns = skey;
-                    if (oskey > nb && oskey < ns) ns = oskey;
-                    skey = ns;
-                    bkey = nb;
-                    bcand = take ? ocand : bcand;
+                // ---- (error, index) arg-min + runner-up across the W lanes of the group: redux.sync ------
+                // keys are 64-bit: min of the high words, then min of the low words among the lanes that
+                // hold that high word; ties go to the smallest candidate index (np.nanargmin's first index)
+                if (W > 1) {
+                    const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
+                    const uint32_t mh = __reduce_min_sync(gmask, hi);
+                    const uint32_t ml = __reduce_min_sync(gmask, hi == mh ? lo : 0xffffffffu);
+                    const bool is_min = (hi == mh) && (lo == ml);
+                    const uint32_t mc = __reduce_min_sync(gmask, is_min ? bcand : 0xffffffffu);
+                    // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
+                    const unsigned long long rk = is_min ? skey : bkey;
+                    const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
+                    const uint32_t sh = __reduce_min_sync(gmask, rh);
+                    const uint32_t sl = __reduce_min_sync(gmask, rh == sh ? rl : 0xffffffffu);
+                    bkey = ((unsigned long long)mh << 32) | ml;
+                    skey = ((unsigned long long)sh << 32) | sl;
+                    bcand = mc;
                 }
-                // after the butterfly every lane of the group knows (bkey, bcand); the lane that
-                // evaluated bcand (sub == bcand % W) still holds its Q / masks
+                // every lane of the group now knows (bkey, bcand); the lane that evaluated bcand
+                // (sub == bcand % W) still holds its Q / masks
                 if (on && bcand != 0xffffffffu && (uint32_t)sub == (bcand & (uint32_t)(W - 1))) {
                     const double e = key_err(bkey);
                     S.r_err[ul] = e;
@@ -319,6 +334,10 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
             const uint32_t s_c = __reduce_add_sync(P2S_FULL, t_cands);
             const uint32_t s_m = __reduce_add_sync(P2S_FULL, t_cams);
             const uint32_t s_i = __reduce_add_sync(P2S_FULL, t_iters);
+            const uint32_t s_s = __reduce_add_sync(P2S_FULL, t_solved);
+            const uint32_t s_d = __reduce_add_sync(P2S_FULL, t_direct);
+            const uint32_t s_b = __reduce_add_sync(P2S_FULL, t_blocks);
+            const uint32_t s_a = __reduce_add_sync(P2S_FULL, t_adds);
             const uint32_t n_fail = __popc(__ballot_sync(P2S_FULL, failed));
             const uint32_t n_noev = __popc(__ballot_sync(P2S_FULL, active && last_level < 0));
             const uint32_t n_bthr = __popc(__ballot_sync(P2S_FULL, active && band_thr));
@@ -331,7 +350,8 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
             }
             if (lane < 8) S.st32[lane] += hist;
             if (lane == 0) {
-                S.st64[0] += s_c; S.st64[1] += s_m; S.st64[2] += s_i;
+                S.st64[0] += s_c; S.st64[1] += s_m; S.st64[2] += s_i; S.st64[3] += s_s;
+                S.st64[4] += s_d; S.st64[5] += s_b; S.st64[6] += s_a;
                 S.st32[8] += n_fail; S.st32[9] += n_noev; S.st32[10] += n_bthr; S.st32[11] += n_barg;
             }
             if (active && last_level >= 8) atomicAdd(a.stats + P2S_STAT_LEVEL0 + last_level, 1ULL);
@@ -347,6 +367,10 @@ __global__ void __launch_bounds__(128, 4) triangulate_kernel(const CamParams<CMA
             if (S.st64[0]) atomicAdd(a.stats + P2S_STAT_CANDIDATES, S.st64[0]);
             if (S.st64[1]) atomicAdd(a.stats + P2S_STAT_CAM_SOLVES, S.st64[1]);
             if (S.st64[2]) atomicAdd(a.stats + P2S_STAT_NEWTON_STEPS, S.st64[2]);
+            if (S.st64[3]) atomicAdd(a.stats + P2S_STAT_SOLVED, S.st64[3]);
+            if (S.st64[4]) atomicAdd(a.stats + P2S_STAT_DIRECT_CAMS, S.st64[4]);
+            if (S.st64[5]) atomicAdd(a.stats + P2S_STAT_BLOCKS, S.st64[5]);
+            if (S.st64[6]) atomicAdd(a.stats + P2S_STAT_ENTRY_ADDS, S.st64[6]);
             if (S.st32[8]) atomicAdd(a.stats + P2S_STAT_FAILED, (unsigned long long)S.st32[8]);
             if (S.st32[9]) atomicAdd(a.stats + P2S_STAT_NOT_EVALUATED, (unsigned long long)S.st32[9]);
             if (S.st32[10]) atomicAdd(a.stats + P2S_STAT_BAND_THRESHOLD, (unsigned long long)S.st32[10]);
@@ -402,7 +426,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 
 // ---- host-side launchers ----------------------------------------------------------------------------
 template <int CMAX>
-static cudaError_t launch_tri(const TriLaunch &L) {
+static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     CamParams<CMAX> cams;
     for (int c = 0; c < CMAX; ++c)
         for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
@@ -419,6 +443,8 @@ static cudaError_t launch_tri(const TriLaunch &L) {
         auto kern = triangulate_kernel<CMAX, 0>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         if (e != cudaSuccess) return e;
@@ -427,11 +453,14 @@ static cudaError_t launch_tri(const TriLaunch &L) {
         long long grid = (long long)L.sm_count * per_sm;
         if (grid > want) grid = want;
         if (grid < 1) grid = 1;
+        if (grid_out) *grid_out = (int)grid;
         kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
     } else {
         auto kern = triangulate_kernel<CMAX, 1>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         if (e != cudaSuccess) return e;
@@ -440,16 +469,17 @@ static cudaError_t launch_tri(const TriLaunch &L) {
         long long grid = (long long)L.sm_count * per_sm;
         if (grid > want) grid = want;
         if (grid < 1) grid = 1;
+        if (grid_out) *grid_out = (int)grid;
         kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_triangulate(const TriLaunch &L) {
-    if (L.n_cams <= 4) return launch_tri<4>(L);
-    if (L.n_cams <= 8) return launch_tri<8>(L);
-    if (L.n_cams <= 16) return launch_tri<16>(L);
-    return launch_tri<32>(L);
+cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
+    if (L.n_cams <= 4) return launch_tri<4>(L, grid_out);
+    if (L.n_cams <= 8) return launch_tri<8>(L, grid_out);
+    if (L.n_cams <= 16) return launch_tri<16>(L, grid_out);
+    return launch_tri<32>(L, grid_out);
 }
 
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,

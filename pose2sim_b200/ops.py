@@ -49,7 +49,8 @@ def stats_dict(stats):
     return {"level_hist": levels, "not_evaluated": s[_lib.STAT_NOT_EVALUATED], "failed": s[_lib.STAT_FAILED],
             "candidates": s[_lib.STAT_CANDIDATES], "cam_solves": s[_lib.STAT_CAM_SOLVES],
             "band_threshold": s[_lib.STAT_BAND_THRESHOLD], "band_argmin": s[_lib.STAT_BAND_ARGMIN],
-            "solver_steps": s[_lib.STAT_NEWTON_STEPS]}
+            "solver_steps": s[_lib.STAT_NEWTON_STEPS], "solved": s[_lib.STAT_SOLVED],
+            "direct_cams": s[_lib.STAT_DIRECT_CAMS], "blocks": s[_lib.STAT_BLOCKS], "entry_adds": s[_lib.STAT_ENTRY_ADDS]}
 
 
 class Engine:
@@ -78,6 +79,9 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.p2s_launch_count(self.h))
+
+    def last_grid(self):
+        return int(self.lib.p2s_last_grid(self.h))
 
     def fp64_peak(self):
         tf, ms = C.c_double(), C.c_double()
