@@ -24,6 +24,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+JSON_OUT = sys.stdout
 METRIC = "keypoint triangulations/sec w/ exclusion search"
 UNIT = "triangulations/s"
 
@@ -202,10 +203,19 @@ def run_reference_arm(args, cfg, rank, world):
                                         "what": "plain-C restatement (one-sided Jacobi SVD), OpenMP"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Route fd 1 to stderr for the duration of the run (NCCL and torch print banners on stdout) and
+    return a file object on the ORIGINAL stdout for the one JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +225,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global JSON_OUT
+    JSON_OUT = _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = WORKLOADS[args.workload]
 
@@ -392,7 +404,7 @@ def main():
                                               f"triangulation_from_best_cameras (oracle/p2s_oracle.py), one process per core",
                                     "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
                                                "what": "plain-C restatement (oracle/p2s_oracle.c), OpenMP"}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

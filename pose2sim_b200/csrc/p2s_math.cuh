@@ -84,11 +84,17 @@ __device__ __forceinline__ void accumulate_camera(Sym4 &M, const double *Pc, dou
 }
 
 // Smallest eigenvector of M, de-homogenised: safeguarded Newton on the secular equation.
-// (Newton on f is Rayleigh-quotient iteration for v = (q, 1): lam + f/g is the Rayleigh quotient of
-// the current v, so convergence is cubic.)  When the step dl is already tiny against the smallest
-// pivot, q(lam + dl) is obtained from the factorisation at hand by the first-order update
-// q += dl (A - lam I)^-1 q   [d q/d lam = (A - lam I)^-1 q],  error O((dl/dmin)^2) <= 1e-16 |q|,
-// instead of paying one more factorisation just to confirm.  Returns the factorisations used.
+//
+// Newton on f is Rayleigh-quotient iteration for v = (q, 1): lam + f/g is the Rayleigh quotient of the
+// current v, so convergence is cubic.  Two refinements keep the number of 3x3 factorisations near two:
+//   * chord step (first factorisation only): with w = (A - lam I)^-1 q = dq/dlam from the factors at
+//     hand, q~ = q + dl w solves (A - lam - dl) q~ = -b up to the residual r = -dl^2 w, and the exact
+//     Rayleigh quotient of (q~, 1) is lam + dl + (f~ - dl^2 q~.w) / (1 + |q~|^2); its error is the
+//     square of q~'s, i.e. O((dl/dmin)^4), so the SECOND factorisation already sits at the root to
+//     ~1e-8 relative for any candidate whose cameras roughly agree;
+//   * final step: once |dl| ||(A - lam I)^-1|| <= 1e-8, q(lam + dl) = q + dl w to O(1e-16), so no
+//     factorisation is spent on confirming convergence.
+// Returns the number of factorisations used.
 __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
     double lam = 0.0, lo = 0.0;
     double x0 = nan64(), x1 = x0, x2 = x0;
@@ -118,16 +124,27 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
         const double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
         const double dl = f * rcp_fast(g);
         if (f > 0.0) lo = lam;
-        // converged when |dl| ||(A - lam I)^-1|| is tiny; r0 + r1 + r2 bounds the largest reciprocal pivot
-        if (fabs(dl) * (r0 + r1 + r2) <= 1e-8) {             // -> first-order update, no refactorisation
-            const double y1 = fma(-l10, x0, x1);
-            const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
-            const double w2 = y2 * r2;
-            const double w1 = fma(-l21, w2, y1 * r1);
-            const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
-            x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);
-            ++it;
-            break;
+        // w = (A - lam I)^-1 q from the factors at hand
+        const double y1 = fma(-l10, x0, x1);
+        const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
+        const double w2 = y2 * r2;
+        const double w1 = fma(-l21, w2, y1 * r1);
+        const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
+        const bool done = fabs(dl) * (r0 + r1 + r2) <= 1e-8;
+#ifdef P2S_NO_CHORD                                         /* A/B switch, tools/kernel_ab.py */
+        if (done) {
+#else
+        if (done || it == 0) {
+#endif
+            x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);      // q(lam + dl), first order
+            if (done) { ++it; break; }
+            // chord step: Rayleigh quotient of (q~, 1)
+            const double lam1 = lam + dl;
+            const double f1 = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - lam1)));
+            const double g1 = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
+            const double qw = fma(x0, w0, fma(x1, w1, x2 * w2));
+            lam = lam1 + fma(-dl * dl, qw, f1) * rcp_fast(g1);
+            continue;
         }
         lam += dl;
     }
