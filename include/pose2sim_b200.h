@@ -138,6 +138,21 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
                        double reproj_thr, double lik_thr, int min_cams,
                        double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats);
 
+/* ---- host staging: OpenPose JSON -> observation planes (no GPU involved) --------------------- *
+ * Replaces the file handling of triangulation.py:607-653 extract_files_frame_f (+ :77-90
+ * count_persons_in_json): every file is parsed ONCE, on `n_threads` host threads (<= 0: all cores).
+ * paths      : n_frames x n_cams C strings, frame-major ("" or unreadable / unparsable => NaN)
+ * keypoint_ids: n_keypoints OpenPose ids (skeleton pre-order); value = pose_keypoints_2d[3 id : 3 id + 3]
+ * x, y, lik  : float32 [n_frames][n_persons][n_keypoints][n_cams] — the unit-major, camera-fastest
+ *              layout p2s_triangulate_host takes; NaN wherever the reference's lookup would raise
+ * n_people   : int32 [n_frames][n_cams] len(people) of each file (-1: unparsable), or NULL
+ * status     : uint8 [n_frames][n_cams] 1 = parsed, or NULL
+ * n_inexact  : number of finite values that float32 cannot represent exactly, or NULL            */
+int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams,
+                        const int32_t *keypoint_ids, int n_keypoints, int n_persons,
+                        float *x, float *y, float *lik, int32_t *n_people, uint8_t *status,
+                        long long *n_inexact, int n_threads);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Dependent-chain FP64 FMA microbenchmark on the handle's device: achieved DFMA TFLOP/s
  * (2 flops per FMA) — the FP64 roofline denominator MEASURED_PEAKS.json does not carry.         */

@@ -1,0 +1,335 @@
+// Host staging: OpenPose-format JSON files -> packed float32 observation planes, multi-threaded.
+//
+// Replaces the per-frame / per-person file handling of the reference
+//   Pose2Sim/triangulation.py:607-653  extract_files_frame_f   (re-opens every file once per person)
+//   Pose2Sim/triangulation.py:77-90    count_persons_in_json
+// with ONE parse per file.  The value taken for (person n, keypoint id) is what
+// `js['people'][n]['pose_keypoints_2d'][3*id : 3*id+3]` yields in Python; anything that would raise
+// there (missing / unparsable file, person or key absent, list too short, non-numeric entry) is a NaN
+// triple, like the reference's bare `except:` (:629-644).
+//
+// The parser validates the WHOLE document with the grammar Python's `json.load` accepts (RFC 8259 plus
+// the NaN / Infinity / -Infinity literals; duplicate keys: the last one wins), because a syntax error
+// anywhere makes `json.load` raise and the reference then treats the file as missing.
+#include <atomic>
+#include <cctype>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pose2sim_b200.h"
+
+namespace {
+
+struct Person {
+    bool is_object = false;
+    bool has_keypoints = false;      // key present and its value is an array
+    bool bad_entry = false;          // an array element that float() would reject (string, array, object)
+    std::vector<double> kp;
+};
+
+struct Doc {
+    bool has_people = false;         // top level is an object with a "people" array
+    std::vector<Person> people;
+};
+
+class Parser {
+  public:
+    Parser(const char *b, const char *e) : p_(b), end_(e) {}
+
+    bool parse(Doc &doc) {
+        ws();
+        if (!top(doc)) return false;
+        ws();
+        return p_ == end_;           // trailing data is an error in json.load
+    }
+
+  private:
+    const char *p_, *end_;
+    int depth_ = 0;
+
+    void ws() { while (p_ < end_ && (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r')) ++p_; }
+    bool lit(const char *s) {
+        const size_t n = std::strlen(s);
+        if ((size_t)(end_ - p_) < n || std::memcmp(p_, s, n) != 0) return false;
+        p_ += n;
+        return true;
+    }
+
+    bool string(std::string *out) {
+        if (p_ >= end_ || *p_ != '"') return false;
+        ++p_;
+        while (p_ < end_) {
+            const unsigned char c = (unsigned char)*p_;
+            if (c == '"') { ++p_; return true; }
+            if (c < 0x20) return false;                          // control characters are rejected (strict mode)
+            if (c == '\\') {
+                if (++p_ >= end_) return false;
+                const char e = *p_;
+                if (e == 'u') {
+                    if (end_ - p_ < 5) return false;
+                    for (int i = 1; i <= 4; ++i) if (!std::isxdigit((unsigned char)p_[i])) return false;
+                    if (out) out->push_back('?');                // keys of interest are ASCII
+                    p_ += 5;
+                    continue;
+                }
+                if (!std::strchr("\"\\/bfnrt", e)) return false;
+                if (out) out->push_back(e == 'n' ? '\n' : e == 't' ? '\t' : e);
+                ++p_;
+                continue;
+            }
+            if (out) out->push_back((char)c);
+            ++p_;
+        }
+        return false;
+    }
+
+    // JSON number grammar: -?(0|[1-9]\d*)(\.\d+)?([eE][-+]?\d+)?
+    bool number(double *out) {
+        const char *s = p_;
+        if (p_ < end_ && *p_ == '-') ++p_;
+        if (p_ >= end_) return false;
+        if (*p_ == '0') ++p_;
+        else if (*p_ >= '1' && *p_ <= '9') { while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_; }
+        else return false;
+        if (p_ < end_ && *p_ == '.') {
+            ++p_;
+            if (p_ >= end_ || *p_ < '0' || *p_ > '9') return false;
+            while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+        }
+        if (p_ < end_ && (*p_ == 'e' || *p_ == 'E')) {
+            ++p_;
+            if (p_ < end_ && (*p_ == '+' || *p_ == '-')) ++p_;
+            if (p_ >= end_ || *p_ < '0' || *p_ > '9') return false;
+            while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+        }
+        if (out) {
+            double v = 0.0;
+            auto r = std::from_chars(s, p_, v);                  // correctly rounded, locale independent
+            if (r.ec == std::errc::result_out_of_range) {        // overflow -> +-inf, underflow -> +-0 / denormal, like float()
+                const std::string tok(s, p_);
+                v = std::strtod(tok.c_str(), nullptr);
+            }
+            else if (r.ec != std::errc()) return false;
+            *out = v;
+        }
+        return true;
+    }
+
+    // scalar-or-container; when `num` is given and the value is numeric-like, *num receives what
+    // numpy's float conversion would give (true -> 1, false -> 0, null -> NaN) and *is_num = true
+    bool value(double *num, bool *is_num) {
+        if (is_num) *is_num = false;
+        ws();
+        if (p_ >= end_) return false;
+        const char c = *p_;
+        if (c == '{') return object(nullptr, nullptr);
+        if (c == '[') return array_skip();
+        if (c == '"') return string(nullptr);
+        double v;
+        bool ok;
+        if (c == 't') { ok = lit("true"); v = 1.0; }
+        else if (c == 'f') { ok = lit("false"); v = 0.0; }
+        else if (c == 'n') { ok = lit("null"); v = std::numeric_limits<double>::quiet_NaN(); }
+        else if (c == 'N') { ok = lit("NaN"); v = std::numeric_limits<double>::quiet_NaN(); }
+        else if (c == 'I') { ok = lit("Infinity"); v = HUGE_VAL; }
+        else if (c == '-' && p_ + 1 < end_ && p_[1] == 'I') { ok = lit("-Infinity"); v = -HUGE_VAL; }
+        else ok = number(&v);
+        if (!ok) return false;
+        if (num) *num = v;
+        if (is_num) *is_num = true;
+        return true;
+    }
+
+    bool array_skip() {
+        if (++depth_ > 512) return false;
+        ++p_;
+        ws();
+        if (p_ < end_ && *p_ == ']') { ++p_; --depth_; return true; }
+        for (;;) {
+            if (!value(nullptr, nullptr)) return false;
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == ']') { ++p_; --depth_; return true; }
+            return false;
+        }
+    }
+
+    bool number_array(Person &person) {
+        person.kp.clear();
+        person.bad_entry = false;
+        ++p_;
+        ws();
+        if (p_ < end_ && *p_ == ']') { ++p_; return true; }
+        for (;;) {
+            double v;
+            bool is_num;
+            if (!value(&v, &is_num)) return false;
+            if (is_num) person.kp.push_back(v);
+            else { person.bad_entry = true; person.kp.push_back(std::numeric_limits<double>::quiet_NaN()); }
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == ']') { ++p_; return true; }
+            return false;
+        }
+    }
+
+    // generic object; `person` != null: capture "pose_keypoints_2d"; `doc` != null: capture "people"
+    bool object(Person *person, Doc *doc) {
+        if (++depth_ > 512) return false;
+        ++p_;
+        ws();
+        if (p_ < end_ && *p_ == '}') { ++p_; --depth_; return true; }
+        std::string key;
+        for (;;) {
+            ws();
+            key.clear();
+            if (!string(&key)) return false;
+            ws();
+            if (p_ >= end_ || *p_ != ':') return false;
+            ++p_;
+            ws();
+            if (person && key == "pose_keypoints_2d") {
+                if (p_ < end_ && *p_ == '[') {
+                    person->has_keypoints = true;
+                    if (!number_array(*person)) return false;
+                } else {                                         // not a list: indexing it raises in Python
+                    person->has_keypoints = false;
+                    person->kp.clear();
+                    if (!value(nullptr, nullptr)) return false;
+                }
+            } else if (doc && key == "people") {
+                doc->people.clear();
+                if (p_ < end_ && *p_ == '[') {
+                    doc->has_people = true;
+                    if (!people_array(*doc)) return false;
+                } else {
+                    doc->has_people = false;
+                    if (!value(nullptr, nullptr)) return false;
+                }
+            } else if (!value(nullptr, nullptr)) {
+                return false;
+            }
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == '}') { ++p_; --depth_; return true; }
+            return false;
+        }
+    }
+
+    bool people_array(Doc &doc) {
+        ++p_;
+        ws();
+        if (p_ < end_ && *p_ == ']') { ++p_; return true; }
+        for (;;) {
+            ws();
+            doc.people.emplace_back();
+            Person &person = doc.people.back();
+            if (p_ < end_ && *p_ == '{') {
+                person.is_object = true;
+                if (!object(&person, nullptr)) return false;
+            } else if (!value(nullptr, nullptr)) {
+                return false;
+            }
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == ']') { ++p_; return true; }
+            return false;
+        }
+    }
+
+    bool top(Doc &doc) {
+        if (p_ < end_ && *p_ == '{') return object(nullptr, &doc);
+        return value(nullptr, nullptr);
+    }
+};
+
+bool read_file(const char *path, std::string &buf) {
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return false;
+    buf.clear();
+    char tmp[1 << 16];
+    size_t n;
+    while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, n);
+    const bool ok = !std::ferror(f);
+    std::fclose(f);
+    return ok;
+}
+
+}  // namespace
+
+extern "C" int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams,
+                                   const int32_t *keypoint_ids, int n_keypoints, int n_persons,
+                                   float *x, float *y, float *lik, int32_t *n_people, uint8_t *status,
+                                   long long *n_inexact, int n_threads) {
+    if (!paths || n_frames < 0 || n_cams < 1 || n_keypoints < 0 || n_persons < 0 || (n_keypoints > 0 && !keypoint_ids))
+        return P2S_EINVAL;
+    if ((long long)n_persons * n_keypoints > 0 && (!x || !y || !lik)) return P2S_EINVAL;
+    for (int k = 0; k < n_keypoints; ++k) if (keypoint_ids[k] < 0) return P2S_EINVAL;
+    const long long n_files = n_frames * n_cams;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if ((long long)n_threads > n_files) n_threads = (int)(n_files > 0 ? n_files : 1);
+    std::atomic<long long> next{0};
+    std::atomic<long long> inexact{0};
+    const float fnan = std::numeric_limits<float>::quiet_NaN();
+    const size_t C = (size_t)n_cams, K = (size_t)n_keypoints, N = (size_t)n_persons;
+
+    auto work = [&]() {
+        std::string buf;
+        Doc doc;
+        long long my_inexact = 0;
+        for (;;) {
+            const long long i0 = next.fetch_add(16);
+            if (i0 >= n_files) break;
+            const long long i1 = i0 + 16 < n_files ? i0 + 16 : n_files;
+            for (long long i = i0; i < i1; ++i) {
+                const size_t f = (size_t)(i / n_cams), c = (size_t)(i % n_cams);
+                doc.has_people = false;
+                doc.people.clear();
+                bool ok = paths[i] && paths[i][0] && read_file(paths[i], buf);
+                if (ok) {
+                    Parser ps(buf.data(), buf.data() + buf.size());
+                    ok = ps.parse(doc);
+                }
+                if (status) status[i] = ok ? 1 : 0;
+                if (n_people) n_people[i] = (ok && doc.has_people) ? (int32_t)doc.people.size() : (ok ? 0 : -1);
+                for (size_t n = 0; n < N; ++n) {
+                    const Person *person = (ok && doc.has_people && n < doc.people.size()) ? &doc.people[n] : nullptr;
+                    const bool usable = person && person->is_object && person->has_keypoints && !person->bad_entry;
+                    for (size_t k = 0; k < K; ++k) {
+                        const size_t o = ((f * N + n) * K + k) * C + c;
+                        const size_t j = 3 * (size_t)keypoint_ids[k];
+                        if (usable && j + 2 < person->kp.size()) {
+                            const double vx = person->kp[j], vy = person->kp[j + 1], vl = person->kp[j + 2];
+                            const float fx = (float)vx, fy = (float)vy, fl = (float)vl;
+                            x[o] = fx; y[o] = fy; lik[o] = fl;
+                            my_inexact += (std::isfinite(vx) && (double)fx != vx) + (std::isfinite(vy) && (double)fy != vy) +
+                                          (std::isfinite(vl) && (double)fl != vl);
+                        } else {
+                            x[o] = fnan; y[o] = fnan; lik[o] = fnan;
+                        }
+                    }
+                }
+            }
+        }
+        inexact.fetch_add(my_inexact);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (n_inexact) *n_inexact = inexact.load();
+    return P2S_OK;
+}

@@ -151,11 +151,47 @@ def float32_inexact(*arrays):
     return n
 
 
-def stage_triangulation(input_dir, cam_dirs, json_files_names, f_range, keypoints_ids, nb_persons):
-    """All frames of `extract_files_frame_f` (triangulation.py:607-653) at once.
+def frame_paths(input_dir, cam_dirs, table):
+    """Absolute path per (frame, camera); '' where the frame has no file ('none' in the reference)."""
+    return [[os.path.join(input_dir, cam_dirs[c], names[c]) if names[c] != "none" else "" for c in range(len(cam_dirs))]
+            for names in table]
 
-    Returns x, y, lik as float64 arrays [F, N, K, C] (unit-major, camera fastest: the layout
-    `p2s_triangulate_host` takes once cast to float32 and viewed as [F*N*K, C])."""
+
+def read_pose_files(paths, keypoints_ids, nb_persons, n_threads=0):
+    """Native multi-threaded reader (csrc/p2s_json.cpp, `p2s_read_pose_files`): every file parsed once.
+    paths: [F][C] strings.  Returns x, y, lik float32 [F, N, K, C], n_people int32 [F, C], n_inexact."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    F = len(paths)
+    n_cams = len(paths[0]) if F else 1
+    K, N = len(keypoints_ids), int(nb_persons)
+    flat = [p.encode() for row in paths for p in row]
+    arr = (C.c_char_p * len(flat))(*flat)
+    ids = np.ascontiguousarray(keypoints_ids, dtype=np.int32)
+    x = np.empty((F, N, K, n_cams), np.float32)
+    y = np.empty_like(x)
+    lik = np.empty_like(x)
+    n_people = np.empty((F, n_cams), np.int32)
+    inexact = C.c_longlong(0)
+    _lib.check(None, lib.p2s_read_pose_files(C.cast(arr, C.c_void_p), F, n_cams, ids.ctypes.data, K, N, x.ctypes.data,
+                                             y.ctypes.data, lik.ctypes.data, n_people.ctypes.data, None,
+                                             C.cast(C.pointer(inexact), C.c_void_p), int(n_threads)))
+    return x, y, lik, n_people, int(inexact.value)
+
+
+def stage_triangulation(input_dir, cam_dirs, json_files_names, f_range, keypoints_ids, nb_persons):
+    """All frames of `extract_files_frame_f` (triangulation.py:607-653) at once, through the native reader.
+    Returns x, y, lik float32 [F, N, K, C] (unit-major, camera fastest: the layout `p2s_triangulate_host`
+    takes viewed as [F*N*K, C]) and the number of values float32 could not represent exactly."""
+    table = frame_file_table(json_files_names, f_range)
+    x, y, lik, _, inexact = read_pose_files(frame_paths(input_dir, cam_dirs, table), keypoints_ids, nb_persons)
+    return x, y, lik, inexact
+
+
+def stage_triangulation_python(input_dir, cam_dirs, json_files_names, f_range, keypoints_ids, nb_persons):
+    """Pure-Python twin of `stage_triangulation` (json.load per file), kept as the restatement the native
+    parser is tested against (tests/test_native_staging.py).  Returns float64 arrays [F, N, K, C]."""
     table = frame_file_table(json_files_names, f_range)
     F, C, K, N = len(table), len(cam_dirs), len(keypoints_ids), nb_persons
     ids3 = 3 * np.asarray(keypoints_ids, dtype=np.int64)
@@ -174,13 +210,18 @@ def stage_triangulation(input_dir, cam_dirs, json_files_names, f_range, keypoint
 
 
 def count_persons(input_dir, cam_dirs, json_files_names):
-    """triangulation.py:784 + :77-90: the largest `len(people)` over EVERY listed json of every camera.
-    A file that cannot be parsed raises, as in the reference."""
+    """triangulation.py:784 + :77-90: the largest `len(people)` over EVERY listed json of every camera
+    (native reader, one parse per file).  A file that cannot be parsed raises, as in the reference."""
     best = 0
     for c, names in enumerate(json_files_names):
-        for name in names:
-            with open(os.path.join(input_dir, cam_dirs[c], name), "r") as f:
-                best = max(best, len(json.load(f).get("people", [])))
+        paths = [[os.path.join(input_dir, cam_dirs[c], name)] for name in names]
+        if not paths:
+            continue
+        _, _, _, n_people, _ = read_pose_files(paths, [], 0)
+        if (n_people < 0).any():
+            bad = names[int(np.flatnonzero(n_people[:, 0] < 0)[0])]
+            raise ValueError(f"cannot parse {os.path.join(input_dir, cam_dirs[c], bad)}")
+        best = max(best, int(n_people.max(initial=0)))
     return best
 
 

@@ -92,13 +92,13 @@ def stage_project(config_dict):
                         f"file, and {n_cams} cameras based on the number of pose folders.")
     n_persons = _stg.count_persons(input_dir, cam_dirs, files) if s["multi_person"] else 1
 
-    x, y, lik = _stg.stage_triangulation(input_dir, cam_dirs, files, f_range, ids, n_persons)
+    x, y, lik, inexact = _stg.stage_triangulation(input_dir, cam_dirs, files, f_range, ids, n_persons)
     st = StagedProject()
     st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
     st.keypoints_ids, st.keypoints_names = ids, names
     st.cam_dirs, st.input_dir, st.f_range, st.n_cams, st.n_persons = cam_dirs, input_dir, list(f_range), n_cams, n_persons
-    st.inexact = _stg.float32_inexact(x, y, lik)
-    st.x, st.y, st.lik = (a.astype(np.float32) for a in (x, y, lik))
+    st.inexact = inexact
+    st.x, st.y, st.lik = x, y, lik
     if st.inexact:
         logging.warning(f"{st.inexact} 2D values are not exactly representable in float32 and were rounded for the "
                         f"device staging layout (Pose2Sim's own pose stage writes float32 values).")

@@ -35,6 +35,9 @@ def build(specs):
                 regs = [l for l in r.stderr.splitlines() if "Used" in l or "spill" in l]
                 open(os.path.join(AB, f"{name}.ptxas.log"), "w").write(r.stderr)
             objs.append(obj)
+        jobj = os.path.join(AB, f"{name}_p2s_json.o")
+        subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(CSRC, "p2s_json.cpp"), "-o", jobj], check=True)
+        objs.append(jobj)
         out = os.path.join(AB, f"libp2s_{name}.so")
         subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
         for o in objs:
