@@ -177,5 +177,36 @@ def main():
         print("   " + "\n   ".join(l for l in log.splitlines() if l.startswith("-->")))
 
 
+def multi_association_trial():
+    """Multi-person association: 4 ring cameras, 3 persons in random per-camera order, a detection
+    missing now and then."""
+    calib_text, cams, kp, present = association_trial()
+    return calib_text, cams, kp[:40], present[:40]
+
+
+def main_multi_association():
+    ref = ref_shim.load_reference()
+    calib_text, cams, kp, present = multi_association_trial()
+    with tempfile.TemporaryDirectory() as td:
+        proj = synth_project.write_project(os.path.join(td, "trial_massoc"), calib_text, cams, kp, present=present)
+        cfg = synth_project.base_config(proj, multi_person=True)
+        log = run_reference(ref.personAssociation.associate_all, cfg, proj)
+        chosen, exists = read_people_arrays(os.path.join(proj, "pose-associated"), cams, range(kp.shape[0]), 8)
+        n_people = np.zeros(exists.shape, np.int32)
+        for c, cam in enumerate(cams):
+            for f in range(kp.shape[0]):
+                path = os.path.join(proj, "pose-associated", f"{cam}_json", f"{cam}_{f:06d}.json")
+                if os.path.exists(path):
+                    n_people[f, c] = len(json.load(open(path))["people"])
+        np.savez_compressed(os.path.join(GOLDEN, "e2e_assoc_multi.npz"), calib=np.array(calib_text), cams=np.array(cams),
+                            kp=kp.astype(np.float32), present=present, multi_person=np.array(True),
+                            chosen=chosen.astype(np.float32), exists=exists, n_people=n_people, log=np.array(log))
+        print("e2e_assoc_multi: persons per frame", np.bincount(n_people[:, 0]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "multi_assoc":
+        main_multi_association()
+    else:
+        main()
+        main_multi_association()

@@ -7,8 +7,9 @@ replaced by ONE batched call into the sm_100a library (`p2s_associate_host`).
     solve_frames()     DEVICE  :771-774   ordered person-combination x camera-subset search, all frames
     write_outputs()    host    :776-808   rewrite JSON with the chosen person per camera, recap
 
-Multi-person mode (Plücker-ray affinity + SVT matching, :277-549) is a SURVEY §8(f) "next" row and is
-refused loudly; there is no CPU search in this package.
+Multi-person mode (Plücker-ray affinity + SVT matching, :277-549) is a different
+kernel family — small dense linear algebra per frame — and runs on the host (`multi_person.py`); the
+single-person search has no CPU implementation in this package.
 """
 import json
 import logging
@@ -73,21 +74,26 @@ def stage_project(config_dict):
     if n_cams != len(P):
         raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
                         f"file, and {n_cams} cameras based on the number of pose folders.")
+    kid = 0
     if s["multi_person"]:
         logging.info("\nMulti-person analysis selected.")
-        raise NotImplementedError("multi_person association (affinity + SVT, personAssociation.py:277-549) is not "
-                                  "available in the B200 path yet")
-    logging.info("\nSingle-person analysis selected.")
-    kid, fallback = _skel.tracked_keypoint_id(s["pose_model"], s["tracked_keypoint"], config_dict)
-    if fallback is not None:
-        logging.warning(f"{s['tracked_keypoint']} not found in {s['pose_model']}, consider editing tracked_keypoint "
-                        f"in Config.toml. Tracking {fallback} instead.")
+    else:
+        logging.info("\nSingle-person analysis selected.")
+        kid, fallback = _skel.tracked_keypoint_id(s["pose_model"], s["tracked_keypoint"], config_dict)
+        if fallback is not None:
+            logging.warning(f"{s['tracked_keypoint']} not found in {s['pose_model']}, consider editing "
+                            f"tracked_keypoint in Config.toml. Tracking {fallback} instead.")
 
     st = StagedAssociation()
     st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
     st.cam_dirs, st.dirs, st.f_range, st.n_cams, st.tracked_keypoint_id = cam_dirs, dirs, list(f_range), n_cams, kid
     st.table = _stg.frame_file_table(files, f_range)
     # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
+    if s["multi_person"]:
+        st.parsed = [[_stg.load_json(os.path.join(dirs.pose_dir, cam_dirs[c], names[c])) for c in range(n_cams)]
+                     for names in st.table]
+        st.obs, st.count, st.inexact = None, None, 0
+        return st
     obs, st.count, st.parsed = _stg.stage_association(dirs.pose_dir, cam_dirs, st.table, kid, _lib.P2S_MAX_PERSONS)
     st.inexact = _stg.float32_inexact(obs[..., :3])
     if st.inexact:
@@ -108,6 +114,23 @@ def solve_frames(st, engine=None):
     comb = out["comb"].astype(np.float64)
     comb[out["comb"] < 0] = np.nan
     return {"err": out["err"], "comb": comb, "Q": out["Q"]}
+
+
+def solve_frames_multi_person(st):
+    """Host: personAssociation.py:783-801 for every frame.  Returns the list of proposals per frame."""
+    import warnings
+    from . import multi_person as mp
+    s = st.settings
+    calib, keys = _calib.load_calibration(st.calib_file)
+    cams = mp.camera_ray_params([calib[k] for k in keys])
+    out = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for parsed in st.parsed:
+            detections = [_stg.read_people(js) if js is not None else [] for js in parsed]
+            out.append(mp.associate_frame(detections, cams, s["reconstruction_error_threshold"], s["min_affinity"],
+                                          s["min_cams"]))
+    return out
 
 
 def rewrite_frame(tracked_paths, source_js, proposals):
@@ -143,6 +166,18 @@ def write_outputs(st, res):
     return {"error": errors, "cameras_off": cams_off}
 
 
+def write_outputs_multi_person(st, proposals):
+    for fi, names in enumerate(st.table):
+        tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
+        rewrite_frame(tracked, st.parsed[fi], proposals[fi])
+    s = st.settings
+    logging.info(f"\n--> A person was reconstructed if the lines from cameras to their keypoints intersected within "
+                 f"{s['reconstruction_error_threshold']} m and if the calculated affinity stayed above {s['min_affinity']}.")
+    logging.info("--> Beware that people were sorted across cameras, but not across frames. This will be done in the "
+                 "triangulation stage.")
+    logging.info(f"\nTracked json files are stored in {os.path.realpath(st.dirs.tracked_dir)}.")
+
+
 def log_recap(st, errors, cams_off):
     """personAssociation.py:583-639 `recap_tracking`, single-person branch."""
     s = st.settings
@@ -164,5 +199,8 @@ def associate_all(config_dict):
     """Same contract as Pose2Sim/personAssociation.py:642: reads calibration + per-camera JSON, writes
     `pose-associated/<cam>_json/*.json` with one person of interest, logs the recap.  Returns None."""
     st = stage_project(config_dict)
+    if st.settings["multi_person"]:
+        write_outputs_multi_person(st, solve_frames_multi_person(st))
+        return
     res = solve_frames(st)
     write_outputs(st, res)

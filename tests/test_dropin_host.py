@@ -120,3 +120,31 @@ def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
     assert np.array_equal(exists, g["exists"])
     assert np.array_equal(np.isnan(chosen), np.isnan(g["chosen"]))
     assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
+
+
+def test_multi_person_association_matches_reference_json(golden, tmp_path):
+    """`associate_all` with multi_person = true (host NumPy: ray affinity + SVT matching) writes the
+    same people, in the same order, as the reference did (tests/golden/e2e_assoc_multi.npz)."""
+    import json as _json
+    import os as _os
+    import pose2sim_b200
+    g = golden("e2e_assoc_multi.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_massoc")
+    with in_dir(proj):
+        assert pose2sim_b200.associate_all(cfg) is None
+    cams = [str(c) for c in g["cams"]]
+    F, C, S, V = g["chosen"].shape
+    for c, cam in enumerate(cams):
+        for f in range(F):
+            path = _os.path.join(proj, "pose-associated", f"{cam}_json", f"{cam}_{f:06d}.json")
+            assert _os.path.exists(path) == bool(g["exists"][f, c])
+            if not g["exists"][f, c]:
+                continue
+            people = _json.load(open(path))["people"]
+            assert len(people) == int(g["n_people"][f, c]), (f, c)
+            for p, person in enumerate(people):
+                ref = g["chosen"][f, c, p]
+                if person:
+                    assert np.array_equal(np.asarray(person["pose_keypoints_2d"], np.float32), ref), (f, c, p)
+                else:
+                    assert np.isnan(ref).all(), (f, c, p)
