@@ -16,12 +16,17 @@
 //           best updated on strict '<'; first row with err_last < thr ends the row loop      (:242-248)
 //       k += 1
 //
-// Mapping: one warp per frame (frames are plentiful, rows per frame usually few), one LANE PER ROW
-// in ordered chunks of 32 rows.  Each lane walks its row's candidate subsets serially (the
-// lexicographic k-subsets of the active cameras are the subsequence of the all-camera table whose
-// members are subsets of `active`, so the triangulation kernel's mask table is reused).  The ordered
-// early exit is a ballot: the first lane whose row is under the threshold wins and later lanes of
-// the chunk are discarded; the running best is a shuffle arg-min over (error, row).
+// Mapping: one warp per frame (frames are plentiful), one LANE PER ROW in ordered chunks of 32 rows.
+//   * per frame the warp first builds, camera-person-parallel, the 10-entry normal-matrix block
+//     a a^T + b b^T of EVERY detection (camera c, person p) in shared memory; a row's normal matrix is
+//     then the sum of its active cameras' blocks (10 FP64 adds per camera instead of 64 flops), and a
+//     candidate that drops cameras subtracts their blocks;
+//   * a lane keeps its row's person indices as packed 4-bit digits and steps them by 32 rows per chunk
+//     with a small mixed-radix addition (multiply-shift by the reciprocal radix) — no 64-bit division;
+//   * the lexicographic k-subsets of the active cameras are the subsequence of the all-camera table
+//     whose members are subsets of `active`, so the triangulation kernel's mask table is reused;
+//   * the ordered early exit is a ballot: the first lane whose row is under the threshold wins and later
+//     lanes of the chunk are discarded; the running best is a shuffle arg-min over (error, row).
 #include "p2s_math.cuh"
 #include "p2s_internal.h"
 
@@ -43,19 +48,54 @@ struct AssocArgs {
     unsigned int *tile_counter;
 };
 
+__host__ __device__ inline size_t assoc_slab_bytes(int cmax, int np) {
+    return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 3 * (size_t)cmax * sizeof(uint32_t);
+}
+
+template <int CMAX>
+__device__ __forceinline__ uint32_t digit_of(const uint32_t (&dig)[4], int c) { return (dig[c >> 3] >> ((c & 7) * 4)) & 15u; }
+
+// same for a camera index only known at run time (select chain instead of a local-memory array index)
+__device__ __forceinline__ uint32_t digit_rt(const uint32_t (&dig)[4], int c) {
+    const uint32_t w = c < 8 ? dig[0] : c < 16 ? dig[1] : c < 24 ? dig[2] : dig[3];
+    return (w >> ((c & 7) * 4)) & 15u;
+}
+
+// digits += v in the mixed radix n[c] (last camera fastest, itertools.product order); v < 64, n <= 16:
+// floor(t / n) = (t * ceil(65536 / n)) >> 16 is exact for t < 128
+template <int CMAX>
+__device__ __forceinline__ void radix_add(uint32_t (&dig)[4], uint32_t v, const uint32_t *s_n, const uint32_t *s_inv, int C) {
+    uint32_t carry = v;
+#pragma unroll
+    for (int c = CMAX - 1; c >= 0; --c) {
+        if (c < C) {
+            const uint32_t n = s_n[c] ? s_n[c] : 1u;
+            const uint32_t t = digit_of<CMAX>(dig, c) + carry;
+            const uint32_t q = (t * s_inv[c]) >> 16;
+            const uint32_t d = t - q * n;
+            dig[c >> 3] = (dig[c >> 3] & ~(15u << ((c & 7) * 4))) | (d << ((c & 7) * 4));
+            carry = q;
+        }
+    }
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int C = a.n_cams, NP = a.max_persons;
-    // per-warp slab: obs float4 [C][NP], then n_c' (uint32 [CMAX]), ok masks (uint32 [CMAX])
-    const size_t slab = (size_t)CMAX * NP * sizeof(float4) + 2 * CMAX * sizeof(uint32_t);
-    unsigned char *base = smem_raw + slab * warp;
+    double *sP = reinterpret_cast<double *>(smem_raw);
+    // per-warp slab: obs float4 [CMAX][NP], blocks double [CMAX * NP][10], n_c, ok masks, reciprocal radices
+    unsigned char *base = smem_raw + CMAX * 12 * sizeof(double) + assoc_slab_bytes(CMAX, NP) * warp;
     float4 *sobs = reinterpret_cast<float4 *>(base);
-    uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * sizeof(float4));
+    double *sblk = reinterpret_cast<double *>(base + (size_t)CMAX * NP * sizeof(float4));
+    uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * (sizeof(float4) + 10 * sizeof(double)));
     uint32_t *s_ok = s_n + CMAX;
-    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    uint32_t *s_inv = s_ok + CMAX;
+
+    for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
+    __syncthreads();
 
     for (;;) {
         unsigned int f = 0;
@@ -63,9 +103,17 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
         f = __shfl_sync(P2S_FULL, f, 0);
         if ((long long)f >= a.n_frames) break;
 
-        // ---- stage the frame ------------------------------------------------------------------------
+        // ---- stage the frame, gate the detections, build every detection's block ----------------------
         const float4 *fobs = a.obs + (long long)f * C * NP;
-        for (int i = lane; i < C * NP; i += 32) sobs[i] = __ldg(fobs + i);
+        for (int i = lane; i < C * NP; i += 32) {
+            const float4 o = __ldg(fobs + i);
+            sobs[i] = o;
+            double b[10];
+            camera_block(sP + (i / NP) * 12, (double)o.x, (double)o.y, (double)o.z, b);
+            double2 *dst = reinterpret_cast<double2 *>(sblk + (size_t)i * 10);
+#pragma unroll
+            for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
+        }
         __syncwarp();
         if (lane < C) {
             int n = a.count[(long long)f * C + lane];
@@ -78,6 +126,8 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
             }
             s_n[lane] = (uint32_t)n;
             s_ok[lane] = ok;
+            const uint32_t nn = n ? (uint32_t)n : 1u;
+            s_inv[lane] = (65536u + nn - 1u) / nn;
         }
         __syncwarp();
         uint32_t present = 0;
@@ -95,47 +145,73 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
         unsigned long long best_key = P2S_KEY_EMPTY;          // key of the global best (strict '<' updates)
         double bqx = nan64(), bqy = bqx, bqz = bqx;
         uint32_t b_valid = 0;                                 // cameras used by the best candidate
-        unsigned long long b_row = 0;
+        uint32_t b_dig[4] = {0, 0, 0, 0};                     // person digits of the best row
         unsigned int st_rows = 0, st_cands = 0;
 
         for (int k = 0; !overflow && err_last > a.thr && C - (n_missing + k) >= a.min_cams; ++k) {
             const bool tabled = k <= a.max_table_level;
-            const uint32_t ncand_all = tabled ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
+            const uint32_t ncand_all = (k == 0) ? 1u : tabled ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             bool hit = false;
+            uint32_t dig[4] = {0, 0, 0, 0};                   // 4 bits per camera: the row's person indices
+            radix_add<CMAX>(dig, (uint32_t)lane, s_n, s_inv, C);
             for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += 32) {
                 const unsigned long long r = rbase + lane;
                 const bool row_ok = r < total_rows;
-                // decode the row: last camera fastest (itertools.product)
-                uint32_t dig[4] = {0, 0, 0, 0};               // 4 bits per camera
                 uint32_t active = 0;
-                {
-                    unsigned long long q = r;
 #pragma unroll
-                    for (int c = CMAX - 1; c >= 0; --c) {
-                        if (c < C) {
-                            const uint32_t n = s_n[c];
-                            uint32_t p = 0;
-                            if (n > 1) { p = (uint32_t)(q % n); q /= n; }
-                            dig[c >> 3] |= p << ((c & 7) * 4);
-                            if (n && ((s_ok[c] >> p) & 1u)) active |= 1u << c;
-                        }
-                    }
-                }
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < C && s_n[c] && ((s_ok[c] >> digit_of<CMAX>(dig, c)) & 1u)) active |= 1u << c;
                 const int na = __popc(active);
                 unsigned long long rkey = P2S_KEY_EMPTY;
                 double rqx = nan64(), rqy = rqx, rqz = rqx;
                 uint32_t rvalid = 0;
                 if (row_ok && na >= a.min_cams && k <= na) {
-                    auto fetch = [&](int c) -> float4 { return sobs[c * NP + ((dig[c >> 3] >> ((c & 7) * 4)) & 15u)]; };
+                    // the row's normal matrix: sum of its active cameras' blocks, ascending camera order
+                    Sym4 Mrow;
+                    sym4_zero(Mrow);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) {
+                        if ((active >> c) & 1u) {
+                            const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(dig, c)) * 10);
+                            const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                            Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
+                            Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
+                        }
+                    }
                     for (uint32_t ci = 0; ci < ncand_all; ++ci) {
-                        const uint32_t cm = tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
+                        const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
                         if (cm & ~active) continue;           // not a subset of the active cameras
+                        const uint32_t valid = active & ~cm;
+                        const int m = __popc(valid);
                         double cqx, cqy, cqz, e;
-                        solve_subset<CMAX, 0>(cams, fetch, C, active & ~cm, cqx, cqy, cqz, e);
+                        if (m < 2) {
+                            cqx = cqy = cqz = nan64();
+                            e = (m == 0) ? nan64() : inf64();
+                        } else {
+                            Sym4 M = Mrow;
+                            uint32_t bits = cm;
+                            while (bits) {
+                                const int c = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_rt(dig, c)) * 10);
+                                const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                M.m00 -= v0.x; M.m01 -= v0.y; M.m02 -= v1.x; M.m03 -= v1.y; M.m11 -= v2.x;
+                                M.m12 -= v2.y; M.m13 -= v3.x; M.m22 -= v3.y; M.m23 -= v4.x; M.m33 -= v4.y;
+                            }
+                            smallest_eigvec_secular(M, cqx, cqy, cqz);
+                            double sum = 0.0;
+#pragma unroll
+                            for (int c = 0; c < CMAX; ++c) {
+                                const float4 o = sobs[c * NP + digit_of<CMAX>(dig, c)];
+                                const double dist = reproj_distance(cams.P[c], cqx, cqy, cqz, (double)o.x, (double)o.y);
+                                sum += ((valid >> c) & 1u) ? dist : 0.0;
+                            }
+                            e = div_small(sum, (double)m);
+                        }
                         ++st_cands;
                         const unsigned long long key = err_key(e);
-                        if (key < rkey) { rkey = key; rqx = cqx; rqy = cqy; rqz = cqz; rvalid = active & ~cm; }
+                        if (key < rkey) { rkey = key; rqx = cqx; rqy = cqy; rqz = cqz; rvalid = valid; }
                     }
                 }
                 // all-NaN rows are skipped (:235-236); rows without candidates too
@@ -166,9 +242,11 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
                         bqy = __shfl_sync(P2S_FULL, rqy, cl);
                         bqz = __shfl_sync(P2S_FULL, rqz, cl);
                         b_valid = __shfl_sync(P2S_FULL, rvalid, cl);
-                        b_row = rbase + (unsigned long long)cl;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) b_dig[w] = __shfl_sync(P2S_FULL, dig[w], cl);
                     }
                 }
+                radix_add<CMAX>(dig, 32u, s_n, s_inv, C);     // this lane's next row
             }
         }
 
@@ -189,21 +267,13 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
         if (lane < C) {
             int8_t v = -1;
             if (best_key != P2S_KEY_EMPTY && ((b_valid >> lane) & 1u)) {
-                // digit of camera `lane` in row b_row
-                unsigned long long q = b_row;
-                uint32_t p = 0;
-                for (int c = C - 1; c >= lane; --c) {
-                    const uint32_t n = s_n[c];
-                    p = 0;
-                    if (n > 1) { p = (uint32_t)(q % n); q /= n; }
-                }
-                v = (int8_t)p;
+                const uint32_t w = lane < 8 ? b_dig[0] : lane < 16 ? b_dig[1] : lane < 24 ? b_dig[2] : b_dig[3];
+                v = (int8_t)((w >> ((lane & 7) * 4)) & 15u);
             }
             a.out_comb[(long long)f * C + lane] = v;
         }
         __syncwarp();
     }
-    (void)cmask;
 }
 
 template <int CMAX>
@@ -212,8 +282,7 @@ static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0, int *
     for (int c = 0; c < CMAX; ++c)
         for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
     AssocArgs a = a0;
-    const size_t slab = (size_t)CMAX * L.max_persons * sizeof(float4) + 2 * CMAX * sizeof(uint32_t);
-    const size_t smem = slab * 4;
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + assoc_slab_bytes(CMAX, L.max_persons) * 4;
     auto kern = associate_kernel<CMAX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
