@@ -67,6 +67,18 @@ enum {
     P2S_STAT_COUNT = 48
 };
 
+/* Lens model of one camera for `[triangulation] undistort_points = true` (calibration TOML values;
+ * common.py:254-288 retrieve_calib_params).  dist = k1 k2 p1 p2 k3 k4 k5 k6 in OpenCV order, unused
+ * coefficients 0; newK = cv2.getOptimalNewCameraMatrix(K, dist, size, 1, size), the matrix the
+ * reference builds P from (common.py:310-313) and re-projects the undistorted points with.        */
+typedef struct p2s_camera_model {
+    double K[9];
+    double dist[8];
+    double R[9];
+    double T[3];
+    double newK[9];
+} p2s_camera_model;
+
 typedef struct p2s_device_info {
     int device;
     int sm_count;
@@ -119,6 +131,24 @@ int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const fl
                          double lik_thr, double reproj_thr, int min_cams,
                          double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
                          unsigned long long *stats);
+
+/* `undistort_points = true` variants (triangulation.py:808-813, :472-476).  `lens`: HOST pointer to
+ * n_cams models.  Staging additionally undistorts x, y like cv2.undistortPoints(float32 points, K, dist,
+ * None, newK) before the gate; the search measures the error between the undistorted observation and the
+ * DISTORTED re-projection (cv2.projectPoints with K, dist), exactly as the reference does.  P must be
+ * the projection built on newK.                                                                  */
+int p2s_stage_undistort_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                               long long n_units, int n_cams, double lik_thr, const p2s_camera_model *lens,
+                               void *obs_out, void *stream);
+int p2s_triangulate_distorted_device(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens,
+                                     long long n_units, int n_cams, double reproj_thr, int min_cams,
+                                     double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                     unsigned long long *stats, void *stream);
+int p2s_triangulate_undistort_host(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                   const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
+                                   double lik_thr, double reproj_thr, int min_cams,
+                                   double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                   unsigned long long *stats);
 
 /* ---- single-person association search (personAssociation.py:154) ---------------------------- *
  * obs        : float4 [n_frames][n_cams][max_persons] = {x, y, likelihood, 0} of the tracked keypoint

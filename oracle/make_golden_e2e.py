@@ -177,6 +177,93 @@ def main():
         print("   " + "\n   ".join(l for l in log.splitlines() if l.startswith("-->")))
 
 
+def undistort_trial():
+    """Ring cameras WITH lens distortion (5 coefficients, like the fork's k3-enabled calibration),
+    observations produced by cv2.projectPoints on the truth, `[triangulation] undistort_points = true`."""
+    import cv2
+    from pose2sim_b200 import calib
+    ids, names = skeletons.keypoints("HALPE_26")
+    C, F, K = 4, 60, 26
+    P, Ks, Rs, ts = synth.ring_cameras(C)
+    dists = [[-0.06, 0.03, 8e-4, -6e-4, 0.01], [-0.04, 0.01, -5e-4, 3e-4, 0.0], [0.03, -0.02, 2e-4, 1e-4, 0.005],
+             [-0.08, 0.05, 0.0, 0.0, -0.01]]
+    cams = [f"cam{c + 1:02d}" for c in range(C)]
+    td = tempfile.mkdtemp()
+    path = os.path.join(td, "c.toml")
+    calib.write_calibration_toml(path, cams, [(1080.0, 1920.0)] * C, Ks, dists, [calib.rotation_to_rodrigues(R) for R in Rs], ts)
+    calib_text = open(path).read()
+    Q = synth.truth_points(F, 1, K, 444)[:, 0]                                   # [F, K, 3]
+    g = np.random.default_rng(444)
+    x = np.empty((F, C, 1, K)); y = np.empty((F, C, 1, K)); lik = np.empty((F, C, 1, K))
+    for c in range(C):
+        rvec = cv2.Rodrigues(Rs[c])[0]
+        uv = cv2.projectPoints(Q.reshape(-1, 3), rvec, ts[c], Ks[c], np.array(dists[c]))[0].reshape(F, K, 2)
+        x[:, c, 0], y[:, c, 0] = uv[..., 0], uv[..., 1]
+    x += g.normal(0, 1.5, x.shape); y += g.normal(0, 1.5, y.shape)
+    out = g.random(x.shape) < 0.06
+    x = np.where(out, x + g.uniform(60, 200, x.shape), x)
+    lik[:] = g.uniform(0.5, 1.0, lik.shape)
+    lik = np.where(g.random(lik.shape) < 0.06, g.uniform(0.0, 0.3, lik.shape), lik)
+    kp = synth_project.pack_openpose(x.astype(np.float32), y.astype(np.float32), lik.astype(np.float32), ids, J)
+    return calib_text, cams, kp, None
+
+
+def main_undistort():
+    ref = ref_shim.load_reference()
+    calib_text, cams, kp, present = undistort_trial()
+    with tempfile.TemporaryDirectory() as td:
+        proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+        extra = {"undistort_points": True}
+        cfg = synth_project.base_config(proj, **extra)
+        log = run_reference(ref.triangulation.triangulate_all, cfg, proj)
+        trcs = sorted(glob.glob(os.path.join(proj, "pose-3d", "*.trc")))
+        assert trcs
+        out = {"calib": np.array(calib_text), "cams": np.array(cams), "kp": kp.astype(np.float32),
+               "present": np.ones(kp.shape[:3], bool), "multi_person": np.array(False), "extra": np.array(json.dumps(extra)),
+               "trc_names": np.array([os.path.basename(t) for t in trcs]), "log": np.array(log)}
+        for i, t in enumerate(trcs):
+            out[f"trc{i}"] = np.array(open(t).read())
+        # per-unit outputs of the reference's search on the same (cv2-undistorted, gated) inputs
+        import cv2
+        calib_file = glob.glob(os.path.join(proj, "calibration", "*.toml"))[0]
+        Pm = ref.common.computeP(calib_file, undistort=True)
+        cp = ref.common.retrieve_calib_params(calib_file)
+        ids, _ = skeletons.keypoints("HALPE_26")
+        F, C = kp.shape[0], kp.shape[1]
+        Kn = len(ids)
+        xs = kp[:, :, 0, :][:, :, 3 * np.asarray(ids)].astype(np.float64)                  # [F, C, K]
+        ys = kp[:, :, 0, :][:, :, 3 * np.asarray(ids) + 1].astype(np.float64)
+        ls = kp[:, :, 0, :][:, :, 3 * np.asarray(ids) + 2].astype(np.float64)
+        ux, uy = np.empty_like(xs), np.empty_like(ys)
+        for f in range(F):
+            for c in range(C):
+                pts = np.stack([xs[f, c], ys[f, c]], 1).reshape(-1, 1, 2).astype("float32")
+                u = cv2.undistortPoints(pts, cp["K"][c], cp["dist"][c], None, cp["optim_K"][c]).reshape(-1, 2)
+                ux[f, c], uy[f, c] = u[:, 0], u[:, 1]
+        low = ls < 0.3
+        gx, gy, gl = np.where(low, np.nan, ux), np.where(low, np.nan, uy), np.where(low, np.nan, ls)
+        cfg_u = {"triangulation": {"reproj_error_threshold_triangulation": 15, "min_cameras_for_triangulation": 2,
+                                   "handle_LR_swap": False, "undistort_points": True}}
+        U = F * Kn
+        Qo, eo, no, mo = np.empty((U, 3)), np.empty(U), np.empty(U, np.int32), np.zeros(U, np.uint32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for f in range(F):
+                for k in range(Kn):
+                    coords = np.array([gx[f, :, k], gy[f, :, k], gl[f, :, k]])
+                    q, e, n, idl = ref.triangulation.triangulation_from_best_cameras(cfg_u, coords, coords.copy(), Pm, cp)
+                    u = f * Kn + k
+                    Qo[u], eo[u], no[u] = np.asarray(q, float)[:3], e, n
+                    for c in np.asarray(idl).ravel():
+                        mo[u] |= np.uint32(1 << int(c))
+        out.update(unit_x=xs.transpose(0, 2, 1).reshape(U, C).astype(np.float32), unit_y=ys.transpose(0, 2, 1).reshape(U, C).astype(np.float32),
+                   unit_lik=ls.transpose(0, 2, 1).reshape(U, C).astype(np.float32),
+                   unit_ux=ux.transpose(0, 2, 1).reshape(U, C).astype(np.float32), unit_uy=uy.transpose(0, 2, 1).reshape(U, C).astype(np.float32),
+                   unit_Q=Qo, unit_err=eo, unit_nexcl=no, unit_mask=mo, unit_P=np.array(Pm))
+        np.savez_compressed(os.path.join(GOLDEN, "e2e_tri_undistort.npz"), **out)
+        print("e2e_tri_undistort", [os.path.basename(t) for t in trcs], "triangulated", np.isfinite(eo).mean(), "mean nexcl", no.mean())
+
+
 def multi_association_trial():
     """Multi-person association: 4 ring cameras, 3 persons in random per-camera order, a detection
     missing now and then."""
@@ -207,6 +294,9 @@ def main_multi_association():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "multi_assoc":
         main_multi_association()
+    elif len(sys.argv) > 1 and sys.argv[1] == "undistort":
+        main_undistort()
     else:
         main()
         main_multi_association()
+        main_undistort()

@@ -20,7 +20,7 @@ import math
 import numpy as np
 
 __all__ = [
-    "weighted_dlt", "reproject", "pixel_distance", "solve_subset",
+    "weighted_dlt", "reproject", "pixel_distance", "solve_subset", "undistort_points", "project_distorted",
     "triangulate_unit", "triangulate_units", "person_id_rows", "associate_frame",
 ]
 
@@ -69,18 +69,67 @@ def pixel_distance(q1, q2):
     return float(np.sqrt(np.nansum(d * d)))
 
 
-def solve_subset(P, x, y, w, cams):
+def undistort_points(x, y, K, dist, new_K):
+    """Pose2Sim/triangulation.py:808-813: `cv2.undistortPoints(points.astype('float32'), K, dist, None,
+    optim_K)` — OpenCV's algorithm restated: 5 fixed-point iterations of the inverse radial/tangential
+    model in double, re-projection with the new camera matrix, float32 result.  (cv2 itself is absent
+    from this restatement on purpose; tests compare it with cv2 where cv2 is importable.)"""
+    k = np.zeros(8)
+    k[:len(dist)] = np.asarray(dist, float).reshape(-1)
+    u = np.asarray(x, np.float32).astype(np.float64)
+    v = np.asarray(y, np.float32).astype(np.float64)
+    x0 = (u - K[0][2]) * (1.0 / K[0][0])
+    y0 = (v - K[1][2]) * (1.0 / K[1][1])
+    xx, yy = x0.copy(), y0.copy()
+    with np.errstate(all="ignore"):
+        for _ in range(5):
+            r2 = xx * xx + yy * yy
+            icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+            dx = 2 * k[2] * xx * yy + k[3] * (r2 + 2 * xx * xx)
+            dy = k[2] * (r2 + 2 * yy * yy) + 2 * k[3] * xx * yy
+            xx, yy = (x0 - dx) * icdist, (y0 - dy) * icdist
+        nk = np.asarray(new_K, float)
+        ww = 1.0 / (nk[2, 0] * xx + nk[2, 1] * yy + nk[2, 2])
+        ox = (nk[0, 0] * xx + nk[0, 1] * yy + nk[0, 2]) * ww
+        oy = (nk[1, 0] * xx + nk[1, 1] * yy + nk[1, 2]) * ww
+    return ox.astype(np.float32), oy.astype(np.float32)
+
+
+def project_distorted(lens, Q):
+    """Pose2Sim/triangulation.py:472-476: `cv2.projectPoints(Q, R, T, K, dist)` — pinhole projection
+    followed by OpenCV's radial/tangential model (k1 k2 p1 p2 k3 k4 k5 k6)."""
+    k = np.zeros(8)
+    k[:len(lens["dist"])] = np.asarray(lens["dist"], float).reshape(-1)
+    K = lens["K"]
+    with np.errstate(all="ignore"):
+        X = np.asarray(lens["R"], float) @ np.asarray(Q[:3], float) + np.asarray(lens["T"], float)
+        x, y = X[0] / X[2], X[1] / X[2]
+        r2 = x * x + y * y
+        r4, r6 = r2 * r2, r2 * r2 * r2
+        a1, a2, a3 = 2 * x * y, r2 + 2 * x * x, r2 + 2 * y * y
+        s = (1 + k[0] * r2 + k[1] * r4 + k[4] * r6) / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6)
+        xd = x * s + k[2] * a1 + k[3] * a2
+        yd = y * s + k[2] * a3 + k[3] * a1
+        return xd * K[0][0] + K[0][2], yd * K[1][1] + K[1][2]
+
+
+def solve_subset(P, x, y, w, cams, lens=None):
     """DLT + reprojection + mean pixel error over the cameras `cams` (ascending indices).
 
     Pose2Sim/triangulation.py:469 (DLT), :478 (reprojection), :485-489 (mean distance).
     Zero cameras -> mean of an empty list = NaN; one camera -> NaN point -> distance inf.
+    `lens` (undistort_points): the re-projection goes through the lens model (:472-476).
     """
     P_sub = [P[c] for c in cams]
     xs = [x[c] for c in cams]
     ys = [y[c] for c in cams]
     ws = [w[c] for c in cams]
     Q = weighted_dlt(P_sub, xs, ys, ws)
-    xc, yc = reproject(P_sub, Q)
+    if lens is not None:
+        proj = [project_distorted(lens[c], Q) for c in cams]
+        xc, yc = [p[0] for p in proj], [p[1] for p in proj]
+    else:
+        xc, yc = reproject(P_sub, Q)
     d = [pixel_distance((xs[i], ys[i]), (xc[i], yc[i])) for i in range(len(cams))]
     err = float(np.mean(d)) if len(d) else float("nan")
     return Q, err
@@ -90,7 +139,7 @@ def solve_subset(P, x, y, w, cams):
 # triangulation exclusion search  (Pose2Sim/triangulation.py:363-604, handle_LR_swap and
 # undistort_points off, as in every shipped config: SURVEY.md §5)
 # ---------------------------------------------------------------------------------------------
-def triangulate_unit(x, y, w, P, thr, min_cams):
+def triangulate_unit(x, y, w, P, thr, min_cams, lens=None):
     """One (frame, person, keypoint) unit.  Returns (Q[3], err, nb_cams_excluded, id_excluded_cams).
 
     Follows `triangulation_from_best_cameras`:
@@ -129,7 +178,7 @@ def triangulate_unit(x, y, w, P, thr, min_cams):
             wl = w.copy()
             wl[list(cand)] = np.nan
             cams = [c for c in range(C) if not np.isnan(wl[c]) and wl[c] != 0.0]
-            Qc, ec = solve_subset(P, x, y, w, cams)
+            Qc, ec = solve_subset(P, x, y, w, cams, lens)
             Qs.append(Qc)
             errs.append(ec)
         errs = np.array(errs)
@@ -155,7 +204,7 @@ def triangulate_unit(x, y, w, P, thr, min_cams):
     return Q, err, nexcl, ids
 
 
-def triangulate_units(x, y, w, P, thr, min_cams):
+def triangulate_units(x, y, w, P, thr, min_cams, lens=None):
     """Batched convenience wrapper: x, y, w are [U, C]; returns (Q[U,3], err[U], nexcl[U], mask[U])
     with mask bit c set iff camera c is in `id_excluded_cams`."""
     U = x.shape[0]
@@ -164,7 +213,7 @@ def triangulate_units(x, y, w, P, thr, min_cams):
     nexcl = np.empty(U, np.int32)
     mask = np.zeros(U, np.uint32)
     for u in range(U):
-        q, e, n, ids = triangulate_unit(x[u], y[u], w[u], P, thr, min_cams)
+        q, e, n, ids = triangulate_unit(x[u], y[u], w[u], P, thr, min_cams, lens)
         Q[u], err[u], nexcl[u] = q, e, n
         m = 0
         for c in ids:

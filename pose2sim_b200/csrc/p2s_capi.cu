@@ -128,14 +128,14 @@ int check_tri_args(int n_cams, int min_cams, long long n_units) {
     return P2S_OK;
 }
 
-int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, long long n_units, int n_cams,
+int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
                         double thr, int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask,
                         unsigned long long *stats, cudaStream_t stream) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_units == 0) return P2S_OK;
     p2s::TriLaunch L;
-    L.obs = obs; L.P = P; L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams;
+    L.obs = obs; L.P = P; L.lens = lens; L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams;
     L.solver = h->solver; L.sm_count = h->prop.multiProcessorCount;
     L.thr = thr; L.band_eps = h->band_eps;
     const SubsetTable &t = h->tables[n_cams];
@@ -268,32 +268,61 @@ size_t p2s_obs_bytes(long long n_units, int n_cams) {
     return (size_t)n_units * (size_t)n_cams * 16u;
 }
 
-int p2s_stage_observations_device(p2s_handle *h, const float *x, const float *y, const float *lik,
-                                  long long n_units, int n_cams, double lik_thr, void *obs_out, void *stream) {
+static int stage_device(p2s_handle *h, const float *x, const float *y, const float *lik, long long n_units, int n_cams,
+                        double lik_thr, const p2s_camera_model *lens, void *obs_out, void *stream) {
     if (!h || !x || !y || !lik || !obs_out) return P2S_EINVAL;
     if (n_cams < 1 || n_cams > P2S_MAX_CAMS || n_units < 0) return P2S_EINVAL;
     if (n_units == 0) return P2S_OK;
     P2S_CUDA(h, cudaSetDevice(h->device));
-    P2S_CUDA(h, p2s::launch_stage(x, y, lik, n_units, n_cams, lik_thr, obs_out, h->prop.multiProcessorCount, (cudaStream_t)stream));
+    P2S_CUDA(h, p2s::launch_stage(x, y, lik, n_units, n_cams, lik_thr, lens, obs_out, h->prop.multiProcessorCount, (cudaStream_t)stream));
     h->launches += 1;
     return P2S_OK;
+}
+
+int p2s_stage_observations_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                  long long n_units, int n_cams, double lik_thr, void *obs_out, void *stream) {
+    return stage_device(h, x, y, lik, n_units, n_cams, lik_thr, nullptr, obs_out, stream);
+}
+
+int p2s_stage_undistort_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                               long long n_units, int n_cams, double lik_thr, const p2s_camera_model *lens,
+                               void *obs_out, void *stream) {
+    if (!lens) return P2S_EINVAL;
+    return stage_device(h, x, y, lik, n_units, n_cams, lik_thr, lens, obs_out, stream);
+}
+
+static int triangulate_device(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens,
+                              long long n_units, int n_cams, double reproj_thr, int min_cams, double *out_Q,
+                              double *out_err, uint8_t *out_nexcl, uint32_t *out_mask, unsigned long long *stats,
+                              void *stream) {
+    if (!h || !P || (n_units > 0 && (!obs || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    return enqueue_triangulate(h, obs, P, lens, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl, out_mask,
+                               stats, (cudaStream_t)stream);
 }
 
 int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P, long long n_units, int n_cams,
                            double reproj_thr, int min_cams, double *out_Q, double *out_err, uint8_t *out_nexcl,
                            uint32_t *out_mask, unsigned long long *stats, void *stream) {
-    if (!h || !P || (n_units > 0 && (!obs || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
-    int rc = check_tri_args(n_cams, min_cams, n_units);
-    if (rc) return rc;
-    P2S_CUDA(h, cudaSetDevice(h->device));
-    return enqueue_triangulate(h, obs, P, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl, out_mask,
-                               stats, (cudaStream_t)stream);
+    return triangulate_device(h, obs, P, nullptr, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
+                              out_mask, stats, stream);
 }
 
-int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik, const double *P,
-                         long long n_units, int n_cams, double lik_thr, double reproj_thr, int min_cams,
-                         double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
-                         unsigned long long *stats) {
+int p2s_triangulate_distorted_device(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens,
+                                     long long n_units, int n_cams, double reproj_thr, int min_cams,
+                                     double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                     unsigned long long *stats, void *stream) {
+    if (!lens) return P2S_EINVAL;
+    return triangulate_device(h, obs, P, lens, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
+                              out_mask, stats, stream);
+}
+
+static int triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik, const double *P,
+                            const p2s_camera_model *lens, long long n_units, int n_cams, double lik_thr,
+                            double reproj_thr, int min_cams, double *out_Q, double *out_err, uint8_t *out_nexcl,
+                            uint32_t *out_mask, unsigned long long *stats) {
     if (!h || !P || (n_units > 0 && (!x || !y || !lik || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
     int rc = check_tri_args(n_cams, min_cams, n_units);
     if (rc) return rc;
@@ -314,9 +343,9 @@ int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const fl
         P2S_CUDA(h, cudaMemcpyAsync(s.y.p, y + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.lik.p, lik + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, p2s::launch_stage((const float *)s.x.p, (const float *)s.y.p, (const float *)s.lik.p, nu, n_cams,
-                                     lik_thr, s.obs.p, h->prop.multiProcessorCount, s.stream));
+                                     lik_thr, lens, s.obs.p, h->prop.multiProcessorCount, s.stream));
         h->launches += 1;
-        rc = enqueue_triangulate(h, s.obs.p, P, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
+        rc = enqueue_triangulate(h, s.obs.p, P, lens, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
                                  (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream);
         if (rc) return rc;
         P2S_CUDA(h, cudaMemcpyAsync(out_Q + u0 * 3, s.Q.p, nu * 24, cudaMemcpyDeviceToHost, s.stream));
@@ -327,6 +356,24 @@ int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const fl
     for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
     if (stats) P2S_CUDA(h, cudaMemcpy(stats, h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return P2S_OK;
+}
+
+int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik, const double *P,
+                         long long n_units, int n_cams, double lik_thr, double reproj_thr, int min_cams,
+                         double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                         unsigned long long *stats) {
+    return triangulate_host(h, x, y, lik, P, nullptr, n_units, n_cams, lik_thr, reproj_thr, min_cams, out_Q, out_err,
+                            out_nexcl, out_mask, stats);
+}
+
+int p2s_triangulate_undistort_host(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                   const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
+                                   double lik_thr, double reproj_thr, int min_cams,
+                                   double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                   unsigned long long *stats) {
+    if (!lens) return P2S_EINVAL;
+    return triangulate_host(h, x, y, lik, P, lens, n_units, n_cams, lik_thr, reproj_thr, min_cams, out_Q, out_err,
+                            out_nexcl, out_mask, stats);
 }
 
 int p2s_associate_device(p2s_handle *h, const void *obs, const int32_t *count, const double *P, long long n_frames,

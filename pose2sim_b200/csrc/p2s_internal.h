@@ -9,6 +9,7 @@ namespace p2s {
 struct TriLaunch {
     const void *obs;              // float4 [n_cams][n_units], device
     const double *P;              // host, n_cams x 12
+    const p2s_camera_model *lens; // host, n_cams lens models (undistort_points) or null
     long long n_units;
     int n_cams, min_cams, solver, sm_count;
     double thr, band_eps;
@@ -43,7 +44,7 @@ struct AssocLaunch {
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out);
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
-                         double lik_thr, void *out, int sm_count, cudaStream_t stream);
+                         double lik_thr, const p2s_camera_model *lens, void *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_associate(const AssocLaunch &L, int *grid_out);
 

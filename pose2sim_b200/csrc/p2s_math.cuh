@@ -222,6 +222,43 @@ __device__ __forceinline__ double reproj_distance(const double *Pc, double qx, d
     return N * r;
 }
 
+// Lens model of one camera for `undistort_points = true` (OpenCV's pinhole + radial/tangential model).
+struct LensParams {
+    double R[9], T[3];           // world -> camera
+    double fx, fy, cx, cy;       // ORIGINAL intrinsics (cv2.projectPoints re-projects with these)
+    double k[8];                 // k1 k2 p1 p2 k3 k4 k5 k6
+};
+template <int CMAX>
+struct LensSet { LensParams cam[CMAX]; };
+
+// Pixel distance between the (undistorted) observation and the DISTORTED re-projection of Q — what
+// the reference compares when undistort_points is on (triangulation.py:472-476, cv2.projectPoints with
+// the original K and distortion coefficients).
+__device__ __forceinline__ double reproj_distance_distorted(const LensParams &L, double qx, double qy, double qz,
+                                                            double ox, double oy) {
+    const double X = fma(L.R[0], qx, fma(L.R[1], qy, fma(L.R[2], qz, L.T[0])));
+    const double Y = fma(L.R[3], qx, fma(L.R[4], qy, fma(L.R[5], qz, L.T[1])));
+    const double Z = fma(L.R[6], qx, fma(L.R[7], qy, fma(L.R[8], qz, L.T[2])));
+    const double iz = rcp_fast(Z);
+    const double x = X * iz, y = Y * iz;
+    const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2.0 * x * y, a2 = fma(2.0 * x, x, r2), a3 = fma(2.0 * y, y, r2);
+    const double cdist = fma(L.k[4], r6, fma(L.k[1], r4, fma(L.k[0], r2, 1.0)));
+    const double icd2 = rcp_fast(fma(L.k[7], r6, fma(L.k[6], r4, fma(L.k[5], r2, 1.0))));
+    const double s = cdist * icd2;
+    const double xd = fma(x, s, fma(L.k[2], a1, L.k[3] * a2));
+    const double yd = fma(y, s, fma(L.k[2], a3, L.k[3] * a1));
+    const double dx = ox - fma(xd, L.fx, L.cx), dy = oy - fma(yd, L.fy, L.cy);
+    const double N = fma(dx, dx, dy * dy);
+    const double S = N + 1e-300;
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(S));
+    const double t = S * r;
+    const double e = fma(-t, r, 1.0);
+    r = fma(r * e, fma(0.375, e, 0.5), r);
+    return N * r;
+}
+
 // sum / m for a small positive integer m without the IEEE division slow path: reciprocal + one
 // residual correction (correctly rounded except in rare half-way cases).
 __device__ __forceinline__ double div_small(double sum, double m) {

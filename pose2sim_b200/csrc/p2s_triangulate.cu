@@ -25,6 +25,8 @@
 //     warp shuffles; the winning lane publishes Q / error / masks to the unit's slot in shared
 //     memory;
 //   * projection matrices are a by-value kernel parameter => constant-bank operands.
+#include <cstring>
+
 #include "p2s_math.cuh"
 #include "p2s_internal.h"
 
@@ -88,21 +90,28 @@ __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX>
 
 // Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded
 // ones are dropped by a select: no branch, full instruction-level parallelism across cameras).
-template <int CMAX>
-__device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const float4 (*obs)[32], int ul,
-                                                    uint32_t valid, int m, double qx, double qy, double qz) {
+template <int CMAX, bool DISTORT>
+__device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const LensSet<DISTORT ? CMAX : 1> &lens,
+                                                    const float4 (*obs)[32], int ul, uint32_t valid, int m,
+                                                    double qx, double qy, double qz) {
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
         const float4 o = obs[c][ul];
-        const double dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
+        double dist;
+        if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, (double)o.x, (double)o.y);
+        else dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
         sum += ((valid >> c) & 1u) ? dist : 0.0;
     }
     return div_small(sum, (double)m);
 }
 
-template <int CMAX, int SOLVER>
-__global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams, const TriArgs a) {
+// DISTORT: `undistort_points = true` — observations were undistorted by the stage kernel, P is built on
+// the optimal new camera matrix, and the error is measured against the distorted re-projection.
+template <int CMAX, int SOLVER, bool DISTORT>
+__global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams,
+                                                                               const LensSet<DISTORT ? CMAX : 1> lens,
+                                                                               const TriArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                             int it;
                             if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            e = mean_reproj_error<CMAX>(cams, S.obs, ul, valid, m, cqx, cqy, cqz);
+                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.obs, ul, valid, m, cqx, cqy, cqz);
                             t_iters += (uint32_t)it;
                             t_solved += 1u;
                         }
@@ -380,9 +389,49 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
 }
 
 // ---- staging: [U][C] planes -> float4 [C][U] with the likelihood gate (triangulation.py:817-821) ----
+// UNDISTORT: the points are first undistorted like cv2.undistortPoints(points.astype('float32'), K, dist,
+// None, optim_K) (triangulation.py:808-813): OpenCV's 5 fixed-point iterations in double, re-projection
+// with the new camera matrix, result rounded to float32.  The arithmetic is written with explicit
+// round-to-nearest multiplies / adds in OpenCV's expression order (no FMA contraction), so the float32
+// results equal cv2's bit for bit (tests/test_gpu_undistort.py).
+struct UndistortCam {
+    double cx, cy, ifx, ify;
+    double k[8];
+    double nk[9];                // new camera matrix, row-major
+};
+struct UndistortSet { UndistortCam cam[P2S_MAX_CAMS]; };
+
+__device__ __forceinline__ void undistort_point(const UndistortCam &c, float &px, float &py) {
+    const double u = (double)px, v = (double)py;
+    const double x0 = __dmul_rn(__dsub_rn(u, c.cx), c.ifx), y0 = __dmul_rn(__dsub_rn(v, c.cy), c.ify);
+    double x = x0, y = y0;
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k[7], r2), c.k[6]), r2), c.k[5]), r2));
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c.k[4], r2), c.k[1]), r2), c.k[0]), r2));
+        const double icdist = __ddiv_rn(num, den);
+        if (icdist < 0.0) { x = x0; y = y0; break; }
+        // deltaX = 2 p1 x y + p2 (r2 + 2 x x);  deltaY = p1 (r2 + 2 y y) + 2 p2 x y   (k[2] = p1, k[3] = p2)
+        const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, c.k[2]), x), y),
+                                    __dmul_rn(c.k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+        const double dY = __dadd_rn(__dmul_rn(c.k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                    __dmul_rn(__dmul_rn(__dmul_rn(2.0, c.k[3]), x), y));
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(c.nk[0], x), __dmul_rn(c.nk[1], y)), c.nk[2]);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(c.nk[3], x), __dmul_rn(c.nk[4], y)), c.nk[5]);
+    const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(c.nk[6], x), __dmul_rn(c.nk[7], y)), c.nk[8]));
+    px = (float)__dmul_rn(xx, ww);
+    py = (float)__dmul_rn(yy, ww);
+}
+
+template <bool UNDISTORT>
 __global__ void __launch_bounds__(256) stage_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                     const float *__restrict__ lik, long long n_units, int n_cams,
-                                                    double lik_thr, int gate, float4 *__restrict__ out) {
+                                                    double lik_thr, int gate, const UndistortSet lens,
+                                                    float4 *__restrict__ out) {
     extern __shared__ float sh[];                 // 3 planes of 256 * n_cams floats (+1 pad per row)
     const int C = n_cams;
     const int ld = C + 1;
@@ -394,8 +443,10 @@ __global__ void __launch_bounds__(256) stage_kernel(const float *__restrict__ x,
         const int n = nu * C;
         for (int i = threadIdx.x; i < n; i += 256) {       // coalesced reads of the row-major planes
             const int uu = i / C, cc = i - uu * C;
-            sx[uu * ld + cc] = x[u0 * C + i];
-            sy[uu * ld + cc] = y[u0 * C + i];
+            float vx = x[u0 * C + i], vy = y[u0 * C + i];
+            if (UNDISTORT) undistort_point(lens.cam[cc], vx, vy);
+            sx[uu * ld + cc] = vx;
+            sy[uu * ld + cc] = vy;
             sl[uu * ld + cc] = lik[u0 * C + i];
         }
         __syncthreads();
@@ -425,6 +476,25 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 }
 
 // ---- host-side launchers ----------------------------------------------------------------------------
+template <class Kern, class... Args>
+static cudaError_t launch_persistent(Kern kern, size_t smem, const TriLaunch &L, int *grid_out, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((L.n_units + 31) / 32 + 3) / 4;
+    long long grid = (long long)L.sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    kern<<<(unsigned)grid, 128, smem, L.stream>>>(args...);
+    return cudaGetLastError();
+}
+
 template <int CMAX>
 static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     CamParams<CMAX> cams;
@@ -438,41 +508,23 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;
-    cudaError_t e;
-    if (L.solver == 0) {
-        auto kern = triangulate_kernel<CMAX, 0>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        long long want = ((L.n_units + 31) / 32 + 3) / 4;
-        long long grid = (long long)L.sm_count * per_sm;
-        if (grid > want) grid = want;
-        if (grid < 1) grid = 1;
-        if (grid_out) *grid_out = (int)grid;
-        kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
-    } else {
-        auto kern = triangulate_kernel<CMAX, 1>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        long long want = ((L.n_units + 31) / 32 + 3) / 4;
-        long long grid = (long long)L.sm_count * per_sm;
-        if (grid > want) grid = want;
-        if (grid < 1) grid = 1;
-        if (grid_out) *grid_out = (int)grid;
-        kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
+    if (L.lens) {                                             // undistort_points: distorted re-projection
+        LensSet<CMAX> lens;
+        std::memset(&lens, 0, sizeof lens);
+        for (int c = 0; c < L.n_cams; ++c) {
+            const p2s_camera_model &m = L.lens[c];
+            LensParams &o = lens.cam[c];
+            for (int j = 0; j < 9; ++j) o.R[j] = m.R[j];
+            for (int j = 0; j < 3; ++j) o.T[j] = m.T[j];
+            o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
+            for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
+        }
+        return launch_persistent(triangulate_kernel<CMAX, 0, true>, smem, L, grid_out, cams, lens, a);
     }
-    return cudaGetLastError();
+    LensSet<1> none;
+    std::memset(&none, 0, sizeof none);
+    if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false>, smem, L, grid_out, cams, none, a);
+    return launch_persistent(triangulate_kernel<CMAX, 1, false>, smem, L, grid_out, cams, none, a);
 }
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
@@ -483,16 +535,33 @@ cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
 }
 
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
-                         double lik_thr, void *out, int sm_count, cudaStream_t stream) {
+                         double lik_thr, const p2s_camera_model *lens, void *out, int sm_count, cudaStream_t stream) {
     const int gate = (lik_thr == lik_thr) && !(lik_thr == -INFINITY);
     const size_t smem = (size_t)3 * 256 * (n_cams + 1) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     long long blocks = (n_units + 255) / 256;
     long long grid = (long long)sm_count * 8;
     if (grid > blocks) grid = blocks;
     if (grid < 1) grid = 1;
-    stage_kernel<<<(unsigned)grid, 256, smem, stream>>>(x, y, lik, n_units, n_cams, lik_thr, gate, (float4 *)out);
+    static UndistortSet set;                                  // zero-initialised; filled per call when used
+    cudaError_t e;
+    if (lens) {
+        UndistortSet u;
+        std::memset(&u, 0, sizeof u);
+        for (int c = 0; c < n_cams; ++c) {
+            const p2s_camera_model &m = lens[c];
+            UndistortCam &o = u.cam[c];
+            o.cx = m.K[2]; o.cy = m.K[5]; o.ifx = 1.0 / m.K[0]; o.ify = 1.0 / m.K[4];
+            for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
+            for (int j = 0; j < 9; ++j) o.nk[j] = m.newK[j];
+        }
+        e = cudaFuncSetAttribute(stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        stage_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(x, y, lik, n_units, n_cams, lik_thr, gate, u, (float4 *)out);
+    } else {
+        e = cudaFuncSetAttribute(stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        stage_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(x, y, lik, n_units, n_cams, lik_thr, gate, set, (float4 *)out);
+    }
     return cudaGetLastError();
 }
 

@@ -32,6 +32,23 @@ def _as_P(P, n_cams):
     return P
 
 
+def lens_array(models):
+    """List of dicts {K[3,3], dist[<=8], R[3,3], T[3], newK[3,3]} -> ctypes array of p2s_camera_model."""
+    arr = (_lib.CameraModel * len(models))()
+    for m, o in zip(models, arr):
+        o.K[:] = np.asarray(m["K"], float).reshape(9)
+        d = np.zeros(8)
+        dist = np.asarray(m["dist"], float).reshape(-1)
+        if dist.size > 8:
+            raise ValueError("at most 8 distortion coefficients (k1 k2 p1 p2 k3 k4 k5 k6) are supported")
+        d[:dist.size] = dist
+        o.dist[:] = d
+        o.R[:] = np.asarray(m["R"], float).reshape(9)
+        o.T[:] = np.asarray(m["T"], float).reshape(3)
+        o.newK[:] = np.asarray(m["newK"], float).reshape(9)
+    return arr
+
+
 def _ptr(a):
     """Raw pointer of a numpy array or torch tensor (None -> NULL)."""
     if a is None:
@@ -92,9 +109,10 @@ class Engine:
         return _torch().cuda.current_stream(self.device).cuda_stream
 
     # ---- device-resident path ------------------------------------------------------------------------
-    def stage_observations(self, x, y, lik, lik_thr=None, out=None):
+    def stage_observations(self, x, y, lik, lik_thr=None, out=None, lens=None):
         """x, y, lik: CUDA float32 tensors [U, C] -> staged float4 tensor [C, U, 4] with the
-        likelihood gate of triangulation.py:817-821 (lik_thr=None: no gate)."""
+        likelihood gate of triangulation.py:817-821 (lik_thr=None: no gate).  lens: list of camera
+        models -> the points are undistorted first (undistort_points, triangulation.py:808-813)."""
         torch = _torch()
         U, Cn = x.shape
         for t in (x, y, lik):
@@ -102,11 +120,16 @@ class Engine:
         if out is None:
             out = torch.empty((Cn, U, 4), dtype=torch.float32, device=x.device)
         thr = float("-inf") if lik_thr is None else float(lik_thr)
+        if lens is not None:
+            arr = lens_array(lens)
+            _lib.check(self.h, self.lib.p2s_stage_undistort_device(self.h, _ptr(x), _ptr(y), _ptr(lik), U, Cn, thr,
+                                                                   C.cast(arr, C.c_void_p), _ptr(out), self._stream()))
+            return out
         _lib.check(self.h, self.lib.p2s_stage_observations_device(self.h, _ptr(x), _ptr(y), _ptr(lik), U, Cn, thr,
                                                                   _ptr(out), self._stream()))
         return out
 
-    def triangulate(self, obs, P, reproj_thr, min_cams, out=None, stats=None):
+    def triangulate(self, obs, P, reproj_thr, min_cams, out=None, stats=None, lens=None):
         """obs: staged CUDA tensor [C, U, 4]; returns dict of CUDA tensors Q[U,3] f64, err[U] f64,
         nexcl[U] u8, mask[U] i32 (bit pattern of the uint32 mask).  Asynchronous on the current stream."""
         torch = _torch()
@@ -119,6 +142,12 @@ class Engine:
                    "nexcl": torch.empty((U,), dtype=torch.uint8, device=dev),
                    "mask": torch.empty((U,), dtype=torch.int32, device=dev)}
         Pm = _as_P(P, Cn)
+        if lens is not None:
+            arr = lens_array(lens)
+            _lib.check(self.h, self.lib.p2s_triangulate_distorted_device(
+                self.h, _ptr(obs), Pm.ctypes.data, C.cast(arr, C.c_void_p), U, Cn, float(reproj_thr), int(min_cams),
+                _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
+            return out
         _lib.check(self.h, self.lib.p2s_triangulate_device(
             self.h, _ptr(obs), Pm.ctypes.data, U, Cn, float(reproj_thr), int(min_cams),
             _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
@@ -129,7 +158,7 @@ class Engine:
         return torch.zeros(_lib.P2S_STAT_COUNT, dtype=torch.int64, device=f"cuda:{self.device}")
 
     # ---- host-buffer path (what triangulate_all calls) ---------------------------------------------
-    def triangulate_host(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, want_stats=True):
+    def triangulate_host(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, want_stats=True, lens=None):
         """x, y, lik: host float32 arrays [U, C] (numpy, or pinned torch CPU tensors).  Returns dict of
         numpy arrays Q[U,3], err[U], nexcl[U] (uint8), mask[U] (uint32) and `stats`."""
         U, Cn = x.shape
@@ -142,9 +171,16 @@ class Engine:
         stats = np.zeros(_lib.P2S_STAT_COUNT, np.uint64) if want_stats else None
         Pm = _as_P(P, Cn)
         thr = float("-inf") if lik_thr is None else float(lik_thr)
-        _lib.check(self.h, self.lib.p2s_triangulate_host(
-            self.h, _ptr(xs), _ptr(ys), _ptr(ls), Pm.ctypes.data, U, Cn, thr, float(reproj_thr), int(min_cams),
-            _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats)))
+        if lens is not None:
+            arr = lens_array(lens)
+            _lib.check(self.h, self.lib.p2s_triangulate_undistort_host(
+                self.h, _ptr(xs), _ptr(ys), _ptr(ls), Pm.ctypes.data, C.cast(arr, C.c_void_p), U, Cn, thr,
+                float(reproj_thr), int(min_cams), _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]),
+                _ptr(out["mask"]), _ptr(stats)))
+        else:
+            _lib.check(self.h, self.lib.p2s_triangulate_host(
+                self.h, _ptr(xs), _ptr(ys), _ptr(ls), Pm.ctypes.data, U, Cn, thr, float(reproj_thr), int(min_cams),
+                _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats)))
         if want_stats:
             out["stats"] = stats_dict(stats)
         return out

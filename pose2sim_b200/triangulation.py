@@ -9,8 +9,9 @@ Pose2Sim/triangulation.py:656-959, with the per-(frame, person, keypoint) Python
     write_outputs()     host   :877-959   interpolation, trimming, fill, TRC (+C3D), exclusion recap
 
 There is no CPU implementation of the search in this package: `solve_units` needs the built CUDA
-library and a B200 and raises otherwise.  `handle_LR_swap` / `undistort_points` under
-`[triangulation]` (off in every shipped config) are refused loudly.
+library and a B200 and raises otherwise.  `[triangulation] undistort_points = true` runs on the device
+too (points undistorted by the stage kernel, distorted re-projection in the search kernel);
+`handle_LR_swap = true` (off in every shipped config) is refused loudly.
 """
 import glob
 import logging
@@ -58,8 +59,6 @@ def read_settings(config_dict):
 
 def refuse_unsupported(s):
     """not built yet -> refuse, never fall back to a CPU path."""
-    if s["undistort_points"]:
-        raise NotImplementedError("[triangulation] undistort_points = true is not available in the B200 path")
     if s["handle_LR_swap"]:
         raise NotImplementedError("[triangulation] handle_LR_swap = true is not available in the B200 path")
 
@@ -69,7 +68,7 @@ def refuse_unsupported(s):
 # ---------------------------------------------------------------------------------------------------
 class StagedProject:
     """Everything `solve_units` / `write_outputs` need; arrays are unit-major, camera fastest."""
-    __slots__ = ("settings", "calib_file", "P", "keypoints_ids", "keypoints_names", "cam_dirs", "input_dir",
+    __slots__ = ("settings", "calib_file", "P", "lens", "keypoints_ids", "keypoints_names", "cam_dirs", "input_dir",
                  "f_range", "n_cams", "n_persons", "x", "y", "lik", "inexact")
 
 
@@ -78,7 +77,8 @@ def stage_project(config_dict):
     refuse_unsupported(s)
     session_dir = _calib.session_dir_of(s["project_dir"])
     calib_file = _calib.find_calibration_file(session_dir)
-    P = _calib.compute_P(calib_file, undistort=False)
+    P = _calib.compute_P(calib_file, undistort=bool(s["undistort_points"]))
+    lens = _calib.camera_models(calib_file) if s["undistort_points"] else None
     ids, names = _skel.keypoints(s["pose_model"], config_dict)
 
     dirs = _stg.PoseDirs(s["project_dir"])
@@ -94,7 +94,7 @@ def stage_project(config_dict):
 
     x, y, lik, inexact = _stg.stage_triangulation(input_dir, cam_dirs, files, f_range, ids, n_persons)
     st = StagedProject()
-    st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
+    st.settings, st.calib_file, st.P, st.lens = s, calib_file, np.asarray(P, dtype=np.float64), lens
     st.keypoints_ids, st.keypoints_names = ids, names
     st.cam_dirs, st.input_dir, st.f_range, st.n_cams, st.n_persons = cam_dirs, input_dir, list(f_range), n_cams, n_persons
     st.inexact = inexact
@@ -117,7 +117,7 @@ def solve_units(st, engine=None):
     U = F * N * K
     s = st.settings
     out = eng.triangulate_host(st.x.reshape(U, C), st.y.reshape(U, C), st.lik.reshape(U, C), st.P,
-                               s["lik_thr"], s["reproj_thr"], s["min_cams"])
+                               s["lik_thr"], s["reproj_thr"], s["min_cams"], lens=st.lens)
     return {"Q": out["Q"].reshape(F, N, K, 3), "err": out["err"].reshape(F, N, K),
             "nexcl": out["nexcl"].reshape(F, N, K).astype(np.int64), "mask": out["mask"].reshape(F, N, K),
             "stats": out.get("stats")}

@@ -21,17 +21,21 @@ def oracle_units(st):
     U = F * N * K
     s = st.settings
     x, y, w = (a.reshape(U, C).astype(np.float64) for a in (st.x, st.y, st.lik))
+    if st.lens is not None:                                 # undistort_points (triangulation.py:808-813)
+        for c, L in enumerate(st.lens):
+            ux, uy = orc.undistort_points(x[:, c], y[:, c], L["K"], L["dist"], L["newK"])
+            x[:, c], y[:, c] = ux, uy
     with np.errstate(invalid="ignore"):
         low = w < s["lik_thr"]                              # triangulation.py:817-821
     x[low] = np.nan; y[low] = np.nan; w[low] = np.nan
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"])
+        Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"], lens=st.lens)
     return {"Q": Q.reshape(F, N, K, 3), "err": err.reshape(F, N, K), "nexcl": nexcl.reshape(F, N, K).astype(np.int64),
             "mask": mask.reshape(F, N, K)}
 
 
-@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi"])
+@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi", "e2e_tri_undistort"])
 def test_triangulation_host_pipeline_matches_reference_trc(golden, tmp_path, tag, caplog):
     g = golden(tag + ".npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
@@ -92,10 +96,6 @@ def test_valid_chunk_and_gap_filling():
 def test_refuses_unbuilt_modes(golden, tmp_path):
     g = golden("e2e_tri_single.npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
-    cfg["triangulation"]["undistort_points"] = True
-    with in_dir(proj), pytest.raises(NotImplementedError):
-        tri.stage_project(cfg)
-    cfg["triangulation"]["undistort_points"] = False
     cfg["triangulation"]["handle_LR_swap"] = True
     with in_dir(proj), pytest.raises(NotImplementedError):
         tri.stage_project(cfg)

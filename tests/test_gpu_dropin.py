@@ -9,7 +9,7 @@ from dropin_util import assert_trc_equal, associated_people, golden_trcs, in_dir
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi"])
+@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi", "e2e_tri_undistort"])
 def test_triangulate_all_writes_the_reference_trc(golden, tmp_path, tag):
     import pose2sim_b200
     g = golden(tag + ".npz")

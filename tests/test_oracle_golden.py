@@ -137,3 +137,37 @@ def test_c_and_numpy_oracles_agree_on_synthetic():
         q, e, nx, m, lv, nc = co.triangulate_units(wl["x"], wl["y"], wl["lik"], wl["P"], 15.0, mc)
         assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask)
         assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+
+
+def test_undistort_mode_units(golden):
+    """`undistort_points = true`: the restated lens inversion (vs cv2.undistortPoints, stored by the
+    generator) and the search with distorted re-projection (vs triangulation_from_best_cameras)."""
+    import io
+    import tomllib
+    from pose2sim_b200 import calib
+    g = golden("e2e_tri_undistort.npz")
+    lens = []
+    toml = tomllib.load(io.BytesIO(str(g["calib"]).encode()))
+    for name in [str(c) for c in g["cams"]]:
+        cam = toml[name]
+        K = np.array(cam["matrix"], float)
+        lens.append({"K": K, "dist": np.array(cam["distortions"], float), "R": calib.rodrigues(cam["rotation"]),
+                     "T": np.array(cam["translation"], float),
+                     "newK": calib.optimal_new_camera_matrix(K, cam["distortions"], cam["size"])})
+    x, y, lik = g["unit_x"], g["unit_y"], g["unit_lik"]
+    ux, uy = np.empty_like(x), np.empty_like(y)
+    for c, L in enumerate(lens):
+        ux[:, c], uy[:, c] = orc.undistort_points(x[:, c], y[:, c], L["K"], L["dist"], L["newK"])
+    assert np.array_equal(ux, g["unit_ux"]) and np.array_equal(uy, g["unit_uy"])       # bit-exact vs cv2
+    P = np.stack([np.hstack([L["newK"], np.zeros((3, 1))]) @ np.vstack([np.hstack([L["R"], L["T"][:, None]]), [0, 0, 0, 1]])
+                  for L in lens])
+    assert np.allclose(P, g["unit_P"], atol=1e-9, rtol=0)
+    low = lik.astype(np.float64) < 0.3
+    gx, gy, gl = (np.where(low, np.nan, a.astype(np.float64)) for a in (ux, uy, lik))
+    sub = np.arange(0, len(gx), 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q, e, n, m = orc.triangulate_units(gx[sub], gy[sub], gl[sub], P, 15.0, 2, lens=lens)
+    assert np.array_equal(n, g["unit_nexcl"][sub]) and np.array_equal(m, g["unit_mask"][sub])
+    assert np.allclose(q, g["unit_Q"][sub], atol=Q_TOL, rtol=0, equal_nan=True)
+    assert np.allclose(e, g["unit_err"][sub], atol=E_TOL, rtol=0, equal_nan=True)
