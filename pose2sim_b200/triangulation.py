@@ -72,7 +72,20 @@ class StagedProject:
                  "f_range", "n_cams", "n_persons", "x", "y", "lik", "inexact")
 
 
-def stage_project(config_dict):
+def _world():
+    """(rank, world_size, local_rank) of an initialised torch.distributed job, else (0, 1, 0)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+    except ImportError:
+        pass
+    return 0, 1, 0
+
+
+def stage_project(config_dict, rank=0, world=1):
+    """Host staging.  With world > 1 (one process per GPU under torchrun) every rank discovers the whole
+    trial but parses only the JSON of its own contiguous frame block (sharding.frame_block)."""
     s = read_settings(config_dict)
     refuse_unsupported(s)
     session_dir = _calib.session_dir_of(s["project_dir"])
@@ -90,9 +103,23 @@ def stage_project(config_dict):
     if n_cams != len(P):
         raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
                         f"file, and {n_cams} cameras based on the number of pose folders.")
-    n_persons = _stg.count_persons(input_dir, cam_dirs, files) if s["multi_person"] else 1
+    if s["multi_person"]:
+        n_persons = _stg.count_persons(input_dir, cam_dirs, [f[rank::world] for f in files])
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([n_persons], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_persons = int(t.item())
+    else:
+        n_persons = 1
 
-    x, y, lik, inexact = _stg.stage_triangulation(input_dir, cam_dirs, files, f_range, ids, n_persons)
+    from . import sharding
+    n_frames = len(range(*f_range))
+    b0, b1 = sharding.frame_block(n_frames, rank, world)
+    my_range = [f_range[0] + b0, f_range[0] + b1]
+    x, y, lik, inexact = _stg.stage_triangulation(input_dir, cam_dirs, files, my_range, ids, n_persons)
     st = StagedProject()
     st.settings, st.calib_file, st.P, st.lens = s, calib_file, np.asarray(P, dtype=np.float64), lens
     st.keypoints_ids, st.keypoints_names = ids, names
@@ -108,11 +135,11 @@ def stage_project(config_dict):
 # ---------------------------------------------------------------------------------------------------
 # device
 # ---------------------------------------------------------------------------------------------------
-def solve_units(st, engine=None):
+def solve_units(st, engine=None, device=0):
     """ONE device call for all F*N*K units: likelihood gate (:817-821) + exclusion search (:363-604).
     Returns Q[F,N,K,3], err[F,N,K], nexcl[F,N,K] (int), mask[F,N,K] (uint32 id_excluded_cams bit sets)."""
     from . import ops
-    eng = engine if engine is not None else ops.get_engine(0)
+    eng = engine if engine is not None else ops.get_engine(device)
     F, N, K, C = st.x.shape
     U = F * N * K
     s = st.settings
@@ -453,9 +480,49 @@ def log_recap(st, r):
 
 
 # ---------------------------------------------------------------------------------------------------
+def gather_units(res, n_frames, rank, world):
+    """The ONE collective of the path: every rank's packed per-unit outputs (37 B/unit) to rank 0
+    (NCCL over NVLink on a GPU box, gloo in the CPU tests).  Returns the full result on rank 0, None
+    elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import sharding
+    F, N, K, _ = res["Q"].shape
+    per_frame = N * K
+    units = [(b - a) * per_frame for a, b in sharding.frame_blocks(n_frames, world)]
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.empty(sharding.PACK_BYTES * units[rank], dtype=torch.uint8, device=dev)
+    v = sharding.packed_views(buf, units[rank])
+    v["Q"].copy_(torch.from_numpy(np.ascontiguousarray(res["Q"].reshape(-1, 3))))
+    v["err"].copy_(torch.from_numpy(np.ascontiguousarray(res["err"].reshape(-1))))
+    v["mask"].copy_(torch.from_numpy(np.ascontiguousarray(res["mask"].reshape(-1)).view(np.int32)))
+    v["nexcl"].copy_(torch.from_numpy(np.ascontiguousarray(res["nexcl"].reshape(-1)).astype(np.uint8)))
+    bufs, _ = sharding.gather_packed(buf, units, dst=0)
+    if rank != 0:
+        return None
+    out = sharding.unpack_concat(bufs, units)
+    return {"Q": out["Q"].reshape(n_frames, N, K, 3), "err": out["err"].reshape(n_frames, N, K),
+            "nexcl": out["nexcl"].reshape(n_frames, N, K).astype(np.int64), "mask": out["mask"].reshape(n_frames, N, K)}
+
+
 def triangulate_all(config_dict):
     """Same contract as Pose2Sim/triangulation.py:656: reads the calibration TOML and the per-camera
-    OpenPose JSON of the trial, writes `pose-3d/*.trc`, logs the recap.  Returns None."""
+    OpenPose JSON of the trial, writes `pose-3d/*.trc`, logs the recap.  Returns None.
+
+    Under torchrun (torch.distributed initialised, one process per GPU) the frames are sharded in
+    contiguous blocks over the ranks, each rank stages and solves its block on its own GPU, the packed
+    outputs are gathered once on rank 0, which alone writes the files."""
+    rank, world, local = _world()
+    if world > 1:
+        st = stage_project(config_dict, rank, world)
+        res = solve_units(st, device=local)
+        res = gather_units(res, len(range(*st.f_range)), rank, world)
+        if rank != 0:
+            return
+        if st.settings["multi_person"]:
+            res = reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
+        write_outputs(st, res)
+        return
     st = stage_project(config_dict)
     res = solve_units(st)
     if st.settings["multi_person"]:

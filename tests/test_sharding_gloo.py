@@ -63,3 +63,52 @@ def test_gather_packed_outputs_gloo(tmp_path, world, F):
     Q, err, mask, nexcl = _fake_results(0, F, K)
     assert np.array_equal(got["Q"], Q) and np.array_equal(got["err"], err, equal_nan=True)
     assert np.array_equal(got["mask"], mask) and np.array_equal(got["nexcl"], nexcl)
+
+
+# ---- the drop-in itself under a 2-rank job: sharded staging, ONE gather, rank 0 writes the TRC -------------
+def _dropin_worker(rank, world, port, proj, cfg, tag):
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import p2s_oracle as orc
+    from pose2sim_b200 import triangulation as tri
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def oracle_solve(st, engine=None, device=0):          # TEST stand-in for the device call (no GPU here)
+        F, N, K, C = st.x.shape
+        U = F * N * K
+        s = st.settings
+        x, y, w = (a.reshape(U, C).astype(np.float64) for a in (st.x, st.y, st.lik))
+        with np.errstate(invalid="ignore"):
+            low = w < s["lik_thr"]
+        x[low] = np.nan; y[low] = np.nan; w[low] = np.nan
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"])
+        return {"Q": Q.reshape(F, N, K, 3), "err": err.reshape(F, N, K), "nexcl": nexcl.reshape(F, N, K).astype(np.int64),
+                "mask": mask.reshape(F, N, K)}
+
+    tri.solve_units = oracle_solve
+    try:
+        os.chdir(proj)
+        tri.triangulate_all(cfg)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi"])
+def test_dropin_two_ranks_writes_the_reference_trc(golden, tmp_path, tag):
+    from dropin_util import assert_trc_equal, golden_trcs, rebuild_trial, written_trcs
+    g = golden(tag + ".npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dropin_worker, args=(2, port, proj, cfg, tag), nprocs=2, join=True)
+    got, ref = written_trcs(proj), golden_trcs(g)
+    assert sorted(got) == sorted(ref)
+    for name in ref:
+        assert_trc_equal(got[name], ref[name], tol=1e-6)
