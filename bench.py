@@ -61,7 +61,7 @@ NCU_TRAFFIC_SOURCE = "profiles/r1c_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
-    return (16 * C + 37) * U     # float4 obs in, Q + err + mask + count out
+    return (12 * C + 37) * U     # x, y, likelihood planes in (12 B per camera), Q + err + mask + count out
 
 
 class ClockSampler(threading.Thread):
@@ -258,7 +258,6 @@ def main():
     U = wl["x"].shape[0]
     hx, hy, hl = (torch.from_numpy(wl[k]).pin_memory() for k in ("x", "y", "lik"))
     x, y, lik = (t.to(dev, non_blocking=True) for t in (hx, hy, hl))
-    obs = torch.empty((C, U, 4), dtype=torch.float32, device=dev)
     # per-unit outputs packed contiguously (Q | err | mask | nexcl = 37 B/unit) so that the final
     # gather is ONE NCCL call; two buffers alternate so the gather of step i overlaps step i+1
     packs = [torch.empty(sharding.PACK_BYTES * U, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -274,10 +273,10 @@ def main():
         step_no[0] += 1
         if pending[b] is not None:
             pending[b].wait()              # stream-side wait: the buffer's previous gather must be done
-        eng.stage_observations(x, y, lik, cfg["lik_thr"], out=obs)
         if record is not None:
             record[0].record()
-        eng.triangulate(obs, wl["P"], thr, mc, out=outs[b])
+        # ONE kernel: likelihood gate + float4 SoA staging (in shared memory) + exclusion search
+        eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc, out=outs[b])
         if record is not None:
             record[1].record()
         if world > 1:
@@ -290,8 +289,7 @@ def main():
         torch.cuda.synchronize()
 
     # one counted pass for the level histogram / algorithmic work of this workload
-    eng.stage_observations(x, y, lik, cfg["lik_thr"], out=obs)
-    eng.triangulate(obs, wl["P"], thr, mc, out=out, stats=stats)
+    eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc, out=out, stats=stats)
     torch.cuda.synchronize()
     st = ops.stats_dict(stats.cpu().numpy())
     fp64_peak = eng.fp64_peak()
@@ -367,8 +365,9 @@ def main():
             "config": {"workload": cfg["name"], "n_cams": C, "keypoints": cfg["K"], "frames_per_gpu": F,
                        "units_per_gpu": U, "reproj_error_threshold_triangulation": thr,
                        "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
-                       "seed": cfg["seed"], "l2": f"inputs {((12 + 16) * C * U) >> 20} MiB per step > 126 MB L2, no flush",
-                       "step": "stage kernel + triangulation kernel" + (" + NCCL gather to rank 0" if world > 1 else ""),
+                       "seed": cfg["seed"], "l2": f"inputs {(12 * C * U) >> 20} MiB + outputs {(37 * U) >> 20} MiB per step > 126 MB L2, no flush",
+                       "step": "one kernel (likelihood gate + float4 SoA staging in shared memory + exclusion search)"
+                               + (" + NCCL gather to rank 0" if world > 1 else ""),
                        "level_hist": st["level_hist"], "candidates_per_unit": st["candidates"] / U,
                        "failed_units": st["failed"], "eps_band_px": 1e-6,
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},

@@ -123,6 +123,15 @@ int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P,
                            double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
                            unsigned long long *stats, void *stream);
 
+/* Same search straight from the raw planes x, y, lik [n_units][n_cams] (DEVICE pointers, 16-byte
+ * aligned): the likelihood gate and the float4 SoA staging happen inside the kernel's tile load, so no
+ * staged buffer is written to or read from HBM.                                                  */
+int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                  const double *P, long long n_units, int n_cams, double lik_thr,
+                                  double reproj_thr, int min_cams,
+                                  double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                  unsigned long long *stats, void *stream);
+
 /* Whole job from host buffers: chunked H2D -> stage -> search -> D2H, overlapped on internal
  * streams.  x/y/lik as for p2s_stage_observations_device but HOST pointers (pinned = faster);
  * outputs HOST pointers; stats: HOST pointer to P2S_STAT_COUNT uint64 (overwritten) or NULL.     */

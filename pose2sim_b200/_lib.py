@@ -61,6 +61,7 @@ SIGNATURES = {
     "p2s_obs_bytes": (C.c_size_t, [_ll, _i]),
     "p2s_stage_observations_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp]),
     "p2s_triangulate_device": (_i, [_vp, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p2s_triangulate_planes_device": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "p2s_triangulate_host": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_stage_undistort_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp, _vp]),
     "p2s_triangulate_distorted_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

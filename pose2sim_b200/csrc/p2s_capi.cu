@@ -128,13 +128,19 @@ int check_tri_args(int n_cams, int min_cams, long long n_units) {
     return P2S_OK;
 }
 
+struct Planes {                                    // raw-plane input of the fused path (device pointers)
+    const float *x = nullptr, *y = nullptr, *lik = nullptr;
+    double lik_thr = -INFINITY;
+};
+
 int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
                         double thr, int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask,
-                        unsigned long long *stats, cudaStream_t stream) {
+                        unsigned long long *stats, cudaStream_t stream, const Planes *planes = nullptr) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_units == 0) return P2S_OK;
     p2s::TriLaunch L;
+    if (planes) { L.px = planes->x; L.py = planes->y; L.pl = planes->lik; L.lik_thr = planes->lik_thr; }
     L.obs = obs; L.P = P; L.lens = lens; L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams;
     L.solver = h->solver; L.sm_count = h->prop.multiProcessorCount;
     L.thr = thr; L.band_eps = h->band_eps;
@@ -310,6 +316,22 @@ int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P, long
                               out_mask, stats, stream);
 }
 
+int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                  const double *P, long long n_units, int n_cams, double lik_thr,
+                                  double reproj_thr, int min_cams,
+                                  double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                  unsigned long long *stats, void *stream) {
+    if (!h || !P || (n_units > 0 && (!x || !y || !lik || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)lik) & 15u) return P2S_EINVAL;
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    Planes pl;
+    pl.x = x; pl.y = y; pl.lik = lik; pl.lik_thr = lik_thr;
+    return enqueue_triangulate(h, nullptr, P, nullptr, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
+                               out_mask, stats, (cudaStream_t)stream, &pl);
+}
+
 int p2s_triangulate_distorted_device(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens,
                                      long long n_units, int n_cams, double reproj_thr, int min_cams,
                                      double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
@@ -342,11 +364,18 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
         P2S_CUDA(h, cudaMemcpyAsync(s.x.p, x + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.y.p, y + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.lik.p, lik + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
-        P2S_CUDA(h, p2s::launch_stage((const float *)s.x.p, (const float *)s.y.p, (const float *)s.lik.p, nu, n_cams,
-                                     lik_thr, lens, s.obs.p, h->prop.multiProcessorCount, s.stream));
-        h->launches += 1;
-        rc = enqueue_triangulate(h, s.obs.p, P, lens, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
-                                 (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream);
+        if (lens) {                                               // undistort: separate stage kernel (iterative lens inversion)
+            P2S_CUDA(h, p2s::launch_stage((const float *)s.x.p, (const float *)s.y.p, (const float *)s.lik.p, nu, n_cams,
+                                         lik_thr, lens, s.obs.p, h->prop.multiProcessorCount, s.stream));
+            h->launches += 1;
+            rc = enqueue_triangulate(h, s.obs.p, P, lens, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
+                                     (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream);
+        } else {                                                  // gate + staging fused into the search kernel
+            Planes pl;
+            pl.x = (const float *)s.x.p; pl.y = (const float *)s.y.p; pl.lik = (const float *)s.lik.p; pl.lik_thr = lik_thr;
+            rc = enqueue_triangulate(h, nullptr, P, nullptr, nu, n_cams, reproj_thr, min_cams, (double *)s.Q.p, (double *)s.err.p,
+                                     (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream, &pl);
+        }
         if (rc) return rc;
         P2S_CUDA(h, cudaMemcpyAsync(out_Q + u0 * 3, s.Q.p, nu * 24, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_err + u0, s.err.p, nu * 8, cudaMemcpyDeviceToHost, s.stream));

@@ -1,5 +1,6 @@
 // Internal launch descriptors shared by the kernel translation units and the C-ABI layer.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/pose2sim_b200.h"
@@ -7,7 +8,9 @@
 namespace p2s {
 
 struct TriLaunch {
-    const void *obs;              // float4 [n_cams][n_units], device
+    const void *obs;              // float4 [n_cams][n_units], device (null: raw planes below)
+    const float *px = nullptr, *py = nullptr, *pl = nullptr;   // raw planes [n_units][n_cams], device
+    double lik_thr = -INFINITY;   // gate of the raw-plane path
     const double *P;              // host, n_cams x 12
     const p2s_camera_model *lens; // host, n_cams lens models (undistort_points) or null
     long long n_units;

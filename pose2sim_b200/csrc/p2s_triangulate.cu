@@ -33,7 +33,10 @@
 namespace p2s {
 
 struct TriArgs {
-    const float4 *obs;            // [n_cams][n_units]
+    const float4 *obs;            // staged [n_cams][n_units], or null when the raw planes are given
+    const float *px, *py, *pl;    // raw planes [n_units][n_cams] (x, y, likelihood) or null
+    double lik_thr;               // gate for the raw-plane path
+    int gate;
     long long n_units;
     int n_cams;
     int min_cams;
@@ -90,6 +93,12 @@ __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX>
 
 // Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded
 // ones are dropped by a select: no branch, full instruction-level parallelism across cameras).
+// min over the aligned group of W = 2^k lanes this lane belongs to (all 32 lanes take part)
+__device__ __forceinline__ uint32_t group_min(uint32_t v, int W) {
+    for (int off = W >> 1; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(P2S_FULL, v, off));
+    return v;
+}
+
 template <int CMAX, bool DISTORT>
 __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const LensSet<DISTORT ? CMAX : 1> &lens,
                                                     const float4 (*obs)[32], int ul, uint32_t valid, int m,
@@ -137,16 +146,60 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
         const long long u = (long long)tile * 32 + lane;
         const bool active = u < a.n_units;
 
-        // ---- stage the tile: one coalesced 512 B row per camera ------------------------------
+        // ---- stage the tile ---------------------------------------------------------------------
         uint32_t nan0 = 0, inv0 = 0;
+        if (a.px == nullptr) {
+            // staged float4 SoA [C][U]: one coalesced 512 B row per camera
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                float4 o = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f);
+                if (c < C && active) o = __ldg(a.obs + (long long)c * a.n_units + u);
+                S.obs[c][lane] = o;
+            }
+        } else {
+            // raw planes x, y, lik [U][C] (what the host hands over): the tile is 32 C contiguous floats per
+            // plane, read as coalesced float4 and transposed into the float4 SoA slab, with the likelihood
+            // gate of triangulation.py:817-821 fused in (compared in double like the reference)
+            const long long e0 = (long long)tile * 32 * C;             // first element of the tile
+            const long long e_end = a.n_units * C;
+            const float nanf_ = __int_as_float(0x7fc00000);
+            __syncwarp();
+            for (int c = 0; c < CMAX; ++c) S.obs[c][lane] = make_float4(0.f, 0.f, nanf_, 0.f);
+            __syncwarp();
+            for (int j = lane * 4; j < 32 * C; j += 128) {
+                float vx[4], vy[4], vl[4];
+                if (e0 + j + 3 < e_end) {
+                    const float4 tx = __ldg(reinterpret_cast<const float4 *>(a.px + e0 + j));
+                    const float4 ty = __ldg(reinterpret_cast<const float4 *>(a.py + e0 + j));
+                    const float4 tl = __ldg(reinterpret_cast<const float4 *>(a.pl + e0 + j));
+                    vx[0] = tx.x; vx[1] = tx.y; vx[2] = tx.z; vx[3] = tx.w;
+                    vy[0] = ty.x; vy[1] = ty.y; vy[2] = ty.z; vy[3] = ty.w;
+                    vl[0] = tl.x; vl[1] = tl.y; vl[2] = tl.z; vl[3] = tl.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const bool in = e0 + j + t < e_end;
+                        vx[t] = in ? a.px[e0 + j + t] : 0.f;
+                        vy[t] = in ? a.py[e0 + j + t] : 0.f;
+                        vl[t] = in ? a.pl[e0 + j + t] : nanf_;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int uu = (j + t) / C, cc = (j + t) - uu * C;
+                    float fx = vx[t], fy = vy[t], fl = vl[t];
+                    if (a.gate && (double)fl < a.lik_thr) { fx = fy = fl = nanf_; }
+                    S.obs[cc][uu] = make_float4(fx, fy, fl, 0.f);
+                }
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            float4 o = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f);
-            if (c < C && active) o = __ldg(a.obs + (long long)c * a.n_units + u);
-            S.obs[c][lane] = o;
-            const bool isn = o.z != o.z;
+            const float lz = S.obs[c][lane].z;
+            const bool isn = lz != lz;
             nan0 |= (uint32_t)isn << c;
-            inv0 |= (uint32_t)(isn || o.z == 0.f) << c;
+            inv0 |= (uint32_t)(isn || lz == 0.f) << c;
         }
         nan0 &= cmask; inv0 &= cmask;
         S.nan0[lane] = nan0;
@@ -175,11 +228,11 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             const int npend = __popc(pmask);
             if (pend) S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
             const uint32_t ncand = (k == 0) ? 1u : (k <= a.max_table_level) ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
-            int W = 32;
-            if (ncand <= 16) { W = 1; while ((uint32_t)W < ncand) W <<= 1; }
-            const int G = 32 / W;
-            const int grp = lane / W, sub = lane - grp * W;
-            const uint32_t gmask = (W == 32) ? P2S_FULL : (((1u << W) - 1u) << (grp * W));
+            int lw = 5;                                      // W = 2^lw lanes per unit
+            if (ncand <= 16) { lw = 0; while ((1u << lw) < ncand) ++lw; }
+            const int W = 1 << lw;
+            const int G = 32 >> lw;
+            const int grp = lane >> lw, sub = lane & (W - 1);
             const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
             const bool blocks = k > 0;                       // then W >= C: one lane per camera for the block pass
             double *gblk = S.blk + grp * (C * 10 + 2);
@@ -283,20 +336,20 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                         }
                     }
                 }
-                // ---- (error, index) arg-min + runner-up across the W lanes of the group: redux.sync ------
+                // ---- (error, index) arg-min + runner-up across the W lanes of the group (xor butterflies) ----
                 // keys are 64-bit: min of the high words, then min of the low words among the lanes that
                 // hold that high word; ties go to the smallest candidate index (np.nanargmin's first index)
                 if (W > 1) {
                     const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
-                    const uint32_t mh = __reduce_min_sync(gmask, hi);
-                    const uint32_t ml = __reduce_min_sync(gmask, hi == mh ? lo : 0xffffffffu);
+                    const uint32_t mh = group_min(hi, W);
+                    const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W);
                     const bool is_min = (hi == mh) && (lo == ml);
-                    const uint32_t mc = __reduce_min_sync(gmask, is_min ? bcand : 0xffffffffu);
+                    const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W);
                     // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
                     const unsigned long long rk = is_min ? skey : bkey;
                     const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
-                    const uint32_t sh = __reduce_min_sync(gmask, rh);
-                    const uint32_t sl = __reduce_min_sync(gmask, rh == sh ? rl : 0xffffffffu);
+                    const uint32_t sh = group_min(rh, W);
+                    const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W);
                     bkey = ((unsigned long long)mh << 32) | ml;
                     skey = ((unsigned long long)sh << 32) | sl;
                     bcand = mc;
@@ -502,6 +555,8 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
         for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
     TriArgs a;
     a.obs = (const float4 *)L.obs; a.n_units = L.n_units; a.n_cams = L.n_cams; a.min_cams = L.min_cams;
+    a.px = L.px; a.py = L.py; a.pl = L.pl; a.lik_thr = L.lik_thr;
+    a.gate = (L.lik_thr == L.lik_thr) && !(L.lik_thr == -INFINITY);
     a.thr = L.thr; a.band_eps = L.band_eps; a.cand_masks = L.cand_masks;
     for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
     a.max_table_level = L.max_table_level;

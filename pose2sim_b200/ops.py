@@ -153,6 +153,26 @@ class Engine:
             _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
         return out
 
+    def triangulate_planes(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, stats=None):
+        """x, y, lik: CUDA float32 tensors [U, C] (raw planes).  Gate + float4 staging are fused into the
+        search kernel's tile load: ONE kernel, no staged buffer in HBM.  Returns the same dict as `triangulate`."""
+        torch = _torch()
+        U, Cn = x.shape
+        for t in (x, y, lik):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (U, Cn)
+        if out is None:
+            dev = x.device
+            out = {"Q": torch.empty((U, 3), dtype=torch.float64, device=dev),
+                   "err": torch.empty((U,), dtype=torch.float64, device=dev),
+                   "nexcl": torch.empty((U,), dtype=torch.uint8, device=dev),
+                   "mask": torch.empty((U,), dtype=torch.int32, device=dev)}
+        Pm = _as_P(P, Cn)
+        thr = float("-inf") if lik_thr is None else float(lik_thr)
+        _lib.check(self.h, self.lib.p2s_triangulate_planes_device(
+            self.h, _ptr(x), _ptr(y), _ptr(lik), Pm.ctypes.data, U, Cn, thr, float(reproj_thr), int(min_cams),
+            _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
+        return out
+
     def new_stats(self):
         torch = _torch()
         return torch.zeros(_lib.P2S_STAT_COUNT, dtype=torch.int64, device=f"cuda:{self.device}")

@@ -167,3 +167,18 @@ def test_jacobi_solver_agrees(engine):
     assert np.array_equal(a["nexcl"], b["nexcl"]) and np.array_equal(a["mask"], b["mask"])
     assert np.allclose(a["Q"], b["Q"], atol=1e-9, rtol=0, equal_nan=True)
     assert np.allclose(a["err"], b["err"], atol=1e-8, rtol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("C,U", [(8, 2600), (8, 37), (5, 333), (4, 1), (16, 257), (3, 1000), (32, 65)])
+def test_fused_planes_path_equals_staged_path(engine, C, U):
+    """`p2s_triangulate_planes_device` (gate + float4 staging fused into the tile load) is bit-identical to
+    `p2s_stage_observations_device` + `p2s_triangulate_device`, for ragged sizes and odd camera counts."""
+    import torch
+    wl = synth.make_triangulation_workload(C, -(-U // 26), 1, 26, seed=77 + C, lik_thr=None)
+    x, y, lik = (torch.from_numpy(np.ascontiguousarray(wl[k][:U])).cuda() for k in ("x", "y", "lik"))
+    mc = 2 if C < 32 else 28
+    a = engine.triangulate(engine.stage_observations(x, y, lik, 0.3), wl["P"], 15.0, mc)
+    b = engine.triangulate_planes(x, y, lik, wl["P"], 0.3, 15.0, mc)
+    torch.cuda.synchronize()
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
