@@ -55,9 +55,10 @@ def algorithmic_flops(st):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/): 332.9 MB read + 77.9 MB written on cfg2.
-NCU_TRAFFIC = {("cfg2", 1): 410.8e6}
-NCU_TRAFFIC_SOURCE = "profiles/r1c_triangulate_ncu_full.csv"
+# `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 72.7 MB written on cfg2
+# (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
+NCU_TRAFFIC = {("cfg2", 1): 322.3e6}
+NCU_TRAFFIC_SOURCE = "profiles/r1h_triangulate_fused_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
