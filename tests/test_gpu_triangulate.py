@@ -182,3 +182,38 @@ def test_fused_planes_path_equals_staged_path(engine, C, U):
     torch.cuda.synchronize()
     for k in ("Q", "err", "nexcl", "mask"):
         assert torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
+
+
+def test_full_size_properties_cfg3_shard(engine):
+    """BASELINE config 3 (16 cams x Body_with_feet, min_cameras = 3) at the per-GPU shard size bench.py uses
+    (125 k of the 1 M frames = 3.25 M units): determinism, permutation invariance, decision consistency and
+    the oracle on a subsample — through the fused raw-plane entry point and the host entry point."""
+    import torch
+    C, F, thr, mc = 16, 125_000, 15.0, 3
+    wl = synth.make_triangulation_workload(C, F, 1, 26, seed=303, lik_thr=None)
+    U = F * 26
+    x, y, lik = (torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik"))
+    stats = engine.new_stats()
+    a = engine.triangulate_planes(x, y, lik, wl["P"], 0.3, thr, mc, stats=stats)
+    torch.cuda.synchronize()
+    from pose2sim_b200 import ops
+    st = ops.stats_dict(stats.cpu().numpy())
+    assert sum(st["level_hist"]) + st["not_evaluated"] == U
+    err, Q = a["err"].cpu().numpy(), a["Q"].cpu().numpy()
+    ok = np.isfinite(err)
+    assert ok.mean() > 0.99 and (err[ok] <= thr).all() and np.isfinite(Q[ok]).all() and np.isnan(Q[~ok]).all()
+    nexcl, mask = a["nexcl"].cpu().numpy(), a["mask"].cpu().numpy().view(np.uint32)
+    popc = np.array([bin(int(m)).count("1") for m in mask[:20000]])
+    assert (popc == nexcl[:20000]).all()                     # no zero likelihoods here: listed == counted
+    assert (nexcl[ok] <= C - mc).all()
+    assert np.median(np.linalg.norm(Q[ok] - wl["truth"][ok], axis=1)) < 0.02
+    perm = torch.randperm(U, generator=torch.Generator().manual_seed(1)).cuda()
+    b = engine.triangulate_planes(x[perm].contiguous(), y[perm].contiguous(), lik[perm].contiguous(), wl["P"], 0.3, thr, mc)
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert torch.equal(torch.nan_to_num(a[k][perm].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
+    sub = np.arange(0, U, U // 400)
+    gx, gy, gl = synth.gate_likelihood(wl["x"][sub], wl["y"][sub], wl["lik"][sub], 0.3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oQ, oerr, onexcl, omask = orc.triangulate_units(gx.astype(float), gy.astype(float), gl.astype(float), wl["P"], thr, mc)
+    compare({"Q": Q[sub], "err": err[sub], "nexcl": nexcl[sub], "mask": mask[sub]}, oQ, oerr, onexcl, omask, thr)
