@@ -264,6 +264,47 @@ def main_undistort():
         print("e2e_tri_undistort", [os.path.basename(t) for t in trcs], "triangulated", np.isfinite(eo).mean(), "mean nexcl", no.mean())
 
 
+VARIANTS = [
+    # (name, config overrides under [triangulation] / [project], files to delete as (camera index, frame))
+    ("frame_range", {"frame_range": [10, 80]}, []),
+    ("incomplete_largest_zeros", {"remove_incomplete_frames": True, "sections_to_keep": "largest",
+                                  "fill_large_gaps_with": "zeros", "min_chunk_size": 5}, []),
+    ("no_interp_nan_fill", {"interpolation": "none", "fill_large_gaps_with": "nan", "show_interp_indices": False}, []),
+    ("cubic_first_section", {"interpolation": "cubic", "sections_to_keep": "first", "interp_if_gap_smaller_than": 4}, []),
+    ("missing_files", {"sections_to_keep": "last"}, [(1, f) for f in range(20, 26)] + [(3, 50), (0, 97), (0, 98), (0, 99)]),
+    ("min_cams_3_thr_8", {"min_cameras_for_triangulation": 3, "reproj_error_threshold_triangulation": 8,
+                          "likelihood_threshold_triangulation": 0.5}, []),
+]
+
+
+def main_variants():
+    """The single-person trial under other settings: frame ranges, trimming / fill / interpolation modes,
+    missing files, other thresholds.  Inputs are those of e2e_tri_single.npz; only the reference's TRC text
+    per variant is stored."""
+    ref = ref_shim.load_reference()
+    calib_text, cams, kp, present = single_person_trial()
+    out = {"names": np.array([v[0] for v in VARIANTS])}
+    for i, (name, over, missing) in enumerate(VARIANTS):
+        with tempfile.TemporaryDirectory() as td:
+            proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+            for c, f in missing:
+                os.remove(os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json"))
+            prj = {k: over[k] for k in over if k in ("frame_range",)}
+            tri = {k: over[k] for k in over if k not in prj}
+            cfg = synth_project.base_config(proj, **tri)
+            cfg["project"].update(prj)
+            log = run_reference(ref.triangulation.triangulate_all, cfg, proj)
+            trcs = sorted(glob.glob(os.path.join(proj, "pose-3d", "*.trc")))
+            assert len(trcs) == 1, (name, trcs)
+            out[f"v{i}_over"] = np.array(json.dumps(over))
+            out[f"v{i}_missing"] = np.array(missing, dtype=np.int64).reshape(-1, 2)
+            out[f"v{i}_trc_name"] = np.array(os.path.basename(trcs[0]))
+            out[f"v{i}_trc"] = np.array(open(trcs[0]).read())
+            out[f"v{i}_log"] = np.array(log)
+            print("variant", name, os.path.basename(trcs[0]))
+    np.savez_compressed(os.path.join(GOLDEN, "e2e_tri_variants.npz"), **out)
+
+
 def multi_association_trial():
     """Multi-person association: 4 ring cameras, 3 persons in random per-camera order, a detection
     missing now and then."""
@@ -296,7 +337,10 @@ if __name__ == "__main__":
         main_multi_association()
     elif len(sys.argv) > 1 and sys.argv[1] == "undistort":
         main_undistort()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+        main_variants()
     else:
         main()
         main_multi_association()
         main_undistort()
+        main_variants()

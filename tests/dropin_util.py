@@ -72,3 +72,16 @@ def associated_people(proj, cams, n_frames, n_values):
             if people[0]:
                 chosen[f, c] = people[0]["pose_keypoints_2d"]
     return chosen, exists
+
+
+def rebuild_variant(g_single, g_var, i, tmp_path):
+    """Variant i of tests/golden/e2e_tri_variants.npz on the inputs of e2e_tri_single.npz."""
+    proj, _ = rebuild_trial(g_single, tmp_path, "trial_demo")
+    cams = [str(c) for c in g_single["cams"]]
+    for c, f in g_var[f"v{i}_missing"]:
+        os.remove(os.path.join(proj, "pose", f"{cams[int(c)]}_json", f"{cams[int(c)]}_{int(f):06d}.json"))
+    over = json.loads(str(g_var[f"v{i}_over"]))
+    prj = {k: over[k] for k in over if k in ("frame_range",)}
+    cfg = synth_project.base_config(proj, **{k: over[k] for k in over if k not in prj})
+    cfg["project"].update(prj)
+    return proj, cfg

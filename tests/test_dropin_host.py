@@ -148,3 +148,17 @@ def test_multi_person_association_matches_reference_json(golden, tmp_path):
                     assert np.array_equal(np.asarray(person["pose_keypoints_2d"], np.float32), ref), (f, c, p)
                 else:
                     assert np.isnan(ref).all(), (f, c, p)
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_config_variants_match_reference_trc(golden, tmp_path, i):
+    """Frame ranges, trimming / fill / interpolation modes, missing files, other thresholds."""
+    from dropin_util import rebuild_variant
+    gs, gv = golden("e2e_tri_single.npz"), golden("e2e_tri_variants.npz")
+    proj, cfg = rebuild_variant(gs, gv, i, tmp_path)
+    with in_dir(proj):
+        st = tri.stage_project(cfg)
+        tri.write_outputs(st, oracle_units(st))
+    got = written_trcs(proj)
+    assert list(got) == [str(gv[f"v{i}_trc_name"])], (str(gv["names"][i]), list(got))
+    assert_trc_equal(got[str(gv[f"v{i}_trc_name"])], str(gv[f"v{i}_trc"]), tol=1e-6)

@@ -46,3 +46,16 @@ def test_association_then_triangulation_chain(golden, tmp_path):
         pose2sim_b200.triangulate_all(cfg)
     trcs = glob.glob(os.path.join(proj, "pose-3d", "*.trc"))
     assert len(trcs) == 1
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_triangulate_all_config_variants(golden, tmp_path, i):
+    import pose2sim_b200
+    from dropin_util import rebuild_variant
+    gs, gv = golden("e2e_tri_single.npz"), golden("e2e_tri_variants.npz")
+    proj, cfg = rebuild_variant(gs, gv, i, tmp_path)
+    with in_dir(proj):
+        pose2sim_b200.triangulate_all(cfg)
+    got = written_trcs(proj)
+    assert list(got) == [str(gv[f"v{i}_trc_name"])]
+    assert_trc_equal(got[str(gv[f"v{i}_trc_name"])], str(gv[f"v{i}_trc"]), tol=1e-6)
