@@ -100,6 +100,11 @@ int p2s_set_band_eps(p2s_handle *h, double eps_px);
  * (the north-star's nominal solver; kept for A/B evidence). */
 int p2s_set_solver(p2s_handle *h, int solver);
 
+/* association kernel team width: 0 = automatic (a warp per frame when frames are plentiful or small, a
+ * 256-thread CTA per frame when the person-combination product is large and frames are few), 1 or 8 to
+ * force one of the two (tests, A/B). */
+int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame);
+
 /* ---- staging (triangulation.py:817-821 + layout) -------------------------------------------- *
  * x, y, lik: [n_units][n_cams] float32, row-major (unit = frame x person x keypoint).
  * obs_out  : float4 [n_cams][n_units] = {x, y, likelihood, 0}; likelihood < lik_thr (and not NaN)

@@ -61,8 +61,8 @@ __device__ __forceinline__ uint32_t digit_rt(const uint32_t (&dig)[4], int c) {
     return (w >> ((c & 7) * 4)) & 15u;
 }
 
-// digits += v in the mixed radix n[c] (last camera fastest, itertools.product order); v < 64, n <= 16:
-// floor(t / n) = (t * ceil(65536 / n)) >> 16 is exact for t < 128
+// digits += v in the mixed radix n[c] (last camera fastest, itertools.product order); n <= 16:
+// floor(t / n) = (t * ceil(65536 / n)) >> 16 is exact for t < 65536 / n, i.e. for any v <= 4000
 template <int CMAX>
 __device__ __forceinline__ void radix_add(uint32_t (&dig)[4], uint32_t v, const uint32_t *s_n, const uint32_t *s_inv, int C) {
     uint32_t carry = v;
@@ -79,33 +79,67 @@ __device__ __forceinline__ void radix_add(uint32_t (&dig)[4], uint32_t v, const 
     }
 }
 
-template <int CMAX>
-__global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
+// Team = NW warps that share one frame.  NW = 1: a warp per frame (4 frames per CTA) — best when there are
+// many frames with few rows.  NW = 8: a 256-thread CTA per frame, 256 consecutive rows per step — for frames
+// with many rows (cfg4: 6^8 rows per frame) or few frames; the ordered early exit is resolved across the
+// team's warps through shared memory with two CTA barriers per step.
+template <int NW>
+struct alignas(16) TeamScratch {  // per team, in shared memory (only used when NW > 1)
+    uint32_t eval[NW], hit[NW], any[NW];
+    unsigned long long key[NW];
+    double last[NW];
+    double q[NW][3];
+    uint32_t valid[NW];
+    uint32_t dig[NW][4];
+    unsigned int frame;
+    unsigned int rows, cands;
+};
+
+template <int NW>
+__device__ __forceinline__ void team_sync() {
+    if (NW == 1) __syncwarp(); else __syncthreads();
+}
+
+template <int CMAX, int NW>
+__global__ void __launch_bounds__(NW == 1 ? 128 : 32 * NW, NW == 1 ? 4 : 2)
+associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TEAMS = (NW == 1) ? 4 : 1;
+    constexpr int TEAM_THREADS = 32 * NW;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int team = (NW == 1) ? warp_in_cta : 0;
+    const int warp = (NW == 1) ? 0 : warp_in_cta;           // warp index inside the team
+    const int ttid = warp * 32 + lane;                        // thread index inside the team
     const int C = a.n_cams, NP = a.max_persons;
     double *sP = reinterpret_cast<double *>(smem_raw);
-    // per-warp slab: obs float4 [CMAX][NP], blocks double [CMAX * NP][10], n_c, ok masks, reciprocal radices
-    unsigned char *base = smem_raw + CMAX * 12 * sizeof(double) + assoc_slab_bytes(CMAX, NP) * warp;
+    // per-team slab: obs float4 [CMAX][NP], blocks double [CMAX * NP][10], n_c, ok masks, reciprocal radices
+    unsigned char *base = smem_raw + CMAX * 12 * sizeof(double) + (assoc_slab_bytes(CMAX, NP) + sizeof(TeamScratch<NW>)) * team;
     float4 *sobs = reinterpret_cast<float4 *>(base);
     double *sblk = reinterpret_cast<double *>(base + (size_t)CMAX * NP * sizeof(float4));
     uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * (sizeof(float4) + 10 * sizeof(double)));
     uint32_t *s_ok = s_n + CMAX;
     uint32_t *s_inv = s_ok + CMAX;
+    TeamScratch<NW> &T = *reinterpret_cast<TeamScratch<NW> *>(base + assoc_slab_bytes(CMAX, NP));
 
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
     __syncthreads();
 
     for (;;) {
         unsigned int f = 0;
-        if (lane == 0) f = atomicAdd(a.tile_counter, 1u);
-        f = __shfl_sync(P2S_FULL, f, 0);
+        if (NW == 1) {
+            if (lane == 0) f = atomicAdd(a.tile_counter, 1u);
+            f = __shfl_sync(P2S_FULL, f, 0);
+        } else {
+            if (ttid == 0) T.frame = atomicAdd(a.tile_counter, 1u);
+            __syncthreads();
+            f = T.frame;
+        }
         if ((long long)f >= a.n_frames) break;
 
         // ---- stage the frame, gate the detections, build every detection's block ----------------------
         const float4 *fobs = a.obs + (long long)f * C * NP;
-        for (int i = lane; i < C * NP; i += 32) {
+        for (int i = ttid; i < C * NP; i += TEAM_THREADS) {
             const float4 o = __ldg(fobs + i);
             sobs[i] = o;
             double b[10];
@@ -114,22 +148,23 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
 #pragma unroll
             for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
         }
-        __syncwarp();
-        if (lane < C) {
-            int n = a.count[(long long)f * C + lane];
+        if (NW > 1 && ttid == 0) { T.rows = 0; T.cands = 0; }
+        team_sync<NW>();
+        if (ttid < C) {
+            int n = a.count[(long long)f * C + ttid];
             n = max(0, min(n, NP));
             uint32_t ok = 0;
             for (int p = 0; p < n; ++p) {
-                const double l = (double)sobs[lane * NP + p].z;
+                const double l = (double)sobs[ttid * NP + p].z;
                 // gate (:215-216): likelihood < thr -> 0 -> off; likelihood == 0 -> off; NaN stays on
                 if (!(l < a.lik_thr) && !(l == 0.0)) ok |= 1u << p;
             }
-            s_n[lane] = (uint32_t)n;
-            s_ok[lane] = ok;
+            s_n[ttid] = (uint32_t)n;
+            s_ok[ttid] = ok;
             const uint32_t nn = n ? (uint32_t)n : 1u;
-            s_inv[lane] = (65536u + nn - 1u) / nn;
+            s_inv[ttid] = (65536u + nn - 1u) / nn;
         }
-        __syncwarp();
+        team_sync<NW>();
         uint32_t present = 0;
         unsigned long long total_rows = 1;
         bool overflow = false;
@@ -141,12 +176,13 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
         }
         const int n_missing = C - __popc(present);
 
+        // replicated in every thread of the team (all threads apply the same updates)
         double err_last = inf64();
         unsigned long long best_key = P2S_KEY_EMPTY;          // key of the global best (strict '<' updates)
         double bqx = nan64(), bqy = bqx, bqz = bqx;
         uint32_t b_valid = 0;                                 // cameras used by the best candidate
         uint32_t b_dig[4] = {0, 0, 0, 0};                     // person digits of the best row
-        unsigned int st_rows = 0, st_cands = 0;
+        unsigned int st_rows = 0, st_cands = 0;               // per warp / per lane counters
 
         for (int k = 0; !overflow && err_last > a.thr && C - (n_missing + k) >= a.min_cams; ++k) {
             const bool tabled = k <= a.max_table_level;
@@ -154,9 +190,9 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             bool hit = false;
             uint32_t dig[4] = {0, 0, 0, 0};                   // 4 bits per camera: the row's person indices
-            radix_add<CMAX>(dig, (uint32_t)lane, s_n, s_inv, C);
-            for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += 32) {
-                const unsigned long long r = rbase + lane;
+            radix_add<CMAX>(dig, (uint32_t)ttid, s_n, s_inv, C);
+            for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += TEAM_THREADS) {
+                const unsigned long long r = rbase + ttid;
                 const bool row_ok = r < total_rows;
                 uint32_t active = 0;
 #pragma unroll
@@ -219,84 +255,139 @@ __global__ void __launch_bounds__(128, 4) associate_kernel(const CamParams<CMAX>
                 const double rerr = key_err(rkey);
                 const uint32_t evalmask = __ballot_sync(P2S_FULL, evaluated);
                 const uint32_t hitmask = __ballot_sync(P2S_FULL, evaluated && rerr < a.thr);
-                uint32_t upto = 0xffffffffu;                  // lanes at or before the first hit
-                if (hitmask) { const int fh = __ffs(hitmask) - 1; upto = (fh == 31) ? 0xffffffffu : ((2u << fh) - 1u); hit = true; }
-                const uint32_t considered = evalmask & upto;
-                st_rows += (unsigned)__popc(__ballot_sync(P2S_FULL, row_ok) & upto);
-                if (considered) {
-                    // err_last = error of the last evaluated row in visiting order
-                    const int last = 31 - __clz(considered);
-                    err_last = __shfl_sync(P2S_FULL, rerr, last);
-                    // chunk arg-min over (key, lane) among considered lanes
-                    unsigned long long ck = ((considered >> lane) & 1u) ? rkey : P2S_KEY_EMPTY;
-                    int cl = lane;
+                const uint32_t rowmask = __ballot_sync(P2S_FULL, row_ok);
+                // ---- which rows of this step count: everything up to the first row under the threshold ------
+                int wh = NW;                                  // first warp of the team with a hit
+                if (NW == 1) {
+                    if (hitmask) wh = 0;
+                } else {
+                    if (lane == 0) { T.eval[warp] = evalmask; T.hit[warp] = hitmask; }
+                    __syncthreads();
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const unsigned long long ok2 = __shfl_xor_sync(P2S_FULL, ck, off);
-                        const int ol = __shfl_xor_sync(P2S_FULL, cl, off);
-                        if (ok2 < ck || (ok2 == ck && ol < cl)) { ck = ok2; cl = ol; }
-                    }
-                    if (ck < best_key) {                      // strict '<' (:242)
-                        best_key = ck;
-                        bqx = __shfl_sync(P2S_FULL, rqx, cl);
-                        bqy = __shfl_sync(P2S_FULL, rqy, cl);
-                        bqz = __shfl_sync(P2S_FULL, rqz, cl);
-                        b_valid = __shfl_sync(P2S_FULL, rvalid, cl);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) b_dig[w] = __shfl_sync(P2S_FULL, dig[w], cl);
-                    }
+                    for (int w = NW - 1; w >= 0; --w) if (T.hit[w]) wh = w;
                 }
-                radix_add<CMAX>(dig, 32u, s_n, s_inv, C);     // this lane's next row
+                uint32_t upto = 0xffffffffu;                  // my warp's lanes at or before the first hit
+                if (warp > wh) upto = 0u;
+                else if (warp == wh) { const int fh = __ffs(hitmask) - 1; upto = (fh == 31) ? 0xffffffffu : ((2u << fh) - 1u); }
+                if (wh < NW) hit = true;
+                const uint32_t considered = evalmask & upto;
+                if (lane == 0) st_rows += (unsigned)__popc(rowmask & upto);
+                // warp arg-min over (key, lane) among the considered lanes
+                unsigned long long ck = ((considered >> lane) & 1u) ? rkey : P2S_KEY_EMPTY;
+                int cl = lane;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const unsigned long long ok2 = __shfl_xor_sync(P2S_FULL, ck, off);
+                    const int ol = __shfl_xor_sync(P2S_FULL, cl, off);
+                    if (ok2 < ck || (ok2 == ck && ol < cl)) { ck = ok2; cl = ol; }
+                }
+                if (NW == 1) {
+                    if (considered) {
+                        // err_last = error of the last evaluated row in visiting order
+                        err_last = __shfl_sync(P2S_FULL, rerr, 31 - __clz(considered));
+                        if (ck < best_key) {                  // strict '<' (:242)
+                            best_key = ck;
+                            bqx = __shfl_sync(P2S_FULL, rqx, cl);
+                            bqy = __shfl_sync(P2S_FULL, rqy, cl);
+                            bqz = __shfl_sync(P2S_FULL, rqz, cl);
+                            b_valid = __shfl_sync(P2S_FULL, rvalid, cl);
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) b_dig[w] = __shfl_sync(P2S_FULL, dig[w], cl);
+                        }
+                    }
+                } else {
+                    if (lane == 0) { T.any[warp] = considered; T.key[warp] = ck; }
+                    if (considered && lane == 31 - __clz(considered)) T.last[warp] = rerr;
+                    if (considered && lane == cl) {
+                        T.q[warp][0] = rqx; T.q[warp][1] = rqy; T.q[warp][2] = rqz;
+                        T.valid[warp] = rvalid;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) T.dig[warp][w] = dig[w];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {            // visiting order: ascending warp, first wins ties
+                        if (T.any[w]) {
+                            err_last = T.last[w];
+                            if (T.key[w] < best_key) {
+                                best_key = T.key[w];
+                                bqx = T.q[w][0]; bqy = T.q[w][1]; bqz = T.q[w][2];
+                                b_valid = T.valid[w];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) b_dig[j] = T.dig[w][j];
+                            }
+                        }
+                    }
+                    __syncthreads();                          // scratch is rewritten by the next step
+                }
+                // this lane's next row: + TEAM_THREADS in the mixed radix
+                radix_add<CMAX>(dig, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
             }
         }
 
         // ---- write the frame's result -----------------------------------------------------------------
-        if (lane == 0) {
-            const bool any = best_key != P2S_KEY_EMPTY;
-            a.out_err[f] = any ? key_err(best_key) : inf64();
-            double *q = a.out_Q + (long long)f * 3;
-            q[0] = any ? bqx : nan64(); q[1] = any ? bqy : nan64(); q[2] = any ? bqz : nan64();
-            if (a.out_stats) { a.out_stats[(long long)f * 2] = st_rows; a.out_stats[(long long)f * 2 + 1] = 0; }
-        }
         if (a.out_stats) {
             unsigned int sc = st_cands;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sc += __shfl_xor_sync(P2S_FULL, sc, off);
-            if (lane == 0) a.out_stats[(long long)f * 2 + 1] = sc;
-        }
-        if (lane < C) {
-            int8_t v = -1;
-            if (best_key != P2S_KEY_EMPTY && ((b_valid >> lane) & 1u)) {
-                const uint32_t w = lane < 8 ? b_dig[0] : lane < 16 ? b_dig[1] : lane < 24 ? b_dig[2] : b_dig[3];
-                v = (int8_t)((w >> ((lane & 7) * 4)) & 15u);
+            if (NW == 1) {
+                if (lane == 0) { a.out_stats[(long long)f * 2] = st_rows; a.out_stats[(long long)f * 2 + 1] = sc; }
+            } else {
+                if (lane == 0) { atomicAdd(&T.rows, st_rows); atomicAdd(&T.cands, sc); }
+                __syncthreads();
+                if (ttid == 0) { a.out_stats[(long long)f * 2] = T.rows; a.out_stats[(long long)f * 2 + 1] = T.cands; }
             }
-            a.out_comb[(long long)f * C + lane] = v;
         }
-        __syncwarp();
+        if (ttid == 0) {
+            const bool any = best_key != P2S_KEY_EMPTY;
+            a.out_err[f] = any ? key_err(best_key) : inf64();
+            double *q = a.out_Q + (long long)f * 3;
+            q[0] = any ? bqx : nan64(); q[1] = any ? bqy : nan64(); q[2] = any ? bqz : nan64();
+        }
+        if (ttid < C) {
+            int8_t v = -1;
+            if (best_key != P2S_KEY_EMPTY && ((b_valid >> ttid) & 1u)) {
+                const uint32_t w = ttid < 8 ? b_dig[0] : ttid < 16 ? b_dig[1] : ttid < 24 ? b_dig[2] : b_dig[3];
+                v = (int8_t)((w >> ((ttid & 7) * 4)) & 15u);
+            }
+            a.out_comb[(long long)f * C + ttid] = v;
+        }
+        team_sync<NW>();
     }
 }
 
-template <int CMAX>
-static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0, int *grid_out) {
+template <int CMAX, int NW>
+static cudaError_t launch_assoc_nw(const AssocLaunch &L, const AssocArgs &a0, int *grid_out) {
     CamParams<CMAX> cams;
     for (int c = 0; c < CMAX; ++c)
         for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
     AssocArgs a = a0;
-    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + assoc_slab_bytes(CMAX, L.max_persons) * 4;
-    auto kern = associate_kernel<CMAX>;
+    constexpr int teams = (NW == 1) ? 4 : 1;
+    constexpr int threads = (NW == 1) ? 128 : 32 * NW;
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + (assoc_slab_bytes(CMAX, L.max_persons) + sizeof(TeamScratch<NW>)) * teams;
+    auto kern = associate_kernel<CMAX, NW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    long long want = (L.n_frames + 3) / 4;
+    long long want = (L.n_frames + teams - 1) / teams;
     long long grid = (long long)L.sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
-    kern<<<(unsigned)grid, 128, smem, L.stream>>>(cams, a);
+    kern<<<(unsigned)grid, threads, smem, L.stream>>>(cams, a);
     return cudaGetLastError();
+}
+
+// A warp per frame when there are enough frames to fill the machine (or the frames are small), else a
+// 256-thread CTA per frame.  `mean_rows`: average size of the person-combination product per frame.
+template <int CMAX>
+static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0, int *grid_out) {
+    const bool wide = L.team == 8 || (L.team == 0 && L.mean_rows >= 512.0 && (double)L.n_frames < 16.0 * L.sm_count * 4);
+    if (wide) return launch_assoc_nw<CMAX, 8>(L, a0, grid_out);
+    return launch_assoc_nw<CMAX, 1>(L, a0, grid_out);
 }
 
 cudaError_t launch_associate(const AssocLaunch &L, int *grid_out) {

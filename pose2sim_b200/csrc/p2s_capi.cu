@@ -39,6 +39,7 @@ struct p2s_handle {
     cudaDeviceProp prop;
     double band_eps = 1e-6;
     int solver = 0;
+    int assoc_team = 0;
     long long launches = 0;
     int last_grid = 0;
     std::string last_error;
@@ -159,13 +160,15 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
 
 int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, const double *P, long long n_frames,
                       int n_cams, int max_persons, double thr, double lik_thr, int min_cams,
-                      double *err, int8_t *comb, double *Q, uint32_t *stats, cudaStream_t stream) {
+                      double *err, int8_t *comb, double *Q, uint32_t *stats, cudaStream_t stream, double mean_rows) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_frames == 0) return P2S_OK;
     p2s::AssocLaunch L;
     L.obs = obs; L.count = count; L.P = P; L.n_frames = n_frames; L.n_cams = n_cams;
     L.max_persons = max_persons; L.min_cams = min_cams; L.sm_count = h->prop.multiProcessorCount;
+    L.mean_rows = mean_rows;
+    L.team = h->assoc_team;
     L.thr = thr; L.lik_thr = lik_thr;
     const SubsetTable &t = h->tables[n_cams];
     L.cand_masks = t.d_masks;
@@ -260,6 +263,12 @@ int p2s_get_device_info(const p2s_handle *h, p2s_device_info *info) {
 int p2s_set_band_eps(p2s_handle *h, double eps) {
     if (!h || !(eps >= 0.0)) return P2S_EINVAL;
     h->band_eps = eps;
+    return P2S_OK;
+}
+
+int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame) {
+    if (!h || (warps_per_frame != 0 && warps_per_frame != 1 && warps_per_frame != 8)) return P2S_EINVAL;
+    h->assoc_team = warps_per_frame;
     return P2S_OK;
 }
 
@@ -412,8 +421,10 @@ int p2s_associate_device(p2s_handle *h, const void *obs, const int32_t *count, c
     if (n_cams < 2 || n_cams > P2S_MAX_CAMS || min_cams < 1 || n_frames < 0 || n_frames > 0xfffffff0LL) return P2S_EINVAL;
     if (max_persons < 1 || max_persons > P2S_MAX_PERSONS) return P2S_EINVAL;
     P2S_CUDA(h, cudaSetDevice(h->device));
+    // the per-camera counts live on the device here: size the team for the largest possible product
+    const double rows_bound = std::pow((double)max_persons, (double)n_cams);
     return enqueue_associate(h, obs, count, P, n_frames, n_cams, max_persons, reproj_thr, lik_thr, min_cams, out_err,
-                             out_comb, out_Q, out_stats, (cudaStream_t)stream);
+                             out_comb, out_Q, out_stats, (cudaStream_t)stream, rows_bound);
 }
 
 int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, const double *P, long long n_frames,
@@ -434,9 +445,15 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
             return rc;
         P2S_CUDA(h, cudaMemcpyAsync(s.obs.p, obs + f0 * C * NP * 4, nf * C * NP * 16, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.count.p, count + f0 * C, nf * C * 4, cudaMemcpyHostToDevice, s.stream));
+        double rows = 0.0;                                        // mean size of the person-combination product
+        for (long long f = f0; f < f0 + nf; ++f) {
+            double r = 1.0;
+            for (size_t c = 0; c < C; ++c) { const int n = count[f * C + c]; r *= (n > 1) ? (double)n : 1.0; }
+            rows += r;
+        }
         rc = enqueue_associate(h, s.obs.p, (const int32_t *)s.count.p, P, nf, n_cams, max_persons, reproj_thr, lik_thr,
                                min_cams, (double *)s.err.p, (int8_t *)s.comb.p, (double *)s.Q.p,
-                               out_stats ? (uint32_t *)s.astats.p : nullptr, s.stream);
+                               out_stats ? (uint32_t *)s.astats.p : nullptr, s.stream, rows / (double)nf);
         if (rc) return rc;
         P2S_CUDA(h, cudaMemcpyAsync(out_err + f0, s.err.p, nf * 8, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_comb + f0 * C, s.comb.p, nf * C, cudaMemcpyDeviceToHost, s.stream));

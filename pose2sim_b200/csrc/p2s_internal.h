@@ -33,6 +33,8 @@ struct AssocLaunch {
     const double *P;              // host
     long long n_frames;
     int n_cams, max_persons, min_cams, sm_count;
+    int team = 0;                 // 0 auto, 1 or 8 warps per frame
+    double mean_rows;             // average rows (product of persons per camera) per frame, picks the team width
     double thr, lik_thr;
     const uint32_t *cand_masks;   // same lexicographic all-camera table as the triangulation kernel
     uint32_t level_off[P2S_MAX_CAMS + 2];

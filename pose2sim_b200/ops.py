@@ -94,6 +94,9 @@ class Engine:
     def set_solver(self, solver):
         _lib.check(self.h, self.lib.p2s_set_solver(self.h, {"secular": 0, "jacobi": 1}.get(solver, solver)))
 
+    def set_assoc_team(self, warps_per_frame):
+        _lib.check(self.h, self.lib.p2s_set_assoc_team(self.h, int(warps_per_frame)))
+
     def launch_count(self):
         return int(self.lib.p2s_launch_count(self.h))
 
