@@ -197,6 +197,13 @@ int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams
                         float *x, float *y, float *lik, int32_t *n_people, uint8_t *status,
                         long long *n_inexact, int n_threads);
 
+/* TRC body (triangulation.py:206-213 `Q.to_csv(sep='\t', index=True, header=None)`): APPENDS n_rows lines
+ * "frame \t time \t v0 \t ... \n" to `path` (the caller has written the 5 header lines); values is
+ * [n_rows][n_cols] float64, NaN = empty field, numbers formatted like Python's repr(float) (what pandas
+ * writes), so the file is byte-identical to the reference's for equal values.                      */
+int p2s_write_trc_rows(const char *path, const long long *frames, const double *time_s,
+                       const double *values, long long n_rows, int n_cols);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Dependent-chain FP64 FMA microbenchmark on the handle's device: achieved DFMA TFLOP/s
  * (2 flops per FMA) — the FP64 roofline denominator MEASURED_PEAKS.json does not carry.         */

@@ -333,3 +333,82 @@ extern "C" int p2s_read_pose_files(const char *const *paths, long long n_frames,
     if (n_inexact) *n_inexact = inexact.load();
     return P2S_OK;
 }
+
+// ---- TRC body writer (Pose2Sim/triangulation.py:206-213: DataFrame.to_csv(sep='\t', header=None)) -----------
+// One row per frame: frame number, time, 3 K coordinates, tab separated, '\n' terminated; NaN is an empty
+// field (pandas na_rep='').  Numbers are written like Python's repr(float) — the shortest string that
+// round-trips, fixed notation for 1e-4 <= |v| < 1e16 (always with a fractional part, "2.0"), scientific
+// with a two-digit exponent otherwise ("1e-05") — which is what pandas emits for float64 columns.
+namespace {
+
+char *repr_double(char *p, double v) {
+    if (std::isnan(v)) return p;                                   // empty field
+    if (std::isinf(v)) { const char *s = v > 0 ? "inf" : "-inf"; while (*s) *p++ = *s++; return p; }
+    if (v == 0.0) { if (std::signbit(v)) *p++ = '-'; *p++ = '0'; *p++ = '.'; *p++ = '0'; return p; }
+    char buf[40];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // shortest: d[.ddd]e[+-]XX
+    char *b = buf, *e = r.ptr;
+    if (*b == '-') { *p++ = '-'; ++b; }
+    char digits[24];
+    int nd = 0;
+    char *q = b;
+    for (; q < e && *q != 'e'; ++q) if (*q != '.') digits[nd++] = *q;
+    int exp10 = 0;
+    {
+        ++q;                                                        // past 'e'
+        const bool neg = (*q == '-');
+        ++q;
+        for (; q < e; ++q) exp10 = exp10 * 10 + (*q - '0');
+        if (neg) exp10 = -exp10;
+    }
+    if (exp10 >= -4 && exp10 < 16) {
+        if (exp10 < 0) {                                            // 0.000ddd
+            *p++ = '0'; *p++ = '.';
+            for (int i = 0; i < -exp10 - 1; ++i) *p++ = '0';
+            for (int i = 0; i < nd; ++i) *p++ = digits[i];
+        } else {
+            int i = 0;
+            for (; i <= exp10; ++i) *p++ = (i < nd) ? digits[i] : '0';
+            *p++ = '.';
+            if (i >= nd) *p++ = '0';
+            for (; i < nd; ++i) *p++ = digits[i];
+        }
+    } else {                                                        // d[.ddd]e[+-]XX
+        *p++ = digits[0];
+        if (nd > 1) { *p++ = '.'; for (int i = 1; i < nd; ++i) *p++ = digits[i]; }
+        *p++ = 'e';
+        *p++ = exp10 < 0 ? '-' : '+';
+        const int a = exp10 < 0 ? -exp10 : exp10;
+        if (a >= 100) { *p++ = (char)('0' + a / 100); *p++ = (char)('0' + (a / 10) % 10); *p++ = (char)('0' + a % 10); }
+        else { *p++ = (char)('0' + a / 10); *p++ = (char)('0' + a % 10); }
+    }
+    return p;
+}
+
+}  // namespace
+
+extern "C" int p2s_write_trc_rows(const char *path, const long long *frames, const double *time_s,
+                                  const double *values, long long n_rows, int n_cols) {
+    if (!path || n_rows < 0 || n_cols < 0 || (n_rows > 0 && (!frames || !time_s || (n_cols > 0 && !values)))) return P2S_EINVAL;
+    FILE *f = std::fopen(path, "ab");
+    if (!f) return P2S_EINVAL;
+    std::vector<char> line((size_t)(n_cols + 2) * 32 + 64);
+    std::string chunk;
+    chunk.reserve(1 << 20);
+    for (long long r = 0; r < n_rows; ++r) {
+        char *p = line.data();
+        auto fr = std::to_chars(p, p + 24, frames[r]);
+        p = fr.ptr;
+        *p++ = '\t';
+        p = repr_double(p, time_s[r]);
+        const double *row = values + (size_t)r * (size_t)n_cols;
+        for (int c = 0; c < n_cols; ++c) { *p++ = '\t'; p = repr_double(p, row[c]); }
+        *p++ = '\n';
+        chunk.append(line.data(), (size_t)(p - line.data()));
+        if (chunk.size() > (1u << 20) - 65536) { std::fwrite(chunk.data(), 1, chunk.size(), f); chunk.clear(); }
+    }
+    if (!chunk.empty()) std::fwrite(chunk.data(), 1, chunk.size(), f);
+    const bool ok = !std::ferror(f);
+    std::fclose(f);
+    return ok ? P2S_OK : P2S_EINVAL;
+}

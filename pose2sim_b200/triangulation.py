@@ -275,8 +275,10 @@ def frame_rate_of(s):
 
 
 def write_trc(s, Q, frames, keypoints_names, id_person=-1):
-    """triangulation.py:151-215 `make_trc`: Q [n, 3K] Z-up, `frames` their labels.  Returns the path."""
-    import pandas as pd
+    """triangulation.py:151-215 `make_trc`: Q [n, 3K] Z-up, `frames` their labels.  Returns the path.
+    The body is written by the native writer (`p2s_write_trc_rows`, Python-repr number formatting =
+    what `DataFrame.to_csv` emits) instead of pandas' per-value string conversion."""
+    from . import _lib
     project_dir = s["project_dir"]
     base = os.path.basename(os.path.realpath(project_dir))
     seq = f"{base}_P{id_person}" if s["multi_person"] else base
@@ -289,15 +291,16 @@ def write_trc(s, Q, frames, keypoints_names, id_person=-1):
               "\t".join(map(str, [rate, rate, len(Q), K, "m", rate, frames[0], len(Q)])),
               "Frame#\tTime\t" + "\t\t\t".join(keypoints_names) + "\t\t\t",
               "\t\t" + "\t".join(f"X{i + 1}\tY{i + 1}\tZ{i + 1}" for i in range(K)) + "\t"]
-    yup = Q.reshape(len(Q), K, 3)[:, :, [1, 2, 0]].reshape(len(Q), 3 * K)      # common.py:596-612: X,Y,Z <- Y,Z,X
-    df = pd.DataFrame(yup, index=pd.Index(frames))
-    df.insert(0, "t", df.index / rate)
+    yup = np.ascontiguousarray(Q.reshape(len(Q), K, 3)[:, :, [1, 2, 0]].reshape(len(Q), 3 * K), dtype=np.float64)
+    fr = np.ascontiguousarray(frames, dtype=np.int64)               # common.py:596-612: X,Y,Z <- Y,Z,X
+    t = np.ascontiguousarray(fr / rate, dtype=np.float64)
     if not os.path.exists(out_dir):
         os.mkdir(out_dir)
     path = os.path.realpath(os.path.join(out_dir, name))
     with open(path, "w") as f:
         f.write("\n".join(header) + "\n")
-        df.to_csv(f, sep="\t", index=True, header=None, lineterminator="\n")
+    _lib.check(None, _lib.load().p2s_write_trc_rows(path.encode(), fr.ctypes.data, t.ctypes.data, yup.ctypes.data,
+                                                    len(fr), 3 * K))
     return path
 
 
