@@ -11,7 +11,9 @@
  *   p2s_stage_*         replaces  the likelihood gate at triangulation.py:817-821 plus the
  *                       (3, n_cams) slicing at triangulation.py:837-838;
  *   p2s_associate_*     replaces  Pose2Sim/personAssociation.py:154  best_persons_and_cameras_combination
- *                       (+ :67 persons_combinations, :102 triangulate_comb), called per frame at :774.
+ *                       (+ :67 persons_combinations, :102 triangulate_comb), called per frame at :774;
+ *   p2s_associate_multi_* replaces  personAssociation.py:793-801 (compute_affinity :347, matchSVT :450,
+ *                       the arg-max half of person_index_per_cam :512), the multi_person branch.
  *
  * Conventions
  *   - plain C, no torch / C++ types; all sizes are explicit;
@@ -37,6 +39,7 @@ extern "C" {
 
 #define P2S_MAX_CAMS 32          /* one uint32 exclusion mask per unit */
 #define P2S_MAX_PERSONS 16       /* persons per camera in the association search */
+#define P2S_MAX_DETECTIONS 64    /* detections per frame (all cameras together) in the multi-person matching */
 
 enum {
     P2S_OK = 0,
@@ -181,6 +184,32 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
                        long long n_frames, int n_cams, int max_persons,
                        double reproj_thr, double lik_thr, int min_cams,
                        double *out_err, int8_t *out_comb, double *out_Q, uint32_t *out_stats);
+
+/* ---- multi-person cross-view association (personAssociation.py:783-801) ---------------------- *
+ * Per frame: Plücker-ray affinity between every two detections of different cameras (compute_rays :277,
+ * compute_affinity :347), the one-person-per-view constraint (:411), matchSVT (:450, max_iter 20,
+ * w_rank 50, tol 1e-4, w_sparse 0.1 as at the call site :799), the min_affinity cut (:800) and the first
+ * half of person_index_per_cam (:526-531): for every detection (row) the arg-max detection of each view.
+ * The integer bookkeeping that follows in the reference (unique rows, ordering, duplicate and
+ * min-cameras filters, :535-547) is left to the caller.
+ * obs          : float32 [n_frames][n_cams][max_persons][3 n_joints] = pose_keypoints_2d of each detection
+ *                (x, y, likelihood per joint; NaN allowed); entries >= count are ignored
+ * count        : int32 [n_frames][n_cams] detections per camera
+ * cams         : HOST pointer, n_cams models; K, R (world -> camera rotation matrix) and T are used
+ * n_max        : row capacity per frame, >= the largest per-frame sum of count, <= P2S_MAX_DETECTIONS
+ * out_rows     : int8 [n_frames][n_max][n_cams]; row r < sum(count[f]) holds per view the index (within
+ *                that view) of the best-matching detection, -1 when none has affinity > 0; rows beyond
+ *                the frame's detections are left untouched
+ * out_affinity : float64 [n_frames][n_max][n_max] matched and thresholded affinity (top-left N x N used) or NULL
+ * out_iters    : int32 [n_frames] matchSVT iterations used, or NULL                                  */
+int p2s_associate_multi_device(p2s_handle *h, const float *obs, const int32_t *count, const p2s_camera_model *cams,
+                               long long n_frames, int n_cams, int max_persons, int n_joints, int n_max,
+                               double reconstruction_error_threshold, double min_affinity,
+                               int8_t *out_rows, double *out_affinity, int32_t *out_iters, void *stream);
+int p2s_associate_multi_host(p2s_handle *h, const float *obs, const int32_t *count, const p2s_camera_model *cams,
+                             long long n_frames, int n_cams, int max_persons, int n_joints, int n_max,
+                             double reconstruction_error_threshold, double min_affinity,
+                             int8_t *out_rows, double *out_affinity, int32_t *out_iters);
 
 /* ---- host staging: OpenPose JSON -> observation planes (no GPU involved) --------------------- *
  * Replaces the file handling of triangulation.py:607-653 extract_files_frame_f (+ :77-90

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("P2S_LIB") or os.path.join(_HERE, "libp2s_b200.so")
 
 P2S_MAX_CAMS = 32
 P2S_MAX_PERSONS = 16
+P2S_MAX_DETECTIONS = 64
 P2S_STAT_COUNT = 48
 STAT_LEVEL0 = 0
 STAT_NOT_EVALUATED = 33
@@ -69,6 +70,8 @@ SIGNATURES = {
     "p2s_triangulate_undistort_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "p2s_associate_multi_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
+    "p2s_associate_multi_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "p2s_read_pose_files": (_i, [_vp, _ll, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "p2s_write_trc_rows": (_i, [C.c_char_p, _vp, _vp, _vp, _ll, _i]),
     "p2s_measure_fp64_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),

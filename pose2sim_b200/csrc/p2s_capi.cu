@@ -29,7 +29,7 @@ struct DevBuf {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf x, y, lik, obs, Q, err, nexcl, mask, count, comb, astats;
+    DevBuf x, y, lik, obs, Q, err, nexcl, mask, count, comb, astats, rows, aff, iters;
 };
 
 }  // namespace
@@ -232,7 +232,7 @@ int p2s_destroy(p2s_handle *h) {
     cudaDeviceSynchronize();
     for (auto &t : h->tables) if (t.d_masks) cudaFree(t.d_masks);
     for (auto &s : h->slots) {
-        for (DevBuf *b : {&s.x, &s.y, &s.lik, &s.obs, &s.Q, &s.err, &s.nexcl, &s.mask, &s.count, &s.comb, &s.astats})
+        for (DevBuf *b : {&s.x, &s.y, &s.lik, &s.obs, &s.Q, &s.err, &s.nexcl, &s.mask, &s.count, &s.comb, &s.astats, &s.rows, &s.aff, &s.iters})
             if (b->p) cudaFree(b->p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -459,6 +459,77 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
         P2S_CUDA(h, cudaMemcpyAsync(out_comb + f0 * C, s.comb.p, nf * C, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_Q + f0 * 3, s.Q.p, nf * 24, cudaMemcpyDeviceToHost, s.stream));
         if (out_stats) P2S_CUDA(h, cudaMemcpyAsync(out_stats + f0 * 2, s.astats.p, nf * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
+    return P2S_OK;
+}
+
+static int check_mp_args(const p2s_handle *h, const void *obs, const void *count, const void *cams, long long n_frames,
+                         int n_cams, int max_persons, int n_joints, int n_max, double d_max, const void *rows) {
+    if (!h || !cams || (n_frames > 0 && (!obs || !count || !rows))) return P2S_EINVAL;
+    if (n_cams < 1 || n_cams > P2S_MAX_CAMS || n_frames < 0 || n_frames > 0x7ffffff0LL) return P2S_EINVAL;
+    if (max_persons < 1 || max_persons > P2S_MAX_DETECTIONS || n_joints < 1 || n_joints > 1024) return P2S_EINVAL;
+    if (n_max < 1 || n_max > P2S_MAX_DETECTIONS || !(d_max > 0.0)) return P2S_EINVAL;
+    if (p2s::mp_smem_bytes(n_max, n_joints) > (size_t)h->prop.sharedMemPerBlockOptin) return P2S_EINVAL;
+    return P2S_OK;
+}
+
+static int enqueue_mp(p2s_handle *h, const float *obs, const int32_t *count, const p2s_camera_model *cams, long long n_frames,
+                      int n_cams, int max_persons, int n_joints, int n_max, double d_max, double min_affinity,
+                      int8_t *rows, double *aff, int32_t *iters, cudaStream_t stream) {
+    if (n_frames == 0) return P2S_OK;
+    p2s::MpLaunch L;
+    L.obs = obs; L.count = count; L.cams = cams; L.n_frames = n_frames; L.n_cams = n_cams; L.max_persons = max_persons;
+    L.n_joints = n_joints; L.n_max = n_max; L.sm_count = h->prop.multiProcessorCount; L.d_max = d_max;
+    L.min_affinity = min_affinity; L.out_rows = rows; L.out_affinity = aff; L.out_iters = iters;
+    L.tile_counter = next_counter(h);
+    L.stream = stream;
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
+    P2S_CUDA(h, p2s::launch_mp_associate(L, &h->last_grid));
+    h->launches += 1;
+    return P2S_OK;
+}
+
+int p2s_associate_multi_device(p2s_handle *h, const float *obs, const int32_t *count, const p2s_camera_model *cams,
+                               long long n_frames, int n_cams, int max_persons, int n_joints, int n_max,
+                               double d_max, double min_affinity, int8_t *out_rows, double *out_affinity,
+                               int32_t *out_iters, void *stream) {
+    int rc = check_mp_args(h, obs, count, cams, n_frames, n_cams, max_persons, n_joints, n_max, d_max, out_rows);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    return enqueue_mp(h, obs, count, cams, n_frames, n_cams, max_persons, n_joints, n_max, d_max, min_affinity, out_rows,
+                      out_affinity, out_iters, (cudaStream_t)stream);
+}
+
+int p2s_associate_multi_host(p2s_handle *h, const float *obs, const int32_t *count, const p2s_camera_model *cams,
+                             long long n_frames, int n_cams, int max_persons, int n_joints, int n_max,
+                             double d_max, double min_affinity, int8_t *out_rows, double *out_affinity,
+                             int32_t *out_iters) {
+    int rc = check_mp_args(h, obs, count, cams, n_frames, n_cams, max_persons, n_joints, n_max, d_max, out_rows);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    const size_t C = (size_t)n_cams, per_frame = C * (size_t)max_persons * 3u * (size_t)n_joints, NM = (size_t)n_max;
+    long long chunk = std::max<long long>(1, std::min<long long>(kChunkFrames, (long long)((64u << 20) / (per_frame * 4u + 1))));
+    int i = 0;
+    for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
+        const long long nf = std::min(chunk, n_frames - f0);
+        Slot &s = h->slots[i % kSlots];
+        if ((rc = ensure(h, s.obs, nf * per_frame * 4)) || (rc = ensure(h, s.count, nf * C * 4)) ||
+            (rc = ensure(h, s.rows, nf * NM * C)) || (rc = ensure(h, s.iters, nf * 4)) ||
+            (out_affinity && (rc = ensure(h, s.aff, nf * NM * NM * 8))))
+            return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(s.obs.p, obs + f0 * per_frame, nf * per_frame * 4, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, cudaMemcpyAsync(s.count.p, count + f0 * C, nf * C * 4, cudaMemcpyHostToDevice, s.stream));
+        P2S_CUDA(h, cudaMemsetAsync(s.rows.p, 0xff, nf * NM * C, s.stream));
+        if (out_affinity) P2S_CUDA(h, cudaMemsetAsync(s.aff.p, 0, nf * NM * NM * 8, s.stream));
+        rc = enqueue_mp(h, (const float *)s.obs.p, (const int32_t *)s.count.p, cams, nf, n_cams, max_persons, n_joints, n_max,
+                        d_max, min_affinity, (int8_t *)s.rows.p, out_affinity ? (double *)s.aff.p : nullptr,
+                        (int32_t *)s.iters.p, s.stream);
+        if (rc) return rc;
+        P2S_CUDA(h, cudaMemcpyAsync(out_rows + f0 * NM * C, s.rows.p, nf * NM * C, cudaMemcpyDeviceToHost, s.stream));
+        if (out_affinity)
+            P2S_CUDA(h, cudaMemcpyAsync(out_affinity + f0 * NM * NM, s.aff.p, nf * NM * NM * 8, cudaMemcpyDeviceToHost, s.stream));
+        if (out_iters) P2S_CUDA(h, cudaMemcpyAsync(out_iters + f0, s.iters.p, nf * 4, cudaMemcpyDeviceToHost, s.stream));
     }
     for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
     return P2S_OK;

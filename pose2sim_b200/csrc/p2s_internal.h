@@ -47,7 +47,23 @@ struct AssocLaunch {
     cudaStream_t stream;
 };
 
+struct MpLaunch {
+    const float *obs;             // [n_frames][n_cams][max_persons][3 n_joints] float32 {x, y, likelihood}, device
+    const int32_t *count;         // [n_frames][n_cams], device
+    const p2s_camera_model *cams; // host: K, R, T are used
+    long long n_frames;
+    int n_cams, max_persons, n_joints, n_max, sm_count;
+    double d_max, min_affinity;
+    int8_t *out_rows;             // [n_frames][n_max][n_cams]
+    double *out_affinity;         // [n_frames][n_max][n_max] or null
+    int32_t *out_iters;           // [n_frames] or null
+    unsigned int *tile_counter;
+    cudaStream_t stream;
+};
+
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out);
+cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out);
+size_t mp_smem_bytes(int n_max, int n_joints);
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
                          double lik_thr, const p2s_camera_model *lens, void *out, int sm_count, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);

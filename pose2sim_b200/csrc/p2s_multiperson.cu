@@ -1,0 +1,328 @@
+// Multi-person cross-view association on the device: one CTA per frame.
+//
+// Replaces, per frame, the `multi_person = true` branch of associate_all
+// (Pose2Sim/personAssociation.py:783-801):
+//   compute_rays / compute_affinity   :277-408   Plücker rays of every joint of every detection, affinity
+//                                                = 1 - d / d_max with d the likelihood-weighted mean
+//                                                |reciprocal product| of two detections of different views
+//   circular_constraint               :411-428   one person per view
+//   matchSVT                          :450-509   <= 20 ADMM steps: singular-value shrinkage of X + Y/mu,
+//                                                projection on [0,1] / zero same-view blocks / unit
+//                                                diagonal / symmetry, dual update, mu doubling/halving
+//   person_index_per_cam (first half) :526-533   per row and view the arg-max detection, -1 if none > 0
+// The remaining, discrete half of person_index_per_cam (unique rows, ordering by multiplicity, duplicate
+// and min-cameras filters) stays on the host: it is a few integer rows per frame.
+//
+// The SVD of the symmetric N x N matrix (N = detections in the frame, <= 64) is a one-sided Jacobi
+// (Hestenes) in shared memory, FP64: round-robin pairing gives N/2 disjoint column pairs per round, four
+// lanes per pair split the rows, three dot products by xor-shuffles, the rotation applied to A and V.
+// U S V^T with S shrunk by tau is then sum_k max(s_k - tau, 0)/s_k a_k v_k^T — only the few columns above
+// tau (about one per person) contribute.
+#include <cmath>
+#include <cstring>
+
+#include "p2s_math.cuh"
+#include "p2s_internal.h"
+
+namespace p2s {
+
+struct RayCam { double iK[9], Rt[9], T[3], ctr[3]; };
+struct RayCams { RayCam cam[P2S_MAX_CAMS]; };
+
+struct MpArgs {
+    const float *obs;             // [n_frames][n_cams][max_persons][3 * n_joints]
+    const int32_t *count;         // [n_frames][n_cams] detections per camera
+    long long n_frames;
+    int n_cams, max_persons, n_joints, n_max;      // n_max: largest sum of detections over the frames
+    double d_max, min_affinity;
+    int max_iter;
+    double w_rank, tol, w_sparse;
+    int8_t *out_rows;             // [n_frames][n_max][n_cams]: arg-max detection per view or -1
+    double *out_affinity;         // [n_frames][n_max][n_max] final (thresholded) affinity, or null
+    int32_t *out_iters;           // [n_frames] ADMM iterations used, or null
+    unsigned int *tile_counter;
+};
+
+constexpr int kMpThreads = 128;
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(P2S_FULL, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+// Plücker coordinates of the camera->keypoint ray (personAssociation.py:301-315): unit direction, moment
+// about the origin; returns false (zero weight) when anything is NaN.
+__device__ __forceinline__ bool joint_ray(const RayCam &c, float fx, float fy, float fl, double *l, double *m) {
+    const double x = (double)fx, y = (double)fy;
+    double q[3], w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q[i] = c.iK[3 * i] * x + c.iK[3 * i + 1] * y + c.iK[3 * i + 2] - c.T[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = c.Rt[3 * i] * q[0] + c.Rt[3 * i + 1] * q[1] + c.Rt[3 * i + 2] * q[2] - c.ctr[i];
+    const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) l[i] = w[i] / n;
+    m[0] = c.ctr[1] * l[2] - c.ctr[2] * l[1];
+    m[1] = c.ctr[2] * l[0] - c.ctr[0] * l[2];
+    m[2] = c.ctr[0] * l[1] - c.ctr[1] * l[0];
+    const double s = l[0] + l[1] + l[2] + m[0] + m[1] + m[2] + (double)fl;
+    return s == s;                                                     // any NaN -> the joint carries no weight
+}
+
+__global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams cams, const MpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int C = a.n_cams, NP = a.max_persons, J = a.n_joints, NM = a.n_max;
+    const int LD = NM | 1;                                              // odd leading dimension: fewer bank conflicts
+    double *X = reinterpret_cast<double *>(smem_raw);
+    double *Y = X + (size_t)NM * LD;
+    double *W = Y + (size_t)NM * LD;
+    double *A = W + (size_t)NM * LD;                                   // column-major: A[col * LD + row]
+    double *V = A + (size_t)NM * LD;
+    double *Qp = V + (size_t)NM * LD;
+    double *sig = Qp + (size_t)NM * LD;                                // NM shrink factors
+    double *red = sig + NM;                                            // 4
+    float *sobs = reinterpret_cast<float *>(red + 4);                  // [N][3 J]
+    int *s_view = reinterpret_cast<int *>(sobs + (size_t)NM * 3 * J);  // NM: view of each detection
+    int *s_cum = s_view + NM;                                          // C + 1
+    int *s_flag = s_cum + P2S_MAX_CAMS + 1;                            // [0] frame, [1] rotations in the sweep
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_flag[0] = (int)atomicAdd(a.tile_counter, 1u);
+        __syncthreads();
+        const long long f = s_flag[0];
+        if (f >= a.n_frames) break;
+
+        // ---- detections of the frame -----------------------------------------------------------------------
+        if (tid == 0) {
+            int acc = 0;
+            for (int c = 0; c < C; ++c) {
+                s_cum[c] = acc;
+                int n = a.count[f * C + c];
+                n = max(0, min(n, NP));
+                for (int p = 0; p < n; ++p) s_view[acc + p] = c;
+                acc += n;
+            }
+            s_cum[C] = acc;
+        }
+        __syncthreads();
+        const int N = s_cum[C];
+        for (int i = tid; i < N * 3 * J; i += kMpThreads) {
+            const int n = i / (3 * J), r = i - n * 3 * J;
+            const int c = s_view[n], p = n - s_cum[c];
+            sobs[i] = a.obs[((f * C + c) * NP + p) * (size_t)(3 * J) + r];
+        }
+        __syncthreads();
+
+        // ---- affinity between detections of different views (:347-408), times the view constraint -----------
+        for (int e = tid; e < N * N; e += kMpThreads) {
+            const int i = e / N, j = e - i * N;
+            if (i > j) continue;
+            double aff = 0.0;                                           // same view (and the diagonal): distance 2 d_max -> 0
+            const int ci = s_view[i], cj = s_view[j];
+            if (ci != cj) {
+                double num = 0.0, den = 0.0;
+                const float *oi = sobs + (size_t)i * 3 * J, *oj = sobs + (size_t)j * 3 * J;
+                for (int k = 0; k < J; ++k) {
+                    double li[3], mi[3], lj[3], mj[3];
+                    const bool vi = joint_ray(cams.cam[ci], oi[3 * k], oi[3 * k + 1], oi[3 * k + 2], li, mi);
+                    const bool vj = joint_ray(cams.cam[cj], oj[3 * k], oj[3 * k + 1], oj[3 * k + 2], lj, mj);
+                    if (vi && vj) {
+                        const double prod = (li[0] * mj[0] + li[1] * mj[1] + li[2] * mj[2]) + (lj[0] * mi[0] + lj[1] * mi[1] + lj[2] * mi[2]);
+                        const double w = sqrt((double)oi[3 * k + 2] * (double)oj[3 * k + 2]);
+                        num += fabs(prod) * w;
+                        den += w;
+                    }
+                }
+                double d = num / (1e-5 + den);
+                if (d > a.d_max) d = a.d_max;
+                aff = 1.0 - d / a.d_max;
+            }
+            X[i * LD + j] = aff; X[j * LD + i] = aff;
+        }
+        __syncthreads();
+        // matchSVT start (:468-476): zero diagonal, Y = 0, W = w_sparse - X
+        for (int e = tid; e < N * N; e += kMpThreads) {
+            const int i = e / N, j = e - i * N;
+            if (i == j) X[i * LD + j] = 0.0;
+            Y[i * LD + j] = 0.0;
+            W[i * LD + j] = a.w_sparse - ((i == j) ? 0.0 : X[i * LD + j]);
+        }
+        __syncthreads();
+
+        double mu = 64.0;
+        int iters = 0;
+        for (int it = 0; it < a.max_iter && N > 0; ++it) {
+            iters = it + 1;
+            // ---- A = X + Y / mu (symmetric), V = I ------------------------------------------------------------
+            for (int e = tid; e < N * N; e += kMpThreads) {
+                const int i = e / N, j = e - i * N;
+                A[j * LD + i] = X[i * LD + j] + Y[i * LD + j] * 1.0 / mu;
+                V[j * LD + i] = (i == j) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            // ---- one-sided Jacobi: orthogonalise the columns of A, accumulate V ----------------------------------
+            const int n_even = (N + 1) & ~1;
+            const int pair = tid >> 2, sub = tid & 3;
+            for (int sweep = 0; sweep < 40; ++sweep) {
+                if (tid == 0) s_flag[1] = 0;
+                __syncthreads();
+                for (int r = 0; r < n_even - 1; ++r) {
+                    int p = -1, q = -1;
+                    if (pair < n_even / 2) {
+                        if (pair == 0) { p = n_even - 1; q = r; }
+                        else { p = (r + pair) % (n_even - 1); q = (r - pair + (n_even - 1)) % (n_even - 1); }
+                        if (p > q) { const int t = p; p = q; q = t; }
+                        if (q >= N) p = -1;                                 // the padding column of an odd N
+                    }
+                    double al = 0.0, be = 0.0, ga = 0.0;
+                    if (p >= 0) {
+                        const double *ap = A + (size_t)p * LD, *aq = A + (size_t)q * LD;
+                        for (int i = sub; i < N; i += 4) { const double u = ap[i], v = aq[i]; al = fma(u, u, al); be = fma(v, v, be); ga = fma(u, v, ga); }
+                    }
+                    al += __shfl_xor_sync(P2S_FULL, al, 1); be += __shfl_xor_sync(P2S_FULL, be, 1); ga += __shfl_xor_sync(P2S_FULL, ga, 1);
+                    al += __shfl_xor_sync(P2S_FULL, al, 2); be += __shfl_xor_sync(P2S_FULL, be, 2); ga += __shfl_xor_sync(P2S_FULL, ga, 2);
+                    if (p >= 0 && fabs(ga) > 1e-15 * sqrt(al * be) && ga != 0.0) {
+                        const double zeta = (be - al) / (2.0 * ga);
+                        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                        double *ap = A + (size_t)p * LD, *aq = A + (size_t)q * LD;
+                        double *vp = V + (size_t)p * LD, *vq = V + (size_t)q * LD;
+                        for (int i = sub; i < N; i += 4) {
+                            const double u = ap[i], v = aq[i];
+                            ap[i] = cs * u - sn * v; aq[i] = sn * u + cs * v;
+                            const double x = vp[i], y = vq[i];
+                            vp[i] = cs * x - sn * y; vq[i] = sn * x + cs * y;
+                        }
+                        if (sub == 0) s_flag[1] = 1;
+                    }
+                    __syncthreads();
+                }
+                if (s_flag[1] == 0) break;
+                __syncthreads();
+            }
+            // ---- shrink: factor_k = max(s_k - tau, 0) / s_k, s_k = |a_k| --------------------------------------------
+            const double tau = a.w_rank / mu;
+            for (int k = tid; k < N; k += kMpThreads) {
+                double s2 = 0.0;
+                for (int i = 0; i < N; ++i) s2 = fma(A[(size_t)k * LD + i], A[(size_t)k * LD + i], s2);
+                const double s = sqrt(s2);
+                sig[k] = (s > tau) ? (s - tau) / s : 0.0;
+            }
+            __syncthreads();
+            // ---- Qp = U max(S - tau, 0) V^T, then the projection / dual update / residuals -------------------------
+            for (int e = tid; e < N * N; e += kMpThreads) {
+                const int i = e / N, j = e - i * N;
+                double acc = 0.0;
+                for (int k = 0; k < N; ++k) {
+                    const double fk = sig[k];
+                    if (fk != 0.0) acc = fma(fk * A[(size_t)k * LD + i], V[(size_t)k * LD + j], acc);
+                }
+                Qp[i * LD + j] = acc;
+            }
+            __syncthreads();
+            double pr = 0.0, dr = 0.0;
+            for (int e = tid; e < N * N; e += kMpThreads) {
+                const int i = e / N, j = e - i * N;
+                if (i > j) continue;
+                const bool same = s_view[i] == s_view[j];
+                double xij = Qp[i * LD + j] - (W[i * LD + j] + Y[i * LD + j]) / mu;
+                double xji = Qp[j * LD + i] - (W[j * LD + i] + Y[j * LD + i]) / mu;
+                if (same) { xij = 0.0; xji = 0.0; }
+                if (i == j) { xij = 1.0; xji = 1.0; }
+                if (xij < 0.0) xij = 0.0; if (xij > 1.0) xij = 1.0;
+                if (xji < 0.0) xji = 0.0; if (xji > 1.0) xji = 1.0;
+                const double xs = (xij + xji) / 2.0;
+                const double oij = X[i * LD + j], oji = X[j * LD + i];
+                const double eij = xs - Qp[i * LD + j], eji = xs - Qp[j * LD + i];
+                Y[i * LD + j] += mu * eij;
+                pr += eij * eij;
+                dr += (xs - oij) * (xs - oij);
+                if (i != j) {
+                    Y[j * LD + i] += mu * eji;
+                    pr += eji * eji;
+                    dr += (xs - oji) * (xs - oji);
+                }
+                X[i * LD + j] = xs; X[j * LD + i] = xs;
+            }
+            const double pres = sqrt(block_sum(pr, red)) / N;
+            const double dres = mu * sqrt(block_sum(dr, red)) / N;
+            __syncthreads();
+            if (pres < a.tol && dres < a.tol) break;
+            if (pres > 10.0 * dres) mu = 2.0 * mu;
+            else if (dres > 10.0 * pres) mu = mu / 2.0;
+        }
+
+        // ---- min_affinity threshold (:800) and the per-row / per-view arg-max (:526-533) ---------------------------
+        for (int e = tid; e < N * N; e += kMpThreads) {
+            const int i = e / N, j = e - i * N;
+            if (X[i * LD + j] < a.min_affinity) X[i * LD + j] = 0.0;
+            if (a.out_affinity) a.out_affinity[(f * NM + i) * NM + j] = X[i * LD + j];
+        }
+        __syncthreads();
+        for (int e = tid; e < N * C; e += kMpThreads) {
+            const int r = e / C, v = e - r * C;
+            int best = -1;
+            double bv = 0.0;
+            for (int j = s_cum[v]; j < s_cum[v + 1]; ++j) {
+                const double x = X[r * LD + j];
+                if (x > bv) { bv = x; best = j - s_cum[v]; }                // first maximum, and only if > 0
+            }
+            a.out_rows[(f * NM + r) * C + v] = (int8_t)best;
+        }
+        if (tid == 0 && a.out_iters) a.out_iters[f] = iters;
+        (void)lane;
+    }
+}
+
+size_t mp_smem_bytes(int n_max, int n_joints) {
+    const size_t LD = (size_t)(n_max | 1);
+    return 6 * (size_t)n_max * LD * sizeof(double) + ((size_t)n_max + 4) * sizeof(double) + (size_t)n_max * 3 * n_joints * sizeof(float) +
+           ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + 16;
+}
+
+cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out) {
+    RayCams cams;
+    std::memset(&cams, 0, sizeof cams);
+    for (int c = 0; c < L.n_cams; ++c) {
+        const p2s_camera_model &m = L.cams[c];
+        RayCam &o = cams.cam[c];
+        // inverse of K (common.py:282 np.linalg.inv) by the adjugate; K is upper triangular in practice
+        const double *K = m.K;
+        const double det = K[0] * (K[4] * K[8] - K[5] * K[7]) - K[1] * (K[3] * K[8] - K[5] * K[6]) + K[2] * (K[3] * K[7] - K[4] * K[6]);
+        o.iK[0] = (K[4] * K[8] - K[5] * K[7]) / det; o.iK[1] = (K[2] * K[7] - K[1] * K[8]) / det; o.iK[2] = (K[1] * K[5] - K[2] * K[4]) / det;
+        o.iK[3] = (K[5] * K[6] - K[3] * K[8]) / det; o.iK[4] = (K[0] * K[8] - K[2] * K[6]) / det; o.iK[5] = (K[2] * K[3] - K[0] * K[5]) / det;
+        o.iK[6] = (K[3] * K[7] - K[4] * K[6]) / det; o.iK[7] = (K[1] * K[6] - K[0] * K[7]) / det; o.iK[8] = (K[0] * K[4] - K[1] * K[3]) / det;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) o.Rt[3 * i + j] = m.R[3 * j + i];
+        for (int i = 0; i < 3; ++i) o.T[i] = m.T[i];
+        for (int i = 0; i < 3; ++i) o.ctr[i] = -(o.Rt[3 * i] * m.T[0] + o.Rt[3 * i + 1] * m.T[1] + o.Rt[3 * i + 2] * m.T[2]);
+    }
+    MpArgs a;
+    a.obs = L.obs; a.count = L.count; a.n_frames = L.n_frames; a.n_cams = L.n_cams; a.max_persons = L.max_persons;
+    a.n_joints = L.n_joints; a.n_max = L.n_max; a.d_max = L.d_max; a.min_affinity = L.min_affinity;
+    a.max_iter = 20; a.w_rank = 50.0; a.tol = 1e-4; a.w_sparse = 0.1;            // matchSVT's call-site constants (:799)
+    a.out_rows = L.out_rows; a.out_affinity = L.out_affinity; a.out_iters = L.out_iters; a.tile_counter = L.tile_counter;
+    const size_t smem = mp_smem_bytes(L.n_max, L.n_joints);
+    cudaError_t e = cudaFuncSetAttribute(mp_associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mp_associate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_associate_kernel, kMpThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)L.sm_count * per_sm;
+    if (grid > L.n_frames) grid = L.n_frames;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    mp_associate_kernel<<<(unsigned)grid, kMpThreads, smem, L.stream>>>(cams, a);
+    return cudaGetLastError();
+}
+
+}  // namespace p2s

@@ -1,129 +1,59 @@
-"""Multi-person cross-view association (host, NumPy) — the `multi_person = true` branch of
-`associate_all` (Pose2Sim/personAssociation.py:783-801): Plücker-ray affinity between every pair of
-detections of different cameras, low-rank matching by singular-value thresholding under the "one
-person per view" constraint, proposal extraction.
+"""Multi-person cross-view association — the `multi_person = true` branch of `associate_all`
+(Pose2Sim/personAssociation.py:783-801), SURVEY §8(f) row 3.
 
-This is SURVEY §8(f) row 3: a different kernel family (batched small dense linear algebra), not the
-triangulation hot path; it lives on the host so that the drop-in covers the reference's Demo_MultiPerson
-configuration.  Per frame the work is a few 7-vector dot products per detection pair and at most twenty
-SVDs of a (sum of persons) x (sum of persons) matrix.
+    stage_detections()      host     :783-790  `read_json` lists -> obs[F, C, NP, 3 J] float32, count[F, C]
+    Engine.associate_multi  DEVICE   :793-800 + :526-531  ray affinity, view constraint, matchSVT, min_affinity
+                                     cut, per-row / per-view arg-max — `mp_associate_kernel`, one CTA per frame
+    proposals_from_rows()   host     :535-547  integer bookkeeping on <= 64 small rows per frame (unique rows,
+                                     ordering by multiplicity, duplicate and min-cameras filters)
+
+All floating-point work is on the GPU; nothing here computes an affinity or an SVD, and there is no CPU
+fallback (the NumPy restatement lives in oracle/p2s_oracle_mp.py, test infrastructure).
 """
 import numpy as np
 
-
-def camera_ray_params(calib):
-    """Per camera: inverse intrinsics, world-from-camera rotation, translation, optical centre
-    (common.py:254-288 `retrieve_calib_params`: inv_K, R_mat = Rodrigues(rotation), T)."""
-    from .calib import rodrigues
-    out = []
-    for cam in calib:
-        K = np.array(cam["matrix"], dtype=np.float64)
-        R = rodrigues(cam["rotation"])
-        T = np.array(cam["translation"], dtype=np.float64)
-        out.append({"inv_K": np.linalg.inv(K), "Rt": R.T, "T": T, "centre": -R.T @ T})
-    return out
+from . import _lib
+from . import staging as _stg
 
 
-def person_rays(keypoints, cam):
-    """personAssociation.py:277-318 `compute_rays` for one detection: keypoints = flat [x, y, lik, ...].
-    Returns [J, 7]: unit direction of the camera->keypoint ray, its moment about the origin, likelihood;
-    a joint with any NaN becomes seven zeros (zero weight)."""
-    kp = np.asarray(keypoints, dtype=np.float64)
-    x, y, lik = kp[0::3], kp[1::3], kp[2::3]
-    pix = np.stack([x, y, np.ones_like(x)], axis=1)                         # [J, 3]
-    with np.errstate(invalid="ignore", divide="ignore"):
-        world = (cam["Rt"] @ ((cam["inv_K"] @ pix.T) - cam["T"][:, None])).T   # R^T (K^-1 q - T)
-        line = world - cam["centre"]
-        line = line / np.linalg.norm(line, axis=1, keepdims=True)
-        moment = np.cross(np.broadcast_to(cam["centre"], line.shape), line)
-    rays = np.concatenate([line, moment, lik[:, None]], axis=1)
-    rays[np.isnan(rays).any(axis=1)] = 0.0
-    return rays
+def stage_detections(parsed):
+    """parsed[f][c] = decoded JSON (or None).  Returns obs [F, C, NP, 3 J] float32, count [F, C] int32 and the
+    number of values float32 cannot hold exactly.  Detections are `read_json`'s lists (people with >= 3
+    values, personAssociation.py:260-274).  All keypoint lists must have the same length: the reference
+    stacks them with np.array (:378) and broadcasts across cameras (:390-392), which raises otherwise."""
+    F = len(parsed)
+    C = len(parsed[0]) if F else 0
+    people = [[_stg.read_people(js) if js is not None else [] for js in row] for row in parsed]
+    lengths = {len(p) for row in people for cam in row for p in cam}
+    if len(lengths) > 1:
+        raise ValueError(f"pose_keypoints_2d lists of different lengths {sorted(lengths)}: the reference cannot "
+                         f"stack them either (personAssociation.py:378)")
+    L = lengths.pop() if lengths else 3
+    if L % 3:
+        raise ValueError(f"pose_keypoints_2d has {L} values, not a multiple of 3")
+    NP = max([len(cam) for row in people for cam in row] + [1])
+    count = np.zeros((F, C), np.int32)
+    obs64 = np.full((F, C, NP, L), np.nan, np.float64)
+    for f, row in enumerate(people):
+        for c, cam in enumerate(row):
+            count[f, c] = len(cam)
+            for p, kp in enumerate(cam):
+                obs64[f, c, p] = [np.nan if v is None else v for v in kp]
+    n_max = int(count.sum(axis=1).max(initial=0))
+    if n_max > _lib.P2S_MAX_DETECTIONS:
+        raise ValueError(f"{n_max} detections in one frame: the device matching handles at most "
+                         f"{_lib.P2S_MAX_DETECTIONS} per frame")
+    return obs64.astype(np.float32), count, _stg.float32_inexact(obs64)
 
 
-def ray_affinity(detections, cams, cum, max_distance):
-    """personAssociation.py:347-408 `compute_affinity`.  detections[c] = list of flat keypoint lists of
-    camera c; cum = cumulative person counts.  Affinity = 1 - d / max_distance with d the
-    likelihood-weighted mean |reciprocal product| of the two detections' joint rays, clamped at
-    max_distance; pairs of the same camera (and cameras without detection) keep d = 2 max_distance."""
-    rays = [np.array([person_rays(p, cams[c]) for p in det]) for c, det in enumerate(detections)]
-    n = cum[-1]
-    dist = np.zeros((n, n)) + 2 * max_distance
-    C = len(detections)
-    for c0 in range(C):
-        for c1 in range(c0 + 1, C):
-            if cum[c0] == cum[c0 + 1] or cum[c1] == cum[c1 + 1]:
-                continue
-            a, b = rays[c0][:, None], rays[c1][None, :]                    # [n0, 1, J, 7], [1, n1, J, 7]
-            recip = np.abs(np.sum(a[..., :3] * b[..., 3:6], axis=-1) + np.sum(b[..., :3] * a[..., 3:6], axis=-1))
-            w = np.sqrt(a[..., -1] * b[..., -1])
-            d = np.sum(recip * w, axis=-1) / (1e-5 + w.sum(axis=-1))
-            dist[cum[c0]:cum[c0 + 1], cum[c1]:cum[c1 + 1]] = d
-            dist[cum[c1]:cum[c1 + 1], cum[c0]:cum[c0 + 1]] = d.T
-    dist[dist > max_distance] = max_distance
-    return 1 - dist / max_distance
-
-
-def view_constraint(cum):
-    """personAssociation.py:411-428: 1 on the diagonal and between detections of different views."""
-    n = cum[-1]
-    view = np.repeat(np.arange(len(cum) - 1), np.diff(cum))
-    return ((view[:, None] != view[None, :]) | np.eye(n, dtype=bool)).astype(np.float64)
-
-
-def shrink_singular_values(matrix, tau):
-    """personAssociation.py:431-447 `SVT`."""
-    U, s, Vt = np.linalg.svd(matrix)
-    return U @ np.diag(np.maximum(s - tau, 0)) @ Vt
-
-
-def match_svt(affinity, cum, constraint, max_iter=20, w_rank=50, tol=1e-4, w_sparse=0.1):
-    """personAssociation.py:450-509 `matchSVT`: ADMM-style alternation between a low-rank step
-    (singular-value shrinkage by w_rank / mu) and the projection on [0, 1] with zero same-view blocks,
-    unit diagonal and symmetry; mu doubles / halves on the ratio of primal and dual residuals."""
-    X = affinity.copy()
-    n = X.shape[0]
-    di = np.arange(n)
-    X[di, di] = 0.0
-    Y = np.zeros_like(X)
-    W = w_sparse - X
-    mu = 64
-    for _ in range(max_iter):
-        X_prev = X.copy()
-        Q = shrink_singular_values(X + Y * 1.0 / mu, w_rank / mu)
-        X = Q - (W + Y) / mu
-        for i in range(len(cum) - 1):
-            X[cum[i]:cum[i + 1], cum[i]:cum[i + 1]] = 0
-        X[di, di] = 1.0
-        X[X < 0] = 0
-        X[X > 1] = 1
-        X = X * constraint
-        X = (X + X.T) / 2
-        Y = Y + mu * (X - Q)
-        primal = np.linalg.norm(X - Q) / n
-        dual = mu * np.linalg.norm(X - X_prev) / n
-        if primal < tol and dual < tol:
-            break
-        if primal > 10 * dual:
-            mu = 2 * mu
-        elif dual > 10 * primal:
-            mu = mu / 2
-    return X
-
-
-def proposals_from_affinity(affinity, cum, min_cams):
-    """personAssociation.py:512-549 `person_index_per_cam`: per row the arg-max detection of every view
-    (-1 when the view has none above 0), unique rows ordered by multiplicity, rows that reuse a
-    detection of an earlier row dropped, rows seen by fewer than min_cams views dropped."""
-    n_views = len(cum) - 1
-    rows = []
-    for r in range(affinity.shape[0]):
-        row = []
-        for v in range(n_views):
-            seg = affinity[r, cum[v]:cum[v + 1]]
-            row.append(np.argmax(seg) if (len(seg) > 0 and max(seg) > 0) else -1)
-        rows.append(row)
+def proposals_from_rows(rows, min_cams):
+    """personAssociation.py:532-547 on the per-row arg-max table of one frame (rows [N, C] integers, -1 = no
+    detection): unique rows ordered by multiplicity, rows reusing a detection of an earlier row dropped,
+    rows seen by fewer than min_cams views dropped.  Returns [n_persons, C] float (NaN = not seen).
+    The calls are the reference's own (np.unique / argsort), so ties order identically."""
     prop = np.array(rows, dtype=float)
+    if prop.ndim != 2:
+        prop = prop.reshape(0, 0)
     prop, counts = np.unique(prop, axis=0, return_counts=True)
     prop = prop[np.argsort(counts)[::-1]]
     prop[prop == -1] = np.nan
@@ -135,13 +65,9 @@ def proposals_from_affinity(affinity, cum, min_cams):
     return np.array([p for n, p in zip(seen, prop) if n >= min_cams])
 
 
-def associate_frame(detections, cams, max_distance, min_affinity, min_cams):
-    """One frame of the multi-person branch (personAssociation.py:783-801).  Returns proposals
-    [n_persons, n_cams] (detection index per camera, NaN = not seen)."""
-    cum = np.cumsum([0] + [len(d) for d in detections])
-    affinity = ray_affinity(detections, cams, cum, max_distance)
-    constraint = view_constraint(cum)
-    affinity = affinity * constraint
-    affinity = match_svt(affinity, cum, constraint)
-    affinity[affinity < min_affinity] = 0
-    return proposals_from_affinity(affinity, cum, min_cams)
+def associate_frames(engine, obs, count, models, max_distance, min_affinity, min_cams):
+    """All frames in ONE device call; returns the list of proposals per frame."""
+    n_max = max(1, int(count.sum(axis=1).max(initial=0)))
+    out = engine.associate_multi_host(obs, count, models, max_distance, min_affinity, n_max=n_max)
+    n = count.sum(axis=1)
+    return [proposals_from_rows(out["rows"][f, :n[f]], min_cams) for f in range(len(count))]

@@ -33,19 +33,20 @@ def _as_P(P, n_cams):
 
 
 def lens_array(models):
-    """List of dicts {K[3,3], dist[<=8], R[3,3], T[3], newK[3,3]} -> ctypes array of p2s_camera_model."""
+    """List of dicts {K[3,3], dist[<=8], R[3,3], T[3], newK[3,3]} -> ctypes array of p2s_camera_model
+    (dist and newK optional: the multi-person matching only uses K, R, T)."""
     arr = (_lib.CameraModel * len(models))()
     for m, o in zip(models, arr):
         o.K[:] = np.asarray(m["K"], float).reshape(9)
         d = np.zeros(8)
-        dist = np.asarray(m["dist"], float).reshape(-1)
+        dist = np.asarray(m.get("dist", []), float).reshape(-1)
         if dist.size > 8:
             raise ValueError("at most 8 distortion coefficients (k1 k2 p1 p2 k3 k4 k5 k6) are supported")
         d[:dist.size] = dist
         o.dist[:] = d
         o.R[:] = np.asarray(m["R"], float).reshape(9)
         o.T[:] = np.asarray(m["T"], float).reshape(3)
-        o.newK[:] = np.asarray(m["newK"], float).reshape(9)
+        o.newK[:] = np.asarray(m.get("newK", m["K"]), float).reshape(9)
     return arr
 
 
@@ -246,4 +247,46 @@ class Engine:
             int(min_cams), _ptr(out["err"]), _ptr(out["comb"]), _ptr(out["Q"]), _ptr(st)))
         if want_stats:
             out["stats"] = st
+        return out
+
+    # ---- multi-person association -----------------------------------------------------------------------
+    def associate_multi_host(self, obs, count, models, max_distance, min_affinity, n_max=None, want_affinity=False):
+        """personAssociation.py:793-801 for all frames.  obs: host float32 [F, C, NP, 3 J] (pose_keypoints_2d of
+        every detection); count: int32 [F, C]; models: list of {K, R, T} per camera.  Returns `rows`
+        int8 [F, n_max, C] (per detection the arg-max detection of each view, -1 = none), `iters` [F] and, on
+        request, the matched affinity [F, n_max, n_max]."""
+        obs = np.ascontiguousarray(obs, dtype=np.float32)
+        F, Cn, NP, L = obs.shape
+        assert L % 3 == 0
+        count = np.ascontiguousarray(count, dtype=np.int32)
+        assert tuple(count.shape) == (F, Cn) and len(models) == Cn
+        if n_max is None:
+            n_max = max(1, int(count.sum(axis=1).max(initial=0)))
+        out = {"rows": np.full((F, n_max, Cn), -1, np.int8), "iters": np.zeros(F, np.int32)}
+        aff = np.zeros((F, n_max, n_max), np.float64) if want_affinity else None
+        arr = lens_array(models)
+        _lib.check(self.h, self.lib.p2s_associate_multi_host(
+            self.h, obs.ctypes.data, count.ctypes.data, C.cast(arr, C.c_void_p), F, Cn, NP, L // 3, int(n_max),
+            float(max_distance), float(min_affinity), _ptr(out["rows"]), _ptr(aff), _ptr(out["iters"])))
+        if want_affinity:
+            out["affinity"] = aff
+        return out
+
+    def associate_multi(self, obs, count, models, max_distance, min_affinity, n_max, want_affinity=False):
+        """Device-resident variant: obs CUDA float32 [F, C, NP, 3 J], count CUDA int32 [F, C]; asynchronous on the
+        current stream.  Returns CUDA tensors."""
+        torch = _torch()
+        F, Cn, NP, L = obs.shape
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and L % 3 == 0
+        assert count.is_cuda and count.dtype == torch.int32 and tuple(count.shape) == (F, Cn) and count.is_contiguous()
+        dev = obs.device
+        out = {"rows": torch.full((F, n_max, Cn), -1, dtype=torch.int8, device=dev),
+               "iters": torch.zeros((F,), dtype=torch.int32, device=dev)}
+        aff = torch.zeros((F, n_max, n_max), dtype=torch.float64, device=dev) if want_affinity else None
+        arr = lens_array(models)
+        _lib.check(self.h, self.lib.p2s_associate_multi_device(
+            self.h, _ptr(obs), _ptr(count), C.cast(arr, C.c_void_p), F, Cn, NP, L // 3, int(n_max),
+            float(max_distance), float(min_affinity), _ptr(out["rows"]), _ptr(aff), _ptr(out["iters"]), self._stream()))
+        if want_affinity:
+            out["affinity"] = aff
         return out

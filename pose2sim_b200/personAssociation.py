@@ -8,8 +8,8 @@ replaced by ONE batched call into the sm_100a library (`p2s_associate_host`).
     write_outputs()    host    :776-808   rewrite JSON with the chosen person per camera, recap
 
 Multi-person mode (Plücker-ray affinity + SVT matching, :277-549) is a different
-kernel family — small dense linear algebra per frame — and runs on the host (`multi_person.py`); the
-single-person search has no CPU implementation in this package.
+kernel family — small dense linear algebra per frame — and also runs on the device (`multi_person.py`,
+`p2s_associate_multi_host`, one CTA per frame).  Neither search has a CPU implementation in this package.
 """
 import json
 import logging
@@ -116,21 +116,25 @@ def solve_frames(st, engine=None):
     return {"err": out["err"], "comb": comb, "Q": out["Q"]}
 
 
-def solve_frames_multi_person(st):
-    """Host: personAssociation.py:783-801 for every frame.  Returns the list of proposals per frame."""
-    import warnings
+def stage_multi_person(st):
+    """personAssociation.py:783-790 for every frame -> obs[F, C, NP, 3 J], count[F, C], camera models."""
     from . import multi_person as mp
+    obs, count, inexact = mp.stage_detections(st.parsed)
+    if inexact:
+        logging.warning(f"{inexact} 2D values are not exactly representable in float32 and were rounded for the "
+                        f"device staging layout.")
+    return obs, count, _calib.camera_models(st.calib_file)
+
+
+def solve_frames_multi_person(st, engine=None):
+    """DEVICE: personAssociation.py:793-801 for all frames in one call.  Returns the proposals per frame."""
+    from . import multi_person as mp
+    from . import ops
+    eng = engine if engine is not None else ops.get_engine(0)
     s = st.settings
-    calib, keys = _calib.load_calibration(st.calib_file)
-    cams = mp.camera_ray_params([calib[k] for k in keys])
-    out = []
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", RuntimeWarning)
-        for parsed in st.parsed:
-            detections = [_stg.read_people(js) if js is not None else [] for js in parsed]
-            out.append(mp.associate_frame(detections, cams, s["reconstruction_error_threshold"], s["min_affinity"],
-                                          s["min_cams"]))
-    return out
+    obs, count, models = stage_multi_person(st)
+    return mp.associate_frames(eng, obs, count, models, s["reconstruction_error_threshold"], s["min_affinity"],
+                               s["min_cams"])
 
 
 def rewrite_frame(tracked_paths, source_js, proposals):

@@ -137,3 +137,31 @@ def make_association_workload(C, F, n_persons, seed=404, K=HALPE_26_COUNT, track
         drop = g.random((F, C)) < p_missing
         count = np.where(drop, g.integers(0, n_persons, (F, C)), count).astype(np.int32)
     return {"P": P, "obs": obs, "count": count, "perm": perm, "truth": Q, "F": F, "C": C, "Np": n_persons}
+
+
+def make_multi_person_workload(C, F, n_persons, seed=404, K=HALPE_26_COUNT, sigma=2.0, p_out=0.05, p_low=0.05,
+                               p_missing=0.1, p_nan=0.02):
+    """Multi-person association frames (cfg4 shape): every camera lists its detected persons in a random
+    order, each with ALL K keypoints; with probability p_missing a (frame, camera) loses some persons, and
+    with probability p_nan a keypoint triple is NaN (an undetected joint).
+
+    Returns dict with models (list of {K, R, T}), P, obs[F, C, n_persons, 3 K] float32 (pose_keypoints_2d
+    layout x, y, likelihood per joint), count[F, C], perm[F, C, n_persons]."""
+    P, Ks, Rs, ts = ring_cameras(C)
+    Q = truth_points(F, n_persons, K, seed)                             # [F, Np, K, 3]
+    x, y, lik = observe(Q, P, seed, sigma, p_out, p_low)                # [F, Np, K, C]
+    g = _rng(seed * 31 + 11)
+    perm = np.stack([np.stack([g.permutation(n_persons) for _ in range(C)]) for _ in range(F)])
+    kp = np.stack([x, y, lik], axis=-1).transpose(0, 3, 1, 2, 4)        # [F, C, Np, K, 3]
+    fidx = np.arange(F)[:, None, None]
+    cidx = np.arange(C)[None, :, None]
+    kp = kp[fidx, cidx, perm]                                           # detection order per camera
+    nan = g.random((F, C, n_persons, K)) < p_nan
+    kp = np.where(nan[..., None], np.float32(np.nan), kp)
+    obs = np.ascontiguousarray(kp.reshape(F, C, n_persons, 3 * K), dtype=np.float32)
+    count = np.full((F, C), n_persons, np.int32)
+    if p_missing > 0:
+        drop = g.random((F, C)) < p_missing
+        count = np.where(drop, g.integers(0, n_persons, (F, C)), count).astype(np.int32)
+    models = [{"K": Ks[c], "R": Rs[c], "T": ts[c]} for c in range(C)]
+    return {"P": P, "models": models, "obs": obs, "count": count, "perm": perm, "F": F, "C": C, "Np": n_persons}

@@ -122,16 +122,10 @@ def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
     assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
 
 
-def test_multi_person_association_matches_reference_json(golden, tmp_path):
-    """`associate_all` with multi_person = true (host NumPy: ray affinity + SVT matching) writes the
-    same people, in the same order, as the reference did (tests/golden/e2e_assoc_multi.npz)."""
+def assert_multi_person_json_equal(proj, g):
+    """pose-associated/ of a multi-person trial against tests/golden/e2e_assoc_multi.npz."""
     import json as _json
     import os as _os
-    import pose2sim_b200
-    g = golden("e2e_assoc_multi.npz")
-    proj, cfg = rebuild_trial(g, tmp_path, "trial_massoc")
-    with in_dir(proj):
-        assert pose2sim_b200.associate_all(cfg) is None
     cams = [str(c) for c in g["cams"]]
     F, C, S, V = g["chosen"].shape
     for c, cam in enumerate(cams):
@@ -148,6 +142,33 @@ def test_multi_person_association_matches_reference_json(golden, tmp_path):
                     assert np.array_equal(np.asarray(person["pose_keypoints_2d"], np.float32), ref), (f, c, p)
                 else:
                     assert np.isnan(ref).all(), (f, c, p)
+
+
+def test_multi_person_association_matches_reference_json(golden, tmp_path):
+    """Host half of `associate_all` with multi_person = true (staging, proposal bookkeeping, JSON rewrite)
+    with the NumPy oracle standing in for the device call: same people, in the same order, as the
+    reference wrote (tests/golden/e2e_assoc_multi.npz).  This also pins oracle/p2s_oracle_mp.py."""
+    import p2s_oracle_mp as omp
+    from pose2sim_b200 import multi_person as mp
+    g = golden("e2e_assoc_multi.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_massoc")
+    with in_dir(proj):
+        st = pa.stage_project(cfg)
+        obs, count, models = pa.stage_multi_person(st)
+        s = st.settings
+        cams = omp.camera_ray_params(models)
+        proposals = []
+        for f in range(len(count)):
+            det = [[obs[f, c, p].astype(float) for p in range(count[f, c])] for c in range(st.n_cams)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                aff, cum = omp.frame_affinity(det, cams, s["reconstruction_error_threshold"], s["min_affinity"])
+                ref = omp.proposals_from_affinity(aff, cum, s["min_cams"])
+            got = mp.proposals_from_rows(omp.argmax_rows(aff, cum), s["min_cams"])
+            assert np.array_equal(got, ref, equal_nan=True)
+            proposals.append(got)
+        pa.write_outputs_multi_person(st, proposals)
+    assert_multi_person_json_equal(proj, g)
 
 
 @pytest.mark.parametrize("i", range(6))
