@@ -225,6 +225,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
+                    help="N > 1: 'push' = the kernel stores its outputs straight into rank 0's memory over NVLink "
+                         "(sharding.PeerGather), 'nccl' = dist.gather after the kernel")
     args = ap.parse_args()
     global JSON_OUT
     JSON_OUT = _claim_stdout()
@@ -264,23 +267,50 @@ def main():
     packs = [torch.empty(sharding.PACK_BYTES * U, dtype=torch.uint8, device=dev) for _ in range(2)]
     outs = [sharding.packed_views(p, U) for p in packs]
     out = outs[0]
-    gather_lists = [[torch.empty_like(packs[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     stats = eng.new_stats()
     pending = [None, None]
     step_no = [0]
+    # ---- N > 1: how the packed outputs reach rank 0 ------------------------------------------------------
+    pg, side, gather_mode, gather_note = None, None, "none", ""
+    if world > 1 and args.gather == "push":
+        ok = torch.ones(1, device=dev)
+        try:
+            pg = sharding.PeerGather(eng, [U] * world, dst=0, n_buffers=2)
+        except Exception as e:                                  # e.g. CUDA IPC not permitted in this container
+            ok.zero_()
+            gather_note = f"push unavailable ({type(e).__name__}: {e}); "
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            if pg is not None:
+                pg.close()
+            pg = None
+        else:
+            gather_mode = "push"
+            side = torch.cuda.Stream(device=dev)
+    if world > 1 and pg is None:
+        gather_mode = "nccl"
+    gather_lists = [[torch.empty_like(packs[0]) for _ in range(world)] for _ in range(2)] \
+        if (gather_mode == "nccl" and rank == 0) else [None, None]
 
     def step(record=None):
-        b = step_no[0] & 1
+        s_no = step_no[0]
+        b = s_no & 1
         step_no[0] += 1
         if pending[b] is not None:
             pending[b].wait()              # stream-side wait: the buffer's previous gather must be done
         if record is not None:
             record[0].record()
         # ONE kernel: likelihood gate + float4 SoA staging (in shared memory) + exclusion search
-        eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc, out=outs[b])
+        if gather_mode == "push":
+            # ... whose stores land in rank 0's gather buffer (NVLink), followed by the arrival flag
+            eng.triangulate_planes_push(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc, **pg.push_args(s_no))
+            if rank == 0:
+                pg.collect(s_no, stream=side.cuda_stream)       # device-side wait for all ranks + buffer release
+        else:
+            eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc, out=outs[b])
         if record is not None:
             record[1].record()
-        if world > 1:
+        if gather_mode == "nccl":
             pending[b] = dist.gather(packs[b], gather_lists[b], dst=0, async_op=True)
         return pending[b]
 
@@ -314,6 +344,8 @@ def main():
     for w in works:
         if w is not None:
             w.wait()
+    if side is not None and rank == 0:
+        torch.cuda.current_stream().wait_stream(side)   # every rank's last step has arrived in rank 0's buffer
     e_end.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -321,6 +353,23 @@ def main():
     launches = eng.launch_count() - launches0
     dev_ms = e_begin.elapsed_time(e_end)
     tri_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    peer_err = 0
+    if pg is not None:
+        # the gathered bytes must be the results: compare rank 0's own slot and one peer slot with a plain launch
+        chk = eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], thr, mc)
+        torch.cuda.synchronize()
+        if rank == 0:
+            mine = pg.views((step_no[0] - 1) & 1)[0]
+            for k in ("Q", "err", "mask", "nexcl"):
+                same = torch.equal(torch.nan_to_num(mine[k].double()), torch.nan_to_num(chk[k].double()))
+                if not same:
+                    raise SystemExit(f"push gather: rank 0's slot differs from a plain launch in {k}")
+        peer_err = eng.peer_error()
+        pe = torch.tensor([peer_err], device=dev)
+        dist.all_reduce(pe, op=dist.ReduceOp.MAX)
+        peer_err = int(pe.item())
+        if peer_err:
+            raise SystemExit(f"push gather: flag wait timed out (bits {peer_err}) — the measurement is void")
 
     # ---- e2e: host buffers through the C ABI (H2D + stage + search + D2H inside the timed region) -----
     ho = {"Q": torch.empty((U, 3), dtype=torch.float64).pin_memory().numpy(),
@@ -368,7 +417,11 @@ def main():
                        "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
                        "seed": cfg["seed"], "l2": f"inputs {(12 * C * U) >> 20} MiB + outputs {(37 * U) >> 20} MiB per step > 126 MB L2, no flush",
                        "step": "one kernel (likelihood gate + float4 SoA staging in shared memory + exclusion search)"
-                               + (" + NCCL gather to rank 0" if world > 1 else ""),
+                               + ("" if world == 1 else
+                                  " whose stores land in rank 0's memory over NVLink (peer-mapped gather buffer, arrival / "
+                                  "release flags, no collective)" if gather_mode == "push" else
+                                  " + NCCL gather to rank 0"),
+                       "gather": gather_note + gather_mode,
                        "level_hist": st["level_hist"], "candidates_per_unit": st["candidates"] / U,
                        "failed_units": st["failed"], "eps_band_px": 1e-6,
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
@@ -406,6 +459,9 @@ def main():
                                                "what": "plain-C restatement (oracle/p2s_oracle.c), OpenMP"}}
         print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
+        dist.barrier()
+        if pg is not None:
+            pg.close()
         dist.destroy_process_group()
 
 

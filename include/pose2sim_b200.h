@@ -39,6 +39,8 @@ extern "C" {
 
 #define P2S_MAX_CAMS 32          /* one uint32 exclusion mask per unit */
 #define P2S_MAX_PERSONS 16       /* persons per camera in the association search */
+#define P2S_MAX_PEERS 16         /* GPUs of one node that can push into one consumer */
+#define P2S_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 #define P2S_MAX_DETECTIONS 64    /* detections per frame (all cameras together) in the multi-person matching */
 
 enum {
@@ -210,6 +212,39 @@ int p2s_associate_multi_host(p2s_handle *h, const float *obs, const int32_t *cou
                              long long n_frames, int n_cams, int max_persons, int n_joints, int n_max,
                              double reconstruction_error_threshold, double min_affinity,
                              int8_t *out_rows, double *out_affinity, int32_t *out_iters);
+
+/* ---- multi-GPU: the final gather fused into the search kernel (one node, NVLink / NVSwitch) ---- *
+ * Units shard over GPUs without any data-path exchange (triangulation.py:831-845 keeps no cross-unit state);
+ * the only exchange is the gather of the 37 bytes per unit to the rank that writes the TRC.  Instead of a
+ * collective after the kernel, the producer's kernel stores its outputs straight into the CONSUMER's memory
+ * (peer mapping, full 16-byte vectors per 32-unit tile) while it computes, and its last CTA raises an arrival
+ * flag there; the consumer releases a buffer for reuse by writing an acknowledgement flag back.
+ *
+ * p2s_peer_alloc   : device buffer that other processes of this node can map; `handle` is what they need
+ *                    (exchange it with any host-side channel, e.g. torch.distributed / MPI / a pipe)
+ * p2s_peer_open    : map a buffer exported by another process (peer access is enabled on demand)
+ * p2s_peer_close / p2s_peer_free : undo the above
+ * p2s_triangulate_planes_push_device : p2s_triangulate_planes_device whose out_* may point into a mapped peer
+ *                    buffer; before the first store the kernel waits until *wait_flag >= wait_value (LOCAL flag,
+ *                    NULL = no wait; wrap-around safe); after the last store it sets *done_flag = done_value
+ *                    (local or peer flag, NULL = none) with system-scope release ordering
+ * p2s_peer_collect_device : consumer side, one tiny kernel on `stream`: waits until arrive[i] >= value for all
+ *                    i < n (LOCAL flags), then writes `value` to every non-NULL ack[i] (local or peer flags)
+ * p2s_peer_error   : bit 0: a producer's wait timed out (2 s), bit 1: the consumer's; cleared by the call      */
+int p2s_peer_alloc(p2s_handle *h, size_t bytes, void **dptr, unsigned char handle[P2S_IPC_HANDLE_BYTES]);
+int p2s_peer_open(p2s_handle *h, const unsigned char handle[P2S_IPC_HANDLE_BYTES], void **dptr);
+int p2s_peer_close(p2s_handle *h, void *dptr);
+int p2s_peer_free(p2s_handle *h, void *dptr);
+int p2s_triangulate_planes_push_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                       const double *P, long long n_units, int n_cams, double lik_thr,
+                                       double reproj_thr, int min_cams,
+                                       double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                       unsigned long long *stats,
+                                       const unsigned int *wait_flag, unsigned int wait_value,
+                                       unsigned int *done_flag, unsigned int done_value, void *stream);
+int p2s_peer_collect_device(p2s_handle *h, const unsigned int *arrive, int n, unsigned int value,
+                            unsigned int *const *ack, void *stream);
+int p2s_peer_error(p2s_handle *h, unsigned int *bits);
 
 /* ---- host staging: OpenPose JSON -> observation planes (no GPU involved) --------------------- *
  * Replaces the file handling of triangulation.py:607-653 extract_files_frame_f (+ :77-90

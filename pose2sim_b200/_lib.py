@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("P2S_LIB") or os.path.join(_HERE, "libp2s_b200.so")
 P2S_MAX_CAMS = 32
 P2S_MAX_PERSONS = 16
 P2S_MAX_DETECTIONS = 64
+P2S_MAX_PEERS = 16
+P2S_IPC_HANDLE_BYTES = 64
 P2S_STAT_COUNT = 48
 STAT_LEVEL0 = 0
 STAT_NOT_EVALUATED = 33
@@ -72,6 +74,14 @@ SIGNATURES = {
     "p2s_associate_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "p2s_associate_multi_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
     "p2s_associate_multi_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
+    "p2s_peer_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp), _vp]),
+    "p2s_peer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "p2s_peer_close": (_i, [_vp, _vp]),
+    "p2s_peer_free": (_i, [_vp, _vp]),
+    "p2s_triangulate_planes_push_device": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp,
+                                                _vp, C.c_uint, _vp, C.c_uint, _vp]),
+    "p2s_peer_collect_device": (_i, [_vp, _vp, _i, C.c_uint, _vp, _vp]),
+    "p2s_peer_error": (_i, [_vp, C.POINTER(C.c_uint)]),
     "p2s_read_pose_files": (_i, [_vp, _ll, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "p2s_write_trc_rows": (_i, [C.c_char_p, _vp, _vp, _vp, _ll, _i]),
     "p2s_measure_fp64_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),

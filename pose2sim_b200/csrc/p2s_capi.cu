@@ -53,7 +53,7 @@ struct p2s_handle {
 
 namespace {
 
-constexpr int kCounterRing = 256;
+constexpr int kCounterRing = 256;                 // pairs {tile dispenser, CTAs finished}; one extra word = error bits
 
 int cuda_fail(p2s_handle *h, cudaError_t e, const char *what) {
     char buf[512];
@@ -117,10 +117,19 @@ int build_table(p2s_handle *h, int n) {
 }
 
 unsigned int *next_counter(p2s_handle *h) {
-    unsigned int *c = h->d_counters + h->counter_next;
+    unsigned int *c = h->d_counters + 2 * h->counter_next;
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     return c;
 }
+
+unsigned int *error_word(p2s_handle *h) { return h->d_counters + 2 * kCounterRing; }
+
+struct PushFlags {
+    const unsigned int *wait_flag = nullptr;
+    unsigned int wait_value = 0;
+    unsigned int *done_flag = nullptr;
+    unsigned int done_value = 0;
+};
 
 int check_tri_args(int n_cams, int min_cams, long long n_units) {
     if (n_cams < 2 || n_cams > P2S_MAX_CAMS) return P2S_EINVAL;
@@ -136,7 +145,8 @@ struct Planes {                                    // raw-plane input of the fus
 
 int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
                         double thr, int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask,
-                        unsigned long long *stats, cudaStream_t stream, const Planes *planes = nullptr) {
+                        unsigned long long *stats, cudaStream_t stream, const Planes *planes = nullptr,
+                        const PushFlags *push = nullptr) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_units == 0) return P2S_OK;
@@ -152,7 +162,9 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     L.out_Q = Q; L.out_err = err; L.out_nexcl = nexcl; L.out_mask = mask; L.stats = stats;
     L.tile_counter = next_counter(h);
     L.stream = stream;
-    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
+    L.err_word = error_word(h);
+    if (push) { L.wait_flag = push->wait_flag; L.wait_value = push->wait_value; L.done_flag = push->done_flag; L.done_value = push->done_value; }
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 2 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
     h->launches += 1;
     return P2S_OK;
@@ -217,7 +229,8 @@ int p2s_create(int device, p2s_handle **out) {
     }
     for (int i = 0; i < kSlots; ++i)
         if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return P2S_ECUDA; }
-    if (cudaMalloc((void **)&h->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc((void **)&h->d_counters, (2 * kCounterRing + 2) * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(h->d_counters, 0, (2 * kCounterRing + 2) * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc((void **)&h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
         return P2S_ENOMEM;
@@ -339,6 +352,93 @@ int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y,
     pl.x = x; pl.y = y; pl.lik = lik; pl.lik_thr = lik_thr;
     return enqueue_triangulate(h, nullptr, P, nullptr, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
                                out_mask, stats, (cudaStream_t)stream, &pl);
+}
+
+int p2s_triangulate_planes_push_device(p2s_handle *h, const float *x, const float *y, const float *lik,
+                                       const double *P, long long n_units, int n_cams, double lik_thr,
+                                       double reproj_thr, int min_cams,
+                                       double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                       unsigned long long *stats,
+                                       const unsigned int *wait_flag, unsigned int wait_value,
+                                       unsigned int *done_flag, unsigned int done_value, void *stream) {
+    if (!h || !P || (n_units > 0 && (!x || !y || !lik || !out_Q || !out_err || !out_nexcl || !out_mask))) return P2S_EINVAL;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)lik) & 15u) return P2S_EINVAL;
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    if (n_units == 0) {                                         // nothing to compute: still hand the flag on
+        if (done_flag) {                                        // error_word + 1 is a word that stays 0
+            P2S_CUDA(h, p2s::launch_collect(wait_flag ? wait_flag : error_word(h) + 1, &done_flag, 1, wait_flag ? wait_value : 0,
+                                            done_value, error_word(h), (cudaStream_t)stream));
+            h->launches += 1;
+        }
+        return P2S_OK;
+    }
+    Planes pl;
+    pl.x = x; pl.y = y; pl.lik = lik; pl.lik_thr = lik_thr;
+    PushFlags pf;
+    pf.wait_flag = wait_flag; pf.wait_value = wait_value; pf.done_flag = done_flag; pf.done_value = done_value;
+    return enqueue_triangulate(h, nullptr, P, nullptr, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
+                               out_mask, stats, (cudaStream_t)stream, &pl, &pf);
+}
+
+int p2s_peer_alloc(p2s_handle *h, size_t bytes, void **dptr, unsigned char handle[P2S_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == P2S_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!h || !dptr || !handle || bytes == 0) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cuda_fail(h, e, "cudaMalloc"); return P2S_ENOMEM; }
+    cudaIpcMemHandle_t ih;
+    e = cudaIpcGetMemHandle(&ih, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(h, e, "cudaIpcGetMemHandle"); }
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(h, e, "cudaMemset"); }
+    std::memcpy(handle, &ih, sizeof ih);
+    *dptr = p;
+    return P2S_OK;
+}
+
+int p2s_peer_open(p2s_handle *h, const unsigned char handle[P2S_IPC_HANDLE_BYTES], void **dptr) {
+    if (!h || !dptr || !handle) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, handle, sizeof ih);
+    void *p = nullptr;
+    P2S_CUDA(h, cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = p;
+    return P2S_OK;
+}
+
+int p2s_peer_close(p2s_handle *h, void *dptr) {
+    if (!h || !dptr) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, cudaIpcCloseMemHandle(dptr));
+    return P2S_OK;
+}
+
+int p2s_peer_free(p2s_handle *h, void *dptr) {
+    if (!h || !dptr) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, cudaFree(dptr));
+    return P2S_OK;
+}
+
+int p2s_peer_collect_device(p2s_handle *h, const unsigned int *arrive, int n, unsigned int value,
+                            unsigned int *const *ack, void *stream) {
+    if (!h || !arrive || n < 1 || n > P2S_MAX_PEERS) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, p2s::launch_collect(arrive, ack, n, value, value, error_word(h), (cudaStream_t)stream));
+    h->launches += 1;
+    return P2S_OK;
+}
+
+int p2s_peer_error(p2s_handle *h, unsigned int *bits) {
+    if (!h || !bits) return P2S_EINVAL;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, cudaMemcpy(bits, error_word(h), sizeof *bits, cudaMemcpyDeviceToHost));
+    P2S_CUDA(h, cudaMemset(error_word(h), 0, sizeof(unsigned int)));
+    return P2S_OK;
 }
 
 int p2s_triangulate_distorted_device(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens,

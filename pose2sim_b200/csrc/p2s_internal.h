@@ -23,7 +23,12 @@ struct TriLaunch {
     uint8_t *out_nexcl;
     uint32_t *out_mask;
     unsigned long long *stats;    // device or null
-    unsigned int *tile_counter;   // device, zeroed on the same stream before the launch
+    unsigned int *tile_counter;   // device, two words, zeroed on the same stream before the launch
+    const unsigned int *wait_flag = nullptr;   // push path (see TriArgs)
+    unsigned int wait_value = 0;
+    unsigned int *done_flag = nullptr;
+    unsigned int done_value = 0;
+    unsigned int *err_word = nullptr;
     cudaStream_t stream;
 };
 
@@ -66,6 +71,8 @@ cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out);
 size_t mp_smem_bytes(int n_max, int n_joints);
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
                          double lik_thr, const p2s_camera_model *lens, void *out, int sm_count, cudaStream_t stream);
+cudaError_t launch_collect(const unsigned int *arrive, unsigned int *const *ack, int n, unsigned int value,
+                           unsigned int ack_value, unsigned int *err_word, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_associate(const AssocLaunch &L, int *grid_out);
 

@@ -50,8 +50,21 @@ struct TriArgs {
     uint8_t *out_nexcl;
     uint32_t *out_mask;
     unsigned long long *stats;
-    unsigned int *tile_counter;
+    unsigned int *tile_counter;   // [0] tile dispenser, [1] CTAs finished (both zeroed before the launch)
+    int vec_out;                  // output planes 16-byte aligned: full tiles are written as 16-byte vectors
+    // multi-GPU push (outputs may live in a PEER's memory, p2s_triangulate_planes_push_device):
+    const unsigned int *wait_flag;   // local: no output is written before *wait_flag >= wait_value (back-pressure)
+    unsigned int wait_value;
+    unsigned int *done_flag;         // local or peer: set to done_value once every output of the launch is visible
+    unsigned int done_value;
+    unsigned int *err_word;          // local: bit 0 set when the wait timed out
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 #ifndef P2S_TRI_MIN_BLOCKS
 #define P2S_TRI_MIN_BLOCKS 4        /* 4 vs 5 resident CTAs per SM measured equal (tools/kernel_ab.py); 4 has no spills */
@@ -62,7 +75,8 @@ struct WarpSlab {                 // per-warp shared memory
     float4 obs[CMAX][32];         // staged observations of the tile
     double blk[32 * 10 + 32];     // camera blocks of the current group pass: block (group, camera) at
                                   // group * (10 C + 2) + 10 camera (the +2 staggers the groups over the banks)
-    double mall[16][10];          // per group: sum of the unit's valid camera blocks
+    double m0[10][32];            // level 0's normal matrix of every unit of the tile (entry-major): the sum over the
+                                  // unit's valid cameras, from which levels >= 1 subtract the excluded blocks
     double r_err[32];             // level results published by the winning lane of each unit
     double r_qx[32], r_qy[32], r_qz[32];
     unsigned long long st64[8];   // per-warp statistics: candidates, camera-solves, solver steps, solved,
@@ -94,9 +108,15 @@ __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX>
 // Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded
 // ones are dropped by a select: no branch, full instruction-level parallelism across cameras).
 // min over the aligned group of W = 2^k lanes this lane belongs to (all 32 lanes take part)
-__device__ __forceinline__ uint32_t group_min(uint32_t v, int W) {
+// P2S_SHFL_ARGMIN (A/B switch): xor-shuffle butterfly; default: ONE redux.sync over the group's member mask
+// (every group of the warp executes the same instruction with its own mask, like a cooperative-groups tile).
+__device__ __forceinline__ uint32_t group_min(uint32_t v, int W, uint32_t gmask) {
+#ifdef P2S_SHFL_ARGMIN
     for (int off = W >> 1; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(P2S_FULL, v, off));
     return v;
+#else
+    return __reduce_min_sync(gmask, v);
+#endif
 }
 
 template <int CMAX, bool DISTORT>
@@ -117,7 +137,9 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 
 // DISTORT: `undistort_points = true` — observations were undistorted by the stage kernel, P is built on
 // the optimal new camera matrix, and the error is measured against the distorted re-projection.
-template <int CMAX, int SOLVER, bool DISTORT>
+// EXACT: n_cams == CMAX, so the camera count is a compile-time constant (index arithmetic of the tile transposition
+// and the camera loops fold).
+template <int CMAX, int SOLVER, bool DISTORT, bool EXACT>
 __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams,
                                                                                const LensSet<DISTORT ? CMAX : 1> lens,
                                                                                const TriArgs a) {
@@ -127,7 +149,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
     double *sP = reinterpret_cast<double *>(smem_raw);                 // projection matrices for dynamic camera index
     WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
 
-    const int C = a.n_cams;
+    const int C = EXACT ? CMAX : a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
     const uint32_t lt_mask = (1u << lane) - 1u;
     const long long n_tiles = (a.n_units + 31) >> 5;
@@ -135,6 +157,17 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
     if (lane < 8) S.st64[lane] = 0ULL;
     if (lane < 12) S.st32[lane] = 0u;
+    if (a.wait_flag != nullptr && threadIdx.x == 0) {
+        // back-pressure of the push path: the consumer has released this output buffer once the flag reaches
+        // wait_value.  Bounded (2 s): a lost peer must not hang the GPU; the time-out is reported, not hidden.
+        const volatile unsigned int *wf = a.wait_flag;
+        const unsigned long long t0 = global_ns();
+        while ((int)(*wf - a.wait_value) < 0) {
+            __nanosleep(200);
+            if (global_ns() - t0 > 2000000000ULL) { atomicOr(a.err_word, 1u); break; }
+        }
+        __threadfence_system();
+    }
     __syncthreads();
 
     for (;;) {
@@ -233,6 +266,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             const int W = 1 << lw;
             const int G = 32 >> lw;
             const int grp = lane >> lw, sub = lane & (W - 1);
+            const uint32_t gmask = (W >= 32) ? P2S_FULL : (((1u << W) - 1u) << (grp << lw));   // lanes of my group
             const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
             const bool blocks = k > 0;                       // then W >= C: one lane per camera for the block pass
             double *gblk = S.blk + grp * (C * 10 + 2);
@@ -246,8 +280,8 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                 const uint32_t u_nan0 = S.nan0[ul], u_inv0 = S.inv0[ul];
 
                 if (blocks) {
-                    // camera-parallel: lane `sub` builds the block of camera `sub` of its group's unit,
-                    // then the group's M_all (fixed ascending camera order => identical for every candidate)
+                    // camera-parallel: lane `sub` builds the block of camera `sub` of its group's unit (the sum of the
+                    // valid blocks, M_all, is level 0's normal matrix, kept in S.m0)
                     __syncwarp();
                     if (on && sub < C) {
                         float4 o = S.obs[sub][ul];
@@ -261,16 +295,8 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                         for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
                     }
                     __syncwarp();
-                    if (on) {
-                        for (int e = sub; e < 10; e += W) {
-                            double s = 0.0;
-                            for (int c = 0; c < C; ++c) s += gblk[c * 10 + e];
-                            S.mall[grp][e] = s;
-                            t_adds += (uint32_t)C;
-                        }
-                    }
-                    __syncwarp();
                 }
+
 
                 unsigned long long bkey = P2S_KEY_EMPTY, skey = P2S_KEY_EMPTY;
                 uint32_t bcand = 0xffffffffu, bnan = 0, bexcl = 0;
@@ -291,14 +317,15 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                             if (!blocks) {
                                 accumulate_direct<CMAX>(M, cams, S.obs, ul, valid);
                                 t_direct += (uint32_t)m;
+                                // ul == lane at level 0: conflict-free column of the entry-major array
+                                S.m0[0][ul] = M.m00; S.m0[1][ul] = M.m01; S.m0[2][ul] = M.m02; S.m0[3][ul] = M.m03; S.m0[4][ul] = M.m11;
+                                S.m0[5][ul] = M.m12; S.m0[6][ul] = M.m13; S.m0[7][ul] = M.m22; S.m0[8][ul] = M.m23; S.m0[9][ul] = M.m33;
                             } else {
                                 uint32_t bits;
                                 double sgn;
                                 if (subtract) {
-                                    const double2 *src = reinterpret_cast<const double2 *>(S.mall[grp]);
-                                    const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                                    M.m00 = v0.x; M.m01 = v0.y; M.m02 = v1.x; M.m03 = v1.y; M.m11 = v2.x;
-                                    M.m12 = v2.y; M.m13 = v3.x; M.m22 = v3.y; M.m23 = v4.x; M.m33 = v4.y;
+                                    M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
+                                    M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
                                     bits = cm & ~u_inv0 & cmask;
                                     sgn = -1.0;
                                 } else {
@@ -341,15 +368,15 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                 // hold that high word; ties go to the smallest candidate index (np.nanargmin's first index)
                 if (W > 1) {
                     const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
-                    const uint32_t mh = group_min(hi, W);
-                    const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W);
+                    const uint32_t mh = group_min(hi, W, gmask);
+                    const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
                     const bool is_min = (hi == mh) && (lo == ml);
-                    const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W);
+                    const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);
                     // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
                     const unsigned long long rk = is_min ? skey : bkey;
                     const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
-                    const uint32_t sh = group_min(rh, W);
-                    const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W);
+                    const uint32_t sh = group_min(rh, W, gmask);
+                    const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
                     bkey = ((unsigned long long)mh << 32) | ml;
                     skey = ((unsigned long long)sh << 32) | sl;
                     bcand = mc;
@@ -382,9 +409,30 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
 
         // ---- finalise (:588-602) and write -------------------------------------------------------
         const bool failed = active && (err_min > a.thr);
-        if (active) {
-            double e_out = err_min;
-            if (failed) { e_out = nan64(); qx = qy = qz = nan64(); }
+        double e_out = err_min;
+        if (failed) { e_out = nan64(); qx = qy = qz = nan64(); }
+        if (a.vec_out && (long long)tile * 32 + 32 <= a.n_units) {
+            // full tile: the four output planes are contiguous per tile (768 + 256 + 128 + 32 bytes); stage them in
+            // the warp's scratch and write whole 16-byte vectors — full sectors, which is what keeps NVLink packets
+            // large when the planes live in a peer's memory, and 3 store instructions instead of 6 locally
+            double *stg = S.blk;
+            stg[3 * lane] = qx; stg[3 * lane + 1] = qy; stg[3 * lane + 2] = qz;
+            stg[96 + lane] = e_out;
+            reinterpret_cast<uint32_t *>(stg + 128)[lane] = ids;
+            reinterpret_cast<uint8_t *>(stg + 144)[lane] = (uint8_t)nexcl;
+            __syncwarp();
+            const float4 *src = reinterpret_cast<const float4 *>(stg);
+            float4 *dq = reinterpret_cast<float4 *>(a.out_Q + (long long)tile * 96);
+            float4 *de = reinterpret_cast<float4 *>(a.out_err + (long long)tile * 32);
+            float4 *dm = reinterpret_cast<float4 *>(a.out_mask + (long long)tile * 32);
+            float4 *dn = reinterpret_cast<float4 *>(a.out_nexcl + (long long)tile * 32);
+            dq[lane] = src[lane];
+            if (lane < 16) dq[32 + lane] = src[32 + lane];
+            else de[lane - 16] = src[48 + lane - 16];
+            if (lane < 8) dm[lane] = src[64 + lane];
+            else if (lane < 10) dn[lane - 8] = src[72 + lane - 8];
+            __syncwarp();
+        } else if (active) {
             double *q = a.out_Q + u * 3;
             q[0] = qx; q[1] = qy; q[2] = qz;
             a.out_err[u] = e_out;
@@ -439,6 +487,44 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             if (S.st32[11]) atomicAdd(a.stats + P2S_STAT_BAND_ARGMIN, (unsigned long long)S.st32[11]);
         }
     }
+
+    // ---- push path: publish "every output of this launch is visible" to the consumer (possibly a peer GPU) ------
+    if (a.done_flag != nullptr) {
+        __syncthreads();                                       // the CTA's stores are all issued
+        if (threadIdx.x == 0) {
+            __threadfence_system();                            // ... and ordered before the count at system scope
+            const unsigned int prev = atomicAdd(a.tile_counter + 1, 1u);
+            if (prev == gridDim.x - 1) {                       // last CTA of the launch
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int *>(a.done_flag) = a.done_value;
+            }
+        }
+    }
+}
+
+// Consumer side of the push path (rank 0): wait until every producer's arrival flag reached `value`, then
+// release the buffer by writing `value` to each producer's acknowledgement flag (peer memory).
+struct CollectArgs {
+    const unsigned int *arrive;                 // local [n]
+    unsigned int *ack[P2S_MAX_PEERS];           // local or peer
+    int n;
+    unsigned int value, ack_value;
+    unsigned int *err_word;
+};
+
+__global__ void __launch_bounds__(32) collect_kernel(const CollectArgs a) {
+    const int lane = threadIdx.x;
+    if (lane < a.n) {
+        const volatile unsigned int *f = a.arrive + lane;
+        const unsigned long long t0 = global_ns();
+        while ((int)(*f - a.value) < 0) {
+            __nanosleep(200);
+            if (global_ns() - t0 > 2000000000ULL) { atomicOr(a.err_word, 2u); break; }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (lane < a.n && a.ack[lane] != nullptr) *reinterpret_cast<volatile unsigned int *>(a.ack[lane]) = a.ack_value;
 }
 
 // ---- staging: [U][C] planes -> float4 [C][U] with the likelihood gate (triangulation.py:817-821) ----
@@ -562,6 +648,9 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.max_table_level = L.max_table_level;
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
+    a.vec_out = ((((uintptr_t)L.out_Q | (uintptr_t)L.out_err | (uintptr_t)L.out_nexcl | (uintptr_t)L.out_mask) & 15u) == 0) ? 1 : 0;
+    a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
+    a.err_word = L.err_word;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;
     if (L.lens) {                                             // undistort_points: distorted re-projection
         LensSet<CMAX> lens;
@@ -574,12 +663,13 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
             o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
             for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
         }
-        return launch_persistent(triangulate_kernel<CMAX, 0, true>, smem, L, grid_out, cams, lens, a);
+        return launch_persistent(triangulate_kernel<CMAX, 0, true, false>, smem, L, grid_out, cams, lens, a);
     }
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);
-    if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false>, smem, L, grid_out, cams, none, a);
-    return launch_persistent(triangulate_kernel<CMAX, 1, false>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0 && L.n_cams == CMAX) return launch_persistent(triangulate_kernel<CMAX, 0, false, true>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false, false>, smem, L, grid_out, cams, none, a);
+    return launch_persistent(triangulate_kernel<CMAX, 1, false, false>, smem, L, grid_out, cams, none, a);
 }
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
@@ -617,6 +707,16 @@ cudaError_t launch_stage(const float *x, const float *y, const float *lik, long 
         if (e != cudaSuccess) return e;
         stage_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(x, y, lik, n_units, n_cams, lik_thr, gate, set, (float4 *)out);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_collect(const unsigned int *arrive, unsigned int *const *ack, int n, unsigned int value,
+                           unsigned int ack_value, unsigned int *err_word, cudaStream_t stream) {
+    CollectArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.arrive = arrive; a.n = n; a.value = value; a.ack_value = ack_value; a.err_word = err_word;
+    for (int i = 0; i < n && i < P2S_MAX_PEERS; ++i) a.ack[i] = ack ? ack[i] : nullptr;
+    collect_kernel<<<1, 32, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

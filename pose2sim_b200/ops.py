@@ -290,3 +290,52 @@ class Engine:
         if want_affinity:
             out["affinity"] = aff
         return out
+
+    # ---- multi-GPU push path (include/pose2sim_b200.h "the final gather fused into the search kernel") ------------
+    def peer_alloc(self, nbytes):
+        """Device buffer other processes of this node can map.  Returns (device address, 64-byte handle)."""
+        p = C.c_void_p()
+        hb = (C.c_ubyte * _lib.P2S_IPC_HANDLE_BYTES)()
+        _lib.check(self.h, self.lib.p2s_peer_alloc(self.h, int(nbytes), C.byref(p), C.cast(hb, C.c_void_p)))
+        return int(p.value), bytes(hb)
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        hb = (C.c_ubyte * _lib.P2S_IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        _lib.check(self.h, self.lib.p2s_peer_open(self.h, C.cast(hb, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr):
+        _lib.check(self.h, self.lib.p2s_peer_close(self.h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        _lib.check(self.h, self.lib.p2s_peer_free(self.h, C.c_void_p(ptr)))
+
+    def peer_error(self):
+        bits = C.c_uint()
+        _lib.check(self.h, self.lib.p2s_peer_error(self.h, C.byref(bits)))
+        return int(bits.value)
+
+    def peer_collect(self, arrive_ptr, n, value, ack_ptrs, stream=None):
+        """Consumer side: wait (on the device, on `stream`) until arrive[i] >= value for i < n, then write `value`
+        to every ack pointer (0 = skip)."""
+        arr = (C.c_void_p * n)(*[C.c_void_p(p or None) for p in ack_ptrs])
+        st = self._stream() if stream is None else stream
+        _lib.check(self.h, self.lib.p2s_peer_collect_device(self.h, C.c_void_p(arrive_ptr), int(n), int(value) & 0xffffffff,
+                                                            C.cast(arr, C.c_void_p), st))
+
+    def triangulate_planes_push(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out_ptrs, wait_flag=0, wait_value=0,
+                                done_flag=0, done_value=0, stats=None):
+        """`triangulate_planes` whose outputs are raw device addresses {"Q", "err", "nexcl", "mask"} — typically a
+        slot in the CONSUMER GPU's memory (sharding.PeerGather) — bracketed by the flag protocol of the push path."""
+        torch = _torch()
+        U, Cn = x.shape
+        for t in (x, y, lik):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (U, Cn)
+        Pm = _as_P(P, Cn)
+        thr = float("-inf") if lik_thr is None else float(lik_thr)
+        _lib.check(self.h, self.lib.p2s_triangulate_planes_push_device(
+            self.h, _ptr(x), _ptr(y), _ptr(lik), Pm.ctypes.data, U, Cn, thr, float(reproj_thr), int(min_cams),
+            C.c_void_p(out_ptrs["Q"]), C.c_void_p(out_ptrs["err"]), C.c_void_p(out_ptrs["nexcl"]), C.c_void_p(out_ptrs["mask"]),
+            _ptr(stats), C.c_void_p(wait_flag or None), int(wait_value) & 0xffffffff, C.c_void_p(done_flag or None),
+            int(done_value) & 0xffffffff, self._stream()))

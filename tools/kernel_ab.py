@@ -26,7 +26,7 @@ def build(specs):
         name, _, flags = spec.partition(":")
         flags = flags.split()
         objs = []
-        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu"):
+        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu", "p2s_multiperson.cu"):
             obj = os.path.join(AB, f"{name}_{src[:-3]}.o")
             r = subprocess.run(NVCC + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
             if r.returncode:
@@ -55,18 +55,17 @@ def time_one(workload, steps):
     wl = synth.make_triangulation_workload(cfg["C"], F, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=None)
     eng = ops.get_engine(0)
     x, y, lik = (torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik"))
-    obs = eng.stage_observations(x, y, lik, cfg["lik_thr"])
     stats = eng.new_stats()
-    out = eng.triangulate(obs, wl["P"], cfg["thr"], cfg["min_cams"], stats=stats)
+    out = eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], cfg["thr"], cfg["min_cams"], stats=stats)
     torch.cuda.synchronize()
     st = ops.stats_dict(stats.cpu().numpy())
     for _ in range(5):
-        eng.triangulate(obs, wl["P"], cfg["thr"], cfg["min_cams"], out=out)
+        eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], cfg["thr"], cfg["min_cams"], out=out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(steps):
-        eng.triangulate(obs, wl["P"], cfg["thr"], cfg["min_cams"], out=out)
+        eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], cfg["thr"], cfg["min_cams"], out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
