@@ -260,7 +260,10 @@ def main():
     wl = synth.make_triangulation_workload(C, F, cfg["N"], cfg["K"], seed=cfg["seed"] + 1000 * rank,
                                            lik_thr=None, frame0=rank * F)
     U = wl["x"].shape[0]
-    hx, hy, hl = (torch.from_numpy(wl[k]).pin_memory() for k in ("x", "y", "lik"))
+    # pinned staging buffers are first-touched on the cores NVML calls local to this GPU (matters at N > 1, where
+    # every rank streams 250 MB per step through its own PCIe root); restored before the CPU legs
+    prev_affinity = ops.bind_host_threads_to_gpu(local)
+    hx, hy, hl = (torch.from_numpy(wl[k].copy()).pin_memory() for k in ("x", "y", "lik"))
     x, y, lik = (t.to(dev, non_blocking=True) for t in (hx, hy, hl))
     # per-unit outputs packed contiguously (Q | err | mask | nexcl = 37 B/unit) so that the final
     # gather is ONE NCCL call; two buffers alternate so the gather of step i overlaps step i+1
@@ -388,6 +391,8 @@ def main():
     e2e_s = (time.perf_counter() - t1) / e2e_steps
     sampler.active = False
     sampler.stop_flag = True
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)
 
     # ---- max over ranks --------------------------------------------------------------------------------
     tm = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, tri_ms], dtype=torch.float64, device=dev)
@@ -436,7 +441,8 @@ def main():
                                  "peak_source": hbm_src, "algorithmic_bytes_per_launch": algorithmic_bytes(U, C)}},
             "e2e": {"value": total_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * C * U,
                     "d2h_bytes_per_step": 37 * U, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "p2s_triangulate_host (pinned host buffers, chunked H2D/compute/D2H on 3 streams)"},
+                    "api": "p2s_triangulate_host (pinned host buffers, chunked H2D/compute/D2H on 4 streams)",
+                    "host_threads_bound_to_gpu": prev_affinity is not None},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "wall_ms_per_step": wall_ms / args.steps,

@@ -105,6 +105,10 @@ int p2s_set_band_eps(p2s_handle *h, double eps_px);
  * (the north-star's nominal solver; kept for A/B evidence). */
 int p2s_set_solver(p2s_handle *h, int solver);
 
+/* units per H2D -> search -> D2H pipeline chunk of the *_host entry points (4 chunks in flight);
+ * 0 (default) = automatic, about a quarter of the call's units clamped to [2^16, 2^20] */
+int p2s_set_chunk_units(p2s_handle *h, long long units);
+
 /* association kernel team width: 0 = automatic (a warp per frame when frames are plentiful or small, a
  * 256-thread CTA per frame when the person-combination product is large and frames are few), 1 or 8 to
  * force one of the two (tests, A/B). */

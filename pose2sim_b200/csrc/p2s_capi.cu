@@ -11,8 +11,11 @@
 
 namespace {
 
-constexpr int kSlots = 3;                         // H2D / compute / D2H overlap
-constexpr long long kChunkUnits = 1 << 18;        // units per pipeline chunk
+constexpr int kSlots = 4;                         // H2D / compute / D2H overlap
+constexpr long long kChunkUnitsDefault = 0;       // units per pipeline chunk; 0 = automatic: about four chunks per call,
+                                                  // between 2^16 and 2^20 units (measured, tools/e2e_sweep.py: below ~1e5
+                                                  // units per chunk the host-side cost of the 7 copies + launch per chunk
+                                                  // shows, above it the call is PCIe-bound at ~47 + 18 GB/s)
 constexpr long long kChunkFrames = 1 << 14;       // association frames per chunk
 constexpr unsigned long long kMaxTableEntries = 1ULL << 22;
 
@@ -40,6 +43,7 @@ struct p2s_handle {
     double band_eps = 1e-6;
     int solver = 0;
     int assoc_team = 0;
+    long long chunk_units = kChunkUnitsDefault;
     long long launches = 0;
     int last_grid = 0;
     std::string last_error;
@@ -285,6 +289,12 @@ int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame) {
     return P2S_OK;
 }
 
+int p2s_set_chunk_units(p2s_handle *h, long long units) {
+    if (!h || (units != 0 && (units < 32 || units > (1LL << 26)))) return P2S_EINVAL;
+    h->chunk_units = (units + 31) & ~31LL;            // whole tiles, keeps the chunk's planes 16-byte aligned
+    return P2S_OK;
+}
+
 int p2s_set_solver(p2s_handle *h, int solver) {
     if (!h || (solver != 0 && solver != 1)) return P2S_EINVAL;
     h->solver = solver;
@@ -461,7 +471,9 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
     if (stats) P2S_CUDA(h, cudaMemsetAsync(h->d_stats, 0, P2S_STAT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
     if (stats) P2S_CUDA(h, cudaStreamSynchronize(h->slots[0].stream));
     const size_t C = (size_t)n_cams;
-    long long chunk = std::min<long long>(kChunkUnits, std::max<long long>(n_units, 1));
+    long long chunk = h->chunk_units;
+    if (chunk <= 0) chunk = std::min<long long>(1LL << 20, std::max<long long>(1LL << 16, ((n_units / 4) + 31) & ~31LL));
+    chunk = std::min<long long>(chunk, std::max<long long>(n_units, 1));
     int i = 0;
     for (long long u0 = 0; u0 < n_units; u0 += chunk, ++i) {
         const long long nu = std::min(chunk, n_units - u0);

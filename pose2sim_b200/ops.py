@@ -98,6 +98,9 @@ class Engine:
     def set_assoc_team(self, warps_per_frame):
         _lib.check(self.h, self.lib.p2s_set_assoc_team(self.h, int(warps_per_frame)))
 
+    def set_chunk_units(self, units):
+        _lib.check(self.h, self.lib.p2s_set_chunk_units(self.h, int(units)))
+
     def launch_count(self):
         return int(self.lib.p2s_launch_count(self.h))
 
@@ -339,3 +342,24 @@ class Engine:
             C.c_void_p(out_ptrs["Q"]), C.c_void_p(out_ptrs["err"]), C.c_void_p(out_ptrs["nexcl"]), C.c_void_p(out_ptrs["mask"]),
             _ptr(stats), C.c_void_p(wait_flag or None), int(wait_value) & 0xffffffff, C.c_void_p(done_flag or None),
             int(done_value) & 0xffffffff, self._stream()))
+
+
+def bind_host_threads_to_gpu(device=0):
+    """Pin this process to the CPU cores NVML reports as local to `device` (same NUMA node / PCIe root), so that
+    the pinned staging buffers allocated afterwards are first-touched next to the GPU.  Returns the previous
+    affinity (restore with os.sched_setaffinity(0, prev)) or None when NVML or the call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if not want:
+            return None
+        os.sched_setaffinity(0, want)
+        return prev
+    except Exception:
+        return None
