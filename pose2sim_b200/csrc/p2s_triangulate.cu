@@ -60,6 +60,12 @@ struct TriArgs {
     unsigned int *err_word;          // local: bit 0 set when the wait timed out
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#ifndef P2S_NO_PREFETCH                                        /* A/B switch, tools/kernel_ab.py */
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -170,11 +176,32 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
     }
     __syncthreads();
 
+    // Tile dispenser, two deep: the tile after next is claimed (one atomic, result not touched for a whole tile)
+    // and the next tile's input lines are pulled into L2 while the current tile is searched, so neither the
+    // atomic's round trip nor HBM latency sits on the warp's critical path.
+    unsigned int t1 = 0, t2 = 0;
+    if (lane == 0) { t1 = atomicAdd(a.tile_counter, 1u); t2 = atomicAdd(a.tile_counter, 1u); }
     for (;;) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
-        tile = __shfl_sync(P2S_FULL, tile, 0);
+        const unsigned int tile = __shfl_sync(P2S_FULL, t1, 0);
         if ((long long)tile >= n_tiles) break;
+        t1 = t2;
+        if (lane == 0) t2 = atomicAdd(a.tile_counter, 1u);
+        {
+            const unsigned int nt = __shfl_sync(P2S_FULL, t1, 0);
+            if ((long long)nt < n_tiles) {
+                if (a.px == nullptr) {
+                    for (int i = lane; i < 4 * C; i += 32) {          // 128-byte lines of the C staged rows of the tile
+                        const long long e = (long long)(i >> 2) * a.n_units + (long long)nt * 32 + (i & 3) * 8;
+                        if ((long long)nt * 32 + (i & 3) * 8 < a.n_units) prefetch_l2(a.obs + e);
+                    }
+                } else {
+                    const long long e0n = (long long)nt * 32 * C, e_endn = a.n_units * C;
+                    for (int off = lane * 32; off < 32 * C; off += 1024) {   // 32 floats = one 128-byte line
+                        if (e0n + off < e_endn) { prefetch_l2(a.px + e0n + off); prefetch_l2(a.py + e0n + off); prefetch_l2(a.pl + e0n + off); }
+                    }
+                }
+            }
+        }
 
         const long long u = (long long)tile * 32 + lane;
         const bool active = u < a.n_units;
@@ -366,30 +393,38 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                 // ---- (error, index) arg-min + runner-up across the W lanes of the group (xor butterflies) ----
                 // keys are 64-bit: min of the high words, then min of the low words among the lanes that
                 // hold that high word; ties go to the smallest candidate index (np.nanargmin's first index)
+                bool winner = on && bcand != 0xffffffffu;     // W == 1: the lane's own (only) candidate
+                bool barg = false;
                 if (W > 1) {
                     const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
                     const uint32_t mh = group_min(hi, W, gmask);
-                    const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
-                    const bool is_min = (hi == mh) && (lo == ml);
-                    const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);
-                    // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
-                    const unsigned long long rk = is_min ? skey : bkey;
-                    const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
-                    const uint32_t sh = group_min(rh, W, gmask);
-                    const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
-                    bkey = ((unsigned long long)mh << 32) | ml;
-                    skey = ((unsigned long long)sh << 32) | sl;
-                    bcand = mc;
+                    // Fast path (warp-uniform): in every group exactly one lane holds the minimal HIGH word, so that
+                    // lane is the arg-min — one redux + one ballot.  Otherwise (high words tie: duplicates, all-NaN
+                    // levels, errors closer than 2^-20 relative) or when the eps-band statistics are wanted, the
+                    // full 64-bit (error, index) reduction with the runner-up runs.
+                    const uint32_t holders = __ballot_sync(P2S_FULL, hi == mh) & gmask;
+                    const bool full = (a.stats != nullptr) || (on && __popc(holders) != 1);
+                    if (!__any_sync(P2S_FULL, full)) {
+                        winner = on && (hi == mh);
+                    } else {
+                        const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
+                        const bool is_min = (hi == mh) && (lo == ml);
+                        const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);   // first index wins
+                        // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
+                        const unsigned long long rk = is_min ? skey : bkey;
+                        const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
+                        const uint32_t sh = group_min(rh, W, gmask);
+                        const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
+                        skey = ((unsigned long long)sh << 32) | sl;
+                        // the lane that evaluated candidate mc (sub == mc % W) still holds its Q / masks
+                        winner = on && mc != 0xffffffffu && is_min && bcand == mc;
+                        barg = (key_err(skey) - key_err(bkey)) < a.band_eps;   // NaN / inf compare false
+                    }
                 }
-                // every lane of the group now knows (bkey, bcand); the lane that evaluated bcand
-                // (sub == bcand % W) still holds its Q / masks
-                if (on && bcand != 0xffffffffu && (uint32_t)sub == (bcand & (uint32_t)(W - 1))) {
-                    const double e = key_err(bkey);
-                    S.r_err[ul] = e;
+                if (winner) {
+                    S.r_err[ul] = key_err(bkey);
                     S.r_qx[ul] = bqx; S.r_qy[ul] = bqy; S.r_qz[ul] = bqz;
                     S.r_nan[ul] = bnan;
-                    // runner-up among DISTINCT errors (duplicates of the winner are bitwise equal)
-                    const bool barg = (key_err(skey) - e) < a.band_eps;   // NaN / inf compare false
                     S.r_flags[ul] = bexcl | (barg ? 0x100u : 0u);
                 }
             }
