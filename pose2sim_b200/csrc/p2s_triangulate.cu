@@ -25,6 +25,7 @@
 //     warp shuffles; the winning lane publishes Q / error / masks to the unit's slot in shared
 //     memory;
 //   * projection matrices are a by-value kernel parameter => constant-bank operands.
+#include <cstddef>
 #include <cstring>
 
 #include "p2s_math.cuh"
@@ -66,6 +67,30 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 #endif
 }
 
+// ---- TMA bulk copy global -> shared with a transaction barrier (sm_90+ PTX) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -77,8 +102,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
 #endif
 
 template <int CMAX>
-struct WarpSlab {                 // per-warp shared memory
-    float4 obs[CMAX][32];         // staged observations of the tile
+struct alignas(16) WarpSlab {     // per-warp shared memory
+    // next tile's raw planes x | y | likelihood ([32 units][C] floats each), written by cp.async.bulk (TMA) while the
+    // current tile is searched; only for CMAX <= 8 (3 KB per warp) — wider slabs would cost a resident CTA
+    float raw[(CMAX <= 8) ? 3 * 32 * CMAX : 4];
+    float2 xy[CMAX][32];          // staged observations of the tile: pixel coordinates ...
+    float w[CMAX][32];            // ... and likelihood (NaN = invalid)
+    unsigned long long mbar;      // transaction barrier of the raw buffer
+    unsigned long long pad_;      // keeps blk (read back as 16-byte vectors by the output staging) 16-byte aligned
     double blk[32 * 10 + 32];     // camera blocks of the current group pass: block (group, camera) at
                                   // group * (10 C + 2) + 10 camera (the +2 staggers the groups over the banks)
     double m0[10][32];            // level 0's normal matrix of every unit of the tile (entry-major): the sum over the
@@ -95,19 +126,23 @@ struct WarpSlab {                 // per-warp shared memory
     uint32_t plist[32];           // owner lanes of the units pending at the current level, compacted
 };
 
+static_assert(sizeof(WarpSlab<8>) % 16 == 0 && offsetof(WarpSlab<8>, blk) % 16 == 0 && offsetof(WarpSlab<8>, xy) % 16 == 0, "slab alignment");
+static_assert(sizeof(WarpSlab<32>) % 16 == 0 && offsetof(WarpSlab<32>, blk) % 16 == 0, "slab alignment");
+
 // Weighted-DLT normal matrix of ONE unit accumulated straight from the observations (level 0:
 // thread per unit).  Invalid cameras enter with x = y = w = 0, i.e. exact zeros are added — no
 // branch per camera, so the unrolled cameras interleave in the FP64 pipe.
 template <int CMAX>
-__device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX> &cams, const float4 (*obs)[32],
-                                                  int ul, uint32_t valid) {
+__device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX> &cams, const float2 (*xy)[32],
+                                                  const float (*wt)[32], int ul, uint32_t valid) {
     sym4_zero(M);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        float4 o = obs[c][ul];
+        float2 o = xy[c][ul];
+        float ow = wt[c][ul];
         const bool v = (valid >> c) & 1u;
-        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; o.z = v ? o.z : 0.f;
-        accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)o.z);
+        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
+        accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)ow);
     }
 }
 
@@ -127,12 +162,12 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v, int W, uint32_t gmask)
 
 template <int CMAX, bool DISTORT>
 __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const LensSet<DISTORT ? CMAX : 1> &lens,
-                                                    const float4 (*obs)[32], int ul, uint32_t valid, int m,
+                                                    const float2 (*obs)[32], int ul, uint32_t valid, int m,
                                                     double qx, double qy, double qz) {
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        const float4 o = obs[c][ul];
+        const float2 o = obs[c][ul];
         double dist;
         if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, (double)o.x, (double)o.y);
         else dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
@@ -181,24 +216,49 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
     // atomic's round trip nor HBM latency sits on the warp's critical path.
     unsigned int t1 = 0, t2 = 0;
     if (lane == 0) { t1 = atomicAdd(a.tile_counter, 1u); t2 = atomicAdd(a.tile_counter, 1u); }
+    // TMA staging (raw planes, compile-time camera count <= 8): lane 0 issues three cp.async.bulk copies of the NEXT
+    // tile's 32 C floats per plane into S.raw, completion is counted by the warp's transaction barrier.
+#ifdef P2S_NO_TMA                                              /* A/B switch, tools/kernel_ab.py */
+    const bool tma = false;
+#else
+    const bool tma = EXACT && CMAX <= 8 && a.px != nullptr;
+#endif
+    const uint32_t bar = smem_u32(&S.mbar);
+    uint32_t phase = 0;
+    auto issue_tile = [&](unsigned int t) {                    // lane 0 only
+        const long long e0t = (long long)t * 32 * C;
+        const long long left = a.n_units * C - e0t;
+        const uint32_t bytes = (uint32_t)(left < 32LL * C ? left : 32LL * C) * 4u;      // multiple of 16: C in {4, 8}
+        mbar_expect_tx(bar, 3u * bytes);
+        bulk_g2s(smem_u32(S.raw), a.px + e0t, bytes, bar);
+        bulk_g2s(smem_u32(S.raw + 32 * CMAX), a.py + e0t, bytes, bar);
+        bulk_g2s(smem_u32(S.raw + 64 * CMAX), a.pl + e0t, bytes, bar);
+    };
+    if (tma) {
+        if (lane == 0) {
+            mbar_init(bar, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_proxy_async();
+            if ((long long)t1 < n_tiles) issue_tile(t1);
+        }
+        __syncwarp();
+    }
     for (;;) {
         const unsigned int tile = __shfl_sync(P2S_FULL, t1, 0);
         if ((long long)tile >= n_tiles) break;
         t1 = t2;
         if (lane == 0) t2 = atomicAdd(a.tile_counter, 1u);
-        {
-            const unsigned int nt = __shfl_sync(P2S_FULL, t1, 0);
-            if ((long long)nt < n_tiles) {
-                if (a.px == nullptr) {
-                    for (int i = lane; i < 4 * C; i += 32) {          // 128-byte lines of the C staged rows of the tile
-                        const long long e = (long long)(i >> 2) * a.n_units + (long long)nt * 32 + (i & 3) * 8;
-                        if ((long long)nt * 32 + (i & 3) * 8 < a.n_units) prefetch_l2(a.obs + e);
-                    }
-                } else {
-                    const long long e0n = (long long)nt * 32 * C, e_endn = a.n_units * C;
-                    for (int off = lane * 32; off < 32 * C; off += 1024) {   // 32 floats = one 128-byte line
-                        if (e0n + off < e_endn) { prefetch_l2(a.px + e0n + off); prefetch_l2(a.py + e0n + off); prefetch_l2(a.pl + e0n + off); }
-                    }
+        const unsigned int nt = __shfl_sync(P2S_FULL, t1, 0);   // the tile after this one
+        if (!tma && (long long)nt < n_tiles) {
+            if (a.px == nullptr) {
+                for (int i = lane; i < 4 * C; i += 32) {          // 128-byte lines of the C staged rows of the tile
+                    const long long e = (long long)(i >> 2) * a.n_units + (long long)nt * 32 + (i & 3) * 8;
+                    if ((long long)nt * 32 + (i & 3) * 8 < a.n_units) prefetch_l2(a.obs + e);
+                }
+            } else {
+                const long long e0n = (long long)nt * 32 * C, e_endn = a.n_units * C;
+                for (int off = lane * 32; off < 32 * C; off += 1024) {   // 32 floats = one 128-byte line
+                    if (e0n + off < e_endn) { prefetch_l2(a.px + e0n + off); prefetch_l2(a.py + e0n + off); prefetch_l2(a.pl + e0n + off); }
                 }
             }
         }
@@ -214,7 +274,8 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             for (int c = 0; c < CMAX; ++c) {
                 float4 o = make_float4(0.f, 0.f, __int_as_float(0x7fc00000), 0.f);
                 if (c < C && active) o = __ldg(a.obs + (long long)c * a.n_units + u);
-                S.obs[c][lane] = o;
+                S.xy[c][lane] = make_float2(o.x, o.y);
+                S.w[c][lane] = o.z;
             }
         } else {
             // raw planes x, y, lik [U][C] (what the host hands over): the tile is 32 C contiguous floats per
@@ -224,11 +285,24 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             const long long e_end = a.n_units * C;
             const float nanf_ = __int_as_float(0x7fc00000);
             __syncwarp();
-            for (int c = 0; c < CMAX; ++c) S.obs[c][lane] = make_float4(0.f, 0.f, nanf_, 0.f);
+            for (int c = 0; c < CMAX; ++c) { S.xy[c][lane] = make_float2(0.f, 0.f); S.w[c][lane] = nanf_; }
             __syncwarp();
+            if (tma) mbar_wait(bar, phase);                            // this tile's planes have landed in S.raw
             for (int j = lane * 4; j < 32 * C; j += 128) {
                 float vx[4], vy[4], vl[4];
-                if (e0 + j + 3 < e_end) {
+                if (tma) {
+                    const float4 tx = *reinterpret_cast<const float4 *>(S.raw + j);
+                    const float4 ty = *reinterpret_cast<const float4 *>(S.raw + 32 * CMAX + j);
+                    const float4 tl = *reinterpret_cast<const float4 *>(S.raw + 64 * CMAX + j);
+                    vx[0] = tx.x; vx[1] = tx.y; vx[2] = tx.z; vx[3] = tx.w;
+                    vy[0] = ty.x; vy[1] = ty.y; vy[2] = ty.z; vy[3] = ty.w;
+                    vl[0] = tl.x; vl[1] = tl.y; vl[2] = tl.z; vl[3] = tl.w;
+                    if (e0 + j + 3 >= e_end) {                         // beyond the last unit: stale bytes of an older tile
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (e0 + j + t >= e_end) { vx[t] = 0.f; vy[t] = 0.f; vl[t] = nanf_; }
+                    }
+                } else if (e0 + j + 3 < e_end) {
                     const float4 tx = __ldg(reinterpret_cast<const float4 *>(a.px + e0 + j));
                     const float4 ty = __ldg(reinterpret_cast<const float4 *>(a.py + e0 + j));
                     const float4 tl = __ldg(reinterpret_cast<const float4 *>(a.pl + e0 + j));
@@ -249,14 +323,20 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                     const int uu = (j + t) / C, cc = (j + t) - uu * C;
                     float fx = vx[t], fy = vy[t], fl = vl[t];
                     if (a.gate && (double)fl < a.lik_thr) { fx = fy = fl = nanf_; }
-                    S.obs[cc][uu] = make_float4(fx, fy, fl, 0.f);
+                    S.xy[cc][uu] = make_float2(fx, fy);
+                    S.w[cc][uu] = fl;
                 }
             }
             __syncwarp();
+            if (tma) {
+                // every lane has consumed S.raw: hand the buffer back to the copy engine for the next tile
+                phase ^= 1u;
+                if (lane == 0 && (long long)nt < n_tiles) { fence_proxy_async(); issue_tile(nt); }
+            }
         }
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            const float lz = S.obs[c][lane].z;
+            const float lz = S.w[c][lane];
             const bool isn = lz != lz;
             nan0 |= (uint32_t)isn << c;
             inv0 |= (uint32_t)(isn || lz == 0.f) << c;
@@ -311,11 +391,12 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                     // valid blocks, M_all, is level 0's normal matrix, kept in S.m0)
                     __syncwarp();
                     if (on && sub < C) {
-                        float4 o = S.obs[sub][ul];
+                        float2 o = S.xy[sub][ul];
+                        float ow = S.w[sub][ul];
                         const bool v = !((u_inv0 >> sub) & 1u);
-                        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; o.z = v ? o.z : 0.f;
+                        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
                         double b[10];
-                        camera_block(sP + sub * 12, (double)o.x, (double)o.y, (double)o.z, b);
+                        camera_block(sP + sub * 12, (double)o.x, (double)o.y, (double)ow, b);
                         t_blocks += v ? 1u : 0u;
                         double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
 #pragma unroll
@@ -342,7 +423,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                         } else {
                             Sym4 M;
                             if (!blocks) {
-                                accumulate_direct<CMAX>(M, cams, S.obs, ul, valid);
+                                accumulate_direct<CMAX>(M, cams, S.xy, S.w, ul, valid);
                                 t_direct += (uint32_t)m;
                                 // ul == lane at level 0: conflict-free column of the entry-major array
                                 S.m0[0][ul] = M.m00; S.m0[1][ul] = M.m01; S.m0[2][ul] = M.m02; S.m0[3][ul] = M.m03; S.m0[4][ul] = M.m11;
@@ -375,7 +456,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                             int it;
                             if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.obs, ul, valid, m, cqx, cqy, cqz);
+                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.xy, ul, valid, m, cqx, cqy, cqz);
                             t_iters += (uint32_t)it;
                             t_solved += 1u;
                         }
