@@ -171,7 +171,7 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
         double dist;
         if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, (double)o.x, (double)o.y);
         else dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
-        sum += ((valid >> c) & 1u) ? dist : 0.0;
+        if ((valid >> c) & 1u) sum += dist;                      // predicated DADD, no select
     }
     return div_small(sum, (double)m);
 }
@@ -180,7 +180,9 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 // the optimal new camera matrix, and the error is measured against the distorted re-projection.
 // EXACT: n_cams == CMAX, so the camera count is a compile-time constant (index arithmetic of the tile transposition
 // and the camera loops fold).
-template <int CMAX, int SOLVER, bool DISTORT, bool EXACT>
+// STATS: the statistics block (work counters, level histogram, eps-band counts incl. the arg-min runner-up) is
+// wanted; the lean variant compiles all of that bookkeeping out of the candidate loop.
+template <int CMAX, int SOLVER, bool DISTORT, bool EXACT, bool STATS>
 __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams,
                                                                                const LensSet<DISTORT ? CMAX : 1> lens,
                                                                                const TriArgs a) {
@@ -484,22 +486,24 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                     // levels, errors closer than 2^-20 relative) or when the eps-band statistics are wanted, the
                     // full 64-bit (error, index) reduction with the runner-up runs.
                     const uint32_t holders = __ballot_sync(P2S_FULL, hi == mh) & gmask;
-                    const bool full = (a.stats != nullptr) || (on && __popc(holders) != 1);
+                    const bool full = STATS || (on && __popc(holders) != 1);
                     if (!__any_sync(P2S_FULL, full)) {
                         winner = on && (hi == mh);
                     } else {
                         const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
                         const bool is_min = (hi == mh) && (lo == ml);
                         const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);   // first index wins
-                        // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
-                        const unsigned long long rk = is_min ? skey : bkey;
-                        const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
-                        const uint32_t sh = group_min(rh, W, gmask);
-                        const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
-                        skey = ((unsigned long long)sh << 32) | sl;
-                        // the lane that evaluated candidate mc (sub == mc % W) still holds its Q / masks
+                        // the lane that evaluated candidate mc still holds its Q / masks
                         winner = on && mc != 0xffffffffu && is_min && bcand == mc;
-                        barg = (key_err(skey) - key_err(bkey)) < a.band_eps;   // NaN / inf compare false
+                        if (STATS) {
+                            // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
+                            const unsigned long long rk = is_min ? skey : bkey;
+                            const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
+                            const uint32_t sh = group_min(rh, W, gmask);
+                            const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
+                            skey = ((unsigned long long)sh << 32) | sl;
+                            barg = (key_err(skey) - key_err(bkey)) < a.band_eps;   // NaN / inf compare false
+                        }
                     }
                 }
                 if (winner) {
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             a.out_mask[u] = ids;
         }
         // ---- per-tile statistics: warp-wide counts, lane 0 keeps the warp's totals in shared ----------
-        if (a.stats) {
+        if (STATS && a.stats != nullptr) {
             const uint32_t s_c = __reduce_add_sync(P2S_FULL, t_cands);
             const uint32_t s_m = __reduce_add_sync(P2S_FULL, t_cams);
             const uint32_t s_i = __reduce_add_sync(P2S_FULL, t_iters);
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
     }
 
     // ---- flush statistics: one atomic per counter per warp ---------------------------------------------
-    if (a.stats) {
+    if (STATS && a.stats != nullptr) {
         __syncwarp();
         if (lane < 8 && S.st32[lane]) atomicAdd(a.stats + P2S_STAT_LEVEL0 + lane, (unsigned long long)S.st32[lane]);
         if (lane == 8) {
@@ -779,13 +783,16 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
             o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
             for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
         }
-        return launch_persistent(triangulate_kernel<CMAX, 0, true, false>, smem, L, grid_out, cams, lens, a);
+        return launch_persistent(triangulate_kernel<CMAX, 0, true, false, true>, smem, L, grid_out, cams, lens, a);
     }
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);
-    if (L.solver == 0 && L.n_cams == CMAX) return launch_persistent(triangulate_kernel<CMAX, 0, false, true>, smem, L, grid_out, cams, none, a);
-    if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false, false>, smem, L, grid_out, cams, none, a);
-    return launch_persistent(triangulate_kernel<CMAX, 1, false, false>, smem, L, grid_out, cams, none, a);
+    const bool st = L.stats != nullptr, exact = L.n_cams == CMAX;
+    if (L.solver == 0 && exact && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0 && exact) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0 && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, false>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, true>, smem, L, grid_out, cams, none, a);
+    return launch_persistent(triangulate_kernel<CMAX, 1, false, false, true>, smem, L, grid_out, cams, none, a);
 }
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
