@@ -46,6 +46,8 @@ struct TriArgs {
     const uint32_t *cand_masks;   // lexicographic subset table, level k at level_off[k]
     uint32_t level_off[P2S_MAX_CAMS + 2];
     int max_table_level;          // levels above this are unranked arithmetically
+    uint32_t ncand[P2S_MAX_CAMS + 1];       // candidates of level k: C(n_cams, k) (saturating)
+    unsigned char lw[P2S_MAX_CAMS + 1];     // log2 of the lanes per unit at level k: W = min(32, pow2 >= ncand)
     double *out_Q;
     double *out_err;
     uint8_t *out_nexcl;
@@ -163,14 +165,18 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v, int W, uint32_t gmask)
 template <int CMAX, bool DISTORT>
 __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const LensSet<DISTORT ? CMAX : 1> &lens,
                                                     const float2 (*obs)[32], int ul, uint32_t valid, int m,
-                                                    double qx, double qy, double qz) {
+                                                    double qx, double qy, double qz, const double *sP) {
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
         const float2 o = obs[c][ul];
         double dist;
         if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, (double)o.x, (double)o.y);
+#ifdef P2S_SMEM_P                                              /* A/B switch: projection rows from shared memory */
+        else dist = reproj_distance(sP + c * 12, qx, qy, qz, (double)o.x, (double)o.y);
+#else
         else dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
+#endif
         if ((valid >> c) & 1u) sum += dist;                      // predicated DADD, no select
     }
     return div_small(sum, (double)m);
@@ -369,9 +375,8 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
             if (pmask == 0) break;
             const int npend = __popc(pmask);
             if (pend) S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
-            const uint32_t ncand = (k == 0) ? 1u : (k <= a.max_table_level) ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
-            int lw = 5;                                      // W = 2^lw lanes per unit
-            if (ncand <= 16) { lw = 0; while ((1u << lw) < ncand) ++lw; }
+            const uint32_t ncand = a.ncand[k];
+            const int lw = a.lw[k];                          // W = 2^lw lanes per unit (host table)
             const int W = 1 << lw;
             const int G = 32 >> lw;
             const int grp = lane >> lw, sub = lane & (W - 1);
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
                             int it;
                             if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.xy, ul, valid, m, cqx, cqy, cqz);
+                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.xy, ul, valid, m, cqx, cqy, cqz, sP);
                             t_iters += (uint32_t)it;
                             t_solved += 1u;
                         }
@@ -766,6 +771,17 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.thr = L.thr; a.band_eps = L.band_eps; a.cand_masks = L.cand_masks;
     for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
     a.max_table_level = L.max_table_level;
+    for (int k = 0; k <= P2S_MAX_CAMS; ++k) {
+        unsigned long long r = (k <= L.n_cams) ? 1ULL : 0ULL;
+        for (int i = 1; i <= k && k <= L.n_cams; ++i) {
+            r = r * (unsigned)(L.n_cams - k + i) / (unsigned)i;
+            if (r > 0xffffffffULL) { r = 0xffffffffULL; break; }
+        }
+        a.ncand[k] = (uint32_t)r;
+        int lw = 5;
+        if (r <= 16) { lw = 0; while ((1ULL << lw) < r) ++lw; }
+        a.lw[k] = (unsigned char)lw;
+    }
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
     a.vec_out = ((((uintptr_t)L.out_Q | (uintptr_t)L.out_err | (uintptr_t)L.out_nexcl | (uintptr_t)L.out_mask) & 15u) == 0) ? 1 : 0;
