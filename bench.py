@@ -55,10 +55,10 @@ def algorithmic_flops(st):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 72.7 MB written on cfg2
+# `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 71.8 MB written on cfg2
 # (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
-NCU_TRAFFIC = {("cfg2", 1): 322.3e6}
-NCU_TRAFFIC_SOURCE = "profiles/r1h_triangulate_fused_ncu_full.csv"
+NCU_TRAFFIC = {("cfg2", 1): 321.5e6}
+NCU_TRAFFIC_SOURCE = "profiles/r1n_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
@@ -421,7 +421,7 @@ def main():
                        "units_per_gpu": U, "reproj_error_threshold_triangulation": thr,
                        "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
                        "seed": cfg["seed"], "l2": f"inputs {(12 * C * U) >> 20} MiB + outputs {(37 * U) >> 20} MiB per step > 126 MB L2, no flush",
-                       "step": "one kernel (likelihood gate + float4 SoA staging in shared memory + exclusion search)"
+                       "step": "one kernel (TMA-staged raw planes, likelihood gate + SoA transposition in shared memory, exclusion search)"
                                + ("" if world == 1 else
                                   " whose stores land in rank 0's memory over NVLink (peer-mapped gather buffer, arrival / "
                                   "release flags, no collective)" if gather_mode == "push" else
@@ -432,7 +432,7 @@ def main():
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
             "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                          "traffic": NCU_TRAFFIC.get((args.workload, world)), "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "kernel": f"triangulate_kernel<{4 if C <= 4 else 8 if C <= 8 else 16 if C <= 16 else 32},secular>",
+                         "kernel": f"triangulate_kernel<{4 if C <= 4 else 8 if C <= 8 else 16 if C <= 16 else 32},secular,exact,lean>",
                          "grid_ctas": eng.last_grid(),
                          "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "dependent-chain DFMA microbenchmark in this run (p2s_measure_fp64_peak); "
