@@ -2,7 +2,7 @@
 """Association-search benchmark (BASELINE.json configs[3]: Demo_MultiPerson-shaped synthetic, 8 cameras x
 6 persons per camera => 6^8 = 1 679 616 person combinations per frame, single-person search mode).
 
-    python tools/assoc_bench.py [frames] [persons] [cams]
+    python tests/perf/assoc_bench.py [frames] [persons] [cams]
 
 Prints one JSON line (also appended to gpurun_out/assoc_bench.jsonl): frames/s, combination rows/s and
 candidate solves/s of `associate_kernel` with the inputs resident in HBM, the same through
@@ -15,7 +15,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 

@@ -4,7 +4,7 @@ layout (JSON directories in, TRC out) — BASELINE.json configs[0] shape (4 ship
 frames x HALPE_26) and a larger 8-camera trial.  Phases: host staging (native JSON reader), device call,
 host post-processing + TRC writer.
 
-    python tools/dropin_bench.py [--reference]     # --reference: time the UNMODIFIED reference instead
+    python tests/perf/dropin_bench.py [--reference]     # --reference: time the UNMODIFIED reference instead
                                                    #   (build container only; needs /root/reference)
 Lines go to stdout and gpurun_out/dropin_bench.jsonl."""
 import json
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 

@@ -2,7 +2,7 @@
 """Multi-person matching benchmark (BASELINE.json configs[3] in `multi_person = true` mode: 8 cameras x 6
 persons per camera => 48 detections per frame, ray affinity + matchSVT + arg-max rows per frame).
 
-    python tools/mp_bench.py [frames] [persons] [cams]
+    python tests/perf/mp_bench.py [frames] [persons] [cams]
 
 Prints one JSON line (also appended to gpurun_out/mp_bench.jsonl): frames/s of `mp_associate_kernel` with
 the inputs resident in HBM, the same through `p2s_associate_multi_host`, the NumPy restatement's frames/s on
@@ -15,7 +15,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
