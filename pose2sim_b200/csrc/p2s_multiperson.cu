@@ -14,8 +14,9 @@
 // and min-cameras filters) stays on the host: it is a few integer rows per frame.
 //
 // The SVD of the symmetric N x N matrix (N = detections in the frame, <= 64) is a one-sided Jacobi
-// (Hestenes) in shared memory, FP64: round-robin pairing gives N/2 disjoint column pairs per round, four
-// lanes per pair split the rows, three dot products by xor-shuffles, the rotation applied to A and V.
+// (Hestenes) in shared memory, FP64: round-robin pairing gives N/2 disjoint column pairs per round, one
+// half-warp per pair (16 consecutive rows per access), three dot products by xor-shuffles, the rotation
+// applied to A and V; every ADMM step after the first warm-starts from the previous step's V.
 // U S V^T with S shrunk by tau is then sum_k max(s_k - tau, 0)/s_k a_k v_k^T — only the few columns above
 // tau (about one per person) contribute.
 #include <cmath>
@@ -43,7 +44,8 @@ struct MpArgs {
     unsigned int *tile_counter;
 };
 
-constexpr int kMpThreads = 128;
+constexpr int kMpThreads = 512;
+constexpr int kMpWarps = kMpThreads / 32;
 
 __device__ __forceinline__ double block_sum(double v, double *red) {
 #pragma unroll
@@ -51,7 +53,10 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return red[0] + red[1] + red[2] + red[3];
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMpWarps; ++w) s += red[w];                 // same order in every thread
+    return s;
 }
 
 // Plücker coordinates of the camera->keypoint ray (personAssociation.py:301-315): unit direction, moment
@@ -85,8 +90,8 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
     double *V = A + (size_t)NM * LD;
     double *Qp = V + (size_t)NM * LD;
     double *sig = Qp + (size_t)NM * LD;                                // NM shrink factors
-    double *red = sig + NM;                                            // 4
-    float *sobs = reinterpret_cast<float *>(red + 4);                  // [N][3 J]
+    double *red = sig + NM;                                            // one per warp
+    float *sobs = reinterpret_cast<float *>(red + kMpWarps);           // [N][3 J]
     int *s_view = reinterpret_cast<int *>(sobs + (size_t)NM * 3 * J);  // NM: view of each detection
     int *s_cum = s_view + NM;                                          // C + 1
     int *s_flag = s_cum + P2S_MAX_CAMS + 1;                            // [0] frame, [1] rotations in the sweep
@@ -159,18 +164,56 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
         int iters = 0;
         for (int it = 0; it < a.max_iter && N > 0; ++it) {
             iters = it + 1;
-            // ---- A = X + Y / mu (symmetric), V = I ------------------------------------------------------------
+            // ---- B = X + Y / mu (symmetric), held in Qp until the shrinkage overwrites it ------------------------
+            // First step: A = B, V = I.  Later steps WARM-START the Jacobi SVD from the previous step's V:
+            // A = B V_prev has nearly orthogonal columns already (B moves little between ADMM steps), so one or
+            // two sweeps finish where a cold start needs eight to ten.  B = (B V) V^T, so the SVD is the same.
             for (int e = tid; e < N * N; e += kMpThreads) {
                 const int i = e / N, j = e - i * N;
-                A[j * LD + i] = X[i * LD + j] + Y[i * LD + j] * 1.0 / mu;
-                V[j * LD + i] = (i == j) ? 1.0 : 0.0;
+                const double b = X[i * LD + j] + Y[i * LD + j] * 1.0 / mu;
+                Qp[i * LD + j] = b;
+                if (it == 0) {
+                    A[j * LD + i] = b;
+                    V[j * LD + i] = (i == j) ? 1.0 : 0.0;
+                }
             }
             __syncthreads();
+            if (it > 0) {
+                for (int e = tid; e < N * N; e += kMpThreads) {
+                    const int k = e / N, i = e - k * N;                 // A[:, k] = B V[:, k]; lanes walk i: Qp row reads are
+                    const double *vk = V + (size_t)k * LD;             // conflict-free (LD odd), V[k][j] is a broadcast
+                    double acc = 0.0;
+                    for (int j = 0; j < N; ++j) acc = fma(Qp[i * LD + j], vk[j], acc);
+                    A[(size_t)k * LD + i] = acc;
+                }
+                __syncthreads();
+            }
+            const double tau = a.w_rank / mu;
             // ---- one-sided Jacobi: orthogonalise the columns of A, accumulate V ----------------------------------
+            // Round-robin pairing: n_even / 2 disjoint column pairs per round (<= 32), ONE HALF-WARP per pair.  Its 16
+            // lanes read 16 consecutive rows of a column at a time (one conflict-free 128-byte wavefront), keep the
+            // pair's A and V entries in registers between the dot products and the rotation, and meet by four
+            // xor-shuffles.  The rotation's scalar chain uses the MUFU-seeded reciprocal / square root of p2s_math.cuh:
+            // c^2 + s^2 = 1 to a few ulp is what orthogonality needs, the angle itself only steers convergence.
+            // A sweep whose largest rotation was below 1e-7 ends the SVD: Jacobi converges quadratically, so the
+            // columns are orthogonal to ~1e-14 after it and a confirming sweep would only cost time.
             const int n_even = (N + 1) & ~1;
-            const int pair = tid >> 2, sub = tid & 3;
+            const int pair = tid >> 4, l16 = tid & 15;
             for (int sweep = 0; sweep < 40; ++sweep) {
                 if (tid == 0) s_flag[1] = 0;
+                // squared column norms, refreshed once per sweep and carried through the rotations in between
+                // (|a_p'|^2 = |a_p|^2 - t g, |a_q'|^2 = |a_q|^2 + t g): the rounds only need the cross product g
+                for (int k0 = 0; k0 < N; k0 += kMpThreads / 16) {       // trip count uniform over the CTA: full-mask shuffles inside
+                    const int k = k0 + pair;
+                    double n2 = 0.0;
+                    if (k < N) {
+                        const double *ak = A + (size_t)k * LD;
+                        for (int i = l16; i < N; i += 16) n2 = fma(ak[i], ak[i], n2);
+                    }
+#pragma unroll
+                    for (int off = 8; off > 0; off >>= 1) n2 += __shfl_xor_sync(P2S_FULL, n2, off);
+                    if (k < N && l16 == 0) sig[k] = n2;
+                }
                 __syncthreads();
                 for (int r = 0; r < n_even - 1; ++r) {
                     int p = -1, q = -1;
@@ -181,25 +224,55 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                         if (q >= N) p = -1;                                 // the padding column of an odd N
                     }
                     double al = 0.0, be = 0.0, ga = 0.0;
+                    double ru[4], rv[4];
                     if (p >= 0) {
                         const double *ap = A + (size_t)p * LD, *aq = A + (size_t)q * LD;
-                        for (int i = sub; i < N; i += 4) { const double u = ap[i], v = aq[i]; al = fma(u, u, al); be = fma(v, v, be); ga = fma(u, v, ga); }
+                        al = sig[p]; be = sig[q];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int i = l16 + 16 * t;
+                            const bool in = i < N;
+                            ru[t] = in ? ap[i] : 0.0;
+                            rv[t] = in ? aq[i] : 0.0;
+                            ga = fma(ru[t], rv[t], ga);
+                        }
                     }
-                    al += __shfl_xor_sync(P2S_FULL, al, 1); be += __shfl_xor_sync(P2S_FULL, be, 1); ga += __shfl_xor_sync(P2S_FULL, ga, 1);
-                    al += __shfl_xor_sync(P2S_FULL, al, 2); be += __shfl_xor_sync(P2S_FULL, be, 2); ga += __shfl_xor_sync(P2S_FULL, ga, 2);
-                    if (p >= 0 && fabs(ga) > 1e-15 * sqrt(al * be) && ga != 0.0) {
-                        const double zeta = (be - al) / (2.0 * ga);
-                        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+                    for (int off = 8; off > 0; off >>= 1) ga += __shfl_xor_sync(P2S_FULL, ga, off);
+                    // A pair whose columns together carry less than tau^2 spans only singular values below the
+                    // shrinkage threshold: whatever basis it ends in contributes exactly zero, so it is left alone.
+                    const double ab = al * be, g2 = ga * ga;
+                    if (p >= 0 && g2 > 1e-30 * ab && ga != 0.0 && al + be > 0.25 * tau * tau) {
+                        // Jacobi angle with |theta| <= pi/4 from two reciprocal square roots:
+                        //   d = be - al, h = hypot(d, 2 g), cos 2theta = |d| / h, sin 2theta = sign(d) 2 g / h,
+                        //   c = sqrt((1 + cos 2theta) / 2), s = sin 2theta / (2 c)          (c^2 + s^2 = 1 identically)
+                        const double d = be - al;
+                        const double h2 = fma(d, d, 4.0 * g2);
+                        double rh;
+                        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rh) : "d"(h2));
+                        { const double e = fma(-h2 * rh, rh, 1.0); rh = fma(rh * e, fma(0.375, e, 0.5), rh); }       // 1 / h
+                        const double c2 = fma(0.5 * fabs(d), rh, 0.5);                                           // c^2 in [0.5, 1]
+                        double rc;
+                        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(c2));
+                        { const double e = fma(-c2 * rc, rc, 1.0); rc = fma(rc * e, fma(0.375, e, 0.5), rc); }       // 1 / c
+                        const double cs = c2 * rc;
+                        const double sn = (d >= 0.0 ? ga : -ga) * rh * rc;
                         double *ap = A + (size_t)p * LD, *aq = A + (size_t)q * LD;
                         double *vp = V + (size_t)p * LD, *vq = V + (size_t)q * LD;
-                        for (int i = sub; i < N; i += 4) {
-                            const double u = ap[i], v = aq[i];
-                            ap[i] = cs * u - sn * v; aq[i] = sn * u + cs * v;
-                            const double x = vp[i], y = vq[i];
-                            vp[i] = cs * x - sn * y; vq[i] = sn * x + cs * y;
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt) {
+                            const int i = l16 + 16 * tt;
+                            if (i < N) {
+                                ap[i] = fma(cs, ru[tt], -sn * rv[tt]); aq[i] = fma(sn, ru[tt], cs * rv[tt]);
+                                const double x = vp[i], y = vq[i];
+                                vp[i] = fma(cs, x, -sn * y); vq[i] = fma(sn, x, cs * y);
+                            }
                         }
-                        if (sub == 0) s_flag[1] = 1;
+                        if (l16 == 0) {
+                            const double tg = sn * rc * ga;                 // t g, t = s / c
+                            sig[p] = fmax(al - tg, 0.0); sig[q] = be + tg;
+                            if (g2 > 1e-14 * ab) s_flag[1] = 1;             // a rotation above 1e-7: sweep again
+                        }
                     }
                     __syncthreads();
                 }
@@ -207,7 +280,6 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                 __syncthreads();
             }
             // ---- shrink: factor_k = max(s_k - tau, 0) / s_k, s_k = |a_k| --------------------------------------------
-            const double tau = a.w_rank / mu;
             for (int k = tid; k < N; k += kMpThreads) {
                 double s2 = 0.0;
                 for (int i = 0; i < N; ++i) s2 = fma(A[(size_t)k * LD + i], A[(size_t)k * LD + i], s2);
@@ -276,13 +348,12 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
             a.out_rows[(f * NM + r) * C + v] = (int8_t)best;
         }
         if (tid == 0 && a.out_iters) a.out_iters[f] = iters;
-        (void)lane;
-    }
+        }
 }
 
 size_t mp_smem_bytes(int n_max, int n_joints) {
     const size_t LD = (size_t)(n_max | 1);
-    return 6 * (size_t)n_max * LD * sizeof(double) + ((size_t)n_max + 4) * sizeof(double) + (size_t)n_max * 3 * n_joints * sizeof(float) +
+    return 6 * (size_t)n_max * LD * sizeof(double) + ((size_t)n_max + kMpWarps) * sizeof(double) + (size_t)n_max * 3 * n_joints * sizeof(float) +
            ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + 16;
 }
 
