@@ -17,6 +17,7 @@ float32 values (`kp[0].item()`, poseEstimation.py:260), so nothing is lost for i
 holds values that float32 cannot represent, `float32_inexact` counts them and the callers log it.
 """
 import fnmatch
+import functools
 import json
 import os
 import re
@@ -26,18 +27,29 @@ import numpy as np
 _LAST_NUMBER = re.compile(r"\d+")
 
 
+@functools.lru_cache(maxsize=1 << 20)
+def _last_int(name):
+    """Last run of digits of `name` as an int, None without digits (one regex pass per distinct name: the sort
+    keys and the frame table of a 40 k-file trial share it)."""
+    nums = _LAST_NUMBER.findall(name)
+    return int(nums[-1]) if nums else None
+
+
 def sort_by_last_number(names):
     """common.py:568-583: strings with a number first, by their last number; the rest alphabetically."""
     def key(s):
-        nums = _LAST_NUMBER.findall(s)
-        return (False, int(nums[-1])) if nums else (True, s)
+        n = _last_int(s)
+        return (True, s) if n is None else (False, n)
     return sorted(names, key=key)
 
 
 def frame_number(name):
     """triangulation.py:799 `int(re.split(r'(\\d+)', j)[-2])`: the last run of digits in the name.
     Raises IndexError for a name without digits, like the reference."""
-    return int(re.split(r"(\d+)", name)[-2])
+    n = _last_int(name)
+    if n is None:
+        raise IndexError("list index out of range")
+    return n
 
 
 class PoseDirs:
@@ -153,8 +165,9 @@ def float32_inexact(*arrays):
 
 def frame_paths(input_dir, cam_dirs, table):
     """Absolute path per (frame, camera); '' where the frame has no file ('none' in the reference)."""
-    return [[os.path.join(input_dir, cam_dirs[c], names[c]) if names[c] != "none" else "" for c in range(len(cam_dirs))]
-            for names in table]
+    prefix = [os.path.join(input_dir, d, "") for d in cam_dirs]          # one join per camera, not per file
+    n = len(cam_dirs)
+    return [[prefix[c] + names[c] if names[c] != "none" else "" for c in range(n)] for names in table]
 
 
 def read_pose_files(paths, keypoints_ids, nb_persons, n_threads=0):
