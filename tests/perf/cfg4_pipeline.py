@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3] — "Demo_MultiPerson-shaped synthetic: 8 cams x 6 persons, person association +
+triangulation" — as one in-memory pipeline on a B200:
+
+    detections [F, C, 6, 3 K]  --mp_associate_kernel-->  arg-max rows  --host (NumPy, the reference's own
+    np.unique bookkeeping)-->  proposals [F][n_persons, C]  --gather-->  x, y, lik [F, 6, K, C]
+    --triangulate_kernel-->  Q [F, 6, K, 3]
+
+    python tests/perf/cfg4_pipeline.py [frames]
+
+One JSON line (also gpurun_out/cfg4_pipeline.jsonl): time and rate of every stage, the share of proposals that
+group detections of ONE true person, the triangulation error against the synthetic truth, and a parity check of
+the first frames against the NumPy restatements (association proposals identical, Q within 1e-6 m)."""
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def gather_persons(obs, props, n_persons):
+    """obs [F, C, NP, 3 K], props[f] = [n_f, C] detection index per camera (NaN = not seen) ->
+    x, y, lik float32 [F, n_persons, K, C] (NaN where a person / camera is missing)."""
+    F, C, NP, L = obs.shape
+    K = L // 3
+    idx = np.full((F, n_persons, C), -1, np.int64)
+    for f, p in enumerate(props):
+        if p.size:
+            n = min(len(p), n_persons)
+            idx[f, :n] = np.where(np.isnan(p[:n]), -1, p[:n]).astype(np.int64)
+    safe = np.maximum(idx, 0)
+    g = obs[np.arange(F)[:, None, None], np.arange(C)[None, None, :], safe]          # [F, n, C, 3K]
+    g = np.where((idx >= 0)[..., None], g, np.float32(np.nan)).reshape(F, n_persons, C, K, 3)
+    g = g.transpose(0, 1, 3, 2, 4)                                                   # [F, n, K, C, 3]
+    return (np.ascontiguousarray(g[..., i]) for i in range(3))
+
+
+def main():
+    import torch
+    import p2s_oracle as orc
+    import p2s_oracle_mp as omp
+    from pose2sim_b200 import multi_person as mp
+    from pose2sim_b200 import ops, synth
+    F = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+    C, NP, K = 8, 6, 26
+    d_max, min_aff, min_cams, thr, lik_thr = 0.1, 0.2, 2, 15.0, 0.3
+    w = synth.make_multi_person_workload(C, F, NP, seed=404)
+    eng = ops.get_engine(0)
+    n_max = max(1, int(w["count"].sum(axis=1).max()))
+    for _ in range(2):                                                   # second pass is the timed one
+        t0 = time.perf_counter()
+        out = eng.associate_multi_host(w["obs"], w["count"], w["models"], d_max, min_aff, n_max=n_max)
+        t1 = time.perf_counter()
+        n = w["count"].sum(axis=1)
+        props = [mp.proposals_from_rows(out["rows"][f, :n[f]], min_cams) for f in range(F)]
+        t2 = time.perf_counter()
+        x, y, lik = gather_persons(w["obs"], props, NP)
+        t3 = time.perf_counter()
+        U = F * NP * K
+        res = eng.triangulate_host(x.reshape(U, C), y.reshape(U, C), lik.reshape(U, C), w["P"], lik_thr, thr, min_cams)
+        t4 = time.perf_counter()
+    # ---- quality: a proposal should group detections of one true person --------------------------------
+    pure = total = 0
+    for f, p in enumerate(props):
+        for row in p:
+            seen = ~np.isnan(row)
+            true = w["perm"][f, np.flatnonzero(seen), row[seen].astype(int)]
+            pure += int(len(set(true.tolist())) == 1)
+            total += 1
+    # ---- parity of the first frames against the NumPy restatements ---------------------------------------
+    cams = omp.camera_ray_params(w["models"])
+    n_chk, bad_props, worst = min(F, 40), 0, 0.0
+    for f in range(n_chk):
+        det = [[w["obs"][f, c, p].astype(float) for p in range(w["count"][f, c])] for c in range(C)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            aff, cum = omp.frame_affinity(det, cams, d_max, min_aff)
+            ref = omp.proposals_from_affinity(aff, cum, min_cams)
+        bad_props += int(not np.array_equal(ref, props[f], equal_nan=True))
+    u_chk = n_chk * NP * K
+    xs, ys, ls = (a.reshape(U, C)[:u_chk].astype(np.float64) for a in (x, y, lik))
+    low = ls < lik_thr
+    xs[low] = np.nan; ys[low] = np.nan; ls[low] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Qo, eo, no, mo = orc.triangulate_units(xs, ys, ls, w["P"], thr, min_cams)
+    same_dec = bool(np.array_equal(no.astype(np.uint8), res["nexcl"][:u_chk]) and np.array_equal(mo, res["mask"][:u_chk]))
+    both = np.isfinite(Qo).all(axis=1) & np.isfinite(res["Q"][:u_chk]).all(axis=1)
+    worst = float(np.abs(Qo[both] - res["Q"][:u_chk][both]).max(initial=0.0))
+    nan_same = bool(np.array_equal(np.isnan(Qo), np.isnan(res["Q"][:u_chk])))
+    line = {"bench": "cfg4_pipeline", "frames": F, "cams": C, "persons": NP, "keypoints": K,
+            "associate_ms": (t1 - t0) * 1e3, "associate_frames_per_s": F / (t1 - t0),
+            "proposals_host_ms": (t2 - t1) * 1e3, "gather_host_ms": (t3 - t2) * 1e3,
+            "triangulate_ms": (t4 - t3) * 1e3, "triangulate_units_per_s": U / (t4 - t3),
+            "pipeline_frames_per_s": F / (t4 - t0), "pipeline_units_per_s": U / (t4 - t0),
+            "proposals": total, "proposals_of_one_true_person": pure / max(total, 1),
+            "level_hist": res["stats"]["level_hist"], "failed_units": res["stats"]["failed"],
+            "parity_frames_checked": n_chk, "proposal_mismatches": bad_props, "decisions_identical": same_dec,
+            "nan_pattern_identical": nan_same, "max_abs_dQ_m": worst}
+    print(json.dumps(line))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "cfg4_pipeline.jsonl"), "a") as f:
+        f.write(json.dumps(line) + "\n")
+
+
+if __name__ == "__main__":
+    main()
