@@ -432,7 +432,7 @@ def main():
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
             "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                          "traffic": NCU_TRAFFIC.get((args.workload, world)), "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "kernel": f"triangulate_kernel<{4 if C <= 4 else 8 if C <= 8 else 16 if C <= 16 else 32},secular,exact,lean>",
+                         "kernel": f"triangulate_kernel<{next(m for m in (4, 6, 8, 12, 16, 24, 32) if C <= m)},secular,exact,lean>",
                          "grid_ctas": eng.last_grid(),
                          "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "dependent-chain DFMA microbenchmark in this run (p2s_measure_fp64_peak); "

@@ -100,7 +100,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 #ifndef P2S_TRI_MIN_BLOCKS
-#define P2S_TRI_MIN_BLOCKS 4        /* 4 vs 5 resident CTAs per SM measured equal (tools/kernel_ab.py); 4 has no spills */
+#define P2S_TRI_MIN_BLOCKS 4        /* 4 vs 5 resident CTAs per SM measured equal (tools/kernel_ab.py); 4 has no spills.
+                                       Wider slabs only fit 3 (24 cameras) / 2 (32 cameras) CTAs per SM anyway: the
+                                       register cap follows, which removes the spills of the 32-camera unrolls */
 #endif
 
 template <int CMAX>
@@ -189,7 +191,7 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 // STATS: the statistics block (work counters, level histogram, eps-band counts incl. the arg-min runner-up) is
 // wanted; the lean variant compiles all of that bookkeeping out of the candidate loop.
 template <int CMAX, int SOLVER, bool DISTORT, bool EXACT, bool STATS>
-__global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(const CamParams<CMAX> cams,
+__global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <= 24 ? 3 : 2) triangulate_kernel(const CamParams<CMAX> cams,
                                                                                const LensSet<DISTORT ? CMAX : 1> lens,
                                                                                const TriArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_kernel(co
 #ifdef P2S_NO_TMA                                              /* A/B switch, tools/kernel_ab.py */
     const bool tma = false;
 #else
-    const bool tma = EXACT && CMAX <= 8 && a.px != nullptr;
+    const bool tma = EXACT && CMAX <= 8 && (CMAX * 4) % 16 == 0 && a.px != nullptr;   // bulk copies move multiples of 16 bytes
 #endif
     const uint32_t bar = smem_u32(&S.mbar);
     uint32_t phase = 0;
@@ -759,7 +761,9 @@ static cudaError_t launch_persistent(Kern kern, size_t smem, const TriLaunch &L,
     return cudaGetLastError();
 }
 
-template <int CMAX>
+// FULLSET = false (the camera counts 6, 12, 24 between the powers of two): only the exact-count secular kernels are
+// instantiated — they are what a 6 / 12 / 24-camera rig runs; everything else goes to the next power of two.
+template <int CMAX, bool FULLSET>
 static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     CamParams<CMAX> cams;
     for (int c = 0; c < CMAX; ++c)
@@ -788,6 +792,12 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
     a.err_word = L.err_word;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;
+    if constexpr (!FULLSET) {
+        LensSet<1> none;
+        std::memset(&none, 0, sizeof none);
+        if (L.stats == nullptr) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem, L, grid_out, cams, none, a);
+        return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true>, smem, L, grid_out, cams, none, a);
+    } else {
     if (L.lens) {                                             // undistort_points: distorted re-projection
         LensSet<CMAX> lens;
         std::memset(&lens, 0, sizeof lens);
@@ -809,13 +819,18 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     if (L.solver == 0 && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, false>, smem, L, grid_out, cams, none, a);
     if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, true>, smem, L, grid_out, cams, none, a);
     return launch_persistent(triangulate_kernel<CMAX, 1, false, false, true>, smem, L, grid_out, cams, none, a);
+    }
 }
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
-    if (L.n_cams <= 4) return launch_tri<4>(L, grid_out);
-    if (L.n_cams <= 8) return launch_tri<8>(L, grid_out);
-    if (L.n_cams <= 16) return launch_tri<16>(L, grid_out);
-    return launch_tri<32>(L, grid_out);
+    const bool plain = L.solver == 0 && L.lens == nullptr;
+    if (plain && L.n_cams == 6) return launch_tri<6, false>(L, grid_out);
+    if (plain && L.n_cams == 12) return launch_tri<12, false>(L, grid_out);
+    if (plain && L.n_cams == 24) return launch_tri<24, false>(L, grid_out);
+    if (L.n_cams <= 4) return launch_tri<4, true>(L, grid_out);
+    if (L.n_cams <= 8) return launch_tri<8, true>(L, grid_out);
+    if (L.n_cams <= 16) return launch_tri<16, true>(L, grid_out);
+    return launch_tri<32, true>(L, grid_out);
 }
 
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,
