@@ -471,12 +471,18 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
     if (stats) P2S_CUDA(h, cudaMemsetAsync(h->d_stats, 0, P2S_STAT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
     if (stats) P2S_CUDA(h, cudaStreamSynchronize(h->slots[0].stream));
     const size_t C = (size_t)n_cams;
+    const bool automatic = h->chunk_units <= 0;
     long long chunk = h->chunk_units;
-    if (chunk <= 0) chunk = std::min<long long>(1LL << 20, std::max<long long>(1LL << 16, ((n_units / 4) + 31) & ~31LL));
+    if (automatic) chunk = std::min<long long>(1LL << 20, std::max<long long>(1LL << 16, ((n_units / 4) + 31) & ~31LL));
     chunk = std::min<long long>(chunk, std::max<long long>(n_units, 1));
     int i = 0;
-    for (long long u0 = 0; u0 < n_units; u0 += chunk, ++i) {
-        const long long nu = std::min(chunk, n_units - u0);
+    long long nu = 0;
+    for (long long u0 = 0; u0 < n_units; u0 += nu, ++i) {
+        const long long rem = n_units - u0;
+        nu = std::min(chunk, rem);
+        // Automatic mode tapers the tail: once the rest fits one chunk it is halved down to 2^15 units, so that what
+        // is left exposed after the last H2D copy (one kernel + one D2H) is a ~1 MB chunk instead of a ~25 MB one.
+        if (automatic && rem <= chunk && rem > (1LL << 15)) nu = std::max<long long>(1LL << 15, ((rem / 2) + 31) & ~31LL);
         Slot &s = h->slots[i % kSlots];
         if ((rc = ensure(h, s.x, nu * C * 4)) || (rc = ensure(h, s.y, nu * C * 4)) || (rc = ensure(h, s.lik, nu * C * 4)) ||
             (rc = ensure(h, s.obs, nu * C * 16)) || (rc = ensure(h, s.Q, nu * 24)) || (rc = ensure(h, s.err, nu * 8)) ||

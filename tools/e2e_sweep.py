@@ -33,7 +33,7 @@ def main():
               "err": torch.empty(U, dtype=torch.float64).pin_memory().numpy(),
               "nexcl": torch.empty(U, dtype=torch.uint8).pin_memory().numpy(),
               "mask": torch.empty(U, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
-        for chunk in (1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 20):
+        for chunk in (0, 1 << 16, 1 << 18, 1 << 20):                  # 0 = automatic (quarter of the call, tapered tail)
             eng.set_chunk_units(chunk)
             for _ in range(3):
                 eng.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], cfg["lik_thr"], cfg["thr"], cfg["min_cams"], out=ho, want_stats=False)
