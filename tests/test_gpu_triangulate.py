@@ -71,7 +71,8 @@ def test_reference_cfg1_demo_cameras(engine, golden):
 
 
 @pytest.mark.parametrize("C,mc,thr,seed", [(8, 2, 15.0, 202), (16, 3, 15.0, 303), (4, 2, 15.0, 101),
-                                          (5, 3, 10.0, 7), (12, 8, 15.0, 11), (32, 28, 15.0, 532)])
+                                          (5, 3, 10.0, 7), (12, 8, 15.0, 11), (32, 28, 15.0, 532),
+                                          (6, 2, 15.0, 506), (24, 20, 15.0, 524), (7, 3, 15.0, 9)])
 def test_oracle_synthetic(engine, C, mc, thr, seed):
     F = 12 if C <= 8 else (6 if C <= 16 else 3)
     wl = synth.make_triangulation_workload(C, F, 1, 26, seed=seed)
@@ -169,14 +170,15 @@ def test_jacobi_solver_agrees(engine):
     assert np.allclose(a["err"], b["err"], atol=1e-8, rtol=0, equal_nan=True)
 
 
-@pytest.mark.parametrize("C,U", [(8, 2600), (8, 37), (5, 333), (4, 1), (16, 257), (3, 1000), (32, 65)])
+@pytest.mark.parametrize("C,U", [(8, 2600), (8, 37), (5, 333), (4, 1), (16, 257), (3, 1000), (32, 65), (6, 999), (12, 300),
+                                 (24, 130)])
 def test_fused_planes_path_equals_staged_path(engine, C, U):
     """`p2s_triangulate_planes_device` (gate + float4 staging fused into the tile load) is bit-identical to
     `p2s_stage_observations_device` + `p2s_triangulate_device`, for ragged sizes and odd camera counts."""
     import torch
     wl = synth.make_triangulation_workload(C, -(-U // 26), 1, 26, seed=77 + C, lik_thr=None)
     x, y, lik = (torch.from_numpy(np.ascontiguousarray(wl[k][:U])).cuda() for k in ("x", "y", "lik"))
-    mc = 2 if C < 32 else 28
+    mc = 2 if C < 24 else C - 4
     a = engine.triangulate(engine.stage_observations(x, y, lik, 0.3), wl["P"], 15.0, mc)
     b = engine.triangulate_planes(x, y, lik, wl["P"], 0.3, 15.0, mc)
     torch.cuda.synchronize()
