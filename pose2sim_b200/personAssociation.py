@@ -49,7 +49,10 @@ class StagedAssociation:
                  "tracked_keypoint_id", "obs", "count", "parsed", "inexact")
 
 
-def stage_project(config_dict):
+def stage_project(config_dict, rank=0, world=1):
+    """Host staging.  With world > 1 (one process per GPU under torchrun) every rank discovers the whole trial
+    but stages only its own contiguous frame block (sharding.frame_block): frames are independent
+    (personAssociation.py:758-804 keeps no cross-frame state) and every rank writes its own output files."""
     s = read_settings(config_dict)
     if s["undistort_points"]:
         raise NotImplementedError("[triangulation] undistort_points = true is not available in the B200 path")
@@ -61,13 +64,17 @@ def stage_project(config_dict):
     dirs = _stg.PoseDirs(s["project_dir"])
     cam_dirs = dirs.camera_dirs()
     _, files = dirs.files_for_association(cam_dirs)
-    if not os.path.exists(dirs.tracked_dir):
-        os.mkdir(dirs.tracked_dir)
-    for d in cam_dirs:
-        try:
-            os.mkdir(os.path.join(dirs.tracked_dir, d))
-        except OSError:
-            break                                             # the reference stops at the first failure (:735-736)
+    if rank == 0:
+        if not os.path.exists(dirs.tracked_dir):
+            os.mkdir(dirs.tracked_dir)
+        for d in cam_dirs:
+            try:
+                os.mkdir(os.path.join(dirs.tracked_dir, d))
+            except OSError:
+                break                                         # the reference stops at the first failure (:735-736)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                                        # the output directories exist before anyone writes
     fr = s["frame_range"]
     f_range = [0, max(len(j) for j in files)] if fr in ("all", "auto", []) else fr
     n_cams = len(cam_dirs)
@@ -88,6 +95,10 @@ def stage_project(config_dict):
     st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
     st.cam_dirs, st.dirs, st.f_range, st.n_cams, st.tracked_keypoint_id = cam_dirs, dirs, list(f_range), n_cams, kid
     st.table = _stg.frame_file_table(files, f_range)
+    if world > 1:
+        from . import sharding
+        a, b = sharding.frame_block(len(st.table), rank, world)
+        st.table = st.table[a:b]
     # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
     if s["multi_person"]:
         st.parsed = [[_stg.load_json(os.path.join(dirs.pose_dir, cam_dirs[c], names[c])) for c in range(n_cams)]
@@ -103,10 +114,10 @@ def stage_project(config_dict):
     return st
 
 
-def solve_frames(st, engine=None):
+def solve_frames(st, engine=None, device=0):
     """ONE device call for all frames.  Returns err[F], comb[F, C] (float, NaN = camera off), Q[F, 3]."""
     from . import ops
-    eng = engine if engine is not None else ops.get_engine(0)
+    eng = engine if engine is not None else ops.get_engine(device)
     s = st.settings
     n_p = max(1, int(st.count.max(initial=0)))
     obs = np.ascontiguousarray(st.obs[:, :, :n_p, :])
@@ -126,11 +137,11 @@ def stage_multi_person(st):
     return obs, count, _calib.camera_models(st.calib_file)
 
 
-def solve_frames_multi_person(st, engine=None):
+def solve_frames_multi_person(st, engine=None, device=0):
     """DEVICE: personAssociation.py:793-801 for all frames in one call.  Returns the proposals per frame."""
     from . import multi_person as mp
     from . import ops
-    eng = engine if engine is not None else ops.get_engine(0)
+    eng = engine if engine is not None else ops.get_engine(device)
     s = st.settings
     obs, count, models = stage_multi_person(st)
     return mp.associate_frames(eng, obs, count, models, s["reconstruction_error_threshold"], s["min_affinity"],
@@ -156,7 +167,7 @@ def rewrite_frame(tracked_paths, source_js, proposals):
             os.remove(path)
 
 
-def write_outputs(st, res):
+def write_outputs(st, res, log=True):
     """personAssociation.py:776-808."""
     errors, cams_off = [], []
     for fi, names in enumerate(st.table):
@@ -166,14 +177,17 @@ def write_outputs(st, res):
         cams_off.append(int(np.count_nonzero(np.isnan(comb))))
         tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
         rewrite_frame(tracked, st.parsed[fi], [comb])
-    log_recap(st, errors, cams_off)
+    if log:
+        log_recap(st, errors, cams_off)
     return {"error": errors, "cameras_off": cams_off}
 
 
-def write_outputs_multi_person(st, proposals):
+def write_outputs_multi_person(st, proposals, log=True):
     for fi, names in enumerate(st.table):
         tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
         rewrite_frame(tracked, st.parsed[fi], proposals[fi])
+    if not log:
+        return
     s = st.settings
     logging.info(f"\n--> A person was reconstructed if the lines from cameras to their keypoints intersected within "
                  f"{s['reconstruction_error_threshold']} m and if the calculated affinity stayed above {s['min_affinity']}.")
@@ -201,10 +215,30 @@ def log_recap(st, errors, cams_off):
 
 def associate_all(config_dict):
     """Same contract as Pose2Sim/personAssociation.py:642: reads calibration + per-camera JSON, writes
-    `pose-associated/<cam>_json/*.json` with one person of interest, logs the recap.  Returns None."""
-    st = stage_project(config_dict)
-    if st.settings["multi_person"]:
-        write_outputs_multi_person(st, solve_frames_multi_person(st))
+    `pose-associated/<cam>_json/*.json` with one person of interest, logs the recap.  Returns None.
+
+    Under torchrun (torch.distributed initialised, one process per GPU) the frames are sharded in contiguous
+    blocks over the ranks; each rank stages, solves on its own GPU and writes its own files — no data-path
+    exchange; only the recap's per-frame scalars travel to rank 0, which logs."""
+    from .triangulation import _world
+    rank, world, local = _world()
+    if world == 1:
+        st = stage_project(config_dict)
+        if st.settings["multi_person"]:
+            write_outputs_multi_person(st, solve_frames_multi_person(st))
+            return
+        write_outputs(st, solve_frames(st))
         return
-    res = solve_frames(st)
-    write_outputs(st, res)
+    import torch.distributed as dist
+    st = stage_project(config_dict, rank, world)
+    if st.settings["multi_person"]:
+        proposals = solve_frames_multi_person(st, device=local) if len(st.table) else []
+        write_outputs_multi_person(st, proposals, log=rank == 0)
+        dist.barrier()
+        return
+    res = solve_frames(st, device=local) if len(st.table) else {"err": np.zeros(0), "comb": np.zeros((0, st.n_cams)), "Q": np.zeros((0, 3))}
+    part = write_outputs(st, res, log=False)
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    if rank == 0:
+        log_recap(st, [e for p in parts for e in p["error"]], [c for p in parts for c in p["cameras_off"]])

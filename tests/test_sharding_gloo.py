@@ -112,3 +112,68 @@ def test_dropin_two_ranks_writes_the_reference_trc(golden, tmp_path, tag):
     assert sorted(got) == sorted(ref)
     for name in ref:
         assert_trc_equal(got[name], ref[name], tol=1e-6)
+
+
+# ---- associate_all under a 2-rank job: frames sharded, every rank writes its own files, no gather -------------
+def _assoc_worker(rank, world, port, proj, cfg, multi):
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import p2s_oracle as orc
+    import p2s_oracle_mp as omp
+    from pose2sim_b200 import multi_person as mpx
+    from pose2sim_b200 import personAssociation as pa
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def oracle_single(st, engine=None, device=0):           # TEST stand-ins for the device calls (no GPU here)
+        F, C = st.count.shape
+        err, comb, Q = np.empty(F), np.empty((F, C)), np.empty((F, 3))
+        s = st.settings
+        for f in range(F):
+            ob = [[st.obs[f, c, p, :3].astype(float) for p in range(st.count[f, c])] for c in range(C)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                err[f], comb[f], Q[f] = orc.associate_frame(ob, list(st.count[f]), st.P, s["reproj_thr"], s["lik_thr"], s["min_cams"])
+        return {"err": err, "comb": comb, "Q": Q}
+
+    def oracle_multi(st, engine=None, device=0):
+        obs, count, models = pa.stage_multi_person(st)
+        s = st.settings
+        cams = omp.camera_ray_params(models)
+        out = []
+        for f in range(len(count)):
+            det = [[obs[f, c, p].astype(float) for p in range(count[f, c])] for c in range(st.n_cams)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                aff, cum = omp.frame_affinity(det, cams, s["reconstruction_error_threshold"], s["min_affinity"])
+            out.append(mpx.proposals_from_rows(omp.argmax_rows(aff, cum), s["min_cams"]))
+        return out
+
+    pa.solve_frames, pa.solve_frames_multi_person = oracle_single, oracle_multi
+    try:
+        os.chdir(proj)
+        pa.associate_all(cfg)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tag", ["e2e_assoc_single", "e2e_assoc_multi"])
+def test_associate_all_two_ranks_writes_the_reference_json(golden, tmp_path, tag):
+    from dropin_util import associated_people, rebuild_trial
+    g = golden(tag + ".npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_assoc")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_assoc_worker, args=(2, port, proj, cfg, tag.endswith("multi")), nprocs=2, join=True)
+    if tag.endswith("multi"):
+        from test_dropin_host import assert_multi_person_json_equal
+        assert_multi_person_json_equal(proj, g)
+        return
+    chosen, exists = associated_people(proj, [str(c) for c in g["cams"]], g["kp"].shape[0], g["chosen"].shape[2])
+    assert np.array_equal(exists, g["exists"])
+    assert np.array_equal(np.isnan(chosen), np.isnan(g["chosen"]))
+    assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
