@@ -74,6 +74,26 @@ def associated_people(proj, cams, n_frames, n_values):
     return chosen, exists
 
 
+def assert_multi_person_json_equal(proj, g):
+    """pose-associated/ of a multi-person trial against tests/golden/e2e_assoc_multi.npz."""
+    cams = [str(c) for c in g["cams"]]
+    F, C, S, V = g["chosen"].shape
+    for c, cam in enumerate(cams):
+        for f in range(F):
+            path = os.path.join(proj, "pose-associated", f"{cam}_json", f"{cam}_{f:06d}.json")
+            assert os.path.exists(path) == bool(g["exists"][f, c])
+            if not g["exists"][f, c]:
+                continue
+            people = json.load(open(path))["people"]
+            assert len(people) == int(g["n_people"][f, c]), (f, c)
+            for p, person in enumerate(people):
+                ref = g["chosen"][f, c, p]
+                if person:
+                    assert np.array_equal(np.asarray(person["pose_keypoints_2d"], np.float32), ref), (f, c, p)
+                else:
+                    assert np.isnan(ref).all(), (f, c, p)
+
+
 def rebuild_variant(g_single, g_var, i, tmp_path):
     """Variant i of tests/golden/e2e_tri_variants.npz on the inputs of e2e_tri_single.npz."""
     proj, _ = rebuild_trial(g_single, tmp_path, "trial_demo")

@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 
 import p2s_oracle as orc
-from dropin_util import (assert_trc_equal, associated_people, golden_trcs, in_dir, rebuild_trial, written_trcs)
+from dropin_util import (assert_multi_person_json_equal, assert_trc_equal, associated_people, golden_trcs, in_dir,
+                         rebuild_trial, written_trcs)
 from pose2sim_b200 import personAssociation as pa
 from pose2sim_b200 import staging, triangulation as tri
 
@@ -120,28 +121,6 @@ def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
     assert np.array_equal(exists, g["exists"])
     assert np.array_equal(np.isnan(chosen), np.isnan(g["chosen"]))
     assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
-
-
-def assert_multi_person_json_equal(proj, g):
-    """pose-associated/ of a multi-person trial against tests/golden/e2e_assoc_multi.npz."""
-    import json as _json
-    import os as _os
-    cams = [str(c) for c in g["cams"]]
-    F, C, S, V = g["chosen"].shape
-    for c, cam in enumerate(cams):
-        for f in range(F):
-            path = _os.path.join(proj, "pose-associated", f"{cam}_json", f"{cam}_{f:06d}.json")
-            assert _os.path.exists(path) == bool(g["exists"][f, c])
-            if not g["exists"][f, c]:
-                continue
-            people = _json.load(open(path))["people"]
-            assert len(people) == int(g["n_people"][f, c]), (f, c)
-            for p, person in enumerate(people):
-                ref = g["chosen"][f, c, p]
-                if person:
-                    assert np.array_equal(np.asarray(person["pose_keypoints_2d"], np.float32), ref), (f, c, p)
-                else:
-                    assert np.isnan(ref).all(), (f, c, p)
 
 
 def test_multi_person_association_matches_reference_json(golden, tmp_path):

@@ -89,7 +89,7 @@ def test_argument_errors(engine):
 
 def test_associate_all_multi_person_writes_the_reference_json(golden, tmp_path):
     import pose2sim_b200
-    from test_dropin_host import assert_multi_person_json_equal
+    from dropin_util import assert_multi_person_json_equal
     g = golden("e2e_assoc_multi.npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_massoc")
     with in_dir(proj):

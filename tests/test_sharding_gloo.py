@@ -170,7 +170,7 @@ def test_associate_all_two_ranks_writes_the_reference_json(golden, tmp_path, tag
         port = s.getsockname()[1]
     mp.spawn(_assoc_worker, args=(2, port, proj, cfg, tag.endswith("multi")), nprocs=2, join=True)
     if tag.endswith("multi"):
-        from test_dropin_host import assert_multi_person_json_equal
+        from dropin_util import assert_multi_person_json_equal
         assert_multi_person_json_equal(proj, g)
         return
     chosen, exists = associated_people(proj, [str(c) for c in g["cams"]], g["kp"].shape[0], g["chosen"].shape[2])
