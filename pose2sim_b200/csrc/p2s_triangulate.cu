@@ -37,6 +37,7 @@ struct TriArgs {
     const float4 *obs;            // staged [n_cams][n_units], or null when the raw planes are given
     const float *px, *py, *pl;    // raw planes [n_units][n_cams] (x, y, likelihood) or null
     double lik_thr;               // gate for the raw-plane path
+    float lik_thr_f;              // smallest float >= lik_thr: `fl < lik_thr_f` in float <=> `(double)fl < lik_thr`
     int gate;
     long long n_units;
     int n_cams;
@@ -332,7 +333,9 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 for (int t = 0; t < 4; ++t) {
                     const int uu = (j + t) / C, cc = (j + t) - uu * C;
                     float fx = vx[t], fy = vy[t], fl = vl[t];
-                    if (a.gate && (double)fl < a.lik_thr) { fx = fy = fl = nanf_; }
+                    // the reference compares the float64 likelihood with the float64 threshold (triangulation.py:817-821);
+                    // for a float32 likelihood that is exactly `fl < (smallest float >= threshold)`
+                    if (a.gate && fl < a.lik_thr_f) { fx = fy = fl = nanf_; }
                     S.xy[cc][uu] = make_float2(fx, fy);
                     S.w[cc][uu] = fl;
                 }
@@ -772,6 +775,11 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.obs = (const float4 *)L.obs; a.n_units = L.n_units; a.n_cams = L.n_cams; a.min_cams = L.min_cams;
     a.px = L.px; a.py = L.py; a.pl = L.pl; a.lik_thr = L.lik_thr;
     a.gate = (L.lik_thr == L.lik_thr) && !(L.lik_thr == -INFINITY);
+    {
+        float tf = (float)L.lik_thr;                            // round to nearest
+        if (a.gate && (double)tf < L.lik_thr) tf = nextafterf(tf, INFINITY);
+        a.lik_thr_f = tf;
+    }
     a.thr = L.thr; a.band_eps = L.band_eps; a.cand_masks = L.cand_masks;
     for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
     a.max_table_level = L.max_table_level;

@@ -99,6 +99,24 @@ def test_likelihood_gate_matches_reference_rule(engine):
     assert np.array_equal(obs[keep, 0, 0], x[0][keep]) and np.array_equal(obs[keep, 0, 1], y[0][keep])
 
 
+@pytest.mark.parametrize("thr", [0.3, 0.30000001192092896, 0.29999998211860657, 0.5, 1e-50, 0.0])
+def test_fused_gate_is_the_float64_comparison(engine, thr):
+    """The fused path gates in the float domain against the smallest float >= threshold; that must select exactly
+    the likelihoods the reference's float64 comparison selects, also right at the rounding boundaries."""
+    import torch
+    wl = synth.make_triangulation_workload(8, 40, 1, 26, seed=5, lik_thr=None)
+    lik = wl["lik"].copy()
+    edge = np.array([0.3, 0.29999998, 0.30000004, np.nextafter(np.float32(0.3), np.float32(0)), 0.0, 1e-45, 0.5, 0.49999997], np.float32)
+    lik[:64] = edge[np.arange(64 * 8).reshape(64, 8) % 8]
+    x, y, l = (torch.from_numpy(a).cuda() for a in (wl["x"], wl["y"], lik))
+    a = engine.triangulate_planes(x, y, l, wl["P"], thr, 15.0, 2)
+    gx, gy, gl = synth.gate_likelihood(wl["x"], wl["y"], lik, thr)            # float64 comparison on the host
+    b = engine.triangulate_planes(*(torch.from_numpy(t).cuda() for t in (gx, gy, gl)), wl["P"], None, 15.0, 2)
+    torch.cuda.synchronize()
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
+
+
 def test_ragged_and_empty(engine):
     P = synth.ring_cameras(8)[0]
     out = run_gpu(engine, P, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), 15.0, 2)
