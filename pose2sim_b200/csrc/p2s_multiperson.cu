@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
     int *s_view = reinterpret_cast<int *>(sobs + (size_t)NM * 3 * J);  // NM: view of each detection
     int *s_cum = s_view + NM;                                          // C + 1
     int *s_flag = s_cum + P2S_MAX_CAMS + 1;                            // [0] frame, [1] rotations in the sweep
+    unsigned short *s_sched = reinterpret_cast<unsigned short *>(s_flag + 2);   // [rounds][32] pair schedule: p | q << 8, 0xffff = idle
 
     for (;;) {
         __syncthreads();
@@ -160,6 +161,25 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
         }
         __syncthreads();
 
+        // Round-robin (circle method) schedule of the one-sided Jacobi, once per frame: round r pairs column
+        // n_even-1 with r and (r + k) with (r - k) modulo n_even-1 — the rounds then cost one shared-memory read
+        // instead of two integer divisions per thread.
+        {
+            const int n_even = (N + 1) & ~1, m = n_even - 1;
+            for (int e = tid; e < m * 32; e += kMpThreads) {
+                const int r = e >> 5, k = e & 31;
+                unsigned short v = 0xffffu;
+                if (k < n_even / 2) {
+                    int p, q;
+                    if (k == 0) { p = n_even - 1; q = r; }
+                    else { p = (r + k) % m; q = (r - k + m) % m; }
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    if (q < N) v = (unsigned short)(p | (q << 8));      // q >= N: the padding column of an odd N
+                }
+                s_sched[e] = v;
+            }
+        }
+        __syncthreads();
         double mu = 64.0;
         int iters = 0;
         for (int it = 0; it < a.max_iter && N > 0; ++it) {
@@ -216,13 +236,8 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                 }
                 __syncthreads();
                 for (int r = 0; r < n_even - 1; ++r) {
-                    int p = -1, q = -1;
-                    if (pair < n_even / 2) {
-                        if (pair == 0) { p = n_even - 1; q = r; }
-                        else { p = (r + pair) % (n_even - 1); q = (r - pair + (n_even - 1)) % (n_even - 1); }
-                        if (p > q) { const int t = p; p = q; q = t; }
-                        if (q >= N) p = -1;                                 // the padding column of an odd N
-                    }
+                    const unsigned int pq = s_sched[r * 32 + pair];
+                    const int p = (pq == 0xffffu) ? -1 : (int)(pq & 0xffu), q = (int)(pq >> 8);
                     double al = 0.0, be = 0.0, ga = 0.0;
                     double ru[4], rv[4];
                     if (p >= 0) {
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
 size_t mp_smem_bytes(int n_max, int n_joints) {
     const size_t LD = (size_t)(n_max | 1);
     return 6 * (size_t)n_max * LD * sizeof(double) + ((size_t)n_max + kMpWarps) * sizeof(double) + (size_t)n_max * 3 * n_joints * sizeof(float) +
-           ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + 16;
+           ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + (size_t)(n_max | 1) * 32 * sizeof(unsigned short) + 16;
 }
 
 cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out) {
