@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -477,12 +478,30 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
     chunk = std::min<long long>(chunk, std::max<long long>(n_units, 1));
     int i = 0;
     long long nu = 0;
+    // P2S_TRACE=1: device-side timeline of the pipeline (events after each chunk's H2D, kernel and D2H) on stderr
+    const bool trace = std::getenv("P2S_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<long long> tunits;
+    cudaEvent_t t_begin = nullptr;
+    if (trace) {
+        cudaEventCreate(&t_begin);
+        cudaEventRecord(t_begin, h->slots[0].stream);
+        for (int k = 1; k < kSlots; ++k) cudaStreamWaitEvent(h->slots[k].stream, t_begin, 0);
+    }
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
     for (long long u0 = 0; u0 < n_units; u0 += nu, ++i) {
         const long long rem = n_units - u0;
         nu = std::min(chunk, rem);
-        // Automatic mode tapers the tail: once the rest fits one chunk it is halved down to 2^15 units, so that what
-        // is left exposed after the last H2D copy (one kernel + one D2H) is a ~1 MB chunk instead of a ~25 MB one.
-        if (automatic && rem <= chunk && rem > (1LL << 15)) nu = std::max<long long>(1LL << 15, ((rem / 2) + 31) & ~31LL);
+        // Automatic mode tapers the tail: once the rest fits one chunk it is halved down to 2^17 units, so that what
+        // is left exposed after the last H2D copy (one kernel + one D2H) is a few MB instead of ~25 MB.  Not finer:
+        // every copy costs ~13 us of set-up (P2S_TRACE timeline), which shows below ~10 MB per copy.
+        if (automatic && rem <= chunk && rem > (1LL << 17)) nu = std::max<long long>(1LL << 17, ((rem / 2) + 31) & ~31LL);
         Slot &s = h->slots[i % kSlots];
         if ((rc = ensure(h, s.x, nu * C * 4)) || (rc = ensure(h, s.y, nu * C * 4)) || (rc = ensure(h, s.lik, nu * C * 4)) ||
             (rc = ensure(h, s.obs, nu * C * 16)) || (rc = ensure(h, s.Q, nu * 24)) || (rc = ensure(h, s.err, nu * 8)) ||
@@ -491,6 +510,8 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
         P2S_CUDA(h, cudaMemcpyAsync(s.x.p, x + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.y.p, y + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(s.lik.p, lik + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
+        mark(s.stream);
+        tunits.push_back(nu);
         if (lens) {                                               // undistort: separate stage kernel (iterative lens inversion)
             P2S_CUDA(h, p2s::launch_stage((const float *)s.x.p, (const float *)s.y.p, (const float *)s.lik.p, nu, n_cams,
                                          lik_thr, lens, s.obs.p, h->prop.multiProcessorCount, s.stream));
@@ -504,12 +525,25 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
                                      (uint8_t *)s.nexcl.p, (uint32_t *)s.mask.p, stats ? h->d_stats : nullptr, s.stream, &pl);
         }
         if (rc) return rc;
+        mark(s.stream);
         P2S_CUDA(h, cudaMemcpyAsync(out_Q + u0 * 3, s.Q.p, nu * 24, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_err + u0, s.err.p, nu * 8, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_nexcl + u0, s.nexcl.p, nu, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_mask + u0, s.mask.p, nu * 4, cudaMemcpyDeviceToHost, s.stream));
+        mark(s.stream);
     }
     for (int k = 0; k < kSlots; ++k) P2S_CUDA(h, cudaStreamSynchronize(h->slots[k].stream));
+    if (trace) {
+        for (size_t c = 0; c < tunits.size(); ++c) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, t_begin, tev[3 * c]);
+            cudaEventElapsedTime(&b, t_begin, tev[3 * c + 1]);
+            cudaEventElapsedTime(&d, t_begin, tev[3 * c + 2]);
+            fprintf(stderr, "p2s trace chunk %2zu units %8lld  h2d done %7.3f  kernel done %7.3f  d2h done %7.3f ms\n", c, tunits[c], a, b, d);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t_begin);
+    }
     if (stats) P2S_CUDA(h, cudaMemcpy(stats, h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return P2S_OK;
 }
