@@ -391,6 +391,28 @@ def main():
     e2e_s = (time.perf_counter() - t1) / e2e_steps
     sampler.active = False
     sampler.stop_flag = True
+    # the link's own bound for exactly these volumes: the three input planes H2D and the packed outputs D2H as plain
+    # copies on two streams, no kernel (what `e2e` can reach at best on this box)
+    link_ms = None
+    try:
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        hpack = torch.empty(sharding.PACK_BYTES * U, dtype=torch.uint8).pin_memory()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(3):
+            torch.cuda.synchronize()
+            e0.record()
+            s_in.wait_event(e0); s_out.wait_event(e0)
+            with torch.cuda.stream(s_in):
+                for h, d in ((hx, x), (hy, y), (hl, lik)):
+                    d.copy_(h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hpack.copy_(packs[0], non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out)
+            e1.record()
+            torch.cuda.synchronize()
+            link_ms = e0.elapsed_time(e1) if link_ms is None else min(link_ms, e0.elapsed_time(e1))
+    except Exception:
+        link_ms = None
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
 
@@ -442,7 +464,9 @@ def main():
             "e2e": {"value": total_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * C * U,
                     "d2h_bytes_per_step": 37 * U, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "p2s_triangulate_host (pinned host buffers, chunked H2D/compute/D2H on 4 streams)",
-                    "host_threads_bound_to_gpu": prev_affinity is not None},
+                    "host_threads_bound_to_gpu": prev_affinity is not None,
+                    "link_bound_ms": link_ms,
+                    "link_bound_note": "the same H2D + D2H volumes as plain pinned copies on two streams, no kernel, on rank 0"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "wall_ms_per_step": wall_ms / args.steps,
