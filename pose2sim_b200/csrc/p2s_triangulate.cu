@@ -13,18 +13,23 @@
 //   ids / nexcl from the last evaluated level's best candidate, or all cameras (:588-596)
 //   err_min > thr  ->  Q = NaN, err = NaN                                      (:600-602)
 //
-// Mapping to the machine (persistent grid, warp-autonomous tiles of 32 units):
-//   * a warp stages the tile's float4 observations into its private shared-memory slab with
-//     coalesced 512-byte LDG.128 rows (one per camera);
+// Mapping to the machine (persistent grid, warp-autonomous tiles of 32 units, two-deep tile dispenser):
+//   * staging: on the fused raw-plane path lane 0 issues cp.async.bulk (TMA) copies of the NEXT tile's planes into
+//     the warp's shared-memory buffer while the current tile is searched; the warp then gates the likelihoods and
+//     transposes into its float2 xy[C][32] + float w[C][32] slab (staged-buffer API / C > 8: coalesced LDG.128
+//     after an L2 prefetch one tile ahead);
 //   * level 0 has exactly one candidate per unit, so it runs THREAD-PER-UNIT (32 units per warp,
-//     all lanes busy) — the north-star's warp-per-unit mapping would idle 31 lanes here;
+//     all lanes busy) — the north-star's warp-per-unit mapping would idle 31 lanes here; its normal matrix is kept
+//     (m0) as the sum of the unit's valid camera blocks for the deeper levels;
 //   * levels k >= 1 run LANES-ENUMERATE-SUBSETS: the warp's still-failing units are processed
-//     G = 32/W at a time, W = min(32, pow2 >= C(C,k)) lanes each; a lane walks candidates
-//     sub, sub+W, ...; candidate masks come from a lexicographic table (coalesced LDG); the
-//     (error, index) arg-min and the runner-up for the eps-band statistics are reduced with
-//     warp shuffles; the winning lane publishes Q / error / masks to the unit's slot in shared
-//     memory;
-//   * projection matrices are a by-value kernel parameter => constant-bank operands.
+//     G = 32/W at a time, W = min(32, pow2 >= C(C,k)) lanes each; lane c of a group builds camera c's block, then
+//     a lane walks candidates sub, sub+W, ... (masks from a lexicographic table, coalesced LDG) with
+//     M = m0 - excluded blocks; the arg-min is one redux.sync + ballot in the common case (full 64-bit
+//     (error, index) reduction with the runner-up for the eps-band statistics otherwise); the winning lane
+//     publishes Q / error / masks to the unit's slot in shared memory;
+//   * projection matrices are a by-value kernel parameter => constant-bank operands;
+//   * a full tile's outputs leave as 16-byte vectors from a shared-memory staging area — locally or, on the push
+//     path, straight into the consumer GPU's memory, followed by an arrival flag from the launch's last CTA.
 #include <cstddef>
 #include <cstring>
 
