@@ -285,7 +285,9 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() < 1:
             if pg is not None:
-                pg.close()
+                pg.close()                                      # collective (barrier inside) ...
+            else:
+                dist.barrier()                                  # ... so the ranks whose set-up failed join it here
             pg = None
         else:
             gather_mode = "push"

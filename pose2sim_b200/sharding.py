@@ -112,7 +112,7 @@ class PeerGather:
 
     def __init__(self, engine, units_per_rank, group=None, dst=0, n_buffers=2):
         import torch.distributed as dist
-        self.eng, self.dst, self.nb = engine, int(dst), int(n_buffers)
+        self.eng, self.dst, self.nb, self.group = engine, int(dst), int(n_buffers), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         assert len(units_per_rank) == self.world and self.world <= 16 and self.nb * 16 <= 512
@@ -169,9 +169,13 @@ class PeerGather:
         return [packed_views(whole[self.offs[r]:self.offs[r] + PACK_BYTES * self.units[r]], self.units[r]) for r in range(self.world)]
 
     def close(self):
+        """Collective: every rank unmaps what it opened, then (after a barrier) the owners free their buffers."""
         for p in self.opened:
             self.eng.peer_close(p)
         self.opened = []
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
         if self.out_ptr:
             self.eng.peer_free(self.out_ptr)
             self.out_ptr = 0
