@@ -34,13 +34,19 @@ struct CamParams {           // passed BY VALUE as a kernel parameter => lives i
 __device__ __forceinline__ double nan64() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ double inf64() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// 1/d to ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + one cubic correction (3 DFMA).
+// 1/d: MUFU.RCP64H seed (relative error < 2^-22) + one Newton step (2 DFMA) -> < 2^-44 (6e-14).  That is ample:
+// the reciprocals feed the pivots of a Newton iteration that corrects itself and a mean over <= 32 distances whose
+// tolerance is 1e-6 px.  P2S_RCP_CUBIC (A/B switch): the cubic correction (3 DFMA, ~1 ulp).
 __device__ __forceinline__ double rcp_fast(double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     double e = fma(-d, y, 1.0);
+#ifdef P2S_RCP_CUBIC
     double t = fma(e, e, e);
     return fma(y, t, y);
+#else
+    return fma(y, e, y);
+#endif
 }
 
 // sqrt(a) for a >= 0 to ~1 ulp: MUFU.RSQ64H seed + Halley step + one residual correction.
@@ -220,8 +226,12 @@ __device__ __forceinline__ double reproj_distance(const double *Pc, double qx, d
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(S));
     const double t = S * r;
     const double e = fma(-t, r, 1.0);                // 1 - S r^2
+#ifdef P2S_RCP_CUBIC
     const double p = fma(0.375, e, 0.5);
     r = fma(r * e, p, r);                            // r (1 + e/2 + 3 e^2/8)
+#else
+    r = fma(0.5 * r, e, r);                          // Newton: r (1 + e/2), relative error 3/8 e^2 < 3e-14
+#endif
     return N * r;
 }
 
