@@ -54,6 +54,7 @@ struct TriArgs {
     int max_table_level;          // levels above this are unranked arithmetically
     uint32_t ncand[P2S_MAX_CAMS + 1];       // candidates of level k: C(n_cams, k) (saturating)
     unsigned char lw[P2S_MAX_CAMS + 1];     // log2 of the lanes per unit at level k: W = min(32, pow2 >= ncand)
+    double rinv[P2S_MAX_CAMS + 1];          // 1 / m for the mean over m valid cameras
     double *out_Q;
     double *out_err;
     uint8_t *out_nexcl;
@@ -122,6 +123,8 @@ struct alignas(16) WarpSlab {     // per-warp shared memory
     unsigned long long pad_;      // keeps blk (read back as 16-byte vectors by the output staging) 16-byte aligned
     double blk[32 * 10 + 32];     // camera blocks of the current group pass: block (group, camera) at
                                   // group * (10 C + 2) + 10 camera (the +2 staggers the groups over the banks)
+    double2 gxy[32];              // levels >= 1: pixel coordinates of the current group pass as doubles, entry
+                                  // (group, camera) at group * C + camera (G * C <= 32 because W >= C)
     double m0[10][32];            // level 0's normal matrix of every unit of the tile (entry-major): the sum over the
                                   // unit's valid cameras, from which levels >= 1 subtract the excluded blocks
     double r_err[32];             // level results published by the winning lane of each unit
@@ -156,8 +159,6 @@ __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX>
     }
 }
 
-// Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded
-// ones are dropped by a select: no branch, full instruction-level parallelism across cameras).
 // min over the aligned group of W = 2^k lanes this lane belongs to (all 32 lanes take part)
 // P2S_SHFL_ARGMIN (A/B switch): xor-shuffle butterfly; default: ONE redux.sync over the group's member mask
 // (every group of the warp executes the same instruction with its own mask, like a cooperative-groups tile).
@@ -170,24 +171,30 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v, int W, uint32_t gmask)
 #endif
 }
 
-template <int CMAX, bool DISTORT>
+// Mean reprojection distance over the cameras in `valid` (all cameras are evaluated, the excluded ones are dropped
+// by a predicated add: no branch, full instruction-level parallelism across cameras).  GXY: the unit's pixel
+// coordinates come as doubles from the group's array (levels >= 1: converted once per unit by the camera-parallel
+// block pass instead of twice per camera and candidate); otherwise from the float slab (level 0).
+template <int CMAX, bool DISTORT, bool GXY>
 __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams, const LensSet<DISTORT ? CMAX : 1> &lens,
-                                                    const float2 (*obs)[32], int ul, uint32_t valid, int m,
-                                                    double qx, double qy, double qz, const double *sP) {
+                                                    const float2 (*obs)[32], const double2 *gxy, int ul, uint32_t valid,
+                                                    double rinv_m, double qx, double qy, double qz, const double *sP) {
     double sum = 0.0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        const float2 o = obs[c][ul];
+        double2 o;
+        if (GXY) o = gxy[c];
+        else { const float2 f = obs[c][ul]; o = make_double2((double)f.x, (double)f.y); }
         double dist;
-        if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, (double)o.x, (double)o.y);
+        if (DISTORT) dist = reproj_distance_distorted(lens.cam[DISTORT ? c : 0], qx, qy, qz, o.x, o.y);
 #ifdef P2S_SMEM_P                                              /* A/B switch: projection rows from shared memory */
-        else dist = reproj_distance(sP + c * 12, qx, qy, qz, (double)o.x, (double)o.y);
+        else dist = reproj_distance(sP + c * 12, qx, qy, qz, o.x, o.y);
 #else
-        else dist = reproj_distance(cams.P[c], qx, qy, qz, (double)o.x, (double)o.y);
+        else dist = reproj_distance(cams.P[c], qx, qy, qz, o.x, o.y);
 #endif
         if ((valid >> c) & 1u) sum += dist;                      // predicated DADD, no select
     }
-    return div_small(sum, (double)m);
+    return sum * rinv_m;                                        // mean: 1/m from the host table (exactly rounded 1/m)
 }
 
 // DISTORT: `undistort_points = true` — observations were undistorted by the stage kernel, P is built on
@@ -412,8 +419,10 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                         float ow = S.w[sub][ul];
                         const bool v = !((u_inv0 >> sub) & 1u);
                         o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
+                        const double ox = (double)o.x, oy = (double)o.y;
+                        S.gxy[grp * C + sub] = make_double2(ox, oy);       // invalid cameras: never read under `valid`
                         double b[10];
-                        camera_block(sP + sub * 12, (double)o.x, (double)o.y, (double)ow, b);
+                        camera_block(sP + sub * 12, ox, oy, (double)ow, b);
                         t_blocks += v ? 1u : 0u;
                         double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
 #pragma unroll
@@ -473,7 +482,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                             int it;
                             if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            e = mean_reproj_error<CMAX, DISTORT>(cams, lens, S.xy, ul, valid, m, cqx, cqy, cqz, sP);
+                            if (blocks) e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
+                            else e = mean_reproj_error<CMAX, DISTORT, false>(cams, lens, S.xy, nullptr, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
                             t_iters += (uint32_t)it;
                             t_solved += 1u;
                         }
@@ -799,6 +809,8 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
         if (r <= 16) { lw = 0; while ((1ULL << lw) < r) ++lw; }
         a.lw[k] = (unsigned char)lw;
     }
+    a.rinv[0] = 0.0;
+    for (int m = 1; m <= P2S_MAX_CAMS; ++m) a.rinv[m] = 1.0 / (double)m;
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
     a.vec_out = ((((uintptr_t)L.out_Q | (uintptr_t)L.out_err | (uintptr_t)L.out_nexcl | (uintptr_t)L.out_mask) & 15u) == 0) ? 1 : 0;
