@@ -55,10 +55,10 @@ def algorithmic_flops(st):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 71.8 MB written on cfg2
+# `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 73.5 MB written on cfg2
 # (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
-NCU_TRAFFIC = {("cfg2", 1): 321.5e6}
-NCU_TRAFFIC_SOURCE = "profiles/r1n_triangulate_ncu_full.csv"
+NCU_TRAFFIC = {("cfg2", 1): 323.2e6}
+NCU_TRAFFIC_SOURCE = "profiles/r1s_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
