@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--output-mode", default="vector", choices=["vector", "bulk"],
+                    help="how a finished tile leaves the kernel: 16-byte vector stores or cp.async.bulk (TMA) stores")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N > 1: 'push' = the kernel stores its outputs straight into rank 0's memory over NVLink "
                          "(sharding.PeerGather), 'nccl' = dist.gather after the kernel")
@@ -253,6 +255,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = ops.get_engine(local)
+    eng.set_output_mode(args.output_mode)
 
     # ---- workload: every rank owns its own block of frames (weak scaling) ---------------------------
     C, F, thr, mc = cfg["C"], cfg["F"], cfg["thr"], cfg["min_cams"]
@@ -450,7 +453,7 @@ def main():
                                   " whose stores land in rank 0's memory over NVLink (peer-mapped gather buffer, arrival / "
                                   "release flags, no collective)" if gather_mode == "push" else
                                   " + NCCL gather to rank 0"),
-                       "gather": gather_note + gather_mode,
+                       "gather": gather_note + gather_mode, "output_mode": args.output_mode,
                        "level_hist": st["level_hist"], "candidates_per_unit": st["candidates"] / U,
                        "failed_units": st["failed"], "eps_band_px": 1e-6,
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},

@@ -105,6 +105,10 @@ int p2s_set_band_eps(p2s_handle *h, double eps_px);
  * (the north-star's nominal solver; kept for A/B evidence). */
 int p2s_set_solver(p2s_handle *h, int solver);
 
+/* how the triangulation kernels write a full 32-unit tile of outputs: 0 (default) = 16-byte vector stores from the
+ * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path) */
+int p2s_set_output_mode(p2s_handle *h, int mode);
+
 /* units per H2D -> search -> D2H pipeline chunk of the *_host entry points (4 chunks in flight);
  * 0 (default) = automatic, about a quarter of the call's units clamped to [2^16, 2^20] */
 int p2s_set_chunk_units(p2s_handle *h, long long units);

@@ -45,6 +45,7 @@ struct p2s_handle {
     int solver = 0;
     int assoc_team = 0;
     long long chunk_units = kChunkUnitsDefault;
+    int bulk_out = 0;
     long long launches = 0;
     int last_grid = 0;
     std::string last_error;
@@ -168,6 +169,7 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     L.tile_counter = next_counter(h);
     L.stream = stream;
     L.err_word = error_word(h);
+    L.bulk_out = h->bulk_out;
     if (push) { L.wait_flag = push->wait_flag; L.wait_value = push->wait_value; L.done_flag = push->done_flag; L.done_value = push->done_value; }
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 2 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
@@ -287,6 +289,12 @@ int p2s_set_band_eps(p2s_handle *h, double eps) {
 int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame) {
     if (!h || (warps_per_frame != 0 && warps_per_frame != 1 && warps_per_frame != 8)) return P2S_EINVAL;
     h->assoc_team = warps_per_frame;
+    return P2S_OK;
+}
+
+int p2s_set_output_mode(p2s_handle *h, int mode) {
+    if (!h || (mode != 0 && mode != 1)) return P2S_EINVAL;
+    h->bulk_out = mode;
     return P2S_OK;
 }
 

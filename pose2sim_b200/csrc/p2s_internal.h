@@ -29,6 +29,7 @@ struct TriLaunch {
     unsigned int *done_flag = nullptr;
     unsigned int done_value = 0;
     unsigned int *err_word = nullptr;
+    int bulk_out = 0;             // full tiles leave by TMA bulk stores (p2s_set_output_mode)
     cudaStream_t stream;
 };
 

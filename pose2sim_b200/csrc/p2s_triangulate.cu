@@ -62,6 +62,7 @@ struct TriArgs {
     unsigned long long *stats;
     unsigned int *tile_counter;   // [0] tile dispenser, [1] CTAs finished (both zeroed before the launch)
     int vec_out;                  // output planes 16-byte aligned: full tiles are written as 16-byte vectors
+    int bulk_out;                 // ... by cp.async.bulk (TMA) stores from the staging area instead of st.global.v4
     // multi-GPU push (outputs may live in a PEER's memory, p2s_triangulate_planes_push_device):
     const unsigned int *wait_flag;   // local: no output is written before *wait_flag >= wait_value (back-pressure)
     unsigned int wait_value;
@@ -99,6 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -269,6 +276,10 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     for (;;) {
         const unsigned int tile = __shfl_sync(P2S_FULL, t1, 0);
         if ((long long)tile >= n_tiles) break;
+        if (a.bulk_out) {                                       // the previous tile's bulk stores have read the staging area
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+        }
         t1 = t2;
         if (lane == 0) t2 = atomicAdd(a.tile_counter, 1u);
         const unsigned int nt = __shfl_sync(P2S_FULL, t1, 0);   // the tile after this one
@@ -565,6 +576,21 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             stg[96 + lane] = e_out;
             reinterpret_cast<uint32_t *>(stg + 128)[lane] = ids;
             reinterpret_cast<uint8_t *>(stg + 144)[lane] = (uint8_t)nexcl;
+            if (a.bulk_out) {
+                // TMA stores: four bulk copies per tile (768 + 256 + 128 + 32 bytes) issued by one lane; the copy engine
+                // moves them while the warp goes on — no store instructions, whole tile records on the link
+                fence_proxy_async();                             // my staging writes, visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t s0 = smem_u32(stg);
+                    bulk_s2g(a.out_Q + (long long)tile * 96, s0, 768u);
+                    bulk_s2g(a.out_err + (long long)tile * 32, s0 + 768u, 256u);
+                    bulk_s2g(a.out_mask + (long long)tile * 32, s0 + 1024u, 128u);
+                    bulk_s2g(a.out_nexcl + (long long)tile * 32, s0 + 1152u, 32u);
+                    bulk_commit();
+                }
+                __syncwarp();
+            } else {
             __syncwarp();
             const float4 *src = reinterpret_cast<const float4 *>(stg);
             float4 *dq = reinterpret_cast<float4 *>(a.out_Q + (long long)tile * 96);
@@ -577,6 +603,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             if (lane < 8) dm[lane] = src[64 + lane];
             else if (lane < 10) dn[lane - 8] = src[72 + lane - 8];
             __syncwarp();
+            }
         } else if (active) {
             double *q = a.out_Q + u * 3;
             q[0] = qx; q[1] = qy; q[2] = qz;
@@ -633,6 +660,10 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         }
     }
 
+    if (a.bulk_out) {                                           // every bulk store of this warp has been performed
+        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+    }
     // ---- push path: publish "every output of this launch is visible" to the consumer (possibly a peer GPU) ------
     if (a.done_flag != nullptr) {
         __syncthreads();                                       // the CTA's stores are all issued
@@ -814,6 +845,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.stats = L.stats; a.tile_counter = L.tile_counter;
     a.vec_out = ((((uintptr_t)L.out_Q | (uintptr_t)L.out_err | (uintptr_t)L.out_nexcl | (uintptr_t)L.out_mask) & 15u) == 0) ? 1 : 0;
+    a.bulk_out = (a.vec_out && L.bulk_out) ? 1 : 0;
     a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
     a.err_word = L.err_word;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;

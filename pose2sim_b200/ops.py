@@ -98,6 +98,10 @@ class Engine:
     def set_assoc_team(self, warps_per_frame):
         _lib.check(self.h, self.lib.p2s_set_assoc_team(self.h, int(warps_per_frame)))
 
+    def set_output_mode(self, mode):
+        """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`)."""
+        _lib.check(self.h, self.lib.p2s_set_output_mode(self.h, {"vector": 0, "bulk": 1}.get(mode, mode)))
+
     def set_chunk_units(self, units):
         _lib.check(self.h, self.lib.p2s_set_chunk_units(self.h, int(units)))
 

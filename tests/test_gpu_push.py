@@ -37,6 +37,34 @@ def test_push_equals_plain_path(engine, F):
         pg.close()
 
 
+@pytest.mark.parametrize("F", [64, 37])
+def test_bulk_store_mode_equals_vector_stores(engine, F):
+    """`p2s_set_output_mode(1)`: full tiles leave by cp.async.bulk (TMA) stores — same bytes as the vector stores."""
+    import torch
+    wl, (x, y, lik) = _planes(F)
+    ref = engine.triangulate_planes(x, y, lik, wl["P"], 0.3, 15.0, 2)
+    torch.cuda.synchronize()
+    engine.set_output_mode("bulk")
+    try:
+        got = engine.triangulate_planes(x, y, lik, wl["P"], 0.3, 15.0, 2)
+        pg = sharding.PeerGather(engine, [x.shape[0]], n_buffers=2)
+        try:
+            for step in range(3):
+                engine.triangulate_planes_push(x, y, lik, wl["P"], 0.3, 15.0, 2, **pg.push_args(step))
+                pg.collect(step)
+            torch.cuda.synchronize()
+            pushed = pg.views(0)[0]
+            for k in ("Q", "err", "mask", "nexcl"):
+                for t in (got[k], pushed[k]):
+                    a, b = t.cpu().numpy(), ref[k].cpu().numpy()
+                    assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
+            assert engine.peer_error() == 0
+        finally:
+            pg.close()
+    finally:
+        engine.set_output_mode("vector")
+
+
 def test_producer_times_out_instead_of_hanging(engine):
     """A buffer that is never released: the kernel gives up after its bounded wait and reports it."""
     import torch

@@ -25,6 +25,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     eng = ops.get_engine(local)
+    eng.set_output_mode(os.environ.get("P2S_OUTPUT_MODE", "vector"))
     F = 20_000 + 1000 * rank                                     # ragged blocks
     wl = synth.make_triangulation_workload(8, F, 1, 26, seed=202 + rank, lik_thr=None, frame0=rank * 100_000)
     x, y, lik = (torch.from_numpy(wl[k]).to(dev) for k in ("x", "y", "lik"))
@@ -59,7 +60,7 @@ def main():
     pg.close()
     if rank == 0:
         line = {"tool": "push_multi_gpu", "world": world, "steps": 6, "units_per_rank": units, "mismatching_planes": bad,
-                "peer_error_bits": int(err.item()), "ok": bad == 0 and int(err.item()) == 0}
+                "peer_error_bits": int(err.item()), "output_mode": os.environ.get("P2S_OUTPUT_MODE", "vector"), "ok": bad == 0 and int(err.item()) == 0}
         print(json.dumps(line), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(line, open(os.path.join(ROOT, "gpurun_out", "push_multi_gpu.json"), "w"))
