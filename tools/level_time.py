@@ -1,5 +1,8 @@
-import sys, json
-sys.path.insert(0,'/root/repo')
+#!/usr/bin/env python
+"""Kernel time of cfg2 by exclusion level: all levels, level 0 only (threshold 1e9), levels 0-1 and 0-2 (min_cameras 7 / 6).
+python tools/level_time.py"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from pose2sim_b200 import ops, synth
 eng=ops.get_engine(0)

@@ -1,5 +1,8 @@
-import sys, os, time
-sys.path.insert(0,'/root/repo')
+#!/usr/bin/env python
+"""Device-side timeline of the p2s_triangulate_host pipeline on cfg2 (P2S_TRACE=1): per chunk, when its H2D copies,
+its kernel and its D2H copies finished.  python tools/trace_e2e.py"""
+import os, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pose2sim_b200 import ops, synth
 wl=synth.make_triangulation_workload(8,100000,1,26,seed=202,lik_thr=None)
