@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-side timeline of the p2s_triangulate_host pipeline on cfg2 (P2S_TRACE=1): per chunk, when its H2D copies,
 its kernel and its D2H copies finished.  python tools/trace_e2e.py"""
-import os, sys, os, time
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pose2sim_b200 import ops, synth
