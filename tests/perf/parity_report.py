@@ -3,7 +3,7 @@
 through `p2s_triangulate_host` against the plain-C oracle (oracle/p2s_oracle.c, pinned by the reference's golden
 vectors) on EVERY unit of a BASELINE workload.
 
-    python tests/perf/parity_report.py [cfg2|cfg3] [frames]
+    python tests/perf/parity_report.py [cfg2|cfg3|cfg5-<cams>] [frames]      (cfg5-C: min_cameras = max(2, C - 4), seed 500 + C)
 
 One JSON line (also gpurun_out/parity_report.jsonl): max / percentiles of |dQ| (m) and |d err| (px), units whose
 nb_cams_excluded / id_excluded_cams / NaN-ness differ, and how many of those sit inside the eps-band
@@ -25,7 +25,12 @@ def main():
     import c_oracle as co
     from pose2sim_b200 import ops, synth
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-    cfg = bench.WORKLOADS[name]
+    if name.startswith("cfg5-"):
+        Cn = int(name[5:])
+        cfg = dict(C=Cn, F=2000, N=1, K=26, seed=500 + Cn, thr=15.0, min_cams=max(2, Cn - 4), lik_thr=0.3,
+                   name=f"cfg5 sweep point: synthetic {Cn} cams x HALPE_26, min_cameras = {max(2, Cn - 4)}")
+    else:
+        cfg = bench.WORKLOADS[name]
     F = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["F"]
     wl = synth.make_triangulation_workload(cfg["C"], F, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=None)
     eng = ops.get_engine(0)
