@@ -10,7 +10,9 @@ owns its own frame block (weak scaling, no data-path collective) and the packed 
 gathered to rank 0 over NCCL inside the timed region (north_star's "final gather").
 
 Keys beyond the base contract: `roofline` (FP64 CUDA-core bound, plus the HBM view), `cpu_baseline`
-(the oracle port on this box's host cores), `e2e` (host buffers through the C ABI, copies timed).
+(the oracle port on this box's host cores), `e2e` (host buffers through the C ABI, copies timed; `link_bound_ms` =
+the same bytes as plain pinned copies), `parity` (this run's CUDA results on the CPU leg's sample against the
+plain-C oracle: max |dQ|, max |d err|, differing decisions and how many of them sit in the eps-band).
 """
 import argparse
 import json
@@ -157,15 +159,33 @@ class PythonPort:
         self.pool.terminate()
 
 
-def c_port_rate(wl, cfg, n_units):
+def c_port_rate(wl, cfg, n_units, want_results=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle as co
     n_units = min(n_units, wl["x"].shape[0])
     co.triangulate_units(wl["x"][:2000], wl["y"][:2000], wl["lik"][:2000], wl["P"], cfg["thr"], cfg["min_cams"])
     t0 = time.perf_counter()
-    co.triangulate_units(wl["x"][:n_units], wl["y"][:n_units], wl["lik"][:n_units], wl["P"], cfg["thr"], cfg["min_cams"])
+    res = co.triangulate_units(wl["x"][:n_units], wl["y"][:n_units], wl["lik"][:n_units], wl["P"], cfg["thr"], cfg["min_cams"])
     dt = time.perf_counter() - t0
+    if want_results:
+        return n_units / dt, co.max_threads(), n_units, res
     return n_units / dt, co.max_threads(), n_units
+
+
+def parity_block(eng, cwl, cfg, n_units, oracle_res, eps=1e-6):
+    """Parity of THIS run: the CUDA path through the host entry point on the CPU leg's sample against
+    the plain-C oracle's results for the same units (the oracle is the checker here, never the thing measured)."""
+    Q, err, nexcl, mask = oracle_res[:4]
+    out = eng.triangulate_host(cwl["x"][:n_units], cwl["y"][:n_units], cwl["lik"][:n_units], cwl["P"], None,
+                               cfg["thr"], cfg["min_cams"], want_stats=False)
+    nan_diff = np.isnan(Q).any(axis=1) != np.isnan(out["Q"]).any(axis=1)
+    dec = (nexcl != out["nexcl"]) | (mask != out["mask"]) | nan_diff
+    ok = ~np.isnan(Q).any(axis=1) & ~np.isnan(out["Q"]).any(axis=1) & ~dec
+    in_band = dec & (np.abs(np.nan_to_num(err, nan=np.inf) - cfg["thr"]) < eps)
+    return {"units": int(n_units), "oracle": "oracle/p2s_oracle.c", "tolerance_m": 1e-6, "eps_px": eps,
+            "max_abs_dQ_m": float(np.abs(Q[ok] - out["Q"][ok]).max(initial=0.0)),
+            "max_abs_derr_px": float(np.abs(err[ok] - out["err"][ok]).max(initial=0.0)),
+            "units_with_differing_decision": int(dec.sum()), "of_which_inside_eps_band": int(in_band.sum())}
 
 
 def run_reference_arm(args, cfg, rank, world):
@@ -486,7 +506,8 @@ def main():
             n_units = int(min(cwl["x"].shape[0], max(port.cores * 64, 12.0 * cn / cdt)))    # ~12 s of CPU work
             dt, n = port.run(n_units)
             port.close()
-            c_rate, c_threads, c_n = c_port_rate(cwl, cfg, 52_000)
+            c_rate, c_threads, c_n, c_res = c_port_rate(cwl, cfg, 52_000, want_results=True)
+            line["parity"] = parity_block(eng, cwl, cfg, c_n, c_res)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
                                     "sample": f"first {n} units (of {U}) of the same workload, NumPy per-unit port of "
                                               f"triangulation_from_best_cameras (oracle/p2s_oracle.py), one process per core",
