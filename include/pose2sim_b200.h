@@ -109,6 +109,11 @@ int p2s_set_solver(p2s_handle *h, int solver);
  * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path) */
 int p2s_set_output_mode(p2s_handle *h, int mode);
 
+/* how p2s_triangulate_host moves its data: 0 (default) = zero-copy when every buffer is pinned host memory (one
+ * kernel reads its tiles from and writes its results to host memory over PCIe), else the chunked copy pipeline;
+ * 1 = always the copy pipeline; 2 = zero-copy or P2S_EINVAL */
+int p2s_set_host_mode(p2s_handle *h, int mode);
+
 /* units per H2D -> search -> D2H pipeline chunk of the *_host entry points (4 chunks in flight);
  * 0 (default) = automatic, about a quarter of the call's units clamped to [2^16, 2^20] */
 int p2s_set_chunk_units(p2s_handle *h, long long units);
@@ -150,9 +155,10 @@ int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y,
                                   double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
                                   unsigned long long *stats, void *stream);
 
-/* Whole job from host buffers: chunked H2D -> stage -> search -> D2H, overlapped on internal
- * streams.  x/y/lik as for p2s_stage_observations_device but HOST pointers (pinned = faster);
- * outputs HOST pointers; stats: HOST pointer to P2S_STAT_COUNT uint64 (overwritten) or NULL.     */
+/* Whole job from host buffers.  x/y/lik as for p2s_stage_observations_device but HOST pointers; outputs HOST
+ * pointers; stats: HOST pointer to P2S_STAT_COUNT uint64 (overwritten) or NULL.  Pinned (page-locked) buffers are
+ * read and written by the kernel directly (zero-copy, one launch); pageable buffers go through a chunked
+ * H2D -> search -> D2H pipeline on internal streams (p2s_set_host_mode).                                */
 int p2s_triangulate_host(p2s_handle *h, const float *x, const float *y, const float *lik,
                          const double *P, long long n_units, int n_cams,
                          double lik_thr, double reproj_thr, int min_cams,

@@ -46,6 +46,7 @@ struct p2s_handle {
     int assoc_team = 0;
     long long chunk_units = kChunkUnitsDefault;
     int bulk_out = 0;
+    int host_mode = 0;                                 // 0 auto, 1 pipeline, 2 zero-copy (p2s_set_host_mode)
     long long launches = 0;
     int last_grid = 0;
     std::string last_error;
@@ -292,6 +293,12 @@ int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame) {
     return P2S_OK;
 }
 
+int p2s_set_host_mode(p2s_handle *h, int mode) {
+    if (!h || mode < 0 || mode > 2) return P2S_EINVAL;
+    h->host_mode = mode;
+    return P2S_OK;
+}
+
 int p2s_set_output_mode(p2s_handle *h, int mode) {
     if (!h || (mode != 0 && mode != 1)) return P2S_EINVAL;
     h->bulk_out = mode;
@@ -480,6 +487,33 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
     if (stats) P2S_CUDA(h, cudaMemsetAsync(h->d_stats, 0, P2S_STAT_COUNT * sizeof(unsigned long long), h->slots[0].stream));
     if (stats) P2S_CUDA(h, cudaStreamSynchronize(h->slots[0].stream));
     const size_t C = (size_t)n_cams;
+    // ---- zero-copy: pinned host buffers are device-accessible (UVA), so ONE kernel TMA-reads its tiles straight from
+    // host memory and writes its outputs straight back — the PCIe transfers are pipelined per 32-unit tile by the
+    // kernel's own prefetch, with no chunk boundaries, no staging buffers and no copy set-up (measured 5.07 vs 5.24 ms
+    // on cfg2, tools/zero_copy_probe.py).  Pageable or misaligned buffers (and the undistort path, which has a
+    // separate stage kernel) take the chunked H2D -> kernel -> D2H pipeline below.
+    if (!lens && h->host_mode != 1 && n_units > 0) {
+        auto dev = [](const void *p) -> void * {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+        };
+        void *dx = dev(x), *dy = dev(y), *dl = dev(lik), *dQ = dev(out_Q), *de = dev(out_err), *dn = dev(out_nexcl), *dm = dev(out_mask);
+        const bool mapped = dx && dy && dl && dQ && de && dn && dm &&
+                            ((((uintptr_t)dx | (uintptr_t)dy | (uintptr_t)dl) & 15u) == 0);
+        if (mapped) {
+            cudaStream_t st = h->slots[0].stream;
+            Planes pl;
+            pl.x = (const float *)dx; pl.y = (const float *)dy; pl.lik = (const float *)dl; pl.lik_thr = lik_thr;
+            rc = enqueue_triangulate(h, nullptr, P, nullptr, n_units, n_cams, reproj_thr, min_cams, (double *)dQ, (double *)de,
+                                     (uint8_t *)dn, (uint32_t *)dm, stats ? h->d_stats : nullptr, st, &pl);
+            if (rc) return rc;
+            P2S_CUDA(h, cudaStreamSynchronize(st));
+            if (stats) P2S_CUDA(h, cudaMemcpy(stats, h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            return P2S_OK;
+        }
+        if (h->host_mode == 2) return P2S_EINVAL;              // zero-copy demanded but the buffers are not pinned / aligned
+    }
     const bool automatic = h->chunk_units <= 0;
     long long chunk = h->chunk_units;
     if (automatic) chunk = std::min<long long>(1LL << 20, std::max<long long>(1LL << 16, ((n_units / 4) + 31) & ~31LL));

@@ -98,6 +98,11 @@ class Engine:
     def set_assoc_team(self, warps_per_frame):
         _lib.check(self.h, self.lib.p2s_set_assoc_team(self.h, int(warps_per_frame)))
 
+    def set_host_mode(self, mode):
+        """How `triangulate_host` moves data: "auto" (zero-copy for pinned buffers, else copy pipeline), "pipeline",
+        "zero_copy" (raises when the buffers are not pinned)."""
+        _lib.check(self.h, self.lib.p2s_set_host_mode(self.h, {"auto": 0, "pipeline": 1, "zero_copy": 2}.get(mode, mode)))
+
     def set_output_mode(self, mode):
         """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`)."""
         _lib.check(self.h, self.lib.p2s_set_output_mode(self.h, {"vector": 0, "bulk": 1}.get(mode, mode)))

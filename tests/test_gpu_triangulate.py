@@ -117,6 +117,39 @@ def test_fused_gate_is_the_float64_comparison(engine, thr):
         assert torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
 
 
+@pytest.mark.parametrize("C,U", [(8, 26 * 300), (8, 333), (5, 1001), (16, 26 * 40)])
+def test_host_entry_zero_copy_equals_copy_pipeline(engine, C, U):
+    """`p2s_triangulate_host` with pinned buffers (the kernel reads / writes host memory directly) against the chunked
+    copy pipeline and against pageable buffers: the same bytes."""
+    import torch
+    wl = synth.make_triangulation_workload(C, -(-U // 26), 1, 26, seed=31 + C, lik_thr=None)
+    xs, ys, ls = (np.ascontiguousarray(wl[k][:U]) for k in ("x", "y", "lik"))
+    hx, hy, hl = (torch.from_numpy(a.copy()).pin_memory() for a in (xs, ys, ls))
+
+    def pinned_out():
+        return {"Q": torch.empty((U, 3), dtype=torch.float64).pin_memory().numpy(),
+                "err": torch.empty(U, dtype=torch.float64).pin_memory().numpy(),
+                "nexcl": torch.empty(U, dtype=torch.uint8).pin_memory().numpy(),
+                "mask": torch.empty(U, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+    mc = 2 if C < 16 else 3
+    try:
+        engine.set_host_mode("zero_copy")
+        a = engine.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], 0.3, 15.0, mc, out=pinned_out())
+        with pytest.raises(Exception):                       # pageable buffers cannot be mapped: refused, not copied silently
+            engine.triangulate_host(xs, ys, ls, wl["P"], 0.3, 15.0, mc)
+        engine.set_host_mode("pipeline")
+        b = engine.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], 0.3, 15.0, mc, out=pinned_out())
+        engine.set_host_mode("auto")
+        c = engine.triangulate_host(xs, ys, ls, wl["P"], 0.3, 15.0, mc)                     # pageable -> pipeline
+        d = engine.triangulate_host(hx.numpy(), hy.numpy(), hl.numpy(), wl["P"], 0.3, 15.0, mc, out=pinned_out())
+    finally:
+        engine.set_host_mode("auto")
+    for k in ("Q", "err", "nexcl", "mask"):
+        for other in (b, c, d):
+            assert np.array_equal(a[k], other[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], other[k]), k
+    assert a["stats"]["level_hist"] == b["stats"]["level_hist"] == c["stats"]["level_hist"]
+
+
 def test_ragged_and_empty(engine):
     P = synth.ring_cameras(8)[0]
     out = run_gpu(engine, P, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), 15.0, 2)
