@@ -37,6 +37,49 @@ def make_trial(td, name, C, F, seed, demo_calib):
     return proj, synth_project.base_config(proj)
 
 
+def make_assoc_trial(td, name, C, F, persons, seed):
+    """Every camera lists `persons` people in a random order, all 26 keypoints each (JSON id order)."""
+    from pose2sim_b200 import synth, synth_project
+    w = synth.make_multi_person_workload(C, F, persons, seed=seed, p_missing=0.1, p_nan=0.0)
+    calib_text, cams, _ = synth_project.ring_calibration_toml(C)
+    present = np.arange(persons)[None, None, :] < w["count"][:, :, None]
+    proj = synth_project.write_project(os.path.join(td, name), calib_text, cams, w["obs"], present=present)
+    return proj
+
+
+def bench_association(td, out):
+    """`associate_all(config)` wall time, single-person (ordered combination search) and multi-person (ray affinity +
+    SVT matching) modes, on an 8-camera x 3-person x 1000-frame trial on disk (8000 JSON files in, 8000 out)."""
+    import shutil
+    from pose2sim_b200 import ops, personAssociation as pa, synth_project
+    C, F, NP = 8, 1000, 3
+    proj = make_assoc_trial(td, "assoc_8cams_3persons_1000frames", C, F, NP, 404)
+    ops.get_engine(0)
+    for multi in (False, True):
+        cfg = synth_project.base_config(proj, multi_person=multi)
+        os.chdir(proj)
+        for rep in range(2):                                   # second pass is the timed one
+            shutil.rmtree(os.path.join(proj, "pose-associated"), ignore_errors=True)
+            t0 = time.perf_counter()
+            st = pa.stage_project(cfg)
+            t1 = time.perf_counter()
+            if multi:
+                res = pa.solve_frames_multi_person(st)
+                t2 = time.perf_counter()
+                pa.write_outputs_multi_person(st, res)
+            else:
+                res = pa.solve_frames(st)
+                t2 = time.perf_counter()
+                pa.write_outputs(st, res)
+            t3 = time.perf_counter()
+        line = {"bench": "dropin_associate_all", "trial": os.path.basename(proj), "multi_person": multi, "cams": C, "frames": F,
+                "persons_per_cam": NP, "json_files": C * F, "impl": "pose2sim_b200", "stage_s": t1 - t0, "device_call_s": t2 - t1,
+                "write_s": t3 - t2, "total_s": t3 - t0, "frames_per_s": F / (t3 - t0)}
+        print(json.dumps(line), flush=True)
+        out.append(line)
+        os.chdir(ROOT)
+
+
 def main():
     use_ref = "--reference" in sys.argv
     logging.getLogger().setLevel(logging.ERROR)
@@ -77,6 +120,8 @@ def main():
             print(json.dumps(line), flush=True)
             out.append(line)
             os.chdir(ROOT)
+        if not use_ref:
+            bench_association(td, out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "dropin_bench.jsonl"), "a") as f:
         for line in out:
