@@ -16,7 +16,7 @@ from . import _lib
 from . import staging as _stg
 
 
-def stage_detections(parsed):
+def stage_detections(parsed, check_total=True, want_length=False):
     """parsed[f][c] = decoded JSON (or None).  Returns obs [F, C, NP, 3 J] float32, count [F, C] int32 and the
     number of values float32 cannot hold exactly.  Detections are `read_json`'s lists (people with >= 3
     values, personAssociation.py:260-274).  All keypoint lists must have the same length: the reference
@@ -40,10 +40,37 @@ def stage_detections(parsed):
             for p, kp in enumerate(cam):
                 obs64[f, c, p] = [np.nan if v is None else v for v in kp]
     n_max = int(count.sum(axis=1).max(initial=0))
+    if check_total and n_max > _lib.P2S_MAX_DETECTIONS:
+        raise ValueError(f"{n_max} detections in one frame: the device matching handles at most "
+                         f"{_lib.P2S_MAX_DETECTIONS} per frame")
+    if want_length:                                             # block of a larger trial (merge_staged)
+        return obs64.astype(np.float32), count, _stg.float32_inexact(obs64), (L if count.any() else None)
+    return obs64.astype(np.float32), count, _stg.float32_inexact(obs64)
+
+
+def merge_staged(parts):
+    """Blocks of `stage_detections(..., check_total=False, want_length=True)` of consecutive frame ranges -> what one
+    call over all frames returns (same checks, same padding)."""
+    lengths = sorted({p[3] for p in parts if p[3] is not None})
+    if len(lengths) > 1:
+        raise ValueError(f"pose_keypoints_2d lists of different lengths {lengths}: the reference cannot "
+                         f"stack them either (personAssociation.py:378)")
+    L = lengths[0] if lengths else 3
+    NP = max([p[0].shape[2] for p in parts if p[3] is not None] + [1])
+    blocks = []
+    for obs, count, _, n_values in parts:
+        F, C = count.shape
+        full = np.full((F, C, NP, L), np.nan, np.float32)
+        if n_values is not None:
+            full[:, :, :obs.shape[2], :] = obs
+        blocks.append(full)
+    obs = np.concatenate(blocks) if blocks else np.zeros((0, 0, NP, L), np.float32)
+    count = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, 0), np.int32)
+    n_max = int(count.sum(axis=1).max(initial=0))
     if n_max > _lib.P2S_MAX_DETECTIONS:
         raise ValueError(f"{n_max} detections in one frame: the device matching handles at most "
                          f"{_lib.P2S_MAX_DETECTIONS} per frame")
-    return obs64.astype(np.float32), count, _stg.float32_inexact(obs64)
+    return obs, count, int(sum(p[2] for p in parts))
 
 
 def proposals_from_rows(rows, min_cams):

@@ -46,7 +46,60 @@ def read_settings(config_dict):
 
 class StagedAssociation:
     __slots__ = ("settings", "calib_file", "P", "cam_dirs", "dirs", "table", "f_range", "n_cams",
-                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact")
+                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact", "workers", "mp_staged")
+
+
+# ---- file I/O on a process pool -------------------------------------------------------------------------------------
+# Reading 8 cameras x N frames of OpenPose JSON with Python's `json` and writing them back is what the stage costs once
+# the search runs on the GPU (1 s per 1000 frames against ~1 ms of device time).  Frames are independent, so large
+# trials are cut into contiguous frame blocks that worker processes (fork) parse into the staging arrays and, after the
+# device call, re-read and rewrite.  The workers never touch CUDA.  P2S_HOST_WORKERS=<n> forces the count (1 = off).
+def host_workers(n_files, world=1):
+    forced = os.environ.get("P2S_HOST_WORKERS")
+    if forced is not None:
+        n = int(forced)
+    elif world > 1:
+        n = 1                                       # a torchrun job already spreads the frames over its ranks
+    else:
+        n = min(len(os.sched_getaffinity(0)), n_files // 512)
+    return n if n >= 2 else 0
+
+
+def _blocks(n_rows, n_workers):
+    n_blocks = min(n_rows, 2 * n_workers)
+    edges = [n_rows * i // n_blocks for i in range(n_blocks + 1)]
+    return [(a, b) for a, b in zip(edges, edges[1:]) if b > a]
+
+
+def _pool_map(fn, jobs, n_workers):
+    import multiprocessing
+    with multiprocessing.get_context("fork").Pool(n_workers) as pool:
+        return pool.map(fn, jobs, chunksize=1)
+
+
+def _stage_block(job):
+    pose_dir, cam_dirs, rows, kid, multi = job
+    if multi:
+        from . import multi_person as mp
+        parsed = [[_stg.load_json(os.path.join(pose_dir, cam_dirs[c], names[c])) for c in range(len(cam_dirs))] for names in rows]
+        obs, count, inexact, n_values = mp.stage_detections(parsed, check_total=False, want_length=True)
+        return obs, count, inexact, n_values
+    obs, count, _ = _stg.stage_association(pose_dir, cam_dirs, rows, kid, _lib.P2S_MAX_PERSONS)
+    return obs, count
+
+
+def _rewrite_block(job):
+    pose_dir, tracked_dir, cam_dirs, rows, proposals = job
+    for names, prop in zip(rows, proposals):
+        source = [_stg.load_json(os.path.join(pose_dir, cam_dirs[c], names[c])) for c in range(len(cam_dirs))]
+        tracked = [os.path.join(tracked_dir, cam_dirs[c], names[c]) for c in range(len(cam_dirs))]
+        rewrite_frame(tracked, source, prop)
+    return len(rows)
+
+
+def _rewrite_parallel(st, proposals):
+    jobs = [(st.dirs.pose_dir, st.dirs.tracked_dir, st.cam_dirs, st.table[a:b], proposals[a:b]) for a, b in _blocks(len(st.table), st.workers)]
+    _pool_map(_rewrite_block, jobs, st.workers)
 
 
 def stage_project(config_dict, rank=0, world=1):
@@ -99,13 +152,26 @@ def stage_project(config_dict, rank=0, world=1):
         from . import sharding
         a, b = sharding.frame_block(len(st.table), rank, world)
         st.table = st.table[a:b]
+    st.workers, st.mp_staged = host_workers(len(st.table) * n_cams, world), None
     # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
-    if s["multi_person"]:
+    if st.workers:
+        jobs = [(dirs.pose_dir, cam_dirs, st.table[a:b], kid, bool(s["multi_person"])) for a, b in _blocks(len(st.table), st.workers)]
+        parts = _pool_map(_stage_block, jobs, st.workers)
+        st.parsed = None                                      # the rewrite re-reads its sources in the workers
+        if s["multi_person"]:
+            from . import multi_person as mp
+            st.mp_staged = mp.merge_staged(parts)
+            st.obs, st.count, st.inexact = None, None, 0
+            return st
+        obs = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, n_cams, _lib.P2S_MAX_PERSONS, 4))
+        st.count = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, n_cams), np.int32)
+    elif s["multi_person"]:
         st.parsed = [[_stg.load_json(os.path.join(dirs.pose_dir, cam_dirs[c], names[c])) for c in range(n_cams)]
                      for names in st.table]
         st.obs, st.count, st.inexact = None, None, 0
         return st
-    obs, st.count, st.parsed = _stg.stage_association(dirs.pose_dir, cam_dirs, st.table, kid, _lib.P2S_MAX_PERSONS)
+    else:
+        obs, st.count, st.parsed = _stg.stage_association(dirs.pose_dir, cam_dirs, st.table, kid, _lib.P2S_MAX_PERSONS)
     st.inexact = _stg.float32_inexact(obs[..., :3])
     if st.inexact:
         logging.warning(f"{st.inexact} 2D values are not exactly representable in float32 and were rounded for the "
@@ -130,7 +196,7 @@ def solve_frames(st, engine=None, device=0):
 def stage_multi_person(st):
     """personAssociation.py:783-790 for every frame -> obs[F, C, NP, 3 J], count[F, C], camera models."""
     from . import multi_person as mp
-    obs, count, inexact = mp.stage_detections(st.parsed)
+    obs, count, inexact = st.mp_staged if st.mp_staged is not None else mp.stage_detections(st.parsed)
     if inexact:
         logging.warning(f"{inexact} 2D values are not exactly representable in float32 and were rounded for the "
                         f"device staging layout.")
@@ -175,17 +241,23 @@ def write_outputs(st, res, log=True):
         if not np.isinf(e):
             errors.append(float(e))
         cams_off.append(int(np.count_nonzero(np.isnan(comb))))
-        tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
-        rewrite_frame(tracked, st.parsed[fi], [comb])
+        if st.parsed is not None:
+            tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
+            rewrite_frame(tracked, st.parsed[fi], [comb])
+    if st.parsed is None:
+        _rewrite_parallel(st, [[res["comb"][fi]] for fi in range(len(st.table))])
     if log:
         log_recap(st, errors, cams_off)
     return {"error": errors, "cameras_off": cams_off}
 
 
 def write_outputs_multi_person(st, proposals, log=True):
-    for fi, names in enumerate(st.table):
-        tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
-        rewrite_frame(tracked, st.parsed[fi], proposals[fi])
+    if st.parsed is None:
+        _rewrite_parallel(st, proposals)
+    else:
+        for fi, names in enumerate(st.table):
+            tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
+            rewrite_frame(tracked, st.parsed[fi], proposals[fi])
     if not log:
         return
     s = st.settings

@@ -102,7 +102,11 @@ def test_refuses_unbuilt_modes(golden, tmp_path):
         tri.stage_project(cfg)
 
 
-def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
+@pytest.mark.parametrize("workers", [None, "3"])
+def test_association_host_pipeline_matches_reference_json(golden, tmp_path, monkeypatch, workers):
+    """workers = "3": the file I/O of the stage runs on a process pool (frame blocks parsed and rewritten by workers)."""
+    if workers:
+        monkeypatch.setenv("P2S_HOST_WORKERS", workers)
     g = golden("e2e_assoc_single.npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_assoc")
     with in_dir(proj):
@@ -123,12 +127,15 @@ def test_association_host_pipeline_matches_reference_json(golden, tmp_path):
     assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
 
 
-def test_multi_person_association_matches_reference_json(golden, tmp_path):
+@pytest.mark.parametrize("workers", [None, "3"])
+def test_multi_person_association_matches_reference_json(golden, tmp_path, monkeypatch, workers):
     """Host half of `associate_all` with multi_person = true (staging, proposal bookkeeping, JSON rewrite)
     with the NumPy oracle standing in for the device call: same people, in the same order, as the
     reference wrote (tests/golden/e2e_assoc_multi.npz).  This also pins oracle/p2s_oracle_mp.py."""
     import p2s_oracle_mp as omp
     from pose2sim_b200 import multi_person as mp
+    if workers:
+        monkeypatch.setenv("P2S_HOST_WORKERS", workers)
     g = golden("e2e_assoc_multi.npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_massoc")
     with in_dir(proj):
