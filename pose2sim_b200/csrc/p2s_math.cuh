@@ -105,7 +105,11 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
     double lam = 0.0, lo = 0.0;
     double x0 = nan64(), x1 = x0, x2 = x0;
     int it = 0;
-#pragma unroll 1
+#ifndef P2S_SOLVER_UNROLL
+#define P2S_SOLVER_UNROLL 1
+#endif
+    constexpr int kUnroll = P2S_SOLVER_UNROLL;                 // A/B switch (tools/kernel_ab.py); 1 = rolled
+#pragma unroll kUnroll
     for (; it < 24; ++it) {
         const double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
         const double r0 = rcp_fast(a00);
