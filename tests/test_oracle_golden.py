@@ -171,3 +171,30 @@ def test_undistort_mode_units(golden):
     assert np.array_equal(n, g["unit_nexcl"][sub]) and np.array_equal(m, g["unit_mask"][sub])
     assert np.allclose(q, g["unit_Q"][sub], atol=Q_TOL, rtol=0, equal_nan=True)
     assert np.allclose(e, g["unit_err"][sub], atol=E_TOL, rtol=0, equal_nan=True)
+
+
+def test_multi_person_oracle_reproduces_reference_frames(golden):
+    """oracle/p2s_oracle_mp.py (and the product's integer bookkeeping `multi_person.proposals_from_rows`) against
+    146 random frames matched by the live reference (oracle/make_golden_mp.py): thresholded affinity within 1e-9,
+    proposals identical — including empty frames, single-view frames and all-NaN detections."""
+    import p2s_oracle_mp as omp
+    from pose2sim_b200 import multi_person as mp
+    g = golden("mp_random_frames.npz")
+    worst = 0.0
+    for i in range(int(g["n"])):
+        p = f"m{i}_"
+        obs, count = g[p + "obs"], g[p + "count"]
+        d_max, min_aff, min_cams = g[p + "params"]
+        models = [{"K": K, "R": R, "T": T} for K, R, T in zip(g[p + "K"], g[p + "R"], g[p + "T"])]
+        det = [[obs[c, q].astype(float) for q in range(count[c])] for c in range(len(count))]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            aff, cum = omp.frame_affinity(det, omp.camera_ray_params(models), float(d_max), float(min_aff))
+            prop = omp.proposals_from_affinity(aff, cum, int(min_cams))
+        ref_aff, ref_prop = g[p + "affinity"], g[p + "proposals"]
+        assert aff.shape == ref_aff.shape, i
+        worst = max(worst, float(np.abs(aff - ref_aff).max(initial=0.0)))
+        assert np.array_equal(np.asarray(prop, float).reshape(-1, len(count)), ref_prop, equal_nan=True), i
+        mine = mp.proposals_from_rows(omp.argmax_rows(aff, cum), int(min_cams))
+        assert np.array_equal(np.asarray(mine, float).reshape(-1, len(count)), ref_prop, equal_nan=True), i
+    assert worst < 1e-9, worst
