@@ -1,6 +1,11 @@
 #!/bin/bash
-# prints: kernel  registers  stack  spill-stores  spill-loads   from the *.ptxas.log files
+# prints: kernel  registers  stack  spill-stores  spill-loads   from the *.ptxas.log files of the last build
 cd "$(dirname "$0")"
-for f in *.ptxas.log; do
-  awk '/Compiling entry function/ {name=$6} /bytes stack frame/ {stack=$1; ss=$5; sl=$9} /Used [0-9]+ registers/ {printf "%-90s regs=%s stack=%s spill_st=%s spill_ld=%s\n", name, $5, stack, ss, sl}' "$f"
-done
+python3 - <<'PY'
+import glob, re
+for f in sorted(glob.glob("*.ptxas.log")):
+    t = open(f).read()
+    for m in re.finditer(r"Compiling entry function '([^']+)'.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                         r"(\d+) bytes spill loads\n.*?Used (\d+) registers", t):
+        print(f"{m.group(1)[:110]:110s} regs={m.group(5)} stack={m.group(2)} spill_st={m.group(3)} spill_ld={m.group(4)}")
+PY
