@@ -53,3 +53,34 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(_lib.P2SError) as ei:
         ops.Engine(0)
     assert ei.value.status == 2
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C program links against the library and calls the
+    entry points that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    src = tmp_path / "use.c"
+    src.write_text("""
+#include <stdio.h>
+#include "pose2sim_b200.h"
+int main(void) {
+    p2s_handle *h = 0;
+    int rc = p2s_create(-1, &h);                 /* invalid device: must fail with a status, not crash */
+    printf("%d %s %zu\\n", rc, p2s_status_string(rc), p2s_obs_bytes(10, 8));
+    return rc == P2S_OK;
+}
+""")
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lp2s_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code, rest = r.stdout.split(" ", 1)
+    assert int(code) == 2 and "no CPU fallback" in rest and rest.strip().endswith("1280")
