@@ -182,8 +182,9 @@ def parity_block(eng, cwl, cfg, n_units, oracle_res, eps=1e-6):
     dec = (nexcl != out["nexcl"]) | (mask != out["mask"]) | nan_diff
     ok = ~np.isnan(Q).any(axis=1) & ~np.isnan(out["Q"]).any(axis=1) & ~dec
     in_band = dec & (np.abs(np.nan_to_num(err, nan=np.inf) - cfg["thr"]) < eps)
+    dq = np.abs(Q[ok] - out["Q"][ok]).max(axis=1) if ok.any() else np.zeros(1)
     return {"units": int(n_units), "oracle": "oracle/p2s_oracle.c", "tolerance_m": 1e-6, "eps_px": eps,
-            "max_abs_dQ_m": float(np.abs(Q[ok] - out["Q"][ok]).max(initial=0.0)),
+            "max_abs_dQ_m": float(dq.max(initial=0.0)), "p99_abs_dQ_m": float(np.percentile(dq, 99)),
             "max_abs_derr_px": float(np.abs(err[ok] - out["err"][ok]).max(initial=0.0)),
             "units_with_differing_decision": int(dec.sum()), "of_which_inside_eps_band": int(in_band.sum())}
 
@@ -525,6 +526,8 @@ def main():
             c_rate, c_threads, c_n, c_res = c_port_rate(cwl, cfg, 52_000, want_results=True)
             line["parity"] = parity_block(eng, cwl, cfg, c_n, c_res)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
+                                    "value_per_core": n / dt / port.cores,
+                                    "full_config_wall_s_extrapolated": U / (n / dt),
                                     "sample": f"first {n} units (of {U}) of the same workload, NumPy per-unit port of "
                                               f"triangulation_from_best_cameras (oracle/p2s_oracle.py), one process per core",
                                     "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
