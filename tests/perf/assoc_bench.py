@@ -51,24 +51,30 @@ def main():
     import p2s_oracle as orc
     cheap = np.flatnonzero(st[:, 0] <= 300)[:20]
     bad = 0
+    t_np = time.perf_counter()
     for f in cheap:
         ob = [[wl["obs"][f, c, p].astype(float) for p in range(wl["count"][f, c])] for c in range(C)]
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             e, comb, q = orc.associate_frame(ob, list(wl["count"][f]), wl["P"], thr, lik_thr, mc)
         bad += int(not np.array_equal(ho["comb"][f].astype(int), np.nan_to_num(comb, nan=-1).astype(int)))
+    t_np = time.perf_counter() - t_np
     # full-size parity against the plain-C oracle (OpenMP) when the search space is small enough for it
     c_checked = c_bad = 0
-    c_maxdq = 0.0
+    c_maxdq, t_c = 0.0, None
     if Np ** C <= 10_000:
         import c_oracle as co
+        t_c = time.perf_counter()
         ce, cc, cq = co.associate_frames(wl["obs"], wl["count"], wl["P"], thr, lik_thr, mc)
+        t_c = time.perf_counter() - t_c
         c_checked = F
         c_bad = int((cc != ho["comb"]).any(axis=1).sum())
         both = np.isfinite(cq).all(axis=1) & np.isfinite(ho["Q"]).all(axis=1)
         c_maxdq = float(np.abs(cq[both] - ho["Q"][both]).max(initial=0.0))
     line = {"bench": "associate", "frames": F, "c_oracle_checked_frames": c_checked, "c_oracle_mismatching_frames": c_bad,
-            "c_oracle_max_abs_dQ_m": c_maxdq, "cams": C, "persons_per_cam": Np, "rows_per_frame_full": Np ** C,
+            "c_oracle_max_abs_dQ_m": c_maxdq,
+            "cpu_c_oracle_frames_per_s": (F / t_c) if t_c else None, "cpu_c_oracle_threads": (co.max_threads() if t_c else None),
+            "cpu_numpy_oracle_frames_per_s_1core_cheapest_frames": (len(cheap) / t_np) if len(cheap) else None, "cams": C, "persons_per_cam": Np, "rows_per_frame_full": Np ** C,
             "kernel_ms": ms, "frames_per_s": F / ms * 1e3, "rows_visited_per_frame": float(st[:, 0].mean()),
             "rows_per_s": float(st[:, 0].sum()) / ms * 1e3, "candidate_solves_per_s": float(st[:, 1].sum()) / ms * 1e3,
             "host_api_ms": host_ms, "host_api_frames_per_s": F / host_ms * 1e3,
