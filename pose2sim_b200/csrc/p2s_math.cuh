@@ -101,6 +101,14 @@ __device__ __forceinline__ void accumulate_camera(Sym4 &M, const double *Pc, dou
 //   * final step: once |dl| ||(A - lam I)^-1|| <= 1e-6, q(lam + dl) = q + dl w to O(1e-12) relative, so no
 //     factorisation is spent on confirming convergence.
 // Returns the number of factorisations used.
+// Iteration cap: almost every candidate needs two factorisations.  The exception is a smallest eigenvector whose last
+// component is almost zero (a solution "at infinity": two nearly parallel rays): the secular root then sits within
+// ~1e-3 relative of the pole, Newton keeps overshooting it and the safeguard degenerates into bisection — about forty
+// steps.  With the former cap of 24 such a candidate came back unconverged, its error was wrong, and a FAILED unit
+// could report another arg-min camera set than the reference (found by tests/perf/fuzz_parity.py).
+#ifndef P2S_SOLVER_MAX_ITERS
+#define P2S_SOLVER_MAX_ITERS 100
+#endif
 __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
     double lam = 0.0, lo = 0.0;
     double x0 = nan64(), x1 = x0, x2 = x0;
@@ -110,7 +118,7 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
 #endif
     constexpr int kUnroll = P2S_SOLVER_UNROLL;                 // A/B switch (tools/kernel_ab.py); 1 = rolled
 #pragma unroll kUnroll
-    for (; it < 24; ++it) {
+    for (; it < P2S_SOLVER_MAX_ITERS; ++it) {
         const double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
         const double r0 = rcp_fast(a00);
         const double l10 = M.m01 * r0, l20 = M.m02 * r0;

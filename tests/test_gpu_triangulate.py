@@ -150,6 +150,30 @@ def test_host_entry_zero_copy_equals_copy_pipeline(engine, C, U):
     assert a["stats"]["level_hist"] == b["stats"]["level_hist"] == c["stats"]["level_hist"]
 
 
+def test_solution_at_infinity_candidate(engine):
+    """Regression (found by tests/perf/fuzz_parity.py): excluding camera 1 leaves two nearly parallel rays, the smallest
+    eigenvector's last component is ~1e-3, so the secular root sits 5e-4 (relative) left of its pole and the safeguarded
+    Newton needs ~40 steps.  That candidate has the smallest error of its level; the unit fails (all errors above the
+    threshold) and must report cameras {1, 3} like the reference, not the runner-up {0, 3}."""
+    P = synth.ring_cameras(4)[0]
+    x = np.array([[443.91367, -123.24936, 654.57043, 1196.4896]], np.float32)
+    y = np.array([[192.70348, 483.57507, 624.25165, 710.6486]], np.float32)
+    w = np.array([[0.44252497, 0.8741765, 0.5474235, np.nan]], np.float32)
+    out = run_gpu(engine, P, x, y, w, 5.0, 2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), P, 5.0, 2)
+    assert int(mask[0]) == 0b1010 and int(nexcl[0]) == 2 and np.isnan(err[0])
+    assert int(out["mask"][0]) == 0b1010 and int(out["nexcl"][0]) == 2 and np.isnan(out["err"][0]) and np.isnan(out["Q"][0]).all()
+    # the same candidate as a passing unit: a huge threshold keeps its far-away point
+    out = run_gpu(engine, P, x, y, w, 100.0, 2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), P, 100.0, 2)
+    assert int(out["mask"][0]) == int(mask[0]) == 0b1010
+    assert np.allclose(out["Q"][0], Q[0], rtol=1e-7, atol=0) and abs(out["err"][0] - err[0]) < 1e-6
+
+
 def test_ragged_and_empty(engine):
     P = synth.ring_cameras(8)[0]
     out = run_gpu(engine, P, np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), np.zeros((0, 8), np.float32), 15.0, 2)
