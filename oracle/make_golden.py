@@ -193,8 +193,10 @@ def association_cases(ref, out):
     kpt = 18                                            # 'Neck' id in HALPE_26 JSON order
     n_kpt_json = 26
     idx = 0
+    # the last two configurations carry NaN and zero likelihoods / NaN coordinates of the tracked keypoint: such a
+    # detection stays ACTIVE in the reference (:215-216) and poisons every subset that keeps its camera
     for C, min_cams, thr, F in [(3, 2, 20.0, 120), (4, 2, 20.0, 200), (4, 3, 5.0, 120), (5, 2, 20.0, 120),
-                                (5, 3, 5.0, 80), (4, 2, 5.0, 120)]:
+                                (5, 3, 5.0, 80), (4, 2, 5.0, 120), (4, 2, 20.0, 100), (5, 1, 5.0, 60)]:
         P = synth.ring_cameras(C)[0]
         wl = synth.make_association_workload(C, F, 3, seed=404 + idx, p_out=0.15, p_low=0.0)
         obs = wl["obs"].copy()
@@ -202,6 +204,11 @@ def association_cases(ref, out):
         lowm = g.random(obs.shape[:3]) < 0.2
         obs[..., 2] = np.where(lowm, g.uniform(0.1, 0.3, obs.shape[:3]), obs[..., 2]).astype(np.float32)
         count = g.integers(0, 4, (F, C)).astype(np.int32)
+        if idx >= 6:
+            m = g.random(obs.shape[:3])
+            obs[..., 2][m < 0.06] = np.nan
+            obs[..., 2][(m >= 0.06) & (m < 0.10)] = 0.0
+            obs[..., 0][(m >= 0.10) & (m < 0.12)] = np.nan
         cfg = {"personAssociation": {"single_person": {"reproj_error_threshold_association": thr},
                                      "likelihood_threshold_association": 0.3},
                "triangulation": {"min_cameras_for_triangulation": min_cams, "undistort_points": False}}
@@ -248,6 +255,11 @@ def association_cases(ref, out):
 def main():
     ref = ref_shim.load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--association-only" in sys.argv:
+        out = {}
+        association_cases(ref, out)
+        np.savez_compressed(os.path.join(GOLDEN, "assoc_random_frames.npz"), **out)
+        return
 
     # 1. edge-case table -----------------------------------------------------------------------
     out = {}

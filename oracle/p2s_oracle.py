@@ -40,6 +40,10 @@ def weighted_dlt(P_sub, x, y, w):
     if 2 * m < 4:
         return np.array([np.nan, np.nan, np.nan, 1.0])
     A = np.empty((2 * m, 4))
+    if not (np.all(np.isfinite(x)) and np.all(np.isfinite(y)) and np.all(np.isfinite(w))):
+        # cv2.SVDecomp does not raise on NaN input, it returns NaN (np.linalg.svd would raise): a NaN observation
+        # that is still "active" (personAssociation.py:215-216 only switches likelihood 0 off) yields Q = NaN
+        return np.array([np.nan, np.nan, np.nan, 1.0])
     for c in range(m):
         Pc = P_sub[c]
         A[2 * c] = (Pc[0] - x[c] * Pc[2]) * w[c]

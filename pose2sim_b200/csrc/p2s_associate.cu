@@ -49,7 +49,7 @@ struct AssocArgs {
 };
 
 __host__ __device__ inline size_t assoc_slab_bytes(int cmax, int np) {
-    return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 3 * (size_t)cmax * sizeof(uint32_t);
+    return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 4 * (size_t)cmax * sizeof(uint32_t);
 }
 
 template <int CMAX>
@@ -120,6 +120,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * (sizeof(float4) + 10 * sizeof(double)));
     uint32_t *s_ok = s_n + CMAX;
     uint32_t *s_inv = s_ok + CMAX;
+    uint32_t *s_nan = s_inv + CMAX;                   // per camera: persons whose x, y or likelihood is NaN
     TeamScratch<NW> &T = *reinterpret_cast<TeamScratch<NW> *>(base + assoc_slab_bytes(CMAX, NP));
 
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
@@ -143,7 +144,12 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             const float4 o = __ldg(fobs + i);
             sobs[i] = o;
             double b[10];
-            camera_block(sP + (i / NP) * 12, (double)o.x, (double)o.y, (double)o.z, b);
+            // A detection with a NaN coordinate / likelihood stays ACTIVE in the reference (NaN < thr and NaN == 0 are
+            // both false, personAssociation.py:215-216) and poisons every subset that keeps its camera (Q = NaN, all
+            // distances +inf) until the subset search drops that camera.  Its block is stored as zero so that the
+            // row's normal matrix and the block subtractions stay finite; the poisoning is applied per candidate below.
+            const bool nanobs = (o.x != o.x) || (o.y != o.y) || (o.z != o.z);
+            camera_block(sP + (i / NP) * 12, nanobs ? 0.0 : (double)o.x, nanobs ? 0.0 : (double)o.y, nanobs ? 0.0 : (double)o.z, b);
             double2 *dst = reinterpret_cast<double2 *>(sblk + (size_t)i * 10);
 #pragma unroll
             for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
@@ -153,14 +159,17 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
         if (ttid < C) {
             int n = a.count[(long long)f * C + ttid];
             n = max(0, min(n, NP));
-            uint32_t ok = 0;
+            uint32_t ok = 0, nanbits = 0;
             for (int p = 0; p < n; ++p) {
-                const double l = (double)sobs[ttid * NP + p].z;
+                const float4 o = sobs[ttid * NP + p];
+                const double l = (double)o.z;
                 // gate (:215-216): likelihood < thr -> 0 -> off; likelihood == 0 -> off; NaN stays on
                 if (!(l < a.lik_thr) && !(l == 0.0)) ok |= 1u << p;
+                if ((o.x != o.x) || (o.y != o.y) || (o.z != o.z)) nanbits |= 1u << p;
             }
             s_n[ttid] = (uint32_t)n;
             s_ok[ttid] = ok;
+            s_nan[ttid] = nanbits;
             const uint32_t nn = n ? (uint32_t)n : 1u;
             s_inv[ttid] = (65536u + nn - 1u) / nn;
         }
@@ -178,7 +187,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
 
         // replicated in every thread of the team (all threads apply the same updates)
         double err_last = inf64();
-        unsigned long long best_key = P2S_KEY_EMPTY;          // key of the global best (strict '<' updates)
+        // key of the global best.  The reference starts from error = +inf and replaces it on a strict '<' (:242-245), so a
+        // row whose best error is +inf (single-camera subsets, subsets poisoned by a NaN observation) never becomes it.
+        const unsigned long long kInfKey = 0x7ff0000000000000ULL;
+        unsigned long long best_key = kInfKey;
         double bqx = nan64(), bqy = bqx, bqz = bqx;
         uint32_t b_valid = 0;                                 // cameras used by the best candidate
         uint32_t b_dig[4] = {0, 0, 0, 0};                     // person digits of the best row
@@ -194,10 +206,13 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += TEAM_THREADS) {
                 const unsigned long long r = rbase + ttid;
                 const bool row_ok = r < total_rows;
-                uint32_t active = 0;
+                uint32_t active = 0, nanact = 0;              // nanact: active cameras whose chosen detection holds a NaN
 #pragma unroll
                 for (int c = 0; c < CMAX; ++c)
-                    if (c < C && s_n[c] && ((s_ok[c] >> digit_of<CMAX>(dig, c)) & 1u)) active |= 1u << c;
+                    if (c < C && s_n[c] && ((s_ok[c] >> digit_of<CMAX>(dig, c)) & 1u)) {
+                        active |= 1u << c;
+                        nanact |= ((s_nan[c] >> digit_of<CMAX>(dig, c)) & 1u) << c;
+                    }
                 const int na = __popc(active);
                 unsigned long long rkey = P2S_KEY_EMPTY;
                 double rqx = nan64(), rqy = rqx, rqz = rqx;
@@ -224,6 +239,9 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                         if (m < 2) {
                             cqx = cqy = cqz = nan64();
                             e = (m == 0) ? nan64() : inf64();
+                        } else if (valid & nanact) {           // a kept camera observes NaN: Q = NaN, every distance +inf
+                            cqx = cqy = cqz = nan64();
+                            e = inf64();
                         } else {
                             Sym4 M = Mrow;
                             uint32_t bits = cm;
@@ -339,14 +357,14 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             }
         }
         if (ttid == 0) {
-            const bool any = best_key != P2S_KEY_EMPTY;
+            const bool any = best_key != kInfKey;
             a.out_err[f] = any ? key_err(best_key) : inf64();
             double *q = a.out_Q + (long long)f * 3;
             q[0] = any ? bqx : nan64(); q[1] = any ? bqy : nan64(); q[2] = any ? bqz : nan64();
         }
         if (ttid < C) {
             int8_t v = -1;
-            if (best_key != P2S_KEY_EMPTY && ((b_valid >> ttid) & 1u)) {
+            if (best_key != kInfKey && ((b_valid >> ttid) & 1u)) {
                 const uint32_t w = ttid < 8 ? b_dig[0] : ttid < 16 ? b_dig[1] : ttid < 24 ? b_dig[2] : b_dig[3];
                 v = (int8_t)((w >> ((ttid & 7) * 4)) & 15u);
             }
