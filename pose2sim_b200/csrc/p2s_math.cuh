@@ -351,6 +351,11 @@ __device__ __forceinline__ int solve_subset(const CamParams<CMAX> &cams, Fetch f
 __device__ __forceinline__ unsigned long long err_key(double e) {
     return (e != e) ? P2S_KEY_NAN : (unsigned long long)__double_as_longlong(e);
 }
+// Triangulation: a NaN candidate error is the reference's +inf — its euclidean_distance (common.py:394-399) returns inf
+// when the re-projection is NaN and never NaN — so it ties with +inf and the first candidate index wins.
+__device__ __forceinline__ unsigned long long err_key_inf(double e) {
+    return (e != e) ? 0x7ff0000000000000ULL : (unsigned long long)__double_as_longlong(e);
+}
 __device__ __forceinline__ double key_err(unsigned long long k) {
     return (k >= P2S_KEY_NAN) ? nan64() : __longlong_as_double((long long)k);
 }

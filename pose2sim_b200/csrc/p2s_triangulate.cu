@@ -152,6 +152,10 @@ static_assert(sizeof(WarpSlab<32>) % 16 == 0 && offsetof(WarpSlab<32>, blk) % 16
 // Weighted-DLT normal matrix of ONE unit accumulated straight from the observations (level 0:
 // thread per unit).  Invalid cameras enter with x = y = w = 0, i.e. exact zeros are added — no
 // branch per camera, so the unrolled cameras interleave in the FP64 pipe.
+// "Poisoned" cameras: valid (likelihood neither NaN nor 0) but x or y is NaN.  The reference keeps such a camera (only the
+// likelihood decides validity, triangulation.py:435-436), its DLT rows are NaN, cv2.SVDecomp returns NaN, and every
+// distance of that candidate is +inf (common.py:394-396) — until the exclusion search drops the camera.  Nothing is
+// tested here: a kept poisoned camera makes M, Q and the error NaN, which err_key_inf() orders as that +inf.
 template <int CMAX>
 __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX> &cams, const float2 (*xy)[32],
                                                   const float (*wt)[32], int ul, uint32_t valid) {
@@ -163,6 +167,28 @@ __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX>
         const bool v = (valid >> c) & 1u;
         o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
         accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)ow);
+    }
+}
+
+// Level-0 fix-up for a unit with poisoned cameras (off the common path, so a rolled loop: small code): the level-0 matrix
+// accumulate_direct() stored is NaN; rebuild it from the clean valid cameras, in the same order, so that the deeper levels
+// subtract finite blocks from a finite sum (the block pass gives poisoned cameras a zero block).
+__device__ __forceinline__ void rebuild_without_poisoned(double (*m0)[32], const double *sP, const float2 (*xy)[32],
+                                                      const float (*wt)[32], int ul, uint32_t valid, int n_cams) {
+    Sym4 M;
+    sym4_zero(M);
+    bool any = false;
+#pragma unroll 1
+    for (int c = 0; c < n_cams; ++c) {
+        const float2 o = xy[c][ul];
+        const bool v = (valid >> c) & 1u;
+        const bool clean = v && (o.x == o.x) && (o.y == o.y);
+        any |= v && !clean;
+        if (clean) accumulate_camera(M, sP + c * 12, (double)o.x, (double)o.y, (double)wt[c][ul]);
+    }
+    if (any) {
+        m0[0][ul] = M.m00; m0[1][ul] = M.m01; m0[2][ul] = M.m02; m0[3][ul] = M.m03; m0[4][ul] = M.m11;
+        m0[5][ul] = M.m12; m0[6][ul] = M.m13; m0[7][ul] = M.m22; m0[8][ul] = M.m23; m0[9][ul] = M.m33;
     }
 }
 
@@ -426,14 +452,17 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                     // valid blocks, M_all, is level 0's normal matrix, kept in S.m0)
                     __syncwarp();
                     if (on && sub < C) {
-                        float2 o = S.xy[sub][ul];
+                        const float2 o = S.xy[sub][ul];
                         float ow = S.w[sub][ul];
+                        // A valid camera whose x or y is NaN ("poisoned", see accumulate_direct) gets a ZERO block, so M and
+                        // its downdates stay finite, but keeps its NaN in gxy: the distance of every candidate that keeps
+                        // the camera is NaN, which err_key_inf() orders as the reference's +inf.
                         const bool v = !((u_inv0 >> sub) & 1u);
-                        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
+                        const bool vb = v && (o.x == o.x) && (o.y == o.y);
                         const double ox = (double)o.x, oy = (double)o.y;
                         S.gxy[grp * C + sub] = make_double2(ox, oy);       // invalid cameras: never read under `valid`
                         double b[10];
-                        camera_block(sP + sub * 12, ox, oy, (double)ow, b);
+                        camera_block(sP + sub * 12, vb ? ox : 0.0, vb ? oy : 0.0, (double)(vb ? ow : 0.f), b);
                         t_blocks += v ? 1u : 0u;
                         double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
 #pragma unroll
@@ -499,7 +528,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                             t_solved += 1u;
                         }
                         t_cands += 1; t_cams += (uint32_t)m;
-                        const unsigned long long key = err_key(e);
+                        const unsigned long long key = err_key_inf(e);
                         if (key < bkey) {                       // ascending cand per lane: strict < keeps the first
                             skey = bkey;
                             bkey = key; bcand = cand; bnan = nanset; bexcl = (uint32_t)__popc(invset);
@@ -552,6 +581,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             __syncwarp();
             if (pend) {
                 err_min = S.r_err[lane];
+                // level 0 came out +inf: a unit with poisoned cameras gets its level-0 matrix rebuilt without them
+                if (k == 0 && !(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, cmask & ~inv0, C);
                 qx = S.r_qx[lane]; qy = S.r_qy[lane]; qz = S.r_qz[lane];
                 ids = S.r_nan[lane];
                 const uint32_t fl = S.r_flags[lane];

@@ -49,6 +49,7 @@ def main():
         m = g.random((U, C))
         lik[m < 0.03] = 0.0                                       # zero likelihoods: counted, not listed
         lik[(m > 0.03) & (m < 0.05)] = np.nan
+        x[(m > 0.05) & (m < 0.06)] = np.nan                       # NaN coordinate with a valid likelihood: camera stays valid
         if C >= 3 and g.random() < dup_rate:                      # duplicated cameras: exactly tied candidates
             P = wl["P"].copy(); P[1] = P[0]; x[:, 1] = x[:, 0]; y[:, 1] = y[:, 0]; lik[:, 1] = lik[:, 0]
         else:

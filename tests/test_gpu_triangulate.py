@@ -150,6 +150,31 @@ def test_host_entry_zero_copy_equals_copy_pipeline(engine, C, U):
     assert a["stats"]["level_hist"] == b["stats"]["level_hist"] == c["stats"]["level_hist"]
 
 
+def test_nan_coordinate_with_valid_likelihood(engine):
+    """Only the likelihood decides whether a camera is valid (triangulation.py:435-436): a NaN x or y with a valid
+    likelihood keeps the camera, poisons every candidate that keeps it (Q = NaN, error +inf) and is removed — and
+    LISTED — by the exclusion search, exactly like an outlier (checked against the live reference when written)."""
+    wl = synth.make_triangulation_workload(8, 6, 1, 26, seed=9, lik_thr=0.3)
+    x, y, w = wl["x"].copy(), wl["y"].copy(), wl["lik"].copy()
+    g = np.random.default_rng(3)
+    m = g.random(x.shape)
+    x[m < 0.06] = np.nan
+    y[(m > 0.06) & (m < 0.10)] = np.nan
+    for mc, thr in ((2, 15.0), (6, 15.0), (2, 1e-3)):
+        out = run_gpu(engine, wl["P"], x, y, w, thr, mc)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, err, nexcl, mask = orc.triangulate_units(x.astype(float), y.astype(float), w.astype(float), wl["P"], thr, mc)
+        compare(out, Q, err, nexcl, mask, thr)
+    # staged-buffer path and fused path agree on it too
+    import torch
+    xs, ys, ls = (torch.from_numpy(a).cuda() for a in (x, y, w))
+    a = engine.triangulate(engine.stage_observations(xs, ys, ls, None), wl["P"], 15.0, 2)
+    b = engine.triangulate_planes(xs, ys, ls, wl["P"], None, 15.0, 2)
+    for k in ("Q", "err", "nexcl", "mask"):
+        assert torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0), torch.nan_to_num(b[k].double(), nan=-7.0)), k
+
+
 def test_solution_at_infinity_candidate(engine):
     """Regression (found by tests/perf/fuzz_parity.py): excluding camera 1 leaves two nearly parallel rays, the smallest
     eigenvector's last component is ~1e-3, so the secular root sits 5e-4 (relative) left of its pole and the safeguarded
