@@ -59,8 +59,8 @@ def algorithmic_flops(st):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 73.5 MB written on cfg2
 # (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
-NCU_TRAFFIC = {("cfg2", 1): 323.2e6, ("cfg3", 1): 739.8e6}      # cfg3: profiles/r1s_triangulate_cfg3_ncu_full.csv
-NCU_TRAFFIC_SOURCE = "profiles/r1s_triangulate_ncu_full.csv"
+NCU_TRAFFIC = {("cfg2", 1): 321.3e6, ("cfg3", 1): 739.8e6}      # cfg3: profiles/r1s_triangulate_cfg3_ncu_full.csv
+NCU_TRAFFIC_SOURCE = "profiles/r1z_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
