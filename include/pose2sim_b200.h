@@ -183,6 +183,21 @@ int p2s_triangulate_undistort_host(p2s_handle *h, const float *x, const float *y
                                    double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
                                    unsigned long long *stats);
 
+/* `handle_LR_swap = true` (triangulation.py:509-579): the same search with the left/right swapped evaluation
+ * after every level whose error is still above the threshold — as the reference EXECUTES it (its sub-configuration
+ * arrays alias, :518-526, so each candidate gets ONE swapped evaluation: the first n_cams - nb_cams_off_tot valid
+ * cameras take the partner keypoint's coordinates and only they enter the error; nb_cams_excluded keeps the
+ * un-swapped winner's count, :574-577).
+ * obs        : staged float4 [n_cams][n_units] (device), units ordered (frame, person, keypoint), so the partner
+ *              of unit u is u - u % n_keypoints + partner[u % n_keypoints]  (triangulation.py:838)
+ * partner    : DEVICE int32 [n_keypoints], 0 <= partner[k] < n_keypoints (keypoints_idx_swapped, :742-745)
+ * lens       : HOST pointer to n_cams models (undistort_points) or NULL                                        */
+int p2s_triangulate_lrswap_device(p2s_handle *h, const void *obs, const int32_t *partner, int n_keypoints,
+                                  const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
+                                  double reproj_thr, int min_cams,
+                                  double *out_Q, double *out_err, uint8_t *out_nexcl, uint32_t *out_mask,
+                                  void *stream);
+
 /* ---- single-person association search (personAssociation.py:154) ---------------------------- *
  * obs        : float4 [n_frames][n_cams][max_persons] = {x, y, likelihood, 0} of the tracked keypoint
  *              (device for *_device, host for *_host); entries >= count are ignored

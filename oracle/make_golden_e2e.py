@@ -274,6 +274,7 @@ VARIANTS = [
     ("missing_files", {"sections_to_keep": "last"}, [(1, f) for f in range(20, 26)] + [(3, 50), (0, 97), (0, 98), (0, 99)]),
     ("min_cams_3_thr_8", {"min_cameras_for_triangulation": 3, "reproj_error_threshold_triangulation": 8,
                           "likelihood_threshold_triangulation": 0.5}, []),
+    ("lr_swap_thr_6", {"handle_LR_swap": True, "reproj_error_threshold_triangulation": 6}, []),
 ]
 
 

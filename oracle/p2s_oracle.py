@@ -143,8 +143,50 @@ def solve_subset(P, x, y, w, cams, lens=None):
 # triangulation exclusion search  (Pose2Sim/triangulation.py:363-604, handle_LR_swap and
 # undistort_points off, as in every shipped config: SURVEY.md §5)
 # ---------------------------------------------------------------------------------------------
-def triangulate_unit(x, y, w, P, thr, min_cams, lens=None):
+def swapped_pass(P, x, y, w, xs, ys, cands, counts, C, lens=None):
+    """`handle_LR_swap` branch of one level (triangulation.py:509-579), as the reference EXECUTES it.
+
+    The reference builds `[[x] * n for x in x_files_filt]` (:518-519): every "sub-configuration" of a
+    candidate is the SAME array object (the candidate's compacted valid-camera array), so the assignments
+    at :525-526 accumulate in place: after the loops the first n_cams - nb_cams_off_tot compacted positions
+    of every candidate hold the swapped coordinates, for every sub-configuration and for every later
+    `n_cams_swapped` (the arrays stay mutated, re-assigning the same values).  Hence one evaluation per
+    candidate: DLT over ALL its valid cameras (first T' = n_cams - nb_cams_off_tot positions swapped, the
+    rest original, original likelihoods :529), error = mean distance over the first T' positions ONLY
+    (:557-559).  Returns (min error, first candidate index with it, its Q) — np.min / argmin (:565-566) —
+    or None when the swap loop's condition (:513) never holds.
+    """
+    T = max(counts)
+    n_first = C - T
+    if not 1 < n_first / 2:                     # n_cams_swapped = 1 < (n_cams - nb_cams_off_tot) / 2   (:513)
+        return None
+    errs, Qs = [], []
+    for cand in cands:
+        wl = w.copy()
+        wl[list(cand)] = np.nan
+        cams = [c for c in range(C) if not np.isnan(wl[c]) and wl[c] != 0.0]
+        xm = [xs[c] if i < n_first else x[c] for i, c in enumerate(cams)]
+        ym = [ys[c] if i < n_first else y[c] for i, c in enumerate(cams)]
+        P_sub = [P[c] for c in cams]
+        Q = weighted_dlt(P_sub, xm, ym, [w[c] for c in cams])
+        if lens is not None:
+            proj = [project_distorted(lens[c], Q) for c in cams]
+            xc, yc = [p[0] for p in proj], [p[1] for p in proj]
+        else:
+            xc, yc = reproject(P_sub, Q)
+        d = [pixel_distance((xm[i], ym[i]), (xc[i], yc[i])) for i in range(n_first)]
+        errs.append(float(np.mean(d)))
+        Qs.append(Q)
+    errs = np.array(errs)
+    b = int(errs.argmin())
+    return float(errs.min()), b, Qs[b]
+
+
+def triangulate_unit(x, y, w, P, thr, min_cams, lens=None, swapped=None):
     """One (frame, person, keypoint) unit.  Returns (Q[3], err, nb_cams_excluded, id_excluded_cams).
+    `swapped` = (x, y) of the left/right partner keypoint turns `handle_LR_swap` on (see swapped_pass):
+    when a level's swapped evaluation beats its error, error / Q / id list become the swapped winner's while
+    `nb_cams_excluded` stays the un-swapped winner's (:574-577 do not touch it).
 
     Follows `triangulation_from_best_cameras`:
       * level loop condition `error_min > thr and n_cams - k >= min_cams`            (:408)
@@ -197,6 +239,12 @@ def triangulate_unit(x, y, w, P, thr, min_cams, lens=None):
         nexcl = counts[best]
         ids = [int(i) for i in nan_sets[best]]
         Q = Qs[best][:3].copy()
+        if swapped is not None and err_min > thr:
+            sw = swapped_pass(P, x, y, w, np.asarray(swapped[0], float), np.asarray(swapped[1], float), cands, counts, C, lens)
+            if sw is not None and sw[0] < err_min:
+                err_min = sw[0]
+                ids = [int(i) for i in nan_sets[sw[1]]]
+                Q = sw[2][:3].copy()
         k += 1
     if ids is None:
         ids = list(range(C))
@@ -208,16 +256,23 @@ def triangulate_unit(x, y, w, P, thr, min_cams, lens=None):
     return Q, err, nexcl, ids
 
 
-def triangulate_units(x, y, w, P, thr, min_cams, lens=None):
+def triangulate_units(x, y, w, P, thr, min_cams, lens=None, partner=None):
     """Batched convenience wrapper: x, y, w are [U, C]; returns (Q[U,3], err[U], nexcl[U], mask[U])
-    with mask bit c set iff camera c is in `id_excluded_cams`."""
+    with mask bit c set iff camera c is in `id_excluded_cams`.  `partner` (K keypoint indices, units ordered
+    (.., keypoint)) turns handle_LR_swap on: unit u's swapped coordinates are those of unit
+    u - u % K + partner[u % K]  (triangulation.py:838)."""
     U = x.shape[0]
     Q = np.empty((U, 3))
     err = np.empty(U)
     nexcl = np.empty(U, np.int32)
     mask = np.zeros(U, np.uint32)
     for u in range(U):
-        q, e, n, ids = triangulate_unit(x[u], y[u], w[u], P, thr, min_cams, lens)
+        swapped = None
+        if partner is not None:
+            K = len(partner)
+            up = u - u % K + int(partner[u % K])
+            swapped = (x[up], y[up])
+        q, e, n, ids = triangulate_unit(x[u], y[u], w[u], P, thr, min_cams, lens, swapped)
         Q[u], err[u], nexcl[u] = q, e, n
         m = 0
         for c in ids:

@@ -72,6 +72,7 @@ SIGNATURES = {
     "p2s_triangulate_host": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_stage_undistort_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp, _vp]),
     "p2s_triangulate_distorted_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p2s_triangulate_lrswap_device": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_triangulate_undistort_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "p2s_associate_host": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp]),

@@ -364,6 +364,34 @@ int p2s_triangulate_device(p2s_handle *h, const void *obs, const double *P, long
                               out_mask, stats, stream);
 }
 
+int p2s_triangulate_lrswap_device(p2s_handle *h, const void *obs, const int32_t *partner, int n_keypoints,
+                                  const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
+                                  double reproj_thr, int min_cams, double *out_Q, double *out_err, uint8_t *out_nexcl,
+                                  uint32_t *out_mask, void *stream) {
+    if (!h || !P || n_keypoints < 1 || (n_units > 0 && (!obs || !partner || !out_Q || !out_err || !out_nexcl || !out_mask)))
+        return P2S_EINVAL;
+    if (n_units % n_keypoints != 0) return P2S_EINVAL;         // units are (frame, person) blocks of n_keypoints
+    int rc = check_tri_args(n_cams, min_cams, n_units);
+    if (rc) return rc;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    rc = build_table(h, n_cams);
+    if (rc) return rc;
+    if (n_units == 0) return P2S_OK;
+    p2s::SwapLaunch L;
+    L.obs = obs; L.partner = partner; L.n_keypoints = n_keypoints; L.P = P; L.lens = lens;
+    L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams; L.sm_count = h->prop.multiProcessorCount;
+    L.thr = reproj_thr;
+    const SubsetTable &t = h->tables[n_cams];
+    L.cand_masks = t.d_masks;
+    std::memcpy(L.level_off, t.level_off, sizeof L.level_off);
+    L.max_table_level = t.max_level;
+    L.out_Q = out_Q; L.out_err = out_err; L.out_nexcl = out_nexcl; L.out_mask = out_mask;
+    L.stream = (cudaStream_t)stream;
+    P2S_CUDA(h, p2s::launch_lrswap(L));
+    h->launches += 1;
+    return P2S_OK;
+}
+
 int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y, const float *lik,
                                   const double *P, long long n_units, int n_cams, double lik_thr,
                                   double reproj_thr, int min_cams,

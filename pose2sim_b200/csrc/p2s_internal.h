@@ -67,7 +67,26 @@ struct MpLaunch {
     cudaStream_t stream;
 };
 
+struct SwapLaunch {               // handle_LR_swap search (p2s_lrswap.cu)
+    const void *obs;              // staged float4 [n_cams][n_units], device
+    const int32_t *partner;       // device, [n_keypoints]
+    int n_keypoints;
+    const double *P;              // host
+    const p2s_camera_model *lens; // host or null
+    long long n_units;
+    int n_cams, min_cams, sm_count;
+    double thr;
+    const uint32_t *cand_masks;
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    double *out_Q, *out_err;
+    uint8_t *out_nexcl;
+    uint32_t *out_mask;
+    cudaStream_t stream;
+};
+
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out);
+cudaError_t launch_lrswap(const SwapLaunch &L);
 cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out);
 size_t mp_smem_bytes(int n_max, int n_joints);
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,

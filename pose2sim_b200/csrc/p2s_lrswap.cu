@@ -1,0 +1,206 @@
+// `handle_LR_swap = true` (Pose2Sim/triangulation.py:509-579): the exclusion search with the left/right
+// swapped evaluation after every level whose error is still above the threshold.
+//
+// What the reference EXECUTES (restated in oracle/p2s_oracle.py::swapped_pass, checked against the live
+// reference): `[[x] * n for x in x_files_filt]` (:518-519) makes every "sub-configuration" of a candidate the
+// SAME array object, so the assignments at :525-526 accumulate in place — after the loops the first
+// T' = n_cams - nb_cams_off_tot compacted positions of every candidate hold the partner keypoint's
+// coordinates, whatever `n_cams_swapped` is.  Per candidate that is ONE extra evaluation: DLT over all its
+// valid cameras (first T' of them, in ascending order, with the swapped coordinates, original likelihoods
+// :529), error = mean distance over those first T' only (:557-559); np.min / argmin over the candidates
+// (:565-566); when it beats the level's error, error / Q / id list become the swapped winner's while
+// nb_cams_excluded stays the un-swapped winner's (:574-577).  The swap loop runs iff 1 < T' / 2 (:513).
+//
+// This mode is off in every shipped configuration (the fork's notes recommend it off), so it gets a plain
+// kernel: one thread per unit, candidates in sequence, the same leaf math as the main kernel
+// (p2s_math.cuh).  Input is the STAGED buffer (gated, undistorted if asked), so the partner's coordinates
+// are already NaN where ITS likelihood failed the gate, like the reference's slices (:838).
+#include <cmath>
+#include <cstring>
+
+#include "p2s_internal.h"
+#include "p2s_math.cuh"
+
+namespace p2s {
+
+struct SwapArgs {
+    const float4 *obs;            // staged [n_cams][n_units]
+    const int32_t *partner;       // [n_keypoints] keypoint index of the left/right partner (itself when none)
+    int n_keypoints;
+    long long n_units;
+    int n_cams, min_cams;
+    double thr;
+    const uint32_t *cand_masks;
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    uint32_t ncand[P2S_MAX_CAMS + 1];
+    double *out_Q, *out_err;
+    uint8_t *out_nexcl;
+    uint32_t *out_mask;
+};
+
+// One candidate.  The first `n_swapped` valid cameras (ascending) take (xs, ys); the error is the mean over the
+// first `n_err` valid cameras (n_err >= m: all of them).
+template <int CMAX, bool DISTORT>
+__device__ __noinline__ void evaluate_candidate(const double *sP, const LensParams *sL,
+                                                const float *x, const float *y, const float *w, const float *xs,
+                                                const float *ys, int n_cams, uint32_t valid, int n_swapped, int n_err,
+                                                double &qx, double &qy, double &qz, double &err) {
+    const int m = __popc(valid);
+    if (m < 2) {
+        qx = qy = qz = nan64();
+        err = (m == 0) ? nan64() : inf64();
+        return;
+    }
+    Sym4 M;
+    sym4_zero(M);
+    int pos = 0;
+#pragma unroll 1
+    for (int c = 0; c < n_cams; ++c) {
+        if ((valid >> c) & 1u) {
+            const bool sw = pos < n_swapped;
+            accumulate_camera(M, sP + c * 12, (double)(sw ? xs[c] : x[c]), (double)(sw ? ys[c] : y[c]), (double)w[c]);
+            ++pos;
+        }
+    }
+    smallest_eigvec_secular(M, qx, qy, qz);
+    double sum = 0.0;
+    pos = 0;
+#pragma unroll 1
+    for (int c = 0; c < n_cams; ++c) {
+        if ((valid >> c) & 1u) {
+            if (pos < n_err) {
+                const bool sw = pos < n_swapped;
+                const double ox = (double)(sw ? xs[c] : x[c]), oy = (double)(sw ? ys[c] : y[c]);
+                if (DISTORT) sum += reproj_distance_distorted(sL[DISTORT ? c : 0], qx, qy, qz, ox, oy);
+                else sum += reproj_distance(sP + c * 12, qx, qy, qz, ox, oy);
+            }
+            ++pos;
+        }
+    }
+    err = div_small(sum, (double)(m < n_err ? m : n_err));
+}
+
+template <int CMAX, bool DISTORT>
+__global__ void __launch_bounds__(128) lrswap_kernel(const CamParams<CMAX> cams, const LensSet<DISTORT ? CMAX : 1> lens,
+                                                     const SwapArgs a) {
+    // projection rows and lens models in shared memory: the candidate evaluation indexes them by camera
+    __shared__ double sP[CMAX * 12];
+    __shared__ LensParams sL[DISTORT ? CMAX : 1];
+    for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
+    if (DISTORT) {
+        const double *src = reinterpret_cast<const double *>(&lens);
+        double *dst = reinterpret_cast<double *>(sL);
+        for (int i = threadIdx.x; i < (int)(sizeof(LensParams) / sizeof(double)) * CMAX; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int C = a.n_cams;
+    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < a.n_units; u += (long long)gridDim.x * blockDim.x) {
+        const int kp = (int)(u % a.n_keypoints);
+        const long long up = u - kp + a.partner[kp];
+        float x[CMAX], y[CMAX], w[CMAX], xs[CMAX], ys[CMAX];
+        uint32_t nan0 = 0, inv0 = 0;
+        for (int c = 0; c < C; ++c) {
+            const float4 o = a.obs[(long long)c * a.n_units + u];
+            const float4 p = a.obs[(long long)c * a.n_units + up];
+            x[c] = o.x; y[c] = o.y; w[c] = o.z; xs[c] = p.x; ys[c] = p.y;
+            if (o.z != o.z) nan0 |= 1u << c;
+            if (o.z != o.z || o.z == 0.f) inv0 |= 1u << c;
+        }
+        const int ninv0 = __popc(inv0);
+        double err_min = inf64(), qx = nan64(), qy = nan64(), qz = nan64();
+        uint32_t ids = cmask, nexcl = (uint32_t)C;
+        for (int k = 0; err_min > a.thr && C - k >= a.min_cams; ++k) {
+            const int T = min(C, ninv0 + k);                        // nb_cams_off_tot: the worst candidate's count (:437)
+            if (T > C - a.min_cams) break;                          // :440-441
+            const uint32_t ncand = a.ncand[k];
+            const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
+            unsigned long long bkey = P2S_KEY_EMPTY;
+            for (uint32_t cand = 0; cand < ncand; ++cand) {
+                const uint32_t cm = (k == 0) ? 0u : (k <= a.max_table_level) ? table[cand] : unrank_subset(C, k, cand);
+                double cx, cy, cz, e;
+                evaluate_candidate<CMAX, DISTORT>(sP, sL, x, y, w, xs, ys, C, cmask & ~(inv0 | cm), 0, C, cx, cy, cz, e);
+                const unsigned long long key = err_key_inf(e);
+                if (key < bkey) {                                   // strict <: np.nanargmin's first index
+                    bkey = key; qx = cx; qy = cy; qz = cz;
+                    ids = nan0 | cm; nexcl = (uint32_t)__popc(inv0 | cm);
+                }
+            }
+            err_min = key_err(bkey);
+            const int n_first = C - T;
+            if (err_min > a.thr && n_first > 2) {                   // :509, :513 with n_cams_swapped = 1
+                unsigned long long skey = P2S_KEY_EMPTY;
+                double sx = 0, sy = 0, sz = 0;
+                uint32_t sids = 0;
+                for (uint32_t cand = 0; cand < ncand; ++cand) {
+                    const uint32_t cm = (k == 0) ? 0u : (k <= a.max_table_level) ? table[cand] : unrank_subset(C, k, cand);
+                    double cx, cy, cz, e;
+                    evaluate_candidate<CMAX, DISTORT>(sP, sL, x, y, w, xs, ys, C, cmask & ~(inv0 | cm), n_first, n_first, cx, cy, cz, e);
+                    const unsigned long long key = err_key_inf(e);
+                    if (key < skey) { skey = key; sx = cx; sy = cy; sz = cz; sids = nan0 | cm; }
+                }
+                const double e_sw = key_err(skey);
+                if (e_sw < err_min) { err_min = e_sw; qx = sx; qy = sy; qz = sz; ids = sids; }    // :574-577
+            }
+        }
+        const bool failed = err_min > a.thr;
+        double *q = a.out_Q + u * 3;
+        q[0] = failed ? nan64() : qx; q[1] = failed ? nan64() : qy; q[2] = failed ? nan64() : qz;
+        a.out_err[u] = failed ? nan64() : err_min;
+        a.out_nexcl[u] = (uint8_t)nexcl;
+        a.out_mask[u] = ids;
+    }
+}
+
+template <int CMAX>
+static cudaError_t launch_swap(const SwapLaunch &L) {
+    CamParams<CMAX> cams;
+    for (int c = 0; c < CMAX; ++c)
+        for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
+    SwapArgs a;
+    a.obs = (const float4 *)L.obs; a.partner = L.partner; a.n_keypoints = L.n_keypoints;
+    a.n_units = L.n_units; a.n_cams = L.n_cams; a.min_cams = L.min_cams; a.thr = L.thr;
+    a.cand_masks = L.cand_masks;
+    for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
+    a.max_table_level = L.max_table_level;
+    for (int k = 0; k <= P2S_MAX_CAMS; ++k) {
+        unsigned long long r = (k <= L.n_cams) ? 1ULL : 0ULL;
+        for (int i = 1; i <= k && k <= L.n_cams; ++i) {
+            r = r * (unsigned)(L.n_cams - k + i) / (unsigned)i;
+            if (r > 0xffffffffULL) { r = 0xffffffffULL; break; }
+        }
+        a.ncand[k] = (uint32_t)r;
+    }
+    a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
+    long long grid = (L.n_units + 127) / 128;
+    const long long cap = (long long)L.sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (L.lens) {
+        LensSet<CMAX> lens;
+        std::memset(&lens, 0, sizeof lens);
+        for (int c = 0; c < L.n_cams; ++c) {
+            const p2s_camera_model &m = L.lens[c];
+            LensParams &o = lens.cam[c];
+            for (int j = 0; j < 9; ++j) o.R[j] = m.R[j];
+            for (int j = 0; j < 3; ++j) o.T[j] = m.T[j];
+            o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
+            for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
+        }
+        lrswap_kernel<CMAX, true><<<(unsigned)grid, 128, 0, L.stream>>>(cams, lens, a);
+    } else {
+        LensSet<1> none;
+        std::memset(&none, 0, sizeof none);
+        lrswap_kernel<CMAX, false><<<(unsigned)grid, 128, 0, L.stream>>>(cams, none, a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lrswap(const SwapLaunch &L) {
+    if (L.n_cams <= 8) return launch_swap<8>(L);
+    if (L.n_cams <= 16) return launch_swap<16>(L);
+    return launch_swap<32>(L);
+}
+
+}  // namespace p2s

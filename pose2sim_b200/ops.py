@@ -169,6 +169,32 @@ class Engine:
             _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), _ptr(stats), self._stream()))
         return out
 
+    def triangulate_lr_swap(self, obs, partner, P, reproj_thr, min_cams, lens=None):
+        """`handle_LR_swap = true` (triangulation.py:509-579).  obs: staged CUDA tensor [C, U, 4] with the units ordered
+        (frame, person, keypoint); partner: K integers, the keypoint index of each keypoint's left/right partner
+        (`keypoints_idx_swapped`, :742-745).  Same outputs as `triangulate`."""
+        torch = _torch()
+        Cn, U, four = obs.shape
+        assert four == 4 and obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous()
+        part = np.ascontiguousarray(partner, dtype=np.int32).ravel()
+        K = int(part.size)
+        if K < 1 or U % K or part.min(initial=0) < 0 or part.max(initial=0) >= K:
+            raise ValueError(f"partner must hold K indices in [0, K) with K dividing the {U} units")
+        dev = obs.device
+        part_d = torch.from_numpy(part).to(dev)
+        out = {"Q": torch.empty((U, 3), dtype=torch.float64, device=dev),
+               "err": torch.empty((U,), dtype=torch.float64, device=dev),
+               "nexcl": torch.empty((U,), dtype=torch.uint8, device=dev),
+               "mask": torch.empty((U,), dtype=torch.int32, device=dev)}
+        Pm = _as_P(P, Cn)
+        arr = lens_array(lens) if lens is not None else None
+        _lib.check(self.h, self.lib.p2s_triangulate_lrswap_device(
+            self.h, _ptr(obs), _ptr(part_d), K, Pm.ctypes.data, C.cast(arr, C.c_void_p) if arr is not None else None,
+            U, Cn, float(reproj_thr), int(min_cams),
+            _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), self._stream()))
+        out["_keepalive"] = part_d
+        return out
+
     def triangulate_planes(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, stats=None):
         """x, y, lik: CUDA float32 tensors [U, C] (raw planes).  Gate + float4 staging are fused into the
         search kernel's tile load: ONE kernel, no staged buffer in HBM.  Returns the same dict as `triangulate`."""

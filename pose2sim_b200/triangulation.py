@@ -11,7 +11,8 @@ Pose2Sim/triangulation.py:656-959, with the per-(frame, person, keypoint) Python
 There is no CPU implementation of the search in this package: `solve_units` needs the built CUDA
 library and a B200 and raises otherwise.  `[triangulation] undistort_points = true` runs on the device
 too (points undistorted by the stage kernel, distorted re-projection in the search kernel);
-`handle_LR_swap = true` (off in every shipped config) is refused loudly.
+`handle_LR_swap = true` (off in every shipped config) runs on the device as well, in its own plain kernel
+(`p2s_lrswap.cu`), reproducing what the reference executes for that flag.
 """
 import glob
 import logging
@@ -58,9 +59,24 @@ def read_settings(config_dict):
 
 
 def refuse_unsupported(s):
-    """not built yet -> refuse, never fall back to a CPU path."""
-    if s["handle_LR_swap"]:
-        raise NotImplementedError("[triangulation] handle_LR_swap = true is not available in the B200 path")
+    """Nothing is refused any more: `undistort_points` and `handle_LR_swap` both run on the device.
+    Kept as the one place where a mode without a device path would be rejected — never a CPU fallback."""
+    return None
+
+
+def swapped_keypoint_indices(keypoints_names):
+    """`keypoints_idx_swapped` (triangulation.py:741-749): the index of each keypoint's left/right partner — an
+    initial 'R' <-> 'L', then a leading 'right' <-> 'left'; a partner name that does not exist disables the swap
+    for ALL keypoints (the reference's bare `except`), with its warning."""
+    names = list(keypoints_names)
+    try:
+        swapped = ["L" + n[1:] if n.startswith("R") else "R" + n[1:] if n.startswith("L") else n for n in names]
+        swapped = [n.replace("right", "left") if n.startswith("right") else n.replace("left", "right") if n.startswith("left")
+                   else n for n in swapped]
+        return [names.index(n) for n in swapped]
+    except ValueError:
+        logging.warning("No left/right swap was performed.")
+        return list(range(len(names)))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -143,6 +159,16 @@ def solve_units(st, engine=None, device=0):
     F, N, K, C = st.x.shape
     U = F * N * K
     s = st.settings
+    if s["handle_LR_swap"]:
+        import torch
+        dev = torch.device("cuda", eng.device)
+        planes = [torch.from_numpy(np.ascontiguousarray(a.reshape(U, C), dtype=np.float32)).to(dev) for a in (st.x, st.y, st.lik)]
+        obs = eng.stage_observations(*planes, s["lik_thr"], lens=st.lens)
+        res = eng.triangulate_lr_swap(obs, swapped_keypoint_indices(st.keypoints_names), st.P, s["reproj_thr"], s["min_cams"],
+                                      lens=st.lens)
+        return {"Q": res["Q"].cpu().numpy().reshape(F, N, K, 3), "err": res["err"].cpu().numpy().reshape(F, N, K),
+                "nexcl": res["nexcl"].cpu().numpy().reshape(F, N, K).astype(np.int64),
+                "mask": res["mask"].cpu().numpy().view(np.uint32).reshape(F, N, K), "stats": None}
     out = eng.triangulate_host(st.x.reshape(U, C), st.y.reshape(U, C), st.lik.reshape(U, C), st.P,
                                s["lik_thr"], s["reproj_thr"], s["min_cams"], lens=st.lens)
     return {"Q": out["Q"].reshape(F, N, K, 3), "err": out["err"].reshape(F, N, K),

@@ -31,7 +31,8 @@ def oracle_units(st):
     x[low] = np.nan; y[low] = np.nan; w[low] = np.nan
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"], lens=st.lens)
+        partner = tri.swapped_keypoint_indices(st.keypoints_names) if s["handle_LR_swap"] else None
+        Q, err, nexcl, mask = orc.triangulate_units(x, y, w, st.P, s["reproj_thr"], s["min_cams"], lens=st.lens, partner=partner)
     return {"Q": Q.reshape(F, N, K, 3), "err": err.reshape(F, N, K), "nexcl": nexcl.reshape(F, N, K).astype(np.int64),
             "mask": mask.reshape(F, N, K)}
 
@@ -94,12 +95,15 @@ def test_valid_chunk_and_gap_filling():
     assert out[2] == 3.0 and np.isnan(out[5:8]).all() and out[8] == 9.0
 
 
-def test_refuses_unbuilt_modes(golden, tmp_path):
-    g = golden("e2e_tri_single.npz")
-    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
-    cfg["triangulation"]["handle_LR_swap"] = True
-    with in_dir(proj), pytest.raises(NotImplementedError):
-        tri.stage_project(cfg)
+def test_swapped_keypoint_indices_follow_the_reference_rule():
+    """triangulation.py:741-749: initial R <-> L, then leading right <-> left; one missing partner disables all."""
+    names = ["Hip", "RHip", "RKnee", "LHip", "LKnee", "Neck", "right_eye", "left_eye"]
+    assert tri.swapped_keypoint_indices(names) == [0, 3, 4, 1, 2, 5, 7, 6]
+    assert tri.swapped_keypoint_indices(["Hip", "RHip", "LHip", "RKnee"]) == [0, 1, 2, 3]      # no LKnee: identity
+    halpe = ["Hip", "RHip", "RKnee", "RAnkle", "RBigToe", "RSmallToe", "RHeel", "LHip", "LKnee", "LAnkle", "LBigToe", "LSmallToe",
+             "LHeel", "Neck", "Head", "Nose", "RShoulder", "RElbow", "RWrist", "LShoulder", "LElbow", "LWrist"]
+    idx = tri.swapped_keypoint_indices(halpe)
+    assert all(idx[idx[k]] == k for k in range(len(halpe))) and idx[1] == 7 and idx[13] == 13
 
 
 @pytest.mark.parametrize("workers", [None, "3"])
@@ -157,7 +161,7 @@ def test_multi_person_association_matches_reference_json(golden, tmp_path, monke
     assert_multi_person_json_equal(proj, g)
 
 
-@pytest.mark.parametrize("i", range(6))
+@pytest.mark.parametrize("i", range(7))
 def test_config_variants_match_reference_trc(golden, tmp_path, i):
     """Frame ranges, trimming / fill / interpolation modes, missing files, other thresholds."""
     from dropin_util import rebuild_variant

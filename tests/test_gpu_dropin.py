@@ -48,7 +48,7 @@ def test_association_then_triangulation_chain(golden, tmp_path):
     assert len(trcs) == 1
 
 
-@pytest.mark.parametrize("i", range(6))
+@pytest.mark.parametrize("i", range(7))
 def test_triangulate_all_config_variants(golden, tmp_path, i):
     import pose2sim_b200
     from dropin_util import rebuild_variant

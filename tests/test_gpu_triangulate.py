@@ -319,3 +319,31 @@ def test_full_size_properties_cfg3_shard(engine):
         warnings.simplefilter("ignore")
         oQ, oerr, onexcl, omask = orc.triangulate_units(gx.astype(float), gy.astype(float), gl.astype(float), wl["P"], thr, mc)
     compare({"Q": Q[sub], "err": err[sub], "nexcl": nexcl[sub], "mask": mask[sub]}, oQ, oerr, onexcl, omask, thr)
+
+
+def test_lr_swap_units_match_reference(engine, golden):
+    """`handle_LR_swap = true` (triangulation.py:509-579) in its own kernel (p2s_lrswap.cu): 3000 units with
+    genuinely swapped limbs, outputs of the unmodified reference (oracle/make_golden_swap.py)."""
+    import torch
+    g = golden("lr_swap_units.npz")
+    partner = g["partner"]
+    for gi, (C, mc, thr, n_pairs, _) in enumerate(g["groups"]):
+        xs, ys, ls = (torch.from_numpy(g[f"g{gi}_{k}"]).cuda() for k in "xyw")
+        obs = engine.stage_observations(xs, ys, ls, None)
+        res = engine.triangulate_lr_swap(obs, partner, g[f"g{gi}_P"], float(thr), int(mc))
+        torch.cuda.synchronize()
+        out = {"Q": res["Q"].cpu().numpy(), "err": res["err"].cpu().numpy(), "nexcl": res["nexcl"].cpu().numpy(),
+               "mask": res["mask"].cpu().numpy().view(np.uint32)}
+        assert compare(out, g[f"g{gi}_Q"], g[f"g{gi}_err"], g[f"g{gi}_nexcl"], g[f"g{gi}_mask"], float(thr), allow_band=False) == 0, gi
+    # without partners (identity map) the swapped evaluation repeats the level's own candidates on fewer cameras;
+    # with the flag's kernel and an identity map on data that never exceeds the threshold the main kernel's answer comes back
+    wl = synth.make_triangulation_workload(8, 40, 1, 26, seed=21, lik_thr=0.3)
+    xs, ys, ls = (torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik"))
+    obs = engine.stage_observations(xs, ys, ls, 0.3)
+    a = engine.triangulate(obs, wl["P"], 1e9, 2)
+    b = engine.triangulate_lr_swap(obs, np.arange(26), wl["P"], 1e9, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(a["nexcl"], b["nexcl"]) and torch.equal(a["mask"], b["mask"])
+    assert torch.allclose(a["Q"], b["Q"], atol=1e-9, rtol=0, equal_nan=True)
+    with pytest.raises(ValueError):
+        engine.triangulate_lr_swap(obs, [0, 5], wl["P"], 15.0, 2)

@@ -198,3 +198,19 @@ def test_multi_person_oracle_reproduces_reference_frames(golden):
         mine = mp.proposals_from_rows(omp.argmax_rows(aff, cum), int(min_cams))
         assert np.array_equal(np.asarray(mine, float).reshape(-1, len(count)), ref_prop, equal_nan=True), i
     assert worst < 1e-9, worst
+
+
+def test_lr_swap_units(golden):
+    """`handle_LR_swap = true`: the restatement of what the reference executes (oracle swapped_pass) against the
+    reference's own outputs on 3000 units, ~15 % of which the swapped evaluation changes."""
+    g = golden("lr_swap_units.npz")
+    partner = g["partner"]
+    for gi, (C, mc, thr, n_pairs, _) in enumerate(g["groups"]):
+        x, y, w = (g[f"g{gi}_{k}"].astype(np.float64) for k in "xyw")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Q, err, nexcl, mask = orc.triangulate_units(x, y, w, g[f"g{gi}_P"], float(thr), int(mc), partner=partner)
+        assert np.array_equal(nexcl, g[f"g{gi}_nexcl"]) and np.array_equal(mask, g[f"g{gi}_mask"])
+        assert np.array_equal(np.isnan(err), np.isnan(g[f"g{gi}_err"]))
+        assert np.allclose(Q, g[f"g{gi}_Q"], atol=1e-8, rtol=0, equal_nan=True)
+        assert np.allclose(err, g[f"g{gi}_err"], atol=1e-7, rtol=0, equal_nan=True)
