@@ -8,6 +8,7 @@ marker) order (triangulation.py:735-736), the tracked keypoint is looked up by n
 as a nested dict (`[pose.CUSTOM]`, triangulation.py:726-730) is traversed here the same way.
 """
 import json
+import logging
 import os
 
 _TABLES = None
@@ -54,13 +55,17 @@ def keypoints(pose_model, config_dict=None):
 
 
 def swapped_indices(names):
-    """Index of the left/right counterpart of every keypoint (triangulation.py:742-749)."""
+    """`keypoints_idx_swapped` (triangulation.py:741-749): the index of each keypoint's left/right partner — an
+    initial 'R' <-> 'L', then a leading 'right' <-> 'left'; a partner name that does not exist disables the swap
+    for ALL keypoints (the reference's bare `except`), with its warning."""
+    names = list(names)
     try:
         sw = ["L" + n[1:] if n.startswith("R") else "R" + n[1:] if n.startswith("L") else n for n in names]
         sw = [n.replace("right", "left") if n.startswith("right") else n.replace("left", "right") if n.startswith("left") else n
               for n in sw]
         return [names.index(n) for n in sw]
     except ValueError:
+        logging.warning("No left/right swap was performed.")
         return list(range(len(names)))
 
 

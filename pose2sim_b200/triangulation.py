@@ -65,18 +65,8 @@ def refuse_unsupported(s):
 
 
 def swapped_keypoint_indices(keypoints_names):
-    """`keypoints_idx_swapped` (triangulation.py:741-749): the index of each keypoint's left/right partner — an
-    initial 'R' <-> 'L', then a leading 'right' <-> 'left'; a partner name that does not exist disables the swap
-    for ALL keypoints (the reference's bare `except`), with its warning."""
-    names = list(keypoints_names)
-    try:
-        swapped = ["L" + n[1:] if n.startswith("R") else "R" + n[1:] if n.startswith("L") else n for n in names]
-        swapped = [n.replace("right", "left") if n.startswith("right") else n.replace("left", "right") if n.startswith("left")
-                   else n for n in swapped]
-        return [names.index(n) for n in swapped]
-    except ValueError:
-        logging.warning("No left/right swap was performed.")
-        return list(range(len(names)))
+    """`keypoints_idx_swapped` (triangulation.py:741-749); see `skeletons.swapped_indices`."""
+    return _skel.swapped_indices(keypoints_names)
 
 
 # ---------------------------------------------------------------------------------------------------
