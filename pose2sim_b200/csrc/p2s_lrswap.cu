@@ -11,10 +11,12 @@
 // (:565-566); when it beats the level's error, error / Q / id list become the swapped winner's while
 // nb_cams_excluded stays the un-swapped winner's (:574-577).  The swap loop runs iff 1 < T' / 2 (:513).
 //
-// This mode is off in every shipped configuration (the fork's notes recommend it off), so it gets a plain
-// kernel: one thread per unit, candidates in sequence, the same leaf math as the main kernel
-// (p2s_math.cuh).  Input is the STAGED buffer (gated, undistorted if asked), so the partner's coordinates
-// are already NaN where ITS likelihood failed the gate, like the reference's slices (:838).
+// This mode is off in every shipped configuration (the fork's notes recommend it off), so it gets a compact
+// kernel of its own rather than more template axes on the main one: a warp owns a tile of 32 units (lane = unit
+// for the search state), and every level's (unit, candidate) pairs are dealt to the 32 lanes as work items
+// (`level_pass`), with the same leaf math as the main kernel (p2s_math.cuh).  Input is the STAGED buffer (gated,
+// undistorted if asked), so the partner's coordinates are already NaN where ITS likelihood failed the gate, like
+// the reference's slices (:838).
 #include <cmath>
 #include <cstring>
 
@@ -81,12 +83,89 @@ __device__ __noinline__ void evaluate_candidate(const double *sP, const LensPara
     err = div_small(sum, (double)(m < n_err ? m : n_err));
 }
 
+// Per-warp exchange area: lane = unit slot of the warp's 32-unit tile.
+struct SwapWarp {
+    unsigned long long rkey[32];   // this round's smallest error key per unit
+    unsigned long long skey[32];   // the pass's smallest error key per unit (first candidate index among equals)
+    long long partner_unit[32];    // unit index of the left/right partner keypoint
+    double q[32][3];               // the pass winner's point
+    uint32_t rcand[32];            // this round's smallest candidate index among the holders of rkey
+    uint32_t cm[32];               // the pass winner's excluded-camera mask
+    uint32_t inv0[32];             // cameras without a usable likelihood (NaN or 0)
+    uint32_t list[32];             // slots of the units taking part in the pass, compacted
+};
+
+// One pass (un-swapped or swapped) of exclusion level k over the units in `active`.  Every (unit, candidate) pair is
+// one work item; the items are dealt to the 32 lanes round by round, so a unit that needs a deep level does not hold
+// up its 31 neighbours (thread-per-unit measured 5.1 ms on the 520 k-unit benchmark, this form see DESIGN §4.6).
+// Per round and unit: atomicMin of the error key, then of the candidate index among its holders; that lane updates
+// the pass's running best on a STRICT `<` — candidates of a unit arrive in ascending order over the rounds, so this
+// is np.nanargmin's "first index wins" (triangulation.py:565-566).
+template <int CMAX, bool DISTORT>
+__device__ __forceinline__ void level_pass(const SwapArgs &a, SwapWarp &S, const double *sP, const LensParams *sL,
+                                           long long tile0, uint32_t active, int k, bool swapped, int lane) {
+    const int C = a.n_cams;
+    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    const uint32_t ncand = a.ncand[k];
+    const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
+    if ((active >> lane) & 1u) {
+        S.list[__popc(active & ((1u << lane) - 1u))] = (uint32_t)lane;
+        S.skey[lane] = P2S_KEY_EMPTY;
+    }
+    __syncwarp();
+    const unsigned long long n_items = (unsigned long long)__popc(active) * ncand;
+    float x[CMAX], y[CMAX], w[CMAX], xs[CMAX], ys[CMAX];
+    int loaded = -1;
+    for (unsigned long long base = 0; base < n_items; base += 32) {
+        S.rkey[lane] = P2S_KEY_EMPTY;
+        S.rcand[lane] = 0xffffffffu;
+        __syncwarp();
+        const unsigned long long item = base + (unsigned)lane;
+        const bool live = item < n_items;
+        int slot = 0;
+        uint32_t cand = 0, cm = 0;
+        unsigned long long key = P2S_KEY_EMPTY;
+        double cx = 0, cy = 0, cz = 0;
+        if (live) {
+            slot = (int)S.list[item / ncand];
+            cand = (uint32_t)(item % ncand);
+            cm = (k == 0) ? 0u : (k <= a.max_table_level) ? table[cand] : unrank_subset(C, k, cand);
+            if (slot != loaded) {                                  // consecutive items of a lane mostly stay on one unit
+                const long long u = tile0 + slot, up = S.partner_unit[slot];
+                for (int c = 0; c < C; ++c) {
+                    const float4 o = a.obs[(long long)c * a.n_units + u];
+                    const float4 p = a.obs[(long long)c * a.n_units + up];
+                    x[c] = o.x; y[c] = o.y; w[c] = o.z; xs[c] = p.x; ys[c] = p.y;
+                }
+                loaded = slot;
+            }
+            const uint32_t inv0 = S.inv0[slot];
+            const int n_first = C - min(C, __popc(inv0) + k);       // n_cams - nb_cams_off_tot (:437, :513)
+            double e;
+            evaluate_candidate<CMAX, DISTORT>(sP, sL, x, y, w, xs, ys, C, cmask & ~(inv0 | cm), swapped ? n_first : 0,
+                                              swapped ? n_first : C, cx, cy, cz, e);
+            key = err_key_inf(e);
+            atomicMin(&S.rkey[slot], key);
+        }
+        __syncwarp();
+        if (live && key == S.rkey[slot]) atomicMin(&S.rcand[slot], cand);
+        __syncwarp();
+        if (live && key == S.rkey[slot] && cand == S.rcand[slot] && key < S.skey[slot]) {
+            S.skey[slot] = key;
+            S.q[slot][0] = cx; S.q[slot][1] = cy; S.q[slot][2] = cz;
+            S.cm[slot] = cm;
+        }
+        __syncwarp();
+    }
+}
+
 template <int CMAX, bool DISTORT>
 __global__ void __launch_bounds__(128) lrswap_kernel(const CamParams<CMAX> cams, const LensSet<DISTORT ? CMAX : 1> lens,
                                                      const SwapArgs a) {
     // projection rows and lens models in shared memory: the candidate evaluation indexes them by camera
     __shared__ double sP[CMAX * 12];
     __shared__ LensParams sL[DISTORT ? CMAX : 1];
+    __shared__ SwapWarp sW[4];
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
     if (DISTORT) {
         const double *src = reinterpret_cast<const double *>(&lens);
@@ -95,61 +174,68 @@ __global__ void __launch_bounds__(128) lrswap_kernel(const CamParams<CMAX> cams,
     }
     __syncthreads();
     const int C = a.n_cams;
+    const int lane = threadIdx.x & 31;
+    SwapWarp &S = sW[threadIdx.x >> 5];
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < a.n_units; u += (long long)gridDim.x * blockDim.x) {
-        const int kp = (int)(u % a.n_keypoints);
-        const long long up = u - kp + a.partner[kp];
-        float x[CMAX], y[CMAX], w[CMAX], xs[CMAX], ys[CMAX];
+    const long long n_tiles = (a.n_units + 31) / 32;
+    const long long warp0 = (long long)blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 4;
+    for (long long tile = warp0; tile < n_tiles; tile += n_warps) {               // warp-uniform loop
+        const long long tile0 = tile * 32, u = tile0 + lane;
+        const bool in = u < a.n_units;
         uint32_t nan0 = 0, inv0 = 0;
-        for (int c = 0; c < C; ++c) {
-            const float4 o = a.obs[(long long)c * a.n_units + u];
-            const float4 p = a.obs[(long long)c * a.n_units + up];
-            x[c] = o.x; y[c] = o.y; w[c] = o.z; xs[c] = p.x; ys[c] = p.y;
-            if (o.z != o.z) nan0 |= 1u << c;
-            if (o.z != o.z || o.z == 0.f) inv0 |= 1u << c;
+        if (in) {
+            for (int c = 0; c < C; ++c) {
+                const float wl = a.obs[(long long)c * a.n_units + u].z;
+                if (wl != wl) nan0 |= 1u << c;
+                if (wl != wl || wl == 0.f) inv0 |= 1u << c;
+            }
+            const int kp = (int)(u % a.n_keypoints);
+            S.partner_unit[lane] = u - kp + a.partner[kp];
         }
+        S.inv0[lane] = inv0;
+        __syncwarp();
         const int ninv0 = __popc(inv0);
         double err_min = inf64(), qx = nan64(), qy = nan64(), qz = nan64();
         uint32_t ids = cmask, nexcl = (uint32_t)C;
-        for (int k = 0; err_min > a.thr && C - k >= a.min_cams; ++k) {
+        for (int k = 0;; ++k) {
             const int T = min(C, ninv0 + k);                        // nb_cams_off_tot: the worst candidate's count (:437)
-            if (T > C - a.min_cams) break;                          // :440-441
-            const uint32_t ncand = a.ncand[k];
-            const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
-            unsigned long long bkey = P2S_KEY_EMPTY;
-            for (uint32_t cand = 0; cand < ncand; ++cand) {
-                const uint32_t cm = (k == 0) ? 0u : (k <= a.max_table_level) ? table[cand] : unrank_subset(C, k, cand);
-                double cx, cy, cz, e;
-                evaluate_candidate<CMAX, DISTORT>(sP, sL, x, y, w, xs, ys, C, cmask & ~(inv0 | cm), 0, C, cx, cy, cz, e);
-                const unsigned long long key = err_key_inf(e);
-                if (key < bkey) {                                   // strict <: np.nanargmin's first index
-                    bkey = key; qx = cx; qy = cy; qz = cz;
-                    ids = nan0 | cm; nexcl = (uint32_t)__popc(inv0 | cm);
+            const bool go = in && err_min > a.thr && C - k >= a.min_cams && T <= C - a.min_cams;    // :408, :440-441
+            const uint32_t active = __ballot_sync(0xffffffffu, go);
+            if (!active) break;
+            level_pass<CMAX, DISTORT>(a, S, sP, sL, tile0, active, k, false, lane);
+            if (go) {
+                const unsigned long long key = S.skey[lane];
+                if (key != P2S_KEY_EMPTY) {
+                    qx = S.q[lane][0]; qy = S.q[lane][1]; qz = S.q[lane][2];
+                    ids = nan0 | S.cm[lane]; nexcl = (uint32_t)__popc(inv0 | S.cm[lane]);
                 }
+                err_min = key_err(key);
             }
-            err_min = key_err(bkey);
-            const int n_first = C - T;
-            if (err_min > a.thr && n_first > 2) {                   // :509, :513 with n_cams_swapped = 1
-                unsigned long long skey = P2S_KEY_EMPTY;
-                double sx = 0, sy = 0, sz = 0;
-                uint32_t sids = 0;
-                for (uint32_t cand = 0; cand < ncand; ++cand) {
-                    const uint32_t cm = (k == 0) ? 0u : (k <= a.max_table_level) ? table[cand] : unrank_subset(C, k, cand);
-                    double cx, cy, cz, e;
-                    evaluate_candidate<CMAX, DISTORT>(sP, sL, x, y, w, xs, ys, C, cmask & ~(inv0 | cm), n_first, n_first, cx, cy, cz, e);
-                    const unsigned long long key = err_key_inf(e);
-                    if (key < skey) { skey = key; sx = cx; sy = cy; sz = cz; sids = nan0 | cm; }
+            __syncwarp();
+            const bool go_sw = go && err_min > a.thr && C - T > 2;  // :509, :513 with n_cams_swapped = 1
+            const uint32_t active_sw = __ballot_sync(0xffffffffu, go_sw);
+            if (active_sw) {
+                level_pass<CMAX, DISTORT>(a, S, sP, sL, tile0, active_sw, k, true, lane);
+                if (go_sw) {
+                    const double e_sw = key_err(S.skey[lane]);
+                    if (e_sw < err_min) {                           // :574-577: nb_cams_excluded keeps the un-swapped count
+                        err_min = e_sw;
+                        qx = S.q[lane][0]; qy = S.q[lane][1]; qz = S.q[lane][2];
+                        ids = nan0 | S.cm[lane];
+                    }
                 }
-                const double e_sw = key_err(skey);
-                if (e_sw < err_min) { err_min = e_sw; qx = sx; qy = sy; qz = sz; ids = sids; }    // :574-577
+                __syncwarp();
             }
         }
-        const bool failed = err_min > a.thr;
-        double *q = a.out_Q + u * 3;
-        q[0] = failed ? nan64() : qx; q[1] = failed ? nan64() : qy; q[2] = failed ? nan64() : qz;
-        a.out_err[u] = failed ? nan64() : err_min;
-        a.out_nexcl[u] = (uint8_t)nexcl;
-        a.out_mask[u] = ids;
+        if (in) {
+            const bool failed = err_min > a.thr;
+            double *q = a.out_Q + u * 3;
+            q[0] = failed ? nan64() : qx; q[1] = failed ? nan64() : qy; q[2] = failed ? nan64() : qz;
+            a.out_err[u] = failed ? nan64() : err_min;
+            a.out_nexcl[u] = (uint8_t)nexcl;
+            a.out_mask[u] = ids;
+        }
+        __syncwarp();
     }
 }
 
@@ -173,7 +259,7 @@ static cudaError_t launch_swap(const SwapLaunch &L) {
         a.ncand[k] = (uint32_t)r;
     }
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
-    long long grid = (L.n_units + 127) / 128;
+    long long grid = (L.n_units + 127) / 128;                     // one 32-unit tile per warp and trip, 4 warps per CTA
     const long long cap = (long long)L.sm_count * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;

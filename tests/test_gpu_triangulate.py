@@ -347,3 +347,32 @@ def test_lr_swap_units_match_reference(engine, golden):
     assert torch.allclose(a["Q"], b["Q"], atol=1e-9, rtol=0, equal_nan=True)
     with pytest.raises(ValueError):
         engine.triangulate_lr_swap(obs, [0, 5], wl["P"], 15.0, 2)
+
+
+@pytest.mark.parametrize("C,mc,thr,frames", [(8, 3, 8.0, 12), (5, 2, 4.0, 20), (12, 9, 6.0, 4)])
+def test_lr_swap_matches_oracle_on_swapped_limbs(engine, C, mc, thr, frames):
+    """HALPE_26 units (ragged last tile, 26 does not divide 32) with the limbs swapped in 20 % of the (frame, camera)
+    views: `lrswap_kernel`'s work-item dealing against the per-unit NumPy restatement."""
+    import torch
+    from pose2sim_b200 import skeletons
+    names = skeletons.keypoints("HALPE_26")[1]
+    partner = np.asarray(skeletons.swapped_indices(names))
+    K = len(names)
+    wl = synth.make_triangulation_workload(C, frames, 1, K, seed=31 + C, lik_thr=None, p_out=0.08)
+    sw = np.random.default_rng(5 + C).random((frames, 1, C)) < 0.2
+    planes = {k: np.ascontiguousarray(np.where(sw, wl[k].reshape(frames, K, C)[:, partner, :], wl[k].reshape(frames, K, C))
+                                      .reshape(frames * K, C)) for k in ("x", "y", "lik")}
+    obs = engine.stage_observations(*(torch.from_numpy(planes[k]).cuda() for k in ("x", "y", "lik")), 0.3)
+    res = engine.triangulate_lr_swap(obs, partner, wl["P"], thr, mc)
+    torch.cuda.synchronize()
+    x, y, w = (planes[k].astype(np.float64) for k in ("x", "y", "lik"))
+    low = w < 0.3
+    x[low] = np.nan; y[low] = np.nan; w[low] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oQ, oerr, onexcl, omask = orc.triangulate_units(x, y, w, wl["P"], thr, mc, partner=partner)
+        pQ = orc.triangulate_units(x, y, w, wl["P"], thr, mc)[0]
+    out = {"Q": res["Q"].cpu().numpy(), "err": res["err"].cpu().numpy(), "nexcl": res["nexcl"].cpu().numpy(),
+           "mask": res["mask"].cpu().numpy().view(np.uint32)}
+    compare(out, oQ, oerr, onexcl, omask, thr)
+    assert (~np.isclose(oQ, pQ, atol=1e-9, rtol=0, equal_nan=True).all(axis=1)).sum() > 0     # the swapped pass mattered
