@@ -259,9 +259,10 @@ static cudaError_t launch_swap(const SwapLaunch &L) {
         a.ncand[k] = (uint32_t)r;
     }
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
-    long long grid = (L.n_units + 127) / 128;                     // one 32-unit tile per warp and trip, 4 warps per CTA
-    const long long cap = (long long)L.sm_count * 8;
-    if (grid > cap) grid = cap;
+    // one CTA per 4 tiles, no persistence: tiles differ a lot in cost (a unit may stop at level 0 or walk every level
+    // twice), so the block scheduler does the balancing (a static stride left 32 % of the SM time idle at the tail)
+    long long grid = (L.n_units + 127) / 128;
+    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;                 // the tile loop strides over the rest
     if (grid < 1) grid = 1;
     if (L.lens) {
         LensSet<CMAX> lens;
