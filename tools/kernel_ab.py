@@ -26,7 +26,7 @@ def build(specs):
         name, _, flags = spec.partition(":")
         flags = flags.split()
         objs = []
-        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu", "p2s_multiperson.cu"):
+        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu", "p2s_multiperson.cu", "p2s_lrswap.cu"):
             obj = os.path.join(AB, f"{name}_{src[:-3]}.o")
             r = subprocess.run(NVCC + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
             if r.returncode:
