@@ -83,6 +83,10 @@ __device__ __noinline__ void evaluate_candidate(const double *sP, const LensPara
     err = div_small(sum, (double)(m < n_err ? m : n_err));
 }
 
+#ifndef P2S_SWAP_WARPS
+#define P2S_SWAP_WARPS 1            /* warps per CTA; 4 measured 2.19 ms, see DESIGN §4.6 */
+#endif
+
 // Per-warp exchange area: lane = unit slot of the warp's 32-unit tile.
 struct SwapWarp {
     unsigned long long rkey[32];   // this round's smallest error key per unit
@@ -160,12 +164,12 @@ __device__ __forceinline__ void level_pass(const SwapArgs &a, SwapWarp &S, const
 }
 
 template <int CMAX, bool DISTORT>
-__global__ void __launch_bounds__(128) lrswap_kernel(const CamParams<CMAX> cams, const LensSet<DISTORT ? CMAX : 1> lens,
+__global__ void __launch_bounds__(32 * P2S_SWAP_WARPS) lrswap_kernel(const CamParams<CMAX> cams, const LensSet<DISTORT ? CMAX : 1> lens,
                                                      const SwapArgs a) {
     // projection rows and lens models in shared memory: the candidate evaluation indexes them by camera
     __shared__ double sP[CMAX * 12];
     __shared__ LensParams sL[DISTORT ? CMAX : 1];
-    __shared__ SwapWarp sW[4];
+    __shared__ SwapWarp sW[P2S_SWAP_WARPS];
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
     if (DISTORT) {
         const double *src = reinterpret_cast<const double *>(&lens);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(128) lrswap_kernel(const CamParams<CMAX> cams,
     SwapWarp &S = sW[threadIdx.x >> 5];
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
     const long long n_tiles = (a.n_units + 31) / 32;
-    const long long warp0 = (long long)blockIdx.x * 4 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 4;
+    const long long warp0 = (long long)blockIdx.x * P2S_SWAP_WARPS + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * P2S_SWAP_WARPS;
     for (long long tile = warp0; tile < n_tiles; tile += n_warps) {               // warp-uniform loop
         const long long tile0 = tile * 32, u = tile0 + lane;
         const bool in = u < a.n_units;
@@ -259,9 +263,11 @@ static cudaError_t launch_swap(const SwapLaunch &L) {
         a.ncand[k] = (uint32_t)r;
     }
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
-    // one CTA per 4 tiles, no persistence: tiles differ a lot in cost (a unit may stop at level 0 or walk every level
-    // twice), so the block scheduler does the balancing (a static stride left 32 % of the SM time idle at the tail)
-    long long grid = (L.n_units + 127) / 128;
+    // one CTA per tile, no persistence: tiles differ a lot in cost (a unit may stop at level 0 or walk every level
+    // twice), so the block scheduler does the balancing (a static stride left 32 % of the SM time idle at the tail,
+    // and four-warp CTAs held their slot for the slowest warp: 11.7 of 20 possible warps per SM active)
+    const long long per_cta = 32 * P2S_SWAP_WARPS;
+    long long grid = (L.n_units + per_cta - 1) / per_cta;
     if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;                 // the tile loop strides over the rest
     if (grid < 1) grid = 1;
     if (L.lens) {
@@ -275,11 +281,11 @@ static cudaError_t launch_swap(const SwapLaunch &L) {
             o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
             for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
         }
-        lrswap_kernel<CMAX, true><<<(unsigned)grid, 128, 0, L.stream>>>(cams, lens, a);
+        lrswap_kernel<CMAX, true><<<(unsigned)grid, 32 * P2S_SWAP_WARPS, 0, L.stream>>>(cams, lens, a);
     } else {
         LensSet<1> none;
         std::memset(&none, 0, sizeof none);
-        lrswap_kernel<CMAX, false><<<(unsigned)grid, 128, 0, L.stream>>>(cams, none, a);
+        lrswap_kernel<CMAX, false><<<(unsigned)grid, 32 * P2S_SWAP_WARPS, 0, L.stream>>>(cams, none, a);
     }
     return cudaGetLastError();
 }

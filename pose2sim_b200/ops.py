@@ -82,6 +82,7 @@ class Engine:
         _lib.check(self.h, self.lib.p2s_get_device_info(self.h, C.byref(info)))
         self.info = {"name": info.name.decode(), "sm_count": info.sm_count, "cc": (info.cc_major, info.cc_minor),
                      "clock_khz": info.clock_khz, "total_mem": info.total_mem}
+        self._partner_maps = {}          # keypoint partner maps resident on the device (triangulate_lr_swap)
 
     def close(self):
         if getattr(self, "h", None):
@@ -181,7 +182,9 @@ class Engine:
         if K < 1 or U % K or part.min(initial=0) < 0 or part.max(initial=0) >= K:
             raise ValueError(f"partner must hold K indices in [0, K) with K dividing the {U} units")
         dev = obs.device
-        part_d = torch.from_numpy(part).to(dev)
+        part_d = self._partner_maps.get(part.tobytes())           # the launch is asynchronous: the map must outlive it
+        if part_d is None or part_d.device != dev:
+            part_d = self._partner_maps[part.tobytes()] = torch.from_numpy(part).to(dev)
         out = {"Q": torch.empty((U, 3), dtype=torch.float64, device=dev),
                "err": torch.empty((U,), dtype=torch.float64, device=dev),
                "nexcl": torch.empty((U,), dtype=torch.uint8, device=dev),
@@ -192,7 +195,6 @@ class Engine:
             self.h, _ptr(obs), _ptr(part_d), K, Pm.ctypes.data, C.cast(arr, C.c_void_p) if arr is not None else None,
             U, Cn, float(reproj_thr), int(min_cams),
             _ptr(out["Q"]), _ptr(out["err"]), _ptr(out["nexcl"]), _ptr(out["mask"]), self._stream()))
-        out["_keepalive"] = part_d
         return out
 
     def triangulate_planes(self, x, y, lik, P, lik_thr, reproj_thr, min_cams, out=None, stats=None):
