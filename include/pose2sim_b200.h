@@ -190,7 +190,8 @@ int p2s_triangulate_undistort_host(p2s_handle *h, const float *x, const float *y
  * un-swapped winner's count, :574-577).
  * obs        : staged float4 [n_cams][n_units] (device), units ordered (frame, person, keypoint), so the partner
  *              of unit u is u - u % n_keypoints + partner[u % n_keypoints]  (triangulation.py:838)
- * partner    : DEVICE int32 [n_keypoints], 0 <= partner[k] < n_keypoints (keypoints_idx_swapped, :742-745)
+ * partner    : DEVICE int32 [n_keypoints], 0 <= partner[k] < n_keypoints (keypoints_idx_swapped, :742-745);
+ *              read back and checked (P2S_EINVAL), which synchronises `stream` once per call
  * lens       : HOST pointer to n_cams models (undistort_points) or NULL                                        */
 int p2s_triangulate_lrswap_device(p2s_handle *h, const void *obs, const int32_t *partner, int n_keypoints,
                                   const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,

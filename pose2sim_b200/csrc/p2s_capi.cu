@@ -377,6 +377,13 @@ int p2s_triangulate_lrswap_device(p2s_handle *h, const void *obs, const int32_t 
     rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_units == 0) return P2S_OK;
+    {   // the partner map indexes the observation buffer: check it here rather than trust the caller (K ints, not a hot path)
+        std::vector<int32_t> part((size_t)n_keypoints);
+        P2S_CUDA(h, cudaMemcpyAsync(part.data(), partner, part.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        P2S_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+        for (int32_t v : part)
+            if (v < 0 || v >= n_keypoints) return P2S_EINVAL;
+    }
     p2s::SwapLaunch L;
     L.obs = obs; L.partner = partner; L.n_keypoints = n_keypoints; L.P = P; L.lens = lens;
     L.n_units = n_units; L.n_cams = n_cams; L.min_cams = min_cams; L.sm_count = h->prop.multiProcessorCount;

@@ -376,3 +376,28 @@ def test_lr_swap_matches_oracle_on_swapped_limbs(engine, C, mc, thr, frames):
            "mask": res["mask"].cpu().numpy().view(np.uint32)}
     compare(out, oQ, oerr, onexcl, omask, thr)
     assert (~np.isclose(oQ, pQ, atol=1e-9, rtol=0, equal_nan=True).all(axis=1)).sum() > 0     # the swapped pass mattered
+
+
+def test_lr_swap_c_abi_checks_the_partner_map(engine):
+    """The C entry point reads the device-resident partner map back and refuses indices outside [0, K) and unit
+    counts that K does not divide (P2S_EINVAL = 1) instead of indexing the observation buffer with them."""
+    import torch
+    wl = synth.make_triangulation_workload(4, 3, 1, 2, seed=3, lik_thr=0.3)
+    obs = engine.stage_observations(*(torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik")), None)
+    U = obs.shape[1]
+    P = np.ascontiguousarray(wl["P"], np.float64).reshape(4, 12)
+    Q = torch.empty((U, 3), dtype=torch.float64, device="cuda")
+    err = torch.empty(U, dtype=torch.float64, device="cuda")
+    nexcl = torch.empty(U, dtype=torch.uint8, device="cuda")
+    mask = torch.empty(U, dtype=torch.int32, device="cuda")
+
+    def call(partner, K):
+        part = torch.tensor(partner, dtype=torch.int32, device="cuda")
+        rc = engine.lib.p2s_triangulate_lrswap_device(engine.h, obs.data_ptr(), part.data_ptr(), K, P.ctypes.data, None, U, 4,
+                                                      15.0, 2, Q.data_ptr(), err.data_ptr(), nexcl.data_ptr(), mask.data_ptr(), None)
+        torch.cuda.synchronize()
+        return rc
+
+    assert call([1, 0], 2) == 0
+    assert call([1, 2], 2) == 1 and call([-1, 0], 2) == 1
+    assert call([1, 0, 2, 3], 4) == 1                       # 6 units are not whole blocks of 4 keypoints
