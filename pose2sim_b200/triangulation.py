@@ -58,12 +58,6 @@ def read_settings(config_dict):
     return s
 
 
-def refuse_unsupported(s):
-    """Nothing is refused any more: `undistort_points` and `handle_LR_swap` both run on the device.
-    Kept as the one place where a mode without a device path would be rejected — never a CPU fallback."""
-    return None
-
-
 def swapped_keypoint_indices(keypoints_names):
     """`keypoints_idx_swapped` (triangulation.py:741-749); see `skeletons.swapped_indices`."""
     return _skel.swapped_indices(keypoints_names)
@@ -93,7 +87,6 @@ def stage_project(config_dict, rank=0, world=1):
     """Host staging.  With world > 1 (one process per GPU under torchrun) every rank discovers the whole
     trial but parses only the JSON of its own contiguous frame block (sharding.frame_block)."""
     s = read_settings(config_dict)
-    refuse_unsupported(s)
     session_dir = _calib.session_dir_of(s["project_dir"])
     calib_file = _calib.find_calibration_file(session_dir)
     P = _calib.compute_P(calib_file, undistort=bool(s["undistort_points"]))
