@@ -39,6 +39,24 @@ def triangulate_units(x, y, w, P, thr, min_cams):
     return Q, err, nexcl, mask, level, nc.value
 
 
+def triangulate_units_lr_swap(x, y, w, partner, P, thr, min_cams):
+    """`handle_LR_swap = true`: x, y, w [U, C] float32 with the units ordered (.., keypoint), partner = K keypoint
+    indices.  Returns Q[U,3], err[U], nexcl[U] u8, mask[U] u32."""
+    lib = load()
+    x, y, w = (np.ascontiguousarray(a, np.float32) for a in (x, y, w))
+    U, Cn = x.shape
+    part = np.ascontiguousarray(partner, np.int32).ravel()
+    assert U % part.size == 0 and part.min() >= 0 and part.max() < part.size
+    P = np.ascontiguousarray(np.asarray(P, np.float64).reshape(Cn, 12))
+    Q = np.empty((U, 3)); err = np.empty(U); nexcl = np.empty(U, np.uint8); mask = np.empty(U, np.uint32)
+    lib.p2s_oracle_triangulate_lrswap(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(w.ctypes.data),
+                                      C.c_void_p(part.ctypes.data), C.c_int(part.size), C.c_void_p(P.ctypes.data),
+                                      C.c_longlong(U), C.c_int(Cn), C.c_double(thr), C.c_int(min_cams),
+                                      C.c_void_p(Q.ctypes.data), C.c_void_p(err.ctypes.data), C.c_void_p(nexcl.ctypes.data),
+                                      C.c_void_p(mask.ctypes.data))
+    return Q, err, nexcl, mask
+
+
 def associate_frames(obs, count, P, thr, lik_thr, min_cams):
     """obs: [F, C, NP, 3|4] float32; count [F, C] int32.  Returns err[F], comb[F,C] int8, Q[F,3]."""
     lib = load()

@@ -72,9 +72,12 @@ static void smallest_right_singular_vector(double *A, int n, double v_out[4]) {
     for (int i = 0; i < 4; ++i) v_out[i] = V[i][k];
 }
 
-/* DLT + reprojection + mean pixel error over the cameras in `valid` (ascending). */
-static void solve_subset(const double *P, const double *x, const double *y, const double *w, int C,
-                         uint32_t valid, double Q[3], double *err) {
+/* DLT + reprojection + mean pixel error over the cameras in `valid` (ascending).
+ * handle_LR_swap (triangulation.py:509-579 as executed, see p2s_oracle.py::swapped_pass): with xs != NULL the first
+ * `n_first` valid cameras take the partner keypoint's coordinates (xs, ys) and the error is the mean over those
+ * first `n_first` cameras only (:557-559); the DLT still runs over all valid cameras with the original likelihoods. */
+static void solve_subset_swapped(const double *P, const double *x, const double *y, const double *w, const double *xs,
+                                 const double *ys, int n_first, int C, uint32_t valid, double Q[3], double *err) {
     int m = __builtin_popcount(valid);
     Q[0] = Q[1] = Q[2] = NAN;
     if (m == 0) { *err = NAN; return; }             /* np.mean([]) */
@@ -84,9 +87,10 @@ static void solve_subset(const double *P, const double *x, const double *y, cons
     for (int c = 0; c < C; ++c) {
         if (!((valid >> c) & 1u)) continue;
         const double *Pc = P + c * 12;
+        const double xc = (xs && r < n_first) ? xs[c] : x[c], yc = (xs && r < n_first) ? ys[c] : y[c];
         for (int j = 0; j < 4; ++j) {
-            A[(2 * r) * 4 + j] = (Pc[j] - x[c] * Pc[8 + j]) * w[c];
-            A[(2 * r + 1) * 4 + j] = (Pc[4 + j] - y[c] * Pc[8 + j]) * w[c];
+            A[(2 * r) * 4 + j] = (Pc[j] - xc * Pc[8 + j]) * w[c];
+            A[(2 * r + 1) * 4 + j] = (Pc[4 + j] - yc * Pc[8 + j]) * w[c];
         }
         ++r;
     }
@@ -94,19 +98,28 @@ static void solve_subset(const double *P, const double *x, const double *y, cons
     smallest_right_singular_vector(A, 2 * m, v);
     Q[0] = v[0] / v[3]; Q[1] = v[1] / v[3]; Q[2] = v[2] / v[3];
     double sum = 0;
+    int pos = 0;
     for (int c = 0; c < C; ++c) {
         if (!((valid >> c) & 1u)) continue;
+        if (xs && pos >= n_first) break;
         const double *Pc = P + c * 12;
+        const double xc = xs ? xs[c] : x[c], yc = xs ? ys[c] : y[c];
         double u = Pc[0] * Q[0] + Pc[1] * Q[1] + Pc[2] * Q[2] + Pc[3];
         double vv = Pc[4] * Q[0] + Pc[5] * Q[1] + Pc[6] * Q[2] + Pc[7];
         double d = Pc[8] * Q[0] + Pc[9] * Q[1] + Pc[10] * Q[2] + Pc[11];
-        double dx = x[c] - u / d, dy = y[c] - vv / d;
+        double dx = xc - u / d, dy = yc - vv / d;
         double dist;
         if (isnan(dx) && isnan(dy)) dist = INFINITY;
         else dist = sqrt((isnan(dx) ? 0 : dx * dx) + (isnan(dy) ? 0 : dy * dy));
         sum += dist;
+        ++pos;
     }
-    *err = sum / m;
+    *err = sum / pos;
+}
+
+static void solve_subset(const double *P, const double *x, const double *y, const double *w, int C,
+                         uint32_t valid, double Q[3], double *err) {
+    solve_subset_swapped(P, x, y, w, NULL, NULL, 0, C, valid, Q, err);
 }
 
 /* next k-subset of {0..n-1} in lexicographic order; returns 0 when exhausted */
@@ -119,14 +132,15 @@ static int next_comb(int *idx, int n, int k) {
     return 1;
 }
 
-static void triangulate_unit(const double *P, const float *xf, const float *yf, const float *wf, int C,
-                             double thr, int min_cams, double Q[3], double *err_out, uint8_t *nexcl_out,
-                             uint32_t *mask_out, int *last_level, long long *n_cands) {
-    double x[MAXC], y[MAXC], w[MAXC];
+static void triangulate_unit(const double *P, const float *xf, const float *yf, const float *wf, const float *xsf,
+                             const float *ysf, int C, double thr, int min_cams, double Q[3], double *err_out,
+                             uint8_t *nexcl_out, uint32_t *mask_out, int *last_level, long long *n_cands) {
+    double x[MAXC], y[MAXC], w[MAXC], xs[MAXC], ys[MAXC];
     uint32_t nan0 = 0, inv0 = 0;
     const uint32_t cmask = C >= 32 ? 0xffffffffu : ((1u << C) - 1u);
     for (int c = 0; c < C; ++c) {
         x[c] = xf[c]; y[c] = yf[c]; w[c] = wf[c];
+        xs[c] = xsf ? xsf[c] : NAN; ys[c] = ysf ? ysf[c] : NAN;
         if (isnan(w[c])) { nan0 |= 1u << c; inv0 |= 1u << c; }
         else if (w[c] == 0.0) inv0 |= 1u << c;
     }
@@ -168,6 +182,28 @@ static void triangulate_unit(const double *P, const float *xf, const float *yf, 
         err_min = have ? best : NAN;
         Qb[0] = bQ[0]; Qb[1] = bQ[1]; Qb[2] = bQ[2];
         ids = bnan; nexcl = bexcl; evaluated = k;
+        /* handle_LR_swap: one swapped evaluation per candidate while the level is still above the threshold and
+         * 1 < (n_cams - nb_cams_off_tot) / 2 (:509-513); np.min / argmin over the candidates (:565-566); error, Q and the
+         * id list become the swapped winner's, nb_cams_excluded keeps the un-swapped winner's count (:574-577) */
+        const int n_first = C - worst;
+        if (xsf && err_min > thr && n_first > 2) {
+            for (int i = 0; i < k; ++i) idx[i] = i;
+            double sbest = INFINITY, sQ[3] = {NAN, NAN, NAN};
+            uint32_t sids = 0;
+            int shave = 0, snan = 0;
+            do {
+                uint32_t cm = 0;
+                for (int i = 0; i < k; ++i) cm |= 1u << idx[i];
+                double q[3], e;
+                solve_subset_swapped(P, x, y, w, xs, ys, n_first, C, cmask & ~(inv0 | cm), q, &e);
+                if (isnan(e)) snan = 1;                  /* np.min would be NaN and `NaN < error_min` false; mean of distances is never NaN */
+                if (!shave || e < sbest) { shave = 1; sbest = e; sids = nan0 | cm; sQ[0] = q[0]; sQ[1] = q[1]; sQ[2] = q[2]; }
+            } while (next_comb(idx, C, k));
+            if (!snan && sbest < err_min) {
+                err_min = sbest; ids = sids;
+                Qb[0] = sQ[0]; Qb[1] = sQ[1]; Qb[2] = sQ[2];
+            }
+        }
     }
     if (err_min > thr) { err_min = NAN; Qb[0] = Qb[1] = Qb[2] = NAN; }
     Q[0] = Qb[0]; Q[1] = Qb[1]; Q[2] = Qb[2];
@@ -184,12 +220,25 @@ void p2s_oracle_triangulate(const float *x, const float *y, const float *w, cons
     for (long long u = 0; u < n_units; ++u) {
         int lv;
         long long nc = 0;
-        triangulate_unit(P, x + u * C, y + u * C, w + u * C, C, thr, min_cams, Q + u * 3, err + u, nexcl + u,
+        triangulate_unit(P, x + u * C, y + u * C, w + u * C, NULL, NULL, C, thr, min_cams, Q + u * 3, err + u, nexcl + u,
                          mask + u, &lv, &nc);
         if (level) level[u] = lv;
         total += nc;
     }
     if (n_candidates) *n_candidates = total;
+}
+
+/* handle_LR_swap = true: units ordered (.., keypoint); the swapped coordinates of unit u are those of unit
+ * u - u % n_keypoints + partner[u % n_keypoints] (triangulation.py:838, keypoints_idx_swapped :742-745). */
+void p2s_oracle_triangulate_lrswap(const float *x, const float *y, const float *w, const int32_t *partner,
+                                   int n_keypoints, const double *P, long long n_units, int C, double thr,
+                                   int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long u = 0; u < n_units; ++u) {
+        const long long up = u - u % n_keypoints + partner[u % n_keypoints];
+        triangulate_unit(P, x + u * C, y + u * C, w + u * C, x + up * C, y + up * C, C, thr, min_cams, Q + u * 3,
+                         err + u, nexcl + u, mask + u, NULL, NULL);
+    }
 }
 
 /* obs: [n_frames][C][NP][4] float32; count: [n_frames][C].  out_comb: int8 [n_frames][C], -1 = off. */

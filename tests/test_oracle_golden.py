@@ -214,3 +214,16 @@ def test_lr_swap_units(golden):
         assert np.array_equal(np.isnan(err), np.isnan(g[f"g{gi}_err"]))
         assert np.allclose(Q, g[f"g{gi}_Q"], atol=1e-8, rtol=0, equal_nan=True)
         assert np.allclose(err, g[f"g{gi}_err"], atol=1e-7, rtol=0, equal_nan=True)
+
+
+def test_lr_swap_units_c_oracle(golden):
+    """The plain-C restatement of the swapped pass (oracle/p2s_oracle.c) against the same reference outputs."""
+    import c_oracle as co
+    g = golden("lr_swap_units.npz")
+    for gi, (C, mc, thr, n_pairs, _) in enumerate(g["groups"]):
+        Q, err, nexcl, mask = co.triangulate_units_lr_swap(g[f"g{gi}_x"], g[f"g{gi}_y"], g[f"g{gi}_w"], g["partner"],
+                                                           g[f"g{gi}_P"], float(thr), int(mc))
+        assert np.array_equal(nexcl, g[f"g{gi}_nexcl"]) and np.array_equal(mask, g[f"g{gi}_mask"])
+        assert np.array_equal(np.isnan(err), np.isnan(g[f"g{gi}_err"]))
+        assert np.allclose(Q, g[f"g{gi}_Q"], atol=1e-10, rtol=0, equal_nan=True)
+        assert np.allclose(err, g[f"g{gi}_err"], atol=1e-9, rtol=0, equal_nan=True)
