@@ -177,9 +177,11 @@ def main():
         print("   " + "\n   ".join(l for l in log.splitlines() if l.startswith("-->")))
 
 
-def undistort_trial():
+def undistort_trial(swap_frac=0.0):
     """Ring cameras WITH lens distortion (5 coefficients, like the fork's k3-enabled calibration),
-    observations produced by cv2.projectPoints on the truth, `[triangulation] undistort_points = true`."""
+    observations produced by cv2.projectPoints on the truth, `[triangulation] undistort_points = true`.
+    swap_frac > 0: in that share of the (frame, camera) views every keypoint trades places with its left/right
+    partner (what `handle_LR_swap` is for); the random draws of the base trial are unchanged."""
     import cv2
     from pose2sim_b200 import calib
     ids, names = skeletons.keypoints("HALPE_26")
@@ -204,16 +206,22 @@ def undistort_trial():
     x = np.where(out, x + g.uniform(60, 200, x.shape), x)
     lik[:] = g.uniform(0.5, 1.0, lik.shape)
     lik = np.where(g.random(lik.shape) < 0.06, g.uniform(0.0, 0.3, lik.shape), lik)
+    if swap_frac > 0:
+        part = np.asarray(skeletons.swapped_indices(names))
+        sw = np.random.default_rng(445).random((F, C, 1, 1)) < swap_frac
+        x, y, lik = (np.where(sw, a[..., part], a) for a in (x, y, lik))
     kp = synth_project.pack_openpose(x.astype(np.float32), y.astype(np.float32), lik.astype(np.float32), ids, J)
     return calib_text, cams, kp, None
 
 
-def main_undistort():
+def main_undistort(tag="e2e_tri_undistort", extra=None, swap_frac=0.0):
+    """`extra` = the [triangulation] overrides of the trial; with handle_LR_swap in it the per-unit reference outputs are
+    taken with the partner keypoint's coordinates as `coords_swapped` (triangulation.py:838)."""
     ref = ref_shim.load_reference()
-    calib_text, cams, kp, present = undistort_trial()
+    calib_text, cams, kp, present = undistort_trial(swap_frac)
     with tempfile.TemporaryDirectory() as td:
         proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
-        extra = {"undistort_points": True}
+        extra = dict(extra or {"undistort_points": True})
         cfg = synth_project.base_config(proj, **extra)
         log = run_reference(ref.triangulation.triangulate_all, cfg, proj)
         trcs = sorted(glob.glob(os.path.join(proj, "pose-3d", "*.trc")))
@@ -228,7 +236,8 @@ def main_undistort():
         calib_file = glob.glob(os.path.join(proj, "calibration", "*.toml"))[0]
         Pm = ref.common.computeP(calib_file, undistort=True)
         cp = ref.common.retrieve_calib_params(calib_file)
-        ids, _ = skeletons.keypoints("HALPE_26")
+        ids, names = skeletons.keypoints("HALPE_26")
+        part = skeletons.swapped_indices(names)
         F, C = kp.shape[0], kp.shape[1]
         Kn = len(ids)
         xs = kp[:, :, 0, :][:, :, 3 * np.asarray(ids)].astype(np.float64)                  # [F, C, K]
@@ -242,8 +251,9 @@ def main_undistort():
                 ux[f, c], uy[f, c] = u[:, 0], u[:, 1]
         low = ls < 0.3
         gx, gy, gl = np.where(low, np.nan, ux), np.where(low, np.nan, uy), np.where(low, np.nan, ls)
-        cfg_u = {"triangulation": {"reproj_error_threshold_triangulation": 15, "min_cameras_for_triangulation": 2,
-                                   "handle_LR_swap": False, "undistort_points": True}}
+        cfg_u = {"triangulation": {"reproj_error_threshold_triangulation": extra.get("reproj_error_threshold_triangulation", 15),
+                                   "min_cameras_for_triangulation": 2,
+                                   "handle_LR_swap": bool(extra.get("handle_LR_swap", False)), "undistort_points": True}}
         U = F * Kn
         Qo, eo, no, mo = np.empty((U, 3)), np.empty(U), np.empty(U, np.int32), np.zeros(U, np.uint32)
         with warnings.catch_warnings():
@@ -251,7 +261,8 @@ def main_undistort():
             for f in range(F):
                 for k in range(Kn):
                     coords = np.array([gx[f, :, k], gy[f, :, k], gl[f, :, k]])
-                    q, e, n, idl = ref.triangulation.triangulation_from_best_cameras(cfg_u, coords, coords.copy(), Pm, cp)
+                    swapped = np.array([gx[f, :, part[k]], gy[f, :, part[k]], gl[f, :, part[k]]])
+                    q, e, n, idl = ref.triangulation.triangulation_from_best_cameras(cfg_u, coords, swapped, Pm, cp)
                     u = f * Kn + k
                     Qo[u], eo[u], no[u] = np.asarray(q, float)[:3], e, n
                     for c in np.asarray(idl).ravel():
@@ -260,8 +271,8 @@ def main_undistort():
                    unit_lik=ls.transpose(0, 2, 1).reshape(U, C).astype(np.float32),
                    unit_ux=ux.transpose(0, 2, 1).reshape(U, C).astype(np.float32), unit_uy=uy.transpose(0, 2, 1).reshape(U, C).astype(np.float32),
                    unit_Q=Qo, unit_err=eo, unit_nexcl=no, unit_mask=mo, unit_P=np.array(Pm))
-        np.savez_compressed(os.path.join(GOLDEN, "e2e_tri_undistort.npz"), **out)
-        print("e2e_tri_undistort", [os.path.basename(t) for t in trcs], "triangulated", np.isfinite(eo).mean(), "mean nexcl", no.mean())
+        np.savez_compressed(os.path.join(GOLDEN, tag + ".npz"), **out)
+        print(tag, [os.path.basename(t) for t in trcs], "triangulated", np.isfinite(eo).mean(), "mean nexcl", no.mean())
 
 
 VARIANTS = [
@@ -333,15 +344,22 @@ def main_multi_association():
         print("e2e_assoc_multi: persons per frame", np.bincount(n_people[:, 0]))
 
 
+# both off-by-default flags at once: lens distortion + left/right swapped limbs in 20 % of the views
+UNDISTORT_LRSWAP = {"undistort_points": True, "handle_LR_swap": True, "reproj_error_threshold_triangulation": 6}
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "multi_assoc":
         main_multi_association()
     elif len(sys.argv) > 1 and sys.argv[1] == "undistort":
         main_undistort()
+    elif len(sys.argv) > 1 and sys.argv[1] == "undistort_lrswap":
+        main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         main_variants()
     else:
         main()
         main_multi_association()
         main_undistort()
+        main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
         main_variants()

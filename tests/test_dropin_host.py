@@ -37,7 +37,7 @@ def oracle_units(st):
             "mask": mask.reshape(F, N, K)}
 
 
-@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi", "e2e_tri_undistort"])
+@pytest.mark.parametrize("tag", ["e2e_tri_single", "e2e_tri_multi", "e2e_tri_undistort", "e2e_tri_undistort_lrswap"])
 def test_triangulation_host_pipeline_matches_reference_trc(golden, tmp_path, tag, caplog):
     g = golden(tag + ".npz")
     proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")

@@ -173,6 +173,36 @@ def test_undistort_mode_units(golden):
     assert np.allclose(e, g["unit_err"][sub], atol=E_TOL, rtol=0, equal_nan=True)
 
 
+def test_undistort_with_lr_swap_units(golden):
+    """Both off-by-default flags at once (`undistort_points` + `handle_LR_swap`, limbs swapped in 20 % of the views):
+    the restated swapped pass with the DISTORTED re-projection against the reference's per-unit outputs."""
+    import io
+    import tomllib
+    from pose2sim_b200 import calib, skeletons
+    g = golden("e2e_tri_undistort_lrswap.npz")
+    toml = tomllib.load(io.BytesIO(str(g["calib"]).encode()))
+    lens = []
+    for name in [str(c) for c in g["cams"]]:
+        cam = toml[name]
+        K = np.array(cam["matrix"], float)
+        lens.append({"K": K, "dist": np.array(cam["distortions"], float), "R": calib.rodrigues(cam["rotation"]),
+                     "T": np.array(cam["translation"], float),
+                     "newK": calib.optimal_new_camera_matrix(K, cam["distortions"], cam["size"])})
+    partner = skeletons.swapped_indices(skeletons.keypoints("HALPE_26")[1])
+    lik = g["unit_lik"]
+    low = lik.astype(np.float64) < 0.3
+    gx, gy, gl = (np.where(low, np.nan, a.astype(np.float64)) for a in (g["unit_ux"], g["unit_uy"], lik))
+    n = 26 * 20                                                  # whole frames: partners live in the same frame
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q, e, nx, m = orc.triangulate_units(gx[:n], gy[:n], gl[:n], g["unit_P"], 6.0, 2, lens=lens, partner=partner)
+        q0 = orc.triangulate_units(gx[:n], gy[:n], gl[:n], g["unit_P"], 6.0, 2, lens=lens)[0]
+    assert np.array_equal(nx, g["unit_nexcl"][:n]) and np.array_equal(m, g["unit_mask"][:n])
+    assert np.allclose(q, g["unit_Q"][:n], atol=Q_TOL, rtol=0, equal_nan=True)
+    assert np.allclose(e, g["unit_err"][:n], atol=E_TOL, rtol=0, equal_nan=True)
+    assert (~np.isclose(q, q0, atol=1e-9, rtol=0, equal_nan=True).all(axis=1)).sum() >= 10     # the swapped pass mattered
+
+
 def test_multi_person_oracle_reproduces_reference_frames(golden):
     """oracle/p2s_oracle_mp.py (and the product's integer bookkeeping `multi_person.proposals_from_rows`) against
     146 random frames matched by the live reference (oracle/make_golden_mp.py): thresholded affinity within 1e-9,
