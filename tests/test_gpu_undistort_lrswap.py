@@ -3,9 +3,8 @@ stage kernel's lens inversion feeding `lrswap_kernel<.., DISTORT = true>` (disto
 pass), against what the UNMODIFIED reference produced for a trial with lens distortion and the limbs swapped in 20 % of
 the views (tests/golden/e2e_tri_undistort_lrswap.npz, oracle/make_golden_e2e.py undistort_lrswap).
 
-Written after the round's GPU minutes were spent: the oracle side of this combination is pinned on the CPU
-(tests/test_oracle_golden.py::test_undistort_with_lr_swap_units, tests/test_dropin_host.py), the device side runs here
-for the first time — the file sorts last so that everything else has run before it."""
+The oracle side of this combination is pinned on the CPU (tests/test_oracle_golden.py::test_undistort_with_lr_swap_units,
+tests/test_dropin_host.py)."""
 import numpy as np
 import pytest
 
