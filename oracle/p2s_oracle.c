@@ -21,6 +21,7 @@
  *   reprojection ................... Pose2Sim/common.py:357-375
  *   distance, all-NaN -> inf ....... Pose2Sim/common.py:378-403
  *   exclusion search ............... Pose2Sim/triangulation.py:408-505, :588-602
+ *   handle_LR_swap swapped pass .... Pose2Sim/triangulation.py:509-579 (as executed, see p2s_oracle.py::swapped_pass)
  *   association search ............. Pose2Sim/personAssociation.py:67-99, :154-257
  */
 #include <math.h>

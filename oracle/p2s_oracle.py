@@ -140,8 +140,8 @@ def solve_subset(P, x, y, w, cams, lens=None):
 
 
 # ---------------------------------------------------------------------------------------------
-# triangulation exclusion search  (Pose2Sim/triangulation.py:363-604, handle_LR_swap and
-# undistort_points off, as in every shipped config: SURVEY.md §5)
+# triangulation exclusion search  (Pose2Sim/triangulation.py:363-604; `lens` turns undistort_points on
+# (:472-476), `swapped` / `partner` turn handle_LR_swap on (:509-579) — both off in every shipped config)
 # ---------------------------------------------------------------------------------------------
 def swapped_pass(P, x, y, w, xs, ys, cands, counts, C, lens=None):
     """`handle_LR_swap` branch of one level (triangulation.py:509-579), as the reference EXECUTES it.

@@ -11,8 +11,8 @@ Pose2Sim/triangulation.py:656-959, with the per-(frame, person, keypoint) Python
 There is no CPU implementation of the search in this package: `solve_units` needs the built CUDA
 library and a B200 and raises otherwise.  `[triangulation] undistort_points = true` runs on the device
 too (points undistorted by the stage kernel, distorted re-projection in the search kernel);
-`handle_LR_swap = true` (off in every shipped config) runs on the device as well, in its own plain kernel
-(`p2s_lrswap.cu`), reproducing what the reference executes for that flag.
+`handle_LR_swap = true` (off in every shipped config) runs on the device as well, in its own kernel
+(`p2s_lrswap.cu`), reproducing what the reference executes for that flag; the two flags combine.
 """
 import glob
 import logging
