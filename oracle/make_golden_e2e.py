@@ -289,14 +289,34 @@ VARIANTS = [
 ]
 
 
-def main_variants():
+# a second batch (own file, so that the first one's bytes stay as they are): the remaining interpolation kinds, the
+# empty-list frame range, a threshold tight enough to fail most units (long gaps -> fill rules), a trial whose first
+# and last frames are missing in one camera, every option at a non-default value at once
+VARIANTS_2 = [
+    ("quadratic_gap_50", {"interpolation": "quadratic", "interp_if_gap_smaller_than": 50}, []),
+    ("slinear_incomplete_all", {"interpolation": "slinear", "remove_incomplete_frames": True, "sections_to_keep": "all"}, []),
+    ("frame_range_empty_list", {"frame_range": []}, []),
+    ("thr_3_min_cams_4_last_value", {"reproj_error_threshold_triangulation": 3, "min_cameras_for_triangulation": 4,
+                                     "interp_if_gap_smaller_than": 3}, []),
+    ("edges_missing_largest", {"sections_to_keep": "largest", "fill_large_gaps_with": "nan", "min_chunk_size": 3},
+     [(2, f) for f in range(0, 4)] + [(1, f) for f in range(95, 100)]),
+    ("everything_non_default", {"frame_range": [5, 90], "interpolation": "cubic", "interp_if_gap_smaller_than": 7,
+                                "sections_to_keep": "last", "min_chunk_size": 4,
+                                "fill_large_gaps_with": "zeros", "show_interp_indices": False,
+                                "reproj_error_threshold_triangulation": 10, "likelihood_threshold_triangulation": 0.4,
+                                "min_cameras_for_triangulation": 3}, [(0, 40), (0, 41), (3, 41)]),
+]
+
+
+def main_variants(variants=None, file_name="e2e_tri_variants.npz"):
     """The single-person trial under other settings: frame ranges, trimming / fill / interpolation modes,
     missing files, other thresholds.  Inputs are those of e2e_tri_single.npz; only the reference's TRC text
     per variant is stored."""
+    variants = VARIANTS if variants is None else variants
     ref = ref_shim.load_reference()
     calib_text, cams, kp, present = single_person_trial()
-    out = {"names": np.array([v[0] for v in VARIANTS])}
-    for i, (name, over, missing) in enumerate(VARIANTS):
+    out = {"names": np.array([v[0] for v in variants])}
+    for i, (name, over, missing) in enumerate(variants):
         with tempfile.TemporaryDirectory() as td:
             proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
             for c, f in missing:
@@ -314,7 +334,7 @@ def main_variants():
             out[f"v{i}_trc"] = np.array(open(trcs[0]).read())
             out[f"v{i}_log"] = np.array(log)
             print("variant", name, os.path.basename(trcs[0]))
-    np.savez_compressed(os.path.join(GOLDEN, "e2e_tri_variants.npz"), **out)
+    np.savez_compressed(os.path.join(GOLDEN, file_name), **out)
 
 
 def multi_association_trial():
@@ -357,9 +377,12 @@ if __name__ == "__main__":
         main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         main_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants2":
+        main_variants(VARIANTS_2, "e2e_tri_variants2.npz")
     else:
         main()
         main_multi_association()
         main_undistort()
         main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
         main_variants()
+        main_variants(VARIANTS_2, "e2e_tri_variants2.npz")

@@ -161,11 +161,13 @@ def test_multi_person_association_matches_reference_json(golden, tmp_path, monke
     assert_multi_person_json_equal(proj, g)
 
 
-@pytest.mark.parametrize("i", range(7))
-def test_config_variants_match_reference_trc(golden, tmp_path, i):
-    """Frame ranges, trimming / fill / interpolation modes, missing files, other thresholds."""
+@pytest.mark.parametrize("batch,i", [("e2e_tri_variants.npz", i) for i in range(7)] + [("e2e_tri_variants2.npz", i) for i in range(6)])
+def test_config_variants_match_reference_trc(golden, tmp_path, batch, i):
+    """Frame ranges, trimming / fill / interpolation modes, missing files, other thresholds; second batch: the other
+    interpolation kinds, the empty-list frame range, mostly-failing units, files missing at the trial's edges, every
+    option non-default at once."""
     from dropin_util import rebuild_variant
-    gs, gv = golden("e2e_tri_single.npz"), golden("e2e_tri_variants.npz")
+    gs, gv = golden("e2e_tri_single.npz"), golden(batch)
     proj, cfg = rebuild_variant(gs, gv, i, tmp_path)
     with in_dir(proj):
         st = tri.stage_project(cfg)
