@@ -5,6 +5,7 @@ UNMODIFIED reference wrote for the same trials (tests/golden/e2e_*.npz).
 The device call in the middle is replaced HERE (test code only) by the NumPy oracle; the product
 functions `triangulate_all` / `associate_all` have no such seam and need the CUDA library."""
 import logging
+import os
 import warnings
 
 import numpy as np
@@ -175,3 +176,18 @@ def test_config_variants_match_reference_trc(golden, tmp_path, batch, i):
     got = written_trcs(proj)
     assert list(got) == [str(gv[f"v{i}_trc_name"])], (str(gv["names"][i]), list(got))
     assert_trc_equal(got[str(gv[f"v{i}_trc_name"])], str(gv[f"v{i}_trc"]), tol=1e-6)
+
+
+def test_nothing_triangulated_raises_like_the_reference(golden, tmp_path):
+    """A threshold nothing can meet: the reference raises `Exception('No persons have been triangulated. ...')`
+    (triangulation.py:955-956) and leaves pose-3d empty; checked side by side with the live reference when this test was
+    written."""
+    import glob
+    g = golden("e2e_tri_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    cfg["triangulation"].update(reproj_error_threshold_triangulation=1, min_cameras_for_triangulation=4)
+    with in_dir(proj):
+        st = tri.stage_project(cfg)
+        with pytest.raises(Exception, match="No persons have been triangulated"):
+            tri.write_outputs(st, oracle_units(st))
+    assert glob.glob(os.path.join(proj, "pose-3d", "*")) == []
