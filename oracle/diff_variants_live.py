@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Side-by-side run of the multi-person trial under other settings: the UNMODIFIED reference's `triangulate_all` and
+this package's host pipeline (staging -> oracle units -> re-ID -> TRC; no GPU needed) on the same on-disk trial, TRC
+files compared.  Build-container tool like make_golden_*.py (needs /root/reference); nothing is stored — a mismatch
+here is a host-logic defect to fix, and the case then becomes a golden variant.
+
+    python oracle/diff_variants_live.py 2>&1 | grep -E " OK | MISMATCH |TRC mismatch"
+"""
+import glob
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, os.path.join(ROOT, "tests"), ROOT):
+    sys.path.insert(0, p)
+import ref_shim, make_golden_e2e as mg
+from pose2sim_b200 import synth_project, triangulation as tri
+import test_dropin_host as tdh
+from dropin_util import assert_trc_equal
+ref = ref_shim.load_reference()
+calib_text, cams, kp, present = mg.multi_person_trial()
+print("multi trial", kp.shape)
+CASES = [
+    ("frame_range", {"frame_range": [5, 30]}, []),
+    ("missing+largest", {"sections_to_keep": "largest", "fill_large_gaps_with": "nan"}, [(1, f) for f in range(8, 12)] + [(0, 0)]),
+    ("thr6_min3_cubic", {"reproj_error_threshold_triangulation": 6, "min_cameras_for_triangulation": 3, "interpolation": "cubic", "max_distance_m": 0.3}, []),
+    ("incomplete_first", {"remove_incomplete_frames": True, "sections_to_keep": "first", "min_chunk_size": 3}, []),
+    ("lr_swap", {"handle_LR_swap": True, "reproj_error_threshold_triangulation": 5}, []),
+]
+for name, over, missing in CASES:
+    out = {}
+    for who in ("ref", "ours"):
+        with tempfile.TemporaryDirectory() as td:
+            proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+            for c, f in missing:
+                os.remove(os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json"))
+            prj = {k: over[k] for k in over if k == "frame_range"}
+            cfg = synth_project.base_config(proj, multi_person=True, **{k: v for k, v in over.items() if k not in prj})
+            cfg["project"].update(prj)
+            try:
+                if who == "ref":
+                    mg.run_reference(ref.triangulation.triangulate_all, cfg, proj)
+                else:
+                    with tdh.in_dir(proj):
+                        st = tri.stage_project(cfg)
+                        res = tdh.oracle_units(st)
+                        res = tri.reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
+                        tri.write_outputs(st, res)
+                exc = None
+            except Exception as e:
+                exc = (type(e).__name__, str(e)[:80])
+            out[who] = (exc, {os.path.basename(f): open(f).read() for f in glob.glob(os.path.join(proj, "pose-3d", "*"))})
+    r, o = out["ref"], out["ours"]
+    ok = r[0] == o[0] and sorted(r[1]) == sorted(o[1])
+    worst = 0.0
+    if ok:
+        try:
+            for k in r[1]:
+                worst = max(worst, assert_trc_equal(o[1][k], r[1][k], tol=1e-6))
+        except AssertionError as e:
+            ok = False; print("   TRC mismatch", k, str(e)[:200])
+    print(name, "OK" if ok else "MISMATCH", r[0], o[0], sorted(r[1]), sorted(o[1]), worst)
