@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Error behaviour side by side: broken trials (no calibration, no pose folder, unknown skeleton, camera-count mismatch,
+an empty camera folder, a frame range past the end, nobody in any file) through the UNMODIFIED reference's
+`triangulate_all` / `associate_all` and this package's host pipelines (oracle in place of the device call; no GPU
+needed).  Prints the exception type and message of both.  Build-container tool (needs /root/reference).
+
+    python oracle/diff_errors_live.py 2>&1 | grep -E " SAME | DIFFERENT "
+"""
+import glob
+import os
+import shutil
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, os.path.join(ROOT, "tests"), ROOT):
+    sys.path.insert(0, p)
+
+import make_golden_e2e as mg  # noqa: E402
+import p2s_oracle as orc  # noqa: E402
+import ref_shim  # noqa: E402
+import test_dropin_host as tdh  # noqa: E402
+from pose2sim_b200 import personAssociation as pa  # noqa: E402
+from pose2sim_b200 import synth_project  # noqa: E402
+from pose2sim_b200 import triangulation as tri  # noqa: E402
+
+
+def break_no_calibration(proj, cfg, cams):
+    shutil.rmtree(os.path.join(proj, "calibration"))
+
+
+def break_no_pose(proj, cfg, cams):
+    shutil.rmtree(os.path.join(proj, "pose"))
+
+
+def break_unknown_model(proj, cfg, cams):
+    cfg["pose"]["pose_model"] = "NO_SUCH_MODEL"
+
+
+def break_camera_mismatch(proj, cfg, cams):
+    shutil.rmtree(os.path.join(proj, "pose", f"{cams[-1]}_json"))
+
+
+def break_empty_camera(proj, cfg, cams):
+    for f in glob.glob(os.path.join(proj, "pose", f"{cams[1]}_json", "*.json")):
+        os.remove(f)
+
+
+def break_range_past_end(proj, cfg, cams):
+    cfg["project"]["frame_range"] = [500, 600]
+
+
+def break_nobody(proj, cfg, cams):
+    for f in glob.glob(os.path.join(proj, "pose", "*", "*.json")):
+        with open(f, "w") as out:
+            out.write('{"version": 1.3, "people": []}')
+
+
+BREAKS = [break_no_calibration, break_no_pose, break_unknown_model, break_camera_mismatch, break_empty_camera,
+          break_range_past_end, break_nobody]
+
+
+def ours_triangulate(cfg, proj):
+    with mg.in_dir(proj):
+        st = tri.stage_project(cfg)
+        tri.write_outputs(st, tdh.oracle_units(st))
+
+
+def ours_associate(cfg, proj):
+    with mg.in_dir(proj):
+        st = pa.stage_project(cfg)
+        F, C = st.count.shape
+        err, comb, Q = np.empty(F), np.empty((F, C)), np.empty((F, 3))
+        s = st.settings
+        for f in range(F):
+            ob = [[st.obs[f, c, p, :3].astype(float) for p in range(st.count[f, c])] for c in range(C)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                err[f], comb[f], Q[f] = orc.associate_frame(ob, list(st.count[f]), st.P, s["reproj_thr"], s["lik_thr"], s["min_cams"])
+        pa.write_outputs(st, {"err": err, "comb": comb, "Q": Q}, log=False)
+
+
+def outputs(proj):
+    """What the stage left on disk: relative path -> text (TRC) or re-serialised JSON (NaN-safe comparison)."""
+    import json
+    out = {}
+    for path in sorted(glob.glob(os.path.join(proj, "pose-3d", "*")) + glob.glob(os.path.join(proj, "pose-associated", "*", "*.json"))):
+        with open(path) as f:
+            out[os.path.relpath(path, proj)] = json.dumps(json.load(f), sort_keys=True) if path.endswith(".json") else f.read()
+    return out
+
+
+def outcome(fn, cfg, proj):
+    try:
+        fn(cfg, proj)
+        return ("no exception", ""), outputs(proj)
+    except BaseException as e:                                   # noqa: BLE001 — the point is to see what comes out
+        return (type(e).__name__, " ".join(str(e).split())[:110]), outputs(proj)
+
+
+def main():
+    ref = ref_shim.load_reference()
+    calib_text, cams, kp, present = mg.single_person_trial()
+    kp, present = kp[:20], (present[:20] if present is not None else None)
+    stages = [("triangulate_all", lambda cfg, proj: mg.run_reference(ref.triangulation.triangulate_all, cfg, proj), ours_triangulate),
+              ("associate_all", lambda cfg, proj: mg.run_reference(ref.personAssociation.associate_all, cfg, proj), ours_associate)]
+    for stage, run_ref, run_ours in stages:
+        for brk in BREAKS:
+            res = {}
+            for who, run in (("ref", run_ref), ("ours", run_ours)):
+                with tempfile.TemporaryDirectory() as td:
+                    proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+                    cfg = synth_project.base_config(proj)
+                    brk(proj, cfg, cams)
+                    res[who] = outcome(run, cfg, proj)
+            (r_exc, r_out), (o_exc, o_out) = res["ref"], res["ours"]
+            same = r_exc[0] == o_exc[0] and r_out == o_out
+            print(stage, brk.__name__, "SAME" if same else "DIFFERENT", "| ref:", r_exc, len(r_out), "files | ours:", o_exc, len(o_out), "files")
+
+
+if __name__ == "__main__":
+    main()

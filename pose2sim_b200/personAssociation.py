@@ -115,7 +115,7 @@ def stage_project(config_dict, rank=0, world=1):
     _skel.model_nodes(s["pose_model"], config_dict)          # NameError when the model is unknown (:689-707)
 
     dirs = _stg.PoseDirs(s["project_dir"])
-    cam_dirs = dirs.camera_dirs()
+    cam_dirs = dirs.camera_dirs_for_association()
     _, files = dirs.files_for_association(cam_dirs)
     if rank == 0:
         if not os.path.exists(dirs.tracked_dir):

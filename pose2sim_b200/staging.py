@@ -62,7 +62,7 @@ class PoseDirs:
         self.tracked_dir = os.path.join(project_dir, "pose-associated")
 
     def camera_dirs(self):
-        """triangulation.py:752-758 / personAssociation.py:713-720."""
+        """triangulation.py:752-758: the probe looks into the first folder in `os.walk` order (unsorted)."""
         try:
             names = next(os.walk(self.pose_dir))[1]
             os.listdir(os.path.join(self.pose_dir, names[0]))[0]
@@ -70,6 +70,19 @@ class PoseDirs:
             raise ValueError(f"No json files found in {self.pose_dir} subdirectories. "
                              f"Make sure you run Pose2Sim.poseEstimation() first.")
         names = sort_by_last_number(names)
+        return [k for k in names if "json" in k]
+
+    def camera_dirs_for_association(self):
+        """personAssociation.py:713-720 — not the same statement order as the triangulation stage: the walk happens
+        outside the `try` (a missing pose folder surfaces as the generator's StopIteration), and the probe looks into the
+        first folder AFTER sorting, so another camera's folder may be empty (that camera is then 'none' in every frame)."""
+        names = next(os.walk(self.pose_dir))[1]
+        try:
+            names = sort_by_last_number(names)
+            os.listdir(os.path.join(self.pose_dir, names[0]))[0]
+        except Exception:
+            raise ValueError(f"No json files found in {self.pose_dir} subdirectories. "
+                             f"Make sure you run Pose2Sim.poseEstimation() first.")
         return [k for k in names if "json" in k]
 
     @staticmethod

@@ -191,3 +191,24 @@ def test_nothing_triangulated_raises_like_the_reference(golden, tmp_path):
         with pytest.raises(Exception, match="No persons have been triangulated"):
             tri.write_outputs(st, oracle_units(st))
     assert glob.glob(os.path.join(proj, "pose-3d", "*")) == []
+
+
+def test_association_directory_probe_follows_the_reference(golden, tmp_path):
+    """personAssociation.py:713-720 differs from the triangulation stage's probe (:752-758): the walk is outside the
+    `try` (no pose folder -> StopIteration, not ValueError) and the probe looks into the first folder AFTER sorting, so an
+    empty folder of another camera is accepted and that camera is absent in every frame.  Both checked side by side with
+    the live reference (oracle/diff_errors_live.py)."""
+    import glob
+    import shutil
+    g = golden("e2e_assoc_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_assoc")
+    cams = [str(c) for c in g["cams"]]
+    for f in glob.glob(os.path.join(proj, "pose", f"{cams[1]}_json", "*.json")):
+        os.remove(f)
+    with in_dir(proj):
+        st = pa.stage_project(cfg)
+    assert st.n_cams == len(cams) and (st.count[:, 1] == 0).all() and (st.count[:, 0] > 0).any()
+    assert all(names[1] == "none" for names in st.table)
+    shutil.rmtree(os.path.join(proj, "pose"))
+    with in_dir(proj), pytest.raises(StopIteration):
+        pa.stage_project(cfg)
