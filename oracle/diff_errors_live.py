@@ -24,6 +24,7 @@ import make_golden_e2e as mg  # noqa: E402
 import p2s_oracle as orc  # noqa: E402
 import ref_shim  # noqa: E402
 import test_dropin_host as tdh  # noqa: E402
+from dropin_util import assert_trc_equal  # noqa: E402
 from pose2sim_b200 import personAssociation as pa  # noqa: E402
 from pose2sim_b200 import synth_project  # noqa: E402
 from pose2sim_b200 import triangulation as tri  # noqa: E402
@@ -60,8 +61,62 @@ def break_nobody(proj, cfg, cams):
             out.write('{"version": 1.3, "people": []}')
 
 
+def _files(proj, cam):
+    return sorted(glob.glob(os.path.join(proj, "pose", f"{cam}_json", "*.json")))
+
+
+def odd_truncated_json(proj, cfg, cams):
+    for path in _files(proj, cams[0])[2:5] + _files(proj, cams[2])[7:8]:
+        text = open(path).read()
+        open(path, "w").write(text[:len(text) // 2])
+
+
+def odd_short_and_null_keypoints(proj, cfg, cams):
+    import json
+    for i, path in enumerate(_files(proj, cams[1])[3:9]):
+        js = json.load(open(path))
+        kp = js["people"][0]["pose_keypoints_2d"]
+        js["people"][0]["pose_keypoints_2d"] = kp[:10] if i % 2 else [None if j % 7 == 0 else v for j, v in enumerate(kp)]
+        json.dump(js, open(path, "w"))
+
+
+def odd_people_entries(proj, cfg, cams):
+    import json
+    variants = [["x"], [{}], [{"pose_keypoints_2d": []}], {"not": "a list"}, [{"pose_keypoints_2d": "abc"}], [None]]
+    for path, people in zip(_files(proj, cams[3])[1:7], variants):
+        js = json.load(open(path))
+        js["people"] = people
+        json.dump(js, open(path, "w"))
+
+
+def odd_extra_dirs(proj, cfg, cams):
+    os.mkdir(os.path.join(proj, "pose", f"{cams[0]}_img"))
+    open(os.path.join(proj, "pose", f"{cams[0]}_img", "frame_000001.png"), "w").write("x")
+    open(os.path.join(proj, "pose", f"{cams[0]}_json", "notes.txt"), "w").write("x")
+
+
+def odd_renumbered(proj, cfg, cams):
+    for cam in cams:
+        for path in reversed(_files(proj, cam)):
+            d, name = os.path.split(path)
+            stem, num = name[:-5].rsplit("_", 1)
+            os.rename(path, os.path.join(d, f"{stem}_{int(num) + 100:06d}.json"))
+
+
+def odd_pose_sync(proj, cfg, cams):
+    shutil.copytree(os.path.join(proj, "pose"), os.path.join(proj, "pose-sync"))
+    os.remove(sorted(glob.glob(os.path.join(proj, "pose-sync", f"{cams[0]}_json", "*.json")))[3])
+    for path in _files(proj, cams[1])[:2]:
+        os.remove(path)                                        # pose/ and pose-sync/ now disagree
+
+
+def odd_frame_range_auto(proj, cfg, cams):
+    cfg["project"]["frame_range"] = "auto"
+
+
 BREAKS = [break_no_calibration, break_no_pose, break_unknown_model, break_camera_mismatch, break_empty_camera,
-          break_range_past_end, break_nobody]
+          break_range_past_end, break_nobody, odd_truncated_json, odd_short_and_null_keypoints, odd_people_entries,
+          odd_extra_dirs, odd_renumbered, odd_pose_sync, odd_frame_range_auto]
 
 
 def ours_triangulate(cfg, proj):
@@ -118,7 +173,15 @@ def main():
                     brk(proj, cfg, cams)
                     res[who] = outcome(run, cfg, proj)
             (r_exc, r_out), (o_exc, o_out) = res["ref"], res["ours"]
-            same = r_exc[0] == o_exc[0] and r_out == o_out
+            same = r_exc[0] == o_exc[0] and sorted(r_out) == sorted(o_out)
+            for k in (r_out if same else ()):
+                if k.endswith(".trc"):                          # coordinates within 1e-6 m, everything else identical
+                    try:
+                        assert_trc_equal(o_out[k], r_out[k], tol=1e-6)
+                    except AssertionError:
+                        same = False
+                else:
+                    same = same and r_out[k] == o_out[k]
             print(stage, brk.__name__, "SAME" if same else "DIFFERENT", "| ref:", r_exc, len(r_out), "files | ours:", o_exc, len(o_out), "files")
 
 
