@@ -75,6 +75,8 @@ def odd_short_and_null_keypoints(proj, cfg, cams):
     import json
     for i, path in enumerate(_files(proj, cams[1])[3:9]):
         js = json.load(open(path))
+        if not js["people"]:
+            continue
         kp = js["people"][0]["pose_keypoints_2d"]
         js["people"][0]["pose_keypoints_2d"] = kp[:10] if i % 2 else [None if j % 7 == 0 else v for j, v in enumerate(kp)]
         json.dump(js, open(path, "w"))
@@ -139,6 +141,31 @@ def ours_associate(cfg, proj):
         pa.write_outputs(st, {"err": err, "comb": comb, "Q": Q}, log=False)
 
 
+def ours_associate_multi(cfg, proj):
+    import p2s_oracle_mp as omp
+    from pose2sim_b200 import multi_person as mp
+    with mg.in_dir(proj):
+        st = pa.stage_project(cfg)
+        obs, count, models = pa.stage_multi_person(st)
+        s = st.settings
+        rays = omp.camera_ray_params(models)
+        proposals = []
+        for f in range(len(count)):
+            det = [[obs[f, c, p].astype(float) for p in range(count[f, c])] for c in range(st.n_cams)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                aff, cum = omp.frame_affinity(det, rays, s["reconstruction_error_threshold"], s["min_affinity"])
+            proposals.append(mp.proposals_from_rows(omp.argmax_rows(aff, cum), s["min_cams"]))
+        pa.write_outputs_multi_person(st, proposals, log=False)
+
+
+def ours_triangulate_multi(cfg, proj):
+    with mg.in_dir(proj):
+        st = tri.stage_project(cfg)
+        res = tri.reidentify(tdh.oracle_units(st), st.f_range, st.n_cams, st.settings["max_distance_m"])
+        tri.write_outputs(st, res)
+
+
 def outputs(proj):
     """What the stage left on disk: relative path -> text (TRC) or re-serialised JSON (NaN-safe comparison)."""
     import json
@@ -159,17 +186,24 @@ def outcome(fn, cfg, proj):
 
 def main():
     ref = ref_shim.load_reference()
-    calib_text, cams, kp, present = mg.single_person_trial()
-    kp, present = kp[:20], (present[:20] if present is not None else None)
-    stages = [("triangulate_all", lambda cfg, proj: mg.run_reference(ref.triangulation.triangulate_all, cfg, proj), ours_triangulate),
-              ("associate_all", lambda cfg, proj: mg.run_reference(ref.personAssociation.associate_all, cfg, proj), ours_associate)]
-    for stage, run_ref, run_ours in stages:
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    run_tri = lambda cfg, proj: mg.run_reference(ref.triangulation.triangulate_all, cfg, proj)          # noqa: E731
+    run_assoc = lambda cfg, proj: mg.run_reference(ref.personAssociation.associate_all, cfg, proj)     # noqa: E731
+    single = mg.single_person_trial()
+    stages = [("triangulate_all", single, False, 20, run_tri, ours_triangulate),
+              ("associate_all", single, False, 20, run_assoc, ours_associate),
+              ("triangulate_all[multi_person]", mg.multi_person_trial(), True, 24, run_tri, ours_triangulate_multi),
+              ("associate_all[multi_person]", mg.multi_association_trial(), True, 16, run_assoc, ours_associate_multi)]
+    for stage, (calib_text, cams, kp, present), multi, n_frames, run_ref, run_ours in stages:
+        if only and only not in stage:
+            continue
+        kp, present = kp[:n_frames], (present[:n_frames] if present is not None else None)
         for brk in BREAKS:
             res = {}
             for who, run in (("ref", run_ref), ("ours", run_ours)):
                 with tempfile.TemporaryDirectory() as td:
                     proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
-                    cfg = synth_project.base_config(proj)
+                    cfg = synth_project.base_config(proj, multi_person=multi)
                     brk(proj, cfg, cams)
                     res[who] = outcome(run, cfg, proj)
             (r_exc, r_out), (o_exc, o_out) = res["ref"], res["ours"]

@@ -245,8 +245,10 @@ def count_persons(input_dir, cam_dirs, json_files_names):
             continue
         _, _, _, n_people, _ = read_pose_files(paths, [], 0)
         if (n_people < 0).any():
-            bad = names[int(np.flatnonzero(n_people[:, 0] < 0)[0])]
-            raise ValueError(f"cannot parse {os.path.join(input_dir, cam_dirs[c], bad)}")
+            bad = os.path.join(input_dir, cam_dirs[c], names[int(np.flatnonzero(n_people[:, 0] < 0)[0])])
+            with open(bad) as f:                      # the reference's own statement (:88-89): the same FileNotFoundError /
+                json.load(f)                          # json.JSONDecodeError (a ValueError) with the same position comes out
+            raise ValueError(f"cannot parse {bad}")
         best = max(best, int(n_people.max(initial=0)))
     return best
 

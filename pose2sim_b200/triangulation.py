@@ -204,6 +204,8 @@ def reidentify(res, f_range, n_cams, max_distance_m):
         memory = np.where(np.isnan(last), memory, last)
         cur = Q[fi]
         if f != 0:
+            if N == 0:                          # nobody in any file: sort_people_sports2d unpacks an empty array (:852)
+                raise ValueError("not enough values to unpack (expected 3, got 2)")
             memory, cur_sorted, ids = match_to_previous(memory, cur, max_distance_m)
             for n in range(N):
                 j = ids[n]

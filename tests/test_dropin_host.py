@@ -212,3 +212,25 @@ def test_association_directory_probe_follows_the_reference(golden, tmp_path):
     shutil.rmtree(os.path.join(proj, "pose"))
     with in_dir(proj), pytest.raises(StopIteration):
         pa.stage_project(cfg)
+
+
+def test_multi_person_crashes_of_the_reference_are_kept(golden, tmp_path):
+    """Two accidents of the reference's multi-person triangulation a caller may be catching (side by side with the live
+    reference in oracle/diff_errors_live.py): a truncated JSON surfaces `json.JSONDecodeError` from the person count
+    (triangulation.py:88-89), and a trial with nobody in any file dies in `sort_people_sports2d` with the unpacking
+    ValueError (:852)."""
+    import glob
+    import json
+    g = golden("e2e_tri_multi.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+    files = sorted(glob.glob(os.path.join(proj, "pose", "*", "*.json")))
+    text = open(files[3]).read()
+    open(files[3], "w").write(text[:len(text) // 2])
+    with in_dir(proj), pytest.raises(json.JSONDecodeError):
+        tri.stage_project(cfg)
+    for f in files:
+        open(f, "w").write('{"version": 1.3, "people": []}')
+    with in_dir(proj):
+        st = tri.stage_project(cfg)
+        with pytest.raises(ValueError, match="not enough values to unpack"):
+            tri.reidentify(oracle_units(st), st.f_range, st.n_cams, st.settings["max_distance_m"])
