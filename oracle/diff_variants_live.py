@@ -4,7 +4,10 @@ this package's host pipeline (staging -> oracle units -> re-ID -> TRC; no GPU ne
 files compared.  Build-container tool like make_golden_*.py (needs /root/reference); nothing is stored — a mismatch
 here is a host-logic defect to fix, and the case then becomes a golden variant.
 
-    python oracle/diff_variants_live.py 2>&1 | grep -E " OK | MISMATCH |TRC mismatch"
+    python oracle/diff_variants_live.py [multi|edge] 2>&1 | grep -E " OK | MISMATCH |TRC mismatch"
+
+`edge`: the single-person trial with configuration values at their edges (thresholds 0 / 1, more cameras required than
+exist, unknown option values, reversed and overshooting frame ranges, ...).
 """
 import glob
 import os
@@ -20,8 +23,23 @@ from pose2sim_b200 import synth_project, triangulation as tri
 import test_dropin_host as tdh
 from dropin_util import assert_trc_equal
 ref = ref_shim.load_reference()
-calib_text, cams, kp, present = mg.multi_person_trial()
-print("multi trial", kp.shape)
+TRIALS = {"multi": mg.multi_person_trial(), "single": mg.single_person_trial()}
+EDGE_CASES = [
+    # configuration values at their edges, single-person trial: (name, [triangulation] / [project] / [pose] overrides, missing)
+    ("lik_thr_0", {"likelihood_threshold_triangulation": 0.0}, []),
+    ("lik_thr_1", {"likelihood_threshold_triangulation": 1.0}, []),
+    ("min_cams_5_of_4", {"min_cameras_for_triangulation": 5}, []),
+    ("min_cams_1", {"min_cameras_for_triangulation": 1}, []),
+    ("interp_gap_0", {"interp_if_gap_smaller_than": 0}, []),
+    ("frame_rate_auto", {"frame_rate": "auto"}, []),
+    ("alias_body_with_feet", {"pose_model": "BODY_WITH_FEET"}, []),
+    ("unknown_interpolation", {"interpolation": "spline9"}, []),
+    ("unknown_fill", {"fill_large_gaps_with": "sevens", "interp_if_gap_smaller_than": 2, "reproj_error_threshold_triangulation": 5}, []),
+    ("unknown_sections", {"sections_to_keep": "middle", "reproj_error_threshold_triangulation": 5}, []),
+    ("frame_range_reversed", {"frame_range": [40, 10]}, []),
+    ("frame_range_partly_past_end", {"frame_range": [90, 130]}, []),
+    ("min_chunk_100", {"min_chunk_size": 100, "reproj_error_threshold_triangulation": 5}, []),
+]
 CASES = [
     ("frame_range", {"frame_range": [5, 30]}, []),
     ("missing+largest", {"sections_to_keep": "largest", "fill_large_gaps_with": "nan"}, [(1, f) for f in range(8, 12)] + [(0, 0)]),
@@ -29,16 +47,21 @@ CASES = [
     ("incomplete_first", {"remove_incomplete_frames": True, "sections_to_keep": "first", "min_chunk_size": 3}, []),
     ("lr_swap", {"handle_LR_swap": True, "reproj_error_threshold_triangulation": 5}, []),
 ]
-for name, over, missing in CASES:
+which = sys.argv[1] if len(sys.argv) > 1 else "multi"
+for name, over, missing in (EDGE_CASES if which == "edge" else CASES):
+    calib_text, cams, kp, present = TRIALS["single" if which == "edge" else "multi"]
+    multi = which != "edge"
     out = {}
     for who in ("ref", "ours"):
         with tempfile.TemporaryDirectory() as td:
             proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
             for c, f in missing:
                 os.remove(os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json"))
-            prj = {k: over[k] for k in over if k == "frame_range"}
-            cfg = synth_project.base_config(proj, multi_person=True, **{k: v for k, v in over.items() if k not in prj})
+            prj = {k: over[k] for k in over if k in ("frame_range", "frame_rate")}
+            cfg = synth_project.base_config(proj, multi_person=multi, **{k: v for k, v in over.items() if k not in prj and k != "pose_model"})
             cfg["project"].update(prj)
+            if "pose_model" in over:
+                cfg["pose"]["pose_model"] = over["pose_model"]
             try:
                 if who == "ref":
                     mg.run_reference(ref.triangulation.triangulate_all, cfg, proj)
@@ -46,7 +69,8 @@ for name, over, missing in CASES:
                     with tdh.in_dir(proj):
                         st = tri.stage_project(cfg)
                         res = tdh.oracle_units(st)
-                        res = tri.reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
+                        if multi:
+                            res = tri.reidentify(res, st.f_range, st.n_cams, st.settings["max_distance_m"])
                         tri.write_outputs(st, res)
                 exc = None
             except Exception as e:
