@@ -26,11 +26,22 @@ def _tables():
     return _TABLES
 
 
-def _preorder_dict(node, out):
+# id given to a node of a Config.toml model whose id cannot index a keypoint list (see _preorder_dict): larger than any
+# pose_keypoints_2d, so every lookup misses and the marker is NaN in every frame
+UNREADABLE_ID = 100_000_000
+
+
+def _preorder_dict(node, out, root=True):
+    """Pre-order [(name, id)] of a `[pose.CUSTOM]` table.  The reference turns the string 'None' into None for the ROOT
+    only (triangulation.py:727-729); any other node keeps a string id, passes the `id != None` filter (:735) and becomes a
+    marker whose lookup `keypoints[id * 3]` always fails into the bare `except` (:629-644): a marker that is NaN in every
+    frame.  Such nodes get UNREADABLE_ID here — same marker list, same NaN columns."""
     nid = node.get("id")
-    out.append([node.get("name"), None if nid == "None" else nid])
+    if isinstance(nid, str):
+        nid = None if (root and nid == "None") else UNREADABLE_ID
+    out.append([node.get("name"), nid])
     for child in node.get("children", []) or []:
-        _preorder_dict(child, out)
+        _preorder_dict(child, out, root=False)
     return out
 
 

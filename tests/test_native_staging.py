@@ -93,3 +93,24 @@ def test_count_persons_raises_on_unparsable(tmp_path):
     (cam / "a_1.json").write_text('{"people": [')
     with pytest.raises(ValueError):
         staging.count_persons(str(tmp_path), ["cam1_json"], [["a_0.json", "a_1.json"]])
+
+
+def test_custom_model_string_ids_follow_the_reference(golden, tmp_path):
+    """`[pose.CUSTOM]` from Config.toml: the reference turns the string id 'None' into None for the ROOT only
+    (triangulation.py:727-729); a deeper node with a string id stays a marker whose lookups always fail, i.e. a marker
+    that is NaN in every frame (side by side with the live reference: oracle/diff_models_live.py, model CUSTOM)."""
+    custom = {"name": "Hip", "id": "None", "children": [
+        {"name": "RKnee", "id": 0, "children": [{"name": "RFoot", "id": 5}]},
+        {"name": "Spine", "id": "None", "children": [{"name": "Neck", "id": 2}]}]}
+    cfg = {"pose": {"pose_model": "CUSTOM", "CUSTOM": custom}}
+    ids, names = skeletons.keypoints("CUSTOM", cfg)
+    assert names == ["RKnee", "RFoot", "Spine", "Neck"]                      # the root is dropped, 'Spine' is kept
+    assert ids == [0, 5, skeletons.UNREADABLE_ID, 2]
+    g = golden("e2e_tri_single.npz")
+    proj, _ = rebuild_trial(g, tmp_path, "trial")
+    dirs = staging.PoseDirs(proj)
+    cam_dirs = dirs.camera_dirs()
+    input_dir, files = dirs.files_for_triangulation(cam_dirs)
+    (x, y, lik, _), (px, py, pl) = _both(input_dir, cam_dirs, files, [0, 5], ids, 1)
+    assert np.isnan(x[:, :, 2]).all() and np.isnan(lik[:, :, 2]).all() and np.isfinite(x[:, :, [0, 1, 3]]).all()
+    assert np.array_equal(x, px.astype(np.float32), equal_nan=True) and np.array_equal(lik, pl.astype(np.float32), equal_nan=True)
