@@ -4,7 +4,7 @@
 on-disk trial; the rewritten pose-associated/ trees are compared file by file (existence, and the decoded JSON).
 Build-container tool like make_golden_*.py (needs /root/reference).
 
-    python oracle/diff_assoc_live.py 2>&1 | grep -E " OK | MISMATCH "
+    python oracle/diff_assoc_live.py [multi] 2>&1 | grep -E " OK | MISMATCH "
 """
 import glob
 import json
@@ -36,6 +36,16 @@ CASES = [
 ]
 
 
+CASES_MULTI = [
+    # (name, [personAssociation] multi_person overrides, [triangulation] overrides, [project] overrides, missing files)
+    ("reconstruction_thr_0.03", {"reconstruction_error_threshold": 0.03}, {}, {}, []),
+    ("reconstruction_thr_0.5", {"reconstruction_error_threshold": 0.5}, {}, {}, []),
+    ("min_affinity_0.7", {"min_affinity": 0.7}, {}, {}, []),
+    ("min_cams_3", {}, {"min_cameras_for_triangulation": 3}, {}, []),
+    ("min_cams_4_frame_range_missing", {}, {"min_cameras_for_triangulation": 4}, {"frame_range": [2, 30]}, [(0, 5), (3, 5), (1, 12)]),
+]
+
+
 def tree(proj):
     out = {}
     for path in sorted(glob.glob(os.path.join(proj, "pose-associated", "*", "*.json"))):
@@ -49,38 +59,47 @@ def same_json(a, b):
     return json.dumps(a, sort_keys=True) == json.dumps(b, sort_keys=True)
 
 
+def ours_single(cfg, proj):
+    with mg.in_dir(proj):
+        st = pa.stage_project(cfg)
+        F, C = st.count.shape
+        err, comb, Q = np.empty(F), np.empty((F, C)), np.empty((F, 3))
+        s = st.settings
+        for f in range(F):
+            ob = [[st.obs[f, c, p, :3].astype(float) for p in range(st.count[f, c])] for c in range(C)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                err[f], comb[f], Q[f] = orc.associate_frame(ob, list(st.count[f]), st.P, s["reproj_thr"], s["lik_thr"], s["min_cams"])
+        pa.write_outputs(st, {"err": err, "comb": comb, "Q": Q}, log=False)
+
+
 def main():
+    import diff_errors_live as de
     ref = ref_shim.load_reference()
-    calib_text, cams, kp, present = mg.association_trial()
+    multi = len(sys.argv) > 1 and sys.argv[1] == "multi"
+    calib_text, cams, kp, present = mg.multi_association_trial() if multi else mg.association_trial()
     kp, present = kp[:30], present[:30]
-    for name, single, tri_over, prj, missing in CASES:
+    for name, over, tri_over, prj, missing in (CASES_MULTI if multi else CASES):
         out = {}
         for who in ("ref", "ours"):
             with tempfile.TemporaryDirectory() as td:
                 proj = synth_project.write_project(os.path.join(td, "trial_assoc"), calib_text, cams, kp, present=present)
                 for c, f in missing:
-                    os.remove(os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json"))
-                cfg = synth_project.base_config(proj, **tri_over)
+                    path = os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json")
+                    if os.path.exists(path):
+                        os.remove(path)
+                cfg = synth_project.base_config(proj, multi_person=multi, **tri_over)
                 cfg["project"].update(prj)
-                cfg["personAssociation"]["single_person"].update(single)
-                if "likelihood_threshold_association" in single:
-                    cfg["personAssociation"]["likelihood_threshold_association"] = single["likelihood_threshold_association"]
+                cfg["personAssociation"]["multi_person" if multi else "single_person"].update(over)
+                if "likelihood_threshold_association" in over:
+                    cfg["personAssociation"]["likelihood_threshold_association"] = over["likelihood_threshold_association"]
                 try:
                     if who == "ref":
                         mg.run_reference(ref.personAssociation.associate_all, cfg, proj)
+                    elif multi:
+                        de.ours_associate_multi(cfg, proj)
                     else:
-                        with mg.in_dir(proj):
-                            st = pa.stage_project(cfg)
-                            F, C = st.count.shape
-                            err, comb, Q = np.empty(F), np.empty((F, C)), np.empty((F, 3))
-                            s = st.settings
-                            for f in range(F):
-                                ob = [[st.obs[f, c, p, :3].astype(float) for p in range(st.count[f, c])] for c in range(C)]
-                                with warnings.catch_warnings():
-                                    warnings.simplefilter("ignore")
-                                    err[f], comb[f], Q[f] = orc.associate_frame(ob, list(st.count[f]), st.P, s["reproj_thr"], s["lik_thr"],
-                                                                                s["min_cams"])
-                            pa.write_outputs(st, {"err": err, "comb": comb, "Q": Q}, log=False)
+                        ours_single(cfg, proj)
                     exc = None
                 except Exception as e:
                     exc = (type(e).__name__, str(e)[:80])
