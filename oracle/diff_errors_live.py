@@ -112,13 +112,43 @@ def odd_pose_sync(proj, cfg, cams):
         os.remove(path)                                        # pose/ and pose-sync/ now disagree
 
 
+def _rename_all(proj, cams, fn):
+    for ci, cam in enumerate(cams):
+        for path in _files(proj, cam):
+            d, name = os.path.split(path)
+            stem, num = name[:-5].rsplit("_", 1)
+            new = fn(ci, stem, int(num))
+            if new != name:
+                os.rename(path, os.path.join(d, new + "__tmp"))
+        for path in glob.glob(os.path.join(proj, "pose", f"{cam}_json", "*__tmp")):
+            os.rename(path, path[:-5])
+
+
+def odd_no_zero_padding(proj, cfg, cams):
+    _rename_all(proj, cams, lambda ci, stem, n: f"{stem}_{n}.json")
+
+
+def odd_extra_numbers_in_names(proj, cfg, cams):
+    _rename_all(proj, cams, lambda ci, stem, n: f"take2_{stem}_v3_{n:04d}_keypoints.json" if ci % 2 else f"{stem}_{n:06d}.json")
+
+
+def odd_one_camera_shifted(proj, cfg, cams):
+    _rename_all(proj, cams, lambda ci, stem, n: f"{stem}_{n + (3 if ci == 1 else 0):06d}.json")
+
+
+def odd_duplicate_frame_number(proj, cfg, cams):
+    src = _files(proj, cams[2])[6]
+    shutil.copy(src, os.path.join(os.path.dirname(src), "again_5.json"))     # a second file carrying frame number 5
+
+
 def odd_frame_range_auto(proj, cfg, cams):
     cfg["project"]["frame_range"] = "auto"
 
 
 BREAKS = [break_no_calibration, break_no_pose, break_unknown_model, break_camera_mismatch, break_empty_camera,
           break_range_past_end, break_nobody, odd_truncated_json, odd_short_and_null_keypoints, odd_people_entries,
-          odd_extra_dirs, odd_renumbered, odd_pose_sync, odd_frame_range_auto]
+          odd_extra_dirs, odd_renumbered, odd_pose_sync, odd_frame_range_auto, odd_no_zero_padding, odd_extra_numbers_in_names,
+          odd_one_camera_shifted, odd_duplicate_frame_number]
 
 
 def ours_triangulate(cfg, proj):
@@ -199,6 +229,8 @@ def main():
             continue
         kp, present = kp[:n_frames], (present[:n_frames] if present is not None else None)
         for brk in BREAKS:
+            if len(sys.argv) > 2 and sys.argv[2] not in brk.__name__:
+                continue
             res = {}
             for who, run in (("ref", run_ref), ("ours", run_ours)):
                 with tempfile.TemporaryDirectory() as td:
