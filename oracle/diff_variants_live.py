@@ -39,6 +39,11 @@ EDGE_CASES = [
     ("frame_range_reversed", {"frame_range": [40, 10]}, []),
     ("frame_range_partly_past_end", {"frame_range": [90, 130]}, []),
     ("min_chunk_100", {"min_chunk_size": 100, "reproj_error_threshold_triangulation": 5}, []),
+    ("frame_rate_59.94", {"frame_rate": 59.94}, []),
+    ("frame_rate_float_30", {"frame_rate": 30.0}, []),
+    ("frame_rate_120_range", {"frame_rate": 120, "frame_range": [7, 61]}, []),
+    ("max_distance_tiny_multi_off", {"max_distance_m": 0.001}, []),
+    ("lik_thr_nan_free_0.999", {"likelihood_threshold_triangulation": 0.999, "min_cameras_for_triangulation": 2}, []),
 ]
 CASES = [
     ("frame_range", {"frame_range": [5, 30]}, []),
