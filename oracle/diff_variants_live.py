@@ -4,7 +4,7 @@ this package's host pipeline (staging -> oracle units -> re-ID -> TRC; no GPU ne
 files compared.  Build-container tool like make_golden_*.py (needs /root/reference); nothing is stored — a mismatch
 here is a host-logic defect to fix, and the case then becomes a golden variant.
 
-    python oracle/diff_variants_live.py [multi|edge] 2>&1 | grep -E " OK | MISMATCH |TRC mismatch"
+    python oracle/diff_variants_live.py [multi|edge|undistort] 2>&1 | grep -E " OK | MISMATCH |TRC mismatch"
 
 `edge`: the single-person trial with configuration values at their edges (thresholds 0 / 1, more cameras required than
 exist, unknown option values, reversed and overshooting frame ranges, ...).
@@ -23,7 +23,15 @@ from pose2sim_b200 import synth_project, triangulation as tri
 import test_dropin_host as tdh
 from dropin_util import assert_trc_equal
 ref = ref_shim.load_reference()
-TRIALS = {"multi": mg.multi_person_trial(), "single": mg.single_person_trial()}
+TRIALS = {"multi": mg.multi_person_trial(), "single": mg.single_person_trial(), "undistort": mg.undistort_trial(0.2)}
+UNDISTORT_CASES = [
+    # the trial with lens distortion (limbs swapped in 20 % of the views), `undistort_points = true` throughout
+    ("undistort_frame_range", {"undistort_points": True, "frame_range": [5, 40]}, []),
+    ("undistort_missing_files_thr_8", {"undistort_points": True, "reproj_error_threshold_triangulation": 8}, [(0, 3), (0, 4), (2, 30), (3, 59)]),
+    ("undistort_lr_swap_min_cams_3", {"undistort_points": True, "handle_LR_swap": True, "min_cameras_for_triangulation": 3,
+                                      "reproj_error_threshold_triangulation": 5}, []),
+    ("undistort_off_on_distorted_data", {"undistort_points": False}, []),
+]
 EDGE_CASES = [
     # configuration values at their edges, single-person trial: (name, [triangulation] / [project] / [pose] overrides, missing)
     ("lik_thr_0", {"likelihood_threshold_triangulation": 0.0}, []),
@@ -53,9 +61,9 @@ CASES = [
     ("lr_swap", {"handle_LR_swap": True, "reproj_error_threshold_triangulation": 5}, []),
 ]
 which = sys.argv[1] if len(sys.argv) > 1 else "multi"
-for name, over, missing in (EDGE_CASES if which == "edge" else CASES):
-    calib_text, cams, kp, present = TRIALS["single" if which == "edge" else "multi"]
-    multi = which != "edge"
+for name, over, missing in {"edge": EDGE_CASES, "undistort": UNDISTORT_CASES}.get(which, CASES):
+    calib_text, cams, kp, present = TRIALS[{"edge": "single", "undistort": "undistort"}.get(which, "multi")]
+    multi = which not in ("edge", "undistort")
     out = {}
     for who in ("ref", "ours"):
         with tempfile.TemporaryDirectory() as td:
