@@ -308,6 +308,69 @@ VARIANTS_2 = [
 ]
 
 
+# third batch: configuration values at their edges (the list oracle/diff_variants_live.py `edge` runs side by side with
+# the live reference) stored as goldens so that the GPU box runs them through the device too.  A variant either writes
+# one TRC or raises; the exception's type and message are then the golden.
+VARIANTS_3 = [
+    ("lik_thr_0", {"likelihood_threshold_triangulation": 0.0}, []),
+    ("lik_thr_1", {"likelihood_threshold_triangulation": 1.0}, []),
+    ("min_cams_5_of_4", {"min_cameras_for_triangulation": 5}, []),
+    ("min_cams_1", {"min_cameras_for_triangulation": 1}, []),
+    ("interp_gap_0", {"interp_if_gap_smaller_than": 0}, []),
+    ("frame_rate_auto", {"frame_rate": "auto"}, []),
+    ("alias_body_with_feet", {"pose_model": "BODY_WITH_FEET"}, []),
+    ("unknown_interpolation", {"interpolation": "spline9"}, []),
+    ("unknown_fill", {"fill_large_gaps_with": "sevens", "interp_if_gap_smaller_than": 2, "reproj_error_threshold_triangulation": 5}, []),
+    ("unknown_sections", {"sections_to_keep": "middle", "reproj_error_threshold_triangulation": 5}, []),
+    ("frame_range_reversed", {"frame_range": [40, 10]}, []),
+    ("frame_range_partly_past_end", {"frame_range": [90, 130]}, []),
+    ("min_chunk_100", {"min_chunk_size": 100, "reproj_error_threshold_triangulation": 5}, []),
+    ("frame_rate_59.94", {"frame_rate": 59.94}, []),
+    ("frame_rate_float_30", {"frame_rate": 30.0}, []),
+    ("frame_rate_120_range", {"frame_rate": 120, "frame_range": [7, 61]}, []),
+    ("max_distance_tiny_multi_off", {"max_distance_m": 0.001}, []),
+    ("lik_thr_nan_free_0.999", {"likelihood_threshold_triangulation": 0.999, "min_cameras_for_triangulation": 2}, []),
+]
+PROJECT_KEYS = ("frame_range", "frame_rate")
+
+
+def variant_config(proj, over):
+    """[project] keys, the pose model and [triangulation] keys of a variant's overrides -> config_dict."""
+    prj = {k: over[k] for k in over if k in PROJECT_KEYS}
+    cfg = synth_project.base_config(proj, **{k: v for k, v in over.items() if k not in prj and k != "pose_model"})
+    cfg["project"].update(prj)
+    if "pose_model" in over:
+        cfg["pose"]["pose_model"] = over["pose_model"]
+    return cfg
+
+
+def main_variants_edge(variants=None, file_name="e2e_tri_variants3.npz"):
+    variants = VARIANTS_3 if variants is None else variants
+    ref = ref_shim.load_reference()
+    calib_text, cams, kp, present = single_person_trial()
+    out = {"names": np.array([v[0] for v in variants])}
+    for i, (name, over, missing) in enumerate(variants):
+        with tempfile.TemporaryDirectory() as td:
+            proj = synth_project.write_project(os.path.join(td, "trial_demo"), calib_text, cams, kp, present=present)
+            for c, f in missing:
+                os.remove(os.path.join(proj, "pose", f"{cams[c]}_json", f"{cams[c]}_{f:06d}.json"))
+            cfg = variant_config(proj, over)
+            exc = ""
+            try:
+                run_reference(ref.triangulation.triangulate_all, cfg, proj)
+            except Exception as e:                                   # the reference's own failure is the contract
+                exc = type(e).__name__ + ": " + str(e)[:60]
+            trcs = sorted(glob.glob(os.path.join(proj, "pose-3d", "*.trc")))
+            assert len(trcs) <= 1, (name, trcs)
+            out[f"v{i}_over"] = np.array(json.dumps(over))
+            out[f"v{i}_missing"] = np.array(missing, dtype=np.int64).reshape(-1, 2)
+            out[f"v{i}_exc"] = np.array(exc)
+            out[f"v{i}_trc_name"] = np.array(os.path.basename(trcs[0]) if trcs else "")
+            out[f"v{i}_trc"] = np.array(open(trcs[0]).read() if trcs else "")
+            print("edge variant", name, os.path.basename(trcs[0]) if trcs else None, exc)
+    np.savez_compressed(os.path.join(GOLDEN, file_name), **out)
+
+
 def main_variants(variants=None, file_name="e2e_tri_variants.npz"):
     """The single-person trial under other settings: frame ranges, trimming / fill / interpolation modes,
     missing files, other thresholds.  Inputs are those of e2e_tri_single.npz; only the reference's TRC text
@@ -377,8 +440,11 @@ if __name__ == "__main__":
         main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         main_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants3":
+        main_variants_edge()
     elif len(sys.argv) > 1 and sys.argv[1] == "variants2":
         main_variants(VARIANTS_2, "e2e_tri_variants2.npz")
+        main_variants_edge()
     else:
         main()
         main_multi_association()
@@ -386,3 +452,4 @@ if __name__ == "__main__":
         main_undistort("e2e_tri_undistort_lrswap", UNDISTORT_LRSWAP, swap_frac=0.2)
         main_variants()
         main_variants(VARIANTS_2, "e2e_tri_variants2.npz")
+        main_variants_edge()

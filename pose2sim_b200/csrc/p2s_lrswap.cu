@@ -57,15 +57,33 @@ __device__ __noinline__ void evaluate_candidate(const double *sP, const LensPara
     Sym4 M;
     sym4_zero(M);
     int pos = 0;
+    float wlo = __int_as_float(0x7f800000), whi = 0.f;
 #pragma unroll 1
     for (int c = 0; c < n_cams; ++c) {
         if ((valid >> c) & 1u) {
             const bool sw = pos < n_swapped;
             accumulate_camera(M, sP + c * 12, (double)(sw ? xs[c] : x[c]), (double)(sw ? ys[c] : y[c]), (double)w[c]);
+            wlo = fminf(wlo, fabsf(w[c])); whi = fmaxf(whi, fabsf(w[c]));
             ++pos;
         }
     }
-    smallest_eigvec_secular(M, qx, qy, qz);
+    if (whi > P2S_WIDE_SPREAD * wlo) {
+        // wide likelihood spread: factorisation of A instead of the normal matrix (p2s_math.cuh)
+        Tri4 T;
+        tri4_zero(T);
+        pos = 0;
+#pragma unroll 1
+        for (int c = 0; c < n_cams; ++c) {
+            if ((valid >> c) & 1u) {
+                const bool sw = pos < n_swapped;
+                givens_add_camera(T, sP + c * 12, (double)(sw ? xs[c] : x[c]), (double)(sw ? ys[c] : y[c]), (double)w[c]);
+                ++pos;
+            }
+        }
+        smallest_singvec_jacobi(T, qx, qy, qz);
+    } else {
+        smallest_eigvec_secular(M, qx, qy, qz);
+    }
     double sum = 0.0;
     pos = 0;
 #pragma unroll 1

@@ -14,10 +14,11 @@
 // whose smallest root lies left of A's smallest eigenvalue.  f is concave and decreasing there, so
 // Newton from lam = 0 overshoots once and then converges monotonically and quadratically from the
 // right; a pivot check on the 3x3 LDL^T (positive definite <=> lam left of the pole) with bisection
-// back towards the last lam known to be left of the root makes it unconditional.  It needs 3-6
-// factorisations of a 3x3 (about 45 FP64 instructions each) instead of the ~2000 flops + 100
-// divisions/square roots of six cyclic Jacobi sweeps, returns q already de-homogenised, and agrees
-// with cv2.SVDecomp to ~3e-14 m (measured).  The Jacobi variant is kept below for A/B.
+// back towards the last lam known to be left of the root makes it unconditional.  With the chord step
+// and the first-order final update below it needs 2.03 factorisations of a 3x3 per candidate on cfg2
+// (measured; about 45 FP64 instructions each) instead of the ~2000 flops + 100 divisions/square roots
+// of six cyclic Jacobi sweeps, returns q already de-homogenised, and agrees with cv2.SVDecomp to
+// ~1e-12 m (measured).  The Jacobi variant is kept below for A/B.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -217,6 +218,107 @@ static __device__ __noinline__ int smallest_eigvec_jacobi(const Sym4 &M, double 
 #pragma unroll
     for (int i = 1; i < 4; ++i) if (a[i][i] < dmin) { dmin = a[i][i]; k = i; }
     double w = 1.0 / (k == 0 ? v[3][0] : k == 1 ? v[3][1] : k == 2 ? v[3][2] : v[3][3]);
+    qx = (k == 0 ? v[0][0] : k == 1 ? v[0][1] : k == 2 ? v[0][2] : v[0][3]) * w;
+    qy = (k == 0 ? v[1][0] : k == 1 ? v[1][1] : k == 2 ? v[1][2] : v[1][3]) * w;
+    qz = (k == 0 ? v[2][0] : k == 1 ? v[2][1] : k == 2 ? v[2][2] : v[2][3]) * w;
+    return sweeps;
+}
+
+// ---- wide likelihood spread: factorisation of A instead of A^T A ------------------------------------------------
+// The reference takes the SVD of the weighted 2m x 4 matrix A itself (common.py:347-350, cv2.SVDecomp).  The normal
+// matrix squares the condition number: with valid likelihoods spanning w_max / w_min = s the eigenvector of A^T A
+// is off by ~2e-16 s^2 metres on ring rigs (measured on reference-generated units: 2e-8 m at s = 1e4, 1.7e-4 m at
+// s = 1e6), so units with s > P2S_WIDE_SPREAD — only possible when the likelihood threshold is near 0 — take this
+// path instead, off the common one and still on the device:
+//   1. A = Q R by Givens rotations, the 2m rows streamed through a 4x4 upper-triangular R (10 registers; each row is
+//      rebuilt from P, x, y, w on the fly), which is backward stable column by column;
+//   2. one-sided Jacobi (Hestenes) on R accumulating V: the right singular vector of the smallest singular value of R
+//      is that of A.  ~5 sweeps of 6 column pairs.
+// Agreement with the reference's outputs on tests/golden/tri_wide_likelihood.npz (spreads up to 1e6): 5e-14 m.
+#ifndef P2S_WIDE_SPREAD
+#define P2S_WIDE_SPREAD 128.0f
+#endif
+struct Tri4 {                                       // upper-triangular 4x4
+    double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;
+};
+__device__ __forceinline__ void tri4_zero(Tri4 &R) {
+    R.r00 = R.r01 = R.r02 = R.r03 = R.r11 = R.r12 = R.r13 = R.r22 = R.r23 = R.r33 = 0.0;
+}
+
+// R <- the triangular factor of [R; a^T]  (four Givens rotations; a NaN row makes R NaN, like the reference's SVD)
+static __device__ __noinline__ void givens_add_row(Tri4 &R, double a0, double a1, double a2, double a3) {
+    if (a0 != 0.0) {
+        const double rho = sqrt(fma(R.r00, R.r00, a0 * a0)), c = R.r00 / rho, s = a0 / rho;
+        R.r00 = rho;
+        double t = R.r01; R.r01 = fma(c, t, s * a1); a1 = fma(-s, t, c * a1);
+        t = R.r02; R.r02 = fma(c, t, s * a2); a2 = fma(-s, t, c * a2);
+        t = R.r03; R.r03 = fma(c, t, s * a3); a3 = fma(-s, t, c * a3);
+    }
+    if (a1 != 0.0) {
+        const double rho = sqrt(fma(R.r11, R.r11, a1 * a1)), c = R.r11 / rho, s = a1 / rho;
+        R.r11 = rho;
+        double t = R.r12; R.r12 = fma(c, t, s * a2); a2 = fma(-s, t, c * a2);
+        t = R.r13; R.r13 = fma(c, t, s * a3); a3 = fma(-s, t, c * a3);
+    }
+    if (a2 != 0.0) {
+        const double rho = sqrt(fma(R.r22, R.r22, a2 * a2)), c = R.r22 / rho, s = a2 / rho;
+        R.r22 = rho;
+        const double t = R.r23; R.r23 = fma(c, t, s * a3); a3 = fma(-s, t, c * a3);
+    }
+    if (a3 != 0.0) R.r33 = sqrt(fma(R.r33, R.r33, a3 * a3));
+}
+
+// camera c's two weighted DLT rows (common.py:344-345) into R
+__device__ __forceinline__ void givens_add_camera(Tri4 &R, const double *Pc, double x, double y, double w) {
+    givens_add_row(R, fma(-x, Pc[8], Pc[0]) * w, fma(-x, Pc[9], Pc[1]) * w, fma(-x, Pc[10], Pc[2]) * w, fma(-x, Pc[11], Pc[3]) * w);
+    givens_add_row(R, fma(-y, Pc[8], Pc[4]) * w, fma(-y, Pc[9], Pc[5]) * w, fma(-y, Pc[10], Pc[6]) * w, fma(-y, Pc[11], Pc[7]) * w);
+}
+
+// Right singular vector of R's smallest singular value, de-homogenised.  Returns the number of sweeps.
+static __device__ __noinline__ int smallest_singvec_jacobi(const Tri4 &R, double &qx, double &qy, double &qz) {
+    double g[4][4] = {{R.r00, R.r01, R.r02, R.r03}, {0.0, R.r11, R.r12, R.r13}, {0.0, 0.0, R.r22, R.r23}, {0.0, 0.0, 0.0, R.r33}};
+    double v[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    int sweeps = 0;
+#pragma unroll 1
+    for (; sweeps < 16; ++sweeps) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double al = fma(g[0][p], g[0][p], fma(g[1][p], g[1][p], fma(g[2][p], g[2][p], g[3][p] * g[3][p])));
+                const double be = fma(g[0][q], g[0][q], fma(g[1][q], g[1][q], fma(g[2][q], g[2][q], g[3][q] * g[3][q])));
+                const double ga = fma(g[0][p], g[0][q], fma(g[1][p], g[1][q], fma(g[2][p], g[2][q], g[3][p] * g[3][q])));
+                if (ga * ga > 1e-30 * al * be) {               // |gamma| > 1e-15 sqrt(alpha beta); false for NaN
+                    rotated = true;
+                    const double z = (be - al) / (2.0 * ga);
+                    double t = 1.0 / (fabs(z) + sqrt(fma(z, z, 1.0)));
+                    t = z < 0.0 ? -t : t;
+                    const double c = 1.0 / sqrt(fma(t, t, 1.0)), s = c * t;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double gp = g[i][p], gq = g[i][q];
+                        g[i][p] = fma(c, gp, -s * gq);
+                        g[i][q] = fma(s, gp, c * gq);
+                        const double vp = v[i][p], vq = v[i][q];
+                        v[i][p] = fma(c, vp, -s * vq);
+                        v[i][q] = fma(s, vp, c * vq);
+                    }
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    double n[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n[j] = fma(g[0][j], g[0][j], fma(g[1][j], g[1][j], fma(g[2][j], g[2][j], g[3][j] * g[3][j])));
+    int k = 0;
+    double nmin = n[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) if (n[j] < nmin) { nmin = n[j]; k = j; }
+    const double s4 = n[0] + n[1] + n[2] + n[3];
+    if (!(s4 == s4)) { qx = qy = qz = nan64(); return sweeps; }       // NaN in A: cv2.SVDecomp returns NaN
+    const double w = 1.0 / (k == 0 ? v[3][0] : k == 1 ? v[3][1] : k == 2 ? v[3][2] : v[3][3]);
     qx = (k == 0 ? v[0][0] : k == 1 ? v[0][1] : k == 2 ? v[0][2] : v[0][3]) * w;
     qy = (k == 0 ? v[1][0] : k == 1 ? v[1][1] : k == 2 ? v[1][2] : v[1][3]) * w;
     qz = (k == 0 ? v[2][0] : k == 1 ? v[2][1] : k == 2 ? v[2][2] : v[2][3]) * w;

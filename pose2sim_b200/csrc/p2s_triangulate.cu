@@ -192,6 +192,91 @@ __device__ __forceinline__ void rebuild_without_poisoned(double (*m0)[32], const
     }
 }
 
+// ---- units whose valid likelihoods span more than P2S_WIDE_SPREAD ------------------------------------------------
+// Their whole exclusion search runs here, one lane per unit, candidate after candidate, every candidate solved from a
+// factorisation of A itself (Givens QR streamed over the cameras in ascending order + one-sided Jacobi on R,
+// p2s_math.cuh) instead of the normal matrix.  Same loop rules as the main level loop (triangulation.py:408-505).
+// Only reachable with a likelihood threshold near 0, so: rolled loops, not inlined, called once per tile AFTER the
+// level loop where few values are live (an ABI call inside the candidate loop costs the common path its registers).
+struct WideArgs {
+    const double *sP;                  // projection matrices (shared memory)
+    const LensParams *lens;            // DISTORT: lens models (shared memory), else null
+    const float2 (*xy)[32];
+    const float (*wt)[32];
+    const uint32_t *table;             // lexicographic subset table, levels concatenated from level 0
+    int max_table_level, n_cams, min_cams, ul;
+    double thr;
+    uint32_t nan0, inv0;
+};
+struct WideRes {
+    double qx, qy, qz, err;
+    uint32_t ids, nexcl;
+    int last_level;
+    uint32_t cands, cams, sweeps, solved;
+};
+
+template <bool DISTORT>
+static __device__ __noinline__ void search_wide_unit(const WideArgs &A, WideRes &R) {
+    const int C = A.n_cams, ul = A.ul;
+    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    const int ninv0 = __popc(A.inv0);
+    double err_min = inf64();
+    uint32_t off = 0;
+    R.qx = R.qy = R.qz = nan64();
+    R.ids = cmask; R.nexcl = (uint32_t)C; R.last_level = -1;
+    R.cands = R.cams = R.sweeps = R.solved = 0;
+#pragma unroll 1
+    for (int k = 0; k <= C; ++k) {
+        if (!(err_min > A.thr) || C - k < A.min_cams || min(C, ninv0 + k) > C - A.min_cams) break;
+        const uint32_t ncand = binom_u32(C, k);
+        unsigned long long bkey = P2S_KEY_EMPTY;
+        uint32_t bnan = 0, bexcl = 0;
+        double bqx = nan64(), bqy = bqx, bqz = bqx;
+#pragma unroll 1
+        for (uint32_t cand = 0; cand < ncand; ++cand) {
+            const uint32_t cm = (k == 0) ? 0u : (k <= A.max_table_level) ? __ldg(A.table + off + cand) : unrank_subset(C, k, cand);
+            const uint32_t invset = A.inv0 | cm;
+            const uint32_t valid = cmask & ~invset;
+            const int m = __popc(valid);
+            double qx, qy, qz, e;
+            if (m < 2) {
+                qx = qy = qz = nan64();
+                e = (m == 0) ? nan64() : inf64();
+            } else {
+                Tri4 T;
+                tri4_zero(T);
+#pragma unroll 1
+                for (int c = 0; c < C; ++c) {
+                    if (!((valid >> c) & 1u)) continue;
+                    const float2 o = A.xy[c][ul];
+                    givens_add_camera(T, A.sP + c * 12, (double)o.x, (double)o.y, (double)A.wt[c][ul]);
+                }
+                R.sweeps += (uint32_t)smallest_singvec_jacobi(T, qx, qy, qz);
+                R.solved += 1u;
+                double sum = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < C; ++c) {
+                    if (!((valid >> c) & 1u)) continue;
+                    const float2 o = A.xy[c][ul];
+                    if (DISTORT) sum += reproj_distance_distorted(A.lens[c], qx, qy, qz, (double)o.x, (double)o.y);
+                    else sum += reproj_distance(A.sP + c * 12, qx, qy, qz, (double)o.x, (double)o.y);
+                }
+                e = sum * (1.0 / (double)m);
+            }
+            R.cands += 1u; R.cams += (uint32_t)m;
+            const unsigned long long key = err_key_inf(e);
+            if (key < bkey) {                                   // strict <: the first index wins (np.nanargmin)
+                bkey = key; bnan = A.nan0 | cm; bexcl = (uint32_t)__popc(invset);
+                bqx = qx; bqy = qy; bqz = qz;
+            }
+        }
+        err_min = key_err(bkey);
+        R.qx = bqx; R.qy = bqy; R.qz = bqz; R.ids = bnan; R.nexcl = bexcl; R.last_level = k;
+        off += ncand;
+    }
+    R.err = err_min;
+}
+
 // min over the aligned group of W = 2^k lanes this lane belongs to (all 32 lanes take part)
 // P2S_SHFL_ARGMIN (A/B switch): xor-shuffle butterfly; default: ONE redux.sync over the group's member mask
 // (every group of the warp executes the same instruction with its own mask, like a cooperative-groups tile).
@@ -245,6 +330,13 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     const int warp = threadIdx.x >> 5;
     double *sP = reinterpret_cast<double *>(smem_raw);                 // projection matrices for dynamic camera index
     WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
+    // DISTORT: lens models for the wide-spread path's dynamic camera index, behind the slabs
+    LensParams *sLens = reinterpret_cast<LensParams *>(smem_raw + CMAX * 12 * sizeof(double) + 4 * sizeof(WarpSlab<CMAX>));
+    if (DISTORT) {
+        const double *src = reinterpret_cast<const double *>(&lens);
+        double *dst = reinterpret_cast<double *>(sLens);
+        for (int i = threadIdx.x; i < (int)(CMAX * sizeof(LensParams) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+    }
 
     const int C = EXACT ? CMAX : a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
@@ -396,16 +488,28 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 if (lane == 0 && (long long)nt < n_tiles) { fence_proxy_async(); issue_tile(nt); }
             }
         }
+        float wlo = __int_as_float(0x7f800000), whi = 0.f;         // smallest / largest valid |likelihood| of the unit
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
             const float lz = S.w[c][lane];
             const bool isn = lz != lz;
             nan0 |= (uint32_t)isn << c;
             inv0 |= (uint32_t)(isn || lz == 0.f) << c;
+            const float la = fabsf(lz);
+            whi = fmaxf(whi, la);                                  // fmaxf / fminf skip NaN
+            wlo = fminf(wlo, la > 0.f ? la : wlo);
         }
         nan0 &= cmask; inv0 &= cmask;
         S.nan0[lane] = nan0;
         S.inv0[lane] = inv0;
+        // units whose valid likelihoods span more than P2S_WIDE_SPREAD solve every candidate from a factorisation of A
+        // (p2s_math.cuh, "wide likelihood spread"); never the case with a likelihood threshold >= 1 / 128
+#ifdef P2S_NO_WIDE                                             /* A/B switch, tools/kernel_ab.py */
+        const bool wide = false;
+#else
+        const bool wide = whi > P2S_WIDE_SPREAD * wlo;
+#endif
+        const uint32_t wide_mask = __ballot_sync(P2S_FULL, wide && active);
 
         // ---- per-unit state (owner lane) -----------------------------------------------------
         double err_min = inf64();
@@ -423,7 +527,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         for (int k = 0; k < C || k == 0; ++k) {
             // reference loop condition (:408) and break rule (:437-441) in closed form:
             // max_i |inv0 U cand_i| = min(C, |inv0| + k)
-            const bool pend = active && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
+            const bool pend = active && !wide && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
                               !(min(C, ninv0 + k) > C - a.min_cams);
             const uint32_t pmask = __ballot_sync(P2S_FULL, pend);
             if (pmask == 0) break;
@@ -590,6 +694,22 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 band_arg |= (fl & 0x100u) != 0;
                 band_thr |= fabs(err_min - a.thr) < a.band_eps;
                 last_level = k;
+            }
+            __syncwarp();
+        }
+
+        // ---- units with a wide likelihood spread: whole search on the factorisation of A (off the common path) ----
+        if (wide_mask != 0u) {
+            if (wide && active) {
+                WideArgs wa;
+                wa.sP = sP; wa.lens = DISTORT ? sLens : nullptr; wa.xy = S.xy; wa.wt = S.w;
+                wa.table = a.cand_masks; wa.max_table_level = a.max_table_level; wa.n_cams = C; wa.min_cams = a.min_cams;
+                wa.ul = lane; wa.thr = a.thr; wa.nan0 = nan0; wa.inv0 = inv0;
+                WideRes wr;
+                search_wide_unit<DISTORT>(wa, wr);
+                err_min = wr.err; qx = wr.qx; qy = wr.qy; qz = wr.qz; ids = wr.ids; nexcl = wr.nexcl; last_level = wr.last_level;
+                band_thr |= fabs(err_min - a.thr) < a.band_eps;
+                t_cands += wr.cands; t_cams += wr.cams; t_iters += wr.sweeps; t_solved += wr.solved;
             }
             __syncwarp();
         }
@@ -897,7 +1017,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
             o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
             for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
         }
-        return launch_persistent(triangulate_kernel<CMAX, 0, true, false, true>, smem, L, grid_out, cams, lens, a);
+        return launch_persistent(triangulate_kernel<CMAX, 0, true, false, true>, smem + sizeof(LensSet<CMAX>), L, grid_out, cams, lens, a);
     }
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);

@@ -101,7 +101,28 @@ def rebuild_variant(g_single, g_var, i, tmp_path):
     for c, f in g_var[f"v{i}_missing"]:
         os.remove(os.path.join(proj, "pose", f"{cams[int(c)]}_json", f"{cams[int(c)]}_{int(f):06d}.json"))
     over = json.loads(str(g_var[f"v{i}_over"]))
-    prj = {k: over[k] for k in over if k in ("frame_range",)}
-    cfg = synth_project.base_config(proj, **{k: over[k] for k in over if k not in prj})
+    prj = {k: over[k] for k in over if k in ("frame_range", "frame_rate")}
+    cfg = synth_project.base_config(proj, **{k: over[k] for k in over if k not in prj and k != "pose_model"})
     cfg["project"].update(prj)
+    if "pose_model" in over:
+        cfg["pose"]["pose_model"] = over["pose_model"]
     return proj, cfg
+
+
+def check_variant_outcome(g_var, i, proj, run):
+    """Run `run()` in the trial directory and compare with what the reference did for variant i: the one TRC it wrote
+    (header identical, coordinates within 1e-6 m), or nothing, and the exception it raised if any (third batch,
+    tests/golden/e2e_tri_variants3.npz stores `v{i}_exc`)."""
+    want_exc = str(g_var[f"v{i}_exc"]) if f"v{i}_exc" in g_var.files else ""
+    got_exc = ""
+    with in_dir(proj):
+        try:
+            run()
+        except Exception as e:
+            got_exc = type(e).__name__ + ": " + str(e)[:60]
+    assert got_exc == want_exc, (str(g_var["names"][i]), got_exc, want_exc)
+    got = written_trcs(proj)
+    name = str(g_var[f"v{i}_trc_name"])
+    assert list(got) == ([name] if name else []), (str(g_var["names"][i]), list(got), name)
+    if name:
+        assert_trc_equal(got[name], str(g_var[f"v{i}_trc"]), tol=1e-6)

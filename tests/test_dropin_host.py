@@ -162,6 +162,19 @@ def test_multi_person_association_matches_reference_json(golden, tmp_path, monke
     assert_multi_person_json_equal(proj, g)
 
 
+@pytest.mark.parametrize("i", range(18))
+def test_edge_config_variants_match_reference(golden, tmp_path, i):
+    """Configuration values at their edges (third batch): the reference's TRC, its writing nothing, or its exception."""
+    from dropin_util import check_variant_outcome, rebuild_variant
+    gs, gv = golden("e2e_tri_single.npz"), golden("e2e_tri_variants3.npz")
+    proj, cfg = rebuild_variant(gs, gv, i, tmp_path)
+
+    def run():
+        st = tri.stage_project(cfg)
+        tri.write_outputs(st, oracle_units(st))
+    check_variant_outcome(gv, i, proj, run)
+
+
 @pytest.mark.parametrize("batch,i", [("e2e_tri_variants.npz", i) for i in range(7)] + [("e2e_tri_variants2.npz", i) for i in range(6)])
 def test_config_variants_match_reference_trc(golden, tmp_path, batch, i):
     """Frame ranges, trimming / fill / interpolation modes, missing files, other thresholds; second batch: the other

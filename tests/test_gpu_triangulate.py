@@ -61,6 +61,21 @@ def test_reference_random_units(engine, golden):
     assert worst < 1e-9          # in practice ~1e-13 m: far inside the 1e-6 m bar
 
 
+def test_wide_likelihood_spread_matches_reference(engine, golden):
+    """Valid likelihoods of one unit spanning 1e-4 ... 1 and 1e-6 ... 1 (`likelihood_threshold_triangulation = 0` is a
+    legal configuration): the reference takes the SVD of A (common.py:347-350); the normal matrix would be off by up to
+    1.7e-4 m on these reference-generated units, the kernel's factorisation-of-A path (p2s_math.cuh) must keep the
+    north_star bar of 1e-6 m — and is held to 1e-9 m here."""
+    g = golden("tri_wide_likelihood.npz")
+    worst = 0.0
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        for lik_thr in (None, 0.0):                              # staged likelihoods as they are / through the gate at 0
+            out = engine.triangulate_host(x, y, w, P, lik_thr, thr, mc)
+            assert compare(out, Q, err, nexcl, mask, thr, allow_band=False) == 0, name
+            worst = max(worst, float(np.nanmax(np.abs(out["Q"] - Q), initial=0.0)))
+    assert worst < 1e-9, worst
+
+
 def test_reference_cfg1_demo_cameras(engine, golden):
     g = golden("tri_cfg1_demo.npz")
     thr, mc = g["params"]

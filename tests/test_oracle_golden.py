@@ -81,6 +81,44 @@ def test_association_frames(golden):
             assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
 
 
+def test_wide_likelihood_units(golden):
+    """Valid likelihoods spanning up to 1e6 within a unit (likelihood threshold 0): both restatements factorise A itself
+    like the reference's SVD, so they stay at rounding level where the normal matrix would be off by 1e-4 m."""
+    import c_oracle as co
+    g = golden("tri_wide_likelihood.npz")
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        q, e, nx, m, lv, nc = co.triangulate_units(x, y, w, P, thr, mc)
+        assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask), name
+        assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+        assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+        sel = slice(0, len(x), 5)
+        _check_units(P, x[sel], y[sel], w[sel], thr, mc, Q[sel], err[sel], nexcl[sel], mask[sel])
+
+
+def test_six_person_association_frames(golden):
+    """Six persons per camera (BASELINE configs[3]'s person count) on 4 and 5 cameras, reference-generated."""
+    import c_oracle as co
+    g = golden("assoc_six_persons.npz")
+    for i in range(int(g["assoc_n"])):
+        p = f"assoc{i}_"
+        thr, lt, mc = g[p + "params"]
+        e, comb, Q = co.associate_frames(g[p + "obs"], g[p + "count"], g[p + "P"], float(thr), float(lt), int(mc))
+        assert np.array_equal(comb.astype(int), np.nan_to_num(g[p + "comb"], nan=-1).astype(int)), i
+        assert np.allclose(e, g[p + "err"], atol=E_TOL, rtol=0)
+        assert np.allclose(Q, g[p + "Q"], atol=Q_TOL, rtol=0, equal_nan=True)
+    # the NumPy restatement on the cheapest frames of the first configuration
+    p = "assoc0_"
+    thr, lt, mc = g[p + "params"]
+    obs, cnt = g[p + "obs"].astype(float), g[p + "count"]
+    for f in range(0, 6):
+        ob = [[obs[f, c, pp] for pp in range(cnt[f, c])] for c in range(obs.shape[1])]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            e, comb, Q = orc.associate_frame(ob, list(cnt[f]), g[p + "P"], float(thr), float(lt), int(mc))
+        assert np.array_equal(np.nan_to_num(comb, nan=-1), np.nan_to_num(g[p + "comb"][f], nan=-1)), f
+        assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
+
+
 def test_subset_order_is_itertools():
     """The kernel's candidate tables must follow itertools.combinations order (triangulation.py:411)."""
     import itertools
