@@ -69,6 +69,8 @@ enum {
     P2S_STAT_DIRECT_CAMS = 41,   /* level 0: valid cameras accumulated straight into the normal matrix */
     P2S_STAT_BLOCKS = 42,        /* levels >= 1: per-camera 4x4 blocks built (valid cameras x unit x level) */
     P2S_STAT_ENTRY_ADDS = 43,    /* levels >= 1: FP64 additions forming M_all and M_all -/+ blocks     */
+    P2S_STAT_WIDE_UNITS = 44,    /* units whose valid likelihoods span more than 1024x: solved from a QR
+                                    factorisation of A (like the reference's SVD) by the fix-up kernel   */
     P2S_STAT_COUNT = 48
 };
 
@@ -94,6 +96,9 @@ typedef struct p2s_device_info {
 } p2s_device_info;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
+/* A handle is used by ONE host thread at a time.  Every launch draws its tile / arrival counters from a ring of 256
+ * entries owned by the handle: at most 256 launches of the *_device entry points may be in flight (enqueued on user
+ * streams and not yet finished) per handle; a caller that pipelines deeper than that creates a second handle.   */
 int p2s_create(int device, p2s_handle **out);
 int p2s_destroy(p2s_handle *h);
 const char *p2s_status_string(int status);

@@ -29,6 +29,7 @@ STAT_SOLVED = 40
 STAT_DIRECT_CAMS = 41
 STAT_BLOCKS = 42
 STAT_ENTRY_ADDS = 43
+STAT_WIDE_UNITS = 44
 
 STATUS = {0: "P2S_OK", 1: "P2S_EINVAL", 2: "P2S_ENODEVICE", 3: "P2S_ECUDA", 4: "P2S_ENOMEM", 5: "P2S_ETOODEEP"}
 

@@ -60,7 +60,7 @@ struct p2s_handle {
 
 namespace {
 
-constexpr int kCounterRing = 256;                 // pairs {tile dispenser, CTAs finished}; one extra word = error bits
+constexpr int kCounterRing = 256;                 // {tile dispenser, fix-up CTAs finished, wide tiles, -} per launch; one extra word = error bits
 
 int cuda_fail(p2s_handle *h, cudaError_t e, const char *what) {
     char buf[512];
@@ -124,12 +124,28 @@ int build_table(p2s_handle *h, int n) {
 }
 
 unsigned int *next_counter(p2s_handle *h) {
-    unsigned int *c = h->d_counters + 2 * h->counter_next;
+    unsigned int *c = h->d_counters + 4 * h->counter_next;
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     return c;
 }
 
-unsigned int *error_word(p2s_handle *h) { return h->d_counters + 2 * kCounterRing; }
+unsigned int *error_word(p2s_handle *h) { return h->d_counters + 4 * kCounterRing; }
+
+// Any early return out of a chunk loop (P2S_CUDA, a non-zero rc) must not leave asynchronous copies into the CALLER's
+// buffers in flight: this guard drains the slot streams on the way out.
+struct DrainSlots {
+    p2s_handle *h;
+    explicit DrainSlots(p2s_handle *hh) : h(hh) {}
+    ~DrainSlots() { for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(h->slots[k].stream); }
+};
+struct EventList {                                 // trace events are destroyed on every path
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t begin = nullptr;
+    ~EventList() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        if (begin) cudaEventDestroy(begin);
+    }
+};
 
 struct PushFlags {
     const unsigned int *wait_flag = nullptr;
@@ -172,9 +188,9 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     L.err_word = error_word(h);
     L.bulk_out = h->bulk_out;
     if (push) { L.wait_flag = push->wait_flag; L.wait_value = push->wait_value; L.done_flag = push->done_flag; L.done_value = push->done_value; }
-    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 2 * sizeof(unsigned int), stream));
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 4 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
-    h->launches += 1;
+    h->launches += 2;                                   // search kernel + wide-spread / arrival-flag kernel
     return P2S_OK;
 }
 
@@ -237,8 +253,8 @@ int p2s_create(int device, p2s_handle **out) {
     }
     for (int i = 0; i < kSlots; ++i)
         if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return P2S_ECUDA; }
-    if (cudaMalloc((void **)&h->d_counters, (2 * kCounterRing + 2) * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(h->d_counters, 0, (2 * kCounterRing + 2) * sizeof(unsigned int)) != cudaSuccess ||
+    if (cudaMalloc((void **)&h->d_counters, (4 * kCounterRing + 4) * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(h->d_counters, 0, (4 * kCounterRing + 4) * sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc((void **)&h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long)) != cudaSuccess) {
         delete h;
         return P2S_ENOMEM;
@@ -557,9 +573,10 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
     long long nu = 0;
     // P2S_TRACE=1: device-side timeline of the pipeline (events after each chunk's H2D, kernel and D2H) on stderr
     const bool trace = std::getenv("P2S_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
+    EventList events;
+    std::vector<cudaEvent_t> &tev = events.ev;
     std::vector<long long> tunits;
-    cudaEvent_t t_begin = nullptr;
+    cudaEvent_t &t_begin = events.begin;
     if (trace) {
         cudaEventCreate(&t_begin);
         cudaEventRecord(t_begin, h->slots[0].stream);
@@ -572,6 +589,7 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
+    DrainSlots drain(h);
     for (long long u0 = 0; u0 < n_units; u0 += nu, ++i) {
         const long long rem = n_units - u0;
         nu = std::min(chunk, rem);
@@ -581,7 +599,7 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
         if (automatic && rem <= chunk && rem > (1LL << 17)) nu = std::max<long long>(1LL << 17, ((rem / 2) + 31) & ~31LL);
         Slot &s = h->slots[i % kSlots];
         if ((rc = ensure(h, s.x, nu * C * 4)) || (rc = ensure(h, s.y, nu * C * 4)) || (rc = ensure(h, s.lik, nu * C * 4)) ||
-            (rc = ensure(h, s.obs, nu * C * 16)) || (rc = ensure(h, s.Q, nu * 24)) || (rc = ensure(h, s.err, nu * 8)) ||
+            (lens && (rc = ensure(h, s.obs, nu * C * 16))) || (rc = ensure(h, s.Q, nu * 24)) || (rc = ensure(h, s.err, nu * 8)) ||
             (rc = ensure(h, s.nexcl, nu)) || (rc = ensure(h, s.mask, nu * 4)))
             return rc;
         P2S_CUDA(h, cudaMemcpyAsync(s.x.p, x + u0 * C, nu * C * 4, cudaMemcpyHostToDevice, s.stream));
@@ -618,8 +636,6 @@ static int triangulate_host(p2s_handle *h, const float *x, const float *y, const
             cudaEventElapsedTime(&d, t_begin, tev[3 * c + 2]);
             fprintf(stderr, "p2s trace chunk %2zu units %8lld  h2d done %7.3f  kernel done %7.3f  d2h done %7.3f ms\n", c, tunits[c], a, b, d);
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
-        cudaEventDestroy(t_begin);
     }
     if (stats) P2S_CUDA(h, cudaMemcpy(stats, h->d_stats, P2S_STAT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return P2S_OK;
@@ -666,6 +682,7 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
     const size_t C = (size_t)n_cams, NP = (size_t)max_persons;
     int rc, i = 0;
     const long long chunk = kChunkFrames;
+    DrainSlots drain(h);
     for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
         const long long nf = std::min(chunk, n_frames - f0);
         Slot &s = h->slots[i % kSlots];
@@ -737,9 +754,17 @@ int p2s_associate_multi_host(p2s_handle *h, const float *obs, const int32_t *cou
     int rc = check_mp_args(h, obs, count, cams, n_frames, n_cams, max_persons, n_joints, n_max, d_max, out_rows);
     if (rc) return rc;
     P2S_CUDA(h, cudaSetDevice(h->device));
+    // the counts are host memory here: a frame with more detections than n_max is an argument error, not something to
+    // truncate silently (the device entry point clamps in the kernel instead)
+    for (long long f = 0; f < n_frames; ++f) {
+        long long tot = 0;
+        for (int c = 0; c < n_cams; ++c) tot += std::max(0, std::min(count[f * n_cams + c], max_persons));
+        if (tot > n_max) return P2S_EINVAL;
+    }
     const size_t C = (size_t)n_cams, per_frame = C * (size_t)max_persons * 3u * (size_t)n_joints, NM = (size_t)n_max;
     long long chunk = std::max<long long>(1, std::min<long long>(kChunkFrames, (long long)((64u << 20) / (per_frame * 4u + 1))));
     int i = 0;
+    DrainSlots drain(h);
     for (long long f0 = 0; f0 < n_frames; f0 += chunk, ++i) {
         const long long nf = std::min(chunk, n_frames - f0);
         Slot &s = h->slots[i % kSlots];

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                 s_cum[c] = acc;
                 int n = a.count[f * C + c];
                 n = max(0, min(n, NP));
+                n = min(n, NM - acc);                                   // never past the shared-memory regions sized for NM
+                                                                        // detections (the host entry rejects such frames)
                 for (int p = 0; p < n; ++p) s_view[acc + p] = c;
                 acc += n;
             }

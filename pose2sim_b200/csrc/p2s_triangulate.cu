@@ -60,7 +60,8 @@ struct TriArgs {
     uint8_t *out_nexcl;
     uint32_t *out_mask;
     unsigned long long *stats;
-    unsigned int *tile_counter;   // [0] tile dispenser, [1] CTAs finished (both zeroed before the launch)
+    unsigned int *tile_counter;   // [0] tile dispenser, [1] fix-up CTAs finished, [2] tiles holding wide-spread units
+                                  // (all zeroed before the launch)
     int vec_out;                  // output planes 16-byte aligned: full tiles are written as 16-byte vectors
     int bulk_out;                 // ... by cp.async.bulk (TMA) stores from the staging area instead of st.global.v4
     // multi-GPU push (outputs may live in a PEER's memory, p2s_triangulate_planes_push_device):
@@ -196,8 +197,9 @@ __device__ __forceinline__ void rebuild_without_poisoned(double (*m0)[32], const
 // Their whole exclusion search runs here, one lane per unit, candidate after candidate, every candidate solved from a
 // factorisation of A itself (Givens QR streamed over the cameras in ascending order + one-sided Jacobi on R,
 // p2s_math.cuh) instead of the normal matrix.  Same loop rules as the main level loop (triangulation.py:408-505).
-// Only reachable with a likelihood threshold near 0, so: rolled loops, not inlined, called once per tile AFTER the
-// level loop where few values are live (an ABI call inside the candidate loop costs the common path its registers).
+// Only reachable with a likelihood threshold near 0, so it lives in a kernel of its own (wide_fixup_kernel below, which
+// returns at once when the main kernel counted no such unit): inside the main kernel an ABI call, even one placed after
+// the level loop, cost the common path 11 registers and 4.9 % of cfg2's time (profiles/r2a_kernel_ab_wide.jsonl).
 struct WideArgs {
     const double *sP;                  // projection matrices (shared memory)
     const LensParams *lens;            // DISTORT: lens models (shared memory), else null
@@ -216,7 +218,7 @@ struct WideRes {
 };
 
 template <bool DISTORT>
-static __device__ __noinline__ void search_wide_unit(const WideArgs &A, WideRes &R) {
+static __device__ __forceinline__ void search_wide_unit(const WideArgs &A, WideRes &R) {
     const int C = A.n_cams, ul = A.ul;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
     const int ninv0 = __popc(A.inv0);
@@ -330,13 +332,6 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     const int warp = threadIdx.x >> 5;
     double *sP = reinterpret_cast<double *>(smem_raw);                 // projection matrices for dynamic camera index
     WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
-    // DISTORT: lens models for the wide-spread path's dynamic camera index, behind the slabs
-    LensParams *sLens = reinterpret_cast<LensParams *>(smem_raw + CMAX * 12 * sizeof(double) + 4 * sizeof(WarpSlab<CMAX>));
-    if (DISTORT) {
-        const double *src = reinterpret_cast<const double *>(&lens);
-        double *dst = reinterpret_cast<double *>(sLens);
-        for (int i = threadIdx.x; i < (int)(CMAX * sizeof(LensParams) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
-    }
 
     const int C = EXACT ? CMAX : a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
@@ -509,7 +504,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
 #else
         const bool wide = whi > P2S_WIDE_SPREAD * wlo;
 #endif
-        const uint32_t wide_mask = __ballot_sync(P2S_FULL, wide && active);
+        // such units are left to wide_fixup_kernel, which runs right after this kernel when the counter is non-zero
+        if (__ballot_sync(P2S_FULL, wide && active) != 0u && lane == 0) atomicAdd(a.tile_counter + 2, 1u);
 
         // ---- per-unit state (owner lane) -----------------------------------------------------
         double err_min = inf64();
@@ -698,22 +694,6 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             __syncwarp();
         }
 
-        // ---- units with a wide likelihood spread: whole search on the factorisation of A (off the common path) ----
-        if (wide_mask != 0u) {
-            if (wide && active) {
-                WideArgs wa;
-                wa.sP = sP; wa.lens = DISTORT ? sLens : nullptr; wa.xy = S.xy; wa.wt = S.w;
-                wa.table = a.cand_masks; wa.max_table_level = a.max_table_level; wa.n_cams = C; wa.min_cams = a.min_cams;
-                wa.ul = lane; wa.thr = a.thr; wa.nan0 = nan0; wa.inv0 = inv0;
-                WideRes wr;
-                search_wide_unit<DISTORT>(wa, wr);
-                err_min = wr.err; qx = wr.qx; qy = wr.qy; qz = wr.qz; ids = wr.ids; nexcl = wr.nexcl; last_level = wr.last_level;
-                band_thr |= fabs(err_min - a.thr) < a.band_eps;
-                t_cands += wr.cands; t_cams += wr.cams; t_iters += wr.sweeps; t_solved += wr.solved;
-            }
-            __syncwarp();
-        }
-
         // ---- finalise (:588-602) and write -------------------------------------------------------
         const bool failed = active && (err_min > a.thr);
         double e_out = err_min;
@@ -771,14 +751,14 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             const uint32_t s_d = __reduce_add_sync(P2S_FULL, t_direct);
             const uint32_t s_b = __reduce_add_sync(P2S_FULL, t_blocks);
             const uint32_t s_a = __reduce_add_sync(P2S_FULL, t_adds);
-            const uint32_t n_fail = __popc(__ballot_sync(P2S_FULL, failed));
-            const uint32_t n_noev = __popc(__ballot_sync(P2S_FULL, active && last_level < 0));
+            const uint32_t n_fail = __popc(__ballot_sync(P2S_FULL, failed && !wide));
+            const uint32_t n_noev = __popc(__ballot_sync(P2S_FULL, active && !wide && last_level < 0));
             const uint32_t n_bthr = __popc(__ballot_sync(P2S_FULL, active && band_thr));
             const uint32_t n_barg = __popc(__ballot_sync(P2S_FULL, active && band_arg));
             uint32_t hist = 0;
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
-                const uint32_t n = __popc(__ballot_sync(P2S_FULL, active && last_level == l));
+                const uint32_t n = __popc(__ballot_sync(P2S_FULL, active && !wide && last_level == l));
                 if (lane == l) hist = n;
             }
             if (lane < 8) S.st32[lane] += hist;
@@ -787,7 +767,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 S.st64[4] += s_d; S.st64[5] += s_b; S.st64[6] += s_a;
                 S.st32[8] += n_fail; S.st32[9] += n_noev; S.st32[10] += n_bthr; S.st32[11] += n_barg;
             }
-            if (active && last_level >= 8) atomicAdd(a.stats + P2S_STAT_LEVEL0 + last_level, 1ULL);
+            if (active && !wide && last_level >= 8) atomicAdd(a.stats + P2S_STAT_LEVEL0 + last_level, 1ULL);
         }
         __syncwarp();
     }
@@ -815,14 +795,121 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         if (lane == 0) bulk_wait_all();
         __syncwarp();
     }
+}
+
+// ---- second kernel of every launch: wide-spread units + the push path's arrival flag ---------------------------
+// Runs right behind triangulate_kernel on the same stream.  When that kernel counted no unit with a wide likelihood
+// spread (tile_counter[2] == 0: always, unless the likelihood threshold is below 1 / P2S_WIDE_SPREAD) it only publishes the
+// push path's arrival flag and returns (~2 us).  Otherwise every warp re-reads the likelihoods of its tiles, finds the
+// wide units again (same float comparison as the main kernel) and runs their whole search on the factorisation of A,
+// one lane per unit, overwriting the placeholder the main kernel wrote.
+struct FixArgs {
+    const float4 *obs;
+    const float *px, *py, *pl;
+    float lik_thr_f;
+    int gate;
+    long long n_units;
+    int n_cams, min_cams;
+    double thr, band_eps;
+    const uint32_t *cand_masks;
+    int max_table_level;
+    double *out_Q, *out_err;
+    uint8_t *out_nexcl;
+    uint32_t *out_mask;
+    unsigned long long *stats;
+    unsigned int *tile_counter;
+    unsigned int *done_flag;
+    unsigned int done_value;
+};
+
+template <bool DISTORT>
+__global__ void __launch_bounds__(128) wide_fixup_kernel(const CamParams<P2S_MAX_CAMS> cams, const LensSet<DISTORT ? P2S_MAX_CAMS : 1> lens,
+                                                         const FixArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = a.n_cams;
+    const bool any = *reinterpret_cast<const volatile unsigned int *>(a.tile_counter + 2) != 0u;
+    if (any) {
+        double *sP = reinterpret_cast<double *>(smem_raw);
+        LensParams *sLens = reinterpret_cast<LensParams *>(smem_raw + P2S_MAX_CAMS * 12 * sizeof(double));
+        unsigned char *slab = smem_raw + P2S_MAX_CAMS * 12 * sizeof(double) + (DISTORT ? sizeof(LensSet<P2S_MAX_CAMS>) : 0) +
+                              (size_t)warp * C * 32 * (sizeof(float2) + sizeof(float));
+        float2 (*xy)[32] = reinterpret_cast<float2 (*)[32]>(slab);
+        float (*wt)[32] = reinterpret_cast<float (*)[32]>(slab + (size_t)C * 32 * sizeof(float2));
+        for (int i = threadIdx.x; i < C * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
+        if (DISTORT) {
+            const double *src = reinterpret_cast<const double *>(&lens);
+            double *dst = reinterpret_cast<double *>(sLens);
+            for (int i = threadIdx.x; i < (int)(C * sizeof(LensParams) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
+        const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+        const float nanf_ = __int_as_float(0x7fc00000);
+        const long long n_tiles = (a.n_units + 31) >> 5;
+        const long long w0 = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+        for (long long tile = w0; tile < n_tiles; tile += nw) {
+            const long long u = tile * 32 + lane;
+            const bool active = u < a.n_units;
+            uint32_t nan0 = 0, inv0 = 0;
+            float wlo = __int_as_float(0x7f800000), whi = 0.f;
+            for (int c = 0; c < C; ++c) {
+                float fx = 0.f, fy = 0.f, fl = nanf_;
+                if (active) {
+                    if (a.px == nullptr) {
+                        const float4 o = __ldg(a.obs + (long long)c * a.n_units + u);
+                        fx = o.x; fy = o.y; fl = o.z;
+                    } else {
+                        fx = a.px[u * C + c]; fy = a.py[u * C + c]; fl = a.pl[u * C + c];
+                        if (a.gate && fl < a.lik_thr_f) { fx = fy = fl = nanf_; }
+                    }
+                }
+                xy[c][lane] = make_float2(fx, fy);
+                wt[c][lane] = fl;
+                const bool isn = fl != fl;
+                nan0 |= (uint32_t)isn << c;
+                inv0 |= (uint32_t)(isn || fl == 0.f) << c;
+                const float la = fabsf(fl);
+                whi = fmaxf(whi, la);
+                wlo = fminf(wlo, la > 0.f ? la : wlo);
+            }
+            nan0 &= cmask; inv0 &= cmask;
+            const bool wide = active && whi > P2S_WIDE_SPREAD * wlo;
+            WideRes wr;
+            wr.cands = wr.cams = wr.sweeps = wr.solved = 0; wr.last_level = -1; wr.err = inf64();
+            if (wide) {
+                WideArgs wa;
+                wa.sP = sP; wa.lens = DISTORT ? sLens : nullptr; wa.xy = xy; wa.wt = wt;
+                wa.table = a.cand_masks; wa.max_table_level = a.max_table_level; wa.n_cams = C; wa.min_cams = a.min_cams;
+                wa.ul = lane; wa.thr = a.thr; wa.nan0 = nan0; wa.inv0 = inv0;
+                search_wide_unit<DISTORT>(wa, wr);
+                const bool failed = wr.err > a.thr;
+                double *q = a.out_Q + u * 3;
+                q[0] = failed ? nan64() : wr.qx; q[1] = failed ? nan64() : wr.qy; q[2] = failed ? nan64() : wr.qz;
+                a.out_err[u] = failed ? nan64() : wr.err;
+                a.out_nexcl[u] = (uint8_t)wr.nexcl;
+                a.out_mask[u] = wr.ids;
+                if (a.stats != nullptr) {
+                    atomicAdd(a.stats + P2S_STAT_CANDIDATES, (unsigned long long)wr.cands);
+                    atomicAdd(a.stats + P2S_STAT_CAM_SOLVES, (unsigned long long)wr.cams);
+                    atomicAdd(a.stats + P2S_STAT_SOLVED, (unsigned long long)wr.solved);
+                    atomicAdd(a.stats + P2S_STAT_WIDE_UNITS, 1ULL);
+                    if (wr.last_level >= 0) atomicAdd(a.stats + P2S_STAT_LEVEL0 + wr.last_level, 1ULL);
+                    else atomicAdd(a.stats + P2S_STAT_NOT_EVALUATED, 1ULL);
+                    if (failed) atomicAdd(a.stats + P2S_STAT_FAILED, 1ULL);
+                    if (fabs(wr.err - a.thr) < a.band_eps) atomicAdd(a.stats + P2S_STAT_BAND_THRESHOLD, 1ULL);
+                }
+            }
+            __syncwarp();
+        }
+    }
     // ---- push path: publish "every output of this launch is visible" to the consumer (possibly a peer GPU) ------
     if (a.done_flag != nullptr) {
         __syncthreads();                                       // the CTA's stores are all issued
         if (threadIdx.x == 0) {
             __threadfence_system();                            // ... and ordered before the count at system scope
             const unsigned int prev = atomicAdd(a.tile_counter + 1, 1u);
-            if (prev == gridDim.x - 1) {                       // last CTA of the launch
-                __threadfence_system();
+            if (prev == gridDim.x - 1) {                       // last CTA of the launch (the main kernel has retired:
+                __threadfence_system();                        //  same stream, its stores are visible device-wide)
                 *reinterpret_cast<volatile unsigned int *>(a.done_flag) = a.done_value;
             }
         }
@@ -1017,7 +1104,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
             o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
             for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
         }
-        return launch_persistent(triangulate_kernel<CMAX, 0, true, false, true>, smem + sizeof(LensSet<CMAX>), L, grid_out, cams, lens, a);
+        return launch_persistent(triangulate_kernel<CMAX, 0, true, false, true>, smem, L, grid_out, cams, lens, a);
     }
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);
@@ -1030,7 +1117,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     }
 }
 
-cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
+static cudaError_t launch_main(const TriLaunch &L, int *grid_out) {
     const bool plain = L.solver == 0 && L.lens == nullptr;
     if (plain && L.n_cams == 6) return launch_tri<6, false>(L, grid_out);
     if (plain && L.n_cams == 12) return launch_tri<12, false>(L, grid_out);
@@ -1039,6 +1126,65 @@ cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
     if (L.n_cams <= 8) return launch_tri<8, true>(L, grid_out);
     if (L.n_cams <= 16) return launch_tri<16, true>(L, grid_out);
     return launch_tri<32, true>(L, grid_out);
+}
+
+// The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 1024
+// rules wide units out rests on likelihoods being <= 1, which is a convention of pose estimators, not a contract of this
+// interface; an empty launch costs ~2 us behind the search kernel and keeps the accuracy guarantee unconditional.
+static cudaError_t launch_fixup(const TriLaunch &L, int main_grid) {
+    CamParams<P2S_MAX_CAMS> cams;
+    for (int c = 0; c < P2S_MAX_CAMS; ++c)
+        for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
+    FixArgs a;
+    a.obs = (const float4 *)L.obs; a.px = L.px; a.py = L.py; a.pl = L.pl;
+    a.gate = (L.lik_thr == L.lik_thr) && !(L.lik_thr == -INFINITY);
+    {
+        float tf = (float)L.lik_thr;
+        if (a.gate && (double)tf < L.lik_thr) tf = nextafterf(tf, INFINITY);
+        a.lik_thr_f = tf;
+    }
+    a.n_units = L.n_units; a.n_cams = L.n_cams; a.min_cams = L.min_cams; a.thr = L.thr; a.band_eps = L.band_eps;
+    a.cand_masks = L.cand_masks; a.max_table_level = L.max_table_level;
+    a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
+    a.stats = L.stats; a.tile_counter = L.tile_counter; a.done_flag = L.done_flag; a.done_value = L.done_value;
+    const long long n_tiles = (L.n_units + 31) / 32;
+    long long grid = (long long)L.sm_count * 4;
+    if (grid > (n_tiles + 3) / 4) grid = (n_tiles + 3) / 4;
+    if (grid < 1) grid = 1;
+    (void)main_grid;
+    const size_t slab = (size_t)4 * L.n_cams * 32 * (sizeof(float2) + sizeof(float));
+    if (L.lens) {
+        LensSet<P2S_MAX_CAMS> lens;
+        std::memset(&lens, 0, sizeof lens);
+        for (int c = 0; c < L.n_cams; ++c) {
+            const p2s_camera_model &m = L.lens[c];
+            LensParams &o = lens.cam[c];
+            for (int j = 0; j < 9; ++j) o.R[j] = m.R[j];
+            for (int j = 0; j < 3; ++j) o.T[j] = m.T[j];
+            o.fx = m.K[0]; o.fy = m.K[4]; o.cx = m.K[2]; o.cy = m.K[5];
+            for (int j = 0; j < 8; ++j) o.k[j] = m.dist[j];
+        }
+        const size_t smem = P2S_MAX_CAMS * 12 * sizeof(double) + sizeof(LensSet<P2S_MAX_CAMS>) + slab;
+        cudaError_t e = cudaFuncSetAttribute(wide_fixup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        wide_fixup_kernel<true><<<(unsigned)grid, 128, smem, L.stream>>>(cams, lens, a);
+    } else {
+        LensSet<1> none;
+        std::memset(&none, 0, sizeof none);
+        const size_t smem = P2S_MAX_CAMS * 12 * sizeof(double) + slab;
+        cudaError_t e = cudaFuncSetAttribute(wide_fixup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        wide_fixup_kernel<false><<<(unsigned)grid, 128, smem, L.stream>>>(cams, none, a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
+    int grid = 0;
+    cudaError_t e = launch_main(L, &grid);
+    if (grid_out) *grid_out = grid;
+    if (e != cudaSuccess) return e;
+    return launch_fixup(L, grid);
 }
 
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,

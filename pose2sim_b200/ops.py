@@ -68,7 +68,8 @@ def stats_dict(stats):
             "candidates": s[_lib.STAT_CANDIDATES], "cam_solves": s[_lib.STAT_CAM_SOLVES],
             "band_threshold": s[_lib.STAT_BAND_THRESHOLD], "band_argmin": s[_lib.STAT_BAND_ARGMIN],
             "solver_steps": s[_lib.STAT_NEWTON_STEPS], "solved": s[_lib.STAT_SOLVED],
-            "direct_cams": s[_lib.STAT_DIRECT_CAMS], "blocks": s[_lib.STAT_BLOCKS], "entry_adds": s[_lib.STAT_ENTRY_ADDS]}
+            "direct_cams": s[_lib.STAT_DIRECT_CAMS], "blocks": s[_lib.STAT_BLOCKS], "entry_adds": s[_lib.STAT_ENTRY_ADDS],
+            "wide_units": s[_lib.STAT_WIDE_UNITS]}
 
 
 class Engine:

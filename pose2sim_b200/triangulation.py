@@ -142,6 +142,11 @@ def solve_units(st, engine=None, device=0):
     F, N, K, C = st.x.shape
     U = F * N * K
     s = st.settings
+    if U == 0:
+        # nothing staged (a reversed or out-of-range frame_range): no device call; write_outputs raises the reference's
+        # "No persons have been triangulated" (triangulation.py:955-956)
+        return {"Q": np.empty((F, N, K, 3)), "err": np.empty((F, N, K)), "nexcl": np.empty((F, N, K), np.int64),
+                "mask": np.empty((F, N, K), np.uint32), "stats": None}
     if s["handle_LR_swap"]:
         import torch
         dev = torch.device("cuda", eng.device)
