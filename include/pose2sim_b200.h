@@ -69,7 +69,7 @@ enum {
     P2S_STAT_DIRECT_CAMS = 41,   /* level 0: valid cameras accumulated straight into the normal matrix */
     P2S_STAT_BLOCKS = 42,        /* levels >= 1: per-camera 4x4 blocks built (valid cameras x unit x level) */
     P2S_STAT_ENTRY_ADDS = 43,    /* levels >= 1: FP64 additions forming M_all and M_all -/+ blocks     */
-    P2S_STAT_WIDE_UNITS = 44,    /* units whose valid likelihoods span more than 1024x: solved from a QR
+    P2S_STAT_WIDE_UNITS = 44,    /* units whose valid likelihoods span more than 256x: solved from a QR
                                     factorisation of A (like the reference's SVD) by the fix-up kernel   */
     P2S_STAT_COUNT = 48
 };
@@ -302,6 +302,19 @@ int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams
  * writes), so the file is byte-identical to the reference's for equal values.                      */
 int p2s_write_trc_rows(const char *path, const long long *frames, const double *time_s,
                        const double *values, long long n_rows, int n_cols);
+
+/* ---- workload generation (benchmarks / tests; produces INPUTS only) ---------------------------- */
+/* Synthetic observations of units [unit0, unit0 + n_units) generated on the device as a pure function of
+ * (seed, unit, camera): Philox4x32-10 counters + IEEE add / multiply / divide in a fixed order, so that the NumPy
+ * twin (pose2sim_b200/synth_philox.py) regenerates any subsample bit for bit for the CPU oracle (SURVEY.md 8(d)/(e):
+ * BASELINE configs[4], 10 M frames x up to 32 cameras, is generated per shard instead of being pushed over PCIe).
+ * Units are (frame, keypoint), keypoint fastest.  P: host n_cams x 12.  kp_offsets [n_keypoints][3], circle [600][2],
+ * dirs [256][2]: DEVICE float64 tables (synth_philox.tables()).  x, y, lik: device float32 [n_units][n_cams], the
+ * likelihood gate NOT applied; truth: device float64 [n_units][3] or NULL.  Asynchronous on `stream`.          */
+int p2s_synth_observations_device(p2s_handle *h, const double *P, int n_cams, int n_keypoints, unsigned int seed,
+                                  long long unit0, long long n_units, double sigma, double p_out, double p_low,
+                                  const double *kp_offsets, const double *circle, const double *dirs,
+                                  float *x, float *y, float *lik, double *truth, void *stream);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Dependent-chain FP64 FMA microbenchmark on the handle's device: achieved DFMA TFLOP/s

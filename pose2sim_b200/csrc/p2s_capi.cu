@@ -818,6 +818,20 @@ int p2s_measure_fp64_peak(p2s_handle *h, double *tflops, double *ms_out) {
     return P2S_OK;
 }
 
+int p2s_synth_observations_device(p2s_handle *h, const double *P, int n_cams, int n_keypoints, unsigned int seed,
+                                  long long unit0, long long n_units, double sigma, double p_out, double p_low,
+                                  const double *kp_offsets, const double *circle, const double *dirs,
+                                  float *x, float *y, float *lik, double *truth, void *stream) {
+    if (!h || !P || !kp_offsets || !circle || !dirs || (n_units > 0 && (!x || !y || !lik))) return P2S_EINVAL;
+    if (n_cams < 1 || n_cams > P2S_MAX_CAMS || n_keypoints < 1 || unit0 < 0 || n_units < 0) return P2S_EINVAL;
+    if (n_units == 0) return P2S_OK;
+    P2S_CUDA(h, cudaSetDevice(h->device));
+    P2S_CUDA(h, p2s::launch_synth(P, n_cams, n_keypoints, seed, unit0, n_units, sigma, p_out, p_low, kp_offsets, circle, dirs,
+                                  x, y, lik, truth, h->prop.multiProcessorCount, (cudaStream_t)stream));
+    h->launches += 1;
+    return P2S_OK;
+}
+
 long long p2s_launch_count(const p2s_handle *h) { return h ? h->launches : 0; }
 
 int p2s_last_grid(const p2s_handle *h) { return h ? h->last_grid : 0; }

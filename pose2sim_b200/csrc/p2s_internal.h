@@ -95,5 +95,8 @@ cudaError_t launch_collect(const unsigned int *arrive, unsigned int *const *ack,
                            unsigned int ack_value, unsigned int *err_word, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_associate(const AssocLaunch &L, int *grid_out);
+cudaError_t launch_synth(const double *P, int n_cams, int n_keypoints, unsigned int seed, long long unit0, long long n_units,
+                         double sigma, double p_out, double p_low, const double *kp_off, const double *circle,
+                         const double *dirs, float *x, float *y, float *lik, double *truth, int sm_count, cudaStream_t stream);
 
 }  // namespace p2s

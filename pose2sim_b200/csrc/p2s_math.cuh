@@ -228,7 +228,7 @@ static __device__ __noinline__ int smallest_eigvec_jacobi(const Sym4 &M, double 
 // The reference takes the SVD of the weighted 2m x 4 matrix A itself (common.py:347-350, cv2.SVDecomp).  The normal
 // matrix squares the condition number: with valid likelihoods spanning w_max / w_min = s the eigenvector of A^T A
 // is off by ~2e-16 s^2 metres on ring rigs (measured on reference-generated units: 2e-8 m at s = 1e4, 1.7e-4 m at
-// s = 1e6; i.e. ~2e-10 m at the switch-over s = 1024), so units with s > P2S_WIDE_SPREAD — only possible when the
+// s = 1e6, at most 2e-11 m for s <= 512 on the reference-generated units of tests/golden/tri_wide_likelihood.npz), so units with s > P2S_WIDE_SPREAD — only possible when the
 // likelihood threshold is near 0 — take this path instead, off the common one and still on the device:
 //   1. A = Q R by Givens rotations, the 2m rows streamed through a 4x4 upper-triangular R (10 registers; each row is
 //      rebuilt from P, x, y, w on the fly), which is backward stable column by column;
@@ -236,7 +236,7 @@ static __device__ __noinline__ int smallest_eigvec_jacobi(const Sym4 &M, double 
 //      is that of A.  ~5 sweeps of 6 column pairs.
 // Agreement with the reference's outputs on tests/golden/tri_wide_likelihood.npz (spreads up to 1e6): 5e-14 m.
 #ifndef P2S_WIDE_SPREAD
-#define P2S_WIDE_SPREAD 1024.0f
+#define P2S_WIDE_SPREAD 256.0f
 #endif
 struct Tri4 {                                       // upper-triangular 4x4
     double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;

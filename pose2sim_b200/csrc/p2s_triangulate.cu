@@ -120,7 +120,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
                                        register cap follows, which removes the spills of the 32-camera unrolls */
 #endif
 
-template <int CMAX>
+template <int CMAX, bool STATS = false>
 struct alignas(16) WarpSlab {     // per-warp shared memory
     // next tile's raw planes x | y | likelihood ([32 units][C] floats each), written by cp.async.bulk (TMA) while the
     // current tile is searched; only for CMAX <= 8 (3 KB per warp) — wider slabs would cost a resident CTA
@@ -135,8 +135,9 @@ struct alignas(16) WarpSlab {     // per-warp shared memory
                                   // (group, camera) at group * C + camera (G * C <= 32 because W >= C)
     double m0[10][32];            // level 0's normal matrix of every unit of the tile (entry-major): the sum over the
                                   // unit's valid cameras, from which levels >= 1 subtract the excluded blocks
-    double r_err[32];             // level results published by the winning lane of each unit
-    double r_qx[32], r_qy[32], r_qz[32];
+    unsigned long long r_key[32]; // levels >= 1: error key of the unit's running best candidate of the level ...
+    double r_qx[32], r_qy[32], r_qz[32];   // ... and its point, published by the winning lane of a pass
+    unsigned long long r_skey[STATS ? 32 : 2];   // STATS kernels: runner-up key (eps-band statistics of the arg-min)
     unsigned long long st64[8];   // per-warp statistics: candidates, camera-solves, solver steps, solved,
                                   // direct cameras, blocks, entry additions
     uint32_t st32[12];            // level histogram [0..7], failed, not evaluated, threshold band, arg-min band
@@ -148,26 +149,24 @@ struct alignas(16) WarpSlab {     // per-warp shared memory
 };
 
 static_assert(sizeof(WarpSlab<8>) % 16 == 0 && offsetof(WarpSlab<8>, blk) % 16 == 0 && offsetof(WarpSlab<8>, xy) % 16 == 0, "slab alignment");
+static_assert(sizeof(WarpSlab<8, true>) % 16 == 0 && sizeof(WarpSlab<16, true>) % 16 == 0, "slab alignment");
 static_assert(sizeof(WarpSlab<32>) % 16 == 0 && offsetof(WarpSlab<32>, blk) % 16 == 0, "slab alignment");
 
 // Weighted-DLT normal matrix of ONE unit accumulated straight from the observations (level 0:
-// thread per unit).  Invalid cameras enter with x = y = w = 0, i.e. exact zeros are added — no
-// branch per camera, so the unrolled cameras interleave in the FP64 pipe.
+// thread per unit).  Invalid cameras hold x = y = w = 0 in the slab (written once when the tile is staged), i.e. exact
+// zeros are added — no branch and no select per camera, so the unrolled cameras interleave in the FP64 pipe.
 // "Poisoned" cameras: valid (likelihood neither NaN nor 0) but x or y is NaN.  The reference keeps such a camera (only the
 // likelihood decides validity, triangulation.py:435-436), its DLT rows are NaN, cv2.SVDecomp returns NaN, and every
 // distance of that candidate is +inf (common.py:394-396) — until the exclusion search drops the camera.  Nothing is
 // tested here: a kept poisoned camera makes M, Q and the error NaN, which err_key_inf() orders as that +inf.
 template <int CMAX>
 __device__ __forceinline__ void accumulate_direct(Sym4 &M, const CamParams<CMAX> &cams, const float2 (*xy)[32],
-                                                  const float (*wt)[32], int ul, uint32_t valid) {
+                                                  const float (*wt)[32], int ul) {
     sym4_zero(M);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        float2 o = xy[c][ul];
-        float ow = wt[c][ul];
-        const bool v = (valid >> c) & 1u;
-        o.x = v ? o.x : 0.f; o.y = v ? o.y : 0.f; ow = v ? ow : 0.f;
-        accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)ow);
+        const float2 o = xy[c][ul];
+        accumulate_camera(M, cams.P[c], (double)o.x, (double)o.y, (double)wt[c][ul]);
     }
 }
 
@@ -312,7 +311,8 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 #else
         else dist = reproj_distance(cams.P[c], qx, qy, qz, o.x, o.y);
 #endif
-        if ((valid >> c) & 1u) sum += dist;                      // predicated DADD, no select
+        if ((valid >> c) & 1u) sum += dist;                      // compiles to two FSEL + DADD (an inline-PTX predicated
+                                                                 // add is if-converted to the same selects, measured)
     }
     return sum * rinv_m;                                        // mean: 1/m from the host table (exactly rounded 1/m)
 }
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     double *sP = reinterpret_cast<double *>(smem_raw);                 // projection matrices for dynamic camera index
-    WarpSlab<CMAX> &S = reinterpret_cast<WarpSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
+    WarpSlab<CMAX, STATS> &S = reinterpret_cast<WarpSlab<CMAX, STATS> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
 
     const int C = EXACT ? CMAX : a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
@@ -488,17 +488,21 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         for (int c = 0; c < CMAX; ++c) {
             const float lz = S.w[c][lane];
             const bool isn = lz != lz;
+            const bool inv = isn || lz == 0.f;
             nan0 |= (uint32_t)isn << c;
-            inv0 |= (uint32_t)(isn || lz == 0.f) << c;
+            inv0 |= (uint32_t)inv << c;
             const float la = fabsf(lz);
             whi = fmaxf(whi, la);                                  // fmaxf / fminf skip NaN
             wlo = fminf(wlo, la > 0.f ? la : wlo);
+            // invalid cameras hold exact zeros from here on: they add nothing to a normal matrix, so no pass below
+            // needs a select per camera (validity lives in the nan0 / inv0 masks)
+            if (inv) { S.xy[c][lane] = make_float2(0.f, 0.f); S.w[c][lane] = 0.f; }
         }
         nan0 &= cmask; inv0 &= cmask;
         S.nan0[lane] = nan0;
         S.inv0[lane] = inv0;
         // units whose valid likelihoods span more than P2S_WIDE_SPREAD solve every candidate from a factorisation of A
-        // (p2s_math.cuh, "wide likelihood spread"); never the case with a likelihood threshold >= 1 / 128
+        // (p2s_math.cuh, "wide likelihood spread"); never the case with a likelihood threshold >= 1 / 256
 #ifdef P2S_NO_WIDE                                             /* A/B switch, tools/kernel_ab.py */
         const bool wide = false;
 #else
@@ -517,26 +521,55 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         uint32_t t_cands = 0, t_cams = 0, t_iters = 0;      // per-tile work counters of this lane
         uint32_t t_solved = 0, t_direct = 0, t_blocks = 0, t_adds = 0;
 
-        // ---- exclusion levels ------------------------------------------------------------------
-        // k = 0 has one candidate per unit: W = 1, thread per unit.  k >= 1: lanes enumerate subsets,
-        // W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units at a time.
-        for (int k = 0; k < C || k == 0; ++k) {
-            // reference loop condition (:408) and break rule (:437-441) in closed form:
-            // max_i |inv0 U cand_i| = min(C, |inv0| + k)
+        // ---- level 0: one candidate per unit, THREAD PER UNIT, straight line ---------------------------------------
+        // reference loop condition (:408) and break rule (:437-441) in closed form: max_i |inv0 U cand_i| = min(C, |inv0| + k)
+        if (active && !wide && (err_min > a.thr) && (C >= a.min_cams) && !(min(C, ninv0) > C - a.min_cams)) {
+            const uint32_t valid = cmask & ~inv0;
+            const int m = C - ninv0;
+            if (m >= 2) {
+                Sym4 M;
+                accumulate_direct<CMAX>(M, cams, S.xy, S.w, lane);
+                // kept (entry-major, conflict-free column): the sum of the unit's valid camera blocks, from which the deeper
+                // levels subtract the blocks they exclude
+                S.m0[0][lane] = M.m00; S.m0[1][lane] = M.m01; S.m0[2][lane] = M.m02; S.m0[3][lane] = M.m03; S.m0[4][lane] = M.m11;
+                S.m0[5][lane] = M.m12; S.m0[6][lane] = M.m13; S.m0[7][lane] = M.m22; S.m0[8][lane] = M.m23; S.m0[9][lane] = M.m33;
+                int it;
+                if (SOLVER == 0) it = smallest_eigvec_secular(M, qx, qy, qz);
+                else it = smallest_eigvec_jacobi(M, qx, qy, qz);
+                const double e = mean_reproj_error<CMAX, DISTORT, false>(cams, lens, S.xy, nullptr, lane, valid, a.rinv[m], qx, qy, qz, sP);
+                err_min = (e != e) ? inf64() : e;            // a NaN error is the reference's +inf (err_key_inf)
+                t_iters += (uint32_t)it; t_solved += 1u; t_direct += (uint32_t)m;
+            }                                                // m < 2: Q = NaN, error +inf (common.py:351, :394-396)
+            t_cands += 1u; t_cams += (uint32_t)m;
+            ids = nan0; nexcl = (uint32_t)ninv0; last_level = 0;
+            band_thr |= fabs(err_min - a.thr) < a.band_eps;
+            // level 0 came out +inf: a unit with poisoned cameras gets its level-0 matrix rebuilt without them
+            if (!(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, valid, C);
+        }
+        __syncwarp();
+
+        // ---- levels k >= 1: lanes enumerate subsets, W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units per pass,
+        // ONE candidate per lane and pass (levels with more than W candidates take several passes over the unit; the
+        // pass winner replaces the unit's running best in its slot on a strict '<', so the first index still wins)
+        for (int k = 1; k < C; ++k) {
             const bool pend = active && !wide && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
                               !(min(C, ninv0 + k) > C - a.min_cams);
             const uint32_t pmask = __ballot_sync(P2S_FULL, pend);
             if (pmask == 0) break;
             const int npend = __popc(pmask);
-            if (pend) S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
+            if (pend) {
+                S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
+                S.r_key[lane] = P2S_KEY_EMPTY;
+                if (STATS) S.r_skey[lane] = P2S_KEY_EMPTY;
+            }
             const uint32_t ncand = a.ncand[k];
-            const int lw = a.lw[k];                          // W = 2^lw lanes per unit (host table)
+            const int lw = a.lw[k];                          // W = 2^lw lanes per unit (host table), W >= C
             const int W = 1 << lw;
             const int G = 32 >> lw;
             const int grp = lane >> lw, sub = lane & (W - 1);
             const uint32_t gmask = (W >= 32) ? P2S_FULL : (((1u << W) - 1u) << (grp << lw));   // lanes of my group
-            const uint32_t *table = a.cand_masks + a.level_off[k <= a.max_table_level ? k : 0];
-            const bool blocks = k > 0;                       // then W >= C: one lane per camera for the block pass
+            const bool tabled = k <= a.max_table_level;
+            const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             double *gblk = S.blk + grp * (C * 10 + 2);
             const bool subtract = 2 * k <= C;                // M = M_all - excluded blocks, else sum of the kept blocks
             __syncwarp();
@@ -547,147 +580,124 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 const int ul = on ? (int)S.plist[idx] : 0;                 // owner lane of my unit
                 const uint32_t u_nan0 = S.nan0[ul], u_inv0 = S.inv0[ul];
 
-                if (blocks) {
-                    // camera-parallel: lane `sub` builds the block of camera `sub` of its group's unit (the sum of the
-                    // valid blocks, M_all, is level 0's normal matrix, kept in S.m0)
-                    __syncwarp();
-                    if (on && sub < C) {
-                        const float2 o = S.xy[sub][ul];
-                        float ow = S.w[sub][ul];
-                        // A valid camera whose x or y is NaN ("poisoned", see accumulate_direct) gets a ZERO block, so M and
-                        // its downdates stay finite, but keeps its NaN in gxy: the distance of every candidate that keeps
-                        // the camera is NaN, which err_key_inf() orders as the reference's +inf.
-                        const bool v = !((u_inv0 >> sub) & 1u);
-                        const bool vb = v && (o.x == o.x) && (o.y == o.y);
-                        const double ox = (double)o.x, oy = (double)o.y;
-                        S.gxy[grp * C + sub] = make_double2(ox, oy);       // invalid cameras: never read under `valid`
-                        double b[10];
-                        camera_block(sP + sub * 12, vb ? ox : 0.0, vb ? oy : 0.0, (double)(vb ? ow : 0.f), b);
-                        t_blocks += v ? 1u : 0u;
-                        double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
+                // camera-parallel: lane `sub` builds the block of camera `sub` of its group's unit (the sum of the
+                // valid blocks, M_all, is level 0's normal matrix, kept in S.m0)
+                __syncwarp();
+                if (on && sub < C) {
+                    const float2 o = S.xy[sub][ul];
+                    const float ow = S.w[sub][ul];
+                    // A valid camera whose x or y is NaN ("poisoned", see accumulate_direct) gets a ZERO block, so M and
+                    // its downdates stay finite, but keeps its NaN in gxy: the distance of every candidate that keeps
+                    // the camera is NaN, which err_key_inf() orders as the reference's +inf.  (Invalid cameras hold zeros.)
+                    const bool clean = (o.x == o.x) && (o.y == o.y);
+                    const double ox = (double)o.x, oy = (double)o.y;
+                    S.gxy[grp * C + sub] = make_double2(ox, oy);
+                    double b[10];
+                    camera_block(sP + sub * 12, clean ? ox : 0.0, clean ? oy : 0.0, (double)(clean ? ow : 0.f), b);
+                    if (STATS) t_blocks += ((u_inv0 >> sub) & 1u) ? 0u : 1u;
+                    double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
 #pragma unroll
-                        for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
-                    }
-                    __syncwarp();
+                    for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
                 }
+                __syncwarp();
 
-
-                unsigned long long bkey = P2S_KEY_EMPTY, skey = P2S_KEY_EMPTY;
-                uint32_t bcand = 0xffffffffu, bnan = 0, bexcl = 0;
-                double bqx = nan64(), bqy = bqx, bqz = bqx;
-                if (on) {
-                    for (uint32_t cand = (uint32_t)sub; cand < ncand; cand += (uint32_t)W) {
-                        const uint32_t cm = !blocks ? 0u : (k <= a.max_table_level) ? __ldg(table + cand) : unrank_subset(C, k, cand);
-                        const uint32_t nanset = u_nan0 | cm;
-                        const uint32_t invset = u_inv0 | cm;
-                        const uint32_t valid = cmask & ~invset;
+                for (uint32_t cbase = 0; cbase < ncand; cbase += (uint32_t)W) {
+                    const uint32_t cand = cbase + (uint32_t)sub;
+                    const bool live = on && cand < ncand;
+                    unsigned long long key = P2S_KEY_EMPTY;
+                    uint32_t cm = 0;
+                    double cqx = nan64(), cqy = cqx, cqz = cqx;
+                    if (live) {
+                        cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
+                        const uint32_t valid = cmask & ~(u_inv0 | cm);
                         const int m = __popc(valid);
-                        double cqx, cqy, cqz, e;
-                        if (m < 2) {                          // common.py:351, :394-396 / mean of an empty list
-                            cqx = cqy = cqz = nan64();
-                            e = (m == 0) ? nan64() : inf64();
-                        } else {
+                        double e = inf64();                  // m < 2: common.py:351, :394-396 / mean of an empty list,
+                        if (m >= 2) {                        // both ordered as +inf
                             Sym4 M;
-                            if (!blocks) {
-                                accumulate_direct<CMAX>(M, cams, S.xy, S.w, ul, valid);
-                                t_direct += (uint32_t)m;
-                                // ul == lane at level 0: conflict-free column of the entry-major array
-                                S.m0[0][ul] = M.m00; S.m0[1][ul] = M.m01; S.m0[2][ul] = M.m02; S.m0[3][ul] = M.m03; S.m0[4][ul] = M.m11;
-                                S.m0[5][ul] = M.m12; S.m0[6][ul] = M.m13; S.m0[7][ul] = M.m22; S.m0[8][ul] = M.m23; S.m0[9][ul] = M.m33;
+                            uint32_t bits;
+                            double sgn;
+                            if (subtract) {
+                                M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
+                                M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
+                                bits = cm & ~u_inv0 & cmask;
+                                sgn = -1.0;
                             } else {
-                                uint32_t bits;
-                                double sgn;
-                                if (subtract) {
-                                    M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
-                                    M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
-                                    bits = cm & ~u_inv0 & cmask;
-                                    sgn = -1.0;
-                                } else {
-                                    sym4_zero(M);
-                                    bits = valid;
-                                    sgn = 1.0;
-                                }
-                                t_adds += 10u * (uint32_t)__popc(bits);
-                                while (bits) {                // ascending camera order
-                                    const int c = __ffs(bits) - 1;
-                                    bits &= bits - 1;
-                                    const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
-                                    const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                                    M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
-                                    M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
-                                    M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
-                                    M.m33 = fma(sgn, v4.y, M.m33);
-                                }
+                                sym4_zero(M);
+                                bits = valid;
+                                sgn = 1.0;
+                            }
+                            if (STATS) t_adds += 10u * (uint32_t)__popc(bits);
+                            while (bits) {                    // ascending camera order
+                                const int c = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
+                                const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
+                                M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
+                                M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
+                                M.m33 = fma(sgn, v4.y, M.m33);
                             }
                             int it;
                             if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
                             else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            if (blocks) e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
-                            else e = mean_reproj_error<CMAX, DISTORT, false>(cams, lens, S.xy, nullptr, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
-                            t_iters += (uint32_t)it;
-                            t_solved += 1u;
+                            e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
+                            if (STATS) { t_iters += (uint32_t)it; t_solved += 1u; }
                         }
-                        t_cands += 1; t_cams += (uint32_t)m;
-                        const unsigned long long key = err_key_inf(e);
-                        if (key < bkey) {                       // ascending cand per lane: strict < keeps the first
-                            skey = bkey;
-                            bkey = key; bcand = cand; bnan = nanset; bexcl = (uint32_t)__popc(invset);
-                            bqx = cqx; bqy = cqy; bqz = cqz;
-                        } else if (key > bkey && key < skey) {
-                            skey = key;
-                        }
+                        if (STATS) { t_cands += 1u; t_cams += (uint32_t)m; }
+                        key = err_key_inf(e);
                     }
-                }
-                // ---- (error, index) arg-min + runner-up across the W lanes of the group (xor butterflies) ----
-                // keys are 64-bit: min of the high words, then min of the low words among the lanes that
-                // hold that high word; ties go to the smallest candidate index (np.nanargmin's first index)
-                bool winner = on && bcand != 0xffffffffu;     // W == 1: the lane's own (only) candidate
-                bool barg = false;
-                if (W > 1) {
-                    const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
+                    // ---- arg-min of the pass across the W lanes of the group: keys are 64-bit — min of the high words (ONE
+                    // redux.sync), then, only if several lanes hold it (duplicates, all-inf levels, errors closer than 2^-20
+                    // relative), min of the low words among them; candidates ascend with the lane, so the lowest lane among
+                    // the holders of the minimum is np.nanargmin's first index
+                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
                     const uint32_t mh = group_min(hi, W, gmask);
-                    // Fast path (warp-uniform): in every group exactly one lane holds the minimal HIGH word, so that
-                    // lane is the arg-min — one redux + one ballot.  Otherwise (high words tie: duplicates, all-NaN
-                    // levels, errors closer than 2^-20 relative) or when the eps-band statistics are wanted, the
-                    // full 64-bit (error, index) reduction with the runner-up runs.
-                    const uint32_t holders = __ballot_sync(P2S_FULL, hi == mh) & gmask;
-                    const bool full = STATS || (on && __popc(holders) != 1);
-                    if (!__any_sync(P2S_FULL, full)) {
-                        winner = on && (hi == mh);
-                    } else {
-                        const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
-                        const bool is_min = (hi == mh) && (lo == ml);
-                        const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);   // first index wins
-                        // the lane that evaluated candidate mc still holds its Q / masks
-                        winner = on && mc != 0xffffffffu && is_min && bcand == mc;
+                    uint32_t holders = __ballot_sync(P2S_FULL, live && hi == mh) & gmask;
+                    uint32_t ml = lo;
+                    if (__any_sync(P2S_FULL, STATS || __popc(holders) > 1)) {
+                        ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
+                        holders = __ballot_sync(P2S_FULL, live && hi == mh && lo == ml) & gmask;
+                    }
+                    const bool winner = holders != 0u && lane == __ffs(holders) - 1;
+                    unsigned long long pskey = P2S_KEY_EMPTY;  // STATS: the pass's smallest key strictly above its minimum
+                    if (STATS) {
+                        const bool is_min = live && hi == mh && lo == ml;
+                        const unsigned long long rk = is_min ? P2S_KEY_EMPTY : key;
+                        const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
+                        const uint32_t sh = group_min(rh, W, gmask);
+                        const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
+                        pskey = ((unsigned long long)sh << 32) | sl;
+                    }
+                    if (winner) {
+                        const unsigned long long old = S.r_key[ul];
                         if (STATS) {
-                            // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
-                            const unsigned long long rk = is_min ? skey : bkey;
-                            const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
-                            const uint32_t sh = group_min(rh, W, gmask);
-                            const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
-                            skey = ((unsigned long long)sh << 32) | sl;
-                            barg = (key_err(skey) - key_err(bkey)) < a.band_eps;   // NaN / inf compare false
+                            // runner-up of the level so far: smallest of {old best, old runner-up, pass best, pass runner-up}
+                            // strictly above the new best (equal keys are duplicates of the winner)
+                            const unsigned long long nb = key < old ? key : old;
+                            unsigned long long sk = P2S_KEY_EMPTY;
+                            const unsigned long long cs[4] = {old, S.r_skey[ul], key, pskey};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (cs[j] > nb && cs[j] < sk) sk = cs[j];
+                            S.r_skey[ul] = sk;
+                        }
+                        if (key < old) {                       // strict '<': an earlier pass (smaller indices) keeps a tie
+                            S.r_key[ul] = key;
+                            S.r_qx[ul] = cqx; S.r_qy[ul] = cqy; S.r_qz[ul] = cqz;
+                            S.r_nan[ul] = u_nan0 | cm;
+                            S.r_flags[ul] = (uint32_t)__popc(u_inv0 | cm);
                         }
                     }
-                }
-                if (winner) {
-                    S.r_err[ul] = key_err(bkey);
-                    S.r_qx[ul] = bqx; S.r_qy[ul] = bqy; S.r_qz[ul] = bqz;
-                    S.r_nan[ul] = bnan;
-                    S.r_flags[ul] = bexcl | (barg ? 0x100u : 0u);
+                    __syncwarp();
                 }
             }
             __syncwarp();
             if (pend) {
-                err_min = S.r_err[lane];
-                // level 0 came out +inf: a unit with poisoned cameras gets its level-0 matrix rebuilt without them
-                if (k == 0 && !(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, cmask & ~inv0, C);
+                const unsigned long long bk = S.r_key[lane];
+                err_min = key_err(bk);
                 qx = S.r_qx[lane]; qy = S.r_qy[lane]; qz = S.r_qz[lane];
                 ids = S.r_nan[lane];
-                const uint32_t fl = S.r_flags[lane];
-                nexcl = fl & 0xffu;
-                band_arg |= (fl & 0x100u) != 0;
+                nexcl = S.r_flags[lane];
+                if (STATS) band_arg |= (key_err(S.r_skey[lane]) - err_min) < a.band_eps;   // NaN / inf compare false
                 band_thr |= fabs(err_min - a.thr) < a.band_eps;
                 last_level = k;
             }
@@ -1086,11 +1096,12 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.bulk_out = (a.vec_out && L.bulk_out) ? 1 : 0;
     a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
     a.err_word = L.err_word;
-    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX>) * 4;
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, true>) * 4;      // STATS slab; the lean one is 240 B smaller per warp
+    const size_t smem_lean = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, false>) * 4;
     if constexpr (!FULLSET) {
         LensSet<1> none;
         std::memset(&none, 0, sizeof none);
-        if (L.stats == nullptr) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem, L, grid_out, cams, none, a);
+        if (L.stats == nullptr) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem_lean, L, grid_out, cams, none, a);
         return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true>, smem, L, grid_out, cams, none, a);
     } else {
     if (L.lens) {                                             // undistort_points: distorted re-projection
@@ -1109,9 +1120,9 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);
     const bool st = L.stats != nullptr, exact = L.n_cams == CMAX;
-    if (L.solver == 0 && exact && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0 && exact && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem_lean, L, grid_out, cams, none, a);
     if (L.solver == 0 && exact) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true>, smem, L, grid_out, cams, none, a);
-    if (L.solver == 0 && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, false>, smem, L, grid_out, cams, none, a);
+    if (L.solver == 0 && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, false>, smem_lean, L, grid_out, cams, none, a);
     if (L.solver == 0) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, true>, smem, L, grid_out, cams, none, a);
     return launch_persistent(triangulate_kernel<CMAX, 1, false, false, true>, smem, L, grid_out, cams, none, a);
     }
@@ -1128,7 +1139,7 @@ static cudaError_t launch_main(const TriLaunch &L, int *grid_out) {
     return launch_tri<32, true>(L, grid_out);
 }
 
-// The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 1024
+// The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 256
 // rules wide units out rests on likelihoods being <= 1, which is a convention of pose estimators, not a contract of this
 // interface; an empty launch costs ~2 us behind the search kernel and keeps the accuracy guarantee unconditional.
 static cudaError_t launch_fixup(const TriLaunch &L, int main_grid) {
@@ -1184,7 +1195,11 @@ cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
     cudaError_t e = launch_main(L, &grid);
     if (grid_out) *grid_out = grid;
     if (e != cudaSuccess) return e;
+#ifdef P2S_NO_FIXUP_LAUNCH                                     /* A/B switch, tools/kernel_ab.py */
+    return e;
+#else
     return launch_fixup(L, grid);
+#endif
 }
 
 cudaError_t launch_stage(const float *x, const float *y, const float *lik, long long n_units, int n_cams,

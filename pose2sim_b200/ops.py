@@ -126,6 +126,32 @@ class Engine:
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
 
+    # ---- workload generation (benchmarks / tests) ------------------------------------------------------
+    def synth_observations(self, P, unit0, n_units, n_keypoints=26, seed=500, sigma=2.0, p_out=0.05, p_low=0.05,
+                           want_truth=False, out=None):
+        """Observations of units [unit0, unit0 + n_units) generated ON THE DEVICE as a pure function of
+        (seed, unit, camera) — the device side of `synth_philox.observations` (bit-identical float32 values).
+        Returns dict of CUDA tensors x, y, lik [n_units, C] float32 (ungated) and, on request, truth [n_units, 3]."""
+        torch = _torch()
+        from . import synth_philox
+        dev = torch.device("cuda", self.device)
+        Pm = _as_P(P, np.asarray(P).reshape(-1, 12).shape[0])
+        Cn = Pm.shape[0]
+        key = ("synth_tables", int(n_keypoints))
+        if key not in self.__dict__.setdefault("_cache", {}):
+            self._cache[key] = tuple(torch.from_numpy(t).to(dev) for t in synth_philox.tables(int(n_keypoints)))
+        off, circle, dirs = self._cache[key]
+        if out is None:
+            out = {k: torch.empty((n_units, Cn), dtype=torch.float32, device=dev) for k in ("x", "y", "lik")}
+        truth = torch.empty((n_units, 3), dtype=torch.float64, device=dev) if want_truth else None
+        _lib.check(self.h, self.lib.p2s_synth_observations_device(
+            self.h, Pm.ctypes.data, Cn, int(n_keypoints), int(seed) & 0xFFFFFFFF, int(unit0), int(n_units), float(sigma),
+            float(p_out), float(p_low), _ptr(off), _ptr(circle), _ptr(dirs), _ptr(out["x"]), _ptr(out["y"]), _ptr(out["lik"]),
+            _ptr(truth), self._stream()))
+        if want_truth:
+            out["truth"] = truth
+        return out
+
     # ---- device-resident path ------------------------------------------------------------------------
     def stage_observations(self, x, y, lik, lik_thr=None, out=None, lens=None):
         """x, y, lik: CUDA float32 tensors [U, C] -> staged float4 tensor [C, U, 4] with the

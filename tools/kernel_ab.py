@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 AB = os.path.join(ROOT, "pose2sim_b200", "ab")
-CSRC = os.path.join(ROOT, "pose2sim_b200", "csrc")
+CSRC = os.environ.get("P2S_AB_SRC", os.path.join(ROOT, "pose2sim_b200", "csrc"))   # P2S_AB_SRC: build another checkout's sources
 NVCC = ["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -26,7 +26,9 @@ def build(specs):
         name, _, flags = spec.partition(":")
         flags = flags.split()
         objs = []
-        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu", "p2s_multiperson.cu", "p2s_lrswap.cu"):
+        for src in ("p2s_capi.cu", "p2s_triangulate.cu", "p2s_associate.cu", "p2s_multiperson.cu", "p2s_lrswap.cu", "p2s_synth.cu"):
+            if not os.path.exists(os.path.join(CSRC, src)):
+                continue
             obj = os.path.join(AB, f"{name}_{src[:-3]}.o")
             r = subprocess.run(NVCC + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
             if r.returncode:
