@@ -302,6 +302,11 @@ int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams
  * writes), so the file is byte-identical to the reference's for equal values.                      */
 int p2s_write_trc_rows(const char *path, const long long *frames, const double *time_s,
                        const double *values, long long n_rows, int n_cols);
+/* The same rows formatted into `buf` (cap >= n_rows * (22 + 25 * (n_cols + 1)) bytes always suffices); *len = bytes
+ * written.  For frame-block sharded writers: every rank formats its rows, the byte counts are exchanged and each rank
+ * writes its range of the one file (triangulation.write_outputs_sharded).                                        */
+int p2s_format_trc_rows(const long long *frames, const double *time_s, const double *values, long long n_rows,
+                        int n_cols, char *buf, size_t cap, size_t *len);
 
 /* ---- workload generation (benchmarks / tests; produces INPUTS only) ---------------------------- */
 /* Synthetic observations of units [unit0, unit0 + n_units) generated on the device as a pure function of

@@ -387,6 +387,28 @@ char *repr_double(char *p, double v) {
 
 }  // namespace
 
+// The same rows formatted into a caller-provided buffer (frame-block sharded writers: every rank formats its own rows,
+// the ranks exchange byte counts and write their ranges of the one file in parallel).  cap >= n_rows * (22 + 25 *
+// (n_cols + 1)) always suffices.
+extern "C" int p2s_format_trc_rows(const long long *frames, const double *time_s, const double *values, long long n_rows,
+                                   int n_cols, char *buf, size_t cap, size_t *len) {
+    if (!len || n_rows < 0 || n_cols < 0 || (n_rows > 0 && (!buf || !frames || !time_s || (n_cols > 0 && !values)))) return P2S_EINVAL;
+    char *p = buf;
+    const size_t per_row = 22 + 25 * ((size_t)n_cols + 1);
+    for (long long r = 0; r < n_rows; ++r) {
+        if ((size_t)(p - buf) + per_row > cap) return P2S_EINVAL;
+        auto fr = std::to_chars(p, p + 24, frames[r]);
+        p = fr.ptr;
+        *p++ = '\t';
+        p = repr_double(p, time_s[r]);
+        const double *row = values + (size_t)r * (size_t)n_cols;
+        for (int c = 0; c < n_cols; ++c) { *p++ = '\t'; p = repr_double(p, row[c]); }
+        *p++ = '\n';
+    }
+    *len = (size_t)(p - buf);
+    return P2S_OK;
+}
+
 extern "C" int p2s_write_trc_rows(const char *path, const long long *frames, const double *time_s,
                                   const double *values, long long n_rows, int n_cols) {
     if (!path || n_rows < 0 || n_cols < 0 || (n_rows > 0 && (!frames || !time_s || (n_cols > 0 && !values)))) return P2S_EINVAL;

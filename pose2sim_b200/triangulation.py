@@ -290,31 +290,43 @@ def frame_rate_of(s):
     return rate
 
 
-def write_trc(s, Q, frames, keypoints_names, id_person=-1):
-    """triangulation.py:151-215 `make_trc`: Q [n, 3K] Z-up, `frames` their labels.  Returns the path.
-    The body is written by the native writer (`p2s_write_trc_rows`, Python-repr number formatting =
-    what `DataFrame.to_csv` emits) instead of pandas' per-value string conversion."""
-    from . import _lib
+def trc_header(s, n_rows, first_frame, last_frame, keypoints_names, id_person=-1):
+    """triangulation.py:151-205: (path, rate, the five header lines) of the TRC of `n_rows` frames."""
     project_dir = s["project_dir"]
     base = os.path.basename(os.path.realpath(project_dir))
     seq = f"{base}_P{id_person}" if s["multi_person"] else base
     out_dir = os.path.join(project_dir, "pose-3d")
     rate = frame_rate_of(s)
-    name = f"{seq}_{frames[0]}-{frames[-1]}.trc"
+    name = f"{seq}_{first_frame}-{last_frame}.trc"
     K = len(keypoints_names)
     header = ["PathFileType\t4\t(X/Y/Z)\t" + name,
               "DataRate\tCameraRate\tNumFrames\tNumMarkers\tUnits\tOrigDataRate\tOrigDataStartFrame\tOrigNumFrames",
-              "\t".join(map(str, [rate, rate, len(Q), K, "m", rate, frames[0], len(Q)])),
+              "\t".join(map(str, [rate, rate, n_rows, K, "m", rate, first_frame, n_rows])),
               "Frame#\tTime\t" + "\t\t\t".join(keypoints_names) + "\t\t\t",
               "\t\t" + "\t".join(f"X{i + 1}\tY{i + 1}\tZ{i + 1}" for i in range(K)) + "\t"]
+    return os.path.realpath(os.path.join(out_dir, name)), out_dir, rate, "\n".join(header) + "\n"
+
+
+def trc_row_arrays(Q, frames, rate, K):
+    """common.py:596-612 `zup2yup` (X, Y, Z <- Y, Z, X) + the frame / time columns, as the native writer takes them."""
     yup = np.ascontiguousarray(Q.reshape(len(Q), K, 3)[:, :, [1, 2, 0]].reshape(len(Q), 3 * K), dtype=np.float64)
-    fr = np.ascontiguousarray(frames, dtype=np.int64)               # common.py:596-612: X,Y,Z <- Y,Z,X
+    fr = np.ascontiguousarray(frames, dtype=np.int64)
     t = np.ascontiguousarray(fr / rate, dtype=np.float64)
+    return fr, t, yup
+
+
+def write_trc(s, Q, frames, keypoints_names, id_person=-1):
+    """triangulation.py:151-215 `make_trc`: Q [n, 3K] Z-up, `frames` their labels.  Returns the path.
+    The body is written by the native writer (`p2s_write_trc_rows`, Python-repr number formatting =
+    what `DataFrame.to_csv` emits) instead of pandas' per-value string conversion."""
+    from . import _lib
+    K = len(keypoints_names)
+    path, out_dir, rate, header = trc_header(s, len(Q), frames[0], frames[-1], keypoints_names, id_person)
+    fr, t, yup = trc_row_arrays(Q, frames, rate, K)
     if not os.path.exists(out_dir):
         os.mkdir(out_dir)
-    path = os.path.realpath(os.path.join(out_dir, name))
     with open(path, "w") as f:
-        f.write("\n".join(header) + "\n")
+        f.write(header)
     _lib.check(None, _lib.load().p2s_write_trc_rows(path.encode(), fr.ctypes.data, t.ctypes.data, yup.ctypes.data,
                                                     len(fr), 3 * K))
     return path
@@ -499,6 +511,204 @@ def log_recap(st, r):
 
 
 # ---------------------------------------------------------------------------------------------------
+# frame-block sharded post-processing (N > 1 ranks, results stay rank-local)
+# ---------------------------------------------------------------------------------------------------
+def rank_local_supported(st):
+    """The sharded writer covers what shards by frame block with a small halo: one person (the multi-person re-ID,
+    triangulation.py:847-865, is sequential over frames) and the interpolation kinds whose value depends on the two
+    neighbouring good samples only ('linear', the shipped default, and 'none'); a spline over the whole column does not."""
+    s = st.settings
+    return (not s["multi_person"]) and st.n_persons == 1 and s["interpolation"] in ("linear", "none")
+
+
+def _halo_points(gathered, rank, j, side):
+    """Up to two nearest good (label, value) samples of column j held by the ranks before (`side` = -1, nearest last)
+    or after (`side` = +1, nearest first) this rank."""
+    pts = []
+    ranks = range(rank - 1, -1, -1) if side < 0 else range(rank + 1, len(gathered))
+    for r in ranks:
+        lab, val = gathered[r]["tail" if side < 0 else "head"]
+        seq = range(1, -1, -1) if side < 0 else range(2)
+        for i in seq:
+            if not np.isnan(lab[j, i]):
+                pts.append((lab[j, i], val[j, i]))
+                if len(pts) == 2:
+                    return pts[::-1] if side < 0 else pts
+    return pts[::-1] if side < 0 else pts
+
+
+def write_outputs_sharded(st, res, rank, world):
+    """`write_outputs` (triangulation.py:877-959) with the results left where they were computed: every rank
+    post-processes its own frame block and writes its own byte range of the TRC; what crosses ranks is per COLUMN a
+    handful of boundary samples (interpolation and fill halos), per FRAME one mean error (the trimming decision), and
+    per rank its text length and its recap sums — a few hundred bytes per keypoint instead of 37 bytes per unit.
+    The file is byte-identical to the single-process one (tests/test_sharding_gloo.py)."""
+    import warnings
+    import torch.distributed as dist
+    from scipy import interpolate
+    from . import _lib, sharding
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    s = st.settings
+    frames_all = np.arange(*st.f_range)
+    F_tot = len(frames_all)
+    b0, b1 = sharding.frame_block(F_tot, rank, world)
+    Fl, K = b1 - b0, res["Q"].shape[2]
+    frames = frames_all[b0:b1]
+    n_cams, min_chunk = st.n_cams, s["min_chunk_size"]
+    Qn = res["Q"][:, 0].reshape(Fl, 3 * K).astype(np.float64).copy()
+    en = res["err"][:, 0].astype(np.float64)
+    xn = res["nexcl"][:, 0].astype(np.float64)
+    mn = res["mask"][:, 0]
+
+    # ---- interpolation of small gaps (common.py:669-712), halo = two good samples per column and side ------------
+    if s["interpolation"] == "linear":
+        good = ~(np.isnan(Qn) | (Qn == 0))
+        head_l, head_v = np.full((3 * K, 2), np.nan), np.full((3 * K, 2), np.nan)
+        tail_l, tail_v = np.full((3 * K, 2), np.nan), np.full((3 * K, 2), np.nan)
+        for j in range(3 * K):
+            idx = np.flatnonzero(good[:, j])
+            h, t = idx[:2], idx[-2:]
+            head_l[j, :len(h)], head_v[j, :len(h)] = frames[h], Qn[h, j]
+            tail_l[j, 2 - len(t):], tail_v[j, 2 - len(t):] = frames[t], Qn[t, j]
+        G = gather({"count": good.sum(axis=0), "head": (head_l, head_v), "tail": (tail_l, tail_v)})
+        total = np.sum([g["count"] for g in G], axis=0)
+        for j in range(3 * K):
+            if total[j] <= 4 or Fl == 0:                              # :683: columns with <= 4 good samples stay as they are
+                continue
+            bad = np.flatnonzero(~good[:, j])
+            if bad.size == 0:
+                continue
+            before, after = _halo_points(G, rank, j, -1), _halo_points(G, rank, j, +1)
+            xs = np.concatenate([[p[0] for p in before], frames[good[:, j]], [p[0] for p in after]]).astype(np.float64)
+            ys = np.concatenate([[p[1] for p in before], Qn[good[:, j], j], [p[1] for p in after]])
+            f = interpolate.interp1d(xs, ys, kind="linear", fill_value="extrapolate", bounds_error=False)
+            col = Qn[:, j].copy()
+            col[bad] = f(frames[bad])
+            first_label = (before[-1][0] + 1) if before else frames_all[0]      # where a gap touching my first row began
+            last_label = (after[0][0] - 1) if after else frames_all[-1]        # ... and where one touching my last row ends
+            for seq in np.split(bad, np.flatnonzero(np.diff(bad) > 1) + 1):
+                g0 = first_label if seq[0] == 0 else frames[seq[0]]
+                g1 = last_label if seq[-1] == Fl - 1 else frames[seq[-1]]
+                if g1 - g0 + 1 > s["interp_gap"]:
+                    col[seq] = np.nan
+            Qn[:, j] = col
+
+    # ---- trimming decision on the whole trial: one mean error per frame ------------------------------------------
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        e_mean = (en.mean(axis=1) if s["remove_incomplete_frames"] else np.nanmean(en, axis=1)) if Fl else np.zeros(0)
+    x_mean = xn.mean(axis=1) if Fl else np.zeros(0)
+    e_all = np.concatenate(gather(e_mean))
+    a, b = valid_chunk(e_all, min_chunk, s["sections_to_keep"])
+    if b - a <= min_chunk:
+        if rank == 0:
+            logging.info(f"\nPerson 0: Less than {min_chunk} valid frames in a row. Deleting person.")
+        if b - a == 0:
+            raise Exception("No persons have been triangulated. Please check your calibration and your synchronization, "
+                            "or the triangulation parameters in Config.toml.")
+        if rank == 0:
+            log_recap(st, {"trc_paths": [""], "f_range_trimmed": [[a, b]], "cam_excluded_count": [{}], "error": [None],
+                           "nb_cams_excluded": [None], "interp_frames": [[]], "non_interp_frames": [[]]})
+        return None
+    lo, hi = min(max(a, b0), b1) - b0, max(min(b, b1), b0) - b0           # my rows of the kept section
+    hi = max(hi, lo)
+    Qt, et, xt, mt, fr = Qn[lo:hi], en[lo:hi], xn[lo:hi], mn[lo:hi], frames[lo:hi]
+    first_pos = lo + b0 - a                                              # position of my first kept row in the section
+
+    # ---- recap inputs (per rank sums; rank 0 adds them up) --------------------------------------------------------
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        err_cols = np.concatenate([et, e_mean[lo:hi, None]], axis=1)
+        nex_cols = np.concatenate([xt, x_mean[lo:hi, None]], axis=1)
+        sums = {"err_sum": np.nansum(err_cols, axis=0), "err_n": np.count_nonzero(~np.isnan(err_cols), axis=0),
+                "nex_sum": np.nansum(nex_cols, axis=0), "nex_n": np.count_nonzero(~np.isnan(nex_cols), axis=0),
+                "cams": np.array([np.count_nonzero((mt >> np.uint32(c)) & np.uint32(1)) for c in range(n_cams)], np.int64)}
+    xs = Qt[:, ::3].T
+    kpt_i, pos = np.where((xs == 0) | ~np.isfinite(xs))
+    pos = pos + first_pos
+    keep = (a < pos) & (b > pos)                                         # sic (:906): positions against frame bounds
+    sums["bad"] = [pos[keep & (kpt_i == k)] for k in range(K)]
+
+    # ---- large gaps (:910-916): forward / backward fill needs the nearest valid sample of the neighbouring ranks ----
+    if s["fill_large_gaps_with"] == "last_value":
+        ok = ~np.isnan(Qt)
+        has = ok.any(axis=0)
+        first_v = np.where(has, Qt[np.argmax(ok, axis=0), np.arange(3 * K)], np.nan) if hi > lo else np.full(3 * K, np.nan)
+        last_v = np.where(has, Qt[len(Qt) - 1 - np.argmax(ok[::-1], axis=0), np.arange(3 * K)], np.nan) if hi > lo else np.full(3 * K, np.nan)
+        H = gather((first_v, last_v))
+        if hi > lo:
+            prev_last = np.full(3 * K, np.nan)
+            for r in range(rank):                                        # nearest previous rank wins
+                prev_last = np.where(np.isnan(H[r][1]), prev_last, H[r][1])
+            next_first = np.full(3 * K, np.nan)
+            for r in range(world - 1, rank, -1):                         # nearest following rank wins
+                next_first = np.where(np.isnan(H[r][0]), next_first, H[r][0])
+            ext = np.concatenate([prev_last[None], Qt, next_first[None]], axis=0)
+            Qt = _ffill_bfill(ext)[1:-1]
+            Qt[np.isnan(Qt) | (Qt == np.inf)] = 0
+    elif s["fill_large_gaps_with"] == "zeros":
+        Qt = Qt.copy()
+        Qt[np.isnan(Qt) | (Qt == np.inf)] = 0
+
+    # ---- TRC: rank 0 writes the header, every rank its own rows at its own offset ------------------------------------
+    path, out_dir, rate, header = trc_header(s, b - a, frames_all[a], frames_all[b - 1], st.keypoints_names)
+    fr_a, t_a, yup = trc_row_arrays(Qt, fr, rate, K)
+    cap = max(1, len(fr_a) * (22 + 25 * (3 * K + 1)))
+    buf = np.empty(cap, np.uint8)
+    import ctypes
+    n_bytes = ctypes.c_size_t(0)
+    _lib.check(None, _lib.load().p2s_format_trc_rows(fr_a.ctypes.data, t_a.ctypes.data, yup.ctypes.data, len(fr_a), 3 * K,
+                                                     buf.ctypes.data, cap, ctypes.byref(n_bytes)))
+    sums["bytes"] = int(n_bytes.value)
+    S = gather(sums)
+    if rank == 0:
+        if not os.path.exists(out_dir):
+            os.mkdir(out_dir)
+        with open(path, "wb") as f:
+            f.write(header.encode())
+            f.truncate(len(header.encode()) + sum(g["bytes"] for g in S))
+    dist.barrier()
+    offset = len(header.encode()) + sum(g["bytes"] for g in S[:rank])
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        os.pwrite(fd, memoryview(buf)[:n_bytes.value], offset)
+    finally:
+        os.close(fd)
+    dist.barrier()
+    if rank != 0:
+        return None
+
+    # ---- recap on rank 0 (triangulation.py:255-360) --------------------------------------------------------------------
+    if s["make_c3d"]:
+        try:
+            write_c3d(path)
+        except ImportError:
+            logging.warning("make_c3d = true but the optional `c3d` package is not installed: no .c3d written.")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        err_mean = np.sum([g["err_sum"] for g in S], axis=0) / np.sum([g["err_n"] for g in S], axis=0)
+        nex_mean = np.sum([g["nex_sum"] for g in S], axis=0) / np.sum([g["nex_n"] for g in S], axis=0)
+    cams = np.sum([g["cams"] for g in S], axis=0)
+    opportunities = (b - a) * K
+    bad_per_kpt = [np.sort(np.concatenate([g["bad"][k] for g in S])) for k in range(K)]
+    if s["show_interp_indices"]:
+        pairs = [_gap_strings(bad_per_kpt[k], s["interp_gap"]) for k in range(K)]
+        interp_frames, non_interp = [[p[0] for p in pairs]], [[p[1] for p in pairs]]
+    else:
+        interp_frames, non_interp = [None], [[]]
+    recap = {"trc_paths": [path], "f_range_trimmed": [[a, b]],
+             "cam_excluded_count": [{c: int(cams[c]) / opportunities for c in range(n_cams)}],
+             "error": [err_mean[None, :]], "nb_cams_excluded": [nex_mean[None, :]],     # one row = the column means
+             "interp_frames": interp_frames, "non_interp_frames": non_interp}
+    log_recap(st, recap)
+    return recap
+
+
+# ---------------------------------------------------------------------------------------------------
 def gather_units(res, n_frames, rank, world):
     """The ONE collective of the path: every rank's packed per-unit outputs (37 B/unit) to rank 0
     (NCCL over NVLink on a GPU box, gloo in the CPU tests).  Returns the full result on rank 0, None
@@ -529,12 +739,22 @@ def triangulate_all(config_dict):
     OpenPose JSON of the trial, writes `pose-3d/*.trc`, logs the recap.  Returns None.
 
     Under torchrun (torch.distributed initialised, one process per GPU) the frames are sharded in
-    contiguous blocks over the ranks, each rank stages and solves its block on its own GPU, the packed
-    outputs are gathered once on rank 0, which alone writes the files."""
+    contiguous blocks over the ranks and each rank stages and solves its block on its own GPU.  For a single
+    person with linear (or no) interpolation the results then STAY rank-local: every rank post-processes its block
+    and writes its byte range of the TRC (`write_outputs_sharded`).  Otherwise (multi-person re-ID is sequential over
+    frames, spline interpolation spans the whole column) the packed outputs are gathered once on rank 0, which alone
+    writes the files (`P2S_GATHER=rank0` forces that path)."""
     rank, world, local = _world()
     if world > 1:
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            import torch
+            torch.cuda.set_device(local)                    # the collectives below put their tensors on the current device
         st = stage_project(config_dict, rank, world)
         res = solve_units(st, device=local)
+        if rank_local_supported(st) and os.environ.get("P2S_GATHER", "local") != "rank0":
+            write_outputs_sharded(st, res, rank, world)     # results stay rank-local: no gather of the 37 B/unit outputs
+            return
         res = gather_units(res, len(range(*st.f_range)), rank, world)
         if rank != 0:
             return

@@ -114,6 +114,91 @@ def test_dropin_two_ranks_writes_the_reference_trc(golden, tmp_path, tag):
         assert_trc_equal(got[name], ref[name], tol=1e-6)
 
 
+# ---- rank-local post-processing: the sharded writer must produce the single-process file byte for byte ----------
+def _variant_worker(rank, world, port, proj, cfg, log_path):
+    import logging
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from pose2sim_b200 import triangulation as tri
+    import test_dropin_host as tdh
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank == 0:
+        logging.basicConfig(filename=log_path, level=logging.INFO, format="%(message)s", force=True)
+    tri.solve_units = lambda st, engine=None, device=0: tdh.oracle_units(st)      # TEST stand-in for the device call
+    try:
+        os.chdir(proj)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                tri.triangulate_all(cfg)
+                outcome = ""
+            except Exception as e:
+                outcome = type(e).__name__ + ": " + str(e)[:60]
+        with open(os.path.join(proj, f"outcome_{rank}.txt"), "w") as f:
+            f.write(outcome)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+SHARDED_VARIANTS = [("e2e_tri_variants.npz", 1, 3), ("e2e_tri_variants.npz", 2, 2), ("e2e_tri_variants.npz", 4, 3),
+                    ("e2e_tri_variants2.npz", 3, 3), ("e2e_tri_variants2.npz", 4, 4), ("e2e_tri_variants3.npz", 0, 3),
+                    ("e2e_tri_variants3.npz", 10, 2), ("e2e_tri_variants3.npz", 9, 5)]
+
+
+@pytest.mark.parametrize("batch,i,world", SHARDED_VARIANTS)
+def test_sharded_writer_equals_single_process(golden, tmp_path, batch, i, world):
+    """`write_outputs_sharded` (results stay rank-local, every rank writes its byte range of the TRC) against
+    `write_outputs` in one process on reference-generated configuration variants: frame ranges, gaps that cross rank
+    boundaries (interpolated and too long), every fill / trimming mode, missing files, failing trials.  Same bytes, same
+    exception, same log lines."""
+    import logging
+    import warnings
+    import test_dropin_host as tdh
+    from dropin_util import in_dir, rebuild_variant, written_trcs
+    from pose2sim_b200 import triangulation as tri
+    gs, gv = golden("e2e_tri_single.npz"), golden(batch)
+    # one process
+    proj1, cfg1 = rebuild_variant(gs, gv, i, tmp_path / "one")
+    log1 = str(tmp_path / "one.log")
+    h = logging.FileHandler(log1)
+    h.setFormatter(logging.Formatter("%(message)s"))
+    logging.getLogger().addHandler(h)
+    logging.getLogger().setLevel(logging.INFO)
+    want_exc = ""
+    try:
+        with in_dir(proj1), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = tri.stage_project(cfg1)
+            assert tri.rank_local_supported(st), "pick variants the sharded writer covers"
+            try:
+                tri.write_outputs(st, tdh.oracle_units(st))
+            except Exception as e:
+                want_exc = type(e).__name__ + ": " + str(e)[:60]
+    finally:
+        logging.getLogger().removeHandler(h)
+        h.close()
+    want = written_trcs(proj1)
+    # `world` ranks
+    proj, cfg = rebuild_variant(gs, gv, i, tmp_path / "many")
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    logn = str(tmp_path / "many.log")
+    mp.spawn(_variant_worker, args=(world, port, proj, cfg, logn), nprocs=world, join=True)
+    got = written_trcs(proj)
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert got[name] == want[name], name                    # byte-identical
+    for r in range(world):
+        assert open(os.path.join(proj, f"outcome_{r}.txt")).read() == want_exc
+    mask = lambda text: text.replace(str(tmp_path / "one"), "<tmp>").replace(str(tmp_path / "many"), "<tmp>")
+    assert mask(open(logn).read()) == mask(open(log1).read())
+
+
 # ---- associate_all under a 2-rank job: frames sharded, every rank writes its own files, no gather -------------
 def _assoc_worker(rank, world, port, proj, cfg, multi):
     import sys
