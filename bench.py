@@ -4,10 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one batch of synthetic input resident in HBM:
-stage (likelihood gate + float4 SoA) -> triangulate with camera-exclusion search; at N > 1 every rank
-owns its own frame block (weak scaling, no data-path collective) and the packed per-unit outputs are
-gathered to rank 0 over NCCL inside the timed region (north_star's "final gather").
+A "step" is one pass of the hot path over one batch of synthetic input resident in HBM: ONE search kernel (likelihood
+gate + SoA staging fused into its tile load, weighted DLT + camera-exclusion search) followed by the wide-likelihood /
+arrival-flag kernel that returns at once on this workload.  At N > 1 every rank owns its own frame block (weak scaling,
+no data-path collective) and — default `--gather local` — the results STAY in the rank's HBM, because that is what the
+product does: `triangulate_all` under torchrun post-processes every frame block on its own rank and writes its byte
+range of the TRC (`triangulation.write_outputs_sharded`).  `--gather push` (every finished tile is stored into rank 0's
+memory over NVLink by the search kernel itself) and `--gather nccl` (`dist.gather` after the kernel) measure the
+gather-to-one alternatives; both are bounded by rank 0's NVLink ingress.
+The same line carries a `cfg3` sub-object: BASELINE.json configs[2] (16 cameras, min_cameras 3, 125 k frames per GPU,
+inputs generated on the device) timed the same way, so that a 1/2/4/8-GPU scaling run shows that configuration too.
 
 Keys beyond the base contract: `roofline` (FP64 CUDA-core bound, plus the HBM view), `cpu_baseline`
 (the oracle port on this box's host cores), `e2e` (host buffers through the C ABI, copies timed; `link_bound_ms` =
@@ -133,13 +139,53 @@ def _port_worker(args):
     return len(x)
 
 
-class PythonPort:
-    """The NumPy restatement of the reference's per-unit path on all host cores (multiprocessing)."""
+_REF = None
 
-    def __init__(self, wl, cfg):
+
+def _ref_init():
+    """Pool initializer of the live-reference arm: import the UNMODIFIED reference through oracle/ref_shim.py."""
+    global _REF
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    _REF = ref_shim.load_reference()
+
+
+def _ref_worker(args):
+    """The reference's own per-unit function (Pose2Sim/triangulation.py:363 `triangulation_from_best_cameras`), called the
+    way `triangulate_all` calls it (:837-840) on the gated (3, C) slices."""
+    import warnings
+    x, y, w, P, thr, mc = args
+    cfg = {"triangulation": {"reproj_error_threshold_triangulation": thr, "min_cameras_for_triangulation": mc,
+                             "handle_LR_swap": False, "undistort_points": False}}
+    Plist = [P[c] for c in range(P.shape[0])]
+    fn = _REF.triangulation.triangulation_from_best_cameras
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for u in range(len(x)):
+            coords = np.array([x[u].astype(np.float64), y[u].astype(np.float64), w[u].astype(np.float64)])
+            fn(cfg, coords, coords, Plist, None)
+    return len(x)
+
+
+def live_reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_shim
+        return ref_shim.reference_available()
+    except Exception:
+        return False
+
+
+class PythonPort:
+    """The reference's per-unit path on all host cores (multiprocessing): the UNMODIFIED reference itself when it is
+    present (`live=True`: build container, or a vendored copy named by P2S_REFERENCE_ROOT), else its NumPy restatement."""
+
+    def __init__(self, wl, cfg, live=False):
         import multiprocessing as mp
         self.cores = len(os.sched_getaffinity(0))
-        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.live = live
+        self.worker = _ref_worker if live else _port_worker
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_ref_init if live else None)
         self.wl, self.cfg = wl, cfg
 
     def run(self, n_units):
@@ -150,7 +196,7 @@ class PythonPort:
         jobs = [(wl["x"][i:min(i + per, n_units)], wl["y"][i:min(i + per, n_units)], wl["lik"][i:min(i + per, n_units)],
                  wl["P"], cfg["thr"], cfg["min_cams"]) for i in range(0, n_units, per)]
         t0 = time.perf_counter()
-        done = sum(self.pool.map(_port_worker, jobs, chunksize=1))
+        done = sum(self.pool.map(self.worker, jobs, chunksize=1))
         dt = time.perf_counter() - t0
         assert done == n_units
         return dt, n_units
@@ -190,15 +236,18 @@ def parity_block(eng, cwl, cfg, n_units, oracle_res, eps=1e-6):
 
 
 def run_reference_arm(args, cfg, rank, world):
-    """`--impl reference`: the reference is pure Python and cannot travel to the GPU box, so this arm
-    times the oracle port (oracle/p2s_oracle.py: same per-unit / per-candidate NumPy structure as the
-    reference) on all host cores, on a bounded sample of the same workload."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores, on a bounded sample of
+    the same workload.  Where the reference is importable (`/root/reference` in the build container, or a copy named by
+    P2S_REFERENCE_ROOT) that is the UNMODIFIED `triangulation_from_best_cameras` through oracle/ref_shim.py
+    (`kind: "reference"`); on the GPU box, where it is absent (pure Python: it cannot travel as a compiled oracle/_ref),
+    the NumPy port with the same per-unit / per-candidate structure (`kind: "port"`)."""
     if rank != 0:
         return
     from pose2sim_b200 import synth
     sample_frames = 4000
     wl = synth.make_triangulation_workload(cfg["C"], sample_frames, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=cfg["lik_thr"])
-    port = PythonPort(wl, cfg)
+    live = live_reference_available()
+    port = PythonPort(wl, cfg, live=live)
     dt, n = port.run(port.cores * 64)                          # calibration (also warms the pool)
     rate = n / dt
     budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
@@ -218,14 +267,49 @@ def run_reference_arm(args, cfg, rank, world):
             "config": {"workload": cfg["name"], "n_cams": cfg["C"], "keypoints": cfg["K"],
                        "reproj_error_threshold_triangulation": cfg["thr"], "min_cameras_for_triangulation": cfg["min_cams"],
                        "likelihood_threshold_triangulation": cfg["lik_thr"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.cores, "kind": "port",
-                             "sample": f"first {per_step} units of the workload per step, NumPy per-unit port of "
-                                       f"triangulation_from_best_cameras, multiprocessing over all host cores",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.cores, "kind": "reference" if live else "port",
+                             "sample": f"first {per_step} units of the workload per step, "
+                                       + ("the UNMODIFIED reference's triangulation_from_best_cameras (Pose2Sim/triangulation.py:363) "
+                                          "through oracle/ref_shim.py" if live else
+                                          "NumPy per-unit port of triangulation_from_best_cameras (the reference is absent on this box)")
+                                       + ", multiprocessing over all host cores",
                              "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
                                         "what": "plain-C restatement (one-sided Jacobi SVD), OpenMP"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+def cfg3_leg(eng, torch, barrier, dev, rank, steps=10):
+    """BASELINE.json configs[2] beside the headline workload: 16 cameras, min_cameras 3, 125 k frames per GPU (1 M / 8),
+    inputs generated ON THE DEVICE (csrc/p2s_synth.cu, a pure function of (seed, unit, camera) — every rank draws its own
+    frame block), timed like the main step: barrier, `steps` launches, CUDA events, max over ranks by the caller."""
+    from pose2sim_b200 import ops, synth
+    cfg = WORKLOADS["cfg3"]
+    C, F, K = cfg["C"], cfg["F"], cfg["K"]
+    U = F * K
+    P = synth.ring_cameras(C)[0]
+    wl = eng.synth_observations(P, rank * U, U, K, cfg["seed"])
+    stats = eng.new_stats()
+    out = eng.triangulate_planes(wl["x"], wl["y"], wl["lik"], P, cfg["lik_thr"], cfg["thr"], cfg["min_cams"], stats=stats)
+    torch.cuda.synchronize()
+    st = ops.stats_dict(stats.cpu().numpy())
+    for _ in range(3):
+        eng.triangulate_planes(wl["x"], wl["y"], wl["lik"], P, cfg["lik_thr"], cfg["thr"], cfg["min_cams"], out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        eng.triangulate_planes(wl["x"], wl["y"], wl["lik"], P, cfg["lik_thr"], cfg["thr"], cfg["min_cams"], out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    del wl, out
+    torch.cuda.empty_cache()
+    return {"workload": cfg["name"] + "; inputs from the device generator (p2s_synth_observations_device)", "n_cams": C,
+            "min_cameras_for_triangulation": cfg["min_cams"], "units_per_gpu": U, "steps": steps, "ms_per_step": ms,
+            "kernel_ms": ms, "flops": algorithmic_flops(st), "level_hist": st["level_hist"],
+            "candidates_per_unit": st["candidates"] / U, "gather": "none: results stay in the rank's HBM"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -248,9 +332,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--output-mode", default="vector", choices=["vector", "bulk"],
                     help="how a finished tile leaves the kernel: 16-byte vector stores or cp.async.bulk (TMA) stores")
-    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
-                    help="N > 1: 'push' = the kernel stores its outputs straight into rank 0's memory over NVLink "
+    ap.add_argument("--gather", default="local", choices=["local", "push", "nccl"],
+                    help="N > 1: 'local' = results stay in the rank's HBM (the product's rank-local post-processing), "
+                         "'push' = the kernel stores its outputs straight into rank 0's memory over NVLink "
                          "(sharding.PeerGather), 'nccl' = dist.gather after the kernel")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 sub-object")
     args = ap.parse_args()
     global JSON_OUT
     JSON_OUT = _claim_stdout()
@@ -317,7 +403,7 @@ def main():
             gather_mode = "push"
             side = torch.cuda.Stream(device=dev)
     if world > 1 and pg is None:
-        gather_mode = "nccl"
+        gather_mode = "nccl" if args.gather != "local" else "local"
     gather_lists = [[torch.empty_like(packs[0]) for _ in range(world)] for _ in range(2)] \
         if (gather_mode == "nccl" and rank == 0) else [None, None]
 
@@ -430,13 +516,14 @@ def main():
     sampler.stop_flag = True
     # the link's own bound for exactly these volumes: the three input planes H2D and the packed outputs D2H as plain
     # copies on two streams, no kernel (what `e2e` can reach at best on this box)
-    link_ms = None
+    link_ms = float("nan")
     try:
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         hpack = torch.empty(sharding.PACK_BYTES * U, dtype=torch.uint8).pin_memory()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for rep in range(3):
-            torch.cuda.synchronize()
+        reps = []
+        for rep in range(4):
+            barrier()                                               # all ranks load the host links at the same time
             e0.record()
             s_in.wait_event(e0); s_out.wait_event(e0)
             with torch.cuda.stream(s_in):
@@ -447,17 +534,27 @@ def main():
             torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out)
             e1.record()
             torch.cuda.synchronize()
-            link_ms = e0.elapsed_time(e1) if link_ms is None else min(link_ms, e0.elapsed_time(e1))
+            reps.append(e0.elapsed_time(e1))
+        link_ms = float(np.mean(reps[1:]))                          # mean of 3 after one warm-up, max over ranks below
     except Exception:
-        link_ms = None
+        link_ms = float("nan")
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
 
     # ---- max over ranks --------------------------------------------------------------------------------
-    tm = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, tri_ms, e2e_pipe_s * 1e3], dtype=torch.float64, device=dev)
+    cfg3 = None if args.no_cfg3 or args.workload == "cfg3" else cfg3_leg(eng, torch, barrier, dev, rank)
+    tm = torch.tensor([dev_ms, wall * 1e3, e2e_s * 1e3, tri_ms, e2e_pipe_s * 1e3, link_ms if link_ms == link_ms else 0.0,
+                       cfg3["ms_per_step"] if cfg3 else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, tri_ms_max, e2e_pipe_ms = (float(v) for v in tm.cpu())
+    per_rank = None
+    if world > 1:                                               # per-rank device times (which rank is the slowest, and by how much)
+        mine = torch.tensor([dev_ms / args.steps, cfg3["ms_per_step"] if cfg3 else 0.0], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"step_ms": [round(float(t[0]), 4) for t in allr], "cfg3_ms": [round(float(t[1]), 4) for t in allr]}
+    dev_ms, wall_ms, e2e_ms, tri_ms_max, e2e_pipe_ms, link_max, cfg3_ms = (float(v) for v in tm.cpu())
+    link_ms = link_max if link_max > 0 else None
     step_ms = max(dev_ms, 0.0) / args.steps
     total_units = U * world
     value = total_units / (step_ms * 1e-3)
@@ -480,8 +577,11 @@ def main():
                        "units_per_gpu": U, "reproj_error_threshold_triangulation": thr,
                        "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
                        "seed": cfg["seed"], "l2": f"inputs {(12 * C * U) >> 20} MiB + outputs {(37 * U) >> 20} MiB per step > 126 MB L2, no flush",
-                       "step": "one kernel (TMA-staged raw planes, likelihood gate + SoA transposition in shared memory, exclusion search)"
+                       "step": "one search kernel (TMA-staged raw planes, likelihood gate + SoA transposition in shared memory, "
+                               "exclusion search) + the wide-likelihood / arrival-flag kernel behind it (returns at once here)"
                                + ("" if world == 1 else
+                                  "; results stay in the rank's HBM (rank-local post-processing, triangulation.write_outputs_sharded)"
+                                  if gather_mode == "local" else
                                   " whose stores land in rank 0's memory over NVLink (peer-mapped gather buffer, arrival / "
                                   "release flags, no collective)" if gather_mode == "push" else
                                   " + NCCL gather to rank 0"),
@@ -490,7 +590,8 @@ def main():
                        "failed_units": st["failed"], "eps_band_px": 1e-6,
                        "band_threshold_units": st["band_threshold"], "band_argmin_units": st["band_argmin"]},
             "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                         "traffic": NCU_TRAFFIC.get((args.workload, world)), "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "traffic": NCU_TRAFFIC.get((args.workload, 1)), "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "traffic_measured_in_run": False,
                          "kernel": f"triangulate_kernel<{next(m for m in (4, 6, 8, 12, 16, 24, 32) if C <= m)},secular,exact,lean>",
                          "grid_ctas": eng.last_grid(),
                          "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
@@ -508,16 +609,24 @@ def main():
                                           "(what pageable buffers get)",
                     "host_threads_bound_to_gpu": prev_affinity is not None,
                     "link_bound_ms": link_ms,
-                    "link_bound_note": "the same H2D + D2H volumes as plain pinned copies on two streams, no kernel, on rank 0"},
+                    "link_bound_note": "the same H2D + D2H volumes as plain pinned copies on two streams, no kernel, on ALL ranks at "
+                                       "the same time (barrier before every repetition, mean of 3, max over ranks)"},
             "gpu_launches": launches,
+            "per_rank_ms": per_rank,
             "clocks": sampler.summary(),
             "wall_ms_per_step": wall_ms / args.steps,
         }
+        if cfg3 is not None:
+            cfg3["ms_per_step"] = cfg3_ms
+            cfg3["value"] = cfg3["units_per_gpu"] * world / (cfg3_ms * 1e-3)
+            cfg3["roofline_frac"] = cfg3.pop("flops") / (cfg3.pop("kernel_ms") * 1e-3) / 1e12 / fp64_peak
+            line["cfg3"] = cfg3
         if world == 1 and not args.no_cpu_baseline:
             # bounded CPU sample: the oracle port on this box's host cores
             sample_frames = 2000
             cwl = synth.make_triangulation_workload(C, sample_frames, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=cfg["lik_thr"])
-            port = PythonPort(cwl, cfg)
+            live = live_reference_available()
+            port = PythonPort(cwl, cfg, live=live)
             port.run(port.cores * 32)                                  # warms the pool
             cdt, cn = port.run(port.cores * 64)                        # calibrates the rate
             n_units = int(min(cwl["x"].shape[0], max(port.cores * 64, 12.0 * cn / cdt)))    # ~12 s of CPU work
@@ -525,11 +634,13 @@ def main():
             port.close()
             c_rate, c_threads, c_n, c_res = c_port_rate(cwl, cfg, 52_000, want_results=True)
             line["parity"] = parity_block(eng, cwl, cfg, c_n, c_res)
-            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": port.cores, "kind": "reference" if live else "port",
                                     "value_per_core": n / dt / port.cores,
                                     "full_config_wall_s_extrapolated": U / (n / dt),
-                                    "sample": f"first {n} units (of {U}) of the same workload, NumPy per-unit port of "
-                                              f"triangulation_from_best_cameras (oracle/p2s_oracle.py), one process per core",
+                                    "sample": f"first {n} units (of {U}) of the same workload, "
+                                              + ("the UNMODIFIED reference's triangulation_from_best_cameras through oracle/ref_shim.py"
+                                                 if live else "NumPy per-unit port of triangulation_from_best_cameras "
+                                                 "(oracle/p2s_oracle.py; the reference is absent on this box)") + ", one process per core",
                                     "c_port": {"value": c_rate, "threads": c_threads, "sample_units": c_n,
                                                "what": "plain-C restatement (oracle/p2s_oracle.c), OpenMP"}}
         print(json.dumps(line), file=JSON_OUT, flush=True)

@@ -296,6 +296,26 @@ int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams
                         float *x, float *y, float *lik, int32_t *n_people, uint8_t *status,
                         long long *n_inexact, int n_threads);
 
+/* Association stage, input side (personAssociation.py:67-99 `persons_combinations`, :260-274 `read_json`, re-read there
+ * once per person combination): every file parsed once.  paths [n_frames][n_cams] ("" = no file).  Per file:
+ * count_named = people whose x values are not all NaN (the index space of the combinations), count_listed = keypoint
+ * lists with >= 3 values (the index space the observations are read from), list_len = their common length (0: none,
+ * -1: they differ); obs [n_frames][n_cams][max_persons][n_values] = values [value_offset, value_offset + n_values) of
+ * the listed people in order, NaN where the list is shorter (n_values = 0: counts only, obs may be NULL).
+ * status: 0 unreadable / not JSON, 1 ok, 2 irregular content (left to the host language's own parser, which mirrors
+ * the reference's exception handling), 3 more people than max_persons.                                             */
+int p2s_read_people_files(const char *const *paths, long long n_frames, int n_cams, int value_offset, int n_values,
+                          int max_persons, float *obs, int32_t *count_named, int32_t *count_listed, int32_t *list_len,
+                          uint8_t *status, long long *n_inexact, int n_threads);
+/* Association stage, output side (personAssociation.py:552-580 `rewrite_json_files`): per (frame, camera) the source
+ * document re-emitted exactly as Python's json.dumps(json.load(f)) writes it, with `people` replaced by the chosen
+ * person of every proposal of the frame ({} where the camera is off).  comb: one row of n_cams indices per proposal
+ * (-1 = off); the proposals of frame f are rows prop_offset[f] .. prop_offset[f + 1].  No readable source or an index
+ * past the people list -> no file (a stale one is removed).  status: 1 written, 0 no file, 2 left to the host
+ * language (strings with escapes, duplicate keys, no `people` list).                                               */
+int p2s_rewrite_people_files(const char *const *src, const char *const *dst, long long n_frames, int n_cams,
+                             const int32_t *prop_offset, const int32_t *comb, uint8_t *status, int n_threads);
+
 /* TRC body (triangulation.py:206-213 `Q.to_csv(sep='\t', index=True, header=None)`): APPENDS n_rows lines
  * "frame \t time \t v0 \t ... \n" to `path` (the caller has written the 5 header lines); values is
  * [n_rows][n_cols] float64, NaN = empty field, numbers formatted like Python's repr(float) (what pandas

@@ -88,6 +88,8 @@ SIGNATURES = {
     "p2s_peer_collect_device": (_i, [_vp, _vp, _i, C.c_uint, _vp, _vp]),
     "p2s_peer_error": (_i, [_vp, C.POINTER(C.c_uint)]),
     "p2s_read_pose_files": (_i, [_vp, _ll, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "p2s_read_people_files": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "p2s_rewrite_people_files": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _i]),
     "p2s_write_trc_rows": (_i, [C.c_char_p, _vp, _vp, _vp, _ll, _i]),
     "p2s_format_trc_rows": (_i, [_vp, _vp, _vp, _ll, _i, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "p2s_synth_observations_device": (_i, [_vp, _vp, _i, _i, C.c_uint, _ll, _ll, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

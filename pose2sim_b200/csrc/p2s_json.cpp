@@ -32,6 +32,7 @@ struct Person {
     bool is_object = false;
     bool has_keypoints = false;      // key present and its value is an array
     bool bad_entry = false;          // an array element that float() would reject (string, array, object)
+    bool odd_entry = false;          // an element that is not a plain JSON number (null, true, false, NaN, Infinity)
     std::vector<double> kp;
 };
 
@@ -125,8 +126,9 @@ class Parser {
 
     // scalar-or-container; when `num` is given and the value is numeric-like, *num receives what
     // numpy's float conversion would give (true -> 1, false -> 0, null -> NaN) and *is_num = true
-    bool value(double *num, bool *is_num) {
+    bool value(double *num, bool *is_num, bool *is_plain = nullptr) {
         if (is_num) *is_num = false;
+        if (is_plain) *is_plain = false;
         ws();
         if (p_ >= end_) return false;
         const char c = *p_;
@@ -141,7 +143,7 @@ class Parser {
         else if (c == 'N') { ok = lit("NaN"); v = std::numeric_limits<double>::quiet_NaN(); }
         else if (c == 'I') { ok = lit("Infinity"); v = HUGE_VAL; }
         else if (c == '-' && p_ + 1 < end_ && p_[1] == 'I') { ok = lit("-Infinity"); v = -HUGE_VAL; }
-        else ok = number(&v);
+        else { ok = number(&v); if (is_plain) *is_plain = ok; }
         if (!ok) return false;
         if (num) *num = v;
         if (is_num) *is_num = true;
@@ -166,13 +168,15 @@ class Parser {
     bool number_array(Person &person) {
         person.kp.clear();
         person.bad_entry = false;
+        person.odd_entry = false;
         ++p_;
         ws();
         if (p_ < end_ && *p_ == ']') { ++p_; return true; }
         for (;;) {
             double v;
-            bool is_num;
-            if (!value(&v, &is_num)) return false;
+            bool is_num, is_plain;
+            if (!value(&v, &is_num, &is_plain)) return false;
+            if (!is_plain) person.odd_entry = true;
             if (is_num) person.kp.push_back(v);
             else { person.bad_entry = true; person.kp.push_back(std::numeric_limits<double>::quiet_NaN()); }
             ws();
@@ -331,6 +335,317 @@ extern "C" int p2s_read_pose_files(const char *const *paths, long long n_frames,
     work();
     for (auto &t : pool) t.join();
     if (n_inexact) *n_inexact = inexact.load();
+    return P2S_OK;
+}
+
+// ---- association stage: people lists in, rewritten files out -------------------------------------------------------
+// Pose2Sim/personAssociation.py reads every camera's JSON once per person COMBINATION (:199-205, :260-274) and rewrites
+// the chosen people with json.load + json.dumps per file (:552-580).  Here every source file is parsed once per pass by
+// the threads below.  Two index spaces of the reference are kept apart (SURVEY.md 8(a) caveat):
+//   A  `persons_combinations` (:81-89): people whose x values are not all NaN  -> `count_named`
+//   B  `read_json` (:260-274): keypoint lists with at least 3 values          -> `count_listed`, the order `obs` follows
+// Anything irregular — a person that is not an object, a missing or non-list `pose_keypoints_2d`, elements that are
+// not plain numbers — gets status 2 and is left to the Python path, which mirrors the reference's exception handling
+// statement by statement; regular files (what pose estimators write) never take it.
+extern "C" int p2s_read_people_files(const char *const *paths, long long n_frames, int n_cams, int value_offset,
+                                     int n_values, int max_persons, float *obs, int32_t *count_named,
+                                     int32_t *count_listed, int32_t *list_len, uint8_t *status, long long *n_inexact,
+                                     int n_threads) {
+    if (!paths || n_frames < 0 || n_cams < 1 || value_offset < 0 || n_values < 0 || max_persons < 0 || !status ||
+        !count_named || !count_listed || !list_len || ((long long)n_values * max_persons > 0 && !obs))
+        return P2S_EINVAL;
+    const long long n_files = n_frames * n_cams;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if ((long long)n_threads > n_files) n_threads = (int)(n_files > 0 ? n_files : 1);
+    std::atomic<long long> next{0}, inexact{0};
+    const float fnan = std::numeric_limits<float>::quiet_NaN();
+    const size_t L = (size_t)n_values, NP = (size_t)max_persons, off = (size_t)value_offset;
+    auto work = [&]() {
+        std::string buf;
+        Doc doc;
+        long long my_inexact = 0;
+        for (;;) {
+            const long long i0 = next.fetch_add(16);
+            if (i0 >= n_files) break;
+            const long long i1 = i0 + 16 < n_files ? i0 + 16 : n_files;
+            for (long long i = i0; i < i1; ++i) {
+                float *o = obs ? obs + (size_t)i * NP * L : nullptr;
+                for (size_t j = 0; j < NP * L; ++j) o[j] = fnan;
+                count_named[i] = count_listed[i] = list_len[i] = 0;
+                doc.has_people = false;
+                doc.people.clear();
+                bool ok = paths[i] && paths[i][0] && read_file(paths[i], buf);
+                if (ok) {
+                    Parser ps(buf.data(), buf.data() + buf.size());
+                    ok = ps.parse(doc);
+                }
+                if (!ok) { status[i] = 0; continue; }
+                if (!doc.has_people) { status[i] = 2; continue; }          // no `people` list: the Python path decides
+                bool regular = true;
+                for (const Person &q : doc.people) regular = regular && q.is_object && q.has_keypoints && !q.bad_entry && !q.odd_entry;
+                if (!regular) { status[i] = 2; continue; }
+                int named = 0, listed = 0, len = 0;
+                for (const Person &q : doc.people) {
+                    if (!q.kp.empty()) ++named;                             // A: a non-empty x slice of plain numbers
+                    if (q.kp.size() >= 3) {                                 // B
+                        if (listed == 0) len = (int)q.kp.size();
+                        else if (len != (int)q.kp.size()) len = -1;
+                        if ((size_t)listed < NP) {
+                            float *dst = o + (size_t)listed * L;
+                            if (off + L <= q.kp.size()) {
+                                for (size_t j = 0; j < L; ++j) {
+                                    const double v = q.kp[off + j];
+                                    const float fv = (float)v;
+                                    dst[j] = fv;
+                                    my_inexact += (std::isfinite(v) && (double)fv != v);
+                                }
+                            }                                               // a short slice stays NaN (:203-205)
+                        }
+                        ++listed;
+                    }
+                }
+                count_named[i] = named; count_listed[i] = listed; list_len[i] = len;
+                status[i] = (named > max_persons || listed > max_persons) ? 3 : 1;
+            }
+        }
+        inexact.fetch_add(my_inexact);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    if (n_inexact) *n_inexact = inexact.load();
+    return P2S_OK;
+}
+
+namespace {
+
+char *repr_double(char *p, double v);
+
+// Re-emits a JSON document the way Python's `json.dumps(json.load(f))` writes it (separators ", " and ": ", floats as
+// repr, "-0" -> "0", key order kept), with the elements of the top-level "people" array collected separately so that the
+// caller can put the chosen ones in their place.  Gives up (`fallback`) on anything whose Python round trip is not a
+// plain copy: strings with escapes or non-ASCII bytes, duplicate keys, a top level that is not an object.
+class Reserializer {
+  public:
+    Reserializer(const char *b, const char *e) : p_(b), end_(e) {}
+    bool fallback = false;
+    bool has_people = false;
+    size_t people_pos = 0;
+    std::vector<std::string> people;
+
+    bool run(std::string &out) {
+        ws();
+        if (p_ >= end_ || *p_ != '{') { fallback = true; return false; }
+        if (!object(out, true)) return false;
+        ws();
+        return p_ == end_;
+    }
+
+  private:
+    const char *p_, *end_;
+    int depth_ = 0;
+    void ws() { while (p_ < end_ && (*p_ == ' ' || *p_ == '\t' || *p_ == '\n' || *p_ == '\r')) ++p_; }
+    bool lit(const char *s, std::string &out) {
+        const size_t n = std::strlen(s);
+        if ((size_t)(end_ - p_) < n || std::memcmp(p_, s, n) != 0) return false;
+        out.append(s, n);
+        p_ += n;
+        return true;
+    }
+    bool string(std::string &out, std::string *key) {
+        if (p_ >= end_ || *p_ != '"') return false;
+        const char *b = ++p_;
+        while (p_ < end_ && *p_ != '"') {
+            const unsigned char c = (unsigned char)*p_;
+            if (c < 0x20 || c >= 0x7f || c == '\\') { fallback = true; return false; }
+            ++p_;
+        }
+        if (p_ >= end_) return false;
+        out.push_back('"'); out.append(b, p_); out.push_back('"');
+        if (key) key->assign(b, p_);
+        ++p_;
+        return true;
+    }
+    bool number(std::string &out) {
+        const char *s = p_;
+        bool is_float = false;
+        if (p_ < end_ && *p_ == '-') ++p_;
+        if (p_ >= end_) return false;
+        if (*p_ == '0') ++p_;
+        else if (*p_ >= '1' && *p_ <= '9') { while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_; }
+        else return false;
+        if (p_ < end_ && *p_ == '.') {
+            is_float = true;
+            ++p_;
+            if (p_ >= end_ || *p_ < '0' || *p_ > '9') return false;
+            while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+        }
+        if (p_ < end_ && (*p_ == 'e' || *p_ == 'E')) {
+            is_float = true;
+            ++p_;
+            if (p_ < end_ && (*p_ == '+' || *p_ == '-')) ++p_;
+            if (p_ >= end_ || *p_ < '0' || *p_ > '9') return false;
+            while (p_ < end_ && *p_ >= '0' && *p_ <= '9') ++p_;
+        }
+        if (!is_float) {
+            if (p_ - s == 2 && s[0] == '-' && s[1] == '0') out.push_back('0');     // int("-0") == 0
+            else out.append(s, p_);
+            return true;
+        }
+        double v = 0.0;
+        auto r = std::from_chars(s, p_, v);
+        if (r.ec == std::errc::result_out_of_range) v = std::strtod(std::string(s, p_).c_str(), nullptr);
+        else if (r.ec != std::errc()) return false;
+        if (std::isinf(v)) { out.append(v < 0 ? "-Infinity" : "Infinity"); return true; }
+        char tmp[40];
+        char *e = repr_double(tmp, v);
+        out.append(tmp, e);
+        return true;
+    }
+    bool value(std::string &out) {
+        ws();
+        if (p_ >= end_) return false;
+        const char c = *p_;
+        if (c == '{') return object(out, false);
+        if (c == '[') return array(out);
+        if (c == '"') return string(out, nullptr);
+        if (c == 't') return lit("true", out);
+        if (c == 'f') return lit("false", out);
+        if (c == 'n') return lit("null", out);
+        if (c == 'N') return lit("NaN", out);
+        if (c == 'I') return lit("Infinity", out);
+        if (c == '-' && p_ + 1 < end_ && p_[1] == 'I') return lit("-Infinity", out);
+        return number(out);
+    }
+    bool array(std::string &out) {
+        if (++depth_ > 512) return false;
+        ++p_;
+        out.push_back('[');
+        ws();
+        if (p_ < end_ && *p_ == ']') { ++p_; --depth_; out.push_back(']'); return true; }
+        for (;;) {
+            if (!value(out)) return false;
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; out.append(", "); continue; }
+            if (*p_ == ']') { ++p_; --depth_; out.push_back(']'); return true; }
+            return false;
+        }
+    }
+    bool people_array() {
+        ++p_;
+        ws();
+        if (p_ < end_ && *p_ == ']') { ++p_; return true; }
+        for (;;) {
+            people.emplace_back();
+            if (!value(people.back())) return false;
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; continue; }
+            if (*p_ == ']') { ++p_; return true; }
+            return false;
+        }
+    }
+    bool object(std::string &out, bool top) {
+        if (++depth_ > 512) return false;
+        ++p_;
+        out.push_back('{');
+        ws();
+        if (p_ < end_ && *p_ == '}') { ++p_; --depth_; out.push_back('}'); return true; }
+        std::vector<std::string> keys;
+        std::string key;
+        for (;;) {
+            ws();
+            if (!string(out, &key)) return false;
+            for (const std::string &k : keys) if (k == key) { fallback = true; return false; }   // dict: last value, first place
+            keys.push_back(key);
+            ws();
+            if (p_ >= end_ || *p_ != ':') return false;
+            ++p_;
+            out.append(": ");
+            ws();
+            if (top && key == "people") {
+                if (p_ >= end_ || *p_ != '[') { fallback = true; return false; }
+                has_people = true;
+                people_pos = out.size();
+                if (!people_array()) return false;
+            } else if (!value(out)) {
+                return false;
+            }
+            ws();
+            if (p_ >= end_) return false;
+            if (*p_ == ',') { ++p_; out.append(", "); continue; }
+            if (*p_ == '}') { ++p_; --depth_; out.push_back('}'); return true; }
+            return false;
+        }
+    }
+};
+
+}  // namespace
+
+// personAssociation.py:552-580 `rewrite_json_files` for all frames: per (frame, camera) the source document re-emitted
+// with `people` replaced by the chosen person of every proposal of the frame ({} where the camera is off).  comb holds
+// one row of n_cams indices per proposal (-1 = off), the proposals of frame f are rows prop_offset[f] .. prop_offset[f+1].
+// A camera without a readable source, or an index past its people list, gets NO file (a stale one is removed), like the
+// reference's `except: os.remove`.  status: 1 written, 0 no file, 2 left to the Python path (see Reserializer).
+extern "C" int p2s_rewrite_people_files(const char *const *src, const char *const *dst, long long n_frames, int n_cams,
+                                        const int32_t *prop_offset, const int32_t *comb, uint8_t *status, int n_threads) {
+    if (!src || !dst || n_frames < 0 || n_cams < 1 || !prop_offset || !status) return P2S_EINVAL;
+    const long long n_files = n_frames * n_cams;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if ((long long)n_threads > n_files) n_threads = (int)(n_files > 0 ? n_files : 1);
+    std::atomic<long long> next{0};
+    auto work = [&]() {
+        std::string buf, out, fin;
+        for (;;) {
+            const long long i0 = next.fetch_add(16);
+            if (i0 >= n_files) break;
+            const long long i1 = i0 + 16 < n_files ? i0 + 16 : n_files;
+            for (long long i = i0; i < i1; ++i) {
+                const long long f = i / n_cams;
+                const int c = (int)(i % n_cams);
+                status[i] = 0;
+                if (!dst[i] || !dst[i][0]) continue;
+                bool ok = src[i] && src[i][0] && read_file(src[i], buf);
+                if (ok) {
+                    out.clear();
+                    Reserializer rs(buf.data(), buf.data() + buf.size());
+                    ok = rs.run(out);
+                    if (rs.fallback || (ok && !rs.has_people)) { status[i] = 2; continue; }
+                    if (ok) {
+                        fin.assign(out, 0, rs.people_pos);
+                        fin.push_back('[');
+                        for (int32_t r = prop_offset[f]; r < prop_offset[f + 1] && ok; ++r) {
+                            const int32_t idx = comb[(size_t)r * n_cams + c];
+                            if (r > prop_offset[f]) fin.append(", ");
+                            if (idx < 0) fin.append("{}");
+                            else if ((size_t)idx < rs.people.size()) fin.append(rs.people[(size_t)idx]);
+                            else ok = false;                                   // IndexError in the reference
+                        }
+                        fin.push_back(']');
+                        fin.append(out, rs.people_pos, std::string::npos);
+                    }
+                }
+                if (ok) {
+                    FILE *g = std::fopen(dst[i], "wb");
+                    ok = g != nullptr;
+                    if (g) {
+                        ok = std::fwrite(fin.data(), 1, fin.size(), g) == fin.size();
+                        ok = (std::fclose(g) == 0) && ok;
+                    }
+                }
+                if (ok) status[i] = 1;
+                else std::remove(dst[i]);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
     return P2S_OK;
 }
 

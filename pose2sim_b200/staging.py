@@ -253,6 +253,55 @@ def count_persons(input_dir, cam_dirs, json_files_names):
     return best
 
 
+# ---- association: native reader / writer ---------------------------------------------------------------------
+def _c_paths(paths):
+    import ctypes as C
+    flat = [p.encode() for row in paths for p in row]
+    return (C.c_char_p * len(flat))(*flat)
+
+
+def read_people_files(paths, value_offset, n_values, max_persons, n_threads=0):
+    """Native reader of the association stage (`p2s_read_people_files`): paths [F][C] -> obs float32
+    [F, C, max_persons, n_values] (None when n_values == 0), count_named, count_listed, list_len int32 [F, C],
+    status uint8 [F, C] and the number of values float32 could not hold exactly."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    F = len(paths)
+    n_cams = len(paths[0]) if F else 1
+    arr = _c_paths(paths)
+    obs = np.empty((F, n_cams, max_persons, n_values), np.float32) if n_values * max_persons else None
+    named, listed, llen = (np.zeros((F, n_cams), np.int32) for _ in range(3))
+    status = np.zeros((F, n_cams), np.uint8)
+    inexact = C.c_longlong(0)
+    _lib.check(None, lib.p2s_read_people_files(C.cast(arr, C.c_void_p), F, n_cams, int(value_offset), int(n_values), int(max_persons),
+                                               obs.ctypes.data if obs is not None else None, named.ctypes.data, listed.ctypes.data,
+                                               llen.ctypes.data, status.ctypes.data, C.cast(C.pointer(inexact), C.c_void_p), int(n_threads)))
+    return obs, named, listed, llen, status, int(inexact.value)
+
+
+def rewrite_people_files(src_paths, dst_paths, proposals, n_threads=0):
+    """Native writer of the association stage (`p2s_rewrite_people_files`).  proposals[f] = array [n_f, C] of person
+    indices (NaN = camera off).  Returns status uint8 [F, C] (1 written, 0 no file, 2 needs the Python writer)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    F = len(src_paths)
+    n_cams = len(src_paths[0]) if F else 1
+    offs = np.zeros(F + 1, np.int32)
+    rows = []
+    for f, prop in enumerate(proposals):
+        a = np.asarray(prop, dtype=np.float64).reshape(-1, n_cams) if np.size(prop) else np.zeros((0, n_cams))
+        rows.append(np.where(np.isnan(a), -1, a).astype(np.int32))
+        offs[f + 1] = offs[f] + len(a)
+    comb = np.ascontiguousarray(np.concatenate(rows) if rows else np.zeros((0, n_cams), np.int32), dtype=np.int32)
+    status = np.zeros((F, n_cams), np.uint8)
+    s_arr, d_arr = _c_paths(src_paths), _c_paths(dst_paths)
+    _lib.check(None, lib.p2s_rewrite_people_files(C.cast(s_arr, C.c_void_p), C.cast(d_arr, C.c_void_p), F, n_cams, offs.ctypes.data,
+                                                  comb.ctypes.data if len(comb) else None, status.ctypes.data, int(n_threads)))
+    return status
+
+
 # ---- association --------------------------------------------------------------------------------------
 def persons_per_camera(js):
     """personAssociation.py:81-89: people whose x values are not all NaN; any failure -> 0."""
