@@ -296,6 +296,25 @@ int p2s_read_pose_files(const char *const *paths, long long n_frames, int n_cams
                         float *x, float *y, float *lik, int32_t *n_people, uint8_t *status,
                         long long *n_inexact, int n_threads);
 
+/* Directory index (triangulation.py:752-803, common.py:568-583): the camera folders listed, *.json kept and sorted by the
+ * last number in the name, and the frame -> file table built with the reference's rule (all files of a camera whose last
+ * number is the frame, or none; flattened; first n_cams entries).  p2s_index_open fails with P2S_EINVAL when a folder
+ * cannot be listed, p2s_index_build_table when a name holds no number (the reference raises there).  The table is
+ * [f1 - f0][n_cams] absolute paths ("" = no file), valid until the next build / close; it is what p2s_read_pose_files
+ * takes.  p2s_index_signature: 128-bit digest of every table entry's path, mtime (ns) and size (staging cache key).   */
+typedef struct p2s_dir_index p2s_dir_index;
+int p2s_index_open(const char *const *dirs, int n_cams, p2s_dir_index **out);
+void p2s_index_close(p2s_dir_index *ix);
+long long p2s_index_file_count(const p2s_dir_index *ix, int cam);
+const char *p2s_index_file_name(const p2s_dir_index *ix, int cam, long long i);
+int p2s_index_build_table(p2s_dir_index *ix, long long f0, long long f1);
+const char *const *p2s_index_table_paths(const p2s_dir_index *ix);
+int p2s_index_signature(const p2s_dir_index *ix, unsigned long long sig[2], int n_threads);
+
+/* (mtime in ns, size in bytes) of n files, -1 / -1 where stat fails: the signature the staging cache is keyed on
+ * (pose2sim_b200/staging.py: parsed trials are kept as memory-mapped float32 planes and reused while no file changed). */
+int p2s_stat_files(const char *const *paths, long long n, long long *mtime_ns, long long *size, int n_threads);
+
 /* Association stage, input side (personAssociation.py:67-99 `persons_combinations`, :260-274 `read_json`, re-read there
  * once per person combination): every file parsed once.  paths [n_frames][n_cams] ("" = no file).  Per file:
  * count_named = people whose x values are not all NaN (the index space of the combinations), count_listed = keypoint

@@ -88,6 +88,14 @@ SIGNATURES = {
     "p2s_peer_collect_device": (_i, [_vp, _vp, _i, C.c_uint, _vp, _vp]),
     "p2s_peer_error": (_i, [_vp, C.POINTER(C.c_uint)]),
     "p2s_read_pose_files": (_i, [_vp, _ll, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "p2s_index_open": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "p2s_index_close": (None, [_vp]),
+    "p2s_index_file_count": (_ll, [_vp, _i]),
+    "p2s_index_file_name": (C.c_char_p, [_vp, _i, _ll]),
+    "p2s_index_build_table": (_i, [_vp, _ll, _ll]),
+    "p2s_index_table_paths": (_vp, [_vp]),
+    "p2s_index_signature": (_i, [_vp, _vp, _i]),
+    "p2s_stat_files": (_i, [_vp, _ll, _vp, _vp, _i]),
     "p2s_read_people_files": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "p2s_rewrite_people_files": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _i]),
     "p2s_write_trc_rows": (_i, [C.c_char_p, _vp, _vp, _vp, _ll, _i]),

@@ -24,6 +24,11 @@
 #include <thread>
 #include <vector>
 
+#include <algorithm>
+#include <dirent.h>
+#include <new>
+#include <sys/stat.h>
+
 #include "../../include/pose2sim_b200.h"
 
 namespace {
@@ -335,6 +340,176 @@ extern "C" int p2s_read_pose_files(const char *const *paths, long long n_frames,
     work();
     for (auto &t : pool) t.join();
     if (n_inexact) *n_inexact = inexact.load();
+    return P2S_OK;
+}
+
+// ---- directory index: listing, the reference's file order and its frame -> file table, natively ---------------------
+// What the reference does per stage in Python (triangulation.py:752-803, common.py:568-583): list every camera folder,
+// keep *.json, sort by the LAST number in the name (names without a number after those, alphabetically; sorted() is
+// stable, so equal numbers keep the listing order), then per frame f pick from every camera ALL its files whose last
+// number is f, or 'none', flatten, and use the first n_cams entries (a camera with two files for one frame shifts the
+// later cameras).  For a 40 k-file trial those list / regex / dict operations cost more than parsing the files, so they
+// live here; staging.py keeps the Python statements as the tested restatement (tests/test_native_staging.py).
+struct p2s_dir_index {
+    struct Entry { std::string name; bool has_num; std::string digits; long long num; };   // digits: last run, no leading zeros
+    std::vector<std::string> dirs;
+    std::vector<std::vector<Entry>> cams;
+    std::vector<std::string> table_store;      // absolute paths of the table, "" = none
+    std::vector<const char *> table;           // [F][C]
+};
+
+namespace {
+
+bool less_digits(const std::string &a, const std::string &b) {      // numeric order of digit strings without leading zeros
+    return a.size() != b.size() ? a.size() < b.size() : a < b;
+}
+
+}  // namespace
+
+extern "C" int p2s_index_open(const char *const *dirs, int n_cams, p2s_dir_index **out) {
+    if (!dirs || n_cams < 1 || !out) return P2S_EINVAL;
+    *out = nullptr;
+    p2s_dir_index *ix = new (std::nothrow) p2s_dir_index();
+    if (!ix) return P2S_ENOMEM;
+    ix->cams.resize((size_t)n_cams);
+    for (int c = 0; c < n_cams; ++c) {
+        ix->dirs.emplace_back(dirs[c] ? dirs[c] : "");
+        DIR *d = ::opendir(ix->dirs.back().c_str());
+        if (!d) { delete ix; return P2S_EINVAL; }                    // os.listdir raises: the caller tries the next folder
+        std::vector<p2s_dir_index::Entry> &v = ix->cams[(size_t)c];
+        while (struct dirent *e = ::readdir(d)) {
+            const char *n = e->d_name;
+            const size_t len = std::strlen(n);
+            if ((len == 1 && n[0] == '.') || (len == 2 && n[0] == '.' && n[1] == '.')) continue;
+            if (len < 5 || std::memcmp(n + len - 5, ".json", 5) != 0) continue;     // fnmatch.filter(..., '*.json')
+            p2s_dir_index::Entry en;
+            en.name.assign(n, len);
+            size_t hi = len;
+            while (hi > 0 && !(n[hi - 1] >= '0' && n[hi - 1] <= '9')) --hi;        // end of the last digit run
+            size_t lo = hi;
+            while (lo > 0 && n[lo - 1] >= '0' && n[lo - 1] <= '9') --lo;
+            en.has_num = hi > lo;
+            en.num = -1;
+            if (en.has_num) {
+                size_t z = lo;
+                while (z + 1 < hi && n[z] == '0') ++z;
+                en.digits.assign(n + z, hi - z);
+                if (en.digits.size() <= 18) en.num = std::strtoll(en.digits.c_str(), nullptr, 10);
+            }
+            v.push_back(std::move(en));
+        }
+        ::closedir(d);
+        std::stable_sort(v.begin(), v.end(), [](const p2s_dir_index::Entry &a, const p2s_dir_index::Entry &b) {
+            if (a.has_num != b.has_num) return a.has_num;             // (False, n) < (True, s)
+            if (a.has_num) return less_digits(a.digits, b.digits);
+            return a.name < b.name;
+        });
+    }
+    *out = ix;
+    return P2S_OK;
+}
+
+extern "C" void p2s_index_close(p2s_dir_index *ix) { delete ix; }
+extern "C" long long p2s_index_file_count(const p2s_dir_index *ix, int cam) {
+    return (ix && cam >= 0 && (size_t)cam < ix->cams.size()) ? (long long)ix->cams[(size_t)cam].size() : -1;
+}
+extern "C" const char *p2s_index_file_name(const p2s_dir_index *ix, int cam, long long i) {
+    if (!ix || cam < 0 || (size_t)cam >= ix->cams.size() || i < 0 || (size_t)i >= ix->cams[(size_t)cam].size()) return nullptr;
+    return ix->cams[(size_t)cam][(size_t)i].name.c_str();
+}
+
+// frames [f0, f1) with the reference's selection rule; P2S_EINVAL when a listed name has no number (the reference raises
+// IndexError at triangulation.py:799 — the caller takes the Python path, which raises it)
+extern "C" int p2s_index_build_table(p2s_dir_index *ix, long long f0, long long f1) {
+    if (!ix) return P2S_EINVAL;
+    const size_t C = ix->cams.size();
+    const long long F = f1 > f0 ? f1 - f0 : 0;
+    for (const auto &v : ix->cams) for (const auto &e : v) if (!e.has_num) return P2S_EINVAL;
+    // per camera: files are sorted by number, so the files of frame f are a contiguous run found by a merge walk
+    std::vector<size_t> pos(C, 0);
+    ix->table_store.clear();
+    ix->table_store.reserve((size_t)F * C);
+    std::vector<std::string> flat;
+    for (long long f = f0; f < f1; ++f) {
+        flat.clear();
+        for (size_t c = 0; c < C; ++c) {
+            const auto &v = ix->cams[c];
+            size_t &p = pos[c];
+            if (f == f0) {                                             // first frame: binary search for the run start
+                size_t lo = 0, hi = v.size();
+                while (lo < hi) { const size_t mid = (lo + hi) / 2; if (v[mid].num >= 0 && v[mid].num < f) lo = mid + 1; else hi = mid; }
+                p = lo;
+            }
+            while (p < v.size() && v[p].num >= 0 && v[p].num < f) ++p;
+            size_t q = p;
+            bool any = false;
+            while (q < v.size() && v[q].num == f) { flat.push_back(v[q].name); ++q; any = true; }
+            if (!any) flat.emplace_back();
+        }
+        // the NAME at flattened position c is joined with camera c's folder (triangulation.py:801-803): after a camera
+        // with two files for the frame the later names land in the wrong folder and read as missing, like in the reference
+        for (size_t c = 0; c < C; ++c) ix->table_store.push_back(flat[c].empty() ? std::string() : ix->dirs[c] + "/" + flat[c]);
+    }
+    ix->table.resize(ix->table_store.size());
+    for (size_t i = 0; i < ix->table_store.size(); ++i) ix->table[i] = ix->table_store[i].c_str();
+    return P2S_OK;
+}
+
+extern "C" const char *const *p2s_index_table_paths(const p2s_dir_index *ix) { return ix ? ix->table.data() : nullptr; }
+
+// ---- file signatures for the staging cache: (mtime in ns, size) per path, -1 / -1 when the file cannot be stat'ed ----
+extern "C" int p2s_stat_files(const char *const *paths, long long n, long long *mtime_ns, long long *size, int n_threads) {
+    if (!paths || n < 0 || !mtime_ns || !size) return P2S_EINVAL;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if ((long long)n_threads > n) n_threads = (int)(n > 0 ? n : 1);
+    std::atomic<long long> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const long long i0 = next.fetch_add(64);
+            if (i0 >= n) break;
+            const long long i1 = i0 + 64 < n ? i0 + 64 : n;
+            for (long long i = i0; i < i1; ++i) {
+                struct stat st;
+                if (paths[i] && paths[i][0] && ::stat(paths[i], &st) == 0) {
+                    mtime_ns[i] = (long long)st.st_mtim.tv_sec * 1000000000LL + (long long)st.st_mtim.tv_nsec;
+                    size[i] = (long long)st.st_size;
+                } else {
+                    mtime_ns[i] = size[i] = -1;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return P2S_OK;
+}
+
+// 128-bit digest of (path, mtime, size) of every table entry: the staging cache key without 40 k Python strings
+extern "C" int p2s_index_signature(const p2s_dir_index *ix, unsigned long long sig[2], int n_threads) {
+    if (!ix || !sig) return P2S_EINVAL;
+    const long long n = (long long)ix->table.size();
+    std::vector<long long> mt((size_t)n), sz((size_t)n);
+    if (n > 0) {
+        const int rc = p2s_stat_files(ix->table.data(), n, mt.data(), sz.data(), n_threads);
+        if (rc) return rc;
+    }
+    unsigned long long h0 = 1469598103934665603ULL, h1 = 0x9e3779b97f4a7c15ULL;
+    auto mix = [&](const void *p, size_t len) {
+        const unsigned char *b = (const unsigned char *)p;
+        for (size_t i = 0; i < len; ++i) {
+            h0 = (h0 ^ b[i]) * 1099511628211ULL;
+            h1 = (h1 + b[i] + (h1 << 6) + (h1 >> 2)) * 0xff51afd7ed558ccdULL;
+        }
+    };
+    for (long long i = 0; i < n; ++i) {
+        mix(ix->table_store[(size_t)i].data(), ix->table_store[(size_t)i].size() + 1);
+        mix(&mt[(size_t)i], sizeof(long long));
+        mix(&sz[(size_t)i], sizeof(long long));
+    }
+    sig[0] = h0; sig[1] = h1;
     return P2S_OK;
 }
 

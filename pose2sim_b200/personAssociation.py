@@ -46,7 +46,7 @@ def read_settings(config_dict):
 
 class StagedAssociation:
     __slots__ = ("settings", "calib_file", "P", "cam_dirs", "dirs", "table", "f_range", "n_cams",
-                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact", "workers", "mp_staged")
+                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact", "workers", "mp_staged", "native", "world")
 
 
 # ---- file I/O on a process pool -------------------------------------------------------------------------------------
@@ -97,7 +97,24 @@ def _rewrite_block(job):
     return len(rows)
 
 
+def _rewrite_native(st, proposals):
+    """`rewrite_json_files` (:552-580) for all frames through the native writer; the few files it leaves alone (status 2:
+    strings with escapes, duplicate keys, no `people` list) are rewritten frame by frame by the Python statements."""
+    C = st.n_cams
+    src = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
+    dst = _stg.frame_paths(st.dirs.tracked_dir, st.cam_dirs, st.table)
+    # 'none' entries: the reference opens <tracked>/<cam>/none for writing, fails on the source and removes it again
+    status = _stg.rewrite_people_files(src, dst, proposals, _io_threads(st.world))
+    for fi in np.flatnonzero((status == 2).any(axis=1)):
+        names = st.table[fi]
+        source = [_stg.load_json(os.path.join(st.dirs.pose_dir, st.cam_dirs[c], names[c])) for c in range(C)]
+        tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(C)]
+        rewrite_frame(tracked, source, proposals[fi])
+
+
 def _rewrite_parallel(st, proposals):
+    if st.native or os.environ.get("P2S_NATIVE_IO", "1") != "0":
+        return _rewrite_native(st, proposals)
     jobs = [(st.dirs.pose_dir, st.dirs.tracked_dir, st.cam_dirs, st.table[a:b], proposals[a:b]) for a, b in _blocks(len(st.table), st.workers)]
     _pool_map(_rewrite_block, jobs, st.workers)
 
@@ -145,6 +162,7 @@ def stage_project(config_dict, rank=0, world=1):
                             f"tracked_keypoint in Config.toml. Tracking {fallback} instead.")
 
     st = StagedAssociation()
+    st.world = world
     st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
     st.cam_dirs, st.dirs, st.f_range, st.n_cams, st.tracked_keypoint_id = cam_dirs, dirs, list(f_range), n_cams, kid
     st.table = _stg.frame_file_table(files, f_range)
@@ -152,8 +170,10 @@ def stage_project(config_dict, rank=0, world=1):
         from . import sharding
         a, b = sharding.frame_block(len(st.table), rank, world)
         st.table = st.table[a:b]
-    st.workers, st.mp_staged = host_workers(len(st.table) * n_cams, world), None
+    st.workers, st.mp_staged, st.native = host_workers(len(st.table) * n_cams, world), None, False
     # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
+    if os.environ.get("P2S_NATIVE_IO", "1") != "0" and _stage_native(st, world):
+        return st
     if st.workers:
         jobs = [(dirs.pose_dir, cam_dirs, st.table[a:b], kid, bool(s["multi_person"])) for a, b in _blocks(len(st.table), st.workers)]
         parts = _pool_map(_stage_block, jobs, st.workers)
@@ -178,6 +198,55 @@ def stage_project(config_dict, rank=0, world=1):
                         f"device staging layout.")
     st.obs = obs.astype(np.float32)
     return st
+
+
+def _io_threads(world):
+    return max(1, len(os.sched_getaffinity(0)) // max(1, world))
+
+
+def _stage_native(st, world):
+    """Staging through the native reader (`p2s_read_people_files`: every file parsed once, all host cores).  Returns
+    False — nothing staged — when any file is irregular (status 2: the Python path below mirrors the reference's
+    exception handling statement by statement) or shows more people than the device search takes (status 3: the
+    Python path raises the documented ValueError)."""
+    s, F, C = st.settings, len(st.table), st.n_cams
+    if F == 0:
+        return False
+    paths = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
+    nt = _io_threads(world)
+    if not s["multi_person"]:
+        NP = _lib.P2S_MAX_PERSONS
+        o3, named, listed, _, status, inexact = _stg.read_people_files(paths, 3 * st.tracked_keypoint_id, 3, NP, nt)
+        if (status >= 2).any():
+            return False
+        obs = np.full((F, C, NP, 4), np.nan, np.float32)
+        obs[..., 3] = 0.0
+        have = np.arange(NP)[None, None, :] < np.minimum(named, listed)[:, :, None]     # :199-205: p < min(A, B)
+        obs[..., :3] = np.where(have[..., None], o3, np.float32(np.nan))
+        st.obs, st.count, st.inexact, st.parsed, st.native = obs, named, inexact, None, True
+        if inexact:
+            logging.warning(f"{inexact} 2D values are not exactly representable in float32 and were rounded for the "
+                            f"device staging layout.")
+        return True
+    _, _, listed, llen, status, _ = _stg.read_people_files(paths, 0, 0, _lib.P2S_MAX_DETECTIONS, nt)
+    if (status >= 2).any():
+        return False
+    lengths = sorted(set(int(v) for v in llen[llen != 0]))
+    if len(lengths) > 1 or (lengths and lengths[0] < 0):
+        return False                                          # the Python path raises the stacking error with the lengths
+    L = lengths[0] if lengths else 3
+    if L % 3:
+        return False
+    NP = max(int(listed.max(initial=0)), 1)
+    obs, _, listed2, _, status2, inexact = _stg.read_people_files(paths, 0, L, NP, nt)
+    if (status2 >= 2).any() or not np.array_equal(listed, listed2):
+        return False
+    n_max = int(listed.sum(axis=1).max(initial=0))
+    if n_max > _lib.P2S_MAX_DETECTIONS:
+        return False
+    st.mp_staged = (obs, listed, inexact)
+    st.obs, st.count, st.inexact, st.parsed, st.native = None, None, 0, None, True
+    return True
 
 
 def solve_frames(st, engine=None, device=0):

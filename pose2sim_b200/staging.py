@@ -100,6 +100,16 @@ class PoseDirs:
         raise Exception(f"No json files found in {self.pose_dir}, {self.sync_dir}, nor {self.tracked_dir} "
                         f"subdirectories. Make sure you run Pose2Sim.poseEstimation() first.")
 
+    def index_for_triangulation(self, cam_dirs):
+        """`files_for_triangulation` through the native lister: (input_dir, NativeIndex)."""
+        for base in (self.tracked_dir, self.sync_dir, self.pose_dir):
+            try:
+                return base, NativeIndex(base, cam_dirs)
+            except OSError:
+                continue
+        raise Exception(f"No json files found in {self.pose_dir}, {self.sync_dir}, nor {self.tracked_dir} "
+                        f"subdirectories. Make sure you run Pose2Sim.poseEstimation() first.")
+
     def files_for_association(self, cam_dirs):
         """pose-sync, else pose (personAssociation.py:724-731).  N.B. the reference LISTS pose-sync but
         then READS from pose/ because of an `os.path.exist` typo (:762-766); both are kept."""
@@ -111,6 +121,76 @@ class PoseDirs:
                 continue
         raise ValueError(f"No json files found in {self.pose_dir} nor {self.sync_dir} subdirectories. "
                          f"Make sure you run Pose2Sim.poseEstimation() first.")
+
+
+class NativeIndex:
+    """The camera folders of one input directory listed, filtered, sorted and tabulated by the native code
+    (`p2s_index_*`, csrc/p2s_json.cpp) — the statements below (`_list`, `sort_by_last_number`, `frame_file_table`,
+    `frame_paths`) without 40 k Python strings in between."""
+
+    def __init__(self, base, cam_dirs):
+        import ctypes as C
+        from . import _lib
+        self.h = None
+        self.lib = _lib.load()
+        self.n_cams = len(cam_dirs)
+        dirs = [os.path.join(base, d).encode() for d in cam_dirs]
+        arr = (C.c_char_p * len(dirs))(*dirs)
+        h = C.c_void_p()
+        if self.lib.p2s_index_open(C.cast(arr, C.c_void_p), len(dirs), C.byref(h)) != 0:
+            raise OSError(f"cannot list the camera folders of {base}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.p2s_index_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def counts(self):
+        return [int(self.lib.p2s_index_file_count(self.h, c)) for c in range(self.n_cams)]
+
+    def names(self):
+        """Per camera the sorted file names (what `files_for_triangulation` returns)."""
+        return [[self.lib.p2s_index_file_name(self.h, c, i).decode() for i in range(n)] for c, n in enumerate(self.counts())]
+
+    def build_table(self, f_range):
+        """False when a listed name holds no number (the Python statements raise the reference's IndexError)."""
+        f0, f1 = (int(f_range[0]), int(f_range[1])) if len(f_range) >= 2 else (0, int(f_range[0]))
+        self.n_frames = len(range(f0, f1))
+        return self.lib.p2s_index_build_table(self.h, f0, f1) == 0
+
+    def table_paths(self):
+        """The current table as [F][C] Python strings ('' = no file) — for tests; the reader takes the C array."""
+        import ctypes as C
+        ptr = C.cast(self.lib.p2s_index_table_paths(self.h), C.POINTER(C.c_char_p))
+        return [[ptr[f * self.n_cams + c].decode() for c in range(self.n_cams)] for f in range(self.n_frames)]
+
+    def signature(self):
+        import ctypes as C
+        sig = (C.c_ulonglong * 2)()
+        if self.lib.p2s_index_signature(self.h, C.cast(sig, C.c_void_p), 0) != 0:
+            raise OSError("signature")
+        return f"{sig[0]:016x}{sig[1]:016x}"
+
+    def read(self, keypoints_ids, nb_persons, n_threads=0):
+        """`read_pose_files` on the current table."""
+        import ctypes as C
+        from . import _lib
+        F, n_cams = self.n_frames, self.n_cams
+        K, N = len(keypoints_ids), int(nb_persons)
+        ids = np.ascontiguousarray(keypoints_ids, dtype=np.int32)
+        x = np.empty((F, N, K, n_cams), np.float32)
+        y, lik = np.empty_like(x), np.empty_like(x)
+        if F == 0:
+            return x, y, lik, 0
+        n_people = np.empty((F, n_cams), np.int32)
+        inexact = C.c_longlong(0)
+        _lib.check(None, self.lib.p2s_read_pose_files(self.lib.p2s_index_table_paths(self.h), F, n_cams, ids.ctypes.data, K, N,
+                                                      x.ctypes.data, y.ctypes.data, lik.ctypes.data, n_people.ctypes.data, None,
+                                                      C.cast(C.pointer(inexact), C.c_void_p), int(n_threads)))
+        return x, y, lik, int(inexact.value)
 
 
 def frame_file_table(json_files_names, f_range):
@@ -206,12 +286,133 @@ def read_pose_files(paths, keypoints_ids, nb_persons, n_threads=0):
     return x, y, lik, n_people, int(inexact.value)
 
 
+# ---- staging cache: parsed trials as memory-mapped SoA planes -------------------------------------------------------
+# once the search takes microseconds, parsing F x C small JSON files is the stage.  A parsed trial
+# is therefore kept as ONE file of float32 planes [3][F][N][K][C] (the layout the device call takes) under
+# $P2S_CACHE_DIR (default ~/.cache/pose2sim_b200) and memory-mapped on the next run.  The key is a digest of every file's
+# path, mtime (ns) and size (one native multi-threaded stat pass, `p2s_stat_files`) plus the keypoint ids and the person
+# count, so any added, removed, rewritten or touched file misses.  P2S_STAGE_CACHE=0 turns it off; trials below
+# CACHE_MIN_FILES are not worth a cache entry; at most CACHE_MAX_ENTRIES entries are kept (oldest access first out).
+CACHE_MIN_FILES = 2000
+CACHE_MAX_ENTRIES = 32
+
+
+def cache_dir():
+    return os.environ.get("P2S_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "pose2sim_b200")
+
+
+def stat_files(paths_flat, n_threads=0):
+    import ctypes as C
+    from . import _lib
+    arr = (C.c_char_p * len(paths_flat))(*[p.encode() for p in paths_flat])
+    mt, sz = np.empty(len(paths_flat), np.int64), np.empty(len(paths_flat), np.int64)
+    _lib.check(None, _lib.load().p2s_stat_files(C.cast(arr, C.c_void_p), len(paths_flat), mt.ctypes.data, sz.ctypes.data, int(n_threads)))
+    return mt, sz
+
+
+def staging_key(paths, keypoints_ids, nb_persons):
+    import hashlib
+    flat = [p for row in paths for p in row]
+    mt, sz = stat_files(flat)
+    h = hashlib.sha1(b"p2s-staging-v1")
+    h.update("\n".join(flat).encode())
+    h.update(mt.tobytes())
+    h.update(sz.tobytes())
+    h.update(np.asarray(keypoints_ids, np.int64).tobytes())
+    h.update(str((int(nb_persons), len(paths), len(paths[0]) if paths else 0)).encode())
+    return h.hexdigest()
+
+
+def _cache_trim(d):
+    try:
+        entries = sorted((e for e in os.scandir(d) if e.name.endswith(".npy")), key=lambda e: e.stat().st_atime)
+        for e in entries[:max(0, len(entries) - CACHE_MAX_ENTRIES)]:
+            os.remove(e.path)
+    except OSError:
+        pass
+
+
+def _cache_lookup(key):
+    d = cache_dir()
+    os.makedirs(d, exist_ok=True)
+    entry = os.path.join(d, key)
+    try:
+        planes = np.load(entry + ".npy", mmap_mode="r")
+        inexact = int(open(entry + ".txt").read())
+        os.utime(entry + ".npy")
+        return entry, (planes[0], planes[1], planes[2], inexact)
+    except (OSError, ValueError):
+        return entry, None
+
+
+def _cache_store(entry, x, y, lik, inexact):
+    try:
+        tmp = entry + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            np.save(f, np.stack([x, y, lik]))
+        with open(entry + ".txt", "w") as f:
+            f.write(str(inexact))
+        os.replace(tmp, entry + ".npy")
+        _cache_trim(os.path.dirname(entry))
+    except OSError:
+        pass
+
+
+def stage_triangulation_indexed(index, f_range, keypoints_ids, nb_persons):
+    """`stage_triangulation` on a NativeIndex: table, cache signature and parse all in native code.  Returns None when
+    the Python statements must run instead (a listed name without a number: they raise the reference's IndexError)."""
+    if not index.build_table(f_range):
+        return None
+    n_files = index.n_frames * index.n_cams
+    entry = None
+    if os.environ.get("P2S_STAGE_CACHE", "1") != "0" and n_files >= CACHE_MIN_FILES:
+        try:
+            import hashlib
+            key = hashlib.sha1((index.signature() + str((list(keypoints_ids), int(nb_persons)))).encode()).hexdigest()
+            entry, hit = _cache_lookup(key)
+            if hit is not None:
+                return hit
+        except OSError:
+            entry = None
+    x, y, lik, inexact = index.read(keypoints_ids, nb_persons)
+    if entry is not None:
+        _cache_store(entry, x, y, lik, inexact)
+    return x, y, lik, inexact
+
+
 def stage_triangulation(input_dir, cam_dirs, json_files_names, f_range, keypoints_ids, nb_persons):
     """All frames of `extract_files_frame_f` (triangulation.py:607-653) at once, through the native reader.
     Returns x, y, lik float32 [F, N, K, C] (unit-major, camera fastest: the layout `p2s_triangulate_host`
-    takes viewed as [F*N*K, C]) and the number of values float32 could not represent exactly."""
+    takes viewed as [F*N*K, C]) and the number of values float32 could not represent exactly.  Large trials come
+    from / go to the staging cache (above)."""
     table = frame_file_table(json_files_names, f_range)
-    x, y, lik, _, inexact = read_pose_files(frame_paths(input_dir, cam_dirs, table), keypoints_ids, nb_persons)
+    paths = frame_paths(input_dir, cam_dirs, table)
+    n_files = len(paths) * (len(paths[0]) if paths else 0)
+    use_cache = os.environ.get("P2S_STAGE_CACHE", "1") != "0" and n_files >= CACHE_MIN_FILES
+    entry = None
+    if use_cache:
+        try:
+            d = cache_dir()
+            os.makedirs(d, exist_ok=True)
+            entry = os.path.join(d, staging_key(paths, keypoints_ids, nb_persons))
+            planes = np.load(entry + ".npy", mmap_mode="r")
+            inexact = int(open(entry + ".txt").read())
+            os.utime(entry + ".npy")
+            return planes[0], planes[1], planes[2], inexact
+        except (OSError, ValueError):
+            pass
+    x, y, lik, _, inexact = read_pose_files(paths, keypoints_ids, nb_persons)
+    if entry is not None:
+        try:
+            tmp = entry + f".tmp{os.getpid()}"
+            with open(tmp, "wb") as f:
+                np.save(f, np.stack([x, y, lik]))
+            with open(entry + ".txt", "w") as f:
+                f.write(str(inexact))
+            os.replace(tmp, entry + ".npy")
+            _cache_trim(os.path.dirname(entry))
+        except OSError:
+            pass
     return x, y, lik, inexact
 
 

@@ -95,14 +95,22 @@ def stage_project(config_dict, rank=0, world=1):
 
     dirs = _stg.PoseDirs(s["project_dir"])
     cam_dirs = dirs.camera_dirs()
-    input_dir, files = dirs.files_for_triangulation(cam_dirs)
+    index, files = None, None
+    if os.environ.get("P2S_NATIVE_IO", "1") != "0":
+        input_dir, index = dirs.index_for_triangulation(cam_dirs)      # listing, order and frame table in native code
+        counts = index.counts()
+    else:
+        input_dir, files = dirs.files_for_triangulation(cam_dirs)
+        counts = [len(j) for j in files]
     n_cams = len(cam_dirs)
     fr = s["frame_range"]
-    f_range = [0, min(len(j) for j in files)] if fr in ("all", "auto", []) else fr
+    f_range = [0, min(counts)] if fr in ("all", "auto", []) else fr
     if n_cams != len(P):
         raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
                         f"file, and {n_cams} cameras based on the number of pose folders.")
     if s["multi_person"]:
+        if files is None:
+            files = index.names()
         n_persons = _stg.count_persons(input_dir, cam_dirs, [f[rank::world] for f in files])
         if world > 1:
             import torch
@@ -118,7 +126,14 @@ def stage_project(config_dict, rank=0, world=1):
     n_frames = len(range(*f_range))
     b0, b1 = sharding.frame_block(n_frames, rank, world)
     my_range = [f_range[0] + b0, f_range[0] + b1]
-    x, y, lik, inexact = _stg.stage_triangulation(input_dir, cam_dirs, files, my_range, ids, n_persons)
+    staged = _stg.stage_triangulation_indexed(index, my_range, ids, n_persons) if index is not None else None
+    if staged is None:
+        if files is None:
+            files = index.names()
+        staged = _stg.stage_triangulation(input_dir, cam_dirs, files, my_range, ids, n_persons)
+    x, y, lik, inexact = staged
+    if index is not None:
+        index.close()
     st = StagedProject()
     st.settings, st.calib_file, st.P, st.lens = s, calib_file, np.asarray(P, dtype=np.float64), lens
     st.keypoints_ids, st.keypoints_names = ids, names
