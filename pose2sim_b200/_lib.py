@@ -119,6 +119,8 @@ def load():
                           f"or `make -C pose2sim_b200/csrc`; there is no CPU fallback")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if "P2S_LIB" in os.environ and not hasattr(lib, name):
+            continue                                  # an A/B build of an older checkout (tools/kernel_ab.py) may lack new entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

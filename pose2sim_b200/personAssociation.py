@@ -371,6 +371,9 @@ def associate_all(config_dict):
         write_outputs(st, solve_frames(st))
         return
     import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+        import torch
+        torch.cuda.set_device(local)                          # the object collectives below use the current device
     st = stage_project(config_dict, rank, world)
     if st.settings["multi_person"]:
         proposals = solve_frames_multi_person(st, device=local) if len(st.table) else []

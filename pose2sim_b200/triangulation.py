@@ -115,7 +115,7 @@ def stage_project(config_dict, rank=0, world=1):
         if world > 1:
             import torch
             import torch.distributed as dist
-            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))) if dist.get_backend() == "nccl" else "cpu"
             t = torch.tensor([n_persons], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             n_persons = int(t.item())
@@ -251,9 +251,10 @@ def fill_small_gaps(col, index, max_gap, kind):
     if np.count_nonzero(good) <= 4:
         return col
     f = interpolate.interp1d(index[good], col[good], kind=kind, fill_value="extrapolate", bounds_error=False)
-    out = np.where(good, col, f(index))
     bad = np.flatnonzero(~good)
+    out = col.copy()
     if bad.size:
+        out[bad] = f(index[bad])                     # = np.where(good, col, f(index)), evaluated only where it is used
         for seq in np.split(bad, np.flatnonzero(np.diff(index[bad]) > 1) + 1):
             if len(seq) > max_gap:
                 out[seq] = np.nan

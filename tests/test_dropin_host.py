@@ -247,3 +247,39 @@ def test_multi_person_crashes_of_the_reference_are_kept(golden, tmp_path):
         st = tri.stage_project(cfg)
         with pytest.raises(ValueError, match="not enough values to unpack"):
             tri.reidentify(oracle_units(st), st.f_range, st.n_cams, st.settings["max_distance_m"])
+
+
+def test_install_into_reference_runs_under_the_unchanged_orchestrator(golden, tmp_path, monkeypatch):
+    """`install_into_reference()` rebinds `Pose2Sim.triangulation.triangulate_all` /
+    `Pose2Sim.personAssociation.associate_all`, and the UNMODIFIED orchestrator (`Pose2Sim.Pose2Sim.triangulation(config)`,
+    Pose2Sim.py:386-388 -> :241-248, which imports the stage function at call time) then runs this package.  Build
+    container only (needs /root/reference through oracle/ref_shim.py); the device call is replaced by the oracle here
+    because this box has no GPU — what is under test is the hook, not the kernel."""
+    import importlib
+    import logging
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("the reference is only present in the build container")
+    ref = ref_shim.load_reference()
+    import pose2sim_b200
+    orchestrator = importlib.import_module("Pose2Sim.Pose2Sim")
+    original = ref.triangulation.triangulate_all, ref.personAssociation.associate_all
+    calls = []
+    monkeypatch.setattr(tri, "solve_units", lambda st, engine=None, device=0: (calls.append("solve_units"), oracle_units(st))[1])
+    try:
+        pose2sim_b200.install_into_reference()
+        assert ref.triangulation.triangulate_all is pose2sim_b200.triangulate_all
+        assert ref.personAssociation.associate_all is pose2sim_b200.associate_all
+        g = golden("e2e_tri_single.npz")
+        proj, cfg = rebuild_trial(g, tmp_path, "trial_demo")
+        cfg.setdefault("logging", {})["use_custom_logging"] = True          # keep the orchestrator from adding log handlers
+        with in_dir(proj):
+            orchestrator.triangulation(cfg)                                  # the reference's own entry point
+        assert calls == ["solve_units"]                                      # ... reached THIS package's device seam
+        got, want = written_trcs(proj), golden_trcs(g)
+        assert sorted(got) == sorted(want)
+        for name in want:
+            assert_trc_equal(got[name], want[name], tol=1e-6)
+    finally:
+        ref.triangulation.triangulate_all, ref.personAssociation.associate_all = original
+        logging.getLogger().handlers = [h for h in logging.getLogger().handlers if not isinstance(h, logging.FileHandler)]
