@@ -123,9 +123,9 @@ int p2s_set_host_mode(p2s_handle *h, int mode);
  * 0 (default) = automatic, about a quarter of the call's units clamped to [2^16, 2^20] */
 int p2s_set_chunk_units(p2s_handle *h, long long units);
 
-/* association kernel team width: 0 = automatic (a warp per frame when frames are plentiful or small, a
- * 256-thread CTA per frame when the person-combination product is large and frames are few), 1 or 8 to
- * force one of the two (tests, A/B). */
+/* association search: warps that share one frame.  0 (default) = automatic: a warp per frame when frames are plentiful,
+ * a 256-thread CTA per frame when the person-combination product is large and frames are few, a 512-thread CTA per
+ * frame when there are fewer frames than SMs; 1, 8 or 16 force one of the three (tests, A/B). */
 int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame);
 
 /* ---- staging (triangulation.py:817-821 + layout) -------------------------------------------- *

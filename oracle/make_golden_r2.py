@@ -5,9 +5,10 @@
   * tests/golden/assoc_six_persons.npz — the single-person association search at six persons per camera (the person
     count of BASELINE configs[3]) on 4 and 5 cameras (6^4 = 1 296 / 6^5 = 7 776 combination rows per frame), through
     persons_combinations + best_persons_and_cameras_combination (Pose2Sim/personAssociation.py:67, :154-257).
-  * tests/golden/tri_wide_likelihood.npz — triangulation units whose valid likelihoods span 1e-4 ... 1 (a likelihood
-    threshold of 0 is a legal configuration): the reference takes the SVD of A (common.py:347-350), so a formulation
-    through A^T A loses (w_max / w_min)^2 and must switch to a factorisation of A for such units.
+  * tests/golden/tri_wide_likelihood.npz — triangulation units whose valid likelihoods span 1e-4 ... 1 and 1e-6 ... 1
+    (a likelihood threshold of 0 is a legal configuration): the reference takes the SVD of A (common.py:347-350), so a
+    formulation through A^T A loses (w_max / w_min)^2 and must switch to a factorisation of A for such units.
+  * tests/golden/assoc_wide_likelihood.npz — the same for the association search (likelihood_threshold_association 0).
 """
 import contextlib
 import io
@@ -76,6 +77,55 @@ def association_six(ref):
     np.savez_compressed(os.path.join(GOLDEN, "assoc_six_persons.npz"), **out)
 
 
+def association_wide(ref):
+    """Association frames whose detections' likelihoods span up to 1e6 (likelihood threshold 0): the search must solve
+    from a factorisation of A there as well."""
+    import make_golden as mg
+    out = {}
+    kpt, n_kpt_json = 18, 26
+    idx = 0
+    for C, n_p, min_cams, thr, F in [(4, 3, 2, 20.0, 60), (5, 2, 3, 10.0, 40)]:
+        wl = synth.make_association_workload(C, F, n_p, seed=690 + idx, p_out=0.1, p_low=0.0, p_missing=0.1)
+        obs, count, P = wl["obs"].copy(), wl["count"].copy(), wl["P"]
+        g = np.random.default_rng(691 + idx)
+        obs[..., 2] = (10.0 ** g.uniform(-6.0, 0.0, obs.shape[:3])).astype(np.float32)
+        keep = g.random(obs.shape[:3]) < 0.4
+        obs[..., 2] = np.where(keep, g.uniform(0.6, 1.0, obs.shape[:3]), obs[..., 2]).astype(np.float32)
+        cfg = {"personAssociation": {"single_person": {"reproj_error_threshold_association": thr},
+                                     "likelihood_threshold_association": 0.0},
+               "triangulation": {"min_cameras_for_triangulation": min_cams, "undistort_points": False}}
+        errs, combs, Qs = np.empty(F), np.empty((F, C)), np.empty((F, 3))
+        Plist = [P[c] for c in range(C)]
+        with tempfile.TemporaryDirectory() as td:
+            for f in range(F):
+                files = []
+                for c in range(C):
+                    people = []
+                    for p in range(count[f, c]):
+                        kp = np.zeros(n_kpt_json * 3)
+                        kp[0::3] = 100.0 + p
+                        kp[2::3] = 0.9
+                        kp[kpt * 3: kpt * 3 + 3] = obs[f, c, p].astype(np.float64)
+                        people.append({"person_id": [-1], "pose_keypoints_2d": kp.tolist()})
+                    fn = os.path.join(td, f"cam{c}_{f:05d}.json")
+                    with open(fn, "w") as js:
+                        json.dump({"version": 1.3, "people": people}, js)
+                    files.append(fn)
+                rows = ref.personAssociation.persons_combinations(files)
+                with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    e, comb, q = ref.personAssociation.best_persons_and_cameras_combination(cfg, files, rows, Plist, kpt, None)
+                errs[f], combs[f], Qs[f] = e, np.asarray(comb[0], float), np.asarray(q[0], float)[:3]
+        pre = f"assoc{idx}_"
+        out[pre + "P"], out[pre + "obs"], out[pre + "count"] = P, obs, count
+        out[pre + "params"] = np.array([thr, 0.0, min_cams])
+        out[pre + "err"], out[pre + "comb"], out[pre + "Q"] = errs, combs, Qs
+        idx += 1
+        print(f"  wide-likelihood association case {idx}: C={C} persons={n_p} F={F} under thr {np.mean(errs < thr):.2f}", flush=True)
+    out["assoc_n"] = np.array(idx)
+    np.savez_compressed(os.path.join(GOLDEN, "assoc_wide_likelihood.npz"), **out)
+
+
 def wide_likelihood(ref):
     """Likelihoods log-uniform in [1e-4, 1]: no gate (threshold 0), so the weights of one unit span up to 1e4."""
     out = {}
@@ -111,7 +161,11 @@ def wide_likelihood(ref):
 
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
+    if "--assoc-wide-only" in sys.argv:
+        association_wide(ref)
+        sys.exit(0)
     if "--wide-only" not in sys.argv:
         association_six(ref)
+        association_wide(ref)
     if "--assoc-only" not in sys.argv:
         wide_likelihood(ref)

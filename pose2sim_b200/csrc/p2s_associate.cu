@@ -45,11 +45,13 @@ struct AssocArgs {
     int8_t *out_comb;
     double *out_Q;
     uint32_t *out_stats;
-    unsigned int *tile_counter;
+    unsigned int *tile_counter;    // [0] frame dispenser of the main pass, [1] of the wide pass, [2] frames flagged wide
+    uint8_t *wide_flags;           // [n_frames]: 1 = the frame's active likelihoods span more than P2S_WIDE_SPREAD
 };
 
 __host__ __device__ inline size_t assoc_slab_bytes(int cmax, int np) {
-    return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 4 * (size_t)cmax * sizeof(uint32_t);
+    return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 4 * (size_t)cmax * sizeof(uint32_t) +
+           (size_t)(cmax / 2) * 256;          // per camera PAIR: byte of two packed digits -> active / NaN bits of the pair
 }
 
 template <int CMAX>
@@ -100,9 +102,14 @@ __device__ __forceinline__ void team_sync() {
     if (NW == 1) __syncwarp(); else __syncthreads();
 }
 
-template <int CMAX, int NW>
-__global__ void __launch_bounds__(NW == 1 ? 128 : 32 * NW, NW == 1 ? 4 : 2)
+// WIDE = false: the main pass; it FLAGS the frames whose active likelihoods span more than P2S_WIDE_SPREAD (only possible
+// with a likelihood threshold near 0) and leaves them alone.  WIDE = true: the pass behind it, which returns at once when
+// nothing was flagged and otherwise searches the flagged frames with every candidate solved from a factorisation of A
+// itself (Givens QR + one-sided Jacobi, p2s_math.cuh) like the reference's SVD, instead of the normal matrix.
+template <int CMAX, int NW, bool WIDE>
+__global__ void __launch_bounds__(NW == 1 ? 128 : 32 * NW, NW == 1 ? 4 : NW == 8 ? 2 : 1)
 associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
+    if (WIDE && *reinterpret_cast<const volatile unsigned int *>(a.tile_counter + 2) == 0u) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TEAMS = (NW == 1) ? 4 : 1;
     constexpr int TEAM_THREADS = 32 * NW;
@@ -121,6 +128,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     uint32_t *s_ok = s_n + CMAX;
     uint32_t *s_inv = s_ok + CMAX;
     uint32_t *s_nan = s_inv + CMAX;                   // per camera: persons whose x, y or likelihood is NaN
+    // s_pair[j][b]: for the camera pair (2j, 2j + 1) and the byte b = digit(2j) | digit(2j + 1) << 4 of a row's packed
+    // digits: bit 0 / 1 = camera 2j / 2j + 1 active, bit 2 / 3 = its chosen detection holds a NaN (one LDS per pair and row
+    // instead of a shift-and-test chain per camera: that chain was 10 % of the kernel's stall samples)
+    unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_nan + CMAX);
     TeamScratch<NW> &T = *reinterpret_cast<TeamScratch<NW> *>(base + assoc_slab_bytes(CMAX, NP));
 
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
@@ -129,14 +140,15 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     for (;;) {
         unsigned int f = 0;
         if (NW == 1) {
-            if (lane == 0) f = atomicAdd(a.tile_counter, 1u);
+            if (lane == 0) f = atomicAdd(a.tile_counter + (WIDE ? 1 : 0), 1u);
             f = __shfl_sync(P2S_FULL, f, 0);
         } else {
-            if (ttid == 0) T.frame = atomicAdd(a.tile_counter, 1u);
+            if (ttid == 0) T.frame = atomicAdd(a.tile_counter + (WIDE ? 1 : 0), 1u);
             __syncthreads();
             f = T.frame;
         }
         if ((long long)f >= a.n_frames) break;
+        if (WIDE && !a.wide_flags[f]) { team_sync<NW>(); continue; }   // team-uniform; the barrier keeps T.frame's readers ahead of its next writer
 
         // ---- stage the frame, gate the detections, build every detection's block ----------------------
         const float4 *fobs = a.obs + (long long)f * C * NP;
@@ -172,8 +184,43 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             s_nan[ttid] = nanbits;
             const uint32_t nn = n ? (uint32_t)n : 1u;
             s_inv[ttid] = (65536u + nn - 1u) / nn;
+            if (!WIDE) {                                      // smallest / largest active |likelihood| of the camera
+                float wlo = __int_as_float(0x7f800000), whi = 0.f;
+                for (int p = 0; p < n; ++p)
+                    if ((ok >> p) & 1u) {
+                        const float la = fabsf(sobs[ttid * NP + p].z);
+                        wlo = fminf(wlo, la); whi = fmaxf(whi, la);
+                    }
+                reinterpret_cast<float *>(s_pair)[2 * ttid] = wlo;         // s_pair is rebuilt below
+                reinterpret_cast<float *>(s_pair)[2 * ttid + 1] = whi;
+            }
         }
         team_sync<NW>();
+        if (!WIDE) {
+            float wlo = __int_as_float(0x7f800000), whi = 0.f;
+            for (int c = 0; c < C; ++c) {
+                wlo = fminf(wlo, reinterpret_cast<const float *>(s_pair)[2 * c]);
+                whi = fmaxf(whi, reinterpret_cast<const float *>(s_pair)[2 * c + 1]);
+            }
+            const bool wide_frame = whi > P2S_WIDE_SPREAD * wlo;
+            team_sync<NW>();
+            if (wide_frame) {                                 // team-uniform: left to the WIDE pass
+                if (ttid == 0) { a.wide_flags[f] = 1; atomicAdd(a.tile_counter + 2, 1u); }
+                continue;
+            }
+            if (ttid == 0) a.wide_flags[f] = 0;
+        }
+#ifndef P2S_ASSOC_OLD_ACTIVE
+        for (int i = ttid; i < (CMAX / 2) * 256; i += TEAM_THREADS) {
+            const int j = i >> 8, c0 = 2 * j, c1 = c0 + 1;
+            const uint32_t d0 = (uint32_t)i & 15u, d1 = ((uint32_t)i >> 4) & 15u;
+            uint32_t t = 0;
+            if (c0 < C && s_n[c0]) t |= ((s_ok[c0] >> d0) & 1u) | (((s_ok[c0] >> d0) & (s_nan[c0] >> d0) & 1u) << 2);
+            if (c1 < C && s_n[c1]) t |= (((s_ok[c1] >> d1) & 1u) << 1) | (((s_ok[c1] >> d1) & (s_nan[c1] >> d1) & 1u) << 3);
+            s_pair[i] = (unsigned char)t;
+        }
+        team_sync<NW>();
+#endif
         uint32_t present = 0;
         unsigned long long total_rows = 1;
         bool overflow = false;
@@ -207,12 +254,21 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                 const unsigned long long r = rbase + ttid;
                 const bool row_ok = r < total_rows;
                 uint32_t active = 0, nanact = 0;              // nanact: active cameras whose chosen detection holds a NaN
+#ifdef P2S_ASSOC_OLD_ACTIVE                                    /* A/B switch */
 #pragma unroll
                 for (int c = 0; c < CMAX; ++c)
                     if (c < C && s_n[c] && ((s_ok[c] >> digit_of<CMAX>(dig, c)) & 1u)) {
                         active |= 1u << c;
                         nanact |= ((s_nan[c] >> digit_of<CMAX>(dig, c)) & 1u) << c;
                     }
+#else
+#pragma unroll
+                for (int j = 0; j < CMAX / 2; ++j) {
+                    const uint32_t t = s_pair[j * 256 + ((dig[j >> 2] >> ((j & 3) * 8)) & 255u)];
+                    active |= (t & 3u) << (2 * j);
+                    nanact |= ((t >> 2) & 3u) << (2 * j);
+                }
+#endif
                 const int na = __popc(active);
                 unsigned long long rkey = P2S_KEY_EMPTY;
                 double rqx = nan64(), rqy = rqx, rqz = rqx;
@@ -253,7 +309,19 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                                 M.m00 -= v0.x; M.m01 -= v0.y; M.m02 -= v1.x; M.m03 -= v1.y; M.m11 -= v2.x;
                                 M.m12 -= v2.y; M.m13 -= v3.x; M.m22 -= v3.y; M.m23 -= v4.x; M.m33 -= v4.y;
                             }
-                            smallest_eigvec_secular(M, cqx, cqy, cqz);
+                            if (WIDE) {
+                                Tri4 R4;
+                                tri4_zero(R4);
+#pragma unroll 1
+                                for (int c = 0; c < C; ++c) {
+                                    if (!((valid >> c) & 1u)) continue;
+                                    const float4 o = sobs[c * NP + digit_rt(dig, c)];
+                                    givens_add_camera(R4, sP + c * 12, (double)o.x, (double)o.y, (double)o.z);
+                                }
+                                smallest_singvec_jacobi(R4, cqx, cqy, cqz);
+                            } else {
+                                smallest_eigvec_secular(M, cqx, cqy, cqz);
+                            }
                             double sum = 0.0;
 #pragma unroll
                             for (int c = 0; c < CMAX; ++c) {
@@ -290,15 +358,32 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                 if (wh < NW) hit = true;
                 const uint32_t considered = evalmask & upto;
                 if (lane == 0) st_rows += (unsigned)__popc(rowmask & upto);
-                // warp arg-min over (key, lane) among the considered lanes
+                // warp arg-min over (key, lane) among the considered lanes: min of the high words (one redux.sync), the low
+                // words only when several lanes hold it; the lowest lane among the holders is the first row in visiting order
                 unsigned long long ck = ((considered >> lane) & 1u) ? rkey : P2S_KEY_EMPTY;
-                int cl = lane;
+                int cl;
+#ifdef P2S_ASSOC_OLD_ARGMIN                                    /* A/B switch */
+                cl = lane;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
                     const unsigned long long ok2 = __shfl_xor_sync(P2S_FULL, ck, off);
                     const int ol = __shfl_xor_sync(P2S_FULL, cl, off);
                     if (ok2 < ck || (ok2 == ck && ol < cl)) { ck = ok2; cl = ol; }
                 }
+#else
+                {
+                    const uint32_t hi = (uint32_t)(ck >> 32), lo = (uint32_t)ck;
+                    const uint32_t mh = __reduce_min_sync(P2S_FULL, hi);
+                    uint32_t holders = __ballot_sync(P2S_FULL, hi == mh);
+                    uint32_t ml = lo;
+                    if (__popc(holders) > 1) {                 // warp-uniform
+                        ml = __reduce_min_sync(P2S_FULL, hi == mh ? lo : 0xffffffffu);
+                        holders = __ballot_sync(P2S_FULL, hi == mh && lo == ml);
+                    }
+                    cl = __ffs(holders) - 1;
+                    ck = ((unsigned long long)mh << 32) | __shfl_sync(P2S_FULL, ml, cl);
+                }
+#endif
                 if (NW == 1) {
                     if (considered) {
                         // err_last = error of the last evaluated row in visiting order
@@ -383,8 +468,11 @@ static cudaError_t launch_assoc_nw(const AssocLaunch &L, const AssocArgs &a0, in
     constexpr int teams = (NW == 1) ? 4 : 1;
     constexpr int threads = (NW == 1) ? 128 : 32 * NW;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + (assoc_slab_bytes(CMAX, L.max_persons) + sizeof(TeamScratch<NW>)) * teams;
-    auto kern = associate_kernel<CMAX, NW>;
+    auto kern = associate_kernel<CMAX, NW, false>;
+    auto kern_wide = associate_kernel<CMAX, NW, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
@@ -396,6 +484,9 @@ static cudaError_t launch_assoc_nw(const AssocLaunch &L, const AssocArgs &a0, in
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
     kern<<<(unsigned)grid, threads, smem, L.stream>>>(cams, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    kern_wide<<<(unsigned)grid, threads, smem, L.stream>>>(cams, a);       // returns at once unless frames were flagged
     return cudaGetLastError();
 }
 
@@ -403,7 +494,11 @@ static cudaError_t launch_assoc_nw(const AssocLaunch &L, const AssocArgs &a0, in
 // 256-thread CTA per frame.  `mean_rows`: average size of the person-combination product per frame.
 template <int CMAX>
 static cudaError_t launch_assoc(const AssocLaunch &L, const AssocArgs &a0, int *grid_out) {
+    // fewer frames than SMs and many rows per frame (BASELINE configs[3] on a short trial): a 512-thread CTA per frame
+    // puts 16 warps on every busy SM instead of 8
+    const bool wide16 = L.team == 16 || (L.team == 0 && L.mean_rows >= 4096.0 && L.n_frames <= (long long)L.sm_count);
     const bool wide = L.team == 8 || (L.team == 0 && L.mean_rows >= 512.0 && (double)L.n_frames < 16.0 * L.sm_count * 4);
+    if (wide16) return launch_assoc_nw<CMAX, 16>(L, a0, grid_out);
     if (wide) return launch_assoc_nw<CMAX, 8>(L, a0, grid_out);
     return launch_assoc_nw<CMAX, 1>(L, a0, grid_out);
 }
@@ -417,6 +512,7 @@ cudaError_t launch_associate(const AssocLaunch &L, int *grid_out) {
     a.max_table_level = L.max_table_level;
     a.out_err = L.out_err; a.out_comb = L.out_comb; a.out_Q = L.out_Q; a.out_stats = L.out_stats;
     a.tile_counter = L.tile_counter;
+    a.wide_flags = L.wide_flags;
     if (L.n_cams <= 4) return launch_assoc<4>(L, a, grid_out);
     if (L.n_cams <= 8) return launch_assoc<8>(L, a, grid_out);
     if (L.n_cams <= 16) return launch_assoc<16>(L, a, grid_out);

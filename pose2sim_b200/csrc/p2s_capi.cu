@@ -33,7 +33,7 @@ struct DevBuf {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf x, y, lik, obs, Q, err, nexcl, mask, count, comb, astats, rows, aff, iters;
+    DevBuf x, y, lik, obs, Q, err, nexcl, mask, count, comb, astats, rows, aff, iters, wflags;
 };
 
 }  // namespace
@@ -56,6 +56,7 @@ struct p2s_handle {
     int counter_next = 0;
     unsigned long long *d_stats = nullptr;
     double *d_peak = nullptr;
+    DevBuf wflags;                                // association: per-frame wide-likelihood flags of the *_device entry point
 };
 
 namespace {
@@ -196,10 +197,13 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
 
 int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, const double *P, long long n_frames,
                       int n_cams, int max_persons, double thr, double lik_thr, int min_cams,
-                      double *err, int8_t *comb, double *Q, uint32_t *stats, cudaStream_t stream, double mean_rows) {
+                      double *err, int8_t *comb, double *Q, uint32_t *stats, cudaStream_t stream, double mean_rows,
+                      DevBuf *wflags = nullptr) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_frames == 0) return P2S_OK;
+    if (!wflags) wflags = &h->wflags;             // one launch in flight per handle on this path (header: lifetime notes)
+    if ((rc = ensure(h, *wflags, (size_t)n_frames))) return rc;
     p2s::AssocLaunch L;
     L.obs = obs; L.count = count; L.P = P; L.n_frames = n_frames; L.n_cams = n_cams;
     L.max_persons = max_persons; L.min_cams = min_cams; L.sm_count = h->prop.multiProcessorCount;
@@ -212,10 +216,11 @@ int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, cons
     L.max_table_level = t.max_level;
     L.out_err = err; L.out_comb = comb; L.out_Q = Q; L.out_stats = stats;
     L.tile_counter = next_counter(h);
+    L.wide_flags = (uint8_t *)wflags->p;
     L.stream = stream;
-    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, sizeof(unsigned int), stream));
+    P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 4 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_associate(L, &h->last_grid));
-    h->launches += 1;
+    h->launches += 2;                                   // main pass + wide-likelihood pass
     return P2S_OK;
 }
 
@@ -269,13 +274,14 @@ int p2s_destroy(p2s_handle *h) {
     cudaDeviceSynchronize();
     for (auto &t : h->tables) if (t.d_masks) cudaFree(t.d_masks);
     for (auto &s : h->slots) {
-        for (DevBuf *b : {&s.x, &s.y, &s.lik, &s.obs, &s.Q, &s.err, &s.nexcl, &s.mask, &s.count, &s.comb, &s.astats, &s.rows, &s.aff, &s.iters})
+        for (DevBuf *b : {&s.x, &s.y, &s.lik, &s.obs, &s.Q, &s.err, &s.nexcl, &s.mask, &s.count, &s.comb, &s.astats, &s.rows, &s.aff, &s.iters, &s.wflags})
             if (b->p) cudaFree(b->p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_peak) cudaFree(h->d_peak);
+    if (h->wflags.p) cudaFree(h->wflags.p);
     delete h;
     return P2S_OK;
 }
@@ -304,7 +310,7 @@ int p2s_set_band_eps(p2s_handle *h, double eps) {
 }
 
 int p2s_set_assoc_team(p2s_handle *h, int warps_per_frame) {
-    if (!h || (warps_per_frame != 0 && warps_per_frame != 1 && warps_per_frame != 8)) return P2S_EINVAL;
+    if (!h || (warps_per_frame != 0 && warps_per_frame != 1 && warps_per_frame != 8 && warps_per_frame != 16)) return P2S_EINVAL;
     h->assoc_team = warps_per_frame;
     return P2S_OK;
 }
@@ -699,7 +705,7 @@ int p2s_associate_host(p2s_handle *h, const float *obs, const int32_t *count, co
         }
         rc = enqueue_associate(h, s.obs.p, (const int32_t *)s.count.p, P, nf, n_cams, max_persons, reproj_thr, lik_thr,
                                min_cams, (double *)s.err.p, (int8_t *)s.comb.p, (double *)s.Q.p,
-                               out_stats ? (uint32_t *)s.astats.p : nullptr, s.stream, rows / (double)nf);
+                               out_stats ? (uint32_t *)s.astats.p : nullptr, s.stream, rows / (double)nf, &s.wflags);
         if (rc) return rc;
         P2S_CUDA(h, cudaMemcpyAsync(out_err + f0, s.err.p, nf * 8, cudaMemcpyDeviceToHost, s.stream));
         P2S_CUDA(h, cudaMemcpyAsync(out_comb + f0 * C, s.comb.p, nf * C, cudaMemcpyDeviceToHost, s.stream));

@@ -49,7 +49,8 @@ struct AssocLaunch {
     int8_t *out_comb;
     double *out_Q;
     uint32_t *out_stats;
-    unsigned int *tile_counter;
+    unsigned int *tile_counter;   // four words, zeroed on the stream before the launch
+    uint8_t *wide_flags;          // device, n_frames bytes of scratch
     cudaStream_t stream;
 };
 

@@ -137,7 +137,6 @@ struct alignas(16) WarpSlab {     // per-warp shared memory
                                   // unit's valid cameras, from which levels >= 1 subtract the excluded blocks
     unsigned long long r_key[32]; // levels >= 1: error key of the unit's running best candidate of the level ...
     double r_qx[32], r_qy[32], r_qz[32];   // ... and its point, published by the winning lane of a pass
-    unsigned long long r_skey[STATS ? 32 : 2];   // STATS kernels: runner-up key (eps-band statistics of the arg-min)
     unsigned long long st64[8];   // per-warp statistics: candidates, camera-solves, solver steps, solved,
                                   // direct cameras, blocks, entry additions
     uint32_t st32[12];            // level histogram [0..7], failed, not evaluated, threshold band, arg-min band
@@ -548,9 +547,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         }
         __syncwarp();
 
-        // ---- levels k >= 1: lanes enumerate subsets, W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units per pass,
-        // ONE candidate per lane and pass (levels with more than W candidates take several passes over the unit; the
-        // pass winner replaces the unit's running best in its slot on a strict '<', so the first index still wins)
+        // ---- levels k >= 1: lanes enumerate subsets, W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units per pass
         for (int k = 1; k < C; ++k) {
             const bool pend = active && !wide && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
                               !(min(C, ninv0 + k) > C - a.min_cams);
@@ -560,7 +557,6 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             if (pend) {
                 S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
                 S.r_key[lane] = P2S_KEY_EMPTY;
-                if (STATS) S.r_skey[lane] = P2S_KEY_EMPTY;
             }
             const uint32_t ncand = a.ncand[k];
             const int lw = a.lw[k];                          // W = 2^lw lanes per unit (host table), W >= C
@@ -601,93 +597,86 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 }
                 __syncwarp();
 
-                for (uint32_t cbase = 0; cbase < ncand; cbase += (uint32_t)W) {
-                    const uint32_t cand = cbase + (uint32_t)sub;
-                    const bool live = on && cand < ncand;
-                    unsigned long long key = P2S_KEY_EMPTY;
-                    uint32_t cm = 0;
+                // a lane walks candidates sub, sub + W, ... and keeps its own best (first = smallest index among equal keys);
+                // levels with at most W candidates — the common ones — run the body once
+                unsigned long long bkey = P2S_KEY_EMPTY, bskey = P2S_KEY_EMPTY;
+                uint32_t bcand = 0xffffffffu, bcm = 0;
+                double bqx, bqy, bqz;
+                for (uint32_t cand = (uint32_t)sub; on && cand < ncand; cand += (uint32_t)W) {
+                    const uint32_t cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
+                    const uint32_t valid = cmask & ~(u_inv0 | cm);
+                    const int m = __popc(valid);
                     double cqx = nan64(), cqy = cqx, cqz = cqx;
-                    if (live) {
-                        cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
-                        const uint32_t valid = cmask & ~(u_inv0 | cm);
-                        const int m = __popc(valid);
-                        double e = inf64();                  // m < 2: common.py:351, :394-396 / mean of an empty list,
-                        if (m >= 2) {                        // both ordered as +inf
-                            Sym4 M;
-                            uint32_t bits;
-                            double sgn;
-                            if (subtract) {
-                                M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
-                                M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
-                                bits = cm & ~u_inv0 & cmask;
-                                sgn = -1.0;
-                            } else {
-                                sym4_zero(M);
-                                bits = valid;
-                                sgn = 1.0;
-                            }
-                            if (STATS) t_adds += 10u * (uint32_t)__popc(bits);
-                            while (bits) {                    // ascending camera order
-                                const int c = __ffs(bits) - 1;
-                                bits &= bits - 1;
-                                const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
-                                const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                                M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
-                                M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
-                                M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
-                                M.m33 = fma(sgn, v4.y, M.m33);
-                            }
-                            int it;
-                            if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
-                            else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
-                            e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
-                            if (STATS) { t_iters += (uint32_t)it; t_solved += 1u; }
+                    double e = inf64();                      // m < 2: common.py:351, :394-396 / mean of an empty list,
+                    if (m >= 2) {                            // both ordered as +inf
+                        Sym4 M;
+                        uint32_t bits;
+                        double sgn;
+                        if (subtract) {
+                            M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
+                            M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
+                            bits = cm & ~u_inv0 & cmask;
+                            sgn = -1.0;
+                        } else {
+                            sym4_zero(M);
+                            bits = valid;
+                            sgn = 1.0;
                         }
-                        if (STATS) { t_cands += 1u; t_cams += (uint32_t)m; }
-                        key = err_key_inf(e);
+                        if (STATS) t_adds += 10u * (uint32_t)__popc(bits);
+                        while (bits) {                        // ascending camera order
+                            const int c = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
+                            const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                            M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
+                            M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
+                            M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
+                            M.m33 = fma(sgn, v4.y, M.m33);
+                        }
+                        int it;
+                        if (SOLVER == 0) it = smallest_eigvec_secular(M, cqx, cqy, cqz);
+                        else it = smallest_eigvec_jacobi(M, cqx, cqy, cqz);
+                        e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
+                        if (STATS) { t_iters += (uint32_t)it; t_solved += 1u; }
                     }
-                    // ---- arg-min of the pass across the W lanes of the group: keys are 64-bit — min of the high words (ONE
-                    // redux.sync), then, only if several lanes hold it (duplicates, all-inf levels, errors closer than 2^-20
-                    // relative), min of the low words among them; candidates ascend with the lane, so the lowest lane among
-                    // the holders of the minimum is np.nanargmin's first index
-                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                    const uint32_t mh = group_min(hi, W, gmask);
-                    uint32_t holders = __ballot_sync(P2S_FULL, live && hi == mh) & gmask;
-                    uint32_t ml = lo;
-                    if (__any_sync(P2S_FULL, STATS || __popc(holders) > 1)) {
-                        ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
-                        holders = __ballot_sync(P2S_FULL, live && hi == mh && lo == ml) & gmask;
+                    if (STATS) { t_cands += 1u; t_cams += (uint32_t)m; }
+                    const unsigned long long key = err_key_inf(e);
+                    if (key < bkey) {                           // ascending cand per lane: strict < keeps the first
+                        if (STATS) bskey = bkey;
+                        bkey = key; bcand = cand; bcm = cm;
+                        bqx = cqx; bqy = cqy; bqz = cqz;
+                    } else if (STATS && key > bkey && key < bskey) {
+                        bskey = key;
                     }
-                    const bool winner = holders != 0u && lane == __ffs(holders) - 1;
-                    unsigned long long pskey = P2S_KEY_EMPTY;  // STATS: the pass's smallest key strictly above its minimum
+                }
+                // ---- arg-min across the W lanes of the group: keys are 64-bit — min of the high words (ONE redux.sync),
+                // then, only if several lanes hold it (duplicates, all-inf levels, errors closer than 2^-20 relative), min of
+                // the low words among them and the smallest candidate index among those (np.nanargmin's first index)
+                const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
+                const uint32_t mh = group_min(hi, W, gmask);
+                const bool have = bcand != 0xffffffffu;
+                uint32_t holders = __ballot_sync(P2S_FULL, have && hi == mh) & gmask;
+                bool winner = holders != 0u && lane == __ffs(holders) - 1;
+                bool barg = false;
+                if (__any_sync(P2S_FULL, STATS || __popc(holders) > 1)) {
+                    const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
+                    const bool is_min = have && hi == mh && lo == ml;
+                    const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);
+                    winner = is_min && bcand == mc;
                     if (STATS) {
-                        const bool is_min = live && hi == mh && lo == ml;
-                        const unsigned long long rk = is_min ? P2S_KEY_EMPTY : key;
+                        // runner-up: smallest key strictly above the minimum (duplicates of the winner are bitwise equal)
+                        const unsigned long long rk = is_min ? bskey : bkey;
                         const uint32_t rh = (uint32_t)(rk >> 32), rl = (uint32_t)rk;
                         const uint32_t sh = group_min(rh, W, gmask);
                         const uint32_t sl = group_min(rh == sh ? rl : 0xffffffffu, W, gmask);
-                        pskey = ((unsigned long long)sh << 32) | sl;
+                        barg = (key_err(((unsigned long long)sh << 32) | sl) - key_err(bkey)) < a.band_eps;   // NaN / inf compare false
                     }
-                    if (winner) {
-                        const unsigned long long old = S.r_key[ul];
-                        if (STATS) {
-                            // runner-up of the level so far: smallest of {old best, old runner-up, pass best, pass runner-up}
-                            // strictly above the new best (equal keys are duplicates of the winner)
-                            const unsigned long long nb = key < old ? key : old;
-                            unsigned long long sk = P2S_KEY_EMPTY;
-                            const unsigned long long cs[4] = {old, S.r_skey[ul], key, pskey};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) if (cs[j] > nb && cs[j] < sk) sk = cs[j];
-                            S.r_skey[ul] = sk;
-                        }
-                        if (key < old) {                       // strict '<': an earlier pass (smaller indices) keeps a tie
-                            S.r_key[ul] = key;
-                            S.r_qx[ul] = cqx; S.r_qy[ul] = cqy; S.r_qz[ul] = cqz;
-                            S.r_nan[ul] = u_nan0 | cm;
-                            S.r_flags[ul] = (uint32_t)__popc(u_inv0 | cm);
-                        }
-                    }
-                    __syncwarp();
+                }
+                if (winner) {
+                    S.r_key[ul] = bkey;
+                    S.r_qx[ul] = bqx; S.r_qy[ul] = bqy; S.r_qz[ul] = bqz;
+                    S.r_nan[ul] = u_nan0 | bcm;
+                    S.r_flags[ul] = (uint32_t)__popc(u_inv0 | bcm) | (barg ? 0x100u : 0u);
                 }
             }
             __syncwarp();
@@ -696,8 +685,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
                 err_min = key_err(bk);
                 qx = S.r_qx[lane]; qy = S.r_qy[lane]; qz = S.r_qz[lane];
                 ids = S.r_nan[lane];
-                nexcl = S.r_flags[lane];
-                if (STATS) band_arg |= (key_err(S.r_skey[lane]) - err_min) < a.band_eps;   // NaN / inf compare false
+                nexcl = S.r_flags[lane] & 0xffu;
+                if (STATS) band_arg |= (S.r_flags[lane] & 0x100u) != 0u;
                 band_thr |= fabs(err_min - a.thr) < a.band_eps;
                 last_level = k;
             }
@@ -1096,7 +1085,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.bulk_out = (a.vec_out && L.bulk_out) ? 1 : 0;
     a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
     a.err_word = L.err_word;
-    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, true>) * 4;      // STATS slab; the lean one is 240 B smaller per warp
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, true>) * 4;
     const size_t smem_lean = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, false>) * 4;
     if constexpr (!FULLSET) {
         LensSet<1> none;

@@ -119,6 +119,17 @@ def test_six_person_association_frames(golden):
         assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
 
 
+def test_wide_likelihood_association_frames(golden):
+    import c_oracle as co
+    g = golden("assoc_wide_likelihood.npz")
+    for i in range(int(g["assoc_n"])):
+        p = f"assoc{i}_"
+        thr, lt, mc = g[p + "params"]
+        e, comb, Q = co.associate_frames(g[p + "obs"], g[p + "count"], g[p + "P"], float(thr), float(lt), int(mc))
+        assert np.array_equal(comb.astype(int), np.nan_to_num(g[p + "comb"], nan=-1).astype(int)), i
+        assert np.allclose(Q, g[p + "Q"], atol=Q_TOL, rtol=0, equal_nan=True)
+
+
 def test_subset_order_is_itertools():
     """The kernel's candidate tables must follow itertools.combinations order (triangulation.py:411)."""
     import itertools
