@@ -794,6 +794,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         if (lane == 0) bulk_wait_all();
         __syncwarp();
     }
+    // the kernel behind this one (wide_fixup_kernel) may be scheduled onto the SMs as the CTAs of this one retire
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---- second kernel of every launch: wide-spread units + the push path's arrival flag ---------------------------
@@ -827,6 +829,9 @@ __global__ void __launch_bounds__(128) wide_fixup_kernel(const CamParams<P2S_MAX
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = a.n_cams;
+    // launched with programmatic stream serialisation: the grid may be scheduled while the search kernel drains; nothing of
+    // that kernel is read before it has completed and its writes are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool any = *reinterpret_cast<const volatile unsigned int *>(a.tile_counter + 2) != 0u;
     if (any) {
         double *sP = reinterpret_cast<double *>(smem_raw);
@@ -1128,6 +1133,22 @@ static cudaError_t launch_main(const TriLaunch &L, int *grid_out) {
     return launch_tri<32, true>(L, grid_out);
 }
 
+// Programmatic dependent launch (sm_90+): the kernel's CTAs may be scheduled while the previous kernel of the stream is
+// still draining; it orders itself behind that kernel with griddepcontrol.wait.  Hides the ~3 us launch gap of the
+// second kernel of every step (P2S_NO_PDL: plain launch, A/B).
+template <class Kern, class... Args>
+static cudaError_t launch_dependent(Kern kern, unsigned grid, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+#ifndef P2S_NO_PDL
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#endif
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 256
 // rules wide units out rests on likelihoods being <= 1, which is a convention of pose estimators, not a contract of this
 // interface; an empty launch costs ~2 us behind the search kernel and keeps the accuracy guarantee unconditional.
@@ -1167,16 +1188,15 @@ static cudaError_t launch_fixup(const TriLaunch &L, int main_grid) {
         const size_t smem = P2S_MAX_CAMS * 12 * sizeof(double) + sizeof(LensSet<P2S_MAX_CAMS>) + slab;
         cudaError_t e = cudaFuncSetAttribute(wide_fixup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        wide_fixup_kernel<true><<<(unsigned)grid, 128, smem, L.stream>>>(cams, lens, a);
+        return launch_dependent(wide_fixup_kernel<true>, (unsigned)grid, smem, L.stream, cams, lens, a);
     } else {
         LensSet<1> none;
         std::memset(&none, 0, sizeof none);
         const size_t smem = P2S_MAX_CAMS * 12 * sizeof(double) + slab;
         cudaError_t e = cudaFuncSetAttribute(wide_fixup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        wide_fixup_kernel<false><<<(unsigned)grid, 128, smem, L.stream>>>(cams, none, a);
+        return launch_dependent(wide_fixup_kernel<false>, (unsigned)grid, smem, L.stream, cams, none, a);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
