@@ -309,6 +309,8 @@ long long p2s_index_file_count(const p2s_dir_index *ix, int cam);
 const char *p2s_index_file_name(const p2s_dir_index *ix, int cam, long long i);
 int p2s_index_build_table(p2s_dir_index *ix, long long f0, long long f1);
 const char *const *p2s_index_table_paths(const p2s_dir_index *ix);
+/* the same table as one buffer: the n_frames x n_cams paths back to back, each NUL-terminated ("" = none); *len = bytes */
+const char *p2s_index_table_arena(const p2s_dir_index *ix, long long *len);
 int p2s_index_signature(const p2s_dir_index *ix, unsigned long long sig[2], int n_threads);
 
 /* (mtime in ns, size in bytes) of n files, -1 / -1 where stat fails: the signature the staging cache is keyed on

@@ -94,6 +94,7 @@ SIGNATURES = {
     "p2s_index_file_name": (C.c_char_p, [_vp, _i, _ll]),
     "p2s_index_build_table": (_i, [_vp, _ll, _ll]),
     "p2s_index_table_paths": (_vp, [_vp]),
+    "p2s_index_table_arena": (_vp, [_vp, _vp]),
     "p2s_index_signature": (_i, [_vp, _vp, _i]),
     "p2s_stat_files": (_i, [_vp, _ll, _vp, _vp, _i]),
     "p2s_read_people_files": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),

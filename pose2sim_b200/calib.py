@@ -36,8 +36,23 @@ def rodrigues(rvec):
     return c * np.eye(3) + (1.0 - c) * np.outer(k, k) + s * Kx
 
 
+_PARSED = {}          # (path, mtime_ns, size) -> parsed TOML: one run reads the same file for P, the lens models and the recap
+
+
 def load_calibration(calib_file):
-    calib = _load(calib_file)
+    """The parsed calibration TOML (read-only for the callers) and its camera tables in file order."""
+    try:
+        st = os.stat(calib_file)
+        key = (os.path.abspath(calib_file), st.st_mtime_ns, st.st_size)
+    except OSError:
+        key = None
+    calib = _PARSED.get(key) if key is not None else None
+    if calib is None:
+        calib = _load(calib_file)
+        if key is not None:
+            if len(_PARSED) >= 16:
+                _PARSED.clear()
+            _PARSED[key] = calib
     keys = [k for k, v in calib.items() if k not in _NOT_CAMERAS and isinstance(v, dict)]
     return calib, keys
 

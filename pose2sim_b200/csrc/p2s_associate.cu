@@ -107,7 +107,13 @@ __device__ __forceinline__ void team_sync() {
 // nothing was flagged and otherwise searches the flagged frames with every candidate solved from a factorisation of A
 // itself (Givens QR + one-sided Jacobi, p2s_math.cuh) like the reference's SVD, instead of the normal matrix.
 template <int CMAX, int NW, bool WIDE>
-__global__ void __launch_bounds__(NW == 1 ? 128 : 32 * NW, NW == 1 ? 4 : NW == 8 ? 2 : 1)
+#ifndef P2S_ASSOC_MIN_BLOCKS
+#define P2S_ASSOC_MIN_BLOCKS 4      /* resident 4-warp CTAs per SM of the warp-per-frame variant (A/B: tools/kernel_ab.py) */
+#endif
+#ifndef P2S_ASSOC_MIN_BLOCKS8
+#define P2S_ASSOC_MIN_BLOCKS8 2     /* resident 8-warp CTAs per SM of the CTA-per-frame variant */
+#endif
+__global__ void __launch_bounds__(NW == 1 ? 128 : 32 * NW, NW == 1 ? P2S_ASSOC_MIN_BLOCKS : NW == 8 ? P2S_ASSOC_MIN_BLOCKS8 : 1)
 associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     if (WIDE && *reinterpret_cast<const volatile unsigned int *>(a.tile_counter + 2) == 0u) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -26,6 +26,8 @@
 
 #include <algorithm>
 #include <dirent.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <new>
 #include <sys/stat.h>
 
@@ -354,8 +356,10 @@ struct p2s_dir_index {
     struct Entry { std::string name; bool has_num; std::string digits; long long num; };   // digits: last run, no leading zeros
     std::vector<std::string> dirs;
     std::vector<std::vector<Entry>> cams;
-    std::vector<std::string> table_store;      // absolute paths of the table, "" = none
-    std::vector<const char *> table;           // [F][C]
+    std::string table_arena;                   // the table's paths back to back, NUL-terminated ("" = none)
+    std::vector<size_t> table_off;             // [F][C] offsets into the arena
+    std::vector<const char *> table;           // [F][C] pointers into the arena
+    std::vector<const char *> table_name;      // [F][C] the file name alone (entry of camera c's folder), null = none
 };
 
 namespace {
@@ -435,9 +439,17 @@ extern "C" int p2s_index_build_table(p2s_dir_index *ix, long long f0, long long 
     for (const auto &v : ix->cams) for (const auto &e : v) if (!e.has_num) return P2S_EINVAL;
     // per camera: files are sorted by number, so the files of frame f are a contiguous run found by a merge walk
     std::vector<size_t> pos(C, 0);
-    ix->table_store.clear();
-    ix->table_store.reserve((size_t)F * C);
-    std::vector<std::string> flat;
+    ix->table_arena.clear();
+    ix->table_off.clear();
+    ix->table_name.clear();
+    size_t longest = 0;
+    for (const auto &v : ix->cams) for (const auto &e : v) longest = std::max(longest, e.name.size());
+    size_t dirlen = 0;
+    for (const auto &d : ix->dirs) dirlen = std::max(dirlen, d.size());
+    ix->table_arena.reserve((size_t)F * C * (dirlen + longest + 2));
+    ix->table_off.reserve((size_t)F * C);
+    ix->table_name.reserve((size_t)F * C);
+    std::vector<const p2s_dir_index::Entry *> flat;
     for (long long f = f0; f < f1; ++f) {
         flat.clear();
         for (size_t c = 0; c < C; ++c) {
@@ -451,19 +463,34 @@ extern "C" int p2s_index_build_table(p2s_dir_index *ix, long long f0, long long 
             while (p < v.size() && v[p].num >= 0 && v[p].num < f) ++p;
             size_t q = p;
             bool any = false;
-            while (q < v.size() && v[q].num == f) { flat.push_back(v[q].name); ++q; any = true; }
-            if (!any) flat.emplace_back();
+            while (q < v.size() && v[q].num == f) { flat.push_back(&v[q]); ++q; any = true; }
+            if (!any) flat.push_back(nullptr);
         }
         // the NAME at flattened position c is joined with camera c's folder (triangulation.py:801-803): after a camera
         // with two files for the frame the later names land in the wrong folder and read as missing, like in the reference
-        for (size_t c = 0; c < C; ++c) ix->table_store.push_back(flat[c].empty() ? std::string() : ix->dirs[c] + "/" + flat[c]);
+        for (size_t c = 0; c < C; ++c) {
+            ix->table_off.push_back(ix->table_arena.size());
+            if (flat[c]) {
+                ix->table_arena.append(ix->dirs[c]);
+                ix->table_arena.push_back('/');
+                ix->table_arena.append(flat[c]->name);
+                ix->table_name.push_back(flat[c]->name.c_str());
+            } else {
+                ix->table_name.push_back(nullptr);
+            }
+            ix->table_arena.push_back('\0');
+        }
     }
-    ix->table.resize(ix->table_store.size());
-    for (size_t i = 0; i < ix->table_store.size(); ++i) ix->table[i] = ix->table_store[i].c_str();
+    ix->table.resize(ix->table_off.size());
+    for (size_t i = 0; i < ix->table_off.size(); ++i) ix->table[i] = ix->table_arena.data() + ix->table_off[i];
     return P2S_OK;
 }
 
 extern "C" const char *const *p2s_index_table_paths(const p2s_dir_index *ix) { return ix ? ix->table.data() : nullptr; }
+extern "C" const char *p2s_index_table_arena(const p2s_dir_index *ix, long long *len) {
+    if (len) *len = ix ? (long long)ix->table_arena.size() : 0;
+    return ix ? ix->table_arena.data() : nullptr;
+}
 
 // ---- file signatures for the staging cache: (mtime in ns, size) per path, -1 / -1 when the file cannot be stat'ed ----
 extern "C" int p2s_stat_files(const char *const *paths, long long n, long long *mtime_ns, long long *size, int n_threads) {
@@ -495,27 +522,65 @@ extern "C" int p2s_stat_files(const char *const *paths, long long n, long long *
     return P2S_OK;
 }
 
-// 128-bit digest of (path, mtime, size) of every table entry: the staging cache key without 40 k Python strings
+// 128-bit digest of (path, mtime, size) of every table entry: the staging cache key without 40 k Python strings.
+// The stat pass runs on all cores with fstatat() relative to each camera folder's descriptor (no walk of the absolute
+// path per file); the digest is mixed per 8-byte word.
 extern "C" int p2s_index_signature(const p2s_dir_index *ix, unsigned long long sig[2], int n_threads) {
     if (!ix || !sig) return P2S_EINVAL;
     const long long n = (long long)ix->table.size();
+    const size_t C = ix->cams.size();
     std::vector<long long> mt((size_t)n), sz((size_t)n);
     if (n > 0) {
-        const int rc = p2s_stat_files(ix->table.data(), n, mt.data(), sz.data(), n_threads);
-        if (rc) return rc;
+        std::vector<int> dfd(C, -1);
+        for (size_t c = 0; c < C; ++c) dfd[c] = ::open(ix->dirs[c].c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+        if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+        if (n_threads < 1) n_threads = 1;
+        if ((long long)n_threads > (n + 255) / 256) n_threads = (int)((n + 255) / 256);
+        std::atomic<long long> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const long long i0 = next.fetch_add(256);
+                if (i0 >= n) break;
+                const long long i1 = i0 + 256 < n ? i0 + 256 : n;
+                for (long long i = i0; i < i1; ++i) {
+                    struct stat st;
+                    const size_t c = (size_t)i % C;
+                    const char *nm = ix->table_name[(size_t)i];
+                    int rc = -1;
+                    if (nm) rc = dfd[c] >= 0 ? ::fstatat(dfd[c], nm, &st, 0) : ::stat(ix->table[(size_t)i], &st);
+                    if (rc == 0) {
+                        mt[(size_t)i] = (long long)st.st_mtim.tv_sec * 1000000000LL + (long long)st.st_mtim.tv_nsec;
+                        sz[(size_t)i] = (long long)st.st_size;
+                    } else {
+                        mt[(size_t)i] = sz[(size_t)i] = -1;
+                    }
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        for (size_t c = 0; c < C; ++c) if (dfd[c] >= 0) ::close(dfd[c]);
     }
     unsigned long long h0 = 1469598103934665603ULL, h1 = 0x9e3779b97f4a7c15ULL;
+    auto mix64 = [&](unsigned long long w) {
+        h0 = (h0 ^ w) * 1099511628211ULL; h0 ^= h0 >> 29;
+        h1 = (h1 + w + (h1 << 6) + (h1 >> 2)) * 0xff51afd7ed558ccdULL; h1 ^= h1 >> 32;
+    };
     auto mix = [&](const void *p, size_t len) {
         const unsigned char *b = (const unsigned char *)p;
-        for (size_t i = 0; i < len; ++i) {
-            h0 = (h0 ^ b[i]) * 1099511628211ULL;
-            h1 = (h1 + b[i] + (h1 << 6) + (h1 >> 2)) * 0xff51afd7ed558ccdULL;
-        }
+        size_t i = 0;
+        for (; i + 8 <= len; i += 8) { unsigned long long w; std::memcpy(&w, b + i, 8); mix64(w); }
+        unsigned long long w = 0x80ULL << 56;
+        if (i < len) std::memcpy(&w, b + i, len - i);
+        mix64(w ^ (unsigned long long)len);
     };
     for (long long i = 0; i < n; ++i) {
-        mix(ix->table_store[(size_t)i].data(), ix->table_store[(size_t)i].size() + 1);
-        mix(&mt[(size_t)i], sizeof(long long));
-        mix(&sz[(size_t)i], sizeof(long long));
+        const char *p = ix->table[(size_t)i];
+        mix(p, std::strlen(p) + 1);
+        mix64((unsigned long long)mt[(size_t)i]);
+        mix64((unsigned long long)sz[(size_t)i]);
     }
     sig[0] = h0; sig[1] = h1;
     return P2S_OK;

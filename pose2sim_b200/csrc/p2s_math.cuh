@@ -110,15 +110,70 @@ __device__ __forceinline__ void accumulate_camera(Sym4 &M, const double *Pc, dou
 #ifndef P2S_SOLVER_MAX_ITERS
 #define P2S_SOLVER_MAX_ITERS 100
 #endif
-__device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
-    double lam = 0.0, lo = 0.0;
-    double x0 = nan64(), x1 = x0, x2 = x0;
-    int it = 0;
-#ifndef P2S_SOLVER_UNROLL
-#define P2S_SOLVER_UNROLL 1
+#ifndef P2S_DONE_TOL
+#define P2S_DONE_TOL 1e-6        /* the first-order final update leaves O(tol^2) = 1e-12 relative in q; A/B: 1e-8 costs 5 % */
 #endif
-    constexpr int kUnroll = P2S_SOLVER_UNROLL;                 // A/B switch (tools/kernel_ab.py); 1 = rolled
-#pragma unroll kUnroll
+
+// What the first factorisation (lam = 0) yields beyond the iterate, for the branch-and-bound of the exclusion search:
+//   s   = c - b^T A^-1 b = min over q of (q,1)^T M (q,1)  (the inhomogeneous least-squares minimum: q0 = -A^-1 b attains it),
+//         so (q,1)^T M (q,1) >= s for EVERY q, in particular for the eigenvector-derived point the solver ends at;
+//   g   = 1 + |q0|^2, s / g = the Rayleigh quotient of (q0, 1) >= the smallest eigenvalue lam*;
+//   tau = trace(A^-1) >= 1 / (smallest eigenvalue of A), from the LDL^T factors at hand.
+struct SecularBound { double s, g, tau; };
+
+// Iteration 0 of the safeguarded Newton iteration (lam = 0, lo = 0), including the chord step.
+// Returns 0: to be continued by secular_rest(M, lam, ...) — x holds q(lam = 0) + dl w;  1: finished, x final;
+//         2: A is not positive definite (or NaN input): x = NaN, like the reference's NaN SVD.
+__device__ __forceinline__ int secular_first(const Sym4 &M, double &lam, double &x0, double &x1, double &x2, SecularBound &B) {
+    const double a00 = M.m00, a11 = M.m11, a22 = M.m22;
+    const double r0 = rcp_fast(a00);
+    const double l10 = M.m01 * r0, l20 = M.m02 * r0;
+    const double d1 = fma(-l10, M.m01, a11), t21 = fma(-l20, M.m01, M.m12);
+    const double r1 = rcp_fast(d1);
+    const double l21 = t21 * r1;
+    const double d2 = fma(-l21, t21, fma(-l20, M.m02, a22));
+    lam = 0.0;
+    if (!(a00 > 0.0 && d1 > 0.0 && d2 > 0.0)) {
+        x0 = x1 = x2 = nan64();
+        B.s = B.g = B.tau = nan64();
+        return 2;
+    }
+    const double r2 = rcp_fast(d2);
+    double z0 = -M.m03;
+    double z1 = fma(-l10, z0, -M.m13);
+    double z2 = fma(-l21, z1, fma(-l20, z0, -M.m23));
+    x2 = z2 * r2;
+    x1 = fma(-l21, x2, z1 * r1);
+    x0 = fma(-l20, x2, fma(-l10, x1, z0 * r0));
+    const double f = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33)));
+    const double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
+    const double dl = f * rcp_fast(g);
+    {   // trace(A^-1) = sum_k r_k |row k of L^-1|^2,  L^-1 = [[1,0,0],[-l10,1,0],[l10 l21 - l20, -l21, 1]]
+        const double t = fma(l10, l21, -l20);
+        B.tau = fma(r2, fma(t, t, fma(l21, l21, 1.0)), fma(r1, fma(l10, l10, 1.0), r0));
+        B.s = f; B.g = g;
+    }
+    const double y1 = fma(-l10, x0, x1);
+    const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
+    const double w2 = y2 * r2;
+    const double w1 = fma(-l21, w2, y1 * r1);
+    const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
+    const bool done = fabs(dl) * (r0 + r1 + r2) <= P2S_DONE_TOL;
+    x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);      // q(lam + dl), first order
+    if (done) return 1;
+    // chord step: Rayleigh quotient of (q~, 1)
+    const double f1 = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - dl)));
+    const double g1 = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
+    const double qw = fma(x0, w0, fma(x1, w1, x2 * w2));
+    lam = dl + fma(-dl * dl, qw, f1) * rcp_fast(g1);
+    return 0;
+}
+
+// Iterations 1.. of the same iteration (lo = 0 after iteration 0).  Returns the number of factorisations used in total.
+__device__ __forceinline__ int secular_rest(const Sym4 &M, double lam, double &x0, double &x1, double &x2) {
+    double lo = 0.0;
+    int it = 1;
+#pragma unroll 1
     for (; it < P2S_SOLVER_MAX_ITERS; ++it) {
         const double a00 = M.m00 - lam, a11 = M.m11 - lam, a22 = M.m22 - lam;
         const double r0 = rcp_fast(a00);
@@ -127,8 +182,8 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
         const double r1 = rcp_fast(d1);
         const double l21 = t21 * r1;
         const double d2 = fma(-l21, t21, fma(-l20, M.m02, a22));
-        if (!(a00 > 0.0 && d1 > 0.0 && d2 > 0.0)) {          // right of the pole (or NaN input)
-            if (!(lam > lo)) break;                          // not even positive definite at lo: give up (NaN)
+        if (!(a00 > 0.0 && d1 > 0.0 && d2 > 0.0)) {          // right of the pole
+            if (!(lam > lo)) break;                          // not even positive definite at lo: give up
             lam = 0.5 * (lam + lo);
             continue;
         }
@@ -143,35 +198,30 @@ __device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx
         const double g = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
         const double dl = f * rcp_fast(g);
         if (f > 0.0) lo = lam;
-        // w = (A - lam I)^-1 q from the factors at hand
-        const double y1 = fma(-l10, x0, x1);
-        const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
-        const double w2 = y2 * r2;
-        const double w1 = fma(-l21, w2, y1 * r1);
-        const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
-#ifndef P2S_DONE_TOL
-#define P2S_DONE_TOL 1e-6        /* the first-order update below leaves O(tol^2) = 1e-12 relative in q; A/B: 1e-8 costs 5 % */
-#endif
         const bool done = fabs(dl) * (r0 + r1 + r2) <= P2S_DONE_TOL;
-#ifdef P2S_NO_CHORD                                         /* A/B switch, tools/kernel_ab.py */
         if (done) {
-#else
-        if (done || it == 0) {
-#endif
-            x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);      // q(lam + dl), first order
-            if (done) { ++it; break; }
-            // chord step: Rayleigh quotient of (q~, 1)
-            const double lam1 = lam + dl;
-            const double f1 = fma(M.m03, x0, fma(M.m13, x1, fma(M.m23, x2, M.m33 - lam1)));
-            const double g1 = fma(x0, x0, fma(x1, x1, fma(x2, x2, 1.0)));
-            const double qw = fma(x0, w0, fma(x1, w1, x2 * w2));
-            lam = lam1 + fma(-dl * dl, qw, f1) * rcp_fast(g1);
-            continue;
+            // w = (A - lam I)^-1 q from the factors at hand; q(lam + dl) = q + dl w, first order
+            const double y1 = fma(-l10, x0, x1);
+            const double y2 = fma(-l21, y1, fma(-l20, x0, x2));
+            const double w2 = y2 * r2;
+            const double w1 = fma(-l21, w2, y1 * r1);
+            const double w0 = fma(-l20, w2, fma(-l10, w1, x0 * r0));
+            x0 = fma(dl, w0, x0); x1 = fma(dl, w1, x1); x2 = fma(dl, w2, x2);
+            ++it;
+            break;
         }
         lam += dl;
     }
-    qx = x0; qy = x1; qz = x2;
     return it;
+}
+
+__device__ __forceinline__ int smallest_eigvec_secular(const Sym4 &M, double &qx, double &qy, double &qz) {
+    double lam;
+    SecularBound B;
+    const int r = secular_first(M, lam, qx, qy, qz, B);
+    if (r == 2) return 0;
+    if (r == 1) return 1;
+    return secular_rest(M, lam, qx, qy, qz);
 }
 
 // Cyclic Jacobi on the 4x4 (north-star's nominal solver), eigenvectors accumulated; A/B only.

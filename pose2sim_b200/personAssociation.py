@@ -46,7 +46,8 @@ def read_settings(config_dict):
 
 class StagedAssociation:
     __slots__ = ("settings", "calib_file", "P", "cam_dirs", "dirs", "table", "f_range", "n_cams",
-                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact", "workers", "mp_staged", "native", "world")
+                 "tracked_keypoint_id", "obs", "count", "parsed", "inexact", "workers", "mp_staged", "native", "world",
+                 "src_c_paths", "index")
 
 
 # ---- file I/O on a process pool -------------------------------------------------------------------------------------
@@ -101,7 +102,9 @@ def _rewrite_native(st, proposals):
     """`rewrite_json_files` (:552-580) for all frames through the native writer; the few files it leaves alone (status 2:
     strings with escapes, duplicate keys, no `people` list) are rewritten frame by frame by the Python statements."""
     C = st.n_cams
-    src = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
+    src = getattr(st, "src_c_paths", None)                 # the C array the native reader was given (same table)
+    if src is None:
+        src = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
     dst = _stg.frame_paths(st.dirs.tracked_dir, st.cam_dirs, st.table)
     # 'none' entries: the reference opens <tracked>/<cam>/none for writing, fails on the source and removes it again
     status = _stg.rewrite_people_files(src, dst, proposals, _io_threads(st.world))
@@ -133,7 +136,19 @@ def stage_project(config_dict, rank=0, world=1):
 
     dirs = _stg.PoseDirs(s["project_dir"])
     cam_dirs = dirs.camera_dirs_for_association()
-    _, files = dirs.files_for_association(cam_dirs)
+    # Listing, file order and the frame table in native code (staging.NativeIndex) when the files are listed where they are
+    # read — pose/ — i.e. when there is no pose-sync/ (the reference lists pose-sync/ but reads pose/, :724-731 / :762-766:
+    # that case keeps the Python statements)
+    index, files = None, None
+    if os.environ.get("P2S_NATIVE_IO", "1") != "0" and not os.path.isdir(dirs.sync_dir):
+        try:
+            index = _stg.NativeIndex(dirs.pose_dir, cam_dirs)
+            counts = index.counts()
+        except OSError:
+            index = None
+    if index is None:
+        _, files = dirs.files_for_association(cam_dirs)
+        counts = [len(j) for j in files]
     if rank == 0:
         if not os.path.exists(dirs.tracked_dir):
             os.mkdir(dirs.tracked_dir)
@@ -146,7 +161,7 @@ def stage_project(config_dict, rank=0, world=1):
         import torch.distributed as dist
         dist.barrier()                                        # the output directories exist before anyone writes
     fr = s["frame_range"]
-    f_range = [0, max(len(j) for j in files)] if fr in ("all", "auto", []) else fr
+    f_range = [0, max(counts)] if fr in ("all", "auto", []) else fr
     n_cams = len(cam_dirs)
     if n_cams != len(P):
         raise Exception(f"Error: The number of cameras is not consistent: Found {len(P)} cameras in the calibration "
@@ -162,14 +177,34 @@ def stage_project(config_dict, rank=0, world=1):
                             f"tracked_keypoint in Config.toml. Tracking {fallback} instead.")
 
     st = StagedAssociation()
-    st.world = world
+    st.world, st.src_c_paths = world, None
     st.settings, st.calib_file, st.P = s, calib_file, np.asarray(P, dtype=np.float64)
     st.cam_dirs, st.dirs, st.f_range, st.n_cams, st.tracked_keypoint_id = cam_dirs, dirs, list(f_range), n_cams, kid
-    st.table = _stg.frame_file_table(files, f_range)
-    if world > 1:
-        from . import sharding
-        a, b = sharding.frame_block(len(st.table), rank, world)
-        st.table = st.table[a:b]
+    st.index = None
+    if index is not None and not all(type(v) is int for v in f_range):
+        files = index.names()                                 # range(*f_range) raises on these like the reference's does
+        index.close()
+        index = None
+    if index is not None:
+        # the table of this rank's frame block only (frames are tabulated independently of each other)
+        fr_all = range(*f_range)
+        a, b = 0, len(fr_all)
+        if world > 1:
+            from . import sharding
+            a, b = sharding.frame_block(len(fr_all), rank, world)
+        step_ok = fr_all.step == 1
+        if step_ok and index.build_table([fr_all.start + a, fr_all.start + b] if len(fr_all) else [0, 0]):
+            st.table, st.index = index.table_names(), index
+        else:                                                 # a name without a number (the statements below raise the
+            files = index.names()                             # reference's IndexError) or a stepped frame range
+            index.close()
+            index = None
+    if index is None:
+        st.table = _stg.frame_file_table(files, f_range)
+        if world > 1:
+            from . import sharding
+            a, b = sharding.frame_block(len(st.table), rank, world)
+            st.table = st.table[a:b]
     st.workers, st.mp_staged, st.native = host_workers(len(st.table) * n_cams, world), None, False
     # the reference always READS from pose/ (`os.path.exist` typo, :762-766)
     if os.environ.get("P2S_NATIVE_IO", "1") != "0" and _stage_native(st, world):
@@ -212,11 +247,16 @@ def _stage_native(st, world):
     s, F, C = st.settings, len(st.table), st.n_cams
     if F == 0:
         return False
-    paths = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
+    if st.index is not None:                                # the native index owns the [F][C] path array
+        paths, c_arr = (F, C), st.index.table_c_array()
+    else:
+        paths = _stg.frame_paths(st.dirs.pose_dir, st.cam_dirs, st.table)
+        c_arr = _stg._c_paths(paths)                        # one ctypes array for every native pass over this table
+    st.src_c_paths = c_arr
     nt = _io_threads(world)
     if not s["multi_person"]:
         NP = _lib.P2S_MAX_PERSONS
-        o3, named, listed, _, status, inexact = _stg.read_people_files(paths, 3 * st.tracked_keypoint_id, 3, NP, nt)
+        o3, named, listed, _, status, inexact = _stg.read_people_files(paths, 3 * st.tracked_keypoint_id, 3, NP, nt, c_arr)
         if (status >= 2).any():
             return False
         obs = np.full((F, C, NP, 4), np.nan, np.float32)
@@ -228,7 +268,7 @@ def _stage_native(st, world):
             logging.warning(f"{inexact} 2D values are not exactly representable in float32 and were rounded for the "
                             f"device staging layout.")
         return True
-    _, _, listed, llen, status, _ = _stg.read_people_files(paths, 0, 0, _lib.P2S_MAX_DETECTIONS, nt)
+    _, _, listed, llen, status, _ = _stg.read_people_files(paths, 0, 0, _lib.P2S_MAX_DETECTIONS, nt, c_arr)
     if (status >= 2).any():
         return False
     lengths = sorted(set(int(v) for v in llen[llen != 0]))
@@ -238,7 +278,7 @@ def _stage_native(st, world):
     if L % 3:
         return False
     NP = max(int(listed.max(initial=0)), 1)
-    obs, _, listed2, _, status2, inexact = _stg.read_people_files(paths, 0, L, NP, nt)
+    obs, _, listed2, _, status2, inexact = _stg.read_people_files(paths, 0, L, NP, nt, c_arr)
     if (status2 >= 2).any() or not np.array_equal(listed, listed2):
         return False
     n_max = int(listed.sum(axis=1).max(initial=0))
@@ -304,17 +344,18 @@ def rewrite_frame(tracked_paths, source_js, proposals):
 
 def write_outputs(st, res, log=True):
     """personAssociation.py:776-808."""
-    errors, cams_off = [], []
-    for fi, names in enumerate(st.table):
-        e, comb = res["err"][fi], res["comb"][fi]
-        if not np.isinf(e):
-            errors.append(float(e))
-        cams_off.append(int(np.count_nonzero(np.isnan(comb))))
-        if st.parsed is not None:
+    F = len(st.table)
+    err, comb_all = np.asarray(res["err"], dtype=np.float64)[:F], np.asarray(res["comb"], dtype=np.float64)[:F]
+    errors = [float(e) for e in err[~np.isinf(err)]]
+    cams_off = [int(v) for v in np.count_nonzero(np.isnan(comb_all), axis=1)] if F else []
+    if st.parsed is not None:
+        for fi, names in enumerate(st.table):
             tracked = [os.path.join(st.dirs.tracked_dir, st.cam_dirs[c], names[c]) for c in range(st.n_cams)]
-            rewrite_frame(tracked, st.parsed[fi], [comb])
-    if st.parsed is None:
-        _rewrite_parallel(st, [[res["comb"][fi]] for fi in range(len(st.table))])
+            rewrite_frame(tracked, st.parsed[fi], [comb_all[fi]])
+    elif st.native or os.environ.get("P2S_NATIVE_IO", "1") != "0":
+        _rewrite_native(st, comb_all.reshape(F, 1, st.n_cams))
+    else:
+        _rewrite_parallel(st, [[comb_all[fi]] for fi in range(F)])
     if log:
         log_recap(st, errors, cams_off)
     return {"error": errors, "cameras_off": cams_off}

@@ -167,6 +167,20 @@ class NativeIndex:
         ptr = C.cast(self.lib.p2s_index_table_paths(self.h), C.POINTER(C.c_char_p))
         return [[ptr[f * self.n_cams + c].decode() for c in range(self.n_cams)] for f in range(self.n_frames)]
 
+    def table_names(self):
+        """The current table as [F][C] file NAMES ('none' = no file), what `frame_file_table` returns — from ONE copy of
+        the native buffer instead of a ctypes call per entry."""
+        import ctypes as C
+        n = C.c_longlong(0)
+        ptr = self.lib.p2s_index_table_arena(self.h, C.cast(C.pointer(n), C.c_void_p))
+        flat = C.string_at(ptr, n.value).decode().split("\0")[:self.n_frames * self.n_cams] if n.value else []
+        nc = self.n_cams
+        return [[(p.rsplit("/", 1)[1] if p else "none") for p in flat[f * nc:(f + 1) * nc]] for f in range(self.n_frames)]
+
+    def table_c_array(self):
+        """The table's `const char *const *` for the native readers / writers (valid until the next build_table / close)."""
+        return self.lib.p2s_index_table_paths(self.h)
+
     def signature(self):
         import ctypes as C
         sig = (C.c_ulonglong * 2)()
@@ -461,21 +475,24 @@ def _c_paths(paths):
     return (C.c_char_p * len(flat))(*flat)
 
 
-def read_people_files(paths, value_offset, n_values, max_persons, n_threads=0):
+def read_people_files(paths, value_offset, n_values, max_persons, n_threads=0, c_array=None):
     """Native reader of the association stage (`p2s_read_people_files`): paths [F][C] -> obs float32
     [F, C, max_persons, n_values] (None when n_values == 0), count_named, count_listed, list_len int32 [F, C],
     status uint8 [F, C] and the number of values float32 could not hold exactly."""
     import ctypes as C
     from . import _lib
     lib = _lib.load()
-    F = len(paths)
-    n_cams = len(paths[0]) if F else 1
-    arr = _c_paths(paths)
+    if isinstance(paths, tuple):                              # (n_frames, n_cams): the paths are in `c_array`
+        F, n_cams = paths
+    else:
+        F = len(paths)
+        n_cams = len(paths[0]) if F else 1
+    arr = c_array if c_array is not None else _c_paths(paths)
     obs = np.empty((F, n_cams, max_persons, n_values), np.float32) if n_values * max_persons else None
     named, listed, llen = (np.zeros((F, n_cams), np.int32) for _ in range(3))
     status = np.zeros((F, n_cams), np.uint8)
     inexact = C.c_longlong(0)
-    _lib.check(None, lib.p2s_read_people_files(C.cast(arr, C.c_void_p), F, n_cams, int(value_offset), int(n_values), int(max_persons),
+    _lib.check(None, lib.p2s_read_people_files(arr if isinstance(arr, int) else C.cast(arr, C.c_void_p), F, n_cams, int(value_offset), int(n_values), int(max_persons),
                                                obs.ctypes.data if obs is not None else None, named.ctypes.data, listed.ctypes.data,
                                                llen.ctypes.data, status.ctypes.data, C.cast(C.pointer(inexact), C.c_void_p), int(n_threads)))
     return obs, named, listed, llen, status, int(inexact.value)
@@ -487,18 +504,29 @@ def rewrite_people_files(src_paths, dst_paths, proposals, n_threads=0):
     import ctypes as C
     from . import _lib
     lib = _lib.load()
-    F = len(src_paths)
-    n_cams = len(src_paths[0]) if F else 1
-    offs = np.zeros(F + 1, np.int32)
-    rows = []
-    for f, prop in enumerate(proposals):
-        a = np.asarray(prop, dtype=np.float64).reshape(-1, n_cams) if np.size(prop) else np.zeros((0, n_cams))
-        rows.append(np.where(np.isnan(a), -1, a).astype(np.int32))
-        offs[f + 1] = offs[f] + len(a)
-    comb = np.ascontiguousarray(np.concatenate(rows) if rows else np.zeros((0, n_cams), np.int32), dtype=np.int32)
+    if isinstance(src_paths, list):
+        F = len(src_paths)
+        n_cams = len(src_paths[0]) if F else 1
+    else:
+        F, n_cams = len(proposals), len(dst_paths[0]) if len(dst_paths) else 1
+    if isinstance(proposals, np.ndarray) and proposals.ndim == 3 and proposals.shape[0] == F:
+        # the same number of proposals in every frame (single-person mode: one): no per-frame loop
+        a = np.asarray(proposals, dtype=np.float64).reshape(F, -1, n_cams)
+        comb = np.ascontiguousarray(np.where(np.isnan(a), -1, a).astype(np.int32).reshape(-1, n_cams))
+        offs = (np.arange(F + 1, dtype=np.int64) * a.shape[1]).astype(np.int32)
+    else:
+        offs = np.zeros(F + 1, np.int32)
+        rows = []
+        for f, prop in enumerate(proposals):
+            a = np.asarray(prop, dtype=np.float64).reshape(-1, n_cams) if np.size(prop) else np.zeros((0, n_cams))
+            rows.append(np.where(np.isnan(a), -1, a).astype(np.int32))
+            offs[f + 1] = offs[f] + len(a)
+        comb = np.ascontiguousarray(np.concatenate(rows) if rows else np.zeros((0, n_cams), np.int32), dtype=np.int32)
     status = np.zeros((F, n_cams), np.uint8)
-    s_arr, d_arr = _c_paths(src_paths), _c_paths(dst_paths)
-    _lib.check(None, lib.p2s_rewrite_people_files(C.cast(s_arr, C.c_void_p), C.cast(d_arr, C.c_void_p), F, n_cams, offs.ctypes.data,
+    s_arr = src_paths if not isinstance(src_paths, list) else _c_paths(src_paths)      # a ctypes array is taken as it is
+    d_arr = dst_paths if not isinstance(dst_paths, list) else _c_paths(dst_paths)
+    _lib.check(None, lib.p2s_rewrite_people_files(s_arr if isinstance(s_arr, int) else C.cast(s_arr, C.c_void_p),
+                                                  d_arr if isinstance(d_arr, int) else C.cast(d_arr, C.c_void_p), F, n_cams, offs.ctypes.data,
                                                   comb.ctypes.data if len(comb) else None, status.ctypes.data, int(n_threads)))
     return status
 

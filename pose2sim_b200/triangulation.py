@@ -246,15 +246,27 @@ def reidentify(res, f_range, n_cams, max_distance_m):
 # ---------------------------------------------------------------------------------------------------
 def fill_small_gaps(col, index, max_gap, kind):
     """common.py:669-712 `interpolate_zeros_nans` on one coordinate column (values at labels `index`)."""
-    from scipy import interpolate
     good = ~(np.isnan(col) | (col == 0))
     if np.count_nonzero(good) <= 4:
         return col
-    f = interpolate.interp1d(index[good], col[good], kind=kind, fill_value="extrapolate", bounds_error=False)
     bad = np.flatnonzero(~good)
     out = col.copy()
     if bad.size:
-        out[bad] = f(index[bad])                     # = np.where(good, col, f(index)), evaluated only where it is used
+        # = np.where(good, col, f(index)) with f = interp1d(index[good], col[good], kind, fill_value="extrapolate"),
+        # evaluated only where it is used
+        xg, yg = index[good], col[good]
+        if kind == "linear" and np.all(np.diff(xg) > 0):
+            # scipy's own statements for kind="linear" with extrapolation (interp1d._call_linear), without building an
+            # interpolator object per column: the segment is found by searchsorted, end segments extrapolate
+            xn = index[bad]
+            hi = np.clip(np.searchsorted(xg, xn), 1, len(xg) - 1).astype(int)
+            lo = hi - 1
+            x_lo, x_hi, y_lo, y_hi = xg[lo], xg[hi], yg[lo], yg[hi]
+            out[bad] = ((xn - x_lo) / (x_hi - x_lo)) * y_hi + ((x_hi - xn) / (x_hi - x_lo)) * y_lo
+        else:
+            from scipy import interpolate
+            f = interpolate.interp1d(xg, yg, kind=kind, fill_value="extrapolate", bounds_error=False)
+            out[bad] = f(index[bad])
         for seq in np.split(bad, np.flatnonzero(np.diff(index[bad]) > 1) + 1):
             if len(seq) > max_gap:
                 out[seq] = np.nan
@@ -279,13 +291,18 @@ def valid_chunk(series, min_chunk_size=10, method="largest"):
 
 
 def _ffill_bfill(a):
-    """DataFrame.ffill().bfill() down the rows (NaN only)."""
+    """DataFrame.ffill().bfill() down the rows (NaN only); only the columns that hold a NaN are touched."""
     def ffill(v):
         idx = np.where(~np.isnan(v), np.arange(v.shape[0])[:, None], 0)
         np.maximum.accumulate(idx, axis=0, out=idx)
         return np.take_along_axis(v, idx, axis=0)
-    a = ffill(a)
-    return ffill(a[::-1])[::-1]
+    cols = np.flatnonzero(np.isnan(a).any(axis=0))
+    if cols.size == 0:
+        return a
+    sub = ffill(a[:, cols])
+    out = a.copy()
+    out[:, cols] = ffill(sub[::-1])[::-1]
+    return out
 
 
 def frame_rate_of(s):
@@ -476,10 +493,14 @@ def log_recap(st, r):
         err, nex = r["error"][n], r["nb_cams_excluded"][n]
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", RuntimeWarning)
+            # np.nanmean(err[:, k]) of every column in one call each: rows of the transposed copy are contiguous, so every
+            # mean is the same pairwise sum as the per-column statement's (tests/test_dropin_host.py checks the bits)
+            err_means = np.nanmean(np.ascontiguousarray(err.T), axis=1)
+            nex_means = np.nanmean(np.ascontiguousarray(nex.T), axis=1)
             for k, name in enumerate(st.keypoints_names):
-                e_px = np.around(np.nanmean(err[:, k]), decimals=1)
+                e_px = np.around(err_means[k], decimals=1)
                 e_m = np.around(e_px * Dm / fm, decimals=3)
-                excl = np.around(np.nanmean(nex[:, k]), decimals=2)
+                excl = np.around(nex_means[k], decimals=2)
                 logging.info(f"Mean reprojection error for {name} is {e_px} px (~ {e_m} m), reached with {excl} excluded cameras. ")
                 if s["show_interp_indices"]:
                     if kind != "none":
@@ -492,9 +513,9 @@ def log_recap(st, r):
                             logging.info("  Frames " + ", ".join(d.replace(":", " to ") for d in skipped) + " were not interpolated.")
                     else:
                         logging.info("  No frames were interpolated because 'interpolation_kind' was set to none. ")
-            e_px = np.around(np.nanmean(err[:, -1]), decimals=1)
+            e_px = np.around(err_means[-1], decimals=1)
             e_mm = np.around(e_px * Dm / fm * 1000, decimals=1)
-            excl = np.around(np.nanmean(nex[:, -1]), decimals=2)
+            excl = np.around(nex_means[-1], decimals=2)
         logging.info(f"\n--> Mean reprojection error for all points on frames {a} to {b} is {e_px} px, which roughly corresponds to {e_mm} mm. ")
         logging.info(f"Cameras were excluded if likelihood was below {s['lik_thr']} and if the reprojection error was above {s['reproj_thr']} px.")
         if kind != "none":

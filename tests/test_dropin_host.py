@@ -283,3 +283,43 @@ def test_install_into_reference_runs_under_the_unchanged_orchestrator(golden, tm
     finally:
         ref.triangulation.triangulate_all, ref.personAssociation.associate_all = original
         logging.getLogger().handlers = [h for h in logging.getLogger().handlers if not isinstance(h, logging.FileHandler)]
+
+
+def test_linear_gap_fill_and_recap_means_keep_the_reference_bits():
+    """`fill_small_gaps` evaluates scipy's linear interp1d statements itself (no interpolator object per column) and
+    `log_recap` takes all column means in one call: both must give the bits of the statements they replace
+    (common.py:669-712 `interpolate_zeros_nans`; triangulation.py:315-328 `np.nanmean` per keypoint)."""
+    from scipy import interpolate
+    rng = np.random.default_rng(11)
+    for trial in range(120):
+        n = int(rng.integers(6, 300))
+        index = np.arange(50, 50 + n)
+        col = rng.normal(size=n) * rng.choice([1.0, 1e3, 1e-3])
+        col[rng.random(n) < rng.choice([0.05, 0.3, 0.7])] = np.nan
+        col[rng.random(n) < 0.02] = 0.0
+        good = ~(np.isnan(col) | (col == 0))
+        got = tri.fill_small_gaps(col, index, 10, "linear")
+        if np.count_nonzero(good) <= 4:
+            assert got is col
+            continue
+        f = interpolate.interp1d(index[good], col[good], kind="linear", fill_value="extrapolate", bounds_error=False)
+        ref = np.where(good, col, f(index))
+        bad = np.flatnonzero(~good)
+        for seq in np.split(bad, np.flatnonzero(np.diff(bad) > 1) + 1):
+            if len(seq) > 10:
+                ref[seq] = np.nan
+        assert np.array_equal(got, ref, equal_nan=True), trial
+    for trial in range(20):
+        e = rng.normal(size=(int(rng.integers(5, 3000)), 27)) * 10
+        e[rng.random(e.shape) < 0.1] = np.nan
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            per_col = np.array([np.nanmean(e[:, k]) for k in range(27)])
+            at_once = np.nanmean(np.ascontiguousarray(e.T), axis=1)
+        assert np.array_equal(per_col, at_once, equal_nan=True)
+    a = rng.normal(size=(40, 9))
+    a[3:7, 2] = np.nan; a[0:2, 5] = np.nan; a[-3:, 7] = np.nan
+    import pandas as pd
+    assert np.array_equal(tri._ffill_bfill(a), pd.DataFrame(a).ffill().bfill().to_numpy())
+    b = rng.normal(size=(10, 4))
+    assert tri._ffill_bfill(b) is b
