@@ -353,7 +353,8 @@ extern "C" int p2s_read_pose_files(const char *const *paths, long long n_frames,
 // later cameras).  For a 40 k-file trial those list / regex / dict operations cost more than parsing the files, so they
 // live here; staging.py keeps the Python statements as the tested restatement (tests/test_native_staging.py).
 struct p2s_dir_index {
-    struct Entry { std::string name; bool has_num; std::string digits; long long num; };   // digits: last run, no leading zeros
+    // d0, dn: the last digit run of the name without its leading zeros (a view into `name`, no second string per file)
+    struct Entry { std::string name; bool has_num; uint32_t d0, dn; long long num; };
     std::vector<std::string> dirs;
     std::vector<std::vector<Entry>> cams;
     std::string table_arena;                   // the table's paths back to back, NUL-terminated ("" = none)
@@ -364,8 +365,9 @@ struct p2s_dir_index {
 
 namespace {
 
-bool less_digits(const std::string &a, const std::string &b) {      // numeric order of digit strings without leading zeros
-    return a.size() != b.size() ? a.size() < b.size() : a < b;
+// numeric order of digit strings without leading zeros
+bool less_digits(const p2s_dir_index::Entry &a, const p2s_dir_index::Entry &b) {
+    return a.dn != b.dn ? a.dn < b.dn : std::memcmp(a.name.data() + a.d0, b.name.data() + b.d0, a.dn) < 0;
 }
 
 }  // namespace
@@ -395,18 +397,23 @@ extern "C" int p2s_index_open(const char *const *dirs, int n_cams, p2s_dir_index
             while (lo > 0 && n[lo - 1] >= '0' && n[lo - 1] <= '9') --lo;
             en.has_num = hi > lo;
             en.num = -1;
+            en.d0 = en.dn = 0;
             if (en.has_num) {
                 size_t z = lo;
                 while (z + 1 < hi && n[z] == '0') ++z;
-                en.digits.assign(n + z, hi - z);
-                if (en.digits.size() <= 18) en.num = std::strtoll(en.digits.c_str(), nullptr, 10);
+                en.d0 = (uint32_t)z; en.dn = (uint32_t)(hi - z);
+                if (en.dn <= 18) {
+                    long long v = 0;
+                    for (size_t i = z; i < hi; ++i) v = v * 10 + (n[i] - '0');
+                    en.num = v;
+                }
             }
             v.push_back(std::move(en));
         }
         ::closedir(d);
         std::stable_sort(v.begin(), v.end(), [](const p2s_dir_index::Entry &a, const p2s_dir_index::Entry &b) {
             if (a.has_num != b.has_num) return a.has_num;             // (False, n) < (True, s)
-            if (a.has_num) return less_digits(a.digits, b.digits);
+            if (a.has_num) return less_digits(a, b);
             return a.name < b.name;
         });
     };

@@ -411,8 +411,10 @@ def write_outputs(st, res):
         mn = res["mask"][:, n]
         if s["interpolation"] != "none":
             try:
-                cols = [fill_small_gaps(Qn[:, j], frames, s["interp_gap"], s["interpolation"]) for j in range(3 * K)]
-                Qn = np.stack(cols, axis=1) if cols else Qn
+                filled = np.empty_like(Qn)                    # assigned as a whole: a failing column leaves Qn as it was
+                for j in range(3 * K):
+                    filled[:, j] = fill_small_gaps(Qn[:, j], frames, s["interp_gap"], s["interpolation"])
+                Qn = filled
             except Exception:
                 logging.warning(f"Interpolation was not possible for person {n}. This means that not enough points "
                                 f"are available, which is often due to a bad calibration.")
