@@ -19,6 +19,8 @@ def one():
     import torch
     from pose2sim_b200 import ops, synth
     eng = ops.get_engine(0)
+    if os.environ.get("P2S_ASSOC_MODE") and hasattr(eng, "set_search_mode"):
+        eng.set_search_mode(os.environ["P2S_ASSOC_MODE"])
     for F, Np, C in SHAPES:
         wl = synth.make_association_workload(C, F, Np, seed=404)
         obs4 = np.zeros((F, C, Np, 4), np.float32)
@@ -38,7 +40,7 @@ def one():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         chk = float(torch.nansum(out["Q"]).item()) + float(out["comb"].long().sum().item())
-        print(json.dumps({"lib": os.path.basename(os.environ.get("P2S_LIB", "default")), "frames": F, "persons": Np, "cams": C,
+        print(json.dumps({"lib": os.path.basename(os.environ.get("P2S_LIB", "default")), "mode": os.environ.get("P2S_ASSOC_MODE", "default"), "frames": F, "persons": Np, "cams": C,
                           "kernel_ms": ms, "frames_per_s": F / ms * 1e3, "rows_per_s": float(st[:, 0].sum()) / ms * 1e3,
                           "cands_per_s": float(st[:, 1].sum()) / ms * 1e3, "grid": eng.last_grid(), "checksum": chk}), flush=True)
 
@@ -50,10 +52,13 @@ if __name__ == "__main__":
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         libs = [None] + sorted(glob.glob(os.path.join(ROOT, "pose2sim_b200", "ab", "libp2s_*.so")))
         with open(os.path.join(ROOT, "gpurun_out", "assoc_ab.jsonl"), "a") as log:
-            for lib in libs:
+            runs = [(lib, None) for lib in libs] + [(None, "exhaustive")]
+            for lib, mode in runs:
                 env = dict(os.environ)
                 if lib:
                     env["P2S_LIB"] = lib
+                if mode:
+                    env["P2S_ASSOC_MODE"] = mode
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=env, capture_output=True, text=True)
                 out = r.stdout.strip() or ("FAILED " + r.stderr[-400:])
                 print(out, flush=True)
