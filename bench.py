@@ -289,7 +289,17 @@ def cfg3_leg(eng, torch, barrier, dev, rank, steps=10):
     C, F, K = cfg["C"], cfg["F"], cfg["K"]
     U = F * K
     P = synth.ring_cameras(C)[0]
-    wl = eng.synth_observations(P, rank * U, U, K, cfg["seed"])
+    # The 1 M-frame stream is dealt to the configuration's 8 GPUs BLOCK-CYCLICALLY (blocks of 600 frames): the cost of a
+    # frame drifts along the stream (the walk carries the subject through regions with more or fewer deep exclusion
+    # levels: contiguous eighths differ by up to 25 % in kernel time, profiles/r2p_bench_n4_contiguous.json), so every
+    # shard is an interleaved sample of the whole stream and N GPUs process N of the 8 shards.
+    # A block is one period of the generator's walk (600 frames), so all shards see the same mix of geometry.
+    BLK, SHARDS = 600, 8
+    wl = {k: torch.empty((U, C), dtype=torch.float32, device=dev) for k in ("x", "y", "lik")}
+    for j in range((F + BLK - 1) // BLK):
+        a, b = j * BLK * K, min((j + 1) * BLK, F) * K
+        eng.synth_observations(P, (j * SHARDS + rank % SHARDS) * BLK * K, b - a, K, cfg["seed"],
+                               out={k: v[a:b] for k, v in wl.items()})
     stats = eng.new_stats()
     out = eng.triangulate_planes(wl["x"], wl["y"], wl["lik"], P, cfg["lik_thr"], cfg["thr"], cfg["min_cams"], stats=stats)
     torch.cuda.synchronize()
@@ -309,7 +319,8 @@ def cfg3_leg(eng, torch, barrier, dev, rank, steps=10):
     return {"workload": cfg["name"] + "; inputs from the device generator (p2s_synth_observations_device)", "n_cams": C,
             "min_cameras_for_triangulation": cfg["min_cams"], "units_per_gpu": U, "steps": steps, "ms_per_step": ms,
             "kernel_ms": ms, "flops": algorithmic_flops(st), "level_hist": st["level_hist"],
-            "candidates_per_unit": st["candidates"] / U, "gather": "none: results stay in the rank's HBM"}
+            "candidates_per_unit": st["candidates"] / U, "gather": "none: results stay in the rank's HBM",
+            "sharding": f"block-cyclic: 1 M frames in blocks of {BLK}, block b belongs to shard b mod {SHARDS}; rank r processes shard r"}
 
 
 # ---------------------------------------------------------------------------------------------------
