@@ -110,6 +110,12 @@ int p2s_set_band_eps(p2s_handle *h, double eps_px);
  * (the north-star's nominal solver; kept for A/B evidence). */
 int p2s_set_solver(p2s_handle *h, int solver);
 
+/* how the single-person association search (p2s_associate_*) visits its rows: 0 (default) = candidates whose lower bound
+ * (one factorisation of the eigen-solve) is above the threshold are not solved and re-projected; a frame whose search
+ * finds no row under the threshold is searched again exhaustively, so the result is the exhaustive search's;
+ * 1 = every row is solved and re-projected (personAssociation.py:196-248 as written).                               */
+int p2s_set_search_mode(p2s_handle *h, int mode);
+
 /* how the triangulation kernels write a full 32-unit tile of outputs: 0 (default) = 16-byte vector stores from the
  * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path) */
 int p2s_set_output_mode(p2s_handle *h, int mode);

@@ -47,11 +47,18 @@ struct AssocArgs {
     uint32_t *out_stats;
     unsigned int *tile_counter;    // [0] frame dispenser of the main pass, [1] of the wide pass, [2] frames flagged wide
     uint8_t *wide_flags;           // [n_frames]: 1 = the frame's active likelihoods span more than P2S_WIDE_SPREAD
+    // row filter (see associate_kernel): |P_c[2] . (q, 1)| <= bnd_k1 |q| + bnd_k2 for every camera
+    double bnd_k1, bnd_k2;
+    int search_mode;               // 0 = rows filtered by their lower bound, 1 = every row solved and re-projected
 };
 
 __host__ __device__ inline size_t assoc_slab_bytes(int cmax, int np) {
     return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 4 * (size_t)cmax * sizeof(uint32_t) +
            (size_t)(cmax / 2) * 256;          // per camera PAIR: byte of two packed digits -> active / NaN bits of the pair
+}
+// row queue of a team: 2 x its threads entries of {row index, candidate mask, packed person digits}
+__host__ __device__ inline size_t assoc_queue_bytes(int cmax, int nw) {
+    return (size_t)2 * 32 * nw * (2 * sizeof(unsigned long long) + (size_t)((cmax + 7) / 8) * sizeof(uint32_t));
 }
 
 template <int CMAX>
@@ -95,6 +102,10 @@ struct alignas(16) TeamScratch {  // per team, in shared memory (only used when 
     uint32_t dig[NW][4];
     unsigned int frame;
     unsigned int rows, cands;
+    uint32_t wcount[NW];          // row filter: survivors per warp of a scan step
+    unsigned long long lastrow[NW];   // row index of T.last[w]
+    unsigned long long deadrow[NW];   // level end: last row of warp w that counts as evaluated but was dropped unsolved
+    unsigned int again;           // the frame has to be searched again without the filter
 };
 
 template <int NW>
@@ -106,6 +117,22 @@ __device__ __forceinline__ void team_sync() {
 // with a likelihood threshold near 0) and leaves them alone.  WIDE = true: the pass behind it, which returns at once when
 // nothing was flagged and otherwise searches the flagged frames with every candidate solved from a factorisation of A
 // itself (Givens QR + one-sided Jacobi, p2s_math.cuh) like the reference's SVD, instead of the normal matrix.
+// ROW FILTER (search_mode 0, not in the WIDE pass).  The reference solves and re-projects every row it visits until the
+// first row whose error is under the threshold (:196-248); when such a row exists it IS the result (every row before it
+// is >= the threshold, and the running best is replaced on a strict '<').  So a candidate only needs its exact error if
+// that error can be under the threshold.  Iteration 0 of the eigen-solve (one 3x3 factorisation) yields
+// q0 = -A^-1 b and s = min_q R(q), R(q) = (q,1)^T M (q,1) = s + (q - q0)^T A (q - q0) >= s + (|q| - |q0|)^2 / tau with
+// tau = trace(A^-1) >= 1 / (smallest eigenvalue of A).  For ANY q, R(q) = sum_c (w_c d_c e_c)^2 (e_c: pixel distance of
+// camera c, d_c = P_c[2].(q,1), common.py:344-345 / :357-375 are the same rows) and |w_c d_c| <= whi (k1 |q| + k2), so the
+// mean error over the m cameras obeys E >= sqrt(sum e_c^2) / m >= sqrt(R(q)) / (m whi (k1 |q| + k2)); minimising the right
+// side over |q| gives a bound that needs no knowledge of where the solver ends:
+//     E^2 >= s / ((k1 |q0| + k2)^2 + k1^2 s tau) / (m whi)^2
+// (p2s_math.cuh, SecularBound).  The team SCANS the rows in product order, computing only that bound for every candidate
+// of a row, and queues the rows that have candidates whose bound is not above the threshold (x 1.001 + 1e-5 px) together
+// with the mask of those candidates; full batches of queued rows then get the exact evaluation of their marked
+// candidates, in row order, with the reference's first-hit rule.  A frame whose search ends WITHOUT a hit needs the exact
+// minimum over all its rows instead (and the exact error of every level's last row): it is searched again with the
+// filter off.  Results are those of the exhaustive search (tests/test_gpu_associate.py compares the two bit for bit).
 template <int CMAX, int NW, bool WIDE>
 #ifndef P2S_ASSOC_MIN_BLOCKS
 #define P2S_ASSOC_MIN_BLOCKS 4      /* resident 4-warp CTAs per SM of the warp-per-frame variant (A/B: tools/kernel_ab.py) */
@@ -127,7 +154,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     const int C = a.n_cams, NP = a.max_persons;
     double *sP = reinterpret_cast<double *>(smem_raw);
     // per-team slab: obs float4 [CMAX][NP], blocks double [CMAX * NP][10], n_c, ok masks, reciprocal radices
-    unsigned char *base = smem_raw + CMAX * 12 * sizeof(double) + (assoc_slab_bytes(CMAX, NP) + sizeof(TeamScratch<NW>)) * team;
+    constexpr int DW = (CMAX + 7) / 8;                        // words of packed person digits per row
+    constexpr int QCAP = 2 * TEAM_THREADS;
+    const size_t team_bytes = assoc_slab_bytes(CMAX, NP) + sizeof(TeamScratch<NW>) + assoc_queue_bytes(CMAX, NW);
+    unsigned char *base = smem_raw + CMAX * 12 * sizeof(double) + team_bytes * team;
     float4 *sobs = reinterpret_cast<float4 *>(base);
     double *sblk = reinterpret_cast<double *>(base + (size_t)CMAX * NP * sizeof(float4));
     uint32_t *s_n = reinterpret_cast<uint32_t *>(base + (size_t)CMAX * NP * (sizeof(float4) + 10 * sizeof(double)));
@@ -139,6 +169,9 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     // instead of a shift-and-test chain per camera: that chain was 10 % of the kernel's stall samples)
     unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_nan + CMAX);
     TeamScratch<NW> &T = *reinterpret_cast<TeamScratch<NW> *>(base + assoc_slab_bytes(CMAX, NP));
+    unsigned long long *q_row = reinterpret_cast<unsigned long long *>(base + assoc_slab_bytes(CMAX, NP) + sizeof(TeamScratch<NW>));
+    unsigned long long *q_mask = q_row + QCAP;                // candidates of the row that need their exact error
+    uint32_t *q_dig = reinterpret_cast<uint32_t *>(q_mask + QCAP);                                 // [QCAP][DW]
 
     for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
     __syncthreads();
@@ -202,12 +235,14 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             }
         }
         team_sync<NW>();
+        float whi_frame = __int_as_float(0x7f800000);        // largest active |likelihood| of the frame (bounds the row weights)
         if (!WIDE) {
             float wlo = __int_as_float(0x7f800000), whi = 0.f;
             for (int c = 0; c < C; ++c) {
                 wlo = fminf(wlo, reinterpret_cast<const float *>(s_pair)[2 * c]);
                 whi = fmaxf(whi, reinterpret_cast<const float *>(s_pair)[2 * c + 1]);
             }
+            whi_frame = whi;
             const bool wide_frame = whi > P2S_WIDE_SPREAD * wlo;
             team_sync<NW>();
             if (wide_frame) {                                 // team-uniform: left to the WIDE pass
@@ -216,7 +251,6 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             }
             if (ttid == 0) a.wide_flags[f] = 0;
         }
-#ifndef P2S_ASSOC_OLD_ACTIVE
         for (int i = ttid; i < (CMAX / 2) * 256; i += TEAM_THREADS) {
             const int j = i >> 8, c0 = 2 * j, c1 = c0 + 1;
             const uint32_t d0 = (uint32_t)i & 15u, d1 = ((uint32_t)i >> 4) & 15u;
@@ -226,7 +260,6 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             s_pair[i] = (unsigned char)t;
         }
         team_sync<NW>();
-#endif
         uint32_t present = 0;
         unsigned long long total_rows = 1;
         bool overflow = false;
@@ -243,38 +276,142 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
         // key of the global best.  The reference starts from error = +inf and replaces it on a strict '<' (:242-245), so a
         // row whose best error is +inf (single-camera subsets, subsets poisoned by a NaN observation) never becomes it.
         const unsigned long long kInfKey = 0x7ff0000000000000ULL;
+        const unsigned long long kNoRow = 0xffffffffffffffffULL;
         unsigned long long best_key = kInfKey;
         double bqx = nan64(), bqy = bqx, bqz = bqx;
         uint32_t b_valid = 0;                                 // cameras used by the best candidate
         uint32_t b_dig[4] = {0, 0, 0, 0};                     // person digits of the best row
         unsigned int st_rows = 0, st_cands = 0;               // per warp / per lane counters
+        const double whi_d = (double)whi_frame;
+        const double thr_b = fma(a.thr, 1.001, 1e-5);
+        const double thr2 = thr_b * thr_b;                    // a bound above this cannot belong to a hit (NaN / inf threshold: never)
+        const double k1sq = a.bnd_k1 * a.bnd_k1;
+
+        for (int pass = 0; pass < 2; ++pass) {                // pass 1 only for a filtered search that ended without a hit
+        const bool filter = !WIDE && a.search_mode == 0 && pass == 0;
+        bool redo = false, hit_found = false;                 // redo: a candidate was dropped, or an exact error equalled the threshold
+        err_last = inf64(); best_key = kInfKey; bqx = bqy = bqz = nan64(); b_valid = 0;
+        b_dig[0] = b_dig[1] = b_dig[2] = b_dig[3] = 0u;
+        st_rows = 0; st_cands = 0;
 
         for (int k = 0; !overflow && err_last > a.thr && C - (n_missing + k) >= a.min_cams; ++k) {
             const bool tabled = k <= a.max_table_level;
             const uint32_t ncand_all = (k == 0) ? 1u : tabled ? (a.level_off[k + 1] - a.level_off[k]) : binom_u32(C, k);
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
+            const bool masked = ncand_all <= 64u;             // a queued row carries the mask of its candidates to evaluate
             bool hit = false;
-            uint32_t dig[4] = {0, 0, 0, 0};                   // 4 bits per camera: the row's person indices
+            uint32_t dig[4] = {0, 0, 0, 0};                   // 4 bits per camera: the person indices of the row I scan
             radix_add<CMAX>(dig, (uint32_t)ttid, s_n, s_inv, C);
-            for (unsigned long long rbase = 0; rbase < total_rows && !hit; rbase += TEAM_THREADS) {
-                const unsigned long long r = rbase + ttid;
-                const bool row_ok = r < total_rows;
-                uint32_t active = 0, nanact = 0;              // nanact: active cameras whose chosen detection holds a NaN
-#ifdef P2S_ASSOC_OLD_ACTIVE                                    /* A/B switch */
+            unsigned long long rbase = 0;                     // next row block to scan
+            unsigned int qhead = 0, qn = 0;                   // the team's row queue (ring): team-uniform
+            unsigned long long my_dead = kNoRow;              // my last row that counts as evaluated but was dropped unsolved
+            unsigned long long surv_row = kNoRow;             // last row that went through the exact evaluation ...
+            double surv_err = inf64();                        // ... and its error (team-uniform)
+            unsigned long long hit_row = 0;
+
+            while (!hit) {
+                // ---- scan rows into the queue until a full batch is waiting (or the rows are used up) -----------------
+                while (qn < (unsigned)TEAM_THREADS && rbase < total_rows) {
+                    const unsigned long long r = rbase + ttid;
+                    unsigned long long smask = 0ULL;          // candidates of my row that need their exact error
+                    if (r < total_rows) {
+                        uint32_t active = 0, nanact = 0;
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c)
-                    if (c < C && s_n[c] && ((s_ok[c] >> digit_of<CMAX>(dig, c)) & 1u)) {
-                        active |= 1u << c;
-                        nanact |= ((s_nan[c] >> digit_of<CMAX>(dig, c)) & 1u) << c;
+                        for (int j = 0; j < CMAX / 2; ++j) {
+                            const uint32_t t = s_pair[j * 256 + ((dig[j >> 2] >> ((j & 3) * 8)) & 255u)];
+                            active |= (t & 3u) << (2 * j);
+                            nanact |= ((t >> 2) & 3u) << (2 * j);
+                        }
+                        const int na = __popc(active);
+                        if (na >= a.min_cams && k <= na) {
+                            if (!filter) {
+                                smask = ~0ULL;
+                            } else {
+                                Sym4 Mrow;
+                                sym4_zero(Mrow);
+#pragma unroll
+                                for (int c = 0; c < CMAX; ++c) {
+                                    if ((active >> c) & 1u) {
+                                        const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(dig, c)) * 10);
+                                        const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                        Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
+                                        Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
+                                    }
+                                }
+                                bool dead_eval = false;       // some candidate has a definite error (so the row is an evaluated one)
+                                for (uint32_t ci = 0; ci < ncand_all; ++ci) {
+                                    const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
+                                    if (cm & ~active) continue;
+                                    const uint32_t valid = active & ~cm;
+                                    const int m = __popc(valid);
+                                    if (m < 2) { dead_eval |= (m == 1); continue; }          // +inf (m == 0: NaN, ignored)
+                                    if (valid & nanact) { dead_eval = true; continue; }       // +inf
+                                    Sym4 M = Mrow;
+                                    uint32_t bits = cm;
+                                    while (bits) {
+                                        const int c = __ffs(bits) - 1;
+                                        bits &= bits - 1;
+                                        const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_rt(dig, c)) * 10);
+                                        const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                        M.m00 -= v0.x; M.m01 -= v0.y; M.m02 -= v1.x; M.m03 -= v1.y; M.m11 -= v2.x;
+                                        M.m12 -= v2.y; M.m13 -= v3.x; M.m22 -= v3.y; M.m23 -= v4.x; M.m33 -= v4.y;
+                                    }
+                                    double lam, x0, x1, x2;
+                                    SecularBound B;
+                                    if (secular_first(M, lam, x0, x1, x2, B) == 2) continue;  // NaN candidate: ignored like in the exact pass
+                                    // E^2 >= s / ((k1 |q0| + k2)^2 + k1^2 s tau) / (m whi)^2, see the comment above the kernel
+                                    const double s_lo = fmax(fma(-2e-9, M.m33, B.s), 0.0);   // rounding of c - b.A^-1 b (|b.A^-1 b| <= c)
+                                    const double d0 = fma(a.bnd_k1, sqrt_fast(B.g - 1.0), a.bnd_k2);
+                                    const double mw = whi_d * (double)m;
+                                    const double den = fma(d0, d0, k1sq * s_lo * B.tau) * (mw * mw);
+                                    if (s_lo > thr2 * den) { dead_eval = true; redo = true; }  // false for NaN: then it is solved
+                                    else smask |= masked ? (1ULL << ci) : ~0ULL;              // needs its exact error
+                                }
+                                if (smask == 0ULL && dead_eval) my_dead = r;
+                            }
+                        }
                     }
-#else
+                    // append the surviving rows in row order
+                    const bool survive = smask != 0ULL;
+                    const uint32_t sb = __ballot_sync(P2S_FULL, survive);
+                    unsigned int off = 0, tot = (unsigned)__popc(sb);
+                    if (NW > 1) {
+                        if (lane == 0) T.wcount[warp] = tot;
+                        __syncthreads();
+                        tot = 0;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) { if (w < warp) off += T.wcount[w]; tot += T.wcount[w]; }
+                    }
+                    if (survive) {
+                        const unsigned int slot = (qhead + qn + off + (unsigned)__popc(sb & ((1u << lane) - 1u))) % (unsigned)QCAP;
+                        q_row[slot] = r;
+                        q_mask[slot] = smask;
+#pragma unroll
+                        for (int w = 0; w < DW; ++w) q_dig[slot * DW + w] = dig[w];
+                    }
+                    qn += tot;
+                    team_sync<NW>();                          // queue visible; T.wcount free for the next step
+                    rbase += TEAM_THREADS;
+                    radix_add<CMAX>(dig, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
+                }
+                if (qn == 0) break;                           // every row of the level has been looked at
+
+                // ---- exact evaluation of the first batch of queued rows, in row order -------------------------------
+                const unsigned int nb = qn < (unsigned)TEAM_THREADS ? qn : (unsigned)TEAM_THREADS;
+                const bool row_ok = (unsigned)ttid < nb;
+                const unsigned int eslot = (qhead + (unsigned)ttid) % (unsigned)QCAP;
+                const unsigned long long er = row_ok ? q_row[eslot] : 0ULL;
+                const unsigned long long emask = row_ok ? q_mask[eslot] : 0ULL;
+                uint32_t edig[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int w = 0; w < DW; ++w) edig[w] = row_ok ? q_dig[eslot * DW + w] : 0u;
+                uint32_t active = 0, nanact = 0;              // nanact: active cameras whose chosen detection holds a NaN
 #pragma unroll
                 for (int j = 0; j < CMAX / 2; ++j) {
-                    const uint32_t t = s_pair[j * 256 + ((dig[j >> 2] >> ((j & 3) * 8)) & 255u)];
+                    const uint32_t t = s_pair[j * 256 + ((edig[j >> 2] >> ((j & 3) * 8)) & 255u)];
                     active |= (t & 3u) << (2 * j);
                     nanact |= ((t >> 2) & 3u) << (2 * j);
                 }
-#endif
                 const int na = __popc(active);
                 unsigned long long rkey = P2S_KEY_EMPTY;
                 double rqx = nan64(), rqy = rqx, rqz = rqx;
@@ -286,13 +423,14 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
 #pragma unroll
                     for (int c = 0; c < CMAX; ++c) {
                         if ((active >> c) & 1u) {
-                            const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(dig, c)) * 10);
+                            const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(edig, c)) * 10);
                             const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
                             Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
                             Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
                         }
                     }
                     for (uint32_t ci = 0; ci < ncand_all; ++ci) {
+                        if (masked && !((emask >> ci) & 1ULL)) continue;      // its bound is above the threshold: not a hit
                         const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
                         if (cm & ~active) continue;           // not a subset of the active cameras
                         const uint32_t valid = active & ~cm;
@@ -310,7 +448,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                             while (bits) {
                                 const int c = __ffs(bits) - 1;
                                 bits &= bits - 1;
-                                const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_rt(dig, c)) * 10);
+                                const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_rt(edig, c)) * 10);
                                 const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
                                 M.m00 -= v0.x; M.m01 -= v0.y; M.m02 -= v1.x; M.m03 -= v1.y; M.m11 -= v2.x;
                                 M.m12 -= v2.y; M.m13 -= v3.x; M.m22 -= v3.y; M.m23 -= v4.x; M.m33 -= v4.y;
@@ -321,7 +459,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
 #pragma unroll 1
                                 for (int c = 0; c < C; ++c) {
                                     if (!((valid >> c) & 1u)) continue;
-                                    const float4 o = sobs[c * NP + digit_rt(dig, c)];
+                                    const float4 o = sobs[c * NP + digit_rt(edig, c)];
                                     givens_add_camera(R4, sP + c * 12, (double)o.x, (double)o.y, (double)o.z);
                                 }
                                 smallest_singvec_jacobi(R4, cqx, cqy, cqz);
@@ -331,7 +469,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                             double sum = 0.0;
 #pragma unroll
                             for (int c = 0; c < CMAX; ++c) {
-                                const float4 o = sobs[c * NP + digit_of<CMAX>(dig, c)];
+                                const float4 o = sobs[c * NP + digit_of<CMAX>(edig, c)];
                                 const double dist = reproj_distance(cams.P[c], cqx, cqy, cqz, (double)o.x, (double)o.y);
                                 sum += ((valid >> c) & 1u) ? dist : 0.0;
                             }
@@ -345,10 +483,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                 // all-NaN rows are skipped (:235-236); rows without candidates too
                 const bool evaluated = rkey < P2S_KEY_NAN;
                 const double rerr = key_err(rkey);
+                if (filter && evaluated && rerr == a.thr) redo = true;   // '>' against the threshold decides the next level (:194)
                 const uint32_t evalmask = __ballot_sync(P2S_FULL, evaluated);
                 const uint32_t hitmask = __ballot_sync(P2S_FULL, evaluated && rerr < a.thr);
-                const uint32_t rowmask = __ballot_sync(P2S_FULL, row_ok);
-                // ---- which rows of this step count: everything up to the first row under the threshold ------
+                // ---- which rows of this batch count: everything up to the first row under the threshold ------
                 int wh = NW;                                  // first warp of the team with a hit
                 if (NW == 1) {
                     if (hitmask) wh = 0;
@@ -363,20 +501,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                 else if (warp == wh) { const int fh = __ffs(hitmask) - 1; upto = (fh == 31) ? 0xffffffffu : ((2u << fh) - 1u); }
                 if (wh < NW) hit = true;
                 const uint32_t considered = evalmask & upto;
-                if (lane == 0) st_rows += (unsigned)__popc(rowmask & upto);
                 // warp arg-min over (key, lane) among the considered lanes: min of the high words (one redux.sync), the low
                 // words only when several lanes hold it; the lowest lane among the holders is the first row in visiting order
                 unsigned long long ck = ((considered >> lane) & 1u) ? rkey : P2S_KEY_EMPTY;
                 int cl;
-#ifdef P2S_ASSOC_OLD_ARGMIN                                    /* A/B switch */
-                cl = lane;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const unsigned long long ok2 = __shfl_xor_sync(P2S_FULL, ck, off);
-                    const int ol = __shfl_xor_sync(P2S_FULL, cl, off);
-                    if (ok2 < ck || (ok2 == ck && ol < cl)) { ck = ok2; cl = ol; }
-                }
-#else
                 {
                     const uint32_t hi = (uint32_t)(ck >> 32), lo = (uint32_t)ck;
                     const uint32_t mh = __reduce_min_sync(P2S_FULL, hi);
@@ -389,11 +517,12 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                     cl = __ffs(holders) - 1;
                     ck = ((unsigned long long)mh << 32) | __shfl_sync(P2S_FULL, ml, cl);
                 }
-#endif
                 if (NW == 1) {
                     if (considered) {
-                        // err_last = error of the last evaluated row in visiting order
-                        err_last = __shfl_sync(P2S_FULL, rerr, 31 - __clz(considered));
+                        // error and index of the last evaluated row in visiting order
+                        const int ll = 31 - __clz(considered);
+                        surv_err = __shfl_sync(P2S_FULL, rerr, ll);
+                        surv_row = __shfl_sync(P2S_FULL, er, ll);
                         if (ck < best_key) {                  // strict '<' (:242)
                             best_key = ck;
                             bqx = __shfl_sync(P2S_FULL, rqx, cl);
@@ -401,23 +530,23 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                             bqz = __shfl_sync(P2S_FULL, rqz, cl);
                             b_valid = __shfl_sync(P2S_FULL, rvalid, cl);
 #pragma unroll
-                            for (int w = 0; w < 4; ++w) b_dig[w] = __shfl_sync(P2S_FULL, dig[w], cl);
+                            for (int w = 0; w < 4; ++w) b_dig[w] = __shfl_sync(P2S_FULL, edig[w], cl);
                         }
                     }
                 } else {
                     if (lane == 0) { T.any[warp] = considered; T.key[warp] = ck; }
-                    if (considered && lane == 31 - __clz(considered)) T.last[warp] = rerr;
+                    if (considered && lane == 31 - __clz(considered)) { T.last[warp] = rerr; T.lastrow[warp] = er; }
                     if (considered && lane == cl) {
                         T.q[warp][0] = rqx; T.q[warp][1] = rqy; T.q[warp][2] = rqz;
                         T.valid[warp] = rvalid;
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) T.dig[warp][w] = dig[w];
+                        for (int w = 0; w < 4; ++w) T.dig[warp][w] = edig[w];
                     }
                     __syncthreads();
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {            // visiting order: ascending warp, first wins ties
                         if (T.any[w]) {
-                            err_last = T.last[w];
+                            surv_err = T.last[w]; surv_row = T.lastrow[w];
                             if (T.key[w] < best_key) {
                                 best_key = T.key[w];
                                 bqx = T.q[w][0]; bqy = T.q[w][1]; bqz = T.q[w][2];
@@ -427,11 +556,56 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                             }
                         }
                     }
-                    __syncthreads();                          // scratch is rewritten by the next step
+                    __syncthreads();                          // scratch is rewritten by the next batch
                 }
-                // this lane's next row: + TEAM_THREADS in the mixed radix
-                radix_add<CMAX>(dig, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
+                if (hit) hit_row = surv_row;                  // the last considered row IS the first hit
+                qhead = (qhead + nb) % (unsigned)QCAP;
+                qn -= nb;
             }
+
+            // ---- end of the level: rows visited, and the error of the LAST evaluated row (:194 tests it against the threshold)
+            if (hit) {
+                err_last = surv_err;
+                hit_found = true;
+                if (ttid == 0) st_rows += (unsigned)(hit_row + 1ULL);
+            } else {
+                if (ttid == 0) st_rows += (unsigned)total_rows;
+                // a dropped row's error is above the threshold, whatever it is: +inf stands for it
+                unsigned long long dead = my_dead;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(P2S_FULL, dead, off);
+                    if (dead == kNoRow || (o != kNoRow && o > dead)) dead = o;
+                }
+                if (NW > 1) {
+                    if (lane == 0) T.deadrow[warp] = dead;
+                    __syncthreads();
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const unsigned long long o = T.deadrow[w];
+                        if (dead == kNoRow || (o != kNoRow && o > dead)) dead = o;
+                    }
+                    __syncthreads();
+                }
+                if (dead != kNoRow && (surv_row == kNoRow || dead > surv_row)) err_last = inf64();
+                else if (surv_row != kNoRow) err_last = surv_err;
+            }
+        }
+        // a filtered search that found no row under the threshold: the result is the minimum over ALL rows (:242-245) — again, unfiltered
+        bool again = false;
+        if (filter && !hit_found) {
+            if (NW == 1) {
+                again = __any_sync(P2S_FULL, redo);
+            } else {
+                if (ttid == 0) T.again = 0u;
+                __syncthreads();
+                if (redo) T.again = 1u;
+                __syncthreads();
+                again = T.again != 0u;
+                __syncthreads();
+            }
+        }
+        if (!again) break;
         }
 
         // ---- write the frame's result -----------------------------------------------------------------
@@ -442,7 +616,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             if (NW == 1) {
                 if (lane == 0) { a.out_stats[(long long)f * 2] = st_rows; a.out_stats[(long long)f * 2 + 1] = sc; }
             } else {
-                if (lane == 0) { atomicAdd(&T.rows, st_rows); atomicAdd(&T.cands, sc); }
+                if (lane == 0) { atomicAdd(&T.rows, ttid == 0 ? st_rows : 0u); atomicAdd(&T.cands, sc); }
                 __syncthreads();
                 if (ttid == 0) { a.out_stats[(long long)f * 2] = T.rows; a.out_stats[(long long)f * 2 + 1] = T.cands; }
             }
@@ -473,7 +647,8 @@ static cudaError_t launch_assoc_nw(const AssocLaunch &L, const AssocArgs &a0, in
     AssocArgs a = a0;
     constexpr int teams = (NW == 1) ? 4 : 1;
     constexpr int threads = (NW == 1) ? 128 : 32 * NW;
-    const size_t smem = (size_t)CMAX * 12 * sizeof(double) + (assoc_slab_bytes(CMAX, L.max_persons) + sizeof(TeamScratch<NW>)) * teams;
+    const size_t smem = (size_t)CMAX * 12 * sizeof(double) +
+                        (assoc_slab_bytes(CMAX, L.max_persons) + sizeof(TeamScratch<NW>) + assoc_queue_bytes(CMAX, NW)) * teams;
     auto kern = associate_kernel<CMAX, NW, false>;
     auto kern_wide = associate_kernel<CMAX, NW, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -519,6 +694,15 @@ cudaError_t launch_associate(const AssocLaunch &L, int *grid_out) {
     a.out_err = L.out_err; a.out_comb = L.out_comb; a.out_Q = L.out_Q; a.out_stats = L.out_stats;
     a.tile_counter = L.tile_counter;
     a.wide_flags = L.wide_flags;
+    a.bnd_k1 = 0.0; a.bnd_k2 = 0.0;
+    for (int c = 0; c < L.n_cams; ++c) {
+        const double *p2 = L.P + c * 12 + 8;
+        a.bnd_k1 = std::fmax(a.bnd_k1, std::sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]));
+        a.bnd_k2 = std::fmax(a.bnd_k2, std::fabs(p2[3]));
+    }
+    a.bnd_k1 *= 1.0 + 1e-12; a.bnd_k2 *= 1.0 + 1e-12;
+    if (!(a.bnd_k1 < INFINITY) || !(a.bnd_k2 < INFINITY)) a.bnd_k1 = a.bnd_k2 = INFINITY;   // NaN / inf matrices: bound 0, no row dropped
+    a.search_mode = L.search_mode;
     if (L.n_cams <= 4) return launch_assoc<4>(L, a, grid_out);
     if (L.n_cams <= 8) return launch_assoc<8>(L, a, grid_out);
     if (L.n_cams <= 16) return launch_assoc<16>(L, a, grid_out);

@@ -46,6 +46,7 @@ struct p2s_handle {
     int assoc_team = 0;
     long long chunk_units = kChunkUnitsDefault;
     int bulk_out = 0;
+    int search_mode = 0;                               // p2s_set_search_mode
     int host_mode = 0;                                 // 0 auto, 1 pipeline, 2 zero-copy (p2s_set_host_mode)
     long long launches = 0;
     int last_grid = 0;
@@ -217,6 +218,7 @@ int enqueue_associate(p2s_handle *h, const void *obs, const int32_t *count, cons
     L.out_err = err; L.out_comb = comb; L.out_Q = Q; L.out_stats = stats;
     L.tile_counter = next_counter(h);
     L.wide_flags = (uint8_t *)wflags->p;
+    L.search_mode = h->search_mode;
     L.stream = stream;
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 4 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_associate(L, &h->last_grid));
@@ -330,6 +332,12 @@ int p2s_set_output_mode(p2s_handle *h, int mode) {
 int p2s_set_chunk_units(p2s_handle *h, long long units) {
     if (!h || (units != 0 && (units < 32 || units > (1LL << 26)))) return P2S_EINVAL;
     h->chunk_units = (units + 31) & ~31LL;            // whole tiles, keeps the chunk's planes 16-byte aligned
+    return P2S_OK;
+}
+
+int p2s_set_search_mode(p2s_handle *h, int mode) {
+    if (!h || (mode != 0 && mode != 1)) return P2S_EINVAL;
+    h->search_mode = mode;
     return P2S_OK;
 }
 

@@ -51,6 +51,7 @@ struct AssocLaunch {
     uint32_t *out_stats;
     unsigned int *tile_counter;   // four words, zeroed on the stream before the launch
     uint8_t *wide_flags;          // device, n_frames bytes of scratch
+    int search_mode = 0;          // 0 rows filtered by their lower bound, 1 exhaustive (p2s_set_search_mode)
     cudaStream_t stream;
 };
 

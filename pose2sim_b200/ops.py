@@ -105,6 +105,11 @@ class Engine:
         "zero_copy" (raises when the buffers are not pinned)."""
         _lib.check(self.h, self.lib.p2s_set_host_mode(self.h, {"auto": 0, "pipeline": 1, "zero_copy": 2}.get(mode, mode)))
 
+    def set_search_mode(self, mode):
+        """Single-person association search: "filtered" (default: candidates whose lower bound is above the threshold are
+        not solved; same results) or "exhaustive" (every row solved and re-projected)."""
+        _lib.check(self.h, self.lib.p2s_set_search_mode(self.h, {"filtered": 0, "exhaustive": 1}.get(mode, mode)))
+
     def set_output_mode(self, mode):
         """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`)."""
         _lib.check(self.h, self.lib.p2s_set_output_mode(self.h, {"vector": 0, "bulk": 1}.get(mode, mode)))
