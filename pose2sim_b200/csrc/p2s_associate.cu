@@ -52,9 +52,16 @@ struct AssocArgs {
     int search_mode;               // 0 = rows filtered by their lower bound, 1 = every row solved and re-projected
 };
 
+// Blocks of camera PAIRS: entry (j, d0, d1) = block of (camera 2j, person d0) + block of (camera 2j + 1, person d1), each only
+// if that detection is active — a row's normal matrix is then four 10-entry additions instead of eight with a test per
+// camera.  Kept when the table is small (np^2 entries per pair), else the per-camera blocks are summed.
+__host__ __device__ inline int assoc_pair_entries(int cmax, int np) {
+    return ((size_t)(cmax / 2) * np * np * 10 * sizeof(double) <= 12288) ? np * np : 0;
+}
 __host__ __device__ inline size_t assoc_slab_bytes(int cmax, int np) {
     return (size_t)cmax * np * (sizeof(float4) + 10 * sizeof(double)) + 4 * (size_t)cmax * sizeof(uint32_t) +
-           (size_t)(cmax / 2) * 256;          // per camera PAIR: byte of two packed digits -> active / NaN bits of the pair
+           (size_t)(cmax / 2) * 256 +        // per camera PAIR: byte of two packed digits -> active / NaN bits of the pair
+           (size_t)(cmax / 2) * assoc_pair_entries(cmax, np) * 10 * sizeof(double);
 }
 // row queue of a team: 2 x its threads entries of {row index, candidate mask, packed person digits}
 __host__ __device__ inline size_t assoc_queue_bytes(int cmax, int nw) {
@@ -77,7 +84,7 @@ __device__ __forceinline__ void radix_add(uint32_t (&dig)[4], uint32_t v, const 
     uint32_t carry = v;
 #pragma unroll
     for (int c = CMAX - 1; c >= 0; --c) {
-        if (c < C) {
+        if (c < C && carry != 0u) {                             // the carry of a small step dies out after a few cameras
             const uint32_t n = s_n[c] ? s_n[c] : 1u;
             const uint32_t t = digit_of<CMAX>(dig, c) + carry;
             const uint32_t q = (t * s_inv[c]) >> 16;
@@ -86,6 +93,21 @@ __device__ __forceinline__ void radix_add(uint32_t (&dig)[4], uint32_t v, const 
             carry = q;
         }
     }
+}
+
+// ---- the same step for rigs of at most 8 cameras, all cameras at once --------------------------------------------------
+// The row's digits live in ONE word with the last camera (the fastest digit) in the lowest nibble, each digit stored with
+// the bias 16 - n_c: a nibble then overflows exactly when its digit reaches n_c, so the binary carry of an ordinary
+// 32-bit addition IS the mixed-radix carry.  Nibbles that overflowed come out unbiased and get their bias back.
+__device__ __forceinline__ uint32_t nibble_reverse(uint32_t x) {
+    x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+    return __byte_perm(x, 0u, 0x0123);
+}
+__device__ __forceinline__ uint32_t swar_step(uint32_t rw, uint32_t stepw, uint32_t biasw) {
+    const uint32_t sum = rw + stepw;
+    const uint32_t cout = (rw & stepw) | ((rw | stepw) & ~sum);      // bit i: carry out of bit i
+    const uint32_t ov = (cout >> 3) & 0x11111111u;                    // nibbles that overflowed
+    return sum + (biasw & (ov * 15u));
 }
 
 // Team = NW warps that share one frame.  NW = 1: a warp per frame (4 frames per CTA) — best when there are
@@ -168,6 +190,8 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
     // digits: bit 0 / 1 = camera 2j / 2j + 1 active, bit 2 / 3 = its chosen detection holds a NaN (one LDS per pair and row
     // instead of a shift-and-test chain per camera: that chain was 10 % of the kernel's stall samples)
     unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_nan + CMAX);
+    const int NPP = assoc_pair_entries(CMAX, NP);             // 0: no pair blocks
+    double *spb = reinterpret_cast<double *>(s_pair + (CMAX / 2) * 256);                          // [CMAX / 2][NPP][10]
     TeamScratch<NW> &T = *reinterpret_cast<TeamScratch<NW> *>(base + assoc_slab_bytes(CMAX, NP));
     unsigned long long *q_row = reinterpret_cast<unsigned long long *>(base + assoc_slab_bytes(CMAX, NP) + sizeof(TeamScratch<NW>));
     unsigned long long *q_mask = q_row + QCAP;                // candidates of the row that need their exact error
@@ -259,7 +283,38 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             if (c1 < C && s_n[c1]) t |= (((s_ok[c1] >> d1) & 1u) << 1) | (((s_ok[c1] >> d1) & (s_nan[c1] >> d1) & 1u) << 3);
             s_pair[i] = (unsigned char)t;
         }
+        for (int i = ttid; i < (CMAX / 2) * NPP; i += TEAM_THREADS) {
+            const int j = i / NPP, rem = i - j * NPP, d1 = rem / NP, d0 = rem - d1 * NP, c0 = 2 * j, c1 = c0 + 1;
+            const bool a0 = c0 < C && s_n[c0] && ((s_ok[c0] >> d0) & 1u), a1 = c1 < C && s_n[c1] && ((s_ok[c1] >> d1) & 1u);
+            const double *b0 = sblk + (size_t)(c0 * NP + d0) * 10, *b1 = sblk + (size_t)(c1 * NP + d1) * 10;
+#pragma unroll
+            for (int e = 0; e < 10; ++e) spb[(size_t)i * 10 + e] = (a0 ? b0[e] : 0.0) + (a1 ? b1[e] : 0.0);
+        }
         team_sync<NW>();
+        // a row's normal matrix: the sum of its active detections' blocks (ascending camera order)
+        auto row_matrix = [&](Sym4 &Mrow, const uint32_t (&dg)[4], uint32_t active) {
+            sym4_zero(Mrow);
+            if (NPP) {
+#pragma unroll
+                for (int j = 0; j < CMAX / 2; ++j) {
+                    const uint32_t byte = (dg[j >> 2] >> ((j & 3) * 8)) & 255u;
+                    const double2 *src = reinterpret_cast<const double2 *>(spb + (size_t)(j * NPP + (int)((byte & 15u) + (uint32_t)NP * (byte >> 4))) * 10);
+                    const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                    Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
+                    Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if ((active >> c) & 1u) {
+                        const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(dg, c)) * 10);
+                        const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                        Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
+                        Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
+                    }
+                }
+            }
+        };
         uint32_t present = 0;
         unsigned long long total_rows = 1;
         bool overflow = false;
@@ -271,6 +326,14 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
         }
         const int n_missing = C - __popc(present);
 
+        // digit stepping for <= 8 cameras (swar_step): bias word and the digits of one step, last camera in the lowest nibble
+        uint32_t biasw = 0u, stepw = 0u;
+        if (CMAX <= 8) {
+            uint32_t sd[4] = {0, 0, 0, 0};
+            radix_add<CMAX>(sd, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
+            stepw = nibble_reverse(sd[0] << (4 * (8 - C)));
+            for (int c = 0; c < C; ++c) biasw |= (16u - (s_n[c] ? s_n[c] : 1u)) << (4 * (C - 1 - c));
+        }
         // replicated in every thread of the team (all threads apply the same updates)
         double err_last = inf64();
         // key of the global best.  The reference starts from error = +inf and replaces it on a strict '<' (:242-245), so a
@@ -302,6 +365,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
             bool hit = false;
             uint32_t dig[4] = {0, 0, 0, 0};                   // 4 bits per camera: the person indices of the row I scan
             radix_add<CMAX>(dig, (uint32_t)ttid, s_n, s_inv, C);
+            uint32_t rw = (CMAX <= 8) ? nibble_reverse(dig[0] << (4 * (8 - C))) + biasw : 0u;   // the same, biased, reversed
             unsigned long long rbase = 0;                     // next row block to scan
             unsigned int qhead = 0, qn = 0;                   // the team's row queue (ring): team-uniform
             unsigned long long my_dead = kNoRow;              // my last row that counts as evaluated but was dropped unsolved
@@ -328,16 +392,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                                 smask = ~0ULL;
                             } else {
                                 Sym4 Mrow;
-                                sym4_zero(Mrow);
-#pragma unroll
-                                for (int c = 0; c < CMAX; ++c) {
-                                    if ((active >> c) & 1u) {
-                                        const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(dig, c)) * 10);
-                                        const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                                        Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
-                                        Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
-                                    }
-                                }
+                                row_matrix(Mrow, dig, active);
                                 bool dead_eval = false;       // some candidate has a definite error (so the row is an evaluated one)
                                 for (uint32_t ci = 0; ci < ncand_all; ++ci) {
                                     const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
@@ -378,9 +433,14 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                     if (NW > 1) {
                         if (lane == 0) T.wcount[warp] = tot;
                         __syncthreads();
-                        tot = 0;
+                        uint32_t inc = lane < NW ? T.wcount[lane] : 0u;         // inclusive scan over the team's warps
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) { if (w < warp) off += T.wcount[w]; tot += T.wcount[w]; }
+                        for (int d = 1; d < NW; d <<= 1) {
+                            const uint32_t o = __shfl_up_sync(P2S_FULL, inc, d);
+                            if (lane >= d) inc += o;
+                        }
+                        tot = __shfl_sync(P2S_FULL, inc, NW - 1);
+                        off = warp ? __shfl_sync(P2S_FULL, inc, warp - 1) : 0u;
                     }
                     if (survive) {
                         const unsigned int slot = (qhead + qn + off + (unsigned)__popc(sb & ((1u << lane) - 1u))) % (unsigned)QCAP;
@@ -392,7 +452,12 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                     qn += tot;
                     team_sync<NW>();                          // queue visible; T.wcount free for the next step
                     rbase += TEAM_THREADS;
-                    radix_add<CMAX>(dig, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
+                    if (CMAX <= 8) {
+                        rw = swar_step(rw, stepw, biasw);
+                        dig[0] = nibble_reverse(rw - biasw) >> (4 * (8 - C));
+                    } else {
+                        radix_add<CMAX>(dig, (uint32_t)TEAM_THREADS, s_n, s_inv, C);
+                    }
                 }
                 if (qn == 0) break;                           // every row of the level has been looked at
 
@@ -419,16 +484,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                 if (row_ok && na >= a.min_cams && k <= na) {
                     // the row's normal matrix: sum of its active cameras' blocks, ascending camera order
                     Sym4 Mrow;
-                    sym4_zero(Mrow);
-#pragma unroll
-                    for (int c = 0; c < CMAX; ++c) {
-                        if ((active >> c) & 1u) {
-                            const double2 *src = reinterpret_cast<const double2 *>(sblk + (size_t)(c * NP + digit_of<CMAX>(edig, c)) * 10);
-                            const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                            Mrow.m00 += v0.x; Mrow.m01 += v0.y; Mrow.m02 += v1.x; Mrow.m03 += v1.y; Mrow.m11 += v2.x;
-                            Mrow.m12 += v2.y; Mrow.m13 += v3.x; Mrow.m22 += v3.y; Mrow.m23 += v4.x; Mrow.m33 += v4.y;
-                        }
-                    }
+                    row_matrix(Mrow, edig, active);
                     for (uint32_t ci = 0; ci < ncand_all; ++ci) {
                         if (masked && !((emask >> ci) & 1ULL)) continue;      // its bound is above the threshold: not a hit
                         const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
