@@ -124,7 +124,7 @@ struct alignas(16) TeamScratch {  // per team, in shared memory (only used when 
     uint32_t dig[NW][4];
     unsigned int frame;
     unsigned int rows, cands;
-    uint32_t wcount[NW];          // row filter: survivors per warp of a scan step
+    uint32_t wcount[2][NW];       // row filter: survivors per warp of a scan step (two buffers, alternating: one barrier per step)
     unsigned long long lastrow[NW];   // row index of T.last[w]
     unsigned long long deadrow[NW];   // level end: last row of warp w that counts as evaluated but was dropped unsolved
     unsigned int again;           // the frame has to be searched again without the filter
@@ -394,8 +394,29 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                                 Sym4 Mrow;
                                 row_matrix(Mrow, dig, active);
                                 bool dead_eval = false;       // some candidate has a definite error (so the row is an evaluated one)
+                                // can the candidate with normal matrix M and m cameras be under the threshold?  (0 no, 1 maybe, 2 NaN)
+                                auto maybe_hit = [&](const Sym4 &M, int m) -> int {
+                                    double lam, x0, x1, x2;
+                                    SecularBound B;
+                                    if (secular_first(M, lam, x0, x1, x2, B) == 2) return 2;  // NaN candidate: ignored like in the exact pass
+                                    // E^2 >= s / ((k1 |q0| + k2)^2 + k1^2 s tau) / (m whi)^2, see the comment above the kernel
+                                    const double s_lo = fmax(fma(-2e-9, M.m33, B.s), 0.0);   // rounding of c - b.A^-1 b (|b.A^-1 b| <= c)
+                                    const double d0 = fma(a.bnd_k1, sqrt_fast(B.g - 1.0), a.bnd_k2);
+                                    const double mw = whi_d * (double)m;
+                                    const double den = fma(d0, d0, k1sq * s_lo * B.tau) * (mw * mw);
+                                    return (s_lo > thr2 * den) ? 0 : 1;                       // NaN compares false: then it is solved
+                                };
+                                if (k == 0) {                 // one candidate: all active cameras
+                                    if (na < 2) dead_eval = na == 1;                          // +inf (na == 0: NaN, ignored)
+                                    else if (nanact) dead_eval = true;                        // +inf
+                                    else {
+                                        const int h = maybe_hit(Mrow, na);
+                                        if (h == 0) { dead_eval = true; redo = true; }
+                                        else if (h == 1) smask = 1ULL;
+                                    }
+                                } else
                                 for (uint32_t ci = 0; ci < ncand_all; ++ci) {
-                                    const uint32_t cm = (k == 0) ? 0u : tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
+                                    const uint32_t cm = tabled ? __ldg(table + ci) : unrank_subset(C, k, ci);
                                     if (cm & ~active) continue;
                                     const uint32_t valid = active & ~cm;
                                     const int m = __popc(valid);
@@ -411,16 +432,9 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                                         M.m00 -= v0.x; M.m01 -= v0.y; M.m02 -= v1.x; M.m03 -= v1.y; M.m11 -= v2.x;
                                         M.m12 -= v2.y; M.m13 -= v3.x; M.m22 -= v3.y; M.m23 -= v4.x; M.m33 -= v4.y;
                                     }
-                                    double lam, x0, x1, x2;
-                                    SecularBound B;
-                                    if (secular_first(M, lam, x0, x1, x2, B) == 2) continue;  // NaN candidate: ignored like in the exact pass
-                                    // E^2 >= s / ((k1 |q0| + k2)^2 + k1^2 s tau) / (m whi)^2, see the comment above the kernel
-                                    const double s_lo = fmax(fma(-2e-9, M.m33, B.s), 0.0);   // rounding of c - b.A^-1 b (|b.A^-1 b| <= c)
-                                    const double d0 = fma(a.bnd_k1, sqrt_fast(B.g - 1.0), a.bnd_k2);
-                                    const double mw = whi_d * (double)m;
-                                    const double den = fma(d0, d0, k1sq * s_lo * B.tau) * (mw * mw);
-                                    if (s_lo > thr2 * den) { dead_eval = true; redo = true; }  // false for NaN: then it is solved
-                                    else smask |= masked ? (1ULL << ci) : ~0ULL;              // needs its exact error
+                                    const int h = maybe_hit(M, m);
+                                    if (h == 0) { dead_eval = true; redo = true; }
+                                    else if (h == 1) smask |= masked ? (1ULL << ci) : ~0ULL;  // needs its exact error
                                 }
                                 if (smask == 0ULL && dead_eval) my_dead = r;
                             }
@@ -431,9 +445,10 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                     const uint32_t sb = __ballot_sync(P2S_FULL, survive);
                     unsigned int off = 0, tot = (unsigned)__popc(sb);
                     if (NW > 1) {
-                        if (lane == 0) T.wcount[warp] = tot;
+                        uint32_t *wc = T.wcount[(unsigned)(rbase / (unsigned)TEAM_THREADS) & 1u];
+                        if (lane == 0) wc[warp] = tot;
                         __syncthreads();
-                        uint32_t inc = lane < NW ? T.wcount[lane] : 0u;         // inclusive scan over the team's warps
+                        uint32_t inc = lane < NW ? wc[lane] : 0u;               // inclusive scan over the team's warps
 #pragma unroll
                         for (int d = 1; d < NW; d <<= 1) {
                             const uint32_t o = __shfl_up_sync(P2S_FULL, inc, d);
@@ -450,7 +465,6 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                         for (int w = 0; w < DW; ++w) q_dig[slot * DW + w] = dig[w];
                     }
                     qn += tot;
-                    team_sync<NW>();                          // queue visible; T.wcount free for the next step
                     rbase += TEAM_THREADS;
                     if (CMAX <= 8) {
                         rw = swar_step(rw, stepw, biasw);
@@ -460,6 +474,7 @@ associate_kernel(const CamParams<CMAX> cams, const AssocArgs a) {
                     }
                 }
                 if (qn == 0) break;                           // every row of the level has been looked at
+                team_sync<NW>();                              // the queued rows are visible to their evaluators
 
                 // ---- exact evaluation of the first batch of queued rows, in row order -------------------------------
                 const unsigned int nb = qn < (unsigned)TEAM_THREADS ? qn : (unsigned)TEAM_THREADS;
