@@ -104,9 +104,72 @@ def proposals_from_rows(rows, min_cams):
     return prop if len(prop) else np.array([], dtype=float)
 
 
+def proposals_from_rows_batch(rows, n, min_cams):
+    """`proposals_from_rows` for all frames at once: rows [F, NM, C] integers (-1 = no detection), n[f] = detections of
+    frame f.  Same results, frame by frame (tests/test_dropin_host.py compares them on random tables): the keys, the stable
+    sort that yields `np.unique`'s sorted unique rows / first occurrences / counts, and the duplicate and min-cameras
+    filters run on padded [F, ...] arrays; only `np.argsort(counts)[::-1]` — whose tie order is NumPy's own — stays a call
+    per frame on exactly the counts array the per-frame function passes."""
+    rows = np.asarray(rows)
+    F, NM, C = rows.shape
+    n = np.asarray(n, dtype=np.int64)
+    empty = np.array([], dtype=float)
+    if F == 0:
+        return []
+    valid = np.arange(NM)[None, :] < n[:, None]
+    r64 = rows.astype(np.int64)
+    base = int(r64[valid].max(initial=-1)) + 2                  # any base > max + 1 keeps the lexicographic order of the rows
+    if NM == 0 or float(base) ** C >= 2.0 ** 62:
+        return [proposals_from_rows(rows[f, :n[f]], min_cams) for f in range(F)]
+    weights = base ** np.arange(C - 1, -1, -1, dtype=np.int64)
+    sentinel = np.iinfo(np.int64).max
+    keys = np.where(valid, (r64 + 1) @ weights, sentinel)
+    order = np.argsort(keys, axis=1, kind="stable")             # equal keys keep their index order: first = first occurrence
+    sk = np.take_along_axis(keys, order, axis=1)
+    start = np.ones((F, NM), bool)
+    start[:, 1:] = sk[:, 1:] != sk[:, :-1]
+    start &= sk != sentinel                                      # run starts of the sorted valid keys = the unique rows, ascending
+    n_unique = start.sum(axis=1)
+    U = int(n_unique.max(initial=0))
+    if U == 0:
+        return [empty for _ in range(F)]
+    fi, pos = np.nonzero(start)                                  # row-major: frame by frame, ascending key
+    first_of_frame = np.concatenate([[0], np.cumsum(n_unique)[:-1]])
+    slot = np.arange(len(fi)) - first_of_frame[fi]
+    run_end = np.empty(len(fi), np.int64)                        # position after the run: next start of the frame, or n[f]
+    run_end[:-1] = pos[1:]
+    run_end[-1] = 0
+    last = np.ones(len(fi), bool)
+    last[:-1] = fi[1:] != fi[:-1]
+    run_end[last] = n[fi[last]]
+    counts_flat = run_end - pos
+    first_flat = order[fi, pos]                                  # np.unique's return_index
+    # order by multiplicity: NumPy's own argsort on each frame's counts (ties are its business), then padded [F, U, C]
+    bounds = np.concatenate([first_of_frame, [len(fi)]]).tolist()
+    sel = np.empty(len(fi), np.int64)
+    for f in np.flatnonzero(n_unique).tolist():
+        a, b = bounds[f], bounds[f + 1]
+        sel[a:b] = first_flat[a:b][np.argsort(counts_flat[a:b])[::-1]]
+    prop = np.full((F, U, C), -1, np.int64)
+    filled = np.zeros((F, U), bool)
+    prop[fi, slot] = r64[fi, sel]
+    filled[fi, slot] = True
+    # a row is dropped when any of its entries equals the entry of ANY earlier row in the same column (:541-542; -1 never matches)
+    seen = prop >= 0
+    same = ((prop[:, :, None, :] == prop[:, None, :, :]) & seen[:, :, None, :]).any(axis=3)
+    lower = np.tril(np.ones((U, U), bool), -1)
+    keep = filled & ~(same & lower[None]).any(axis=2) & (seen.sum(axis=2) >= min_cams)
+    propf = np.where(seen, prop, 0).astype(float)
+    propf[~seen] = np.nan
+    kept = keep.sum(axis=1)
+    out = np.split(propf[keep], np.cumsum(kept)[:-1])           # row-major: frame by frame, in proposal order
+    for f in np.flatnonzero(kept == 0).tolist():
+        out[f] = empty                                          # what the per-frame function returns for "nobody"
+    return out
+
+
 def associate_frames(engine, obs, count, models, max_distance, min_affinity, min_cams):
     """All frames in ONE device call; returns the list of proposals per frame."""
     n_max = max(1, int(count.sum(axis=1).max(initial=0)))
     out = engine.associate_multi_host(obs, count, models, max_distance, min_affinity, n_max=n_max)
-    n = count.sum(axis=1)
-    return [proposals_from_rows(out["rows"][f, :n[f]], min_cams) for f in range(len(count))]
+    return proposals_from_rows_batch(out["rows"], count.sum(axis=1), min_cams)
