@@ -741,6 +741,7 @@ static int enqueue_mp(p2s_handle *h, const float *obs, const int32_t *count, con
     p2s::MpLaunch L;
     L.obs = obs; L.count = count; L.cams = cams; L.n_frames = n_frames; L.n_cams = n_cams; L.max_persons = max_persons;
     L.n_joints = n_joints; L.n_max = n_max; L.sm_count = h->prop.multiProcessorCount; L.d_max = d_max;
+    L.smem_per_sm = h->prop.sharedMemPerMultiprocessor;
     L.min_affinity = min_affinity; L.out_rows = rows; L.out_affinity = aff; L.out_iters = iters;
     L.tile_counter = next_counter(h);
     L.stream = stream;

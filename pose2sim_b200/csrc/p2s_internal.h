@@ -61,6 +61,7 @@ struct MpLaunch {
     const p2s_camera_model *cams; // host: K, R, T are used
     long long n_frames;
     int n_cams, max_persons, n_joints, n_max, sm_count;
+    size_t smem_per_sm;           // cudaDeviceProp::sharedMemPerMultiprocessor: decides one or two resident frames per SM
     double d_max, min_affinity;
     int8_t *out_rows;             // [n_frames][n_max][n_cams]
     double *out_affinity;         // [n_frames][n_max][n_max] or null

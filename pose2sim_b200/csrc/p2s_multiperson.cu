@@ -20,6 +20,7 @@
 // U S V^T with S shrunk by tau is then sum_k max(s_k - tau, 0)/s_k a_k v_k^T — only the few columns above
 // tau (about one per person) contribute.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "p2s_math.cuh"
@@ -78,24 +79,45 @@ __device__ __forceinline__ bool joint_ray(const RayCam &c, float fx, float fy, f
     return s == s;                                                     // any NaN -> the joint carries no weight
 }
 
-__global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams cams, const MpArgs a) {
+// Shared-memory layout: [X packed][W packed][Y][sig][red][views, cum, flags][schedule] then the union region
+// {A, V, Qp | observations}.  Byte offset of the union region (16-byte aligned):
+__host__ __device__ __forceinline__ size_t mp_union_offset(int n_max) {
+    const size_t LD = (size_t)(n_max | 1), tri = ((size_t)n_max * (n_max + 1)) >> 1;
+    size_t b = (2 * tri + (size_t)n_max * LD + (size_t)n_max + kMpWarps) * sizeof(double) +
+               ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + (size_t)(n_max | 1) * 32 * sizeof(unsigned short);
+    return (b + 15) & ~(size_t)15;
+}
+
+// X (the iterate) and W (w_sparse - affinity) are symmetric BIT FOR BIT — both triangles are written with the same
+// value — so they are stored as packed upper triangles; the frame's observations are only read while the affinity is
+// built and share their region with A, V and Qp, which are first written after it.  That brings a frame of 48
+// detections from 131 KB to 98 KB of shared memory: TWO frames are resident per SM (RESIDENT = 2, 64 registers),
+// and one frame's round barriers and rotation chains are covered by the other's work.
+__device__ __forceinline__ int tri_index(int i, int j, int N2) {       // N2 = 2 N - 1; (i, j) and (j, i) -> the same slot
+    const int a = min(i, j), b = max(i, j);
+    return ((a * (N2 - a)) >> 1) + b;                                   // a N - a (a - 1) / 2 + (b - a)
+}
+
+template <int RESIDENT>
+__global__ void __launch_bounds__(kMpThreads, RESIDENT) mp_associate_kernel(const RayCams cams, const MpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = a.n_cams, NP = a.max_persons, J = a.n_joints, NM = a.n_max;
     const int LD = NM | 1;                                              // odd leading dimension: fewer bank conflicts
-    double *X = reinterpret_cast<double *>(smem_raw);
-    double *Y = X + (size_t)NM * LD;
-    double *W = Y + (size_t)NM * LD;
-    double *A = W + (size_t)NM * LD;                                   // column-major: A[col * LD + row]
-    double *V = A + (size_t)NM * LD;
-    double *Qp = V + (size_t)NM * LD;
-    double *sig = Qp + (size_t)NM * LD;                                // NM shrink factors
+    const int TRI = (NM * (NM + 1)) >> 1, N2 = 2 * NM - 1;
+    double *X = reinterpret_cast<double *>(smem_raw);                  // packed upper triangle, tri_index
+    double *W = X + TRI;                                               // packed upper triangle
+    double *Y = W + TRI;
+    double *sig = Y + (size_t)NM * LD;                                 // NM shrink factors
     double *red = sig + NM;                                            // one per warp
-    float *sobs = reinterpret_cast<float *>(red + kMpWarps);           // [N][3 J]
-    int *s_view = reinterpret_cast<int *>(sobs + (size_t)NM * 3 * J);  // NM: view of each detection
+    int *s_view = reinterpret_cast<int *>(red + kMpWarps);             // NM: view of each detection
     int *s_cum = s_view + NM;                                          // C + 1
     int *s_flag = s_cum + P2S_MAX_CAMS + 1;                            // [0] frame, [1] rotations in the sweep
     unsigned short *s_sched = reinterpret_cast<unsigned short *>(s_flag + 2);   // [rounds][32] pair schedule: p | q << 8, 0xffff = idle
+    double *A = reinterpret_cast<double *>(smem_raw + mp_union_offset(NM));     // column-major: A[col * LD + row]
+    double *V = A + (size_t)NM * LD;
+    double *Qp = V + (size_t)NM * LD;
+    float *sobs = reinterpret_cast<float *>(A);                        // [N][3 J], dead before A / V / Qp are born
 
     for (;;) {
         __syncthreads();
@@ -151,15 +173,17 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                 if (d > a.d_max) d = a.d_max;
                 aff = 1.0 - d / a.d_max;
             }
-            X[i * LD + j] = aff; X[j * LD + i] = aff;
+            X[tri_index(i, j, N2)] = aff;
         }
         __syncthreads();
         // matchSVT start (:468-476): zero diagonal, Y = 0, W = w_sparse - X
         for (int e = tid; e < N * N; e += kMpThreads) {
             const int i = e / N, j = e - i * N;
-            if (i == j) X[i * LD + j] = 0.0;
             Y[i * LD + j] = 0.0;
-            W[i * LD + j] = a.w_sparse - ((i == j) ? 0.0 : X[i * LD + j]);
+            if (i > j) continue;
+            const int t = tri_index(i, j, N2);
+            if (i == j) X[t] = 0.0;
+            W[t] = a.w_sparse - ((i == j) ? 0.0 : X[t]);
         }
         __syncthreads();
 
@@ -192,7 +216,7 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
             // two sweeps finish where a cold start needs eight to ten.  B = (B V) V^T, so the SVD is the same.
             for (int e = tid; e < N * N; e += kMpThreads) {
                 const int i = e / N, j = e - i * N;
-                const double b = X[i * LD + j] + Y[i * LD + j] * 1.0 / mu;
+                const double b = X[tri_index(i, j, N2)] + Y[i * LD + j] * 1.0 / mu;
                 Qp[i * LD + j] = b;
                 if (it == 0) {
                     A[j * LD + i] = b;
@@ -320,14 +344,16 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                 const int i = e / N, j = e - i * N;
                 if (i > j) continue;
                 const bool same = s_view[i] == s_view[j];
-                double xij = Qp[i * LD + j] - (W[i * LD + j] + Y[i * LD + j]) / mu;
-                double xji = Qp[j * LD + i] - (W[j * LD + i] + Y[j * LD + i]) / mu;
+                const int t = tri_index(i, j, N2);
+                const double wij = W[t];
+                double xij = Qp[i * LD + j] - (wij + Y[i * LD + j]) / mu;
+                double xji = Qp[j * LD + i] - (wij + Y[j * LD + i]) / mu;
                 if (same) { xij = 0.0; xji = 0.0; }
                 if (i == j) { xij = 1.0; xji = 1.0; }
                 if (xij < 0.0) xij = 0.0; if (xij > 1.0) xij = 1.0;
                 if (xji < 0.0) xji = 0.0; if (xji > 1.0) xji = 1.0;
                 const double xs = (xij + xji) / 2.0;
-                const double oij = X[i * LD + j], oji = X[j * LD + i];
+                const double oij = X[t], oji = oij;
                 const double eij = xs - Qp[i * LD + j], eji = xs - Qp[j * LD + i];
                 Y[i * LD + j] += mu * eij;
                 pr += eij * eij;
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
                     pr += eji * eji;
                     dr += (xs - oji) * (xs - oji);
                 }
-                X[i * LD + j] = xs; X[j * LD + i] = xs;
+                X[t] = xs;
             }
             const double pres = sqrt(block_sum(pr, red)) / N;
             const double dres = mu * sqrt(block_sum(dr, red)) / N;
@@ -350,8 +376,11 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
         // ---- min_affinity threshold (:800) and the per-row / per-view arg-max (:526-533) ---------------------------
         for (int e = tid; e < N * N; e += kMpThreads) {
             const int i = e / N, j = e - i * N;
-            if (X[i * LD + j] < a.min_affinity) X[i * LD + j] = 0.0;
-            if (a.out_affinity) a.out_affinity[(f * NM + i) * NM + j] = X[i * LD + j];
+            if (i > j) continue;
+            const int t = tri_index(i, j, N2);
+            double x = X[t];
+            if (x < a.min_affinity) { x = 0.0; X[t] = 0.0; }
+            if (a.out_affinity) { a.out_affinity[(f * NM + i) * NM + j] = x; a.out_affinity[(f * NM + j) * NM + i] = x; }
         }
         __syncthreads();
         for (int e = tid; e < N * C; e += kMpThreads) {
@@ -359,7 +388,7 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
             int best = -1;
             double bv = 0.0;
             for (int j = s_cum[v]; j < s_cum[v + 1]; ++j) {
-                const double x = X[r * LD + j];
+                const double x = X[tri_index(r, j, N2)];
                 if (x > bv) { bv = x; best = j - s_cum[v]; }                // first maximum, and only if > 0
             }
             a.out_rows[(f * NM + r) * C + v] = (int8_t)best;
@@ -370,8 +399,28 @@ __global__ void __launch_bounds__(kMpThreads) mp_associate_kernel(const RayCams 
 
 size_t mp_smem_bytes(int n_max, int n_joints) {
     const size_t LD = (size_t)(n_max | 1);
-    return 6 * (size_t)n_max * LD * sizeof(double) + ((size_t)n_max + kMpWarps) * sizeof(double) + (size_t)n_max * 3 * n_joints * sizeof(float) +
-           ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + (size_t)(n_max | 1) * 32 * sizeof(unsigned short) + 16;
+    const size_t mats = 3 * (size_t)n_max * LD * sizeof(double);                 // A, V, Qp
+    const size_t obs = (size_t)n_max * 3 * n_joints * sizeof(float);             // alive only before them
+    return mp_union_offset(n_max) + (mats > obs ? mats : obs);
+}
+
+template <int RESIDENT>
+static cudaError_t launch_mp_variant(const RayCams &cams, const MpArgs &a, size_t smem, int sm_count, cudaStream_t stream, int *grid_out) {
+    cudaError_t e = cudaFuncSetAttribute(mp_associate_kernel<RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mp_associate_kernel<RESIDENT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_associate_kernel<RESIDENT>, kMpThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > RESIDENT) per_sm = RESIDENT;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > a.n_frames) grid = a.n_frames;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    mp_associate_kernel<RESIDENT><<<(unsigned)grid, kMpThreads, smem, stream>>>(cams, a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out) {
@@ -397,20 +446,13 @@ cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out) {
     a.max_iter = 20; a.w_rank = 50.0; a.tol = 1e-4; a.w_sparse = 0.1;            // matchSVT's call-site constants (:799)
     a.out_rows = L.out_rows; a.out_affinity = L.out_affinity; a.out_iters = L.out_iters; a.tile_counter = L.tile_counter;
     const size_t smem = mp_smem_bytes(L.n_max, L.n_joints);
-    cudaError_t e = cudaFuncSetAttribute(mp_associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mp_associate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_associate_kernel, kMpThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)L.sm_count * per_sm;
-    if (grid > L.n_frames) grid = L.n_frames;
-    if (grid < 1) grid = 1;
-    if (grid_out) *grid_out = (int)grid;
-    mp_associate_kernel<<<(unsigned)grid, kMpThreads, smem, L.stream>>>(cams, a);
-    return cudaGetLastError();
+    // Two frames per SM when two of them fit the SM's shared memory (228 KB less 1 KB per CTA) — then the kernel is built for
+    // 64 registers; otherwise one frame per SM with the full register file.
+    // (P2S_MP_ONE_RESIDENT in the environment: A/B switch of tests/perf/mp_bench.py)
+    static const bool force_one = std::getenv("P2S_MP_ONE_RESIDENT") != nullptr;
+    const bool two = 2 * (smem + 1024) <= L.smem_per_sm && !force_one;
+    return two ? launch_mp_variant<2>(cams, a, smem, L.sm_count, L.stream, grid_out)
+               : launch_mp_variant<1>(cams, a, smem, L.sm_count, L.stream, grid_out);
 }
 
 }  // namespace p2s
