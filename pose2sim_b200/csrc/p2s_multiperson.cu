@@ -45,9 +45,9 @@ struct MpArgs {
     unsigned int *tile_counter;
 };
 
-constexpr int kMpThreads = 512;
-constexpr int kMpWarps = kMpThreads / 32;
+constexpr int kMpMaxWarps = 16;      // the widest team: 512 threads = 32 half-warps = the column pairs of 64 detections
 
+template <int kMpWarps>
 __device__ __forceinline__ double block_sum(double v, double *red) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(P2S_FULL, v, off);
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool joint_ray(const RayCam &c, float fx, float fy, f
 // {A, V, Qp | observations}.  Byte offset of the union region (16-byte aligned):
 __host__ __device__ __forceinline__ size_t mp_union_offset(int n_max) {
     const size_t LD = (size_t)(n_max | 1), tri = ((size_t)n_max * (n_max + 1)) >> 1;
-    size_t b = (2 * tri + (size_t)n_max * LD + (size_t)n_max + kMpWarps) * sizeof(double) +
+    size_t b = (2 * tri + (size_t)n_max * LD + (size_t)n_max + kMpMaxWarps) * sizeof(double) +
                ((size_t)n_max + P2S_MAX_CAMS + 1 + 2) * sizeof(int) + (size_t)(n_max | 1) * 32 * sizeof(unsigned short);
     return (b + 15) & ~(size_t)15;
 }
@@ -98,8 +98,11 @@ __device__ __forceinline__ int tri_index(int i, int j, int N2) {       // N2 = 2
     return ((a * (N2 - a)) >> 1) + b;                                   // a N - a (a - 1) / 2 + (b - a)
 }
 
-template <int RESIDENT>
+// kMpThreads: one half-warp per column pair of a Jacobi round, so 128 / 256 / 512 threads serve frames of up to 16 / 32 / 64
+// detections; the narrower teams leave room for 8 / 4 resident frames per SM instead of 2.
+template <int kMpThreads, int RESIDENT>
 __global__ void __launch_bounds__(kMpThreads, RESIDENT) mp_associate_kernel(const RayCams cams, const MpArgs a) {
+    constexpr int kMpWarps = kMpThreads / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = a.n_cams, NP = a.max_persons, J = a.n_joints, NM = a.n_max;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kMpThreads, RESIDENT) mp_associate_kernel(cons
     double *Y = W + TRI;
     double *sig = Y + (size_t)NM * LD;                                 // NM shrink factors
     double *red = sig + NM;                                            // one per warp
-    int *s_view = reinterpret_cast<int *>(red + kMpWarps);             // NM: view of each detection
+    int *s_view = reinterpret_cast<int *>(red + kMpMaxWarps);          // NM: view of each detection
     int *s_cum = s_view + NM;                                          // C + 1
     int *s_flag = s_cum + P2S_MAX_CAMS + 1;                            // [0] frame, [1] rotations in the sweep
     unsigned short *s_sched = reinterpret_cast<unsigned short *>(s_flag + 2);   // [rounds][32] pair schedule: p | q << 8, 0xffff = idle
@@ -365,8 +368,8 @@ __global__ void __launch_bounds__(kMpThreads, RESIDENT) mp_associate_kernel(cons
                 }
                 X[t] = xs;
             }
-            const double pres = sqrt(block_sum(pr, red)) / N;
-            const double dres = mu * sqrt(block_sum(dr, red)) / N;
+            const double pres = sqrt(block_sum<kMpWarps>(pr, red)) / N;
+            const double dres = mu * sqrt(block_sum<kMpWarps>(dr, red)) / N;
             __syncthreads();
             if (pres < a.tol && dres < a.tol) break;
             if (pres > 10.0 * dres) mu = 2.0 * mu;
@@ -404,14 +407,14 @@ size_t mp_smem_bytes(int n_max, int n_joints) {
     return mp_union_offset(n_max) + (mats > obs ? mats : obs);
 }
 
-template <int RESIDENT>
+template <int kMpThreads, int RESIDENT>
 static cudaError_t launch_mp_variant(const RayCams &cams, const MpArgs &a, size_t smem, int sm_count, cudaStream_t stream, int *grid_out) {
-    cudaError_t e = cudaFuncSetAttribute(mp_associate_kernel<RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mp_associate_kernel<kMpThreads, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mp_associate_kernel<RESIDENT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(mp_associate_kernel<kMpThreads, RESIDENT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_associate_kernel<RESIDENT>, kMpThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mp_associate_kernel<kMpThreads, RESIDENT>, kMpThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > RESIDENT) per_sm = RESIDENT;
@@ -419,7 +422,7 @@ static cudaError_t launch_mp_variant(const RayCams &cams, const MpArgs &a, size_
     if (grid > a.n_frames) grid = a.n_frames;
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
-    mp_associate_kernel<RESIDENT><<<(unsigned)grid, kMpThreads, smem, stream>>>(cams, a);
+    mp_associate_kernel<kMpThreads, RESIDENT><<<(unsigned)grid, kMpThreads, smem, stream>>>(cams, a);
     return cudaGetLastError();
 }
 
@@ -446,13 +449,17 @@ cudaError_t launch_mp_associate(const MpLaunch &L, int *grid_out) {
     a.max_iter = 20; a.w_rank = 50.0; a.tol = 1e-4; a.w_sparse = 0.1;            // matchSVT's call-site constants (:799)
     a.out_rows = L.out_rows; a.out_affinity = L.out_affinity; a.out_iters = L.out_iters; a.tile_counter = L.tile_counter;
     const size_t smem = mp_smem_bytes(L.n_max, L.n_joints);
-    // Two frames per SM when two of them fit the SM's shared memory (228 KB less 1 KB per CTA) — then the kernel is built for
-    // 64 registers; otherwise one frame per SM with the full register file.
-    // (P2S_MP_ONE_RESIDENT in the environment: A/B switch of tests/perf/mp_bench.py)
+    // Team width from the largest frame (one half-warp per column pair), resident frames per SM from the register file at
+    // 64 registers per thread (8 / 4 / 2); a 512-thread team whose frame does not fit twice into the SM's shared memory
+    // (228 KB less 1 KB per CTA) runs alone with the full register file.
+    // (P2S_MP_ONE_RESIDENT in the environment: A/B switch of tests/perf/mp_bench.py — the round-2 configuration)
     static const bool force_one = std::getenv("P2S_MP_ONE_RESIDENT") != nullptr;
-    const bool two = 2 * (smem + 1024) <= L.smem_per_sm && !force_one;
-    return two ? launch_mp_variant<2>(cams, a, smem, L.sm_count, L.stream, grid_out)
-               : launch_mp_variant<1>(cams, a, smem, L.sm_count, L.stream, grid_out);
+    if (force_one) return launch_mp_variant<512, 1>(cams, a, smem, L.sm_count, L.stream, grid_out);
+    if (L.n_max <= 16) return launch_mp_variant<128, 8>(cams, a, smem, L.sm_count, L.stream, grid_out);
+    if (L.n_max <= 32) return launch_mp_variant<256, 4>(cams, a, smem, L.sm_count, L.stream, grid_out);
+    const bool two = 2 * (smem + 1024) <= L.smem_per_sm;
+    return two ? launch_mp_variant<512, 2>(cams, a, smem, L.sm_count, L.stream, grid_out)
+               : launch_mp_variant<512, 1>(cams, a, smem, L.sm_count, L.stream, grid_out);
 }
 
 }  // namespace p2s
