@@ -149,16 +149,21 @@ def proposals_from_rows_batch(rows, n, min_cams):
     sel = np.empty(len(fi), np.int64)
     for f in np.flatnonzero(n_unique).tolist():
         a, b = bounds[f], bounds[f + 1]
-        sel[a:b] = first_flat[a:b][np.argsort(counts_flat[a:b])[::-1]]
+        sel[a:b] = first_flat[a:b][counts_flat[a:b].argsort()[::-1]]      # = np.argsort(counts)[::-1], the reference's call
     prop = np.full((F, U, C), -1, np.int64)
     filled = np.zeros((F, U), bool)
     prop[fi, slot] = r64[fi, sel]
     filled[fi, slot] = True
     # a row is dropped when any of its entries equals the entry of ANY earlier row in the same column (:541-542; -1 never matches)
+    # — i.e. when one of its entries is not the FIRST occurrence of that detection in its column: one pass per detection index
+    # over [F, U, C] instead of the [F, U, U, C] comparison table
     seen = prop >= 0
-    same = ((prop[:, :, None, :] == prop[:, None, :, :]) & seen[:, :, None, :]).any(axis=3)
-    lower = np.tril(np.ones((U, U), bool), -1)
-    keep = filled & ~(same & lower[None]).any(axis=2) & (seen.sum(axis=2) >= min_cams)
+    upos = np.arange(U)[None, :, None]
+    repeat = np.zeros((F, U, C), bool)
+    for v in range(int(prop.max(initial=-1)) + 1):
+        m = prop == v
+        repeat |= m & (upos > m.argmax(axis=1)[:, None, :])     # argmax of booleans = first True of the column
+    keep = filled & ~repeat.any(axis=2) & (seen.sum(axis=2) >= min_cams)
     propf = np.where(seen, prop, 0).astype(float)
     propf[~seen] = np.nan
     kept = keep.sum(axis=1)
