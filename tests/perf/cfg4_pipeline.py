@@ -30,10 +30,13 @@ def gather_persons(obs, props, n_persons):
     F, C, NP, L = obs.shape
     K = L // 3
     idx = np.full((F, n_persons, C), -1, np.int64)
-    for f, p in enumerate(props):
-        if p.size:
-            n = min(len(p), n_persons)
-            idx[f, :n] = np.where(np.isnan(p[:n]), -1, p[:n]).astype(np.int64)
+    kept = [p[:n_persons] for p in props if p.size]
+    if kept:
+        cnt = np.fromiter((min(len(p), n_persons) if p.size else 0 for p in props), np.int64, F)
+        flat = np.concatenate(kept)
+        fi = np.repeat(np.arange(F), cnt)
+        slot = np.arange(len(fi)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        idx[fi, slot] = np.where(np.isnan(flat), -1, flat).astype(np.int64)
     safe = np.maximum(idx, 0)
     g = obs[np.arange(F)[:, None, None], np.arange(C)[None, None, :], safe]          # [F, n, C, 3K]
     g = np.where((idx >= 0)[..., None], g, np.float32(np.nan)).reshape(F, n_persons, C, K, 3)
@@ -58,7 +61,7 @@ def main():
         out = eng.associate_multi_host(w["obs"], w["count"], w["models"], d_max, min_aff, n_max=n_max)
         t1 = time.perf_counter()
         n = w["count"].sum(axis=1)
-        props = [mp.proposals_from_rows(out["rows"][f, :n[f]], min_cams) for f in range(F)]
+        props = mp.proposals_from_rows_batch(out["rows"], n, min_cams)      # what associate_all calls (multi_person.associate_frames)
         t2 = time.perf_counter()
         x, y, lik = gather_persons(w["obs"], props, NP)
         t3 = time.perf_counter()

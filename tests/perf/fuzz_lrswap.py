@@ -8,8 +8,8 @@ rates.
 
 One JSON line (also gpurun_out/fuzz_lrswap.jsonl): cases run, units compared, units with a differing decision (and how
 many of those inside the eps-band), max relative |dQ|; the first offending cases are printed for reproduction.
-NOT YET RUN ON A GPU (written after the round's GPU minutes were spent); its CPU half — workload generation and the
-C oracle against the NumPy oracle — was exercised with `--cpu-selfcheck`."""
+GPU runs: profiles/r2a_fuzz_lrswap_gpu_seed*.json, r3f_fuzz_lrswap.jsonl; `--cpu-selfcheck` exercises the CPU half alone (workload
+generation and the C oracle against the NumPy oracle)."""
 import json
 import os
 import sys
