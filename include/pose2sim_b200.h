@@ -117,7 +117,10 @@ int p2s_set_solver(p2s_handle *h, int solver);
 int p2s_set_search_mode(p2s_handle *h, int mode);
 
 /* how the triangulation kernels write a full 32-unit tile of outputs: 0 (default) = 16-byte vector stores from the
- * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path) */
+ * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path),
+ * 2 = the pooled kernel where it applies (p2s_triangulate_planes_device without statistics, 4 or 8 cameras): level-1
+ * passes are shared by the pending units of several tiles, whose outputs are overwritten unit by unit after the tile's
+ * vector stores; same results bit for bit, measured equal in time to mode 0, kept as an A/B knob     */
 int p2s_set_output_mode(p2s_handle *h, int mode);
 
 /* how p2s_triangulate_host moves its data: 0 (default) = zero-copy when every buffer is pinned host memory (one

@@ -171,7 +171,7 @@ struct Planes {                                    // raw-plane input of the fus
 int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p2s_camera_model *lens, long long n_units, int n_cams,
                         double thr, int min_cams, double *Q, double *err, uint8_t *nexcl, uint32_t *mask,
                         unsigned long long *stats, cudaStream_t stream, const Planes *planes = nullptr,
-                        const PushFlags *push = nullptr) {
+                        const PushFlags *push = nullptr, bool device_outputs = false) {
     int rc = build_table(h, n_cams);
     if (rc) return rc;
     if (n_units == 0) return P2S_OK;
@@ -188,7 +188,9 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     L.tile_counter = next_counter(h);
     L.stream = stream;
     L.err_word = error_word(h);
-    L.bulk_out = h->bulk_out;
+    L.bulk_out = h->bulk_out == 1;
+    L.allow_pool = device_outputs;
+    L.pool = h->bulk_out == 2;
     if (push) { L.wait_flag = push->wait_flag; L.wait_value = push->wait_value; L.done_flag = push->done_flag; L.done_value = push->done_value; }
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 4 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
@@ -324,7 +326,7 @@ int p2s_set_host_mode(p2s_handle *h, int mode) {
 }
 
 int p2s_set_output_mode(p2s_handle *h, int mode) {
-    if (!h || (mode != 0 && mode != 1)) return P2S_EINVAL;
+    if (!h || (mode != 0 && mode != 1 && mode != 2)) return P2S_EINVAL;
     h->bulk_out = mode;
     return P2S_OK;
 }
@@ -442,7 +444,7 @@ int p2s_triangulate_planes_device(p2s_handle *h, const float *x, const float *y,
     Planes pl;
     pl.x = x; pl.y = y; pl.lik = lik; pl.lik_thr = lik_thr;
     return enqueue_triangulate(h, nullptr, P, nullptr, n_units, n_cams, reproj_thr, min_cams, out_Q, out_err, out_nexcl,
-                               out_mask, stats, (cudaStream_t)stream, &pl);
+                               out_mask, stats, (cudaStream_t)stream, &pl, nullptr, true);
 }
 
 int p2s_triangulate_planes_push_device(p2s_handle *h, const float *x, const float *y, const float *lik,

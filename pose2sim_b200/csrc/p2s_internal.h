@@ -30,6 +30,8 @@ struct TriLaunch {
     unsigned int done_value = 0;
     unsigned int *err_word = nullptr;
     int bulk_out = 0;             // full tiles leave by TMA bulk stores (p2s_set_output_mode)
+    bool allow_pool = false;      // outputs live in this device's memory: the pooled kernel may serve the launch
+    bool pool = false;            // ... and is asked for (p2s_set_output_mode(h, 2))
     cudaStream_t stream;
 };
 

@@ -31,6 +31,7 @@
 //   * a full tile's outputs leave as 16-byte vectors from a shared-memory staging area — locally or, on the push
 //     path, straight into the consumer GPU's memory, followed by an arrival flag from the launch's last CTA.
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "p2s_math.cuh"
@@ -798,6 +799,419 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---- pooled variant: level-1 work of SEVERAL tiles shares its passes ---------------------------------------------------
+// In triangulate_kernel a tile's pending units go through ceil(n / G) passes of G units per level; at 8 cameras ~9.3 of a
+// tile's 32 units reach level 1 (G = 4), so the last pass of almost every tile is partly empty: 227 k of the launch's 447 k
+// warp passes on cfg2 where 187 k would do.  Here the slab is a POOL of 32 unit SLOTS instead of the image of one tile:
+//   * level 0 runs thread per unit straight from the raw planes the TMA copies landed (no transposition of the 71 % of the
+//     units that end at level 0) and the tile's outputs leave as 16-byte vectors at once;
+//   * a unit that needs level 1 is copied into a free slot (observations, level-0 normal matrix, validity masks, unit index);
+//   * level-1 passes take G OCCUPIED SLOTS whatever tile they came from and only run full — up to G - 1 slots wait for the
+//     next tile — except when the stream ends or the pool overflows; the owner lane of a slot (lane == slot) then walks the
+//     deeper levels exactly like the tile kernel does and overwrites the unit's four output entries (the tile store of the
+//     same warp precedes it in program order, with a __syncwarp between).
+// Same arithmetic per candidate and the same arg-min rules, so the results are the tile kernel's bit for bit
+// (tests/test_gpu_triangulate.py::test_pooled_kernel_equals_tile_kernel).  Lean secular kernel on raw planes with a
+// compile-time camera count of 4 or 8 only (what the TMA staging serves); outputs in device memory (the scattered 8-byte
+// overwrites would make poor PCIe / NVLink packets, so the zero-copy host path and the push path keep the tile kernel).
+#ifndef P2S_POOL_HIGH
+#define P2S_POOL_HIGH 18
+#endif
+template <int CMAX>
+struct alignas(16) PoolSlab {
+    float raw[3 * 32 * CMAX];     // the tile's raw planes x | y | likelihood, [32 units][C] floats each (TMA destination)
+    float2 xy[CMAX][32];          // by SLOT: observations of the pooled units ...
+    float w[CMAX][32];            // ... and likelihoods (invalid cameras hold zeros)
+    unsigned long long mbar;
+    unsigned long long pad_;
+    double blk[32 * 10 + 32];     // camera blocks of the current group pass / output staging of a tile
+    double2 gxy[32];
+    double m0[10][32];            // by slot: level-0 normal matrix
+    unsigned long long r_key[32];
+    double r_qx[32], r_qy[32], r_qz[32];
+    uint32_t r_nan[32], r_flags[32], nan0[32], inv0[32], plist[32];
+    uint32_t uid[32];             // by slot: unit index
+};
+static_assert(sizeof(PoolSlab<8>) % 16 == 0 && offsetof(PoolSlab<8>, blk) % 16 == 0 && offsetof(PoolSlab<8>, xy) % 16 == 0, "slab alignment");
+static_assert(sizeof(PoolSlab<4>) % 16 == 0 && offsetof(PoolSlab<4>, blk) % 16 == 0, "slab alignment");
+
+// the unit's C observations of one plane as registers (two / one 16-byte shared-memory loads)
+template <int CMAX>
+__device__ __forceinline__ void load_row(const float *plane, int lane, float (&v)[CMAX]) {
+#pragma unroll
+    for (int j = 0; j < CMAX; j += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(plane + lane * CMAX + j);
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+    }
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kernel(const CamParams<CMAX> cams, const TriArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = CMAX;
+    constexpr bool DISTORT = false, STATS = false;
+    const LensSet<1> lens = {};
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double *sP = reinterpret_cast<double *>(smem_raw);
+    PoolSlab<CMAX> &S = reinterpret_cast<PoolSlab<CMAX> *>(smem_raw + CMAX * 12 * sizeof(double))[warp];
+    constexpr uint32_t cmask = (1u << C) - 1u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const long long n_tiles = (a.n_units + 31) >> 5;
+    const float nanf_ = __int_as_float(0x7fc00000);
+
+    for (int i = threadIdx.x; i < CMAX * 12; i += blockDim.x) sP[i] = (&cams.P[0][0])[i];
+    __syncthreads();
+
+    unsigned int t1 = 0, t2 = 0;
+    if (lane == 0) { t1 = atomicAdd(a.tile_counter, 1u); t2 = atomicAdd(a.tile_counter, 1u); }
+    const uint32_t bar = smem_u32(&S.mbar);
+    uint32_t phase = 0;
+    auto issue_tile = [&](unsigned int t) {                    // lane 0 only
+        const long long e0t = (long long)t * 32 * C;
+        const long long left = a.n_units * C - e0t;
+        const uint32_t bytes = (uint32_t)(left < 32LL * C ? left : 32LL * C) * 4u;
+        mbar_expect_tx(bar, 3u * bytes);
+        bulk_g2s(smem_u32(S.raw), a.px + e0t, bytes, bar);
+        bulk_g2s(smem_u32(S.raw + 32 * CMAX), a.py + e0t, bytes, bar);
+        bulk_g2s(smem_u32(S.raw + 64 * CMAX), a.pl + e0t, bytes, bar);
+    };
+    if (lane == 0) {
+        mbar_init(bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if ((long long)t1 < n_tiles) issue_tile(t1);
+    }
+    __syncwarp();
+
+    const int G1 = 32 >> a.lw[1];                               // slots per level-1 pass
+    // the pool is a ring: slots are handed out in increasing order (mod 32) and the passes take them in the same order
+    uint32_t q_head = 0;                                        // next slot to hand out (the same value in every lane)
+    int q_count = 0;                                            // occupied slots: q_head - q_count ... q_head - 1 (mod 32)
+    uint32_t todo = 0;                                          // lanes of the current tile still waiting for a slot
+    bool have_tile = true, raw_held = false;
+    unsigned int nt = 0;
+    Sym4 M0;                                                    // my unit's level-0 matrix until it has a slot
+    sym4_zero(M0);
+    uint32_t nan0 = 0, inv0 = 0;
+    long long u = 0;
+
+    for (;;) {
+        if (todo == 0u && have_tile) {
+            const unsigned int tile = __shfl_sync(P2S_FULL, t1, 0);
+            if ((long long)tile >= n_tiles) {
+                have_tile = false;
+            } else {
+                t1 = t2;
+                if (lane == 0) t2 = atomicAdd(a.tile_counter, 1u);
+                nt = __shfl_sync(P2S_FULL, t1, 0);
+                u = (long long)tile * 32 + lane;
+                const bool active = u < a.n_units;
+                mbar_wait(bar, phase);                          // this tile's planes have landed in S.raw
+                raw_held = true;
+
+                // ---- level 0: thread per unit, straight from the raw planes --------------------------------------
+                float fx[CMAX], fy[CMAX], fl[CMAX];
+                load_row<CMAX>(S.raw, lane, fx);
+                load_row<CMAX>(S.raw + 32 * CMAX, lane, fy);
+                load_row<CMAX>(S.raw + 64 * CMAX, lane, fl);
+                nan0 = 0; inv0 = 0;
+                float wlo = __int_as_float(0x7f800000), whi = 0.f;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if (!active) { fx[c] = 0.f; fy[c] = 0.f; fl[c] = nanf_; }     // beyond the last unit: stale bytes
+                    if (a.gate && fl[c] < a.lik_thr_f) { fx[c] = fy[c] = fl[c] = nanf_; }
+                    const float lz = fl[c];
+                    const bool isn = lz != lz;
+                    const bool inv = isn || lz == 0.f;
+                    nan0 |= (uint32_t)isn << c;
+                    inv0 |= (uint32_t)inv << c;
+                    const float la = fabsf(lz);
+                    whi = fmaxf(whi, la);
+                    wlo = fminf(wlo, la > 0.f ? la : wlo);
+                    if (inv) { fx[c] = 0.f; fy[c] = 0.f; fl[c] = 0.f; }
+                }
+#ifdef P2S_NO_WIDE
+                const bool wide = false;
+#else
+                const bool wide = whi > P2S_WIDE_SPREAD * wlo;
+#endif
+                if (__ballot_sync(P2S_FULL, wide && active) != 0u && lane == 0) atomicAdd(a.tile_counter + 2, 1u);
+
+                double err_min = inf64();
+                double qx = nan64(), qy = qx, qz = qx;
+                uint32_t ids = cmask, nexcl = (uint32_t)C;
+                int last_level = -1;
+                const int ninv0 = __popc(inv0);
+                if (active && !wide && (C >= a.min_cams) && !(min(C, ninv0) > C - a.min_cams)) {
+                    const uint32_t valid = cmask & ~inv0;
+                    const int m = C - ninv0;
+                    if (m >= 2) {
+                        sym4_zero(M0);
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c) accumulate_camera(M0, cams.P[c], (double)fx[c], (double)fy[c], (double)fl[c]);
+                        smallest_eigvec_secular(M0, qx, qy, qz);
+                        double sum = 0.0;
+#pragma unroll
+                        for (int c = 0; c < CMAX; ++c) {
+                            const double dist = reproj_distance(cams.P[c], qx, qy, qz, (double)fx[c], (double)fy[c]);
+                            if ((valid >> c) & 1u) sum += dist;
+                        }
+                        const double e = sum * a.rinv[m];
+                        err_min = (e != e) ? inf64() : e;
+                    }
+                    ids = nan0; nexcl = (uint32_t)ninv0; last_level = 0;
+                }
+                const bool pend1 = active && !wide && last_level == 0 && (err_min > a.thr) && (C - 1 >= a.min_cams) &&
+                                   !(min(C, ninv0 + 1) > C - a.min_cams);
+
+                // ---- the tile's outputs (units that go on are overwritten by their slot's owner later) --------------
+                const bool failed = active && (err_min > a.thr);
+                double e_out = err_min;
+                if (failed) { e_out = nan64(); qx = qy = qz = nan64(); }
+                if (a.vec_out && (long long)tile * 32 + 32 <= a.n_units) {
+                    double *stg = S.blk;
+                    stg[3 * lane] = qx; stg[3 * lane + 1] = qy; stg[3 * lane + 2] = qz;
+                    stg[96 + lane] = e_out;
+                    reinterpret_cast<uint32_t *>(stg + 128)[lane] = ids;
+                    reinterpret_cast<uint8_t *>(stg + 144)[lane] = (uint8_t)nexcl;
+                    __syncwarp();
+                    const float4 *src = reinterpret_cast<const float4 *>(stg);
+                    float4 *dq = reinterpret_cast<float4 *>(a.out_Q + (long long)tile * 96);
+                    float4 *de = reinterpret_cast<float4 *>(a.out_err + (long long)tile * 32);
+                    float4 *dm = reinterpret_cast<float4 *>(a.out_mask + (long long)tile * 32);
+                    float4 *dn = reinterpret_cast<float4 *>(a.out_nexcl + (long long)tile * 32);
+                    dq[lane] = src[lane];
+                    if (lane < 16) dq[32 + lane] = src[32 + lane];
+                    else de[lane - 16] = src[48 + lane - 16];
+                    if (lane < 8) dm[lane] = src[64 + lane];
+                    else if (lane < 10) dn[lane - 8] = src[72 + lane - 8];
+                    __syncwarp();
+                } else if (active) {
+                    double *q = a.out_Q + u * 3;
+                    q[0] = qx; q[1] = qy; q[2] = qz;
+                    a.out_err[u] = e_out;
+                    a.out_nexcl[u] = (uint8_t)nexcl;
+                    a.out_mask[u] = ids;
+                }
+                todo = __ballot_sync(P2S_FULL, pend1);
+            }
+        }
+
+        // ---- pending units of the tile move into free slots ---------------------------------------------------------
+        if (todo != 0u) {
+            const int nfree = 32 - q_count;
+            const bool mine = (todo >> lane) & 1u;
+            const int rank = __popc(todo & lt_mask);
+            const bool take = mine && rank < nfree;
+            if (take) {
+                const int slot = (int)((q_head + (uint32_t)rank) & 31u);
+                // observations again from the raw planes (still the tile's: the buffer goes back to the copy engine below)
+                float fx[CMAX], fy[CMAX], fl[CMAX];
+                load_row<CMAX>(S.raw, lane, fx);
+                load_row<CMAX>(S.raw + 32 * CMAX, lane, fy);
+                load_row<CMAX>(S.raw + 64 * CMAX, lane, fl);
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    const bool inv = (inv0 >> c) & 1u;
+                    S.xy[c][slot] = make_float2(inv ? 0.f : fx[c], inv ? 0.f : fy[c]);
+                    S.w[c][slot] = inv ? 0.f : fl[c];
+                }
+                if (!(M0.m33 == M0.m33)) {
+                    // level 0 came out +inf through a NaN coordinate under a valid likelihood (a NaN x or y makes m33 = sum of
+                    // (w x)^2-free terms NaN as well): the deeper levels need the sum of the CLEAN cameras
+                    sym4_zero(M0);
+#pragma unroll 1
+                    for (int c = 0; c < C; ++c) {
+                        const float2 o = S.xy[c][slot];
+                        if ((o.x == o.x) && (o.y == o.y))
+                            accumulate_camera(M0, sP + c * 12, (double)o.x, (double)o.y, (double)S.w[c][slot]);
+                    }
+                }
+                S.m0[0][slot] = M0.m00; S.m0[1][slot] = M0.m01; S.m0[2][slot] = M0.m02; S.m0[3][slot] = M0.m03; S.m0[4][slot] = M0.m11;
+                S.m0[5][slot] = M0.m12; S.m0[6][slot] = M0.m13; S.m0[7][slot] = M0.m22; S.m0[8][slot] = M0.m23; S.m0[9][slot] = M0.m33;
+                S.nan0[slot] = nan0;
+                S.inv0[slot] = inv0;
+                S.uid[slot] = (uint32_t)u;
+            }
+            const uint32_t taken = __ballot_sync(P2S_FULL, take);
+            q_head += (uint32_t)__popc(taken);
+            q_count += __popc(taken);
+            todo &= ~taken;
+            __syncwarp();
+        }
+        if (raw_held && todo == 0u) {
+            // every lane is done with S.raw: hand the buffer back to the copy engine for the next tile
+            __syncwarp();
+            raw_held = false;
+            phase ^= 1u;
+            if (lane == 0 && (long long)nt < n_tiles) { fence_proxy_async(); issue_tile(nt); }
+        }
+
+        // ---- passes over occupied slots: full groups of G1, everything when the stream ends or the pool overflowed ----
+        // The passes start when the pool is well filled (P2S_POOL_HIGH slots: two or three tiles' worth at 8 cameras) and then
+        // run back to back until less than one group is left: the level code stays in the instruction cache for 4-6 pass
+        // sets in a row instead of alternating with the level-0 code after every tile.
+        const bool drain = (todo != 0u) || !have_tile;
+        const bool running = drain || q_count >= P2S_POOL_HIGH;
+        while (running && q_count != 0 && (q_count >= G1 || drain)) {
+            // every full group at once (a partial one only when draining): ONE level loop over up to 32 pooled units, so the
+            // per-level set-up is shared by 4-6 level-1 passes
+            const int npass = drain ? q_count : (q_count / G1) * G1;
+            const uint32_t low = (npass >= 32) ? 0xffffffffu : ((1u << npass) - 1u);
+            const uint32_t pm = __funnelshift_l(low, low, (q_head - (uint32_t)q_count) & 31u);   // the npass oldest slots
+            q_count -= npass;
+            const bool owner = (pm >> lane) & 1u;
+            const uint32_t o_nan0 = S.nan0[lane], o_inv0 = S.inv0[lane];
+            const int o_ninv0 = __popc(o_inv0);
+            double err_min = inf64();
+            double qx = nan64(), qy = qx, qz = qx;
+            uint32_t ids = o_nan0, nexcl = (uint32_t)o_ninv0;
+            int last_level = 0;
+
+            for (int k = 1; k < C; ++k) {
+                const bool pend = owner && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
+                                  !(min(C, o_ninv0 + k) > C - a.min_cams);
+                const uint32_t pmask = __ballot_sync(P2S_FULL, pend);
+                if (pmask == 0) break;
+                const int npend = __popc(pmask);
+                if (pend) {
+                    S.plist[__popc(pmask & lt_mask)] = (uint32_t)lane;
+                    S.r_key[lane] = P2S_KEY_EMPTY;
+                }
+                const uint32_t ncand = a.ncand[k];
+                const int lw = a.lw[k];
+                const int W = 1 << lw;
+                const int G = 32 >> lw;
+                const int grp = lane >> lw, sub = lane & (W - 1);
+                const uint32_t gmask = (W >= 32) ? P2S_FULL : (((1u << W) - 1u) << (grp << lw));
+                const bool tabled = k <= a.max_table_level;
+                const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
+                double *gblk = S.blk + grp * (C * 10 + 2);
+                const bool subtract = 2 * k <= C;
+                __syncwarp();
+
+                for (int base = 0; base < npend; base += G) {
+                    const int idx = base + grp;
+                    const bool on = idx < npend;
+                    const int ul = on ? (int)S.plist[idx] : 0;
+                    const uint32_t u_nan0 = S.nan0[ul], u_inv0 = S.inv0[ul];
+                    __syncwarp();
+                    if (on && sub < C) {
+                        const float2 o = S.xy[sub][ul];
+                        const float ow = S.w[sub][ul];
+                        const bool clean = (o.x == o.x) && (o.y == o.y);
+                        const double ox = (double)o.x, oy = (double)o.y;
+                        S.gxy[grp * C + sub] = make_double2(ox, oy);
+                        double b[10];
+                        camera_block(sP + sub * 12, clean ? ox : 0.0, clean ? oy : 0.0, (double)(clean ? ow : 0.f), b);
+                        double2 *dst = reinterpret_cast<double2 *>(gblk + sub * 10);
+#pragma unroll
+                        for (int e = 0; e < 5; ++e) dst[e] = make_double2(b[2 * e], b[2 * e + 1]);
+                    }
+                    __syncwarp();
+
+                    unsigned long long bkey = P2S_KEY_EMPTY;
+                    uint32_t bcand = 0xffffffffu, bcm = 0;
+                    double bqx, bqy, bqz;
+                    for (uint32_t cand = (uint32_t)sub; on && cand < ncand; cand += (uint32_t)W) {
+                        const uint32_t cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
+                        const uint32_t valid = cmask & ~(u_inv0 | cm);
+                        const int m = __popc(valid);
+                        double cqx = nan64(), cqy = cqx, cqz = cqx;
+                        double e = inf64();
+                        if (m >= 2) {
+                            Sym4 M;
+                            uint32_t bits;
+                            double sgn;
+                            if (subtract) {
+                                M.m00 = S.m0[0][ul]; M.m01 = S.m0[1][ul]; M.m02 = S.m0[2][ul]; M.m03 = S.m0[3][ul]; M.m11 = S.m0[4][ul];
+                                M.m12 = S.m0[5][ul]; M.m13 = S.m0[6][ul]; M.m22 = S.m0[7][ul]; M.m23 = S.m0[8][ul]; M.m33 = S.m0[9][ul];
+                                bits = cm & ~u_inv0 & cmask;
+                                sgn = -1.0;
+                            } else {
+                                sym4_zero(M);
+                                bits = valid;
+                                sgn = 1.0;
+                            }
+                            while (bits) {
+                                const int c = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const double2 *src = reinterpret_cast<const double2 *>(gblk + c * 10);
+                                const double2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                                M.m00 = fma(sgn, v0.x, M.m00); M.m01 = fma(sgn, v0.y, M.m01); M.m02 = fma(sgn, v1.x, M.m02);
+                                M.m03 = fma(sgn, v1.y, M.m03); M.m11 = fma(sgn, v2.x, M.m11); M.m12 = fma(sgn, v2.y, M.m12);
+                                M.m13 = fma(sgn, v3.x, M.m13); M.m22 = fma(sgn, v3.y, M.m22); M.m23 = fma(sgn, v4.x, M.m23);
+                                M.m33 = fma(sgn, v4.y, M.m33);
+                            }
+                            smallest_eigvec_secular(M, cqx, cqy, cqz);
+                            e = mean_reproj_error<CMAX, DISTORT, true>(cams, lens, S.xy, S.gxy + grp * C, ul, valid, a.rinv[m], cqx, cqy, cqz, sP);
+                        }
+                        const unsigned long long key = err_key_inf(e);
+                        if (key < bkey) {
+                            bkey = key; bcand = cand; bcm = cm;
+                            bqx = cqx; bqy = cqy; bqz = cqz;
+                        }
+                    }
+                    const uint32_t hi = (uint32_t)(bkey >> 32), lo = (uint32_t)bkey;
+                    const uint32_t mh = group_min(hi, W, gmask);
+                    const bool have = bcand != 0xffffffffu;
+                    uint32_t holders = __ballot_sync(P2S_FULL, have && hi == mh) & gmask;
+                    bool winner = holders != 0u && lane == __ffs(holders) - 1;
+                    if (__any_sync(P2S_FULL, __popc(holders) > 1)) {
+                        const uint32_t ml = group_min(hi == mh ? lo : 0xffffffffu, W, gmask);
+                        const bool is_min = have && hi == mh && lo == ml;
+                        const uint32_t mc = group_min(is_min ? bcand : 0xffffffffu, W, gmask);
+                        winner = is_min && bcand == mc;
+                    }
+                    if (winner) {
+                        S.r_key[ul] = bkey;
+                        S.r_qx[ul] = bqx; S.r_qy[ul] = bqy; S.r_qz[ul] = bqz;
+                        S.r_nan[ul] = u_nan0 | bcm;
+                        S.r_flags[ul] = (uint32_t)__popc(u_inv0 | bcm);
+                    }
+                }
+                __syncwarp();
+                if (pend) {
+                    err_min = key_err(S.r_key[lane]);
+                    qx = S.r_qx[lane]; qy = S.r_qy[lane]; qz = S.r_qz[lane];
+                    ids = S.r_nan[lane];
+                    nexcl = S.r_flags[lane] & 0xffu;
+                    last_level = k;
+                }
+                __syncwarp();
+            }
+            // ---- finalise (:588-602): the slot's owner overwrites the unit's outputs ---------------------------------
+            if (owner) {
+                const long long uu = (long long)S.uid[lane];
+                double e_out = err_min;
+                if (err_min > a.thr) { e_out = nan64(); qx = qy = qz = nan64(); }
+                double *q = a.out_Q + uu * 3;
+                q[0] = qx; q[1] = qy; q[2] = qz;
+                a.out_err[uu] = e_out;
+                a.out_nexcl[uu] = (uint8_t)nexcl;
+                a.out_mask[uu] = ids;
+            }
+            __syncwarp();
+        }
+
+        if (todo != 0u) {
+            // pool overflow: the waiting lanes' matrices did not survive the passes in registers — rebuild them from the raw
+            // planes (rolled loop, off the common path); poisoned cameras are handled when the lane takes its slot
+            sym4_zero(M0);                                       // (every lane: nothing of M0 is live across the passes)
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const float x = S.raw[lane * C + c], y = S.raw[32 * CMAX + lane * C + c];
+                if (((todo & ~lt_mask) & (1u << lane)) != 0u && !((inv0 >> c) & 1u))
+                    accumulate_camera(M0, sP + c * 12, (double)x, (double)y, (double)S.raw[64 * CMAX + lane * C + c]);
+            }
+            continue;
+        }
+        if (!have_tile) break;
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- second kernel of every launch: wide-spread units + the push path's arrival flag ---------------------------
 // Runs right behind triangulate_kernel on the same stream.  When that kernel counted no unit with a wide likelihood
 // spread (tile_counter[2] == 0: always, unless the likelihood threshold is below 1 / P2S_WIDE_SPREAD) it only publishes the
@@ -1092,6 +1506,16 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.err_word = L.err_word;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, true>) * 4;
     const size_t smem_lean = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, false>) * 4;
+    if constexpr (CMAX == 4 || CMAX == 8) {
+        // the pooled variant (opt-in: p2s_set_output_mode(h, 2), or P2S_POOL in the environment for tools/kernel_ab.py /
+        // level_time.py): lean secular search on raw planes with exactly CMAX cameras, outputs in this device's memory
+        static const bool env_pool = std::getenv("P2S_POOL") != nullptr;
+        if (L.allow_pool && (L.pool || env_pool) && L.px != nullptr && L.lens == nullptr && L.solver == 0 && L.n_cams == CMAX && L.stats == nullptr &&
+            !a.bulk_out && L.wait_flag == nullptr && L.done_flag == nullptr && L.n_units < 0xffffffffLL) {
+            const size_t smem_pool = (size_t)CMAX * 12 * sizeof(double) + sizeof(PoolSlab<CMAX>) * 4;
+            return launch_persistent(triangulate_pool_kernel<CMAX>, smem_pool, L, grid_out, cams, a);
+        }
+    }
     if constexpr (!FULLSET) {
         LensSet<1> none;
         std::memset(&none, 0, sizeof none);

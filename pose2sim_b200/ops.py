@@ -111,8 +111,9 @@ class Engine:
         _lib.check(self.h, self.lib.p2s_set_search_mode(self.h, {"filtered": 0, "exhaustive": 1}.get(mode, mode)))
 
     def set_output_mode(self, mode):
-        """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`)."""
-        _lib.check(self.h, self.lib.p2s_set_output_mode(self.h, {"vector": 0, "bulk": 1}.get(mode, mode)))
+        """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`), 2 = the pooled kernel
+        (`pooled`: level-1 passes shared across tiles, device-resident calls without statistics at 4 / 8 cameras)."""
+        _lib.check(self.h, self.lib.p2s_set_output_mode(self.h, {"vector": 0, "bulk": 1, "pooled": 2}.get(mode, mode)))
 
     def set_chunk_units(self, units):
         _lib.check(self.h, self.lib.p2s_set_chunk_units(self.h, int(units)))

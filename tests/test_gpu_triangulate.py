@@ -416,3 +416,42 @@ def test_lr_swap_c_abi_checks_the_partner_map(engine):
     assert call([1, 0], 2) == 0
     assert call([1, 2], 2) == 1 and call([-1, 0], 2) == 1
     assert call([1, 0, 2, 3], 4) == 1                       # 6 units are not whole blocks of 4 keypoints
+
+
+@pytest.mark.parametrize("C,U,mc,thr,lik_thr", [(8, 26 * 400, 2, 15.0, 0.3), (8, 26 * 400 - 7, 2, 1e-3, 0.3), (8, 4099, 6, 15.0, 0.3),
+                                               (8, 3001, 2, 2.0, None), (8, 31, 2, 1e-3, 0.3), (8, 26 * 300, 7, 5.0, 0.3),
+                                               (8, 26 * 300, 8, 5.0, 0.3), (4, 26 * 400 + 5, 2, 15.0, 0.3), (4, 2049, 2, 1e-3, 0.3),
+                                               (4, 1000, 3, 4.0, None), (8, 26 * 200, 2, 1e9, 0.3)])
+def test_pooled_kernel_equals_tile_kernel(engine, C, U, mc, thr, lik_thr):
+    """`triangulate_pool_kernel` (`p2s_set_output_mode(h, 2)`: a device-resident call without statistics at 4 / 8 cameras runs
+    its level-1 passes over a pool of unit slots fed by several tiles) against `triangulate_kernel` (the same call WITH the statistics block): bit
+    for bit, incl. thresholds that send every unit through all levels (pool overflow: 32 pending units meet waiting slots),
+    thresholds nobody fails, `min_cameras` that forbid level 1 / level 2, ragged last tiles, NaN coordinates under a valid
+    likelihood, zero and NaN likelihoods."""
+    import torch
+    F = (U + 25) // 26
+    wl = synth.make_triangulation_workload(C, F, 1, 26, seed=1000 + C + U % 97, lik_thr=None, p_out=0.12, p_low=0.1)
+    x, y, w = (np.ascontiguousarray(wl[k][:U]).copy() for k in ("x", "y", "lik"))
+    g = np.random.default_rng(U)
+    m = g.random(x.shape)
+    x[m < 0.01] = np.nan
+    y[(m > 0.01) & (m < 0.02)] = np.nan
+    w[(m > 0.02) & (m < 0.04)] = 0.0
+    w[(m > 0.04) & (m < 0.06)] = np.nan
+    xs, ys, ls = (torch.from_numpy(a).cuda() for a in (x, y, w))
+    engine.set_output_mode("pooled")
+    try:
+        pooled = engine.triangulate_planes(xs, ys, ls, wl["P"], lik_thr, thr, mc)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_output_mode("vector")
+    st = engine.new_stats()
+    tile = engine.triangulate_planes(xs, ys, ls, wl["P"], lik_thr, thr, mc, stats=st)
+    torch.cuda.synchronize()
+    for k in ("Q", "err", "nexcl", "mask"):
+        a, b = pooled[k].cpu().numpy(), tile[k].cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True), (k, int((~((a == b) | ((a != a) & (b != b)))).sum()))
+    from pose2sim_b200 import ops
+    hist = ops.stats_dict(st.cpu().numpy())["level_hist"]
+    if thr == 1e-3 and mc == 2:
+        assert sum(hist[1:]) > 0.8 * U                              # the overflow case really sends (almost) everyone on
