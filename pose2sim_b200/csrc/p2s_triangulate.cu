@@ -323,7 +323,20 @@ __device__ __forceinline__ double mean_reproj_error(const CamParams<CMAX> &cams,
 // and the camera loops fold).
 // STATS: the statistics block (work counters, level histogram, eps-band counts incl. the arg-min runner-up) is
 // wanted; the lean variant compiles all of that bookkeeping out of the candidate loop.
-template <int CMAX, int SOLVER, bool DISTORT, bool EXACT, bool STATS>
+// the unit's C observations of one plane as registers (two / one 16-byte shared-memory loads)
+template <int CMAX>
+__device__ __forceinline__ void load_row(const float *plane, int lane, float (&v)[CMAX]) {
+#pragma unroll
+    for (int j = 0; j < CMAX; j += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(plane + lane * CMAX + j);
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+    }
+}
+
+// RAW: raw planes with a compile-time camera count of 4 or 8 (what the TMA staging serves; implies EXACT).  The tile's
+// planes land in S.raw unit-major, so a lane reads ITS OWN unit's row with 16-byte shared-memory loads and level 0 runs
+// from registers: no transposition pass, and only the units that go on to level 1 write their slab column.
+template <int CMAX, int SOLVER, bool DISTORT, bool EXACT, bool STATS, bool RAW = false>
 __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <= 24 ? 3 : 2) triangulate_kernel(const CamParams<CMAX> cams,
                                                                                const LensSet<DISTORT ? CMAX : 1> lens,
                                                                                const TriArgs a) {
@@ -364,8 +377,9 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
 #ifdef P2S_NO_TMA                                              /* A/B switch, tools/kernel_ab.py */
     const bool tma = false;
 #else
-    const bool tma = EXACT && CMAX <= 8 && (CMAX * 4) % 16 == 0 && a.px != nullptr;   // bulk copies move multiples of 16 bytes
+    const bool tma = RAW || (EXACT && CMAX <= 8 && (CMAX * 4) % 16 == 0 && a.px != nullptr);   // bulk copies move multiples of 16 bytes
 #endif
+    static_assert(!RAW || (EXACT && !DISTORT && (CMAX == 4 || CMAX == 8)), "RAW: exact camera count of 4 or 8, no lens model");
     const uint32_t bar = smem_u32(&S.mbar);
     uint32_t phase = 0;
     auto issue_tile = [&](unsigned int t) {                    // lane 0 only
@@ -415,7 +429,17 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
 
         // ---- stage the tile ---------------------------------------------------------------------
         uint32_t nan0 = 0, inv0 = 0;
-        if (a.px == nullptr) {
+        float rx[RAW ? CMAX : 1], ry[RAW ? CMAX : 1], rl[RAW ? CMAX : 1];   // RAW: my unit's observations
+        if constexpr (RAW) {
+            mbar_wait(bar, phase);                                     // this tile's planes have landed in S.raw
+            load_row<CMAX>(S.raw, lane, rx);
+            load_row<CMAX>(S.raw + 32 * CMAX, lane, ry);
+            load_row<CMAX>(S.raw + 64 * CMAX, lane, rl);
+            __syncwarp();
+            // every lane has its row in registers: hand the buffer back to the copy engine for the next tile
+            phase ^= 1u;
+            if (lane == 0 && (long long)nt < n_tiles) { fence_proxy_async(); issue_tile(nt); }
+        } else if (a.px == nullptr) {
             // staged float4 SoA [C][U]: one coalesced 512 B row per camera
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) {
@@ -486,7 +510,12 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         float wlo = __int_as_float(0x7f800000), whi = 0.f;         // smallest / largest valid |likelihood| of the unit
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            const float lz = S.w[c][lane];
+            if constexpr (RAW) {
+                const float nanf_ = __int_as_float(0x7fc00000);
+                if (!active) { rx[c] = 0.f; ry[c] = 0.f; rl[c] = nanf_; }          // beyond the last unit: stale bytes
+                if (a.gate && rl[c] < a.lik_thr_f) { rx[c] = ry[c] = rl[c] = nanf_; }
+            }
+            const float lz = RAW ? rl[RAW ? c : 0] : S.w[c][lane];
             const bool isn = lz != lz;
             const bool inv = isn || lz == 0.f;
             nan0 |= (uint32_t)isn << c;
@@ -496,7 +525,11 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             wlo = fminf(wlo, la > 0.f ? la : wlo);
             // invalid cameras hold exact zeros from here on: they add nothing to a normal matrix, so no pass below
             // needs a select per camera (validity lives in the nan0 / inv0 masks)
-            if (inv) { S.xy[c][lane] = make_float2(0.f, 0.f); S.w[c][lane] = 0.f; }
+            if constexpr (RAW) {
+                if (inv) { rx[c] = 0.f; ry[c] = 0.f; rl[c] = 0.f; }
+            } else {
+                if (inv) { S.xy[c][lane] = make_float2(0.f, 0.f); S.w[c][lane] = 0.f; }
+            }
         }
         nan0 &= cmask; inv0 &= cmask;
         S.nan0[lane] = nan0;
@@ -521,6 +554,8 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         uint32_t t_cands = 0, t_cams = 0, t_iters = 0;      // per-tile work counters of this lane
         uint32_t t_solved = 0, t_direct = 0, t_blocks = 0, t_adds = 0;
 
+        Sym4 M0;                                                // RAW: level-0 matrix until the unit's column is written
+        sym4_zero(M0);
         // ---- level 0: one candidate per unit, THREAD PER UNIT, straight line ---------------------------------------
         // reference loop condition (:408) and break rule (:437-441) in closed form: max_i |inv0 U cand_i| = min(C, |inv0| + k)
         if (active && !wide && (err_min > a.thr) && (C >= a.min_cams) && !(min(C, ninv0) > C - a.min_cams)) {
@@ -528,23 +563,50 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             const int m = C - ninv0;
             if (m >= 2) {
                 Sym4 M;
-                accumulate_direct<CMAX>(M, cams, S.xy, S.w, lane);
-                // kept (entry-major, conflict-free column): the sum of the unit's valid camera blocks, from which the deeper
-                // levels subtract the blocks they exclude
-                S.m0[0][lane] = M.m00; S.m0[1][lane] = M.m01; S.m0[2][lane] = M.m02; S.m0[3][lane] = M.m03; S.m0[4][lane] = M.m11;
-                S.m0[5][lane] = M.m12; S.m0[6][lane] = M.m13; S.m0[7][lane] = M.m22; S.m0[8][lane] = M.m23; S.m0[9][lane] = M.m33;
                 int it;
-                if (SOLVER == 0) it = smallest_eigvec_secular(M, qx, qy, qz);
-                else it = smallest_eigvec_jacobi(M, qx, qy, qz);
-                const double e = mean_reproj_error<CMAX, DISTORT, false>(cams, lens, S.xy, nullptr, lane, valid, a.rinv[m], qx, qy, qz, sP);
+                double e;
+                if constexpr (RAW) {
+                    sym4_zero(M);
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) accumulate_camera(M, cams.P[c], (double)rx[c], (double)ry[c], (double)rl[c]);
+                    M0 = M;
+                    it = smallest_eigvec_secular(M, qx, qy, qz);
+                    double sum = 0.0;
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) {
+                        const double dist = reproj_distance(cams.P[c], qx, qy, qz, (double)rx[c], (double)ry[c]);
+                        if ((valid >> c) & 1u) sum += dist;
+                    }
+                    e = sum * a.rinv[m];
+                } else {
+                    accumulate_direct<CMAX>(M, cams, S.xy, S.w, lane);
+                    // kept (entry-major, conflict-free column): the sum of the unit's valid camera blocks, from which the deeper
+                    // levels subtract the blocks they exclude
+                    S.m0[0][lane] = M.m00; S.m0[1][lane] = M.m01; S.m0[2][lane] = M.m02; S.m0[3][lane] = M.m03; S.m0[4][lane] = M.m11;
+                    S.m0[5][lane] = M.m12; S.m0[6][lane] = M.m13; S.m0[7][lane] = M.m22; S.m0[8][lane] = M.m23; S.m0[9][lane] = M.m33;
+                    if (SOLVER == 0) it = smallest_eigvec_secular(M, qx, qy, qz);
+                    else it = smallest_eigvec_jacobi(M, qx, qy, qz);
+                    e = mean_reproj_error<CMAX, DISTORT, false>(cams, lens, S.xy, nullptr, lane, valid, a.rinv[m], qx, qy, qz, sP);
+                }
                 err_min = (e != e) ? inf64() : e;            // a NaN error is the reference's +inf (err_key_inf)
                 t_iters += (uint32_t)it; t_solved += 1u; t_direct += (uint32_t)m;
             }                                                // m < 2: Q = NaN, error +inf (common.py:351, :394-396)
             t_cands += 1u; t_cams += (uint32_t)m;
             ids = nan0; nexcl = (uint32_t)ninv0; last_level = 0;
             band_thr |= fabs(err_min - a.thr) < a.band_eps;
-            // level 0 came out +inf: a unit with poisoned cameras gets its level-0 matrix rebuilt without them
-            if (!(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, valid, C);
+            if constexpr (RAW) {
+                // only a unit that goes on to level 1 needs its slab column (observations, level-0 matrix)
+                if ((err_min > a.thr) && (C - 1 >= a.min_cams) && !(min(C, ninv0 + 1) > C - a.min_cams)) {
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) { S.xy[c][lane] = make_float2(rx[c], ry[c]); S.w[c][lane] = rl[c]; }
+                    S.m0[0][lane] = M0.m00; S.m0[1][lane] = M0.m01; S.m0[2][lane] = M0.m02; S.m0[3][lane] = M0.m03; S.m0[4][lane] = M0.m11;
+                    S.m0[5][lane] = M0.m12; S.m0[6][lane] = M0.m13; S.m0[7][lane] = M0.m22; S.m0[8][lane] = M0.m23; S.m0[9][lane] = M0.m33;
+                    if (!(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, valid, C);
+                }
+            } else {
+                // level 0 came out +inf: a unit with poisoned cameras gets its level-0 matrix rebuilt without them
+                if (!(err_min < inf64())) rebuild_without_poisoned(S.m0, sP, S.xy, S.w, lane, valid, C);
+            }
         }
         __syncwarp();
 
@@ -834,16 +896,6 @@ struct alignas(16) PoolSlab {
 };
 static_assert(sizeof(PoolSlab<8>) % 16 == 0 && offsetof(PoolSlab<8>, blk) % 16 == 0 && offsetof(PoolSlab<8>, xy) % 16 == 0, "slab alignment");
 static_assert(sizeof(PoolSlab<4>) % 16 == 0 && offsetof(PoolSlab<4>, blk) % 16 == 0, "slab alignment");
-
-// the unit's C observations of one plane as registers (two / one 16-byte shared-memory loads)
-template <int CMAX>
-__device__ __forceinline__ void load_row(const float *plane, int lane, float (&v)[CMAX]) {
-#pragma unroll
-    for (int j = 0; j < CMAX; j += 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(plane + lane * CMAX + j);
-        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
-    }
-}
 
 template <int CMAX>
 __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kernel(const CamParams<CMAX> cams, const TriArgs a) {
@@ -1538,6 +1590,16 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     LensSet<1> none;
     std::memset(&none, 0, sizeof none);
     const bool st = L.stats != nullptr, exact = L.n_cams == CMAX;
+#ifndef P2S_NO_TMA
+    if constexpr (CMAX == 4 || CMAX == 8) {
+        // raw planes, exactly CMAX cameras: level 0 straight from the TMA-landed rows (P2S_NO_RAW_L0: A/B switch, kernel_ab.py)
+        static const bool no_raw = std::getenv("P2S_NO_RAW_L0") != nullptr;
+        if (L.solver == 0 && exact && L.px != nullptr && !no_raw) {
+            if (!st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false, true>, smem_lean, L, grid_out, cams, none, a);
+            return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true, true>, smem, L, grid_out, cams, none, a);
+        }
+    }
+#endif
     if (L.solver == 0 && exact && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false>, smem_lean, L, grid_out, cams, none, a);
     if (L.solver == 0 && exact) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true>, smem, L, grid_out, cams, none, a);
     if (L.solver == 0 && !st) return launch_persistent(triangulate_kernel<CMAX, 0, false, false, false>, smem_lean, L, grid_out, cams, none, a);
