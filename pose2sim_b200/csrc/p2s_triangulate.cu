@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
     for (;;) {
         const unsigned int tile = __shfl_sync(P2S_FULL, t1, 0);
         if ((long long)tile >= n_tiles) break;
-        if (a.bulk_out) {                                       // the previous tile's bulk stores have read the staging area
+        if (!RAW && a.bulk_out) {                               // the previous tile's bulk stores have read the staging area
             if (lane == 0) bulk_wait_read();
             __syncwarp();
         }
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             const int G = 32 >> lw;
             const int grp = lane >> lw, sub = lane & (W - 1);
             const uint32_t gmask = (W >= 32) ? P2S_FULL : (((1u << W) - 1u) << (grp << lw));   // lanes of my group
-            const bool tabled = k <= a.max_table_level;
+            const bool tabled = RAW || k <= a.max_table_level;   // <= 8 cameras: every level is in the table (256 entries)
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             double *gblk = S.blk + grp * (C * 10 + 2);
             const bool subtract = 2 * k <= C;                // M = M_all - excluded blocks, else sum of the kept blocks
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             stg[96 + lane] = e_out;
             reinterpret_cast<uint32_t *>(stg + 128)[lane] = ids;
             reinterpret_cast<uint8_t *>(stg + 144)[lane] = (uint8_t)nexcl;
-            if (a.bulk_out) {
+            if (!RAW && a.bulk_out) {                            // (RAW instantiations are not launched with bulk stores)
                 // TMA stores: four bulk copies per tile (768 + 256 + 128 + 32 bytes) issued by one lane; the copy engine
                 // moves them while the warp goes on — no store instructions, whole tile records on the link
                 fence_proxy_async();                             // my staging writes, visible to the async proxy
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
         }
     }
 
-    if (a.bulk_out) {                                           // every bulk store of this warp has been performed
+    if (!RAW && a.bulk_out) {                                   // every bulk store of this warp has been performed
         if (lane == 0) bulk_wait_all();
         __syncwarp();
     }
@@ -1137,7 +1137,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kern
                 const int G = 32 >> lw;
                 const int grp = lane >> lw, sub = lane & (W - 1);
                 const uint32_t gmask = (W >= 32) ? P2S_FULL : (((1u << W) - 1u) << (grp << lw));
-                const bool tabled = k <= a.max_table_level;
+                const bool tabled = true;                               // <= 8 cameras: every level is in the table
                 const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
                 double *gblk = S.blk + grp * (C * 10 + 2);
                 const bool subtract = 2 * k <= C;
@@ -1594,7 +1594,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     if constexpr (CMAX == 4 || CMAX == 8) {
         // raw planes, exactly CMAX cameras: level 0 straight from the TMA-landed rows (P2S_NO_RAW_L0: A/B switch, kernel_ab.py)
         static const bool no_raw = std::getenv("P2S_NO_RAW_L0") != nullptr;
-        if (L.solver == 0 && exact && L.px != nullptr && !no_raw) {
+        if (L.solver == 0 && exact && L.px != nullptr && !no_raw && !a.bulk_out) {
             if (!st) return launch_persistent(triangulate_kernel<CMAX, 0, false, true, false, true>, smem_lean, L, grid_out, cams, none, a);
             return launch_persistent(triangulate_kernel<CMAX, 0, false, true, true, true>, smem, L, grid_out, cams, none, a);
         }
