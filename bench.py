@@ -65,8 +65,8 @@ def algorithmic_flops(st):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 73.5 MB written on cfg2
 # (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
-NCU_TRAFFIC = {("cfg2", 1): 321.3e6, ("cfg3", 1): 739.8e6}      # cfg3: profiles/r1s_triangulate_cfg3_ncu_full.csv
-NCU_TRAFFIC_SOURCE = "profiles/r1z_triangulate_ncu_full.csv"
+NCU_TRAFFIC = {("cfg2", 1): 321.4e6, ("cfg3", 1): 739.8e6}      # cfg3: profiles/r1s_triangulate_cfg3_ncu_full.csv
+NCU_TRAFFIC_SOURCE = "profiles/r3m_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
@@ -588,8 +588,10 @@ def main():
                        "units_per_gpu": U, "reproj_error_threshold_triangulation": thr,
                        "min_cameras_for_triangulation": mc, "likelihood_threshold_triangulation": cfg["lik_thr"],
                        "seed": cfg["seed"], "l2": f"inputs {(12 * C * U) >> 20} MiB + outputs {(37 * U) >> 20} MiB per step > 126 MB L2, no flush",
-                       "step": "one search kernel (TMA-staged raw planes, likelihood gate + SoA transposition in shared memory, "
-                               "exclusion search) + the wide-likelihood / arrival-flag kernel behind it (returns at once here)"
+                       "step": "one search kernel (TMA-staged raw planes; at 4 / 8 cameras every lane reads its own unit's row, likelihood "
+                               "gate and level 0 run from registers and only the units that go on write their slab column, wider rigs "
+                               "transpose the tile in shared memory; exclusion search) + the wide-likelihood / arrival-flag kernel "
+                               "behind it (returns at once here)"
                                + ("" if world == 1 else
                                   "; results stay in the rank's HBM (rank-local post-processing, triangulation.write_outputs_sharded)"
                                   if gather_mode == "local" else
@@ -603,7 +605,7 @@ def main():
             "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                          "traffic": NCU_TRAFFIC.get((args.workload, 1)), "traffic_source": NCU_TRAFFIC_SOURCE,
                          "traffic_measured_in_run": False,
-                         "kernel": f"triangulate_kernel<{next(m for m in (4, 6, 8, 12, 16, 24, 32) if C <= m)},secular,exact,lean>",
+                         "kernel": f"triangulate_kernel<{next(m for m in (4, 6, 8, 12, 16, 24, 32) if C <= m)},secular,exact,lean{',raw' if C in (4, 8) else ''}>",
                          "grid_ctas": eng.last_grid(),
                          "kernel_ms": tri_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "dependent-chain DFMA microbenchmark in this run (p2s_measure_fp64_peak); "
