@@ -630,7 +630,10 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             const bool tabled = RAW || k <= a.max_table_level;   // <= 8 cameras: every level is in the table (256 entries)
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             double *gblk = S.blk + grp * (C * 10 + 2);
-            const bool subtract = 2 * k <= C;                // M = M_all - excluded blocks, else sum of the kept blocks
+            // M = M_all - excluded blocks, else sum of the kept blocks.  RAW (<= 8 cameras): always the downdate — the levels
+            // that drop more cameras than they keep are reached by ~1e-5 of the units, and one path less is code the
+            // candidate loop does not have to carry (the zero-initialisation of M was hoisted in front of the branch)
+            const bool subtract = RAW || 2 * k <= C;
             __syncwarp();
 
             for (int base = 0; base < npend; base += G) {
@@ -1140,7 +1143,7 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kern
                 const bool tabled = true;                               // <= 8 cameras: every level is in the table
                 const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
                 double *gblk = S.blk + grp * (C * 10 + 2);
-                const bool subtract = 2 * k <= C;
+                const bool subtract = true;                             // like the RAW tile kernel
                 __syncwarp();
 
                 for (int base = 0; base < npend; base += G) {
