@@ -66,7 +66,7 @@ def algorithmic_flops(st):
 # `ncu --set full` capture of this same command (profiles/): 249.7 MB read + 73.5 MB written on cfg2
 # (algorithmic: 249.6 MB of planes in, 96.2 MB of results out — the outputs are partly still in L2).
 NCU_TRAFFIC = {("cfg2", 1): 321.4e6, ("cfg3", 1): 739.8e6}      # cfg3: profiles/r1s_triangulate_cfg3_ncu_full.csv
-NCU_TRAFFIC_SOURCE = "profiles/r3m_triangulate_ncu_full.csv"
+NCU_TRAFFIC_SOURCE = "profiles/r3p_triangulate_ncu_full.csv"
 
 
 def algorithmic_bytes(U, C):
