@@ -121,6 +121,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
                                        register cap follows, which removes the spills of the 32-camera unrolls */
 #endif
 
+#ifdef P2S_NO_DOWNDATE_EXACT                                  /* A/B switch, tools/kernel_ab.py: exact-count kernels keep both forms */
+#define P2S_ALWAYS_DOWNDATE(exact) false
+#else
+#define P2S_ALWAYS_DOWNDATE(exact) (exact)                     /* cfg3 (16 cameras): 5.02 -> 4.95 ms */
+#endif
 template <int CMAX, bool STATS = false>
 struct alignas(16) WarpSlab {     // per-warp shared memory
     // next tile's raw planes x | y | likelihood ([32 units][C] floats each), written by cp.async.bulk (TMA) while the
@@ -630,10 +635,10 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             const bool tabled = RAW || k <= a.max_table_level;   // <= 8 cameras: every level is in the table (256 entries)
             const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
             double *gblk = S.blk + grp * (C * 10 + 2);
-            // M = M_all - excluded blocks, else sum of the kept blocks.  RAW (<= 8 cameras): always the downdate — the levels
+            // M = M_all - excluded blocks, else sum of the kept blocks.  Exact-count kernels: always the downdate — the levels
             // that drop more cameras than they keep are reached by ~1e-5 of the units, and one path less is code the
             // candidate loop does not have to carry (the zero-initialisation of M was hoisted in front of the branch)
-            const bool subtract = RAW || 2 * k <= C;
+            const bool subtract = RAW || P2S_ALWAYS_DOWNDATE(EXACT) || 2 * k <= C;
             __syncwarp();
 
             for (int base = 0; base < npend; base += G) {
