@@ -116,6 +116,14 @@ int p2s_set_solver(p2s_handle *h, int solver);
  * 1 = every row is solved and re-projected (personAssociation.py:196-248 as written).                               */
 int p2s_set_search_mode(p2s_handle *h, int mode);
 
+/* deep levels of the exclusion search (triangulation.py:408-411: level k enumerates ALL C(n_cams, k) camera subsets).
+ * A unit that is pending at a level of at least `min_candidates` subsets is not walked by the one warp that holds its
+ * tile: it is parked, and a second kernel behind the search kernel gives every parked unit a 512-thread CTA (same
+ * arithmetic, same outputs bit for bit).  Default 2048 — C(16, 5) = 4368, C(32, 3) = 4960: rigs of 14 cameras and up;
+ * 0 = never park (the single-kernel search); small values exercise the path on small rigs (tests).  Launches that ask
+ * for the statistics block, the Jacobi solver or a lens model never park.                                            */
+int p2s_set_deep_search(p2s_handle *h, long long min_candidates);
+
 /* how the triangulation kernels write a full 32-unit tile of outputs: 0 (default) = 16-byte vector stores from the
  * warp's staging area, 1 = four cp.async.bulk (TMA) stores per tile issued by one lane (A/B knob for the push path),
  * 2 = the pooled kernel where it applies (p2s_triangulate_planes_device without statistics, 4 or 8 cameras): level-1

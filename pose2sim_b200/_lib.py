@@ -66,6 +66,7 @@ SIGNATURES = {
     "p2s_set_chunk_units": (_i, [_vp, _ll]),
     "p2s_set_output_mode": (_i, [_vp, _i]),
     "p2s_set_search_mode": (_i, [_vp, _i]),
+    "p2s_set_deep_search": (_i, [_vp, _ll]),
     "p2s_set_host_mode": (_i, [_vp, _i]),
     "p2s_obs_bytes": (C.c_size_t, [_ll, _i]),
     "p2s_stage_observations_device": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _d, _vp, _vp]),

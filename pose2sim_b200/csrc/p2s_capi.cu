@@ -14,6 +14,7 @@ namespace {
 
 constexpr int kSlots = 4;                         // H2D / compute / D2H overlap
 constexpr long long kChunkUnitsDefault = 0;       // units per pipeline chunk; 0 = automatic: about four chunks per call,
+constexpr unsigned int kDeepMinDefault = 2048;   // candidates per level from which a pending unit is parked for deep_search_kernel
                                                   // between 2^16 and 2^20 units (measured, tools/e2e_sweep.py: below ~1e5
                                                   // units per chunk the host-side cost of the 7 copies + launch per chunk
                                                   // shows, above it the call is PCIe-bound at ~47 + 18 GB/s)
@@ -58,11 +59,16 @@ struct p2s_handle {
     unsigned long long *d_stats = nullptr;
     double *d_peak = nullptr;
     DevBuf wflags;                                // association: per-frame wide-likelihood flags of the *_device entry point
+    // deep levels of the triangulation search (p2s_set_deep_search): one list of parked (unit, level) records per
+    // counter-ring entry, allocated on the first launch that can park
+    unsigned int deep_min = kDeepMinDefault;
+    unsigned long long *d_deep = nullptr;
 };
 
 namespace {
 
-constexpr int kCounterRing = 256;                 // {tile dispenser, fix-up CTAs finished, wide tiles, -} per launch; one extra word = error bits
+constexpr int kDeepCap = 16384;                   // parked units per launch; beyond it units are searched by their warp as before
+constexpr int kCounterRing = 256;                 // {tile dispenser, fix-up CTAs finished, wide tiles, parked units} per launch; one extra word = error bits
 
 int cuda_fail(p2s_handle *h, cudaError_t e, const char *what) {
     char buf[512];
@@ -186,6 +192,20 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     L.max_table_level = t.max_level;
     L.out_Q = Q; L.out_err = err; L.out_nexcl = nexcl; L.out_mask = mask; L.stats = stats;
     L.tile_counter = next_counter(h);
+    if (h->deep_min != 0 && n_cams - min_cams >= 1) {
+        // only rigs whose search can reach a level of deep_min candidates need the list (14 cameras and up by default)
+        unsigned long long most = 1, r = 1;
+        for (int k = 1; k <= n_cams - min_cams; ++k) { r = r * (unsigned)(n_cams - k + 1) / (unsigned)k; if (r > most) most = r; }
+        if (most >= h->deep_min) {
+            if (!h->d_deep) {
+                cudaError_t e = cudaMalloc((void **)&h->d_deep, (size_t)kCounterRing * kDeepCap * sizeof(unsigned long long));
+                if (e != cudaSuccess) { cuda_fail(h, e, "cudaMalloc(deep list)"); return P2S_ENOMEM; }
+            }
+            L.deep_list = h->d_deep + (size_t)((L.tile_counter - h->d_counters) / 4) * kDeepCap;
+            L.deep_cap = kDeepCap;
+            L.deep_min = h->deep_min;
+        }
+    }
     L.stream = stream;
     L.err_word = error_word(h);
     L.bulk_out = h->bulk_out == 1;
@@ -194,7 +214,7 @@ int enqueue_triangulate(p2s_handle *h, const void *obs, const double *P, const p
     if (push) { L.wait_flag = push->wait_flag; L.wait_value = push->wait_value; L.done_flag = push->done_flag; L.done_value = push->done_value; }
     P2S_CUDA(h, cudaMemsetAsync(L.tile_counter, 0, 4 * sizeof(unsigned int), stream));
     P2S_CUDA(h, p2s::launch_triangulate(L, &h->last_grid));
-    h->launches += 2;                                   // search kernel + wide-spread / arrival-flag kernel
+    h->launches += L.kernels;                           // search kernel + wide-spread / arrival-flag kernel (+ deep-level kernel)
     return P2S_OK;
 }
 
@@ -286,6 +306,7 @@ int p2s_destroy(p2s_handle *h) {
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_peak) cudaFree(h->d_peak);
     if (h->wflags.p) cudaFree(h->wflags.p);
+    if (h->d_deep) cudaFree(h->d_deep);
     delete h;
     return P2S_OK;
 }
@@ -340,6 +361,12 @@ int p2s_set_chunk_units(p2s_handle *h, long long units) {
 int p2s_set_search_mode(p2s_handle *h, int mode) {
     if (!h || (mode != 0 && mode != 1)) return P2S_EINVAL;
     h->search_mode = mode;
+    return P2S_OK;
+}
+
+int p2s_set_deep_search(p2s_handle *h, long long min_candidates) {
+    if (!h || min_candidates < 0 || min_candidates > 0xffffffffLL) return P2S_EINVAL;
+    h->deep_min = (unsigned int)min_candidates;
     return P2S_OK;
 }
 

@@ -23,7 +23,7 @@ struct TriLaunch {
     uint8_t *out_nexcl;
     uint32_t *out_mask;
     unsigned long long *stats;    // device or null
-    unsigned int *tile_counter;   // device, two words, zeroed on the same stream before the launch
+    unsigned int *tile_counter;   // device, four words, zeroed on the same stream before the launch
     const unsigned int *wait_flag = nullptr;   // push path (see TriArgs)
     unsigned int wait_value = 0;
     unsigned int *done_flag = nullptr;
@@ -32,6 +32,12 @@ struct TriLaunch {
     int bulk_out = 0;             // full tiles leave by TMA bulk stores (p2s_set_output_mode)
     bool allow_pool = false;      // outputs live in this device's memory: the pooled kernel may serve the launch
     bool pool = false;            // ... and is asked for (p2s_set_output_mode(h, 2))
+    // deep levels (deep_search_kernel): list of parked (unit, level) records of THIS launch, its capacity, and the
+    // candidate count from which a level is parked (0 / null: never); tile_counter[3] counts the parked units
+    unsigned long long *deep_list = nullptr;
+    unsigned int deep_cap = 0;
+    uint32_t deep_min = 0;
+    mutable int kernels = 2;      // kernels the launch enqueued (search + fix-up, + deep search when it applies)
     cudaStream_t stream;
 };
 

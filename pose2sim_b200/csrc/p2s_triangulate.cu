@@ -71,6 +71,11 @@ struct TriArgs {
     unsigned int *done_flag;         // local or peer: set to done_value once every output of the launch is visible
     unsigned int done_value;
     unsigned int *err_word;          // local: bit 0 set when the wait timed out
+    // deep levels (deep_search_kernel below): a unit that is pending at a level with >= deep_min candidates is parked in
+    // deep_list ((unit << 8) | level, counted in tile_counter[3]) instead of being walked by one warp; null = never
+    unsigned long long *deep_list;
+    unsigned int deep_cap;
+    uint32_t deep_min;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -617,8 +622,26 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
 
         // ---- levels k >= 1: lanes enumerate subsets, W = min(32, pow2 >= C(C,k)) lanes per unit, G = 32 / W units per pass
         for (int k = 1; k < C; ++k) {
-            const bool pend = active && !wide && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
-                              !(min(C, ninv0 + k) > C - a.min_cams);
+            bool pend = active && !wide && last_level == k - 1 && (err_min > a.thr) && (C - k >= a.min_cams) &&
+                        !(min(C, ninv0 + k) > C - a.min_cams);
+            if constexpr (!STATS && SOLVER == 0 && !DISTORT && !RAW) {
+                // a level of thousands of candidates is not walked by ONE warp (at 16 cameras a unit that reaches level 7
+                // costs 26 k candidates = ~800 rounds, longer than the rest of the launch takes an SM): the unit is parked
+                // and deep_search_kernel, behind this kernel, gives it a whole 512-thread CTA.  Same arithmetic, same result.
+                if (a.deep_list != nullptr && a.ncand[k] >= a.deep_min) {
+                    const uint32_t pm = __ballot_sync(P2S_FULL, pend);
+                    if (pm != 0u) {
+                        unsigned int base = 0;
+                        if (lane == 0) base = atomicAdd(a.tile_counter + 3, (unsigned int)__popc(pm));
+                        base = __shfl_sync(P2S_FULL, base, 0);
+                        const unsigned int slot = base + (unsigned int)__popc(pm & lt_mask);
+                        if (pend && slot < a.deep_cap) {         // list full: the unit is searched here, as before
+                            a.deep_list[slot] = ((unsigned long long)u << 8) | (unsigned long long)k;
+                            pend = false;
+                        }
+                    }
+                }
+            }
             const uint32_t pmask = __ballot_sync(P2S_FULL, pend);
             if (pmask == 0) break;
             const int npend = __popc(pmask);
@@ -1272,6 +1295,235 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kern
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---- deep levels: one 512-thread CTA per parked unit ---------------------------------------------------------------
+// triangulate_kernel walks a level's candidates with the 32 lanes of ONE warp.  That is the right shape while levels hold
+// tens or hundreds of candidates, but C(16, 5..8) = 4 368 .. 12 870 and C(32, 4) = 35 960: a unit that goes that deep keeps
+// its warp for hundreds of rounds, and the SM that drew it is still busy when every other SM has run out of tiles (cfg3
+// shard, ncu: SMs active 73 % of the kernel's duration, the longest 9.5 M cycles against a mean of 6.9 M).  Such units are
+// rare (6e-4 of cfg3's), so the main kernel parks them — (unit, level) in a list, at the first level with >= deep_min
+// candidates — and this kernel, launched behind it, re-stages a parked unit and walks the rest of its search with 512
+// threads: candidates strided over the threads, the (error key, candidate index) arg-min reduced per warp and then across
+// the 16 warps, the level rules of triangulation.py:408-505 applied by every thread on the published result.
+// The arithmetic is the main kernel's, statement for statement (level-0 matrix accumulated over the cameras in ascending
+// order, camera blocks from camera_block(), M = M_all - excluded blocks or the sum of the kept ones by the same rule,
+// the same solver and distance functions, the mean from the same 1/m table), so parking changes no output bit
+// (tests/test_gpu_triangulate.py::test_deep_levels_*).  STATS / Jacobi / lens-model launches never park.
+struct DeepArgs {
+    const float4 *obs;
+    const float *px, *py, *pl;
+    float lik_thr_f;
+    int gate;
+    long long n_units;
+    int n_cams, min_cams;
+    double thr;
+    const uint32_t *cand_masks;
+    uint32_t level_off[P2S_MAX_CAMS + 2];
+    int max_table_level;
+    int always_downdate;              // the main kernel's `subtract` rule: exact-count kernels always downdate
+    double rinv[P2S_MAX_CAMS + 1];
+    double *out_Q, *out_err;
+    uint8_t *out_nexcl;
+    uint32_t *out_mask;
+    const unsigned long long *list;   // (unit << 8) | level
+    unsigned int cap;
+    const unsigned int *count;        // tile_counter + 3: units the main kernel tried to park (may exceed cap)
+};
+
+constexpr int kDeepThreads = 512;
+
+struct DeepSlab {
+    double sP[P2S_MAX_CAMS * 12];
+    double blk[P2S_MAX_CAMS * 10];
+    double2 gxy[P2S_MAX_CAMS];
+    double m0[10];
+    float2 xy[P2S_MAX_CAMS];
+    float w[P2S_MAX_CAMS];
+    unsigned long long wkey[kDeepThreads / 32];
+    double wq[kDeepThreads / 32][3];
+    uint32_t wcand[kDeepThreads / 32], wcm[kDeepThreads / 32];
+    unsigned long long rkey;
+    double rq[3];
+    uint32_t rcm, nan0, inv0;
+};
+
+// (key, candidate) arg-min over the lanes in `mask`: smallest 64-bit key, then the smallest candidate index among its
+// holders (np.nanargmin's first index).  Returns true on the one winning lane; false everywhere when no lane holds a candidate.
+__device__ __forceinline__ bool deep_argmin(uint32_t mask, unsigned long long key, uint32_t cand) {
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_min_sync(mask, hi);
+    const uint32_t ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+    const bool is_min = cand != 0xffffffffu && hi == mh && lo == ml;
+    const uint32_t mc = __reduce_min_sync(mask, is_min ? cand : 0xffffffffu);
+    return is_min && cand == mc;
+}
+
+__global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamParams<P2S_MAX_CAMS> cams, const DeepArgs a) {
+    __shared__ DeepSlab S;
+    // programmatic dependent launch: nothing the search kernel wrote is read before it has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    unsigned int n = *reinterpret_cast<const volatile unsigned int *>(a.count);
+    if (n > a.cap) n = a.cap;
+    if (n == 0u) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.n_cams;
+    const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
+    for (int i = tid; i < C * 12; i += kDeepThreads) S.sP[i] = (&cams.P[0][0])[i];
+    for (unsigned int j = blockIdx.x; j < n; j += gridDim.x) {
+        __syncthreads();                                       // sP is there; the previous unit's slab has been read
+        const unsigned long long rec = a.list[j];
+        const long long u = (long long)(rec >> 8);
+        int k = (int)(rec & 0xffu);
+        // ---- stage the unit like the main kernel stages a tile: gate, validity masks, zeros for invalid cameras,
+        // camera blocks (a poisoned camera — valid, NaN coordinate — gets a zero block and keeps its NaN in gxy)
+        if (warp == 0) {
+            const float nanf_ = __int_as_float(0x7fc00000);
+            float fx = 0.f, fy = 0.f, fl = nanf_;
+            if (lane < C) {
+                if (a.px == nullptr) {
+                    const float4 o = __ldg(a.obs + (long long)lane * a.n_units + u);
+                    fx = o.x; fy = o.y; fl = o.z;
+                } else {
+                    fx = a.px[u * C + lane]; fy = a.py[u * C + lane]; fl = a.pl[u * C + lane];
+                    if (a.gate && fl < a.lik_thr_f) { fx = fy = fl = nanf_; }
+                }
+            }
+            const bool isn = fl != fl;
+            const bool inv = isn || fl == 0.f;
+            const uint32_t nan0 = __ballot_sync(P2S_FULL, isn) & cmask;
+            const uint32_t inv0 = __ballot_sync(P2S_FULL, inv) & cmask;
+            if (inv) { fx = 0.f; fy = 0.f; fl = 0.f; }
+            if (lane < C) {
+                const bool clean = (fx == fx) && (fy == fy);
+                const double ox = (double)fx, oy = (double)fy;
+                S.xy[lane] = make_float2(fx, fy);
+                S.w[lane] = fl;
+                S.gxy[lane] = make_double2(ox, oy);
+                double b[10];
+                camera_block(S.sP + lane * 12, clean ? ox : 0.0, clean ? oy : 0.0, (double)(clean ? fl : 0.f), b);
+#pragma unroll
+                for (int e = 0; e < 10; ++e) S.blk[lane * 10 + e] = b[e];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // level 0's normal matrix: accumulate_direct(), then rebuild_without_poisoned() when it applies
+                S.nan0 = nan0; S.inv0 = inv0;
+                const uint32_t valid0 = cmask & ~inv0;
+                Sym4 M;
+                sym4_zero(M);
+                bool poisoned = false;
+#pragma unroll 1
+                for (int c = 0; c < C; ++c) {
+                    const float2 o = S.xy[c];
+                    accumulate_camera(M, S.sP + c * 12, (double)o.x, (double)o.y, (double)S.w[c]);
+                    poisoned |= ((valid0 >> c) & 1u) && !((o.x == o.x) && (o.y == o.y));
+                }
+                if (poisoned) {
+                    sym4_zero(M);
+#pragma unroll 1
+                    for (int c = 0; c < C; ++c) {
+                        const float2 o = S.xy[c];
+                        if (((valid0 >> c) & 1u) && (o.x == o.x) && (o.y == o.y))
+                            accumulate_camera(M, S.sP + c * 12, (double)o.x, (double)o.y, (double)S.w[c]);
+                    }
+                }
+                S.m0[0] = M.m00; S.m0[1] = M.m01; S.m0[2] = M.m02; S.m0[3] = M.m03; S.m0[4] = M.m11;
+                S.m0[5] = M.m12; S.m0[6] = M.m13; S.m0[7] = M.m22; S.m0[8] = M.m23; S.m0[9] = M.m33;
+            }
+        }
+        __syncthreads();
+        const uint32_t u_nan0 = S.nan0, u_inv0 = S.inv0;
+        const int ninv0 = __popc(u_inv0);
+        double err_min = inf64();
+        // ---- levels k, k + 1, ...: the parked level is known to be evaluated (the main kernel's `pend`)
+#pragma unroll 1
+        for (;; ++k) {
+            const uint32_t ncand = binom_u32(C, k);
+            const bool tabled = k <= a.max_table_level;
+            const uint32_t *table = a.cand_masks + a.level_off[tabled ? k : 0];
+            const bool subtract = a.always_downdate || 2 * k <= C;
+            unsigned long long bkey = P2S_KEY_EMPTY;
+            uint32_t bcand = 0xffffffffu, bcm = 0;
+            double bqx = nan64(), bqy = bqx, bqz = bqx;
+#pragma unroll 1
+            for (uint32_t cand = (uint32_t)tid; cand < ncand; cand += (uint32_t)kDeepThreads) {
+                const uint32_t cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
+                const uint32_t valid = cmask & ~(u_inv0 | cm);
+                const int m = __popc(valid);
+                double cqx = nan64(), cqy = cqx, cqz = cqx;
+                double e = inf64();
+                if (m >= 2) {
+                    Sym4 M;
+                    uint32_t bits;
+                    double sgn;
+                    if (subtract) {
+                        M.m00 = S.m0[0]; M.m01 = S.m0[1]; M.m02 = S.m0[2]; M.m03 = S.m0[3]; M.m11 = S.m0[4];
+                        M.m12 = S.m0[5]; M.m13 = S.m0[6]; M.m22 = S.m0[7]; M.m23 = S.m0[8]; M.m33 = S.m0[9];
+                        bits = cm & ~u_inv0 & cmask;
+                        sgn = -1.0;
+                    } else {
+                        sym4_zero(M);
+                        bits = valid;
+                        sgn = 1.0;
+                    }
+                    while (bits) {                            // ascending camera order
+                        const int c = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const double *v = S.blk + c * 10;
+                        M.m00 = fma(sgn, v[0], M.m00); M.m01 = fma(sgn, v[1], M.m01); M.m02 = fma(sgn, v[2], M.m02);
+                        M.m03 = fma(sgn, v[3], M.m03); M.m11 = fma(sgn, v[4], M.m11); M.m12 = fma(sgn, v[5], M.m12);
+                        M.m13 = fma(sgn, v[6], M.m13); M.m22 = fma(sgn, v[7], M.m22); M.m23 = fma(sgn, v[8], M.m23);
+                        M.m33 = fma(sgn, v[9], M.m33);
+                    }
+                    smallest_eigvec_secular(M, cqx, cqy, cqz);
+                    double sum = 0.0;
+#pragma unroll 4
+                    for (int c = 0; c < C; ++c) {
+                        const double2 o = S.gxy[c];
+                        const double dist = reproj_distance(S.sP + c * 12, cqx, cqy, cqz, o.x, o.y);
+                        if ((valid >> c) & 1u) sum += dist;
+                    }
+                    e = sum * a.rinv[m];
+                }
+                const unsigned long long key = err_key_inf(e);
+                if (key < bkey) {                               // ascending cand per thread: strict < keeps the first
+                    bkey = key; bcand = cand; bcm = cm;
+                    bqx = cqx; bqy = cqy; bqz = cqz;
+                }
+            }
+            const uint32_t holders = __ballot_sync(P2S_FULL, bcand != 0xffffffffu);
+            if (deep_argmin(P2S_FULL, bkey, bcand)) {
+                S.wkey[warp] = bkey; S.wcand[warp] = bcand; S.wcm[warp] = bcm;
+                S.wq[warp][0] = bqx; S.wq[warp][1] = bqy; S.wq[warp][2] = bqz;
+            }
+            if (holders == 0u && lane == 0) { S.wkey[warp] = P2S_KEY_EMPTY; S.wcand[warp] = 0xffffffffu; }   // fewer candidates than threads
+            __syncthreads();
+            if (warp == 0) {
+                const bool in = lane < kDeepThreads / 32;
+                const unsigned long long wk = in ? S.wkey[lane] : P2S_KEY_EMPTY;
+                const uint32_t wc = in ? S.wcand[lane] : 0xffffffffu;
+                if (deep_argmin(P2S_FULL, wk, wc)) {
+                    S.rkey = wk; S.rcm = S.wcm[lane];
+                    S.rq[0] = S.wq[lane][0]; S.rq[1] = S.wq[lane][1]; S.rq[2] = S.wq[lane][2];
+                }
+            }
+            __syncthreads();
+            err_min = key_err(S.rkey);
+            // the reference's loop condition (:408) and break rule (:437-441) for the next level
+            const bool go_on = (err_min > a.thr) && (C - (k + 1) >= a.min_cams) && !(min(C, ninv0 + k + 1) > C - a.min_cams);
+            if (!go_on) break;
+            __syncthreads();                                   // every thread has read the level's result
+        }
+        if (tid == 0) {
+            const bool failed = err_min > a.thr;
+            double *q = a.out_Q + u * 3;
+            q[0] = failed ? nan64() : S.rq[0]; q[1] = failed ? nan64() : S.rq[1]; q[2] = failed ? nan64() : S.rq[2];
+            a.out_err[u] = failed ? nan64() : err_min;
+            a.out_nexcl[u] = (uint8_t)__popc(u_inv0 | S.rcm);
+            a.out_mask[u] = u_nan0 | S.rcm;
+        }
+    }
+}
+
 // ---- second kernel of every launch: wide-spread units + the push path's arrival flag ---------------------------
 // Runs right behind triangulate_kernel on the same stream.  When that kernel counted no unit with a wide likelihood
 // spread (tile_counter[2] == 0: always, unless the likelihood threshold is below 1 / P2S_WIDE_SPREAD) it only publishes the
@@ -1526,6 +1778,18 @@ static cudaError_t launch_persistent(Kern kern, size_t smem, const TriLaunch &L,
     return cudaGetLastError();
 }
 
+// Does this launch park its deep levels (see deep_search_kernel)?  Only the lean secular kernels without a lens model do,
+// and only when some level the search can reach holds at least deep_min candidates.
+static bool deep_applies(const TriLaunch &L) {
+    if (L.deep_list == nullptr || L.deep_cap == 0 || L.deep_min == 0 || L.stats != nullptr || L.solver != 0 || L.lens != nullptr) return false;
+    for (int k = 1; k <= L.n_cams - L.min_cams; ++k) {
+        unsigned long long r = 1;
+        for (int i = 1; i <= k; ++i) r = r * (unsigned)(L.n_cams - k + i) / (unsigned)i;
+        if (r >= L.deep_min) return true;
+    }
+    return false;
+}
+
 // FULLSET = false (the camera counts 6, 12, 24 between the powers of two): only the exact-count secular kernels are
 // instantiated — they are what a 6 / 12 / 24-camera rig runs; everything else goes to the next power of two.
 template <int CMAX, bool FULLSET>
@@ -1564,6 +1828,7 @@ static cudaError_t launch_tri(const TriLaunch &L, int *grid_out) {
     a.bulk_out = (a.vec_out && L.bulk_out) ? 1 : 0;
     a.wait_flag = L.wait_flag; a.wait_value = L.wait_value; a.done_flag = L.done_flag; a.done_value = L.done_value;
     a.err_word = L.err_word;
+    a.deep_list = deep_applies(L) ? L.deep_list : nullptr; a.deep_cap = L.deep_cap; a.deep_min = L.deep_min;
     const size_t smem = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, true>) * 4;
     const size_t smem_lean = (size_t)CMAX * 12 * sizeof(double) + sizeof(WarpSlab<CMAX, false>) * 4;
     if constexpr (CMAX == 4 || CMAX == 8) {
@@ -1631,9 +1896,9 @@ static cudaError_t launch_main(const TriLaunch &L, int *grid_out) {
 // still draining; it orders itself behind that kernel with griddepcontrol.wait.  Hides the ~3 us launch gap of the
 // second kernel of every step (P2S_NO_PDL: plain launch, A/B).
 template <class Kern, class... Args>
-static cudaError_t launch_dependent(Kern kern, unsigned grid, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_dependent_block(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1641,6 +1906,41 @@ static cudaError_t launch_dependent(Kern kern, unsigned grid, size_t smem, cudaS
     cfg.attrs = attr; cfg.numAttrs = 1;
 #endif
     return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+template <class Kern, class... Args>
+static cudaError_t launch_dependent(Kern kern, unsigned grid, size_t smem, cudaStream_t stream, Args... args) {
+    return launch_dependent_block(kern, grid, 128u, smem, stream, args...);
+}
+
+// The deep-level kernel between the search kernel and the fix-up kernel (only when deep_applies()).  Every CTA reads the
+// parked count first and returns at once when it is zero.
+static cudaError_t launch_deep(const TriLaunch &L) {
+    CamParams<P2S_MAX_CAMS> cams;
+    for (int c = 0; c < P2S_MAX_CAMS; ++c)
+        for (int j = 0; j < 12; ++j) cams.P[c][j] = (c < L.n_cams) ? L.P[c * 12 + j] : 0.0;
+    DeepArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.obs = (const float4 *)L.obs; a.px = L.px; a.py = L.py; a.pl = L.pl;
+    a.gate = (L.lik_thr == L.lik_thr) && !(L.lik_thr == -INFINITY);
+    {
+        float tf = (float)L.lik_thr;
+        if (a.gate && (double)tf < L.lik_thr) tf = nextafterf(tf, INFINITY);
+        a.lik_thr_f = tf;
+    }
+    a.n_units = L.n_units; a.n_cams = L.n_cams; a.min_cams = L.min_cams; a.thr = L.thr;
+    a.cand_masks = L.cand_masks; a.max_table_level = L.max_table_level;
+    for (int i = 0; i < P2S_MAX_CAMS + 2; ++i) a.level_off[i] = L.level_off[i];
+    const int n = L.n_cams;
+#ifdef P2S_NO_DOWNDATE_EXACT
+    a.always_downdate = 0;
+#else
+    a.always_downdate = (n == 4 || n == 6 || n == 8 || n == 12 || n == 16 || n == 24 || n == 32) ? 1 : 0;   // the exact-count kernels
+#endif
+    a.rinv[0] = 0.0;
+    for (int m = 1; m <= P2S_MAX_CAMS; ++m) a.rinv[m] = 1.0 / (double)m;
+    a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
+    a.list = L.deep_list; a.cap = L.deep_cap; a.count = L.tile_counter + 3;
+    return launch_dependent_block(deep_search_kernel, (unsigned)(2 * L.sm_count), (unsigned)kDeepThreads, 0, L.stream, cams, a);
 }
 
 // The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 256
@@ -1698,6 +1998,12 @@ cudaError_t launch_triangulate(const TriLaunch &L, int *grid_out) {
     cudaError_t e = launch_main(L, &grid);
     if (grid_out) *grid_out = grid;
     if (e != cudaSuccess) return e;
+    L.kernels = 2;
+    if (deep_applies(L)) {
+        e = launch_deep(L);
+        if (e != cudaSuccess) return e;
+        L.kernels = 3;
+    }
 #ifdef P2S_NO_FIXUP_LAUNCH                                     /* A/B switch, tools/kernel_ab.py */
     return e;
 #else

@@ -110,6 +110,12 @@ class Engine:
         not solved; same results) or "exhaustive" (every row solved and re-projected)."""
         _lib.check(self.h, self.lib.p2s_set_search_mode(self.h, {"filtered": 0, "exhaustive": 1}.get(mode, mode)))
 
+    def set_deep_search(self, min_candidates):
+        """Triangulation search: a unit pending at a level of >= `min_candidates` camera subsets is parked and searched by
+        a 512-thread CTA of the deep-level kernel instead of by the warp that holds its tile (default 2048; 0 = never).
+        Same outputs bit for bit."""
+        _lib.check(self.h, self.lib.p2s_set_deep_search(self.h, int(min_candidates)))
+
     def set_output_mode(self, mode):
         """0 = vector stores (default), 1 = TMA bulk stores of whole tile records (`bulk`), 2 = the pooled kernel
         (`pooled`: level-1 passes shared across tiles, device-resident calls without statistics at 4 / 8 cameras)."""

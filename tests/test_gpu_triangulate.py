@@ -455,3 +455,79 @@ def test_pooled_kernel_equals_tile_kernel(engine, C, U, mc, thr, lik_thr):
     hist = ops.stats_dict(st.cpu().numpy())["level_hist"]
     if thr == 1e-3 and mc == 2:
         assert sum(hist[1:]) > 0.8 * U                              # the overflow case really sends (almost) everyone on
+
+
+def _deep_case(C, U, seed):
+    F = (U + 25) // 26
+    wl = synth.make_triangulation_workload(C, F, 1, 26, seed=seed, lik_thr=None, p_out=0.12, p_low=0.1)
+    x, y, w = (np.ascontiguousarray(wl[k][:U]).copy() for k in ("x", "y", "lik"))
+    g = np.random.default_rng(seed + U)
+    m = g.random(x.shape)
+    x[m < 0.01] = np.nan
+    y[(m > 0.01) & (m < 0.02)] = np.nan
+    w[(m > 0.02) & (m < 0.04)] = 0.0
+    w[(m > 0.04) & (m < 0.06)] = np.nan
+    return wl["P"], x, y, w
+
+
+@pytest.mark.parametrize("C,U,mc,thr,lik_thr,deep_min", [
+    (16, 26 * 12, 3, 1e-3, 0.3, 2048),       # default threshold, every unit walks every level: C(16, 5..8) parked
+    (16, 26 * 60 + 5, 3, 15.0, 0.3, 100),    # cfg3's settings, parked from level 2 (120 subsets)
+    (16, 26 * 40, 9, 4.0, None, 16),         # parked at level 1, min_cameras ends the search early
+    (12, 26 * 30, 2, 1e-3, 0.3, 200),        # exact-count kernel (downdate rule), parked from level 3
+    (13, 26 * 20, 2, 1e-3, 0.3, 500),        # 13 of 16: the sum-of-kept-blocks form beyond level 6
+    (24, 26 * 8, 20, 1e-3, 0.3, 2048),       # C(24, 3) = 2024 stays, C(24, 4) = 10 626 is parked
+    (32, 26 * 3, 28, 1e-3, 0.3, 2048),       # C(32, 3) = 4 960, C(32, 4) = 35 960
+    (7, 26 * 100 + 3, 2, 1e-3, 0.3, 7),      # small rig, everything parked at level 1; ragged last tile
+    (5, 26 * 100, 3, 2.0, None, 10),         # parked at level 2 only
+    (6, 26 * 800, 2, 1e-3, 0.3, 2),          # 20 800 parked units: more than the list holds (16 384), the rest stay in the kernel
+])
+def test_deep_levels_equal_single_kernel_search(engine, C, U, mc, thr, lik_thr, deep_min):
+    """`deep_search_kernel` (units pending at a level of >= deep_min camera subsets are parked by the lean search kernel and
+    searched by a 512-thread CTA each) against the search that never parks — the same call with `p2s_set_deep_search(h, 0)`
+    and the statistics launch, which never parks either: bit for bit, incl. NaN coordinates under a valid likelihood, zero
+    and NaN likelihoods, thresholds that send every unit through every level, list overflow, ragged tiles."""
+    import torch
+    P, x, y, w = _deep_case(C, U, 4000 + C)
+    xs, ys, ls = (torch.from_numpy(a).cuda() for a in (x, y, w))
+    try:
+        engine.set_deep_search(deep_min)
+        deep = engine.triangulate_planes(xs, ys, ls, P, lik_thr, thr, mc)
+        torch.cuda.synchronize()
+        engine.set_deep_search(0)
+        flat = engine.triangulate_planes(xs, ys, ls, P, lik_thr, thr, mc)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_deep_search(2048)
+    st = engine.new_stats()
+    counted = engine.triangulate_planes(xs, ys, ls, P, lik_thr, thr, mc, stats=st)
+    torch.cuda.synchronize()
+    for other in (flat, counted):
+        for k in ("Q", "err", "nexcl", "mask"):
+            a, b = deep[k].cpu().numpy(), other[k].cpu().numpy()
+            assert np.array_equal(a, b, equal_nan=True), (k, int((~((a == b) | ((a != a) & (b != b)))).sum()))
+    from pose2sim_b200 import ops
+    hist = ops.stats_dict(st.cpu().numpy())["level_hist"]
+    assert sum(hist[1:]) > 0                                        # the case does reach the levels it parks
+
+
+@pytest.mark.parametrize("C,mc,thr,deep_min", [(8, 2, 1e-3, 8), (8, 3, 15.0, 28), (16, 3, 15.0, 16), (4, 2, 1e-3, 4)])
+def test_deep_levels_staged_path_and_oracle(engine, C, mc, thr, deep_min):
+    """The staged-buffer entry point (`p2s_triangulate_device`, also at 4 / 8 cameras where the raw-plane path runs the RAW
+    instantiation, which never parks) with parked units against the NumPy oracle."""
+    import torch
+    wl = synth.make_triangulation_workload(C, 10, 1, 26, seed=900 + C, lik_thr=None, p_out=0.15, p_low=0.1)
+    x, y, lik = (torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik"))
+    try:
+        engine.set_deep_search(deep_min)
+        out = engine.triangulate(engine.stage_observations(x, y, lik, 0.3), wl["P"], thr, mc)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_deep_search(2048)
+    gx, gy, gl = synth.gate_likelihood(wl["x"], wl["y"], wl["lik"], 0.3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Q, err, nexcl, mask = orc.triangulate_units(gx.astype(float), gy.astype(float), gl.astype(float), wl["P"], thr, mc)
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    got["mask"] = got["mask"].view(np.uint32)
+    compare(got, Q, err, nexcl, mask, thr)

@@ -56,6 +56,8 @@ def time_one(workload, steps):
     F = min(cfg["F"], 100_000)
     wl = synth.make_triangulation_workload(cfg["C"], F, cfg["N"], cfg["K"], seed=cfg["seed"], lik_thr=None)
     eng = ops.get_engine(0)
+    if "P2S_DEEP_MIN" in os.environ:                     # A/B of the deep-level kernel: 0 = the single-kernel search
+        eng.set_deep_search(int(os.environ["P2S_DEEP_MIN"]))
     x, y, lik = (torch.from_numpy(wl[k]).cuda() for k in ("x", "y", "lik"))
     stats = eng.new_stats()
     out = eng.triangulate_planes(x, y, lik, wl["P"], cfg["lik_thr"], cfg["thr"], cfg["min_cams"], stats=stats)
@@ -73,7 +75,8 @@ def time_one(workload, steps):
     ms = e0.elapsed_time(e1) / steps
     chk = float(torch.nansum(out["Q"]).item()) + float(torch.nansum(out["err"]).item()) + float(out["mask"].sum().item())
     U = x.shape[0]
-    print(json.dumps({"lib": os.path.basename(os.environ.get("P2S_LIB", "default")), "workload": workload, "kernel_ms": ms,
+    print(json.dumps({"lib": os.path.basename(os.environ.get("P2S_LIB", "default")), "deep_min": os.environ.get("P2S_DEEP_MIN", "default"),
+                      "workload": workload, "kernel_ms": ms,
                       "units_per_s": U / ms * 1e3, "grid": eng.last_grid(), "ctas_per_sm": eng.last_grid() / eng.info["sm_count"],
                       "cands": st["candidates"], "solver_steps_per_cand": st["solver_steps"] / max(st["candidates"], 1),
                       "checksum": chk}))
