@@ -1330,6 +1330,14 @@ struct DeepArgs {
 };
 
 constexpr int kDeepThreads = 512;
+// CTAs of the deep-level kernel per SM's worth of grid.  A parked unit costs between ~9 rounds (one level of 4 368 subsets)
+// and several hundred, and one CTA is resident per SM: with the list strided over 2 x SMs CTAs every CTA walked ~7 units
+// of cfg3's ~2 000 and the kernel waited for the unluckiest sum (ncu: SMs active 46 % of its 297 us).  With 16 x SMs CTAs a
+// CTA walks one or two units and the hardware's block scheduler does the balancing; a CTA beyond the parked count exits
+// on its first comparison.
+#ifndef P2S_DEEP_GRID_MULT
+#define P2S_DEEP_GRID_MULT 16
+#endif
 
 struct DeepSlab {
     double sP[P2S_MAX_CAMS * 12];
@@ -1363,7 +1371,7 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
     asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned int n = *reinterpret_cast<const volatile unsigned int *>(a.count);
     if (n > a.cap) n = a.cap;
-    if (n == 0u) return;
+    if (blockIdx.x >= n) return;                               // (n == 0 included) more CTAs than parked units: nothing to stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
@@ -1913,7 +1921,7 @@ static cudaError_t launch_dependent(Kern kern, unsigned grid, size_t smem, cudaS
 }
 
 // The deep-level kernel between the search kernel and the fix-up kernel (only when deep_applies()).  Every CTA reads the
-// parked count first and returns at once when it is zero.
+// parked count first and returns at once when its index is beyond it.
 static cudaError_t launch_deep(const TriLaunch &L) {
     CamParams<P2S_MAX_CAMS> cams;
     for (int c = 0; c < P2S_MAX_CAMS; ++c)
@@ -1940,7 +1948,7 @@ static cudaError_t launch_deep(const TriLaunch &L) {
     for (int m = 1; m <= P2S_MAX_CAMS; ++m) a.rinv[m] = 1.0 / (double)m;
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.list = L.deep_list; a.cap = L.deep_cap; a.count = L.tile_counter + 3;
-    return launch_dependent_block(deep_search_kernel, (unsigned)(2 * L.sm_count), (unsigned)kDeepThreads, 0, L.stream, cams, a);
+    return launch_dependent_block(deep_search_kernel, (unsigned)(P2S_DEEP_GRID_MULT * L.sm_count), (unsigned)kDeepThreads, 0, L.stream, cams, a);
 }
 
 // The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 256
