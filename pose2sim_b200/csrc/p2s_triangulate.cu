@@ -1330,6 +1330,7 @@ struct DeepArgs {
 };
 
 constexpr int kDeepThreads = 512;
+constexpr int kDeepClusterMax = 8;
 // CTAs of the deep-level kernel per SM's worth of grid.  A parked unit costs between ~9 rounds (one level of 4 368 subsets)
 // and several hundred, and one CTA is resident per SM: with the list strided over 2 x SMs CTAs every CTA walked ~7 units
 // of cfg3's ~2 000 and the kernel waited for the unluckiest sum (ncu: SMs active 46 % of its 297 us).  With 16 x SMs CTAs a
@@ -1337,6 +1338,15 @@ constexpr int kDeepThreads = 512;
 // on its first comparison.
 #ifndef P2S_DEEP_GRID_MULT
 #define P2S_DEEP_GRID_MULT 16
+#endif
+// CTAs per parked unit (thread-block cluster; 1 = one CTA per unit).  One 512-thread CTA already saturates its SM's FP64
+// pipe, so the kernel lasted as long as its ONE longest unit (levels 5-7 of a 16-camera rig: 23 816 subsets = 47 rounds,
+// ~290 us of the kernel's 297, and the grid above changed nothing): only more SMs per unit shorten it.  The CTAs of a
+// cluster each stage the unit, split every level's subsets, exchange their level winners through distributed shared
+// memory (each CTA stores its winner into every CTA's slab, one cluster barrier per level) and all apply the level rules
+// to the same merged winner.  (key, subset index) is a total order, so the winner does not depend on the split.
+#ifndef P2S_DEEP_CLUSTER
+#define P2S_DEEP_CLUSTER 4
 #endif
 
 struct DeepSlab {
@@ -1352,7 +1362,36 @@ struct DeepSlab {
     unsigned long long rkey;
     double rq[3];
     uint32_t rcm, nan0, inv0;
+    // cluster form (KC > 1): every CTA of the cluster stores its level winner into slot [phase][its rank] of EVERY CTA's
+    // slab (distributed shared memory), phase alternating per level so that a slot is rewritten two cluster barriers later
+    unsigned long long ckey[2][kDeepClusterMax];
+    double cq[2][kDeepClusterMax][3];
+    uint32_t ccand[2][kDeepClusterMax], ccm[2][kDeepClusterMax];
 };
+
+// distributed-shared-memory stores / cluster barrier of the cluster form
+__device__ __forceinline__ uint32_t dsmem_addr(const void *own_smem, uint32_t cta_rank) {
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(own_smem), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+    return remote;
+}
+__device__ __forceinline__ void dsmem_st_u64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 // (key, candidate) arg-min over the lanes in `mask`: smallest 64-bit key, then the smallest candidate index among its
 // holders (np.nanargmin's first index).  Returns true on the one winning lane; false everywhere when no lane holds a candidate.
@@ -1365,18 +1404,24 @@ __device__ __forceinline__ bool deep_argmin(uint32_t mask, unsigned long long ke
     return is_min && cand == mc;
 }
 
+template <int KC>
 __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamParams<P2S_MAX_CAMS> cams, const DeepArgs a) {
+    static_assert(KC >= 1 && KC <= kDeepClusterMax, "cluster size");
     __shared__ DeepSlab S;
     // programmatic dependent launch: nothing the search kernel wrote is read before it has completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned int n = *reinterpret_cast<const volatile unsigned int *>(a.count);
     if (n > a.cap) n = a.cap;
-    if (blockIdx.x >= n) return;                               // (n == 0 included) more CTAs than parked units: nothing to stage
+    // KC CTAs (one thread-block cluster) share a parked unit; the whole cluster leaves together
+    const unsigned int team = blockIdx.x / (unsigned)KC, n_teams = gridDim.x / (unsigned)KC;
+    const uint32_t crank = (KC > 1) ? cluster_cta_rank() : 0u;
+    if (team >= n) return;                                     // (n == 0 included) more teams than parked units: nothing to stage
+    uint32_t phase = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.n_cams;
     const uint32_t cmask = (C >= 32) ? 0xffffffffu : ((1u << C) - 1u);
     for (int i = tid; i < C * 12; i += kDeepThreads) S.sP[i] = (&cams.P[0][0])[i];
-    for (unsigned int j = blockIdx.x; j < n; j += gridDim.x) {
+    for (unsigned int j = team; j < n; j += n_teams) {
         __syncthreads();                                       // sP is there; the previous unit's slab has been read
         const unsigned long long rec = a.list[j];
         const long long u = (long long)(rec >> 8);
@@ -1452,8 +1497,11 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
             unsigned long long bkey = P2S_KEY_EMPTY;
             uint32_t bcand = 0xffffffffu, bcm = 0;
             double bqx = nan64(), bqy = bqx, bqz = bqx;
+            // KC == 1: candidates strided over the threads.  Cluster: strided over the KC * 512 threads with the CTAs
+            // interleaved at warp granularity, so a level's last, partial round is spread over all the SMs of the cluster
+            const uint32_t cand0 = (KC > 1) ? (uint32_t)((warp * KC + (int)crank) * 32 + lane) : (uint32_t)tid;
 #pragma unroll 1
-            for (uint32_t cand = (uint32_t)tid; cand < ncand; cand += (uint32_t)kDeepThreads) {
+            for (uint32_t cand = cand0; cand < ncand; cand += (uint32_t)(kDeepThreads * KC)) {
                 const uint32_t cm = tabled ? __ldg(table + cand) : unrank_subset(C, k, cand);
                 const uint32_t valid = cmask & ~(u_inv0 | cm);
                 const int m = __popc(valid);
@@ -1505,29 +1553,73 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
             }
             if (holders == 0u && lane == 0) { S.wkey[warp] = P2S_KEY_EMPTY; S.wcand[warp] = 0xffffffffu; }   // fewer candidates than threads
             __syncthreads();
-            if (warp == 0) {
-                const bool in = lane < kDeepThreads / 32;
-                const unsigned long long wk = in ? S.wkey[lane] : P2S_KEY_EMPTY;
-                const uint32_t wc = in ? S.wcand[lane] : 0xffffffffu;
-                if (deep_argmin(P2S_FULL, wk, wc)) {
-                    S.rkey = wk; S.rcm = S.wcm[lane];
-                    S.rq[0] = S.wq[lane][0]; S.rq[1] = S.wq[lane][1]; S.rq[2] = S.wq[lane][2];
+            double rqx, rqy, rqz;
+            uint32_t rcm_;
+            if constexpr (KC == 1) {
+                if (warp == 0) {
+                    const bool in = lane < kDeepThreads / 32;
+                    const unsigned long long wk = in ? S.wkey[lane] : P2S_KEY_EMPTY;
+                    const uint32_t wc = in ? S.wcand[lane] : 0xffffffffu;
+                    if (deep_argmin(P2S_FULL, wk, wc)) {
+                        S.rkey = wk; S.rcm = S.wcm[lane];
+                        S.rq[0] = S.wq[lane][0]; S.rq[1] = S.wq[lane][1]; S.rq[2] = S.wq[lane][2];
+                    }
                 }
+                __syncthreads();
+                err_min = key_err(S.rkey);
+                rqx = S.rq[0]; rqy = S.rq[1]; rqz = S.rq[2]; rcm_ = S.rcm;
+            } else {
+                if (warp == 0) {
+                    const bool in = lane < kDeepThreads / 32;
+                    const unsigned long long wk = in ? S.wkey[lane] : P2S_KEY_EMPTY;
+                    const uint32_t wc = in ? S.wcand[lane] : 0xffffffffu;
+                    const bool won = deep_argmin(P2S_FULL, wk, wc);
+                    const bool none = __ballot_sync(P2S_FULL, won) == 0u;      // this CTA drew no candidate of the level
+                    if (won || (none && lane == 0)) {
+                        const unsigned long long key = won ? wk : P2S_KEY_EMPTY;
+                        const uint32_t cand = won ? wc : 0xffffffffu, cmw = won ? S.wcm[lane] : 0u;
+                        const double q0 = won ? S.wq[lane][0] : nan64(), q1 = won ? S.wq[lane][1] : nan64(),
+                                     q2 = won ? S.wq[lane][2] : nan64();
+#pragma unroll
+                        for (uint32_t p = 0; p < (uint32_t)KC; ++p) {
+                            dsmem_st_u64(dsmem_addr(&S.ckey[phase][crank], p), key);
+                            dsmem_st_u32(dsmem_addr(&S.ccand[phase][crank], p), cand);
+                            dsmem_st_u32(dsmem_addr(&S.ccm[phase][crank], p), cmw);
+                            dsmem_st_f64(dsmem_addr(&S.cq[phase][crank][0], p), q0);
+                            dsmem_st_f64(dsmem_addr(&S.cq[phase][crank][1], p), q1);
+                            dsmem_st_f64(dsmem_addr(&S.cq[phase][crank][2], p), q2);
+                        }
+                    }
+                }
+                cluster_barrier();                             // release / acquire: every CTA's slots of this phase are complete
+                // every thread of every CTA picks the same winner: smallest key, then the smallest candidate index
+                unsigned long long gk = P2S_KEY_EMPTY;
+                uint32_t gc = 0xffffffffu;
+                int gp = 0;
+#pragma unroll
+                for (int p = 0; p < KC; ++p) {
+                    const unsigned long long pk = S.ckey[phase][p];
+                    const uint32_t pc = S.ccand[phase][p];
+                    if (pc != 0xffffffffu && (gc == 0xffffffffu || pk < gk || (pk == gk && pc < gc))) { gk = pk; gc = pc; gp = p; }
+                }
+                err_min = key_err(gk);
+                rqx = S.cq[phase][gp][0]; rqy = S.cq[phase][gp][1]; rqz = S.cq[phase][gp][2]; rcm_ = S.ccm[phase][gp];
+                phase ^= 1u;
             }
-            __syncthreads();
-            err_min = key_err(S.rkey);
             // the reference's loop condition (:408) and break rule (:437-441) for the next level
             const bool go_on = (err_min > a.thr) && (C - (k + 1) >= a.min_cams) && !(min(C, ninv0 + k + 1) > C - a.min_cams);
-            if (!go_on) break;
-            __syncthreads();                                   // every thread has read the level's result
-        }
-        if (tid == 0) {
-            const bool failed = err_min > a.thr;
-            double *q = a.out_Q + u * 3;
-            q[0] = failed ? nan64() : S.rq[0]; q[1] = failed ? nan64() : S.rq[1]; q[2] = failed ? nan64() : S.rq[2];
-            a.out_err[u] = failed ? nan64() : err_min;
-            a.out_nexcl[u] = (uint8_t)__popc(u_inv0 | S.rcm);
-            a.out_mask[u] = u_nan0 | S.rcm;
+            if (!go_on) {
+                if (tid == 0 && crank == 0u) {
+                    const bool failed = err_min > a.thr;
+                    double *q = a.out_Q + u * 3;
+                    q[0] = failed ? nan64() : rqx; q[1] = failed ? nan64() : rqy; q[2] = failed ? nan64() : rqz;
+                    a.out_err[u] = failed ? nan64() : err_min;
+                    a.out_nexcl[u] = (uint8_t)__popc(u_inv0 | rcm_);
+                    a.out_mask[u] = u_nan0 | rcm_;
+                }
+                break;
+            }
+            if constexpr (KC == 1) __syncthreads();            // every thread has read the level's result
         }
     }
 }
@@ -1948,7 +2040,25 @@ static cudaError_t launch_deep(const TriLaunch &L) {
     for (int m = 1; m <= P2S_MAX_CAMS; ++m) a.rinv[m] = 1.0 / (double)m;
     a.out_Q = L.out_Q; a.out_err = L.out_err; a.out_nexcl = L.out_nexcl; a.out_mask = L.out_mask;
     a.list = L.deep_list; a.cap = L.deep_cap; a.count = L.tile_counter + 3;
-    return launch_dependent_block(deep_search_kernel, (unsigned)(P2S_DEEP_GRID_MULT * L.sm_count), (unsigned)kDeepThreads, 0, L.stream, cams, a);
+    // P2S_DEEP_CLUSTER CTAs (one thread-block cluster, portable size) per parked unit; the grid stays a multiple of it
+    constexpr unsigned KC = P2S_DEEP_CLUSTER;
+    const unsigned grid = ((unsigned)(P2S_DEEP_GRID_MULT * L.sm_count) + KC - 1u) / KC * KC;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)kDeepThreads); cfg.dynamicSmemBytes = 0; cfg.stream = L.stream;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+#ifndef P2S_NO_PDL
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+#endif
+    if (KC > 1u) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = KC; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, deep_search_kernel<(int)KC>, cams, a);
 }
 
 // The wide-spread / arrival-flag kernel behind the main one.  Always launched: that a likelihood threshold >= 1 / 256
