@@ -118,7 +118,7 @@ int p2s_set_search_mode(p2s_handle *h, int mode);
 
 /* deep levels of the exclusion search (triangulation.py:408-411: level k enumerates ALL C(n_cams, k) camera subsets).
  * A unit that is pending at a level of at least `min_candidates` subsets is not walked by the one warp that holds its
- * tile: it is parked, and a second kernel behind the search kernel gives every parked unit a 512-thread CTA (same
+ * tile: it is parked, and a second kernel behind the search kernel gives every parked unit a cluster of two 512-thread CTAs (same
  * arithmetic, same outputs bit for bit).  Default 2048 — C(16, 5) = 4368, C(32, 3) = 4960: rigs of 14 cameras and up;
  * 0 = never park (the single-kernel search); small values exercise the path on small rigs (tests).  Launches that ask
  * for the statistics block, the Jacobi solver or a lens model never park.                                            */

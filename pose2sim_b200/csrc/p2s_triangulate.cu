@@ -1295,14 +1295,14 @@ __global__ void __launch_bounds__(128, P2S_TRI_MIN_BLOCKS) triangulate_pool_kern
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-// ---- deep levels: one 512-thread CTA per parked unit ---------------------------------------------------------------
+// ---- deep levels: a cluster of 512-thread CTAs per parked unit -------------------------------------------------------
 // triangulate_kernel walks a level's candidates with the 32 lanes of ONE warp.  That is the right shape while levels hold
 // tens or hundreds of candidates, but C(16, 5..8) = 4 368 .. 12 870 and C(32, 4) = 35 960: a unit that goes that deep keeps
 // its warp for hundreds of rounds, and the SM that drew it is still busy when every other SM has run out of tiles (cfg3
 // shard, ncu: SMs active 73 % of the kernel's duration, the longest 9.5 M cycles against a mean of 6.9 M).  Such units are
 // rare (6e-4 of cfg3's), so the main kernel parks them — (unit, level) in a list, at the first level with >= deep_min
 // candidates — and this kernel, launched behind it, re-stages a parked unit and walks the rest of its search with 512
-// threads: candidates strided over the threads, the (error key, candidate index) arg-min reduced per warp and then across
+// threads per CTA (P2S_DEEP_CLUSTER CTAs per unit, below): candidates strided over the threads, the (error key, candidate index) arg-min reduced per warp and then across
 // the 16 warps, the level rules of triangulation.py:408-505 applied by every thread on the published result.
 // The arithmetic is the main kernel's, statement for statement (level-0 matrix accumulated over the cameras in ascending
 // order, camera blocks from camera_block(), M = M_all - excluded blocks or the sum of the kept ones by the same rule,
@@ -1339,14 +1339,17 @@ constexpr int kDeepClusterMax = 8;
 #ifndef P2S_DEEP_GRID_MULT
 #define P2S_DEEP_GRID_MULT 16
 #endif
-// CTAs per parked unit (thread-block cluster; 1 = one CTA per unit).  One 512-thread CTA already saturates its SM's FP64
-// pipe, so the kernel lasted as long as its ONE longest unit (levels 5-7 of a 16-camera rig: 23 816 subsets = 47 rounds,
-// ~290 us of the kernel's 297, and the grid above changed nothing): only more SMs per unit shorten it.  The CTAs of a
-// cluster each stage the unit, split every level's subsets, exchange their level winners through distributed shared
-// memory (each CTA stores its winner into every CTA's slab, one cluster barrier per level) and all apply the level rules
-// to the same merged winner.  (key, subset index) is a total order, so the winner does not depend on the split.
+// CTAs per parked unit (thread-block cluster; 1 = one CTA per unit).  The kernel lasted as long as its longest unit
+// (levels 5-7 of a 16-camera rig: 23 816 subsets = 47 rounds of 512 threads, ~290 us of the kernel's 297; the grid above
+// changed nothing), so a unit gets the SMs of a cluster: its CTAs each stage the unit, split every level's subsets (warp
+// interleaved), exchange their level winners through distributed shared memory (each CTA stores its winner into every
+// CTA's slab, one cluster barrier per level) and all apply the level rules to the same merged winner.  (key, subset index)
+// is a total order, so the winner does not depend on the split.  How many: a round is latency-bound (four warps per
+// scheduler on a dependent DFMA chain), it takes about as long with two warps as with sixteen, so a level that fills
+// fewer rounds than CTAs x 512 threads costs SM-time in proportion to the cluster size.  Same-box A/B on the cfg3 shard
+// (profiles/r3v_kernel_ab_deep.jsonl), 1 / 2 / 4 / 8 CTAs: 3.954 / 3.885 / 3.909 / 4.029 ms, identical checksums.
 #ifndef P2S_DEEP_CLUSTER
-#define P2S_DEEP_CLUSTER 4
+#define P2S_DEEP_CLUSTER 2
 #endif
 
 struct DeepSlab {
