@@ -1556,8 +1556,8 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
             }
             if (holders == 0u && lane == 0) { S.wkey[warp] = P2S_KEY_EMPTY; S.wcand[warp] = 0xffffffffu; }   // fewer candidates than threads
             __syncthreads();
-            double rqx, rqy, rqz;
-            uint32_t rcm_;
+            double win_qx, win_qy, win_qz;
+            uint32_t win_cm;
             if constexpr (KC == 1) {
                 if (warp == 0) {
                     const bool in = lane < kDeepThreads / 32;
@@ -1570,7 +1570,7 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
                 }
                 __syncthreads();
                 err_min = key_err(S.rkey);
-                rqx = S.rq[0]; rqy = S.rq[1]; rqz = S.rq[2]; rcm_ = S.rcm;
+                win_qx = S.rq[0]; win_qy = S.rq[1]; win_qz = S.rq[2]; win_cm = S.rcm;
             } else {
                 if (warp == 0) {
                     const bool in = lane < kDeepThreads / 32;
@@ -1606,7 +1606,7 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
                     if (pc != 0xffffffffu && (gc == 0xffffffffu || pk < gk || (pk == gk && pc < gc))) { gk = pk; gc = pc; gp = p; }
                 }
                 err_min = key_err(gk);
-                rqx = S.cq[phase][gp][0]; rqy = S.cq[phase][gp][1]; rqz = S.cq[phase][gp][2]; rcm_ = S.ccm[phase][gp];
+                win_qx = S.cq[phase][gp][0]; win_qy = S.cq[phase][gp][1]; win_qz = S.cq[phase][gp][2]; win_cm = S.ccm[phase][gp];
                 phase ^= 1u;
             }
             // the reference's loop condition (:408) and break rule (:437-441) for the next level
@@ -1615,10 +1615,10 @@ __global__ void __launch_bounds__(kDeepThreads, 1) deep_search_kernel(const CamP
                 if (tid == 0 && crank == 0u) {
                     const bool failed = err_min > a.thr;
                     double *q = a.out_Q + u * 3;
-                    q[0] = failed ? nan64() : rqx; q[1] = failed ? nan64() : rqy; q[2] = failed ? nan64() : rqz;
+                    q[0] = failed ? nan64() : win_qx; q[1] = failed ? nan64() : win_qy; q[2] = failed ? nan64() : win_qz;
                     a.out_err[u] = failed ? nan64() : err_min;
-                    a.out_nexcl[u] = (uint8_t)__popc(u_inv0 | rcm_);
-                    a.out_mask[u] = u_nan0 | rcm_;
+                    a.out_nexcl[u] = (uint8_t)__popc(u_inv0 | win_cm);
+                    a.out_mask[u] = u_nan0 | win_cm;
                 }
                 break;
             }
