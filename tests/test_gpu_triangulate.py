@@ -61,6 +61,24 @@ def test_reference_random_units(engine, golden):
     assert worst < 1e-9          # in practice ~1e-13 m: far inside the 1e-6 m bar
 
 
+@pytest.mark.parametrize("deep_min", [2048, 0, 64])
+def test_reference_deep_units(engine, golden, deep_min):
+    """Units of 12 / 13 / 16 / 20-camera rigs that the unmodified reference walked through levels of thousands of camera
+    subsets (tests/golden/tri_deep_units.npz, oracle/make_golden_deep.py; triangulation.py:408-505): the wide-rig kernels
+    with the deep levels parked for deep_search_kernel (default threshold), searched in place (0) and parked early (64)."""
+    g = golden("tri_deep_units.npz")
+    worst = 0.0
+    try:
+        engine.set_deep_search(deep_min)
+        for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+            out = run_gpu(engine, P, x, y, w, thr, mc)
+            assert compare(out, Q, err, nexcl, mask, thr, allow_band=False) == 0, name
+            worst = max(worst, float(np.nanmax(np.abs(out["Q"] - Q), initial=0.0)))
+    finally:
+        engine.set_deep_search(2048)
+    assert worst < 1e-9, worst
+
+
 def test_wide_likelihood_spread_matches_reference(engine, golden):
     """Valid likelihoods of one unit spanning 1e-4 ... 1 and 1e-6 ... 1 (`likelihood_threshold_triangulation = 0` is a
     legal configuration): the reference takes the SVD of A (common.py:347-350); the normal matrix would be off by up to

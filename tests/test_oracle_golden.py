@@ -56,6 +56,17 @@ def test_random_units(golden):
         _check_units(*case[1:])
 
 
+def test_deep_units(golden):
+    """Wide rigs (12 / 13 / 16 / 20 cameras) walked by the unmodified reference through levels of thousands of camera
+    subsets (oracle/make_golden_deep.py).  The NumPy restatement takes a few units per case (it costs what the reference
+    costs per subset); the plain-C oracle below takes all of them."""
+    g = golden("tri_deep_units.npz")
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        order = np.argsort(-nexcl.astype(int), kind="stable")[:2]          # the two deepest units of the case
+        sel = np.unique(np.concatenate([order, np.arange(0, len(nexcl), 9)]))
+        _check_units(P, x[sel], y[sel], w[sel], thr, mc, Q[sel], err[sel], nexcl[sel], mask[sel])
+
+
 def test_cfg1_demo_cameras(golden):
     g = golden("tri_cfg1_demo.npz")
     thr, mc = g["params"]
@@ -153,6 +164,15 @@ def test_c_oracle_triangulation(golden):
             assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask), name
             assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
             assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+    g = golden("tri_deep_units.npz")                                     # 12-20 cameras, levels of thousands of subsets
+    deepest = 0
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        q, e, nx, m, lv, nc = co.triangulate_units(x, y, w, P, thr, mc)
+        assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask), name
+        assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+        assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+        deepest = max(deepest, int(lv.max()))
+    assert deepest >= 6                                                  # some unit did enumerate C(16, 5) and C(16, 6)
     g = golden("tri_cfg1_demo.npz")
     q, e, nx, m, lv, nc = co.triangulate_units(g["x"], g["y"], g["w"], g["P"], 15.0, 2)
     assert np.array_equal(nx, g["nexcl"].astype(np.uint8)) and np.array_equal(m, g["mask"])
