@@ -130,6 +130,36 @@ def test_six_person_association_frames(golden):
         assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
 
 
+def test_wide_rig_association_frames(golden):
+    """6 / 7 / 8-camera rigs (BASELINE configs[3]'s camera count) with 2-4 persons per camera, searches that reach
+    levels 1-2 of thousands of rows, reference-generated (oracle/make_golden_wide_assoc.py)."""
+    import c_oracle as co
+    g = golden("assoc_wide_rigs.npz")
+    off = 0
+    for i in range(int(g["assoc_n"])):
+        p = f"assoc{i}_"
+        thr, lt, mc = g[p + "params"]
+        e, comb, Q = co.associate_frames(g[p + "obs"], g[p + "count"], g[p + "P"], float(thr), float(lt), int(mc))
+        assert np.array_equal(comb.astype(int), np.nan_to_num(g[p + "comb"], nan=-1).astype(int)), i
+        fin = np.isfinite(g[p + "err"])
+        assert np.array_equal(np.isinf(e), ~fin)
+        assert np.allclose(e[fin], g[p + "err"][fin], atol=E_TOL, rtol=0)
+        assert np.allclose(Q, g[p + "Q"], atol=Q_TOL, rtol=0, equal_nan=True)
+        off = max(off, int(np.isnan(g[p + "comb"]).sum(1).max()))
+    assert off >= 2                                   # some frame did drop two cameras
+    # the NumPy restatement on the two cheapest configurations' first frames
+    for p in ("assoc1_", "assoc3_"):
+        thr, lt, mc = g[p + "params"]
+        obs, cnt = g[p + "obs"].astype(float), g[p + "count"]
+        for f in range(0, 3):
+            ob = [[obs[f, c, pp] for pp in range(cnt[f, c])] for c in range(obs.shape[1])]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                e, comb, Q = orc.associate_frame(ob, list(cnt[f]), g[p + "P"], float(thr), float(lt), int(mc))
+            assert np.array_equal(np.nan_to_num(comb, nan=-1), np.nan_to_num(g[p + "comb"][f], nan=-1)), (p, f)
+            assert np.allclose(Q, g[p + "Q"][f], atol=Q_TOL, rtol=0, equal_nan=True)
+
+
 def test_wide_likelihood_association_frames(golden):
     import c_oracle as co
     g = golden("assoc_wide_likelihood.npz")
