@@ -4,7 +4,7 @@ subsets — thousands at 12-20 cameras), same key layout as tri_random_units.npz
 
 Run in the build container only (needs /root/reference; ~10 minutes, the reference spends ~0.15 ms per subset):
 
-    python oracle/make_golden_deep.py
+    python oracle/make_golden_deep.py [--widest-only]
 
 Why a separate set: tri_random_units.npz stops at 8 cameras.  Beyond that the CUDA path runs other instantiations
 (12 / 16 exact-count kernels, 13 / 20 cameras on the next wider one), forms a candidate's normal matrix by the
@@ -35,13 +35,21 @@ CASES = [
     (20, 16, 16, 15.0, 0.15, 0.04, 0.02),   # C(20, 4) = 4 845
 ]
 
+# tests/golden/tri_widest_units.npz: BASELINE configs[4]'s widest rigs (search capped at four exclusions by min_cameras,
+# like tests/perf/sweep_cfg5.py); pins the ORACLES to the reference there (CPU tests) — the CUDA path is pinned to the
+# oracles at these widths by the fuzzers and the cfg5 sweep
+CASES_WIDEST = [
+    (24, 14, 20, 15.0, 0.10, 0.03, 0.02),   # C(24, 3) = 2 024, C(24, 4) = 10 626
+    (32, 10, 29, 15.0, 0.05, 0.02, 0.01),   # C(32, 3) = 4 960
+    (28, 10, 25, 10.0, 0.06, 0.03, 0.02),   # not an exact-count rig
+]
 
-def main():
-    ref = ref_shim.load_reference()
+
+def generate(ref, cases, seed0, fname):
     out = {}
-    for i, (C, U, mc, thr, p_out, p_nan, p_zero) in enumerate(CASES):
+    for i, (C, U, mc, thr, p_out, p_nan, p_zero) in enumerate(cases):
         t0 = time.time()
-        P, x, y, w = random_units(C, U, seed=7000 + i, p_out=p_out, p_nan=p_nan, p_zero=p_zero)
+        P, x, y, w = random_units(C, U, seed=seed0 + i, p_out=p_out, p_nan=p_nan, p_zero=p_zero)
         Q, err, nexcl, mask = run_reference_units(ref, x, y, w, P, thr, mc)
         pre = f"r{i}_"
         out[pre + "P"], out[pre + "x"], out[pre + "y"], out[pre + "w"] = P, x, y, w
@@ -50,8 +58,15 @@ def main():
         print(f"  deep units C={C} U={U} min_cams={mc} thr={thr}: nexcl histogram "
               f"{np.bincount(nexcl, minlength=C + 1).tolist()}, {int(np.isnan(err).sum())} failed, {time.time() - t0:.0f} s",
               flush=True)
-    out["n"] = np.array(len(CASES))
-    np.savez_compressed(os.path.join(GOLDEN, "tri_deep_units.npz"), **out)
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLDEN, fname), **out)
+
+
+def main():
+    ref = ref_shim.load_reference()
+    if "--widest-only" not in sys.argv:
+        generate(ref, CASES, 7000, "tri_deep_units.npz")
+    generate(ref, CASES_WIDEST, 7100, "tri_widest_units.npz")
 
 
 if __name__ == "__main__":

@@ -67,6 +67,19 @@ def test_deep_units(golden):
         _check_units(P, x[sel], y[sel], w[sel], thr, mc, Q[sel], err[sel], nexcl[sel], mask[sel])
 
 
+def test_widest_units(golden):
+    """24 / 28 / 32-camera rigs (BASELINE configs[4]'s widest, search capped at three or four exclusions by min_cameras),
+    reference-generated (oracle/make_golden_deep.py): both oracles, every unit."""
+    import c_oracle as co
+    g = golden("tri_widest_units.npz")
+    for name, P, x, y, w, thr, mc, Q, err, nexcl, mask in tri_cases(g, "r{}_", int(g["n"])):
+        _check_units(P, x, y, w, thr, mc, Q, err, nexcl, mask)
+        q, e, nx, m, lv, nc = co.triangulate_units(x, y, w, P, thr, mc)
+        assert np.array_equal(nx, nexcl.astype(np.uint8)) and np.array_equal(m, mask), name
+        assert np.allclose(q, Q, atol=Q_TOL, rtol=0, equal_nan=True)
+        assert np.allclose(e, err, atol=E_TOL, rtol=0, equal_nan=True)
+
+
 def test_cfg1_demo_cameras(golden):
     g = golden("tri_cfg1_demo.npz")
     thr, mc = g["params"]
