@@ -149,17 +149,23 @@ def stage_project(config_dict, rank=0, world=1):
     if index is None:
         _, files = dirs.files_for_association(cam_dirs)
         counts = [len(j) for j in files]
+    mkdir_failure = None
     if rank == 0:
-        if not os.path.exists(dirs.tracked_dir):
-            os.mkdir(dirs.tracked_dir)
-        for d in cam_dirs:
-            try:
-                os.mkdir(os.path.join(dirs.tracked_dir, d))
-            except OSError:
-                break                                         # the reference stops at the first failure (:735-736)
+        try:
+            if not os.path.exists(dirs.tracked_dir):
+                os.mkdir(dirs.tracked_dir)
+            for d in cam_dirs:
+                try:
+                    os.mkdir(os.path.join(dirs.tracked_dir, d))
+                except OSError:
+                    break                                     # the reference stops at the first failure (:735-736)
+        except OSError as e:
+            mkdir_failure = e                                 # raised after the barrier: nobody is left waiting in it
     if world > 1:
         import torch.distributed as dist
         dist.barrier()                                        # the output directories exist before anyone writes
+    if mkdir_failure is not None:
+        raise mkdir_failure
     fr = s["frame_range"]
     f_range = [0, max(counts)] if fr in ("all", "auto", []) else fr
     n_cams = len(cam_dirs)
@@ -415,15 +421,28 @@ def associate_all(config_dict):
     if dist.get_backend() == "nccl":
         import torch
         torch.cuda.set_device(local)                          # the object collectives below use the current device
-    st = stage_project(config_dict, rank, world)
+    # rank-local work first, ONE object collective after it: a rank that fails (a file it alone reads is broken, its
+    # device call errors) reports the failure through the collective instead of leaving the others waiting in it
+    failure, part, st = None, None, None
+    try:
+        st = stage_project(config_dict, rank, world)
+        if st.settings["multi_person"]:
+            proposals = solve_frames_multi_person(st, device=local) if len(st.table) else []
+            write_outputs_multi_person(st, proposals, log=rank == 0)
+        else:
+            res = solve_frames(st, device=local) if len(st.table) else {"err": np.zeros(0), "comb": np.zeros((0, st.n_cams)), "Q": np.zeros((0, 3))}
+            part = write_outputs(st, res, log=False)
+    except Exception as e:                                      # noqa: BLE001 — re-raised below
+        failure = e
+    reports = [None] * world
+    dist.all_gather_object(reports, (part, None if failure is None else f"{type(failure).__name__}: {failure}"))
+    if failure is not None:
+        raise failure
+    failed = [(r, msg) for r, (_, msg) in enumerate(reports) if msg is not None]
+    if failed:
+        raise RuntimeError(f"rank {failed[0][0]} failed in associate_all: {failed[0][1]}")
     if st.settings["multi_person"]:
-        proposals = solve_frames_multi_person(st, device=local) if len(st.table) else []
-        write_outputs_multi_person(st, proposals, log=rank == 0)
-        dist.barrier()
         return
-    res = solve_frames(st, device=local) if len(st.table) else {"err": np.zeros(0), "comb": np.zeros((0, st.n_cams)), "Q": np.zeros((0, 3))}
-    part = write_outputs(st, res, log=False)
-    parts = [None] * world
-    dist.all_gather_object(parts, part)
+    parts = [p for p, _ in reports]
     if rank == 0:
         log_recap(st, [e for p in parts for e in p["error"]], [c for p in parts for c in p["cameras_off"]])

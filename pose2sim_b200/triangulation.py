@@ -111,14 +111,25 @@ def stage_project(config_dict, rank=0, world=1):
     if s["multi_person"]:
         if files is None:
             files = index.names()
-        n_persons = _stg.count_persons(input_dir, cam_dirs, [f[rank::world] for f in files])
+        # every rank counts its stride of the files; a file that cannot be parsed raises (like the reference, :88-89) — but
+        # only AFTER the all-reduce, so that the ranks whose files are fine are not left waiting in it: the failure is
+        # part of what is reduced and every rank raises
+        failure = None
+        try:
+            n_persons = _stg.count_persons(input_dir, cam_dirs, [f[rank::world] for f in files])
+        except Exception as e:                                  # noqa: BLE001 — re-raised below, on every rank
+            failure, n_persons = e, 0
         if world > 1:
             import torch
             import torch.distributed as dist
             dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))) if dist.get_backend() == "nccl" else "cpu"
-            t = torch.tensor([n_persons], dtype=torch.int64, device=dev)
+            t = torch.tensor([n_persons, 0 if failure is None else 1], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            n_persons = int(t.item())
+            n_persons = int(t[0].item())
+            if failure is None and int(t[1].item()):
+                failure = RuntimeError("another rank could not parse one of its pose files (see its traceback)")
+        if failure is not None:
+            raise failure
     else:
         n_persons = 1
 

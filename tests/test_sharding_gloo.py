@@ -114,6 +114,53 @@ def test_dropin_two_ranks_writes_the_reference_trc(golden, tmp_path, tag):
         assert_trc_equal(got[name], ref[name], tol=1e-6)
 
 
+def _broken_file_worker(rank, world, port, proj, cfg, out_dir):
+    from pose2sim_b200 import triangulation as tri
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        os.chdir(proj)
+        try:
+            tri.triangulate_all(cfg)
+            outcome = "returned"
+        except Exception as e:                                   # noqa: BLE001 — the outcome is what the test reads
+            outcome = type(e).__name__
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unparsable_file_on_one_rank_raises_on_every_rank(golden, tmp_path):
+    """Multi-person person count (triangulation.py:784, :77-90) under a 2-rank job: each rank parses its stride of the
+    files and the counts are all-reduced.  A file only ONE rank reads is broken: both ranks must raise (the reference's
+    JSONDecodeError on the rank that read it), none may be left waiting in the collective."""
+    import glob
+    from dropin_util import rebuild_trial
+    g = golden("e2e_tri_multi.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_broken")
+    cam_dirs = sorted(d for d in glob.glob(os.path.join(proj, "pose*", "*")) if os.path.isdir(d))
+    files = sorted(glob.glob(os.path.join(cam_dirs[0], "*.json")))
+    with open(files[1], "w") as f:                               # index 1 of the camera's list: rank 1's stride only
+        f.write('{"version": 1.3, "people": [')
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_dir = str(tmp_path)
+    ctx = mp.spawn(_broken_file_worker, args=(2, port, proj, cfg, out_dir), nprocs=2, join=False)
+    deadline = 120
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > deadline:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("a rank was left waiting in the person-count all-reduce")
+    outcomes = [open(os.path.join(out_dir, f"rank{r}.txt")).read() for r in range(2)]
+    assert outcomes[1] == "JSONDecodeError", outcomes
+    assert outcomes[0] == "RuntimeError", outcomes
+
+
 # ---- rank-local post-processing: the sharded writer must produce the single-process file byte for byte ----------
 def _variant_worker(rank, world, port, proj, cfg, log_path):
     import logging
@@ -262,3 +309,51 @@ def test_associate_all_two_ranks_writes_the_reference_json(golden, tmp_path, tag
     assert np.array_equal(exists, g["exists"])
     assert np.array_equal(np.isnan(chosen), np.isnan(g["chosen"]))
     assert np.array_equal(np.nan_to_num(chosen).astype(np.float32), np.nan_to_num(g["chosen"]))
+
+
+def _assoc_failing_worker(rank, world, port, proj, cfg, out_dir):
+    from pose2sim_b200 import personAssociation as pa
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def device_call(st, engine=None, device=0):              # TEST stand-in for the device call: rank 1's fails
+        if rank == 1:
+            raise RuntimeError("device call failed on this rank")
+        F, C = st.count.shape
+        return {"err": np.full(F, np.inf), "comb": np.full((F, C), np.nan), "Q": np.full((F, 3), np.nan)}
+
+    pa.solve_frames = pa.solve_frames_multi_person = device_call
+    try:
+        os.chdir(proj)
+        try:
+            pa.associate_all(cfg)
+            outcome = "returned"
+        except Exception as e:                               # noqa: BLE001 — the outcome is what the test reads
+            outcome = f"{type(e).__name__}: {e}"
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_associate_all_failure_on_one_rank_raises_on_every_rank(golden, tmp_path):
+    """associate_all under a 2-rank job does its rank-local work first and meets in ONE object collective: a rank whose
+    device call fails reports that through the collective — it raises its own error, the other rank raises too, and
+    nobody is left waiting."""
+    import time
+    from dropin_util import rebuild_trial
+    g = golden("e2e_assoc_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_assoc_fail")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.spawn(_assoc_failing_worker, args=(2, port, proj, cfg, str(tmp_path)), nprocs=2, join=False)
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > 120:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("a rank was left waiting in associate_all's collective")
+    outcomes = [open(os.path.join(str(tmp_path), f"rank{r}.txt")).read() for r in range(2)]
+    assert outcomes[1] == "RuntimeError: device call failed on this rank", outcomes
+    assert outcomes[0].startswith("RuntimeError: rank 1 failed in associate_all: RuntimeError: device call failed"), outcomes
