@@ -784,6 +784,19 @@ def gather_units(res, n_frames, rank, world):
             "nexcl": out["nexcl"].reshape(n_frames, N, K).astype(np.int64), "mask": out["mask"].reshape(n_frames, N, K)}
 
 
+def raise_together(failure, world, where):
+    """One small object collective: every rank learns whether any rank failed in its rank-local work.  The failing rank
+    raises its own exception, the others a RuntimeError naming it; with no failure it is a no-op."""
+    import torch.distributed as dist
+    reports = [None] * world
+    dist.all_gather_object(reports, None if failure is None else f"{type(failure).__name__}: {failure}")
+    if failure is not None:
+        raise failure
+    failed = [(r, msg) for r, msg in enumerate(reports) if msg is not None]
+    if failed:
+        raise RuntimeError(f"rank {failed[0][0]} failed in {where}: {failed[0][1]}")
+
+
 def triangulate_all(config_dict):
     """Same contract as Pose2Sim/triangulation.py:656: reads the calibration TOML and the per-camera
     OpenPose JSON of the trial, writes `pose-3d/*.trc`, logs the recap.  Returns None.
@@ -800,8 +813,15 @@ def triangulate_all(config_dict):
         if dist.get_backend() == "nccl":
             import torch
             torch.cuda.set_device(local)                    # the collectives below put their tensors on the current device
-        st = stage_project(config_dict, rank, world)
-        res = solve_units(st, device=local)
+        # rank-local work (staging of the own frame block, the device call) first; then the ranks tell each other whether
+        # it worked, so that a rank-local failure raises everywhere instead of leaving the others in the next collective
+        failure, st, res = None, None, None
+        try:
+            st = stage_project(config_dict, rank, world)
+            res = solve_units(st, device=local)
+        except Exception as e:                              # noqa: BLE001 — re-raised by raise_together
+            failure = e
+        raise_together(failure, world, "triangulate_all")
         if rank_local_supported(st) and os.environ.get("P2S_GATHER", "local") != "rank0":
             write_outputs_sharded(st, res, rank, world)     # results stay rank-local: no gather of the 37 B/unit outputs
             return

@@ -357,3 +357,51 @@ def test_associate_all_failure_on_one_rank_raises_on_every_rank(golden, tmp_path
     outcomes = [open(os.path.join(str(tmp_path), f"rank{r}.txt")).read() for r in range(2)]
     assert outcomes[1] == "RuntimeError: device call failed on this rank", outcomes
     assert outcomes[0].startswith("RuntimeError: rank 1 failed in associate_all: RuntimeError: device call failed"), outcomes
+
+
+def _tri_failing_worker(rank, world, port, proj, cfg, out_dir):
+    from pose2sim_b200 import triangulation as tri
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def device_call(st, engine=None, device=0):              # TEST stand-in for the device call: rank 1's fails
+        if rank == 1:
+            raise RuntimeError("device call failed on this rank")
+        F, N, K, C = st.x.shape
+        return {"Q": np.full((F, N, K, 3), np.nan), "err": np.full((F, N, K), np.nan),
+                "nexcl": np.zeros((F, N, K), np.int64), "mask": np.zeros((F, N, K), np.uint32)}
+
+    tri.solve_units = device_call
+    try:
+        os.chdir(proj)
+        try:
+            tri.triangulate_all(cfg)
+            outcome = "returned"
+        except Exception as e:                               # noqa: BLE001 — the outcome is what the test reads
+            outcome = f"{type(e).__name__}: {e}"
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_triangulate_all_failure_on_one_rank_raises_on_every_rank(golden, tmp_path):
+    """triangulate_all under a 2-rank job: a rank whose device call fails raises its own error, the other rank is told
+    through `raise_together` and raises too instead of waiting in the sharded writer's first collective."""
+    import time
+    from dropin_util import rebuild_trial
+    g = golden("e2e_tri_single.npz")
+    proj, cfg = rebuild_trial(g, tmp_path, "trial_tri_fail")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.spawn(_tri_failing_worker, args=(2, port, proj, cfg, str(tmp_path)), nprocs=2, join=False)
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > 120:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("a rank was left waiting in triangulate_all's collectives")
+    outcomes = [open(os.path.join(str(tmp_path), f"rank{r}.txt")).read() for r in range(2)]
+    assert outcomes[1] == "RuntimeError: device call failed on this rank", outcomes
+    assert outcomes[0].startswith("RuntimeError: rank 1 failed in triangulate_all: RuntimeError: device call failed"), outcomes
