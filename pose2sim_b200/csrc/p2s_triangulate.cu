@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(128, CMAX <= 16 ? P2S_TRI_MIN_BLOCKS : CMAX <=
             if constexpr (!STATS && SOLVER == 0 && !DISTORT && !RAW) {
                 // a level of thousands of candidates is not walked by ONE warp (at 16 cameras a unit that reaches level 7
                 // costs 26 k candidates = ~800 rounds, longer than the rest of the launch takes an SM): the unit is parked
-                // and deep_search_kernel, behind this kernel, gives it a whole 512-thread CTA.  Same arithmetic, same result.
+                // and deep_search_kernel, behind this kernel, gives it a cluster of 512-thread CTAs.  Same arithmetic, same result.
                 if (a.deep_list != nullptr && a.ncand[k] >= a.deep_min) {
                     const uint32_t pm = __ballot_sync(P2S_FULL, pend);
                     if (pm != 0u) {

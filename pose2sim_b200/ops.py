@@ -112,7 +112,7 @@ class Engine:
 
     def set_deep_search(self, min_candidates):
         """Triangulation search: a unit pending at a level of >= `min_candidates` camera subsets is parked and searched by
-        a 512-thread CTA of the deep-level kernel instead of by the warp that holds its tile (default 2048; 0 = never).
+        a cluster of two 512-thread CTAs of the deep-level kernel instead of by the warp that holds its tile (default 2048; 0 = never).
         Same outputs bit for bit."""
         _lib.check(self.h, self.lib.p2s_set_deep_search(self.h, int(min_candidates)))
 

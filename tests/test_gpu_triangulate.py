@@ -502,7 +502,7 @@ def _deep_case(C, U, seed):
 ])
 def test_deep_levels_equal_single_kernel_search(engine, C, U, mc, thr, lik_thr, deep_min):
     """`deep_search_kernel` (units pending at a level of >= deep_min camera subsets are parked by the lean search kernel and
-    searched by a 512-thread CTA each) against the search that never parks — the same call with `p2s_set_deep_search(h, 0)`
+    searched by a cluster of 512-thread CTAs each) against the search that never parks — the same call with `p2s_set_deep_search(h, 0)`
     and the statistics launch, which never parks either: bit for bit, incl. NaN coordinates under a valid likelihood, zero
     and NaN likelihoods, thresholds that send every unit through every level, list overflow, ragged tiles."""
     import torch
